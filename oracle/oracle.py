@@ -1,0 +1,231 @@
+"""ctypes wrapper around the CPU ORACLE (oracle/liborb_oracle.so).
+
+TEST INFRASTRUCTURE ONLY.  May be imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs; never by the product package (visual_sgraphs_b200).
+The library restates reference orb_slam3/src/{ORBextractor,ORBmatcher,Frame}.cc — see oracle.h.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liborb_oracle.so")
+
+KEYPOINT_DTYPE = np.dtype(
+    [("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4"),
+     ("class_id", "<i4")]
+)
+assert KEYPOINT_DTYPE.itemsize == 28
+
+
+def build(force=False):
+    """Compile the oracle with its Makefile (g++ only)."""
+    if force or not os.path.exists(_LIB_PATH) or any(
+        os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB_PATH)
+        for f in ("orb_oracle.cpp", "match_oracle.cpp", "oracle.h", "orb_pattern.inc", "Makefile")
+    ):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "liborb_oracle.so"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        u8p, i32p, f32p = C.POINTER(C.c_uint8), C.POINTER(C.c_int32), C.POINTER(C.c_float)
+        vp = C.c_void_p
+        L.orc_extractor_create.restype = vp
+        L.orc_extractor_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.orc_extractor_destroy.argtypes = [vp]
+        L.orc_levels.argtypes = [vp]
+        L.orc_scale_factors.argtypes = [vp, vp, vp, vp, vp]
+        L.orc_quotas.argtypes = [vp, vp]
+        L.orc_umax.argtypes = [vp, vp]
+        L.orc_extract.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_num_keypoints.argtypes = [vp]
+        L.orc_get_keypoints.argtypes = [vp, vp, vp]
+        L.orc_level_size.argtypes = [vp, C.c_int, i32p, i32p]
+        L.orc_get_level.argtypes = [vp, C.c_int, vp]
+        L.orc_get_level_padded.argtypes = [vp, C.c_int, vp]
+        L.orc_get_blurred.argtypes = [vp, C.c_int, vp]
+        L.orc_num_candidates.argtypes = [vp, C.c_int]
+        L.orc_get_candidates.argtypes = [vp, C.c_int, vp]
+        L.orc_num_level_keypoints.argtypes = [vp, C.c_int]
+        L.orc_get_level_keypoints.argtypes = [vp, C.c_int, vp]
+        L.orc_resize_linear.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int]
+        L.orc_gaussian_blur7.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int]
+        L.orc_border_reflect101.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int]
+        L.orc_fast.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int]
+        L.orc_fast_atan2.restype = C.c_float
+        L.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
+        L.orc_cv_round_f.argtypes = [C.c_float]
+        L.orc_cv_round_d.argtypes = [C.c_double]
+        L.orc_ic_angle.restype = C.c_float
+        L.orc_ic_angle.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+        L.orc_orb_descriptor.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_float, vp]
+        L.orc_distribute_octree.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int]
+        L.orc_descriptor_distance.argtypes = [vp, vp]
+        L.orc_bench_extract.restype = C.c_double
+        L.orc_bench_extract.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.POINTER(C.c_int64)]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class OracleExtractor:
+    """Mirror of VS_GRAPHS::ORBextractor (ORBextractor.h:42-119) on the CPU oracle."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th_fast=20, min_th_fast=7):
+        self._L = lib()
+        self._h = self._L.orc_extractor_create(nfeatures, scale_factor, nlevels, ini_th_fast, min_th_fast)
+        self.nlevels = nlevels
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.orc_extractor_destroy(self._h)
+            self._h = None
+
+    def tables(self):
+        n = self.nlevels
+        s, i, s2, i2 = (np.zeros(n, np.float32) for _ in range(4))
+        q = np.zeros(n, np.int32)
+        u = np.zeros(16, np.int32)
+        self._L.orc_scale_factors(self._h, _ptr(s), _ptr(i), _ptr(s2), _ptr(i2))
+        self._L.orc_quotas(self._h, _ptr(q))
+        self._L.orc_umax(self._h, _ptr(u))
+        return dict(scale=s, inv_scale=i, sigma2=s2, inv_sigma2=i2, quota=q, umax=u)
+
+    def __call__(self, image, lapping=(0, 0)):
+        """operator(): returns (mono_index, keypoints structured array, descriptors n x 32)."""
+        if image is None or image.size == 0:
+            return -1, np.zeros(0, KEYPOINT_DTYPE), np.zeros((0, 32), np.uint8)
+        assert image.dtype == np.uint8 and image.ndim == 2 and image.strides[1] == 1
+        h, w = image.shape
+        mono = self._L.orc_extract(self._h, _ptr(image), w, h, image.strides[0], int(lapping[0]), int(lapping[1]))
+        n = self._L.orc_num_keypoints(self._h)
+        kps = np.zeros(n, KEYPOINT_DTYPE)
+        desc = np.zeros((n, 32), np.uint8)
+        if n:
+            self._L.orc_get_keypoints(self._h, _ptr(kps), _ptr(desc))
+        return mono, kps, desc
+
+    def level_size(self, level):
+        w, h = C.c_int32(), C.c_int32()
+        self._L.orc_level_size(self._h, level, C.byref(w), C.byref(h))
+        return w.value, h.value
+
+    def level(self, level):
+        w, h = self.level_size(level)
+        out = np.zeros((h, w), np.uint8)
+        self._L.orc_get_level(self._h, level, _ptr(out))
+        return out
+
+    def level_padded(self, level):
+        w, h = self.level_size(level)
+        out = np.zeros((h + 38, w + 38), np.uint8)
+        self._L.orc_get_level_padded(self._h, level, _ptr(out))
+        return out
+
+    def blurred(self, level):
+        w, h = self.level_size(level)
+        out = np.zeros((h, w), np.uint8)
+        ok = self._L.orc_get_blurred(self._h, level, _ptr(out))
+        return out if ok else None
+
+    def candidates(self, level):
+        n = self._L.orc_num_candidates(self._h, level)
+        out = np.zeros((n, 3), np.float32)
+        if n:
+            self._L.orc_get_candidates(self._h, level, _ptr(out))
+        return out
+
+    def level_keypoints(self, level):
+        n = self._L.orc_num_level_keypoints(self._h, level)
+        out = np.zeros(n, KEYPOINT_DTYPE)
+        if n:
+            self._L.orc_get_level_keypoints(self._h, level, _ptr(out))
+        return out
+
+
+# ---- primitives -------------------------------------------------------------------------------
+
+def resize_linear(src, dw, dh):
+    src = np.ascontiguousarray(src)
+    dst = np.zeros((dh, dw), np.uint8)
+    lib().orc_resize_linear(_ptr(src), src.shape[1], src.shape[0], src.strides[0], _ptr(dst), dw, dh, dw)
+    return dst
+
+
+def gaussian_blur7(src):
+    src = np.ascontiguousarray(src)
+    dst = np.zeros_like(src)
+    lib().orc_gaussian_blur7(_ptr(src), src.shape[1], src.shape[0], src.strides[0], _ptr(dst), dst.strides[0])
+    return dst
+
+
+def border_reflect101(src, border):
+    src = np.ascontiguousarray(src)
+    h, w = src.shape
+    dst = np.zeros((h + 2 * border, w + 2 * border), np.uint8)
+    lib().orc_border_reflect101(_ptr(src), w, h, src.strides[0], _ptr(dst), border, dst.strides[0])
+    return dst
+
+
+def fast(img, threshold):
+    """FAST-9/16 + NMS on a (possibly strided) 2-D uint8 view. Returns int32 array n x 3 (x, y, score)."""
+    assert img.dtype == np.uint8 and img.strides[1] == 1
+    h, w = img.shape
+    cap = max(1, (w * h) // 2)
+    out = np.zeros((cap, 3), np.int32)
+    n = lib().orc_fast(_ptr(img), w, h, img.strides[0], threshold, _ptr(out), cap)
+    return out[:n].copy()
+
+
+def fast_atan2(y, x):
+    return lib().orc_fast_atan2(float(y), float(x))
+
+
+def ic_angle(img, x, y):
+    assert img.dtype == np.uint8 and img.strides[1] == 1
+    return lib().orc_ic_angle(_ptr(img), img.strides[0], int(x), int(y))
+
+
+def orb_descriptor(img, x, y, angle_deg):
+    assert img.dtype == np.uint8 and img.strides[1] == 1
+    out = np.zeros(32, np.uint8)
+    lib().orc_orb_descriptor(_ptr(img), img.strides[0], int(x), int(y), float(angle_deg), _ptr(out))
+    return out
+
+
+def distribute_octree(xyr, min_x, max_x, min_y, max_y, quota):
+    xyr = np.ascontiguousarray(xyr, np.float32)
+    n = xyr.shape[0]
+    out = np.zeros(max(n, 1), np.int32)
+    m = lib().orc_distribute_octree(_ptr(xyr), n, min_x, max_x, min_y, max_y, quota, _ptr(out), out.size)
+    return out[:m].copy()
+
+
+def descriptor_distance(a, b):
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    return lib().orc_descriptor_distance(_ptr(a), _ptr(b))
+
+
+def bench_extract(frames, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, threads=1):
+    """Times the oracle extractor over a stack of frames (n, h, w) uint8. Returns (seconds, total_keypoints)."""
+    frames = np.ascontiguousarray(frames, np.uint8)
+    n, h, w = frames.shape
+    total = C.c_int64(0)
+    secs = lib().orc_bench_extract(_ptr(frames), n, w, h, nfeatures, scale_factor, nlevels, ini_th, min_th, threads,
+                                   C.byref(total))
+    return secs, total.value

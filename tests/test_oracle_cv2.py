@@ -1,0 +1,166 @@
+"""Pins the C++ oracle's restated OpenCV primitives to real OpenCV (python cv2) — SURVEY §8c.
+
+CPU-only.  Every check is bit-exact.
+"""
+import numpy as np
+import pytest
+
+cv2 = pytest.importorskip("cv2")
+
+from oracle import cv2_ref
+from visual_sgraphs_b200.synth import synth_frame
+
+
+def _rand_img(seed, w, h, kind="uniform"):
+    rng = np.random.default_rng(seed)
+    if kind == "uniform":
+        return rng.integers(0, 256, (h, w), dtype=np.uint8)
+    if kind == "binary":
+        return (rng.integers(0, 2, (h, w)) * 255).astype(np.uint8)
+    if kind == "const":
+        return np.full((h, w), 255, np.uint8)
+    raise ValueError(kind)
+
+
+def test_cv_round_half_even(oracle):
+    L = oracle.lib()
+    for v in (0.5, 1.5, 2.5, -0.5, -1.5, 3.49999, 1e6 + 0.5, 266.5, 399.99997):
+        assert L.orc_cv_round_f(v) == int(np.rint(np.float32(v)))
+        assert L.orc_cv_round_d(v) == int(np.rint(v))
+
+
+@pytest.mark.parametrize("shape", [((640, 480), (533, 400)), ((533, 400), (444, 333)), ((444, 333), (370, 278)),
+                                   ((752, 480), (627, 400)), ((1280, 720), (1067, 600)), ((214, 161), (179, 134)),
+                                   ((101, 77), (84, 64)), ((257, 193), (214, 161))])
+@pytest.mark.parametrize("kind", ["uniform", "binary"])
+def test_resize_matches_cv2(oracle, shape, kind):
+    (sw, sh), (dw, dh) = shape
+    src = _rand_img(sw * 31 + dh, sw, sh, kind)
+    want = cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LINEAR)
+    got = oracle.resize_linear(src, dw, dh)
+    assert np.array_equal(got, want)
+
+
+def test_resize_from_strided_roi(oracle):
+    big = _rand_img(5, 700, 500)
+    roi = big[19:19 + 400, 19:19 + 533]
+    want = cv2.resize(roi, (444, 333), interpolation=cv2.INTER_LINEAR)
+    dst = np.zeros((333, 444), np.uint8)
+    oracle.lib().orc_resize_linear(roi.ctypes.data, 533, 400, roi.strides[0], dst.ctypes.data, 444, 333, 444)
+    assert np.array_equal(dst, want)
+
+
+@pytest.mark.parametrize("wh", [(640, 480), (533, 400), (179, 134), (752, 480), (357, 201), (97, 131), (40, 41)])
+@pytest.mark.parametrize("kind", ["uniform", "binary", "const"])
+def test_gaussian_blur_matches_cv2(oracle, wh, kind):
+    w, h = wh
+    src = _rand_img(w + h, w, h, kind)
+    want = cv2_ref.blur(src)
+    got = oracle.gaussian_blur7(src)
+    assert np.array_equal(got, want)
+
+
+def test_border_matches_cv2(oracle):
+    src = _rand_img(3, 61, 47)
+    want = cv2.copyMakeBorder(src, 19, 19, 19, 19, cv2.BORDER_REFLECT_101)
+    assert np.array_equal(oracle.border_reflect101(src, 19), want)
+
+
+@pytest.mark.parametrize("threshold", [20, 7, 1, 40])
+def test_fast_matches_cv2_on_cells(oracle, threshold):
+    frame = synth_frame(77, 320, 240)
+    noise = _rand_img(9, 320, 240)
+    det = cv2.FastFeatureDetector_create(threshold, True)
+    rng = np.random.default_rng(threshold)
+    ncorners = 0
+    for img in (frame, noise):
+        for _ in range(40):
+            cw, ch = rng.integers(7, 60, 2)
+            x0 = int(rng.integers(0, 320 - cw))
+            y0 = int(rng.integers(0, 240 - ch))
+            roi = img[y0:y0 + ch, x0:x0 + cw]
+            kps = det.detect(roi, None)
+            want = np.array([(int(k.pt[0]), int(k.pt[1]), int(k.response)) for k in kps], np.int32).reshape(-1, 3)
+            got = oracle.fast(roi, threshold)
+            assert np.array_equal(got, want), (x0, y0, cw, ch)
+            ncorners += len(kps)
+    assert ncorners > 50
+
+
+def test_fast_tiny_images(oracle):
+    for w, h in ((6, 30), (30, 6), (7, 7), (3, 3)):
+        img = _rand_img(w * h, w, h)
+        kps = cv2.FastFeatureDetector_create(7, True).detect(img, None)
+        got = oracle.fast(img, 7)
+        assert len(got) == len(kps)
+
+
+def test_fast_atan2_matches_cv2(oracle):
+    rng = np.random.default_rng(0)
+    ys = rng.integers(-200000, 200000, 20000)
+    xs = rng.integers(-200000, 200000, 20000)
+    for y, x in zip(ys[:5000], xs[:5000]):
+        assert oracle.fast_atan2(y, x) == cv2.fastAtan2(float(y), float(x))
+    for y, x in ((0, 0), (0, 5), (5, 0), (0, -5), (-5, 0), (7, 7), (-7, 7), (7, -7), (-7, -7), (1, 100000)):
+        assert oracle.fast_atan2(y, x) == cv2.fastAtan2(float(y), float(x))
+
+
+def test_pyramid_matches_cv2_chain(oracle):
+    frame = synth_frame(1000)
+    ex = oracle.OracleExtractor()
+    ex(frame)
+    want = cv2_ref.pyramid(frame)
+    for level in range(8):
+        assert np.array_equal(ex.level_padded(level), want[level]), level
+
+
+@pytest.mark.parametrize("wh,nfeat", [((640, 480), 1000), ((752, 480), 1200), ((322, 243), 500)])
+def test_fast_candidates_match_cv2_per_cell(oracle, wh, nfeat):
+    frame = synth_frame(1234, *wh)
+    ex = oracle.OracleExtractor(nfeat)
+    ex(frame)
+    total_retries = 0
+    for level in range(8):
+        img = ex.level_padded(level)[19:-19, 19:-19]
+        # the reference runs FAST on ROIs of the padded level; cv2 on a view of the same memory
+        padded = ex.level_padded(level)
+        view = padded[19:-19, 19:-19]
+        want, retries = cv2_ref.fast_candidates(view)
+        total_retries += retries
+        got = ex.candidates(level)
+        assert got.shape == want.shape, level
+        assert np.array_equal(got, want), level
+        assert np.array_equal(img, view)
+    assert total_retries >= 0
+
+
+def test_low_contrast_frame_forces_min_threshold(oracle):
+    frame = (synth_frame(5, 320, 240).astype(np.float32) * 0.12 + 100).astype(np.uint8)
+    ex = oracle.OracleExtractor(500)
+    ex(frame)
+    want, retries = cv2_ref.fast_candidates(ex.level(0))
+    assert retries > 10
+    assert np.array_equal(ex.candidates(0), want)
+
+
+def test_blur_and_angles_and_descriptors_match_cv2(oracle):
+    frame = synth_frame(4321)
+    ex = oracle.OracleExtractor()
+    mono, kps, desc = ex(frame)
+    umax = ex.tables()["umax"]
+    import os
+    pattern = cv2_ref.load_pattern(os.path.join(os.path.dirname(cv2_ref.__file__), "orb_pattern.inc"))
+    row = 0
+    for level in range(8):
+        lk = ex.level_keypoints(level)
+        img = ex.level(level)
+        b = ex.blurred(level)
+        assert np.array_equal(b, cv2_ref.blur(img))
+        step = max(1, len(lk) // 12)
+        for i in range(0, len(lk), step):
+            x, y = int(lk["x"][i]), int(lk["y"][i])
+            assert lk["angle"][i] == np.float32(cv2_ref.ic_angle(img, x, y, umax))
+            d = cv2_ref.orb_descriptor(b, x, y, lk["angle"][i], pattern)
+            assert np.array_equal(d, desc[row + i]), (level, i)
+        row += len(lk)
+    assert row == len(kps) and mono == len(kps)
