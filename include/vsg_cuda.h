@@ -1,0 +1,176 @@
+/*
+ * vsg_cuda.h — C ABI of libvsg_cuda.so: the B200 (sm_100a) ORB feature front-end for vS-Graphs.
+ *
+ * This is the drop-in boundary for the reference's feature front-end (snt-arg/visual_sgraphs; paths
+ * below are relative to that checkout).  The reference has no FFI for this path — the hot path is two
+ * C++ classes compiled into liborb_slam3_ros.so — so every entry point names the reference interface
+ * it replaces; the C++ classes in visual_sgraphs_b200/shim/ (VS_GRAPHS::ORBextractor / ORBmatcher,
+ * same signatures as orb_slam3/include/ORBextractor.h and ORBmatcher.h) forward to these functions.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only; no C++/OpenCV/torch types.
+ *   - pointers are HOST pointers unless the parameter name ends in _dev.
+ *   - every function returns vsg_status (0 = ok, negative = error; vsg_last_error() has the text).
+ *     There is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     VSG_ERR_CUDA.
+ *   - handles are not re-entrant (like the reference's ORBextractor instance, which mutates
+ *     mvImagePyramid) but distinct handles may be used concurrently from different threads; each
+ *     handle owns its CUDA stream and scratch memory.  Matcher entry points take a vsg_matcher
+ *     workspace handle for the same reason (reference: stack-local ORBmatcher objects used from the
+ *     Tracking / LocalMapping / LoopClosing threads).
+ */
+#ifndef VSG_CUDA_H
+#define VSG_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int vsg_status;
+#define VSG_OK 0
+#define VSG_ERR_INVALID (-1)   /* bad argument */
+#define VSG_ERR_CUDA (-2)      /* CUDA runtime error / no device */
+#define VSG_ERR_CAPACITY (-3)  /* output buffer too small */
+#define VSG_EMPTY_IMAGE (-10)  /* operator() on an empty image: the reference returns -1 (ORBextractor.cc:1087) */
+
+/* Same memory layout as cv::KeyPoint (pt.x, pt.y, size, angle, response, octave, class_id; 28 bytes),
+ * the element type of the vector operator() fills (ORBextractor.h:59-61). */
+typedef struct vsg_keypoint {
+    float x, y;
+    float size;
+    float angle;
+    float response;
+    int32_t octave;
+    int32_t class_id;
+} vsg_keypoint;
+
+/* Constructor arguments of ORBextractor (ORBextractor.h:51-52, ORBextractor.cc:411-470). */
+typedef struct vsg_orb_params {
+    int32_t nfeatures;
+    float scale_factor;
+    int32_t nlevels;
+    int32_t ini_th_fast;
+    int32_t min_th_fast;
+} vsg_orb_params;
+
+typedef struct vsg_extractor vsg_extractor;
+typedef struct vsg_matcher vsg_matcher;
+
+const char *vsg_last_error(void);
+/* Number of visible CUDA devices (0 if none / no driver). */
+int vsg_device_count(void);
+/* Kernel launches issued by this library since process start (bench.py's gpu_launches). */
+int64_t vsg_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Extractor — replaces VS_GRAPHS::ORBextractor (orb_slam3/include/ORBextractor.h:42-119)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* ORBextractor::ORBextractor (ORBextractor.cc:411-470).  `max_batch` = frames per vsg_extract_batch
+ * call the handle must be able to hold (1 for the per-frame operator()). */
+vsg_status vsg_extractor_create(const vsg_orb_params *params, int device, int max_batch, vsg_extractor **out);
+void vsg_extractor_destroy(vsg_extractor *ex);
+
+/* GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares / GetInverseScaleSigmaSquares
+ * (ORBextractor.h:73-91) and mnFeaturesPerLevel (ORBextractor.cc:435-446). Any pointer may be NULL. */
+vsg_status vsg_extractor_tables(const vsg_extractor *ex, float *scale, float *inv_scale, float *sigma2,
+                                float *inv_sigma2, int32_t *features_per_level);
+
+/* Upper bound of keypoints operator() can return for one frame of this size (output buffer sizing). */
+int vsg_extractor_max_keypoints(vsg_extractor *ex, int width, int height);
+
+/* ORBextractor::operator()(image, mask, keypoints, descriptors, vLappingArea)
+ * (ORBextractor.cc:1083-1169).  image: 8-bit gray, `pitch` bytes per row.  The mask is ignored by the
+ * reference and has no parameter here.  keypoints_out / descriptors_out (n x 32) must hold `capacity`
+ * entries.  *n_out = number of keypoints, *mono_index_out = the reference's return value
+ * (count of keypoints outside [lap_x0, lap_x1]).  Returns VSG_EMPTY_IMAGE for a NULL/0-sized image. */
+vsg_status vsg_extract(vsg_extractor *ex, const uint8_t *image, int width, int height, int pitch, int lap_x0,
+                       int lap_x1, vsg_keypoint *keypoints_out, uint8_t *descriptors_out, int capacity, int *n_out,
+                       int *mono_index_out);
+
+/* Batched operator(): `nframes` (<= max_batch) frames of identical shape, frame f at
+ * images + f*frame_stride.  Outputs are [nframes][capacity] arrays; n_out / mono_index_out are
+ * [nframes].  This is what BASELINE configs 1 and 4 (sequence extraction) run. */
+vsg_status vsg_extract_batch(vsg_extractor *ex, const uint8_t *images, int nframes, int width, int height, int pitch,
+                             size_t frame_stride, int lap_x0, int lap_x1, vsg_keypoint *keypoints_out,
+                             uint8_t *descriptors_out, int capacity, int *n_out, int *mono_index_out);
+
+/* Same, but the frames already live in device memory (frame f at images_dev + f*frame_stride; pitch
+ * and base 16-byte aligned) and the results stay on the device: keypoints_dev / descriptors_dev /
+ * n_dev / mono_dev are device pointers sized as above.  Asynchronous on the handle's stream; call
+ * vsg_extractor_sync before reading.  Used for the HBM-resident throughput measurement. */
+vsg_status vsg_extract_batch_dev(vsg_extractor *ex, const uint8_t *images_dev, int nframes, int width, int height,
+                                 int pitch, size_t frame_stride, int lap_x0, int lap_x1, vsg_keypoint *keypoints_dev,
+                                 uint8_t *descriptors_dev, int capacity, int32_t *n_dev, int32_t *mono_dev);
+vsg_status vsg_extractor_sync(vsg_extractor *ex);
+/* The handle's CUDA stream (cudaStream_t as void*), so callers can time with events on it. */
+void *vsg_extractor_stream(vsg_extractor *ex);
+
+/* Per-stage device timing (the reference's REGISTER_TIMES hooks, Frame.cc:126-153 / Settings.h:23, made
+ * per kernel group): when enabled, CUDA events bracket each stage on the handle's stream.
+ * vsg_extractor_stage_ms waits for the stream, returns the accumulated milliseconds per stage and the
+ * number of pipeline runs they cover, and resets the accumulators.
+ * Stages: 0 pyramid (7 resize launches), 1 FAST cells, 2 oct-tree, 3 Gaussian blur, 4 slots +
+ * orientation + descriptors. */
+#define VSG_NUM_STAGES 5
+vsg_status vsg_extractor_profile(vsg_extractor *ex, int enable);
+vsg_status vsg_extractor_stage_ms(vsg_extractor *ex, double *ms_out, int64_t *runs_out);
+
+/* mvImagePyramid (ORBextractor.h:93; consumers Frame.cc:964,1054,1069): size of / copy of level
+ * `level` of frame `frame` of the last call, w x h un-bordered pixels into dst with dst_pitch. */
+vsg_status vsg_pyramid_level_size(vsg_extractor *ex, int level, int *width, int *height);
+vsg_status vsg_pyramid_download(vsg_extractor *ex, int frame, int level, uint8_t *dst, int dst_pitch);
+/* Test/diagnostic taps (parity tests compare them with the oracle stage by stage):
+ * the blurred working image of a level (ORBextractor.cc:1129-1130), */
+vsg_status vsg_blurred_download(vsg_extractor *ex, int frame, int level, uint8_t *dst, int dst_pitch);
+/* the FAST candidates of a level in the reference's order, n x 3 int32 (x, y relative to the 16-px
+ * border as in ORBextractor.cc:866-874, score), */
+vsg_status vsg_candidates_download(vsg_extractor *ex, int frame, int level, int32_t *xys, int capacity, int *n_out);
+/* and the per-level keypoints after the oct-tree in list order, n x 3 int32 (x, y level coords, score). */
+vsg_status vsg_level_keypoints_download(vsg_extractor *ex, int frame, int level, int32_t *xys, int capacity,
+                                        int *n_out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Matcher — replaces the arithmetic of VS_GRAPHS::ORBmatcher (orb_slam3/include/ORBmatcher.h:34-99)
+ * on flattened arrays.  Descriptors are rows of 32 bytes.
+ * ---------------------------------------------------------------------------------------------- */
+vsg_status vsg_matcher_create(int device, vsg_matcher **out);
+void vsg_matcher_destroy(vsg_matcher *m);
+void *vsg_matcher_stream(vsg_matcher *m);
+vsg_status vsg_matcher_sync(vsg_matcher *m);
+
+/* ORBmatcher::DescriptorDistance (ORBmatcher.cc:2047-2063) for n pairs: out[i] = |a_i xor b_i|. */
+vsg_status vsg_descriptor_distance(vsg_matcher *m, const uint8_t *a, const uint8_t *b, int n, int32_t *out);
+
+/* Brute-force Hamming kNN, k = 2 — cv::BFMatcher(NORM_HAMMING).knnMatch(q, t, 2) as used at
+ * Frame.cc:1200 (ties: lower train index first).  out_idx / out_dist are [nq][2]; missing neighbours
+ * (nt < 2) are idx -1, dist INT32_MAX.  train_index_offset is added to the reported indices (sharded
+ * train sets). */
+vsg_status vsg_knn2(vsg_matcher *m, const uint8_t *query, int nq, const uint8_t *train, int nt, int train_index_offset,
+                    int32_t *out_idx, int32_t *out_dist);
+vsg_status vsg_knn2_dev(vsg_matcher *m, const uint8_t *query_dev, int nq, const uint8_t *train_dev, int nt,
+                        int train_index_offset, int32_t *out_idx_dev, int32_t *out_dist_dev);
+/* Merge `nparts` per-shard top-2 lists ([nparts][nq][2]) into one ([nq][2]) by (dist, idx)
+ * lexicographic order — the step after the all-gather when the train set is sharded over GPUs. */
+vsg_status vsg_knn2_merge_dev(vsg_matcher *m, const int32_t *idx_parts_dev, const int32_t *dist_parts_dev, int nparts,
+                              int nq, int32_t *out_idx_dev, int32_t *out_dist_dev);
+
+/* Candidate-list ("windowed") search shared by the SearchByProjection family, SearchForInitialization,
+ * Fuse and SearchBySim3: for each query i, scan its candidate train rows cand[cand_ptr[i]..cand_ptr[i+1])
+ * in order and return the best and second-best distances with strict '<' updates (first candidate
+ * wins ties), the best candidate's train index, and the `level` attribute of best / second-best
+ * (ORBmatcher.cc:77-120).  skip[j] != 0 excludes train row j (already-matched keypoints,
+ * ORBmatcher.cc:88-90); may be NULL.  train_level may be NULL (levels reported as -1).
+ * init_dist is the reference's initial bestDist (256 or INT_MAX). */
+vsg_status vsg_match_window(vsg_matcher *m, const uint8_t *query, int nq, const uint8_t *train, int nt,
+                            const int32_t *cand_ptr, const int32_t *cand, const uint8_t *skip,
+                            const int32_t *train_level, int init_dist, int32_t *best_idx, int32_t *best_dist,
+                            int32_t *second_dist, int32_t *best_level, int32_t *second_level);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSG_CUDA_H */

@@ -1,0 +1,106 @@
+"""ctypes binding of libvsg_cuda.so (include/vsg_cuda.h).  No compute happens in Python.
+
+The library is built in-tree by `make -C visual_sgraphs_b200/csrc` (or __graft_entry__.build()).
+Loading fails loudly if the shared object is missing: there is no CPU fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvsg_cuda.so")
+
+KEYPOINT_DTYPE = np.dtype(
+    [("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4"),
+     ("class_id", "<i4")]
+)
+
+VSG_OK = 0
+VSG_ERR_INVALID = -1
+VSG_ERR_CUDA = -2
+VSG_ERR_CAPACITY = -3
+VSG_EMPTY_IMAGE = -10
+
+
+class OrbParams(C.Structure):
+    _fields_ = [("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32),
+                ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32)]
+
+
+class VsgError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("vsg status %d: %s" % (status, message))
+        self.status = status
+
+
+# every symbol include/vsg_cuda.h declares (tests/test_abi.py checks the header against this table)
+_SIGNATURES = {
+    "vsg_last_error": (C.c_char_p, []),
+    "vsg_device_count": (C.c_int, []),
+    "vsg_launch_count": (C.c_int64, []),
+    "vsg_extractor_create": (C.c_int, [C.POINTER(OrbParams), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "vsg_extractor_destroy": (None, [C.c_void_p]),
+    "vsg_extractor_tables": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5),
+    "vsg_extractor_max_keypoints": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "vsg_extract": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                              C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "vsg_extract_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int,
+                                    C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "vsg_extract_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t,
+                                        C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "vsg_extractor_sync": (C.c_int, [C.c_void_p]),
+    "vsg_extractor_stream": (C.c_void_p, [C.c_void_p]),
+    "vsg_extractor_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "vsg_extractor_stage_ms": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
+    "vsg_pyramid_level_size": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "vsg_pyramid_download": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]),
+    "vsg_blurred_download": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]),
+    "vsg_candidates_download": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
+    "vsg_level_keypoints_download": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
+    "vsg_matcher_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "vsg_matcher_destroy": (None, [C.c_void_p]),
+    "vsg_matcher_stream": (C.c_void_p, [C.c_void_p]),
+    "vsg_matcher_sync": (C.c_int, [C.c_void_p]),
+    "vsg_descriptor_distance": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "vsg_knn2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "vsg_knn2_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "vsg_knn2_merge_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "vsg_match_window": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5),
+}
+
+_lib = None
+
+
+def load():
+    """Loads libvsg_cuda.so; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libvsg_cuda.so is not built (%s). Run `make -C visual_sgraphs_b200/csrc` or "
+                "`python -c 'import __graft_entry__ as g; g.build()'`. There is no CPU fallback." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(status):
+    if status != VSG_OK:
+        raise VsgError(status, load().vsg_last_error().decode("utf-8", "replace"))
+
+
+def ptr(a):
+    """void* of a numpy array, a torch tensor (data_ptr) or None."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(type(a))

@@ -1,0 +1,172 @@
+// introsort.cuh — move-for-move emulation of libstdc++'s std::sort (GCC's bits/stl_algo.h: __sort =
+// __introsort_loop + __final_insertion_sort, threshold 16, depth limit 2*floor(log2 n), heapsort
+// fallback) for the oct-tree's "careful" phase.
+//
+// Why: the reference sorts vPrevSizeAndPointerToNode with std::sort and a comparator on
+// (nKeys, UL.x) only (orb_slam3/src/ORBextractor.cc:539-560, :707).  Nodes with equal keys are
+// "equivalent", std::sort is not stable, and their final order decides which nodes get expanded —
+// i.e. which keypoints are selected.  Bit-exact keypoint sets therefore
+// need the very same permutation libstdc++ produces.  tests/test_introsort.py compiles this header
+// with g++ and checks it against std::sort on tie-heavy inputs.
+//
+// Usable from host and device code (one thread runs it; n is a few hundred at most).
+#pragma once
+#if defined(__CUDACC__)
+#define VSG_HD __host__ __device__ __forceinline__
+#else
+#define VSG_HD inline
+#endif
+
+namespace vsg {
+
+struct SortItem {
+    int count;  // pair.first  = node key count
+    int ulx;    // pair.second->UL.x
+    int ref;    // which node (list position); not part of the ordering
+};
+
+VSG_HD bool item_less(const SortItem &a, const SortItem &b) {  // compareNodes, ORBextractor.cc:539-560
+    if (a.count < b.count) return true;
+    if (a.count > b.count) return false;
+    return a.ulx < b.ulx;
+}
+
+VSG_HD void item_swap(SortItem &a, SortItem &b) { SortItem t = a; a = b; b = t; }
+
+// __unguarded_linear_insert
+VSG_HD void linear_insert_unguarded(SortItem *v, int last) {
+    const SortItem val = v[last];
+    int next = last - 1;
+    while (item_less(val, v[next])) {
+        v[last] = v[next];
+        last = next;
+        --next;
+    }
+    v[last] = val;
+}
+
+// __insertion_sort on [first, last)
+VSG_HD void insertion_sort(SortItem *v, int first, int last) {
+    if (first == last) return;
+    for (int i = first + 1; i != last; ++i) {
+        if (item_less(v[i], v[first])) {
+            const SortItem val = v[i];
+            for (int k = i; k > first; --k) v[k] = v[k - 1];  // move_backward(first, i, i + 1)
+            v[first] = val;
+        } else {
+            linear_insert_unguarded(v, i);
+        }
+    }
+}
+
+// __push_heap / __adjust_heap on the sub-array starting at `base`
+VSG_HD void heap_push(SortItem *v, int base, int hole, int top, const SortItem &value) {
+    int parent = (hole - 1) / 2;
+    while (hole > top && item_less(v[base + parent], value)) {
+        v[base + hole] = v[base + parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    v[base + hole] = value;
+}
+
+VSG_HD void heap_adjust(SortItem *v, int base, int hole, int len, const SortItem &value) {
+    const int top = hole;
+    int child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (item_less(v[base + child], v[base + child - 1])) --child;
+        v[base + hole] = v[base + child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        v[base + hole] = v[base + child - 1];
+        hole = child - 1;
+    }
+    heap_push(v, base, hole, top, value);
+}
+
+// __partial_sort(first, last, last) == make_heap + sort_heap
+VSG_HD void heap_sort(SortItem *v, int first, int last) {
+    const int len = last - first;
+    if (len >= 2) {
+        int parent = (len - 2) / 2;
+        while (true) {
+            const SortItem val = v[first + parent];
+            heap_adjust(v, first, parent, len, val);
+            if (parent == 0) break;
+            --parent;
+        }
+    }
+    // __heap_select's scan over [middle, last) is empty because middle == last
+    int end = last;
+    while (end - first > 1) {
+        --end;
+        const SortItem val = v[end];   // __pop_heap(first, end, end)
+        v[end] = v[first];
+        heap_adjust(v, first, 0, end - first, val);
+    }
+}
+
+// __move_median_to_first(result, a, b, c)
+VSG_HD void median_to_first(SortItem *v, int result, int a, int b, int c) {
+    if (item_less(v[a], v[b])) {
+        if (item_less(v[b], v[c])) item_swap(v[result], v[b]);
+        else if (item_less(v[a], v[c])) item_swap(v[result], v[c]);
+        else item_swap(v[result], v[a]);
+    } else if (item_less(v[a], v[c])) item_swap(v[result], v[a]);
+    else if (item_less(v[b], v[c])) item_swap(v[result], v[c]);
+    else item_swap(v[result], v[b]);
+}
+
+// __unguarded_partition(first, last, pivot)
+VSG_HD int partition_unguarded(SortItem *v, int first, int last, int pivot) {
+    while (true) {
+        while (item_less(v[first], v[pivot])) ++first;
+        --last;
+        while (item_less(v[pivot], v[last])) --last;
+        if (!(first < last)) return first;
+        item_swap(v[first], v[last]);
+        ++first;
+    }
+}
+
+// std::sort(v, v + n, compareNodes)
+VSG_HD void libstdcxx_sort(SortItem *v, int n) {
+    if (n <= 0) return;
+    int lg = 0;
+    for (int t = n; t > 1; t >>= 1) ++lg;
+    // __introsort_loop with an explicit stack instead of the recursion on the right part (the two
+    // parts are disjoint, so the processing order does not change the outcome)
+    int stack_first[64], stack_last[64], stack_depth[64];
+    int sp = 0;
+    stack_first[0] = 0; stack_last[0] = n; stack_depth[0] = 2 * lg; sp = 1;
+    while (sp > 0) {
+        --sp;
+        const int first = stack_first[sp];
+        int last = stack_last[sp];
+        int depth = stack_depth[sp];
+        while (last - first > 16) {
+            if (depth == 0) {
+                heap_sort(v, first, last);
+                break;
+            }
+            --depth;
+            const int mid = first + (last - first) / 2;
+            median_to_first(v, first, first + 1, mid, last - 1);
+            const int cut = partition_unguarded(v, first + 1, last, first);
+            stack_first[sp] = cut; stack_last[sp] = last; stack_depth[sp] = depth; ++sp;
+            last = cut;
+        }
+    }
+    // __final_insertion_sort
+    if (n > 16) {
+        insertion_sort(v, 0, 16);
+        for (int i = 16; i < n; ++i) linear_insert_unguarded(v, i);
+    } else {
+        insertion_sort(v, 0, n);
+    }
+}
+
+}  // namespace vsg

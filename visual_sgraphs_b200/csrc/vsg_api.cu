@@ -1,0 +1,602 @@
+// vsg_api.cu — the C ABI of libvsg_cuda.so (include/vsg_cuda.h): extractor object, host-side tables
+// and orchestration of the kernels in pyramid.cu / fast.cu / octree.cu / describe.cu.
+//
+// Reference (snt-arg/visual_sgraphs):
+//   ORBextractor::ORBextractor   orb_slam3/src/ORBextractor.cc:411-470   -> build_tables()
+//   ORBextractor::operator()     :1083-1169                               -> run_batch()
+//   ComputePyramid level sizes   :1171-1180                               -> configure_shape()
+//   cell grid                    :795-828                                 -> configure_shape()
+//   cv::resize coefficient tables                    -> build_resize_tables()
+// There is no CPU compute path in this library: every entry point that produces results launches
+// CUDA kernels and fails with VSG_ERR_CUDA when no device is usable.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "vsg_internal.cuh"
+
+namespace vsg {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+bool cuda_ok(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return true;
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return false;
+}
+void count_launch(int n) { g_launches += n; }
+
+static inline int cv_round(float v) { return (int)lrintf(v); }
+static inline int cv_round(double v) { return (int)lrint(v); }
+static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace vsg
+
+using namespace vsg;
+
+struct vsg_extractor {
+    int device = 0;
+    int max_batch = 1;
+    cudaStream_t stream = nullptr;
+    vsg_orb_params p{};
+    std::vector<float> scale, inv_scale, sigma2, inv_sigma2;
+    std::vector<int> quota;
+
+    // shape dependent state
+    int cur_w = 0, cur_h = 0;
+    FrameGeom g{};
+    std::vector<Cell> cells_h;
+    int max_cw = 0, max_ch = 0, max_nodes = 0;
+    int64_t pyr_bytes_per_frame = 0;
+
+    Cell *cells_d = nullptr;
+    short4 *tabs_d = nullptr;
+    uint8_t *pyr = nullptr, *blur = nullptr;
+    Cand *cand = nullptr;
+    unsigned short *node_of = nullptr;
+    int *cand_count = nullptr;
+    LevelKp *level_kps = nullptr;
+    int *level_kp_count = nullptr;
+    int *slot = nullptr;
+    vsg_keypoint *kps_d = nullptr;
+    uint8_t *desc_d = nullptr;
+    int *n_d = nullptr, *mono_d = nullptr;
+    // pinned staging for results
+    vsg_keypoint *kps_h = nullptr;
+    uint8_t *desc_h = nullptr;
+    int *n_h = nullptr, *mono_h = nullptr;
+
+    // optional per-stage timing: a ring of event sets, harvested lazily
+    bool profile = false;
+    static constexpr int kEvRing = 32;
+    cudaEvent_t ev[kEvRing][VSG_NUM_STAGES + 1] = {};
+    bool ev_created = false;
+    int ev_head = 0, ev_pending = 0;
+    double stage_ms[VSG_NUM_STAGES] = {0, 0, 0, 0, 0};
+    int64_t stage_runs = 0;
+
+    void harvest_one() {   // oldest pending event set -> accumulators (blocks until it completed)
+        const int slot = (ev_head - ev_pending + 2 * kEvRing) % kEvRing;
+        cudaEventSynchronize(ev[slot][VSG_NUM_STAGES]);
+        for (int k = 0; k < VSG_NUM_STAGES; ++k) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[slot][k], ev[slot][k + 1]);
+            stage_ms[k] += ms;
+        }
+        ++stage_runs;
+        --ev_pending;
+    }
+
+    // where level 0 of the last call lives
+    const uint8_t *lvl0_base = nullptr;
+    int lvl0_pitch = 0;
+    int64_t lvl0_stride = 0;
+    int last_nframes = 0;
+
+    void free_shape() {
+        cudaFree(cells_d); cudaFree(tabs_d); cudaFree(pyr); cudaFree(blur); cudaFree(cand); cudaFree(node_of);
+        cudaFree(cand_count); cudaFree(level_kps); cudaFree(level_kp_count); cudaFree(slot); cudaFree(kps_d);
+        cudaFree(desc_d); cudaFree(n_d); cudaFree(mono_d);
+        cudaFreeHost(kps_h); cudaFreeHost(desc_h); cudaFreeHost(n_h); cudaFreeHost(mono_h);
+        cells_d = nullptr; tabs_d = nullptr; pyr = blur = nullptr; cand = nullptr; node_of = nullptr;
+        cand_count = nullptr; level_kps = nullptr; level_kp_count = nullptr; slot = nullptr; kps_d = nullptr;
+        desc_d = nullptr; n_d = mono_d = nullptr; kps_h = nullptr; desc_h = nullptr; n_h = mono_h = nullptr;
+        cur_w = cur_h = 0;
+    }
+};
+
+namespace {
+
+// ORBextractor::ORBextractor — ORBextractor.cc:411-446 (scale tables and per-level quotas)
+void build_tables(vsg_extractor *ex) {
+    const int nl = ex->p.nlevels;
+    const double scale_factor = ex->p.scale_factor;  // the member is a double (ORBextractor.h:105)
+    ex->scale.assign(nl, 1.f);
+    ex->sigma2.assign(nl, 1.f);
+    for (int i = 1; i < nl; ++i) {
+        ex->scale[i] = (float)(ex->scale[i - 1] * scale_factor);
+        ex->sigma2[i] = ex->scale[i] * ex->scale[i];
+    }
+    ex->inv_scale.resize(nl);
+    ex->inv_sigma2.resize(nl);
+    for (int i = 0; i < nl; ++i) {
+        ex->inv_scale[i] = 1.0f / ex->scale[i];
+        ex->inv_sigma2[i] = 1.0f / ex->sigma2[i];
+    }
+    ex->quota.assign(nl, 0);
+    const float factor = (float)(1.0f / scale_factor);
+    float desired = ex->p.nfeatures * (1 - factor) / (1 - (float)std::pow((double)factor, (double)nl));
+    int sum = 0;
+    for (int l = 0; l < nl - 1; ++l) {
+        ex->quota[l] = cv_round(desired);
+        sum += ex->quota[l];
+        desired *= factor;
+    }
+    ex->quota[nl - 1] = std::max(ex->p.nfeatures - sum, 0);
+}
+
+// cv::resize INTER_LINEAR coefficient tables — SURVEY Appendix A1
+void build_resize_tables(int sw, int sh, int dw, int dh, int dw_pad, std::vector<short4> &xt, std::vector<short4> &yt) {
+    const double scale_x = 1.0 / ((double)dw / sw), scale_y = 1.0 / ((double)dh / sh);
+    xt.resize(dw_pad);
+    yt.resize(dh);
+    for (int dx = 0; dx < dw_pad; ++dx) {
+        const int x = std::min(dx, dw - 1);  // pad entries repeat the last column (results land in pitch padding)
+        float fx = (float)((x + 0.5) * scale_x - 0.5);
+        int sx = (int)std::floor(fx);
+        fx -= sx;
+        if (sx < 0) { fx = 0; sx = 0; }
+        if (sx >= sw - 1) { fx = 0; sx = sw - 1; }
+        xt[dx] = make_short4((short)sx, (short)std::min(sx + 1, sw - 1), (short)cv_round((1.f - fx) * 2048.f),
+                             (short)cv_round(fx * 2048.f));
+    }
+    for (int dy = 0; dy < dh; ++dy) {
+        float fy = (float)((dy + 0.5) * scale_y - 0.5);
+        int sy = (int)std::floor(fy);
+        fy -= sy;
+        const int sy0 = std::min(std::max(sy, 0), sh - 1), sy1 = std::min(std::max(sy + 1, 0), sh - 1);
+        yt[dy] = make_short4((short)sy0, (short)sy1, (short)cv_round((1.f - fy) * 2048.f), (short)cv_round(fy * 2048.f));
+    }
+}
+
+#define CK(call)                                 \
+    do {                                         \
+        if (!cuda_ok((call), #call)) return VSG_ERR_CUDA; \
+    } while (0)
+
+vsg_status configure_shape(vsg_extractor *ex, int w, int h) {
+    if (ex->cur_w == w && ex->cur_h == h) return VSG_OK;
+    ex->free_shape();
+    const int nl = ex->p.nlevels;
+    FrameGeom &g = ex->g;
+    memset(&g, 0, sizeof(g));
+    g.nlevels = nl;
+    ex->cells_h.clear();
+    ex->max_cw = ex->max_ch = 7;
+    ex->max_nodes = 8;
+    int64_t plane_off = 0, cand_off = 0;
+    int kp_off = 0;
+    std::vector<std::vector<short4>> xts(nl), yts(nl);
+    for (int l = 0; l < nl; ++l) {
+        LevelGeom &L = g.lv[l];
+        L.w = cv_round((float)w * ex->inv_scale[l]);   // :1176
+        L.h = cv_round((float)h * ex->inv_scale[l]);
+        const int min_b = kBorderMin, max_bx = L.w - kBorderMin, max_by = L.h - kBorderMin;
+        const float width = (float)(max_bx - min_b), height = (float)(max_by - min_b);
+        if (width < 35.f || height < 35.f) {
+            set_error("image %dx%d too small: level %d is %dx%d (needs >= 67x67 for one 35-px cell)", w, h, l, L.w, L.h);
+            return VSG_ERR_INVALID;
+        }
+        L.pitch = (int)align_up(L.w, 64);
+        L.plane_stride = align_up((int64_t)L.pitch * L.h, 256);
+        L.plane_offset = plane_off;
+        plane_off += L.plane_stride * ex->max_batch;
+        L.n_cols = (int)(width / 35.f);                // :803-809
+        L.n_rows = (int)(height / 35.f);
+        L.w_cell = (int)std::ceil(width / L.n_cols);
+        L.h_cell = (int)std::ceil(height / L.n_rows);
+        L.cell_begin = (int)ex->cells_h.size();
+        int cand_cap = 0;
+        for (int i = 0; i < L.n_rows; ++i) {           // :811-828
+            const float ini_y = (float)(min_b + i * L.h_cell);
+            float max_y = ini_y + L.h_cell + 6;
+            if (ini_y >= max_by - 3) continue;
+            if (max_y > max_by) max_y = (float)max_by;
+            for (int j = 0; j < L.n_cols; ++j) {
+                const float ini_x = (float)(min_b + j * L.w_cell);
+                float max_x = ini_x + L.w_cell + 6;
+                if (ini_x >= max_bx - 6) continue;
+                if (max_x > max_bx) max_x = (float)max_bx;
+                Cell c;
+                c.level = (short)l;
+                c.x0 = (short)ini_x; c.y0 = (short)ini_y;
+                c.cw = (short)((int)max_x - (int)ini_x); c.ch = (short)((int)max_y - (int)ini_y);
+                c.pad = 0;
+                if (c.cw < 7 || c.ch < 7) continue;   // cv::FAST finds nothing in such a window
+                ex->cells_h.push_back(c);
+                ex->max_cw = std::max<int>(ex->max_cw, c.cw);
+                ex->max_ch = std::max<int>(ex->max_ch, c.ch);
+                cand_cap += ((c.cw - 6 + 1) / 2) * ((c.ch - 6 + 1) / 2);
+            }
+        }
+        L.cell_count = (int)ex->cells_h.size() - L.cell_begin;
+        L.quota = ex->quota[l];
+        L.n_ini = (int)std::round(static_cast<float>(max_bx - min_b) / (max_by - min_b));   // :566
+        if (L.n_ini < 1) {
+            set_error("image %dx%d: aspect ratio below 0.5 is not supported by the reference oct-tree (nIni = 0)", w, h);
+            return VSG_ERR_INVALID;
+        }
+        L.h_x = static_cast<float>(max_bx - min_b) / L.n_ini;                                // :568
+        L.cand_cap = cand_cap + 8;
+        L.cand_offset = cand_off;
+        cand_off += L.cand_cap;
+        L.kp_cap = std::max(L.quota, 4 * L.n_ini) + 4;
+        L.kp_offset = kp_off;
+        kp_off += L.kp_cap;
+        ex->max_nodes = std::max(ex->max_nodes, L.kp_cap + 4);
+        L.scale = ex->scale[l];
+        L.kp_size = (float)(int)(kPatch * ex->scale[l]);                                    // :884
+        if (l > 0)
+            build_resize_tables(g.lv[l - 1].w, g.lv[l - 1].h, L.w, L.h, (int)align_up(L.w, 4), xts[l], yts[l]);
+    }
+    g.ncells = (int)ex->cells_h.size();
+    g.cand_total = cand_off;
+    g.kp_total = kp_off;
+    g.out_cap = kp_off;
+    ex->pyr_bytes_per_frame = plane_off / ex->max_batch;
+
+    const int B = ex->max_batch;
+    CK(cudaSetDevice(ex->device));
+    // resize tables, one allocation
+    size_t ntab = 0;
+    for (int l = 1; l < nl; ++l) ntab += xts[l].size() + yts[l].size();
+    CK(cudaMalloc(&ex->tabs_d, std::max<size_t>(ntab, 1) * sizeof(short4)));
+    size_t toff = 0;
+    for (int l = 1; l < nl; ++l) {
+        CK(cudaMemcpy(ex->tabs_d + toff, xts[l].data(), xts[l].size() * sizeof(short4), cudaMemcpyHostToDevice));
+        g.lv[l].xtab = ex->tabs_d + toff;
+        toff += xts[l].size();
+        CK(cudaMemcpy(ex->tabs_d + toff, yts[l].data(), yts[l].size() * sizeof(short4), cudaMemcpyHostToDevice));
+        g.lv[l].ytab = ex->tabs_d + toff;
+        toff += yts[l].size();
+    }
+    CK(cudaMalloc(&ex->cells_d, std::max<size_t>(ex->cells_h.size(), 1) * sizeof(Cell)));
+    CK(cudaMemcpy(ex->cells_d, ex->cells_h.data(), ex->cells_h.size() * sizeof(Cell), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&ex->pyr, plane_off + 256));
+    CK(cudaMalloc(&ex->blur, plane_off + 256));
+    CK(cudaMemset(ex->pyr, 0, plane_off + 256));
+    CK(cudaMalloc(&ex->cand, (size_t)g.cand_total * B * sizeof(Cand)));
+    CK(cudaMalloc(&ex->node_of, (size_t)g.cand_total * B * sizeof(unsigned short)));
+    CK(cudaMalloc(&ex->cand_count, (size_t)B * nl * sizeof(int)));
+    CK(cudaMalloc(&ex->level_kps, (size_t)g.kp_total * B * sizeof(LevelKp)));
+    CK(cudaMalloc(&ex->level_kp_count, (size_t)B * nl * sizeof(int)));
+    CK(cudaMalloc(&ex->slot, (size_t)g.kp_total * B * sizeof(int)));
+    CK(cudaMalloc(&ex->kps_d, (size_t)g.out_cap * B * sizeof(vsg_keypoint)));
+    CK(cudaMalloc(&ex->desc_d, (size_t)g.out_cap * B * 32));
+    CK(cudaMalloc(&ex->n_d, (size_t)B * sizeof(int)));
+    CK(cudaMalloc(&ex->mono_d, (size_t)B * sizeof(int)));
+    CK(cudaMallocHost(&ex->kps_h, (size_t)g.out_cap * B * sizeof(vsg_keypoint)));
+    CK(cudaMallocHost(&ex->desc_h, (size_t)g.out_cap * B * 32));
+    CK(cudaMallocHost(&ex->n_h, (size_t)B * sizeof(int)));
+    CK(cudaMallocHost(&ex->mono_h, (size_t)B * sizeof(int)));
+    ex->cur_w = w;
+    ex->cur_h = h;
+    return VSG_OK;
+}
+
+// The device pipeline for `nframes` frames whose level 0 is at (lvl0_base, lvl0_pitch, lvl0_stride).
+vsg_status run_pipeline(vsg_extractor *ex, const uint8_t *lvl0_base, int lvl0_pitch, int64_t lvl0_stride, int nframes,
+                        int lap_x0, int lap_x1, vsg_keypoint *kps_dev, uint8_t *desc_dev, int out_cap, int *n_dev,
+                        int *mono_dev) {
+    const FrameGeom &g = ex->g;
+    cudaStream_t s = ex->stream;
+    ex->lvl0_base = lvl0_base; ex->lvl0_pitch = lvl0_pitch; ex->lvl0_stride = lvl0_stride; ex->last_nframes = nframes;
+    CK(cudaMemsetAsync(ex->cand_count, 0, (size_t)nframes * g.nlevels * sizeof(int), s));
+    cudaEvent_t *ev = nullptr;
+    if (ex->profile) {
+        if (!ex->ev_created) {
+            for (int i = 0; i < vsg_extractor::kEvRing; ++i)
+                for (int k = 0; k <= VSG_NUM_STAGES; ++k) CK(cudaEventCreate(&ex->ev[i][k]));
+            ex->ev_created = true;
+        }
+        if (ex->ev_pending == vsg_extractor::kEvRing) ex->harvest_one();
+        ev = ex->ev[ex->ev_head];
+        ex->ev_head = (ex->ev_head + 1) % vsg_extractor::kEvRing;
+        ++ex->ev_pending;
+    }
+#define STAGE_MARK(k) do { if (ev) CK(cudaEventRecord(ev[k], s)); } while (0)
+    STAGE_MARK(0);
+    for (int l = 1; l < g.nlevels; ++l) {                         // ComputePyramid (:1171-1195)
+        const LevelGeom &P = g.lv[l - 1];
+        if (l == 1) launch_resize_level(g, l, lvl0_base, lvl0_pitch, lvl0_stride, ex->pyr, nframes, s);
+        else launch_resize_level(g, l, ex->pyr + P.plane_offset, P.pitch, P.plane_stride, ex->pyr, nframes, s);
+    }
+    STAGE_MARK(1);
+    launch_fast(g, ex->cells_d, lvl0_base, lvl0_pitch, lvl0_stride, ex->pyr, ex->cand, ex->cand_count, ex->p.ini_th_fast,
+                ex->p.min_th_fast, ex->max_cw, ex->max_ch, nframes, s);
+    STAGE_MARK(2);
+    launch_octree(g, ex->cand, ex->cand_count, ex->node_of, ex->level_kps, ex->level_kp_count, ex->max_nodes, nframes, s);
+    STAGE_MARK(3);
+    launch_blur(g, lvl0_base, lvl0_pitch, lvl0_stride, ex->pyr, ex->blur, nframes, s);
+    STAGE_MARK(4);
+    launch_describe(g, lvl0_base, lvl0_pitch, lvl0_stride, ex->pyr, ex->blur, ex->level_kps, ex->level_kp_count, lap_x0,
+                    lap_x1, kps_dev, desc_dev, out_cap, n_dev, mono_dev, ex->slot, nframes, s);
+    STAGE_MARK(5);
+#undef STAGE_MARK
+    CK(cudaGetLastError());
+    return VSG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *vsg_last_error(void) { return g_err; }
+
+int vsg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int64_t vsg_launch_count(void) { return g_launches.load(); }
+
+vsg_status vsg_extractor_create(const vsg_orb_params *params, int device, int max_batch, vsg_extractor **out) {
+    if (!params || !out || max_batch < 1 || params->nlevels < 1 || params->nlevels > kMaxLevels ||
+        params->scale_factor <= 1.0f || params->nfeatures < 0) {
+        set_error("vsg_extractor_create: invalid argument");
+        return VSG_ERR_INVALID;
+    }
+    if (vsg_device_count() <= device || device < 0) {
+        set_error("vsg_extractor_create: CUDA device %d not available (this library has no CPU fallback)", device);
+        return VSG_ERR_CUDA;
+    }
+    vsg_extractor *ex = new vsg_extractor();
+    ex->device = device;
+    ex->max_batch = max_batch;
+    ex->p = *params;
+    build_tables(ex);
+    if (!cuda_ok(cudaSetDevice(device), "cudaSetDevice") ||
+        !cuda_ok(cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
+        delete ex;
+        return VSG_ERR_CUDA;
+    }
+    *out = ex;
+    return VSG_OK;
+}
+
+void vsg_extractor_destroy(vsg_extractor *ex) {
+    if (!ex) return;
+    cudaSetDevice(ex->device);
+    if (ex->stream) { cudaStreamSynchronize(ex->stream); cudaStreamDestroy(ex->stream); }
+    if (ex->ev_created)
+        for (int i = 0; i < vsg_extractor::kEvRing; ++i)
+            for (int k = 0; k <= VSG_NUM_STAGES; ++k) cudaEventDestroy(ex->ev[i][k]);
+    ex->free_shape();
+    delete ex;
+}
+
+vsg_status vsg_extractor_tables(const vsg_extractor *ex, float *scale, float *inv_scale, float *sigma2,
+                                float *inv_sigma2, int32_t *features_per_level) {
+    if (!ex) return VSG_ERR_INVALID;
+    for (int i = 0; i < ex->p.nlevels; ++i) {
+        if (scale) scale[i] = ex->scale[i];
+        if (inv_scale) inv_scale[i] = ex->inv_scale[i];
+        if (sigma2) sigma2[i] = ex->sigma2[i];
+        if (inv_sigma2) inv_sigma2[i] = ex->inv_sigma2[i];
+        if (features_per_level) features_per_level[i] = ex->quota[i];
+    }
+    return VSG_OK;
+}
+
+int vsg_extractor_max_keypoints(vsg_extractor *ex, int width, int height) {
+    if (!ex) return VSG_ERR_INVALID;
+    vsg_status st = configure_shape(ex, width, height);
+    if (st != VSG_OK) return st;
+    return ex->g.out_cap;
+}
+
+vsg_status vsg_extract_batch(vsg_extractor *ex, const uint8_t *images, int nframes, int width, int height, int pitch,
+                             size_t frame_stride, int lap_x0, int lap_x1, vsg_keypoint *keypoints_out,
+                             uint8_t *descriptors_out, int capacity, int *n_out, int *mono_index_out) {
+    if (!ex) return VSG_ERR_INVALID;
+    if (!images || width <= 0 || height <= 0 || nframes <= 0) return VSG_EMPTY_IMAGE;   // :1087-1088
+    if (nframes > ex->max_batch || pitch < width || capacity < 0) {
+        set_error("vsg_extract_batch: nframes %d > max_batch %d, or bad pitch/capacity", nframes, ex->max_batch);
+        return VSG_ERR_INVALID;
+    }
+    CK(cudaSetDevice(ex->device));
+    vsg_status st = configure_shape(ex, width, height);
+    if (st != VSG_OK) return st;
+    const FrameGeom &g = ex->g;
+    const LevelGeom &L0 = g.lv[0];
+    uint8_t *lvl0 = ex->pyr + L0.plane_offset;
+    if (frame_stride == (size_t)pitch * height && (int64_t)L0.pitch * L0.h == L0.plane_stride) {
+        CK(cudaMemcpy2DAsync(lvl0, L0.pitch, images, pitch, width, (size_t)height * nframes, cudaMemcpyHostToDevice,
+                             ex->stream));
+    } else {
+        for (int f = 0; f < nframes; ++f)
+            CK(cudaMemcpy2DAsync(lvl0 + f * L0.plane_stride, L0.pitch, images + f * frame_stride, pitch, width, height,
+                                 cudaMemcpyHostToDevice, ex->stream));
+    }
+    st = run_pipeline(ex, lvl0, L0.pitch, L0.plane_stride, nframes, lap_x0, lap_x1, ex->kps_d, ex->desc_d, g.out_cap,
+                      ex->n_d, ex->mono_d);
+    if (st != VSG_OK) return st;
+    CK(cudaMemcpyAsync(ex->n_h, ex->n_d, nframes * sizeof(int), cudaMemcpyDeviceToHost, ex->stream));
+    CK(cudaMemcpyAsync(ex->mono_h, ex->mono_d, nframes * sizeof(int), cudaMemcpyDeviceToHost, ex->stream));
+    CK(cudaMemcpyAsync(ex->kps_h, ex->kps_d, (size_t)nframes * g.out_cap * sizeof(vsg_keypoint), cudaMemcpyDeviceToHost,
+                       ex->stream));
+    CK(cudaMemcpyAsync(ex->desc_h, ex->desc_d, (size_t)nframes * g.out_cap * 32, cudaMemcpyDeviceToHost, ex->stream));
+    CK(cudaStreamSynchronize(ex->stream));
+    vsg_status ret = VSG_OK;
+    for (int f = 0; f < nframes; ++f) {
+        const int n = ex->n_h[f];
+        if (n_out) n_out[f] = n;
+        if (mono_index_out) mono_index_out[f] = ex->mono_h[f];
+        if (n > capacity) {
+            set_error("vsg_extract_batch: frame %d has %d keypoints, capacity %d", f, n, capacity);
+            ret = VSG_ERR_CAPACITY;
+            continue;
+        }
+        if (keypoints_out)
+            memcpy(keypoints_out + (size_t)f * capacity, ex->kps_h + (size_t)f * g.out_cap, (size_t)n * sizeof(vsg_keypoint));
+        if (descriptors_out)
+            memcpy(descriptors_out + (size_t)f * capacity * 32, ex->desc_h + (size_t)f * g.out_cap * 32, (size_t)n * 32);
+    }
+    return ret;
+}
+
+vsg_status vsg_extract(vsg_extractor *ex, const uint8_t *image, int width, int height, int pitch, int lap_x0,
+                       int lap_x1, vsg_keypoint *keypoints_out, uint8_t *descriptors_out, int capacity, int *n_out,
+                       int *mono_index_out) {
+    return vsg_extract_batch(ex, image, 1, width, height, pitch, (size_t)pitch * height, lap_x0, lap_x1, keypoints_out,
+                             descriptors_out, capacity, n_out, mono_index_out);
+}
+
+vsg_status vsg_extract_batch_dev(vsg_extractor *ex, const uint8_t *images_dev, int nframes, int width, int height,
+                                 int pitch, size_t frame_stride, int lap_x0, int lap_x1, vsg_keypoint *keypoints_dev,
+                                 uint8_t *descriptors_dev, int capacity, int32_t *n_dev, int32_t *mono_dev) {
+    if (!ex) return VSG_ERR_INVALID;
+    if (!images_dev || width <= 0 || height <= 0 || nframes <= 0) return VSG_EMPTY_IMAGE;
+    if (nframes > ex->max_batch || pitch < width || (pitch & 3) || ((uintptr_t)images_dev & 3) || (frame_stride & 3)) {
+        set_error("vsg_extract_batch_dev: nframes > max_batch or unaligned device frames (need 4-byte aligned base/pitch/stride)");
+        return VSG_ERR_INVALID;
+    }
+    CK(cudaSetDevice(ex->device));
+    vsg_status st = configure_shape(ex, width, height);
+    if (st != VSG_OK) return st;
+    if (capacity < ex->g.out_cap) {
+        set_error("vsg_extract_batch_dev: capacity %d < vsg_extractor_max_keypoints() = %d", capacity, ex->g.out_cap);
+        return VSG_ERR_CAPACITY;
+    }
+    return run_pipeline(ex, images_dev, pitch, (int64_t)frame_stride, nframes, lap_x0, lap_x1, keypoints_dev,
+                        descriptors_dev, capacity, n_dev, mono_dev);
+}
+
+vsg_status vsg_extractor_sync(vsg_extractor *ex) {
+    if (!ex) return VSG_ERR_INVALID;
+    CK(cudaStreamSynchronize(ex->stream));
+    return VSG_OK;
+}
+
+void *vsg_extractor_stream(vsg_extractor *ex) { return ex ? (void *)ex->stream : nullptr; }
+
+vsg_status vsg_extractor_profile(vsg_extractor *ex, int enable) {
+    if (!ex) return VSG_ERR_INVALID;
+    CK(cudaSetDevice(ex->device));
+    CK(cudaStreamSynchronize(ex->stream));
+    while (ex->ev_pending > 0) ex->harvest_one();
+    ex->profile = enable != 0;
+    for (int k = 0; k < VSG_NUM_STAGES; ++k) ex->stage_ms[k] = 0;
+    ex->stage_runs = 0;
+    return VSG_OK;
+}
+
+vsg_status vsg_extractor_stage_ms(vsg_extractor *ex, double *ms_out, int64_t *runs_out) {
+    if (!ex) return VSG_ERR_INVALID;
+    CK(cudaSetDevice(ex->device));
+    CK(cudaStreamSynchronize(ex->stream));
+    while (ex->ev_pending > 0) ex->harvest_one();
+    for (int k = 0; k < VSG_NUM_STAGES; ++k) {
+        if (ms_out) ms_out[k] = ex->stage_ms[k];
+        ex->stage_ms[k] = 0;
+    }
+    if (runs_out) *runs_out = ex->stage_runs;
+    ex->stage_runs = 0;
+    return VSG_OK;
+}
+
+vsg_status vsg_pyramid_level_size(vsg_extractor *ex, int level, int *width, int *height) {
+    if (!ex || ex->cur_w == 0 || level < 0 || level >= ex->g.nlevels) return VSG_ERR_INVALID;
+    if (width) *width = ex->g.lv[level].w;
+    if (height) *height = ex->g.lv[level].h;
+    return VSG_OK;
+}
+
+static vsg_status download_plane(vsg_extractor *ex, const uint8_t *base, int frame, int level, bool allow_lvl0_ext,
+                                 uint8_t *dst, int dst_pitch) {
+    if (!ex || ex->cur_w == 0 || level < 0 || level >= ex->g.nlevels || frame < 0 || frame >= ex->last_nframes || !dst)
+        return VSG_ERR_INVALID;
+    const LevelGeom &L = ex->g.lv[level];
+    const uint8_t *src = base + L.plane_offset + (int64_t)frame * L.plane_stride;
+    int spitch = L.pitch;
+    if (level == 0 && allow_lvl0_ext) { src = ex->lvl0_base + (int64_t)frame * ex->lvl0_stride; spitch = ex->lvl0_pitch; }
+    CK(cudaSetDevice(ex->device));
+    CK(cudaStreamSynchronize(ex->stream));
+    CK(cudaMemcpy2D(dst, dst_pitch, src, spitch, L.w, L.h, cudaMemcpyDeviceToHost));
+    return VSG_OK;
+}
+
+vsg_status vsg_pyramid_download(vsg_extractor *ex, int frame, int level, uint8_t *dst, int dst_pitch) {
+    return download_plane(ex, ex ? ex->pyr : nullptr, frame, level, true, dst, dst_pitch);
+}
+
+vsg_status vsg_blurred_download(vsg_extractor *ex, int frame, int level, uint8_t *dst, int dst_pitch) {
+    return download_plane(ex, ex ? ex->blur : nullptr, frame, level, false, dst, dst_pitch);
+}
+
+vsg_status vsg_candidates_download(vsg_extractor *ex, int frame, int level, int32_t *xys, int capacity, int *n_out) {
+    if (!ex || ex->cur_w == 0 || level < 0 || level >= ex->g.nlevels || frame < 0 || frame >= ex->last_nframes)
+        return VSG_ERR_INVALID;
+    const FrameGeom &g = ex->g;
+    const LevelGeom &L = g.lv[level];
+    CK(cudaSetDevice(ex->device));
+    CK(cudaStreamSynchronize(ex->stream));
+    int n = 0;
+    CK(cudaMemcpy(&n, ex->cand_count + frame * g.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+    n = std::min(n, L.cand_cap);
+    std::vector<Cand> c(n);
+    CK(cudaMemcpy(c.data(), ex->cand + L.cand_offset + (int64_t)frame * g.cand_total, (size_t)n * sizeof(Cand),
+                  cudaMemcpyDeviceToHost));
+    // the device list is unordered; present it in the reference's order (cell-row-major, row-major inside a cell)
+    auto key = [&](const Cand &a) {
+        const int rx = a.x - kEdge, ry = a.y - kEdge;
+        const int cx = rx / L.w_cell, cy = ry / L.h_cell;
+        return ((int64_t)(cy * L.n_cols + cx) << 32) | ((int64_t)(ry - cy * L.h_cell) << 16) | (rx - cx * L.w_cell);
+    };
+    std::sort(c.begin(), c.end(), [&](const Cand &a, const Cand &b) { return key(a) < key(b); });
+    if (n_out) *n_out = n;
+    if (n > capacity) return VSG_ERR_CAPACITY;
+    for (int i = 0; i < n; ++i) {
+        xys[3 * i] = c[i].x - kBorderMin;
+        xys[3 * i + 1] = c[i].y - kBorderMin;
+        xys[3 * i + 2] = c[i].score;
+    }
+    return VSG_OK;
+}
+
+vsg_status vsg_level_keypoints_download(vsg_extractor *ex, int frame, int level, int32_t *xys, int capacity,
+                                        int *n_out) {
+    if (!ex || ex->cur_w == 0 || level < 0 || level >= ex->g.nlevels || frame < 0 || frame >= ex->last_nframes)
+        return VSG_ERR_INVALID;
+    const FrameGeom &g = ex->g;
+    const LevelGeom &L = g.lv[level];
+    CK(cudaSetDevice(ex->device));
+    CK(cudaStreamSynchronize(ex->stream));
+    int n = 0;
+    CK(cudaMemcpy(&n, ex->level_kp_count + frame * g.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<LevelKp> k(n);
+    CK(cudaMemcpy(k.data(), ex->level_kps + (int64_t)frame * g.kp_total + L.kp_offset, (size_t)n * sizeof(LevelKp),
+                  cudaMemcpyDeviceToHost));
+    if (n_out) *n_out = n;
+    if (n > capacity) return VSG_ERR_CAPACITY;
+    for (int i = 0; i < n; ++i) {
+        xys[3 * i] = k[i].x;
+        xys[3 * i + 1] = k[i].y;
+        xys[3 * i + 2] = k[i].score;
+    }
+    return VSG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,94 @@
+// vsg_internal.cuh — shared declarations of libvsg_cuda.so (not part of the public ABI).
+//
+// Geometry notes (reference orb_slam3/src/ORBextractor.cc):
+//   EDGE_THRESHOLD = 19 (:71): FAST runs on [16, dim-16) (:795-798), keypoints live in [19, dim-19).
+//   Device pyramid planes carry NO 19-px reflected border: nothing on the path reads it
+//   (SURVEY App. A3); the shim re-creates it on the host when it materialises mvImagePyramid.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vsg_cuda.h"
+
+namespace vsg {
+
+constexpr int kMaxLevels = 16;
+constexpr int kEdge = 19;        // EDGE_THRESHOLD
+constexpr int kBorderMin = 16;   // minBorderX/Y = EDGE_THRESHOLD - 3
+constexpr int kHalfPatch = 15;   // HALF_PATCH_SIZE
+constexpr int kPatch = 31;       // PATCH_SIZE
+
+// One pyramid level of the current image shape.
+struct LevelGeom {
+    int w, h;              // level size (cvRound(dim * invScale), :1176)
+    int pitch;             // device row pitch in bytes (multiple of 16)
+    int64_t plane_stride;  // bytes between consecutive frames of this level
+    int64_t plane_offset;  // offset of frame 0 inside the pyramid / blurred buffers
+    // cell grid of ComputeKeyPointsOctTree (:795-809)
+    int n_cols, n_rows, w_cell, h_cell;
+    int cell_begin, cell_count;  // slice of the flat cell table
+    // oct-tree
+    int quota;             // mnFeaturesPerLevel[level]
+    int n_ini;             // round(width/height) root nodes (:566)
+    float h_x;             // root width (:568)
+    int cand_cap;          // candidate slots per frame
+    int64_t cand_offset;   // first candidate slot of frame 0 (in elements); frame stride = cand_total
+    int kp_cap;            // selected-keypoint slots per frame
+    int kp_offset;         // first slot of this level inside a frame's level-keypoint array
+    float scale;           // mvScaleFactor[level]
+    float kp_size;         // (float)(int)(PATCH_SIZE * scale) (:884)
+    // resize tables (device pointers) for building this level from the previous one
+    const short4 *xtab;    // per dst x: {sx0, sx1, a0, a1}
+    const short4 *ytab;    // per dst y: {sy0, sy1, b0, b1}
+};
+
+struct FrameGeom {
+    int nlevels;
+    int ncells;            // total cells over all levels
+    int64_t cand_total;    // candidate slots per frame (all levels)
+    int kp_total;          // selected keypoint slots per frame (all levels)
+    int out_cap;           // output keypoint capacity per frame (== kp_total)
+    LevelGeom lv[kMaxLevels];
+};
+
+// One FAST cell: the sub-image the reference hands to cv::FAST (:811-851).
+struct Cell {
+    short level;
+    short x0, y0;          // window origin in level coordinates (iniX, iniY)
+    short cw, ch;          // window size (maxX-iniX, maxY-iniY), includes FAST's 3-px rim
+    short pad;
+};
+
+// FAST candidate as stored on the device: level coordinates, absolute.
+struct __align__(8) Cand {
+    unsigned short x, y;
+    unsigned short score;  // cv::FAST response (K-1)
+    unsigned short pad;
+};
+
+struct __align__(8) LevelKp {
+    unsigned short x, y;   // level coordinates (already + minBorder)
+    unsigned short score;
+    unsigned short pad;
+};
+
+void set_error(const char *fmt, ...);
+bool cuda_ok(cudaError_t e, const char *what);
+void count_launch(int n = 1);
+
+// --- kernel launchers (each file documents the reference lines it implements) ---
+void launch_resize_level(const FrameGeom &g, int level, const uint8_t *src_base, int src_pitch, int64_t src_stride,
+                         uint8_t *pyr, int nframes, cudaStream_t s);
+void launch_blur(const FrameGeom &g, const uint8_t *lvl0_base, int lvl0_pitch, int64_t lvl0_stride, const uint8_t *pyr,
+                 uint8_t *blur, int nframes, cudaStream_t s);
+void launch_fast(const FrameGeom &g, const Cell *cells, const uint8_t *lvl0_base, int lvl0_pitch, int64_t lvl0_stride,
+                 const uint8_t *pyr, Cand *cand, int *cand_count, int ini_th, int min_th, int max_cw, int max_ch,
+                 int nframes, cudaStream_t s);
+void launch_octree(const FrameGeom &g, const Cand *cand, const int *cand_count, unsigned short *node_of,
+                   LevelKp *level_kps, int *level_kp_count, int max_quota_nodes, int nframes, cudaStream_t s);
+void launch_describe(const FrameGeom &g, const uint8_t *lvl0_base, int lvl0_pitch, int64_t lvl0_stride,
+                     const uint8_t *pyr, const uint8_t *blur, const LevelKp *level_kps, const int *level_kp_count,
+                     int lap_x0, int lap_x1, vsg_keypoint *kps_out, uint8_t *desc_out, int out_cap, int *n_out,
+                     int *mono_out, int *slot_scratch, int nframes, cudaStream_t s);
+
+}  // namespace vsg

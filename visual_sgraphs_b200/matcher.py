@@ -1,0 +1,84 @@
+"""Python mirror of the arithmetic of VS_GRAPHS::ORBmatcher (reference orb_slam3/include/ORBmatcher.h:34-99)
+over the C ABI, on flattened arrays.  Used by tests and bench.py; C++ hosts use shim/ORBmatcher.h.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, ptr
+
+TH_HIGH = 100     # ORBmatcher.cc:34
+TH_LOW = 50       # ORBmatcher.cc:35
+HISTO_LENGTH = 30  # ORBmatcher.cc:36
+
+
+class ORBmatcher:
+    def __init__(self, nnratio=0.6, checkOri=True, device=0):
+        self._L = _lib.load()
+        self._h = C.c_void_p()
+        self.mfNNratio = np.float32(nnratio)
+        self.mbCheckOrientation = bool(checkOri)
+        check(self._L.vsg_matcher_create(device, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.vsg_matcher_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def stream(self):
+        return self._L.vsg_matcher_stream(self._h)
+
+    def sync(self):
+        check(self._L.vsg_matcher_sync(self._h))
+
+    def DescriptorDistance(self, a, b):
+        """ORBmatcher.cc:2047-2063 for n pairs (rows of 32 bytes)."""
+        a = np.ascontiguousarray(a, np.uint8).reshape(-1, 32)
+        b = np.ascontiguousarray(b, np.uint8).reshape(-1, 32)
+        assert a.shape == b.shape
+        out = np.zeros(a.shape[0], np.int32)
+        check(self._L.vsg_descriptor_distance(self._h, ptr(a), ptr(b), a.shape[0], ptr(out)))
+        return out
+
+    def knn2(self, query, train, train_index_offset=0):
+        """Brute-force top-2 (Frame.cc:1200 semantics). Returns (idx [nq,2], dist [nq,2])."""
+        query = np.ascontiguousarray(query, np.uint8).reshape(-1, 32)
+        train = np.ascontiguousarray(train, np.uint8).reshape(-1, 32)
+        nq, nt = query.shape[0], train.shape[0]
+        idx = np.zeros((nq, 2), np.int32)
+        dist = np.zeros((nq, 2), np.int32)
+        check(self._L.vsg_knn2(self._h, ptr(query), nq, ptr(train), nt, train_index_offset, ptr(idx), ptr(dist)))
+        return idx, dist
+
+    def knn2_dev(self, query_dev, train_dev, idx_dev, dist_dev, train_index_offset=0):
+        """torch CUDA tensors: query (nq,32) u8, train (nt,32) u8, idx/dist (nq,2) int32. Async on the matcher stream."""
+        check(self._L.vsg_knn2_dev(self._h, ptr(query_dev), query_dev.shape[0], ptr(train_dev), train_dev.shape[0],
+                                   train_index_offset, ptr(idx_dev), ptr(dist_dev)))
+
+    def knn2_merge_dev(self, idx_parts_dev, dist_parts_dev, out_idx_dev, out_dist_dev):
+        """Merge (nparts, nq, 2) per-shard top-2 lists into (nq, 2)."""
+        nparts, nq = idx_parts_dev.shape[0], idx_parts_dev.shape[1]
+        check(self._L.vsg_knn2_merge_dev(self._h, ptr(idx_parts_dev), ptr(dist_parts_dev), nparts, nq,
+                                         ptr(out_idx_dev), ptr(out_dist_dev)))
+
+    def match_window(self, query, train, cand_ptr, cand, skip=None, train_level=None, init_dist=256):
+        """Best / second-best over per-query candidate lists (ORBmatcher.cc:77-120 idiom).
+        Returns dict(best_idx, best_dist, second_dist, best_level, second_level)."""
+        query = np.ascontiguousarray(query, np.uint8).reshape(-1, 32)
+        train = np.ascontiguousarray(train, np.uint8).reshape(-1, 32)
+        cand_ptr = np.ascontiguousarray(cand_ptr, np.int32)
+        cand = np.ascontiguousarray(cand, np.int32)
+        nq, nt = query.shape[0], train.shape[0]
+        assert cand_ptr.shape[0] == nq + 1
+        if skip is not None:
+            skip = np.ascontiguousarray(skip, np.uint8)
+        if train_level is not None:
+            train_level = np.ascontiguousarray(train_level, np.int32)
+        out = {k: np.zeros(nq, np.int32) for k in ("best_idx", "best_dist", "second_dist", "best_level", "second_level")}
+        check(self._L.vsg_match_window(self._h, ptr(query), nq, ptr(train), nt, ptr(cand_ptr), ptr(cand), ptr(skip),
+                                       ptr(train_level), int(init_dist), ptr(out["best_idx"]), ptr(out["best_dist"]),
+                                       ptr(out["second_dist"]), ptr(out["best_level"]), ptr(out["second_level"])))
+        return out
