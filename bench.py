@@ -1,0 +1,332 @@
+#!/usr/bin/env python3
+"""bench.py — ORB extraction throughput of the B200 front-end (BASELINE.json metric) + matching extras.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = one pass of the hot path (ORBextractor::operator(), reference ORBextractor.cc:1083-1169)
+over one batch of B synthetic 640x480 frames per GPU (TUM settings: 1000 features, 8 levels, 1.2,
+FAST 20/7 — BASELINE config 1).  Frames are sharded by rank with no data-path collective (weak
+scaling).  One JSON line is printed by rank 0:
+  value      frames/s with the batch already resident in HBM (device pointers in, device results out)
+  e2e        frames/s through the host-pointer C-ABI call (pinned host frames -> H2D -> kernels -> D2H)
+  roofline   the dominant kernel group's algorithmic bytes / its CUDA-event time vs the measured HBM peak
+  cpu_baseline  the CPU oracle (a port of the reference algorithm) on this box's host cores, bounded sample
+`--impl reference` times that CPU port alone (all host threads) and prints the same line shape.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+W, H, NFEAT, NLEVELS, SCALE, INI_TH, MIN_TH = 640, 480, 1000, 8, 1.2, 20, 7
+METRIC = "orb_extraction_frames_per_s_640x480_1000f"
+UNIT = "frames/s"
+
+
+def level_sizes(w, h):
+    inv, s = [], np.float32(1.0)
+    for _ in range(NLEVELS):
+        inv.append(np.float32(1.0) / s)
+        s = np.float32(float(s) * float(np.float32(SCALE)))
+    return [(int(np.rint(np.float32(w) * i)), int(np.rint(np.float32(h) * i))) for i in inv]
+
+
+def algorithmic_bytes(w, h, n_kp):
+    """per-stage compulsory bytes per frame. P = sum of level pixels."""
+    px = [a * b for a, b in level_sizes(w, h)]
+    P, p0, p7 = sum(px), px[0], px[-1]
+    stages = {
+        "pyramid": (P - p7) + (P - p0),   # read L0..L6, write L1..L7
+        "fast": P,                        # read every level once
+        "blur": 2 * P,                    # read + write every level
+        "describe": 60 * n_kp,            # 28 B keypoint + 32 B descriptor per keypoint
+        "octree": 0,                      # latency-bound bookkeeping; no roofline claim
+    }
+    return stages, 5 * P - p0 - p7 + 60 * n_kp
+
+
+def make_frames(n, seed0):
+    """n distinct corner-rich frames: 32 seeded synthetic frames, each reused with circular shifts."""
+    from visual_sgraphs_b200.synth import synth_frame
+    base = [synth_frame(seed0 + i, W, H) for i in range(min(n, 32))]
+    out = np.empty((n, H, W), np.uint8)
+    for i in range(n):
+        k = i // len(base)
+        out[i] = np.roll(base[i % len(base)], (7 * k, 13 * k), (0, 1))
+    return out
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def run(self):
+        while not self.stop_flag and self.nv is not None:
+            try:
+                self.sm.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        self.stop_flag = True
+        if self.nv is None or not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml_unavailable"]}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.sm)}
+
+
+def cpu_port_throughput(nframes, threads):
+    """The CPU oracle (port of ORBextractor.cc) over `nframes` frames on `threads` host threads."""
+    from oracle import oracle as orc
+    frames = make_frames(nframes, 9000)
+    secs, total_kp = orc.bench_extract(frames, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, threads)
+    return nframes / secs, secs, total_kp
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference itself
+    cannot be compiled here — DESIGN.md), all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    cores = host_threads()
+    per_step = max(cores * 4, 32)
+    from oracle import oracle as orc
+    frames = make_frames(per_step, 9000)
+    for _ in range(args.warmup):
+        orc.bench_extract(frames[:cores], NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, cores)
+    secs = 0.0
+    for _ in range(args.steps):
+        s, _ = orc.bench_extract(frames, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, cores)
+        secs += s
+    value = per_step * args.steps / secs
+    sample = "%d frames per step x %d steps, %d threads, one extractor per thread" % (per_step, args.steps, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "C1: ORBextractor 640x480, 1000 features, 8 levels, scale 1.2, FAST 20/7",
+                   "frames_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def matching_extras(torch, device):
+    """Hamming matching throughput (BASELINE metric part 2): brute-force kNN-2, configs C5 (100k x 1M) and C3
+    (1000 x 200k), device-resident descriptors, CUDA events on the matcher stream."""
+    from visual_sgraphs_b200.matcher import ORBmatcher
+    m = ORBmatcher(device=device)
+    s = torch.cuda.ExternalStream(m.stream(), device=device)
+    out = {}
+    g = torch.Generator(device="cuda").manual_seed(7)
+    for name, nq, nt, reps in (("knn2_100k_x_1M", 100_000, 1_000_000, 2), ("knn2_1000_x_200k", 1000, 200_000, 20)):
+        q = torch.randint(0, 256, (nq, 32), dtype=torch.uint8, device="cuda", generator=g)
+        t = torch.randint(0, 256, (nt, 32), dtype=torch.uint8, device="cuda", generator=g)
+        idx = torch.zeros((nq, 2), dtype=torch.int32, device="cuda")
+        dist = torch.zeros((nq, 2), dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        m.knn2_dev(q, t, idx, dist)
+        m.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s)
+        for _ in range(reps):
+            m.knn2_dev(q, t, idx, dist)
+        e1.record(s)
+        m.sync()
+        ms = e0.elapsed_time(e1) / reps
+        pairs = nq * nt
+        out[name] = {"ms": ms, "pairs_per_s": pairs / (ms * 1e-3), "matches_per_s": nq / (ms * 1e-3),
+                     "popc_per_s": 8 * pairs / (ms * 1e-3)}
+    m.close()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=512, help="frames per step per GPU")
+    ap.add_argument("--no-extras", action="store_true", help="skip the matching and cpu-baseline extras")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from visual_sgraphs_b200._lib import load
+    from visual_sgraphs_b200.extractor import ORBextractor
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = load()
+    B, K, Wm = args.batch, args.steps, max(args.warmup, 3)
+
+    # ---- workload: B distinct frames per rank, pinned on the host and resident in HBM ----
+    host_frames = torch.from_numpy(make_frames(B, 1000 + 100000 * rank)).pin_memory()
+    dev_frames = host_frames.cuda(non_blocking=False)
+    ex = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_batch=B)
+    cap = ex.max_keypoints(W, H)
+    kps_d = torch.zeros((B, cap, 28), dtype=torch.uint8, device="cuda")
+    desc_d = torch.zeros((B, cap, 32), dtype=torch.uint8, device="cuda")
+    n_d = torch.zeros(B, dtype=torch.int32, device="cuda")
+    mono_d = torch.zeros(B, dtype=torch.int32, device="cuda")
+    stream = torch.cuda.ExternalStream(ex.stream(), device=local_rank)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (value) ----
+    for _ in range(Wm):
+        ex.extract_batch_dev(dev_frames, kps_d, desc_d, n_d, mono_d)
+    ex.sync()
+    sampler = ClockSampler(local_rank)
+    ex.profile(True)
+    launches0 = lib.vsg_launch_count()
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(K):
+        ex.extract_batch_dev(dev_frames, kps_d, desc_d, n_d, mono_d)
+    e1.record(stream)
+    ex.sync()
+    barrier()
+    clocks = sampler.result()
+    launches = lib.vsg_launch_count() - launches0
+    elapsed_ms = e0.elapsed_time(e1)
+    stage_ms, runs = ex.stage_ms()
+    ex.profile(False)
+    n_kp_mean = float(n_d.float().mean().item())
+
+    # ---- end to end through the host-pointer C-ABI call (pinned frames in, host results out) ----
+    host_np = host_frames.numpy()
+    kps_h = np.zeros((B, cap), dtype=[("raw", "u1", 28)])
+    desc_h = np.zeros((B, cap, 32), np.uint8)
+    n_h = np.zeros(B, np.int32)
+    mono_h = np.zeros(B, np.int32)
+    from visual_sgraphs_b200._lib import check, ptr
+
+    def e2e_step():
+        check(lib.vsg_extract_batch(ex._h, ptr(host_np), B, W, H, W, W * H, 0, 0, ptr(kps_h), ptr(desc_h), cap,
+                                    ptr(n_h), ptr(mono_h)))
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+
+    times = torch.tensor([elapsed_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    elapsed_ms, e2e_ms = float(times[0]), float(times[1])
+
+    if rank == 0:
+        frames_total = world * B * K
+        value = frames_total / (elapsed_ms * 1e-3)
+        stages_bytes, b_frame = algorithmic_bytes(W, H, n_kp_mean)
+        peak, peak_src = measured_peaks()
+        dominant = max(stage_ms, key=lambda k: stage_ms[k])
+        roof_stage = dominant if stages_bytes[dominant] > 0 else "fast"
+        dur_ms = stage_ms[roof_stage] / max(runs, 1)
+        achieved = stages_bytes[roof_stage] * B / (dur_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "C1: ORBextractor 640x480, 1000 features, 8 levels, scale 1.2, FAST 20/7",
+                       "frames_per_step_per_gpu": B, "sharding": "frames by rank, no collective",
+                       "l2": "inputs larger than L2: %d MB of frames + %d MB of pyramid/blur planes per step" %
+                             (B * W * H >> 20, (2 * B * 1158012) >> 20),
+                       "keypoints_per_frame": n_kp_mean},
+            "clocks": clocks,
+            "e2e": {"value": frames_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * W * H,
+                    "d2h_bytes_per_step": B * cap * 60 + 8 * B, "ms_per_step": e2e_ms / K},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": roof_stage, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_frame": stages_bytes[roof_stage], "launch_ms": dur_ms,
+                         "dominant_stage_by_time": dominant,
+                         "note": "FAST/pyramid/blur are HBM-bound by bytes but issue-bound in practice (see DESIGN.md)"},
+            "stages_ms_per_step": {k: v / max(runs, 1) for k, v in stage_ms.items()},
+            "pipeline_hbm": {"algorithmic_bytes_per_frame": b_frame,
+                             "achieved_gbs": b_frame * B * K / (elapsed_ms * 1e-3) / 1e9,
+                             "frac": b_frame * B * K / (elapsed_ms * 1e-3) / 1e9 / peak},
+        }
+        if world == 1 and not args.no_extras:
+            cores = host_threads()
+            nfr = max(4 * cores, 64)
+            v_all, secs_all, _ = cpu_port_throughput(nfr, cores)
+            v_one, _, _ = cpu_port_throughput(32, 1)
+            line["cpu_baseline"] = {"value": v_all, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "%d frames of the same workload, %d threads (one extractor per thread), %.1f s" %
+                                              (nfr, cores, secs_all),
+                                    "single_thread_value": v_one}
+            line["matching"] = matching_extras(torch, local_rank)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

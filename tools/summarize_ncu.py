@@ -1,0 +1,69 @@
+#!/usr/bin/env python3
+"""Summarise ncu outputs brought back in gpurun_out/ into small tracked files under profiles/.
+
+  python tools/summarize_ncu.py <tag>
+reads  gpurun_out/launches_<tag>.csv   (ncu --metrics gpu__time_duration.sum launch list)
+       gpurun_out/prof_<tag>.ncu-rep   (ncu --set full capture of the top kernels), if present
+writes profiles/<tag>_launches.md, profiles/<tag>_kernels.csv
+"""
+import csv
+import io
+import os
+import subprocess
+import sys
+from collections import OrderedDict
+
+tag = sys.argv[1]
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+out_dir = os.path.join(root, "profiles")
+os.makedirs(out_dir, exist_ok=True)
+
+launch_csv = os.path.join(root, "gpurun_out", "launches_%s.csv" % tag)
+if os.path.exists(launch_csv):
+    lines = [l for l in open(launch_csv) if not l.startswith("==")]
+    rows = list(csv.DictReader(io.StringIO("".join(lines))))
+    agg = OrderedDict()
+    for r in rows:
+        if r.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        name = r["Kernel Name"].split("(")[0]
+        val = float(r["Metric Value"].replace(",", ""))
+        unit = r["Metric Unit"]
+        us = val / 1e3 if unit in ("ns", "nsecond") else val if unit in ("us", "usecond") else val * 1e3
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += us
+    total = sum(v[1] for v in agg.values())
+    with open(os.path.join(out_dir, "%s_launches.md" % tag), "w") as f:
+        f.write("# ncu launch list summary (%s)\n\n" % tag)
+        f.write("Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py "
+                "--steps 1 --warmup 1 --batch 64 --no-extras` (per-launch times are cold-cache and serialised: "
+                "compare SHARES).\n\n| kernel | launches | total us | share |\n|---|---:|---:|---:|\n")
+        for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write("| %s | %d | %.1f | %.1f%% |\n" % (k, n, us, 100 * us / total))
+    print("wrote launches summary,", len(rows), "rows")
+
+rep = os.path.join(root, "gpurun_out", "prof_%s.ncu-rep" % tag)
+if os.path.exists(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    want = ["Kernel Name", "launch__grid_size", "launch__registers_per_thread", "gpu__time_duration.sum",
+            "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+            "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+            "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+            "sm__inst_executed_pipe_alu.sum", "sm__inst_executed_pipe_fma.sum", "sm__inst_executed_pipe_lsu.sum",
+            "sm__inst_executed_pipe_xu.sum", "sm__inst_executed_pipe_uniform.sum",
+            "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+            "sm__pipe_xu_cycles_active.avg.pct_of_peak_sustained_active",
+            "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "launch__occupancy_limit_shared_mem",
+            "launch__occupancy_limit_registers", "sm__maximum_warps_per_active_cycle_pct"]
+    idx = [(w, hdr.index(w)) for w in want if w in hdr]
+    with open(os.path.join(out_dir, "%s_kernels.csv" % tag), "w", newline="") as f:
+        wr = csv.writer(f)
+        wr.writerow([w for w, _ in idx])
+        wr.writerow([units[i] for _, i in idx])
+        for r in rows[2:]:
+            wr.writerow([r[i].split("(")[0] if w == "Kernel Name" else r[i] for w, i in idx])
+    print("wrote kernel metrics,", len(rows) - 2, "kernels")
