@@ -170,6 +170,97 @@ vsg_status vsg_match_window(vsg_matcher *m, const uint8_t *query, int nq, const 
                             const int32_t *train_level, int init_dist, int32_t *best_idx, int32_t *best_dist,
                             int32_t *second_dist, int32_t *best_level, int32_t *second_level);
 
+/* ------------------------------------------------------------------------------------------------
+ * Search* methods on flattened views (single-camera branches, Frame::Nleft == -1).
+ * The GPU does what dominates the reference's cost — Frame::GetFeaturesInArea (grid window query,
+ * Frame.cc:802-868) and the Hamming distance of every candidate — for all queries of a call at once and
+ * returns per-query candidate lists in the reference's order; the order-dependent bookkeeping of each
+ * method (first-come claims, vMatchedDistance stealing, rotation histogram) is then replayed by host
+ * code inside the library exactly as the reference's loops do.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* What the Search* methods read from a Frame / KeyFrame (Frame.h:254-290,363-381). */
+typedef struct vsg_frame_view {
+    int32_t n;                     /* N */
+    const vsg_keypoint *keys;      /* mvKeysUn (pt, octave, angle are read) */
+    const uint8_t *descriptors;    /* mDescriptors, n x 32 */
+    const float *u_right;          /* mvuRight, NULL for monocular */
+    float min_x, min_y, max_x, max_y;      /* mnMinX, mnMinY, mnMaxX, mnMaxY */
+    float grid_inv_w, grid_inv_h;  /* mfGridElementWidthInv / mfGridElementHeightInv */
+    int32_t grid_cols, grid_rows;  /* FRAME_GRID_COLS / FRAME_GRID_ROWS (64 / 48, Frame.h:49-50) */
+    const float *scale_factors;    /* mvScaleFactors */
+    int32_t n_levels;
+} vsg_frame_view;
+
+/* MapPoint fields read by SearchByProjection(Frame&, vector<MapPoint*>&) (MapPoint.h:142-177). */
+typedef struct vsg_track_point {
+    float proj_x, proj_y, proj_xr; /* mTrackProjX, mTrackProjY, mTrackProjXR */
+    float view_cos;                /* mTrackViewCos */
+    float depth;                   /* mTrackDepth */
+    int32_t level;                 /* mnTrackScaleLevel */
+    uint8_t in_view;               /* mbTrackInView */
+    uint8_t bad;                   /* isBad() */
+    uint8_t blocks;                /* Observations() > 0 */
+    uint8_t pad;
+} vsg_track_point;
+
+/* A last-frame map point already projected into the current frame by the caller (ORBmatcher.cc:1690-1716:
+ * the pose / camera-model arithmetic stays with the reference's Sophus / GeometricCamera classes). */
+typedef struct vsg_proj_point {
+    float u, v;                    /* uv = pCamera->project(Tcw * x3Dw) */
+    float ur;                      /* uv(0) - mbf * invzc */
+    float angle;                   /* LastFrame.mvKeysUn[i].angle */
+    int32_t octave;                /* LastFrame.mvKeys[i].octave */
+    uint8_t valid;                 /* pMP && !mvbOutlier[i] && invzc >= 0 && uv inside [mnMinX,mnMaxX]x[mnMinY,mnMaxY] */
+    uint8_t blocks;                /* pMP->Observations() > 0 */
+    uint8_t pad[2];
+} vsg_proj_point;
+
+typedef struct vsg_frame vsg_frame;
+/* Uploads a frame view and builds its keypoint grid (Frame::AssignFeaturesToGrid / PosInGrid,
+ * Frame.cc:521-553,870-880).  The view's arrays are copied; the handle can serve many searches. */
+vsg_status vsg_frame_create(vsg_matcher *m, const vsg_frame_view *view, vsg_frame **out);
+void vsg_frame_destroy(vsg_frame *f);
+
+/* Frame::GetFeaturesInArea for nq windows at once (x, y, r, min_level, max_level per query): CSR lists of
+ * keypoint indices in the reference's order plus their Hamming distance to qdesc (nq x 32).
+ * cand_ptr has nq + 1 entries; cand_idx / cand_dist hold up to `capacity` entries (VSG_ERR_CAPACITY and
+ * *total_out = needed size if more). */
+vsg_status vsg_area_search(vsg_matcher *m, const vsg_frame *f, int nq, const float *qx, const float *qy,
+                           const float *qr, const int32_t *min_level, const int32_t *max_level,
+                           const uint8_t *qdesc, int32_t *cand_ptr, int32_t *cand_idx, int32_t *cand_dist,
+                           int capacity, int *total_out);
+
+/* SearchByProjection(Frame&, const vector<MapPoint*>&, th, bFarPoints, thFarPoints) (ORBmatcher.cc:42-144).
+ * occupied[i] = F.mvpMapPoints[i] && F.mvpMapPoints[i]->Observations() > 0.  assign_out[i] = index of the map
+ * point the reference writes to F.mvpMapPoints[i], or -1 if untouched.  *nmatches_out = return value. */
+vsg_status vsg_search_by_projection_map(vsg_matcher *m, const vsg_frame *F, const uint8_t *occupied, int n_mp,
+                                        const vsg_track_point *pts, const uint8_t *mp_desc, float th, int far_points,
+                                        float th_far, float nnratio, int32_t *assign_out, int *nmatches_out);
+
+/* SearchByProjection(Frame& Cur, const Frame& Last, th, bMono) (ORBmatcher.cc:1667-1878).  mode: 0 = octaves
+ * [o-1, o+1], 1 = forward (>= o), 2 = backward ([0, o]) (:1719-1724).  assign_out[i] = index of the last-frame
+ * point written to Cur.mvpMapPoints[i], -1 untouched, -2 written and then cleared by the rotation check. */
+vsg_status vsg_search_by_projection_last(vsg_matcher *m, const vsg_frame *Cur, const uint8_t *occupied, int n_last,
+                                         const vsg_proj_point *pts, const uint8_t *desc, float th, int mode,
+                                         int check_ori, int32_t *assign_out, int *nmatches_out);
+
+/* SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (ORBmatcher.cc:643-756).
+ * prev_matched: F1.n x 2 floats, updated in place like vbPrevMatched.  matches12_out: F1.n entries. */
+vsg_status vsg_search_for_initialization(vsg_matcher *m, const vsg_frame_view *F1, const vsg_frame *F2,
+                                         float *prev_matched, int window_size, float nnratio, int check_ori,
+                                         int32_t *matches12_out, int *nmatches_out);
+
+/* SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (ORBmatcher.cc:226-428).  DBoW2::FeatureVector
+ * (std::map<NodeId, vector<unsigned>>) is passed as sorted node ids + CSR lists.  kf_mp_valid[i] = the
+ * keyframe's map point i exists and is not bad.  matches_f_out[j] = keyframe feature matched to frame feature j
+ * (the reference stores that feature's MapPoint*), or -1. */
+vsg_status vsg_search_by_bow(vsg_matcher *m, const vsg_frame_view *KF, const uint8_t *kf_mp_valid,
+                             const vsg_frame_view *F, int kf_nnodes, const int32_t *kf_nodes, const int32_t *kf_ptr,
+                             const int32_t *kf_idx, int f_nnodes, const int32_t *f_nodes, const int32_t *f_ptr,
+                             const int32_t *f_idx, float nnratio, int check_ori, int32_t *matches_f_out,
+                             int *nmatches_out);
+
 #ifdef __cplusplus
 }
 #endif

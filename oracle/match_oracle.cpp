@@ -1,16 +1,24 @@
 /*
- * oracle/match_oracle.cpp — CPU ORACLE for the ORB matcher arithmetic (test infrastructure, NOT
- * product code).  Restates orb_slam3/src/ORBmatcher.cc of snt-arg/visual_sgraphs on flattened arrays.
- * See oracle.h for the parity status.
+ * oracle/match_oracle.cpp — CPU ORACLE for the ORB matcher (test infrastructure, NOT product code).
+ * Restates orb_slam3/src/ORBmatcher.cc and Frame::GetFeaturesInArea / AssignFeaturesToGrid / PosInGrid
+ * (orb_slam3/src/Frame.cc:521-553, 802-880) of snt-arg/visual_sgraphs on flattened views.  Only the
+ * single-camera branches (Frame::Nleft == -1) are restated; the two-camera fisheye branches are out of
+ * scope for this round.  See oracle.h for the parity status.
  */
 #include "oracle.h"
 
+#include <climits>
+#include <cmath>
 #include <cstring>
+#include <vector>
 
-extern "C" {
+namespace {
 
-// ORBmatcher::DescriptorDistance — ORBmatcher.cc:2047-2063: 8 x int32 XOR + bit-parallel popcount.
-int orc_descriptor_distance(const uint8_t *a, const uint8_t *b) {
+const int TH_HIGH = 100;      // ORBmatcher.cc:34
+const int TH_LOW = 50;        // ORBmatcher.cc:35
+const int HISTO_LENGTH = 30;  // ORBmatcher.cc:36
+
+int descriptor_distance(const uint8_t *a, const uint8_t *b) {   // ORBmatcher.cc:2047-2063
     int dist = 0;
     for (int i = 0; i < 8; ++i) {
         uint32_t wa, wb;
@@ -22,6 +30,288 @@ int orc_descriptor_distance(const uint8_t *a, const uint8_t *b) {
         dist += (int)((((v + (v >> 4)) & 0x0F0F0F0Fu) * 0x01010101u) >> 24);
     }
     return dist;
+}
+
+// Frame::AssignFeaturesToGrid + PosInGrid (Frame.cc:521-553, 870-880)
+struct Grid {
+    int cols, rows;
+    std::vector<std::vector<int>> cell;   // [ix * rows + iy]
+    explicit Grid(const orc_frame_view *f) : cols(f->grid_cols), rows(f->grid_rows), cell((size_t)cols * rows) {
+        for (int i = 0; i < f->n; ++i) {
+            const int px = (int)std::round((f->keys[i].x - f->min_x) * f->grid_inv_w);
+            const int py = (int)std::round((f->keys[i].y - f->min_y) * f->grid_inv_h);
+            if (px < 0 || px >= cols || py < 0 || py >= rows) continue;
+            cell[(size_t)px * rows + py].push_back(i);
+        }
+    }
+};
+
+// Frame::GetFeaturesInArea (Frame.cc:802-868)
+void features_in_area(const orc_frame_view *f, const Grid &g, float x, float y, float r, int min_level, int max_level,
+                      std::vector<int> &out) {
+    out.clear();
+    const float fx = r, fy = r;
+    const int min_cx = std::max(0, (int)std::floor((x - f->min_x - fx) * f->grid_inv_w));
+    if (min_cx >= g.cols) return;
+    const int max_cx = std::min(g.cols - 1, (int)std::ceil((x - f->min_x + fx) * f->grid_inv_w));
+    if (max_cx < 0) return;
+    const int min_cy = std::max(0, (int)std::floor((y - f->min_y - fy) * f->grid_inv_h));
+    if (min_cy >= g.rows) return;
+    const int max_cy = std::min(g.rows - 1, (int)std::ceil((y - f->min_y + fy) * f->grid_inv_h));
+    if (max_cy < 0) return;
+    const bool check_levels = (min_level > 0) || (max_level >= 0);
+    for (int ix = min_cx; ix <= max_cx; ++ix)
+        for (int iy = min_cy; iy <= max_cy; ++iy)
+            for (int idx : g.cell[(size_t)ix * g.rows + iy]) {
+                const orc_keypoint &kp = f->keys[idx];
+                if (check_levels) {
+                    if (kp.octave < min_level) continue;
+                    if (max_level >= 0 && kp.octave > max_level) continue;
+                }
+                const float dx = kp.x - x, dy = kp.y - y;
+                if (std::fabs(dx) < fx && std::fabs(dy) < fy) out.push_back(idx);
+            }
+}
+
+// ORBmatcher::ComputeThreeMaxima (ORBmatcher.cc:2002-2043)
+void three_maxima(const int *sizes, int L, int &ind1, int &ind2, int &ind3) {
+    int max1 = 0, max2 = 0, max3 = 0;
+    for (int i = 0; i < L; ++i) {
+        const int s = sizes[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+// the rotation-histogram idiom (e.g. ORBmatcher.cc:351-358): factor = 1/HISTO_LENGTH, C round()
+int rot_bin(float a1, float a2) {
+    const float factor = 1.0f / HISTO_LENGTH;
+    float rot = a1 - a2;
+    if (rot < 0.0) rot += 360.0f;
+    int bin = (int)std::round(rot * factor);
+    if (bin == HISTO_LENGTH) bin = 0;
+    return bin;
+}
+
+}  // namespace
+
+extern "C" {
+
+int orc_descriptor_distance(const uint8_t *a, const uint8_t *b) { return descriptor_distance(a, b); }
+
+int orc_get_features_in_area(const orc_frame_view *f, float x, float y, float r, int min_level, int max_level,
+                             int32_t *out, int cap) {
+    Grid g(f);
+    std::vector<int> v;
+    features_in_area(f, g, x, y, r, min_level, max_level, v);
+    for (size_t i = 0; i < v.size() && (int)i < cap; ++i) out[i] = v[i];
+    return (int)v.size();
+}
+
+void orc_three_maxima(const int32_t *sizes, int L, int32_t *ind1, int32_t *ind2, int32_t *ind3) {
+    int a = -1, b = -1, c = -1;
+    three_maxima(sizes, L, a, b, c);
+    *ind1 = a; *ind2 = b; *ind3 = c;
+}
+
+// ORBmatcher.cc:42-144 (left / single-camera branch)
+int orc_search_by_projection_map(const orc_frame_view *F, const uint8_t *occupied_in, int n_mp,
+                                 const orc_track_point *pts, const uint8_t *mp_desc, float th, int far_points,
+                                 float th_far, float nnratio, int32_t *assign) {
+    Grid g(F);
+    std::vector<uint8_t> blocked(occupied_in, occupied_in + F->n);   // F.mvpMapPoints[idx] with Observations() > 0
+    for (int i = 0; i < F->n; ++i) assign[i] = -1;
+    int nmatches = 0;
+    const bool b_factor = th != 1.0;
+    std::vector<int> cand;
+    for (int i = 0; i < n_mp; ++i) {
+        const orc_track_point &mp = pts[i];
+        if (!mp.in_view) continue;
+        if (far_points && mp.depth > th_far) continue;
+        if (mp.bad) continue;
+        const int level = mp.level;
+        float r = (mp.view_cos > 0.998) ? 2.5f : 4.0f;   // RadiusByViewingCos :218-224
+        if (b_factor) r *= th;
+        features_in_area(F, g, mp.proj_x, mp.proj_y, r * F->scale_factors[level], level - 1, level, cand);
+        if (cand.empty()) continue;
+        const uint8_t *d_mp = mp_desc + (size_t)i * 32;
+        int best = 256, best_level = -1, best2 = 256, best_level2 = -1, best_idx = -1;
+        for (int idx : cand) {
+            if (blocked[idx]) continue;
+            if (F->u_right && F->u_right[idx] > 0) {
+                const float er = std::fabs(mp.proj_xr - F->u_right[idx]);
+                if (er > r * F->scale_factors[level]) continue;
+            }
+            const int dist = descriptor_distance(d_mp, F->descriptors + (size_t)idx * 32);
+            if (dist < best) {
+                best2 = best; best = dist; best_level2 = best_level; best_level = F->keys[idx].octave; best_idx = idx;
+            } else if (dist < best2) {
+                best_level2 = F->keys[idx].octave; best2 = dist;
+            }
+        }
+        if (best <= TH_HIGH) {
+            if (best_level == best_level2 && best > nnratio * best2) continue;
+            if (best_level != best_level2 || best <= nnratio * best2) {
+                assign[best_idx] = i;
+                blocked[best_idx] = mp.blocks;   // later points skip it only if this one has observations
+                ++nmatches;
+            }
+        }
+    }
+    return nmatches;
+}
+
+// ORBmatcher.cc:1667-1784, 1856-1878 (single-camera branch)
+int orc_search_by_projection_last(const orc_frame_view *Cur, const uint8_t *occupied_in, int n_last,
+                                  const orc_proj_point *pts, const uint8_t *desc, float th, int mode, int check_ori,
+                                  int32_t *assign) {
+    Grid g(Cur);
+    std::vector<uint8_t> blocked(occupied_in, occupied_in + Cur->n);
+    for (int i = 0; i < Cur->n; ++i) assign[i] = -1;
+    std::vector<int> rot_hist[HISTO_LENGTH];
+    int nmatches = 0;
+    std::vector<int> cand;
+    for (int i = 0; i < n_last; ++i) {
+        const orc_proj_point &p = pts[i];
+        if (!p.valid) continue;
+        const int oct = p.octave;
+        const float radius = th * Cur->scale_factors[oct];
+        if (mode == 1) features_in_area(Cur, g, p.u, p.v, radius, oct, -1, cand);
+        else if (mode == 2) features_in_area(Cur, g, p.u, p.v, radius, 0, oct, cand);
+        else features_in_area(Cur, g, p.u, p.v, radius, oct - 1, oct + 1, cand);
+        if (cand.empty()) continue;
+        const uint8_t *d_mp = desc + (size_t)i * 32;
+        int best = 256, best_idx = -1;
+        for (int i2 : cand) {
+            if (blocked[i2]) continue;
+            if (Cur->u_right && Cur->u_right[i2] > 0) {
+                const float er = std::fabs(p.ur - Cur->u_right[i2]);
+                if (er > radius) continue;
+            }
+            const int dist = descriptor_distance(d_mp, Cur->descriptors + (size_t)i2 * 32);
+            if (dist < best) { best = dist; best_idx = i2; }
+        }
+        if (best <= TH_HIGH) {
+            assign[best_idx] = i;
+            blocked[best_idx] = p.blocks;
+            ++nmatches;
+            if (check_ori) rot_hist[rot_bin(p.angle, Cur->keys[best_idx].angle)].push_back(best_idx);
+        }
+    }
+    if (check_ori) {
+        int sizes[HISTO_LENGTH], ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; ++i) sizes[i] = (int)rot_hist[i].size();
+        three_maxima(sizes, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx : rot_hist[i]) { assign[idx] = -2; --nmatches; }
+        }
+    }
+    return nmatches;
+}
+
+// ORBmatcher.cc:643-756
+int orc_search_for_initialization(const orc_frame_view *F1, const orc_frame_view *F2, float *prev_matched,
+                                  int window_size, float nnratio, int check_ori, int32_t *matches12) {
+    Grid g2(F2);
+    int nmatches = 0;
+    for (int i = 0; i < F1->n; ++i) matches12[i] = -1;
+    std::vector<int> rot_hist[HISTO_LENGTH];
+    std::vector<int> matched_distance(F2->n, INT_MAX), matches21(F2->n, -1);
+    std::vector<int> cand;
+    for (int i1 = 0; i1 < F1->n; ++i1) {
+        const int level1 = F1->keys[i1].octave;
+        if (level1 > 0) continue;
+        features_in_area(F2, g2, prev_matched[2 * i1], prev_matched[2 * i1 + 1], (float)window_size, level1, level1, cand);
+        if (cand.empty()) continue;
+        const uint8_t *d1 = F1->descriptors + (size_t)i1 * 32;
+        int best = INT_MAX, best2 = INT_MAX, best_idx2 = -1;
+        for (int i2 : cand) {
+            const int dist = descriptor_distance(d1, F2->descriptors + (size_t)i2 * 32);
+            if (matched_distance[i2] <= dist) continue;
+            if (dist < best) { best2 = best; best = dist; best_idx2 = i2; }
+            else if (dist < best2) best2 = dist;
+        }
+        if (best <= TH_LOW) {
+            if (best < (float)best2 * nnratio) {
+                if (matches21[best_idx2] >= 0) { matches12[matches21[best_idx2]] = -1; --nmatches; }
+                matches12[i1] = best_idx2;
+                matches21[best_idx2] = i1;
+                matched_distance[best_idx2] = best;
+                ++nmatches;
+                if (check_ori) rot_hist[rot_bin(F1->keys[i1].angle, F2->keys[best_idx2].angle)].push_back(i1);
+            }
+        }
+    }
+    if (check_ori) {
+        int sizes[HISTO_LENGTH], ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; ++i) sizes[i] = (int)rot_hist[i].size();
+        three_maxima(sizes, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx1 : rot_hist[i])
+                if (matches12[idx1] >= 0) { matches12[idx1] = -1; --nmatches; }
+        }
+    }
+    for (int i1 = 0; i1 < F1->n; ++i1)
+        if (matches12[i1] >= 0) {
+            prev_matched[2 * i1] = F2->keys[matches12[i1]].x;
+            prev_matched[2 * i1 + 1] = F2->keys[matches12[i1]].y;
+        }
+    return nmatches;
+}
+
+// ORBmatcher.cc:226-428 (Nleft == -1 branch)
+int orc_search_by_bow(const orc_frame_view *KF, const uint8_t *kf_mp_valid, const orc_frame_view *F, int kf_nnodes,
+                      const int32_t *kf_nodes, const int32_t *kf_ptr, const int32_t *kf_idx, int f_nnodes,
+                      const int32_t *f_nodes, const int32_t *f_ptr, const int32_t *f_idx, float nnratio, int check_ori,
+                      int32_t *matches_f) {
+    for (int i = 0; i < F->n; ++i) matches_f[i] = -1;
+    int nmatches = 0;
+    std::vector<int> rot_hist[HISTO_LENGTH];
+    int a = 0, b = 0;
+    while (a < kf_nnodes && b < f_nnodes) {
+        if (kf_nodes[a] == f_nodes[b]) {
+            for (int ik = kf_ptr[a]; ik < kf_ptr[a + 1]; ++ik) {
+                const int real_kf = kf_idx[ik];
+                if (!kf_mp_valid[real_kf]) continue;
+                const uint8_t *d_kf = KF->descriptors + (size_t)real_kf * 32;
+                int best1 = 256, best_idx_f = -1, best2 = 256;
+                for (int jf = f_ptr[b]; jf < f_ptr[b + 1]; ++jf) {
+                    const int real_f = f_idx[jf];
+                    if (matches_f[real_f] >= 0) continue;
+                    const int dist = descriptor_distance(d_kf, F->descriptors + (size_t)real_f * 32);
+                    if (dist < best1) { best2 = best1; best1 = dist; best_idx_f = real_f; }
+                    else if (dist < best2) best2 = dist;
+                }
+                if (best1 <= TH_LOW) {
+                    if (static_cast<float>(best1) < nnratio * static_cast<float>(best2)) {
+                        matches_f[best_idx_f] = real_kf;
+                        if (check_ori) rot_hist[rot_bin(KF->keys[real_kf].angle, F->keys[best_idx_f].angle)].push_back(best_idx_f);
+                        ++nmatches;
+                    }
+                }
+            }
+            ++a; ++b;
+        } else if (kf_nodes[a] < f_nodes[b]) {
+            while (a < kf_nnodes && kf_nodes[a] < f_nodes[b]) ++a;   // lower_bound
+        } else {
+            while (b < f_nnodes && f_nodes[b] < kf_nodes[a]) ++b;
+        }
+    }
+    if (check_ori) {
+        int sizes[HISTO_LENGTH], ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; ++i) sizes[i] = (int)rot_hist[i].size();
+        three_maxima(sizes, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx : rot_hist[i]) { matches_f[idx] = -1; --nmatches; }
+        }
+    }
+    return nmatches;
 }
 
 }  // extern "C"

@@ -81,8 +81,74 @@ void orc_orb_descriptor(const uint8_t *img, int pitch, int x, int y, float angle
 int orc_distribute_octree(const float *xyr, int n, int min_x, int max_x, int min_y, int max_y, int quota,
                           int32_t *selected_idx, int cap);
 
-/* ---- matcher arithmetic (ORBmatcher.cc) ---- */
+/* ---- matcher arithmetic (ORBmatcher.cc) on flattened views ---- */
 int orc_descriptor_distance(const uint8_t *a, const uint8_t *b);
+
+/* What the Search* methods read from a Frame / KeyFrame (Frame.h:254-290,363-381). Layout-identical to
+ * vsg_frame_view in include/vsg_cuda.h so tests can hand the same buffers to both. */
+typedef struct orc_frame_view {
+    int32_t n;                     /* N */
+    const orc_keypoint *keys;      /* mvKeysUn */
+    const uint8_t *descriptors;    /* mDescriptors, n x 32 */
+    const float *u_right;          /* mvuRight, NULL for monocular */
+    float min_x, min_y, max_x, max_y;      /* mnMinX .. mnMaxY */
+    float grid_inv_w, grid_inv_h;  /* mfGridElementWidthInv / HeightInv */
+    int32_t grid_cols, grid_rows;  /* FRAME_GRID_COLS / ROWS */
+    const float *scale_factors;    /* mvScaleFactors */
+    int32_t n_levels;
+} orc_frame_view;
+
+/* MapPoint fields read by SearchByProjection(Frame&, vector<MapPoint*>&) (MapPoint.h:142-177). */
+typedef struct orc_track_point {
+    float proj_x, proj_y, proj_xr; /* mTrackProjX, mTrackProjY, mTrackProjXR */
+    float view_cos;                /* mTrackViewCos */
+    float depth;                   /* mTrackDepth */
+    int32_t level;                 /* mnTrackScaleLevel */
+    uint8_t in_view;               /* mbTrackInView */
+    uint8_t bad;                   /* isBad() */
+    uint8_t blocks;                /* Observations() > 0 */
+    uint8_t pad;
+} orc_track_point;
+
+/* A last-frame map point already projected into the current frame (ORBmatcher.cc:1690-1716). */
+typedef struct orc_proj_point {
+    float u, v;                    /* uv = pCamera->project(Tcw * x3Dw) */
+    float ur;                      /* uv(0) - mbf * invzc */
+    float angle;                   /* LastFrame.mvKeysUn[i].angle */
+    int32_t octave;                /* LastFrame.mvKeys[i].octave */
+    uint8_t valid;                 /* pMP && !outlier && invzc >= 0 && uv inside the image bounds */
+    uint8_t blocks;                /* pMP->Observations() > 0 */
+    uint8_t pad[2];
+} orc_proj_point;
+
+/* Frame::GetFeaturesInArea (Frame.cc:802-868); returns count, writes up to cap indices. */
+int orc_get_features_in_area(const orc_frame_view *f, float x, float y, float r, int min_level, int max_level,
+                             int32_t *out, int cap);
+/* ORBmatcher::ComputeThreeMaxima (ORBmatcher.cc:2002-2043) on the bin sizes. */
+void orc_three_maxima(const int32_t *sizes, int L, int32_t *ind1, int32_t *ind2, int32_t *ind3);
+
+/* SearchByProjection(Frame&, vector<MapPoint*>&, th, bFarPoints, thFarPoints) (ORBmatcher.cc:42-144, Nleft==-1).
+ * occupied[i] = F.mvpMapPoints[i] && Observations()>0.  assign[i] = index of the map point written to
+ * F.mvpMapPoints[i], or -1 if untouched.  Returns nmatches. */
+int orc_search_by_projection_map(const orc_frame_view *F, const uint8_t *occupied, int n_mp, const orc_track_point *pts,
+                                 const uint8_t *mp_desc, float th, int far_points, float th_far, float nnratio,
+                                 int32_t *assign);
+/* SearchByProjection(Frame& Cur, const Frame& Last, th, bMono) (ORBmatcher.cc:1667-1878, Nleft==-1).
+ * mode: 0 = octave-1..octave+1, 1 = forward (>= octave), 2 = backward (0..octave).  assign[i] = index of the
+ * last-frame point written to Cur.mvpMapPoints[i], -1 untouched, -2 written and then cleared by the rotation check. */
+int orc_search_by_projection_last(const orc_frame_view *Cur, const uint8_t *occupied, int n_last,
+                                  const orc_proj_point *pts, const uint8_t *desc, float th, int mode, int check_ori,
+                                  int32_t *assign);
+/* SearchForInitialization (ORBmatcher.cc:643-756). prev_matched: n1 x 2 floats, updated in place. */
+int orc_search_for_initialization(const orc_frame_view *F1, const orc_frame_view *F2, float *prev_matched,
+                                  int window_size, float nnratio, int check_ori, int32_t *matches12);
+/* SearchByBoW(KeyFrame*, Frame&, ...) (ORBmatcher.cc:226-428, Nleft==-1). Feature vectors are given as sorted
+ * node ids + CSR lists (DBoW2::FeatureVector is a std::map<NodeId, vector<unsigned>>).  kf_mp_valid[i] = map point
+ * present and not bad.  matches_f[j] = KF feature index matched to frame feature j, or -1. */
+int orc_search_by_bow(const orc_frame_view *KF, const uint8_t *kf_mp_valid, const orc_frame_view *F, int kf_nnodes,
+                      const int32_t *kf_nodes, const int32_t *kf_ptr, const int32_t *kf_idx, int f_nnodes,
+                      const int32_t *f_nodes, const int32_t *f_ptr, const int32_t *f_idx, float nnratio, int check_ori,
+                      int32_t *matches_f);
 
 /* ---- throughput harness for bench.py's cpu_baseline: extracts `nframes` frames (tightly packed
  * w*h each) with `threads` worker threads, one extractor instance per thread; returns seconds. ---- */

@@ -71,6 +71,12 @@ def lib():
         L.orc_orb_descriptor.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_float, vp]
         L.orc_distribute_octree.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int]
         L.orc_descriptor_distance.argtypes = [vp, vp]
+        L.orc_get_features_in_area.argtypes = [vp, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, vp, C.c_int]
+        L.orc_three_maxima.argtypes = [vp, C.c_int, i32p, i32p, i32p]
+        L.orc_search_by_projection_map.argtypes = [vp, vp, C.c_int, vp, vp, C.c_float, C.c_int, C.c_float, C.c_float, vp]
+        L.orc_search_by_projection_last.argtypes = [vp, vp, C.c_int, vp, vp, C.c_float, C.c_int, C.c_int, vp]
+        L.orc_search_for_initialization.argtypes = [vp, vp, vp, C.c_int, C.c_float, C.c_int, vp]
+        L.orc_search_by_bow.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, C.c_float, C.c_int, vp]
         L.orc_bench_extract.restype = C.c_double
         L.orc_bench_extract.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.POINTER(C.c_int64)]
@@ -229,3 +235,54 @@ def bench_extract(frames, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20
     secs = lib().orc_bench_extract(_ptr(frames), n, w, h, nfeatures, scale_factor, nlevels, ini_th, min_th, threads,
                                    C.byref(total))
     return secs, total.value
+
+
+# ---- matcher methods on flattened views; `view` is a ctypes struct with the orc_frame_view layout -----------
+# (visual_sgraphs_b200._lib.FrameView has that layout; tests pass the same buffers to both sides)
+
+def get_features_in_area(view, x, y, r, min_level=-1, max_level=-1):
+    out = np.zeros(max(view.n, 1), np.int32)
+    n = lib().orc_get_features_in_area(C.addressof(view), x, y, r, min_level, max_level, _ptr(out), out.size)
+    return out[:n].copy()
+
+
+def three_maxima(sizes):
+    sizes = np.ascontiguousarray(sizes, np.int32)
+    a, b, c = C.c_int32(-1), C.c_int32(-1), C.c_int32(-1)
+    lib().orc_three_maxima(_ptr(sizes), len(sizes), C.byref(a), C.byref(b), C.byref(c))
+    return a.value, b.value, c.value
+
+
+def search_by_projection_map(view, occupied, pts, mp_desc, th, far_points, th_far, nnratio):
+    occupied = np.ascontiguousarray(occupied, np.uint8)
+    mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
+    assign = np.zeros(view.n, np.int32)
+    nm = lib().orc_search_by_projection_map(C.addressof(view), _ptr(occupied), len(pts), _ptr(pts), _ptr(mp_desc), th,
+                                            int(far_points), th_far, nnratio, _ptr(assign))
+    return nm, assign
+
+
+def search_by_projection_last(view, occupied, pts, desc, th, mode, check_ori):
+    occupied = np.ascontiguousarray(occupied, np.uint8)
+    desc = np.ascontiguousarray(desc, np.uint8)
+    assign = np.zeros(view.n, np.int32)
+    nm = lib().orc_search_by_projection_last(C.addressof(view), _ptr(occupied), len(pts), _ptr(pts), _ptr(desc), th,
+                                             mode, int(check_ori), _ptr(assign))
+    return nm, assign
+
+
+def search_for_initialization(view1, view2, prev_matched, window, nnratio, check_ori):
+    m12 = np.zeros(view1.n, np.int32)
+    nm = lib().orc_search_for_initialization(C.addressof(view1), C.addressof(view2), _ptr(prev_matched), window,
+                                             nnratio, int(check_ori), _ptr(m12))
+    return nm, m12
+
+
+def search_by_bow(kf_view, kf_mp_valid, f_view, kf_fv, f_fv, nnratio, check_ori):
+    kn, kp, ki = (np.ascontiguousarray(a, np.int32) for a in kf_fv)
+    fn, fp, fi = (np.ascontiguousarray(a, np.int32) for a in f_fv)
+    valid = np.ascontiguousarray(kf_mp_valid, np.uint8)
+    out = np.zeros(f_view.n, np.int32)
+    nm = lib().orc_search_by_bow(C.addressof(kf_view), _ptr(valid), C.addressof(f_view), len(kn), _ptr(kn), _ptr(kp),
+                                 _ptr(ki), len(fn), _ptr(fn), _ptr(fp), _ptr(fi), nnratio, int(check_ori), _ptr(out))
+    return nm, out

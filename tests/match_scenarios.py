@@ -1,0 +1,81 @@
+"""Synthetic matcher scenarios shared by the CPU and GPU matcher tests: two related frames extracted by the
+oracle (frame B = frame A shifted, plus noise) flattened into the view structs the Search* methods read."""
+import numpy as np
+
+from visual_sgraphs_b200._lib import PROJ_POINT_DTYPE, TRACK_POINT_DTYPE
+from visual_sgraphs_b200.frame import FrameData
+from visual_sgraphs_b200.synth import synth_frame
+
+_cache = {}
+
+
+def two_frames(oracle, seed=11, shift=(9, 5), size=(640, 480), nfeat=1000):
+    key = (seed, shift, size, nfeat)
+    if key not in _cache:
+        a = synth_frame(seed, *size)
+        rng = np.random.default_rng(seed + 1)
+        b = np.roll(a, (shift[1], shift[0]), (0, 1))
+        b = np.clip(b.astype(np.int16) + rng.integers(-3, 4, b.shape), 0, 255).astype(np.uint8)
+        ex = oracle.OracleExtractor(nfeat)
+        _, ka, da = ex(a)
+        _, kb, db = ex(b)
+        _cache[key] = (ka, da, kb, db)
+    return _cache[key]
+
+
+def frame_data(keys, desc, size=(640, 480), stereo_seed=None):
+    u_right = None
+    if stereo_seed is not None:
+        rng = np.random.default_rng(stereo_seed)
+        disp = rng.uniform(2, 40, len(keys)).astype(np.float32)
+        u_right = np.where(rng.random(len(keys)) < 0.7, keys["x"] - disp, -1).astype(np.float32)
+    return FrameData(keys, desc, u_right=u_right, width=size[0], height=size[1])
+
+
+def track_points(fd_target, kb, db, shift, seed, stereo=False):
+    """Map points seen in frame B, projected into frame A (the Frame being searched)."""
+    rng = np.random.default_rng(seed)
+    n = len(kb)
+    pts = np.zeros(n, TRACK_POINT_DTYPE)
+    pts["proj_x"] = kb["x"] - shift[0] + rng.normal(0, 1.5, n)
+    pts["proj_y"] = kb["y"] - shift[1] + rng.normal(0, 1.5, n)
+    pts["proj_xr"] = pts["proj_x"] - rng.uniform(2, 40, n) if stereo else 0
+    pts["view_cos"] = rng.uniform(0.99, 1.0, n)
+    pts["depth"] = rng.uniform(1, 80, n)
+    pts["level"] = np.clip(kb["octave"] + rng.integers(-1, 2, n), 0, 7)
+    pts["in_view"] = rng.random(n) < 0.9
+    pts["bad"] = rng.random(n) < 0.03
+    pts["blocks"] = rng.random(n) < 0.9
+    occupied = (rng.random(fd_target.n) < 0.1).astype(np.uint8)
+    order = rng.permutation(n)            # map points are not sorted like keypoints
+    return pts[order].copy(), db[order].copy(), occupied
+
+
+def proj_points(fd_cur, kb, db, shift, seed):
+    rng = np.random.default_rng(seed)
+    n = len(kb)
+    pts = np.zeros(n, PROJ_POINT_DTYPE)
+    pts["u"] = kb["x"] - shift[0] + rng.normal(0, 1.0, n)
+    pts["v"] = kb["y"] - shift[1] + rng.normal(0, 1.0, n)
+    pts["ur"] = pts["u"] - rng.uniform(2, 40, n)
+    pts["angle"] = kb["angle"]
+    pts["octave"] = kb["octave"]
+    inside = (pts["u"] >= 0) & (pts["u"] <= 640) & (pts["v"] >= 0) & (pts["v"] <= 480)
+    pts["valid"] = inside & (rng.random(n) < 0.9)
+    pts["blocks"] = rng.random(n) < 0.9
+    occupied = (rng.random(fd_cur.n) < 0.05).astype(np.uint8)
+    return pts, db.copy(), occupied
+
+
+def feature_vector(desc, nnodes=64):
+    """A stand-in for DBoW2::FeatureVector (the vocabulary blob is not in the checkout):
+    node id = a hash of the first descriptor byte; CSR lists in increasing feature index like DBoW2 builds them."""
+    node = (desc[:, 0].astype(np.int32) * 7 + 3) % nnodes
+    nodes = np.unique(node)
+    ptr = [0]
+    idx = []
+    for nd in nodes:
+        members = np.nonzero(node == nd)[0]
+        idx.extend(members.tolist())
+        ptr.append(len(idx))
+    return nodes.astype(np.int32), np.array(ptr, np.int32), np.array(idx, np.int32)

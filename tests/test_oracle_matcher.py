@@ -1,0 +1,130 @@
+"""CPU-only: pins the oracle's matcher restatements (oracle/match_oracle.cpp) with direct, independent
+Python restatements of the reference loops on small inputs (the reference ships no fixtures for them)."""
+import numpy as np
+
+from tests import match_scenarios as sc
+
+POP = np.array([bin(i).count("1") for i in range(256)], np.int32)
+
+
+def hamming(a, b):
+    return int(POP[np.bitwise_xor(a, b)].sum())
+
+
+def py_features_in_area(fd, x, y, r, min_level, max_level):
+    """Frame::GetFeaturesInArea + AssignFeaturesToGrid + PosInGrid (Frame.cc:521-553, 802-880), float32 arithmetic."""
+    f32 = np.float32
+    v = fd.view
+    x, y, r = f32(x), f32(y), f32(r)
+    cols, rows = v.grid_cols, v.grid_rows
+    minx, miny, iw, ih = f32(v.min_x), f32(v.min_y), f32(v.grid_inv_w), f32(v.grid_inv_h)
+    grid = {}
+    for i, k in enumerate(fd.keys):
+        px = int(np.floor(f32((k["x"] - minx) * iw) + f32(0.5))) if (k["x"] - minx) * iw >= 0 else int(np.ceil(f32((k["x"] - minx) * iw) - f32(0.5)))
+        py = int(np.floor(f32((k["y"] - miny) * ih) + f32(0.5))) if (k["y"] - miny) * ih >= 0 else int(np.ceil(f32((k["y"] - miny) * ih) - f32(0.5)))
+        if 0 <= px < cols and 0 <= py < rows:
+            grid.setdefault((px, py), []).append(i)
+    c0 = max(0, int(np.floor(f32(f32(x - minx) - r) * iw)))
+    c1 = min(cols - 1, int(np.ceil(f32(f32(x - minx) + r) * iw)))
+    r0 = max(0, int(np.floor(f32(f32(y - miny) - r) * ih)))
+    r1 = min(rows - 1, int(np.ceil(f32(f32(y - miny) + r) * ih)))
+    if c0 >= cols or c1 < 0 or r0 >= rows or r1 < 0:
+        return []
+    check = (min_level > 0) or (max_level >= 0)
+    out = []
+    for ix in range(c0, c1 + 1):
+        for iy in range(r0, r1 + 1):
+            for i in grid.get((ix, iy), []):
+                k = fd.keys[i]
+                if check:
+                    if k["octave"] < min_level:
+                        continue
+                    if max_level >= 0 and k["octave"] > max_level:
+                        continue
+                if abs(f32(k["x"] - x)) < r and abs(f32(k["y"] - y)) < r:
+                    out.append(i)
+    return out
+
+
+def test_descriptor_distance_is_popcount(oracle):
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 256, (200, 32), dtype=np.uint8)
+    b = rng.integers(0, 256, (200, 32), dtype=np.uint8)
+    for i in range(200):
+        assert oracle.descriptor_distance(a[i], b[i]) == hamming(a[i], b[i])
+    assert oracle.descriptor_distance(a[0], a[0]) == 0
+    assert oracle.descriptor_distance(np.zeros(32, np.uint8), np.full(32, 255, np.uint8)) == 256
+
+
+def test_three_maxima_quirks(oracle):
+    assert oracle.three_maxima([0] * 30) == (-1, -1, -1)
+    s = [0] * 30
+    s[3], s[7], s[9] = 50, 40, 30
+    assert oracle.three_maxima(s) == (3, 7, 9)
+    s[7], s[9] = 4, 3                      # below 10 % of the maximum: dropped (ORBmatcher.cc:2033-2042)
+    assert oracle.three_maxima(s) == (3, -1, -1)
+    s[7] = 5
+    assert oracle.three_maxima(s) == (3, 7, -1)
+    t = [0] * 30
+    t[1] = t[2] = t[3] = t[4] = 10          # ties: strict '>' keeps the earliest bins
+    assert oracle.three_maxima(t) == (1, 2, 3)
+
+
+def test_features_in_area_matches_python_restatement(oracle):
+    ka, da, kb, db = sc.two_frames(oracle)
+    fd = sc.frame_data(ka, da)
+    rng = np.random.default_rng(3)
+    for _ in range(150):
+        x, y = rng.uniform(-20, 660), rng.uniform(-20, 500)
+        r = rng.uniform(1, 60)
+        lo, hi = [(-1, -1), (0, 0), (2, 3), (1, -1), (0, 4)][rng.integers(0, 5)]
+        got = oracle.get_features_in_area(fd.view, x, y, r, lo, hi).tolist()
+        assert got == py_features_in_area(fd, x, y, r, lo, hi)
+
+
+def py_search_by_projection_map(fd, occupied, pts, desc, th, far, th_far, nnratio):
+    f32 = np.float32
+    blocked = occupied.astype(bool).copy()
+    assign = np.full(fd.n, -1, np.int32)
+    nm = 0
+    for i, mp in enumerate(pts):
+        if not mp["in_view"] or (far and mp["depth"] > th_far) or mp["bad"]:
+            continue
+        lvl = int(mp["level"])
+        r = f32(2.5) if float(mp["view_cos"]) > 0.998 else f32(4.0)
+        if th != 1.0:
+            r = f32(r * f32(th))
+        win = f32(r * fd.scale_factors[lvl])
+        cand = py_features_in_area(fd, mp["proj_x"], mp["proj_y"], win, lvl - 1, lvl)
+        best, bl, best2, bl2, bi = 256, -1, 256, -1, -1
+        for idx in cand:
+            if blocked[idx]:
+                continue
+            if fd.u_right is not None and fd.u_right[idx] > 0:
+                if abs(f32(mp["proj_xr"] - fd.u_right[idx])) > win:
+                    continue
+            d = hamming(desc[i], fd.descriptors[idx])
+            if d < best:
+                best2, best, bl2, bl, bi = best, d, bl, int(fd.keys[idx]["octave"]), idx
+            elif d < best2:
+                bl2, best2 = int(fd.keys[idx]["octave"]), d
+        if best <= 100:
+            if bl == bl2 and f32(best) > f32(nnratio) * f32(best2):
+                continue
+            if bl != bl2 or f32(best) <= f32(nnratio) * f32(best2):
+                assign[bi] = i
+                blocked[bi] = bool(mp["blocks"])
+                nm += 1
+    return nm, assign
+
+
+def test_search_by_projection_map_matches_python_restatement(oracle):
+    ka, da, kb, db = sc.two_frames(oracle, size=(322, 243), nfeat=400)
+    for stereo in (False, True):
+        fd = sc.frame_data(ka, da, size=(322, 243), stereo_seed=5 if stereo else None)
+        pts, desc, occ = sc.track_points(fd, kb, db, (9, 5), 21, stereo)
+        for th, far in ((3.0, False), (1.0, True)):
+            nm, assign = oracle.search_by_projection_map(fd.view, occ, pts, desc, th, far, 40.0, 0.8)
+            wnm, wassign = py_search_by_projection_map(fd, occ, pts, desc, th, far, 40.0, 0.8)
+            assert nm == wnm and np.array_equal(assign, wassign)
+            assert nm > 20

@@ -28,6 +28,22 @@ class OrbParams(C.Structure):
                 ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32)]
 
 
+class FrameView(C.Structure):
+    """vsg_frame_view (include/vsg_cuda.h)."""
+    _fields_ = [("n", C.c_int32), ("keys", C.c_void_p), ("descriptors", C.c_void_p), ("u_right", C.c_void_p),
+                ("min_x", C.c_float), ("min_y", C.c_float), ("max_x", C.c_float), ("max_y", C.c_float),
+                ("grid_inv_w", C.c_float), ("grid_inv_h", C.c_float), ("grid_cols", C.c_int32),
+                ("grid_rows", C.c_int32), ("scale_factors", C.c_void_p), ("n_levels", C.c_int32)]
+
+
+TRACK_POINT_DTYPE = np.dtype([("proj_x", "<f4"), ("proj_y", "<f4"), ("proj_xr", "<f4"), ("view_cos", "<f4"),
+                              ("depth", "<f4"), ("level", "<i4"), ("in_view", "u1"), ("bad", "u1"), ("blocks", "u1"),
+                              ("pad", "u1")])
+PROJ_POINT_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("ur", "<f4"), ("angle", "<f4"), ("octave", "<i4"),
+                             ("valid", "u1"), ("blocks", "u1"), ("pad", "u1", 2)])
+assert TRACK_POINT_DTYPE.itemsize == 28 and PROJ_POINT_DTYPE.itemsize == 24
+
+
 class VsgError(RuntimeError):
     def __init__(self, status, message):
         super().__init__("vsg status %d: %s" % (status, message))
@@ -68,6 +84,19 @@ _SIGNATURES = {
     "vsg_knn2_merge_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "vsg_match_window": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5),
+    "vsg_frame_create": (C.c_int, [C.c_void_p, C.POINTER(FrameView), C.POINTER(C.c_void_p)]),
+    "vsg_frame_destroy": (None, [C.c_void_p]),
+    "vsg_area_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 9 + [C.c_int, C.POINTER(C.c_int)]),
+    "vsg_search_by_projection_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                               C.c_float, C.c_int, C.c_float, C.c_float, C.c_void_p,
+                                               C.POINTER(C.c_int)]),
+    "vsg_search_by_projection_last": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                                C.c_float, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
+    "vsg_search_for_initialization": (C.c_int, [C.c_void_p, C.POINTER(FrameView), C.c_void_p, C.c_void_p, C.c_int,
+                                                C.c_float, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
+    "vsg_search_by_bow": (C.c_int, [C.c_void_p, C.POINTER(FrameView), C.c_void_p, C.POINTER(FrameView), C.c_int,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_float, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
 }
 
 _lib = None

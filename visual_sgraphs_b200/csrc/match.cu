@@ -14,15 +14,6 @@
 
 #include "vsg_internal.cuh"
 
-struct vsg_matcher {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    // scratch that grows on demand
-    void *buf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int sm_count = 148;
-};
-
 namespace vsg {
 
 #define CK(call)                                          \
@@ -30,7 +21,7 @@ namespace vsg {
         if (!cuda_ok((call), #call)) return VSG_ERR_CUDA; \
     } while (0)
 
-static vsg_status ensure(vsg_matcher *m, int slot, size_t bytes) {
+vsg_status matcher_ensure(vsg_matcher *m, int slot, size_t bytes) {
     if (m->cap[slot] >= bytes) return VSG_OK;
     if (m->buf[slot]) cudaFree(m->buf[slot]);
     m->buf[slot] = nullptr;
@@ -40,6 +31,7 @@ static vsg_status ensure(vsg_matcher *m, int slot, size_t bytes) {
     m->cap[slot] = want;
     return VSG_OK;
 }
+static vsg_status ensure(vsg_matcher *m, int slot, size_t bytes) { return matcher_ensure(m, slot, bytes); }
 
 __device__ __forceinline__ int hamming256(const uint4 &a0, const uint4 &a1, const uint4 &b0, const uint4 &b1) {
     return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
@@ -203,6 +195,15 @@ __global__ void window_match_kernel(const uint4 *__restrict__ query, int nq, con
     if (second_level) second_level[q] = bl2;
 }
 
+void launch_window_dists(vsg_matcher *m, const uint8_t *query_dev, int nq, const uint8_t *train_dev,
+                         const int *cand_ptr_dev, const int *cand_dev, int *all_dist_dev) {
+    if (nq <= 0) return;
+    window_match_kernel<<<(nq + 127) / 128, 128, 0, m->stream>>>((const uint4 *)query_dev, nq, (const uint4 *)train_dev,
+                                                                cand_ptr_dev, cand_dev, nullptr, nullptr, 256, nullptr,
+                                                                nullptr, nullptr, nullptr, nullptr, all_dist_dev);
+    count_launch();
+}
+
 static void knn2_plan(const vsg_matcher *m, int nq, int nt, int *qtiles, int *nchunks, int *chunk_rows) {
     *qtiles = (nq + kKnnThreads * kKnnQ - 1) / (kKnnThreads * kKnnQ);
     // enough CTAs for ~4 waves over the SMs, chunks a multiple of the tile size and below the key's index range
@@ -262,7 +263,7 @@ void vsg_matcher_destroy(vsg_matcher *m) {
     if (!m) return;
     cudaSetDevice(m->device);
     if (m->stream) { cudaStreamSynchronize(m->stream); cudaStreamDestroy(m->stream); }
-    for (int i = 0; i < 8; ++i) cudaFree(m->buf[i]);
+    for (int i = 0; i < 12; ++i) cudaFree(m->buf[i]);
     delete m;
 }
 

@@ -1,0 +1,540 @@
+// match_methods.cu — the reference's Search* methods on flattened views (single-camera branches).
+//
+// Reference (snt-arg/visual_sgraphs):
+//   Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea   orb_slam3/src/Frame.cc:521-553, 870-880, 802-868
+//   ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&)     orb_slam3/src/ORBmatcher.cc:42-144
+//   ORBmatcher::SearchByProjection(Frame&, const Frame&)           :1667-1878
+//   ORBmatcher::SearchByBoW(KeyFrame*, Frame&)                     :226-428
+//   ORBmatcher::SearchForInitialization                            :643-756
+//   ORBmatcher::ComputeThreeMaxima + rotation histogram            :2002-2043, idiom :351-358
+//
+// Split of work: area_search_kernel answers every window query of a call in parallel — the grid walk of
+// GetFeaturesInArea (same cell order, same level / distance tests, same float arithmetic) fused with the
+// 256-bit Hamming distance of each surviving candidate — and returns per-query candidate lists in the
+// reference's order.  The methods' order-dependent bookkeeping (a keypoint claimed by an earlier map point
+// is skipped by later ones, vMatchedDistance stealing, the rotation histogram) is sequential by
+// definition; it is replayed on the host over those lists, which is O(#candidates) integer work.
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <vector>
+
+#include "vsg_internal.cuh"
+
+struct vsg_frame {
+    int device = 0;        // the frame may outlive the matcher that uploaded it
+    int n = 0, cols = 0, rows = 0, n_levels = 0;
+    float min_x = 0, min_y = 0, inv_w = 0, inv_h = 0;
+    bool has_right = false;
+    // device
+    float2 *xy = nullptr;
+    int *octave = nullptr;
+    float *u_right = nullptr;
+    uint8_t *desc = nullptr;
+    int *cell_ptr = nullptr, *cell_idx = nullptr;
+    // host copies the resolve loops read
+    std::vector<vsg_keypoint> keys;
+    std::vector<float> scale;
+};
+
+namespace vsg {
+
+#define CK(call)                                          \
+    do {                                                  \
+        if (!cuda_ok((call), #call)) return VSG_ERR_CUDA; \
+    } while (0)
+
+constexpr int TH_HIGH = 100, TH_LOW = 50, HISTO_LENGTH = 30;   // ORBmatcher.cc:34-36
+
+struct FrameDev {
+    int n, cols, rows;
+    float min_x, min_y, inv_w, inv_h;
+    const float2 *xy;
+    const int *octave;
+    const float *u_right;   // nullptr if monocular
+    const uint4 *desc;
+    const int *cell_ptr, *cell_idx;
+};
+
+struct AreaQuery {          // one GetFeaturesInArea call + the per-candidate stereo gate of the caller
+    float x, y, r;
+    int min_level, max_level;
+    float xr, rr;           // right-image gate: skip if u_right[idx] > 0 && |xr - u_right[idx]| > rr; rr < 0 disables it
+};
+
+__device__ __forceinline__ int hamming256(const uint4 &a0, const uint4 &a1, const uint4 &b0, const uint4 &b1) {
+    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+// One thread per query: walk the cell range twice (count, then fill).  Frame.cc:802-868.
+__global__ void area_search_kernel(FrameDev f, int nq, const AreaQuery *__restrict__ qs,
+                                   const uint4 *__restrict__ qdesc, int *__restrict__ q_off, int *__restrict__ q_cnt,
+                                   int2 *__restrict__ out, int cap, int *__restrict__ total) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const AreaQuery a = qs[q];
+    int cnt = 0, off = 0;
+    const int min_cx = max(0, (int)floorf((a.x - f.min_x - a.r) * f.inv_w));
+    const int max_cx = min(f.cols - 1, (int)ceilf((a.x - f.min_x + a.r) * f.inv_w));
+    const int min_cy = max(0, (int)floorf((a.y - f.min_y - a.r) * f.inv_h));
+    const int max_cy = min(f.rows - 1, (int)ceilf((a.y - f.min_y + a.r) * f.inv_h));
+    const bool ok = !(min_cx >= f.cols || max_cx < 0 || min_cy >= f.rows || max_cy < 0) && a.r == a.r;
+    const bool check_levels = (a.min_level > 0) || (a.max_level >= 0);
+    uint4 qa, qb;
+    if (ok) { qa = __ldg(qdesc + 2 * q); qb = __ldg(qdesc + 2 * q + 1); }
+    for (int pass = 0; pass < 2 && ok; ++pass) {
+        int w = 0;
+        for (int ix = min_cx; ix <= max_cx; ++ix)
+            for (int iy = min_cy; iy <= max_cy; ++iy) {
+                const int c = ix * f.rows + iy;
+                for (int j = f.cell_ptr[c]; j < f.cell_ptr[c + 1]; ++j) {
+                    const int idx = f.cell_idx[j];
+                    if (check_levels) {
+                        const int o = f.octave[idx];
+                        if (o < a.min_level) continue;
+                        if (a.max_level >= 0 && o > a.max_level) continue;
+                    }
+                    const float2 p = f.xy[idx];
+                    if (!(fabsf(p.x - a.x) < a.r && fabsf(p.y - a.y) < a.r)) continue;
+                    if (a.rr >= 0.f && f.u_right) {
+                        const float ur = f.u_right[idx];
+                        if (ur > 0 && fabsf(a.xr - ur) > a.rr) continue;
+                    }
+                    if (pass == 1) {
+                        if (off + w < cap) {
+                            const int d = hamming256(qa, qb, __ldg(f.desc + 2 * idx), __ldg(f.desc + 2 * idx + 1));
+                            out[off + w] = make_int2(idx, d);
+                        }
+                    }
+                    ++w;
+                }
+            }
+        if (pass == 0) {
+            cnt = w;
+            if (cnt == 0) break;
+            off = atomicAdd(total, cnt);
+        }
+    }
+    q_off[q] = off;
+    q_cnt[q] = cnt;
+}
+
+// Runs the area search for nq queries and brings the lists back: ptr[nq+1] and (idx, dist) pairs in query order.
+static vsg_status area_search(vsg_matcher *m, const vsg_frame *f, int nq, const AreaQuery *qs, const uint8_t *qdesc,
+                              std::vector<int> &ptr, std::vector<int2> &ent) {
+    ptr.assign(nq + 1, 0);
+    ent.clear();
+    if (nq == 0) return VSG_OK;
+    cudaStream_t s = m->stream;
+    vsg_status st;
+    // slots: 7 queries, 8 qdesc, 9 off/cnt/total, 10 out entries
+    if ((st = matcher_ensure(m, 7, (size_t)nq * sizeof(AreaQuery))) || (st = matcher_ensure(m, 8, (size_t)nq * 32)) ||
+        (st = matcher_ensure(m, 9, (size_t)(2 * nq + 1) * sizeof(int))))
+        return st;
+    CK(cudaMemcpyAsync(m->buf[7], qs, (size_t)nq * sizeof(AreaQuery), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(m->buf[8], qdesc, (size_t)nq * 32, cudaMemcpyHostToDevice, s));
+    int *off_d = (int *)m->buf[9], *cnt_d = off_d + nq, *total_d = off_d + 2 * nq;
+    FrameDev fd{f->n, f->cols, f->rows, f->min_x, f->min_y, f->inv_w, f->inv_h, f->xy, f->octave,
+                f->has_right ? f->u_right : nullptr, (const uint4 *)f->desc, f->cell_ptr, f->cell_idx};
+    size_t cap = std::max<size_t>(m->cap[10] / sizeof(int2), (size_t)nq * 32);
+    std::vector<int> off(nq), cnt(nq);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if ((st = matcher_ensure(m, 10, cap * sizeof(int2)))) return st;
+        CK(cudaMemsetAsync(total_d, 0, sizeof(int), s));
+        area_search_kernel<<<(nq + 127) / 128, 128, 0, s>>>(fd, nq, (const AreaQuery *)m->buf[7], (const uint4 *)m->buf[8],
+                                                           off_d, cnt_d, (int2 *)m->buf[10], (int)cap, total_d);
+        count_launch();
+        int total = 0;
+        CK(cudaMemcpyAsync(&total, total_d, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(off.data(), off_d, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(cnt.data(), cnt_d, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if ((size_t)total <= cap) {
+            std::vector<int2> raw(total);
+            if (total) CK(cudaMemcpy(raw.data(), m->buf[10], (size_t)total * sizeof(int2), cudaMemcpyDeviceToHost));
+            ent.resize(total);
+            int w = 0;
+            for (int q = 0; q < nq; ++q) {      // segments were allocated in arbitrary order: re-pack by query
+                ptr[q] = w;
+                for (int k = 0; k < cnt[q]; ++k) ent[w++] = raw[off[q] + k];
+            }
+            ptr[nq] = w;
+            return VSG_OK;
+        }
+        cap = (size_t)total + 1024;             // retry once with the exact size
+    }
+    set_error("area_search: candidate buffer overflow");
+    return VSG_ERR_CAPACITY;
+}
+
+// ORBmatcher::ComputeThreeMaxima (ORBmatcher.cc:2002-2043)
+static void three_maxima(const std::vector<int> *hist, int L, int &ind1, int &ind2, int &ind3) {
+    int max1 = 0, max2 = 0, max3 = 0;
+    for (int i = 0; i < L; ++i) {
+        const int s = (int)hist[i].size();
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+static int rot_bin(float a1, float a2) {   // :351-358 — factor is 1/HISTO_LENGTH, C round()
+    const float factor = 1.0f / HISTO_LENGTH;
+    float rot = a1 - a2;
+    if (rot < 0.0) rot += 360.0f;
+    int bin = (int)std::round(rot * factor);
+    if (bin == HISTO_LENGTH) bin = 0;
+    return bin;
+}
+
+}  // namespace vsg
+
+using namespace vsg;
+
+extern "C" {
+
+vsg_status vsg_frame_create(vsg_matcher *m, const vsg_frame_view *v, vsg_frame **out) {
+    if (!m || !v || !out || v->n < 0 || v->grid_cols < 1 || v->grid_rows < 1 || (v->n > 0 && (!v->keys || !v->descriptors)))
+        return VSG_ERR_INVALID;
+    CK(cudaSetDevice(m->device));
+    vsg_frame *f = new vsg_frame();
+    f->device = m->device; f->n = v->n; f->cols = v->grid_cols; f->rows = v->grid_rows; f->n_levels = v->n_levels;
+    f->min_x = v->min_x; f->min_y = v->min_y; f->inv_w = v->grid_inv_w; f->inv_h = v->grid_inv_h;
+    f->has_right = v->u_right != nullptr;
+    f->keys.assign(v->keys, v->keys + v->n);
+    if (v->scale_factors) f->scale.assign(v->scale_factors, v->scale_factors + v->n_levels);
+    // AssignFeaturesToGrid (Frame.cc:521-553): keypoints appended to their cell in index order; PosInGrid uses round()
+    const int ncell = f->cols * f->rows;
+    std::vector<int> cell_of(v->n, -1), cptr(ncell + 1, 0), cidx;
+    for (int i = 0; i < v->n; ++i) {
+        const int px = (int)std::round((v->keys[i].x - v->min_x) * v->grid_inv_w);
+        const int py = (int)std::round((v->keys[i].y - v->min_y) * v->grid_inv_h);
+        if (px < 0 || px >= f->cols || py < 0 || py >= f->rows) continue;
+        cell_of[i] = px * f->rows + py;
+        ++cptr[cell_of[i] + 1];
+    }
+    for (int c = 0; c < ncell; ++c) cptr[c + 1] += cptr[c];
+    cidx.resize(cptr[ncell]);
+    std::vector<int> fill(cptr.begin(), cptr.end() - 1);
+    for (int i = 0; i < v->n; ++i)
+        if (cell_of[i] >= 0) cidx[fill[cell_of[i]]++] = i;
+    std::vector<float2> xy(v->n);
+    std::vector<int> oct(v->n);
+    for (int i = 0; i < v->n; ++i) { xy[i] = make_float2(v->keys[i].x, v->keys[i].y); oct[i] = v->keys[i].octave; }
+    const size_t n1 = std::max(v->n, 1);
+    bool ok = cuda_ok(cudaMalloc(&f->xy, n1 * sizeof(float2)), "cudaMalloc") &&
+              cuda_ok(cudaMalloc(&f->octave, n1 * sizeof(int)), "cudaMalloc") &&
+              cuda_ok(cudaMalloc(&f->u_right, n1 * sizeof(float)), "cudaMalloc") &&
+              cuda_ok(cudaMalloc(&f->desc, n1 * 32), "cudaMalloc") &&
+              cuda_ok(cudaMalloc(&f->cell_ptr, (size_t)(ncell + 1) * sizeof(int)), "cudaMalloc") &&
+              cuda_ok(cudaMalloc(&f->cell_idx, std::max<size_t>(cidx.size(), 1) * sizeof(int)), "cudaMalloc");
+    cudaStream_t s = m->stream;
+    if (ok && v->n) {
+        ok = cuda_ok(cudaMemcpyAsync(f->xy, xy.data(), v->n * sizeof(float2), cudaMemcpyHostToDevice, s), "H2D") &&
+             cuda_ok(cudaMemcpyAsync(f->octave, oct.data(), v->n * sizeof(int), cudaMemcpyHostToDevice, s), "H2D") &&
+             cuda_ok(cudaMemcpyAsync(f->desc, v->descriptors, (size_t)v->n * 32, cudaMemcpyHostToDevice, s), "H2D");
+        if (ok && v->u_right)
+            ok = cuda_ok(cudaMemcpyAsync(f->u_right, v->u_right, v->n * sizeof(float), cudaMemcpyHostToDevice, s), "H2D");
+        if (ok && !cidx.empty())
+            ok = cuda_ok(cudaMemcpyAsync(f->cell_idx, cidx.data(), cidx.size() * sizeof(int), cudaMemcpyHostToDevice, s), "H2D");
+    }
+    if (ok) ok = cuda_ok(cudaMemcpyAsync(f->cell_ptr, cptr.data(), (size_t)(ncell + 1) * sizeof(int), cudaMemcpyHostToDevice, s), "H2D") &&
+                 cuda_ok(cudaStreamSynchronize(s), "sync");
+    if (!ok) { vsg_frame_destroy(f); return VSG_ERR_CUDA; }
+    *out = f;
+    return VSG_OK;
+}
+
+void vsg_frame_destroy(vsg_frame *f) {
+    if (!f) return;
+    cudaSetDevice(f->device);
+    cudaFree(f->xy); cudaFree(f->octave); cudaFree(f->u_right); cudaFree(f->desc); cudaFree(f->cell_ptr); cudaFree(f->cell_idx);
+    delete f;
+}
+
+vsg_status vsg_area_search(vsg_matcher *m, const vsg_frame *f, int nq, const float *qx, const float *qy,
+                           const float *qr, const int32_t *min_level, const int32_t *max_level,
+                           const uint8_t *qdesc, int32_t *cand_ptr, int32_t *cand_idx, int32_t *cand_dist,
+                           int capacity, int *total_out) {
+    if (!m || !f || nq < 0 || (nq > 0 && (!qx || !qy || !qr || !qdesc || !cand_ptr))) return VSG_ERR_INVALID;
+    CK(cudaSetDevice(m->device));
+    std::vector<AreaQuery> qs(nq);
+    for (int i = 0; i < nq; ++i)
+        qs[i] = AreaQuery{qx[i], qy[i], qr[i], min_level ? min_level[i] : -1, max_level ? max_level[i] : -1, 0.f, -1.f};
+    std::vector<int> ptr;
+    std::vector<int2> ent;
+    vsg_status st = area_search(m, f, nq, qs.data(), qdesc, ptr, ent);
+    if (st != VSG_OK) return st;
+    for (int i = 0; i <= nq; ++i) cand_ptr[i] = ptr[i];
+    if (total_out) *total_out = (int)ent.size();
+    if ((int)ent.size() > capacity) return VSG_ERR_CAPACITY;
+    for (size_t k = 0; k < ent.size(); ++k) {
+        if (cand_idx) cand_idx[k] = ent[k].x;
+        if (cand_dist) cand_dist[k] = ent[k].y;
+    }
+    return VSG_OK;
+}
+
+// ORBmatcher.cc:42-144
+vsg_status vsg_search_by_projection_map(vsg_matcher *m, const vsg_frame *F, const uint8_t *occupied, int n_mp,
+                                        const vsg_track_point *pts, const uint8_t *mp_desc, float th, int far_points,
+                                        float th_far, float nnratio, int32_t *assign_out, int *nmatches_out) {
+    if (!m || !F || n_mp < 0 || !assign_out || (n_mp > 0 && (!pts || !mp_desc)) || (F->n > 0 && !occupied)) return VSG_ERR_INVALID;
+    CK(cudaSetDevice(m->device));
+    const bool b_factor = th != 1.0;
+    // queries = the map points that reach GetFeaturesInArea (:48-74)
+    std::vector<AreaQuery> qs;
+    std::vector<int> q_mp;
+    std::vector<uint8_t> qdesc;
+    qs.reserve(n_mp); q_mp.reserve(n_mp);
+    for (int i = 0; i < n_mp; ++i) {
+        const vsg_track_point &mp = pts[i];
+        if (!mp.in_view) continue;
+        if (far_points && mp.depth > th_far) continue;
+        if (mp.bad) continue;
+        if (mp.level < 0 || mp.level >= (int)F->scale.size()) { set_error("map point %d: level %d out of range", i, mp.level); return VSG_ERR_INVALID; }
+        float r = (mp.view_cos > 0.998) ? 2.5f : 4.0f;    // RadiusByViewingCos (:218-224)
+        if (b_factor) r *= th;
+        const float win = r * F->scale[mp.level];
+        qs.push_back(AreaQuery{mp.proj_x, mp.proj_y, win, mp.level - 1, mp.level, mp.proj_xr, win});
+        q_mp.push_back(i);
+    }
+    qdesc.resize(qs.size() * 32);
+    for (size_t k = 0; k < qs.size(); ++k) memcpy(&qdesc[k * 32], mp_desc + (size_t)q_mp[k] * 32, 32);
+    std::vector<int> ptr;
+    std::vector<int2> ent;
+    vsg_status st = area_search(m, F, (int)qs.size(), qs.data(), qdesc.data(), ptr, ent);
+    if (st != VSG_OK) return st;
+    // sequential replay of :76-141
+    std::vector<uint8_t> blocked(occupied, occupied + F->n);
+    for (int i = 0; i < F->n; ++i) assign_out[i] = -1;
+    int nmatches = 0;
+    for (size_t k = 0; k < qs.size(); ++k) {
+        int best = 256, best_level = -1, best2 = 256, best_level2 = -1, best_idx = -1;
+        for (int c = ptr[k]; c < ptr[k + 1]; ++c) {
+            const int idx = ent[c].x, dist = ent[c].y;
+            if (blocked[idx]) continue;
+            if (dist < best) { best2 = best; best = dist; best_level2 = best_level; best_level = F->keys[idx].octave; best_idx = idx; }
+            else if (dist < best2) { best_level2 = F->keys[idx].octave; best2 = dist; }
+        }
+        if (best <= TH_HIGH) {
+            if (best_level == best_level2 && best > nnratio * best2) continue;
+            if (best_level != best_level2 || best <= nnratio * best2) {
+                assign_out[best_idx] = q_mp[k];
+                blocked[best_idx] = pts[q_mp[k]].blocks;
+                ++nmatches;
+            }
+        }
+    }
+    if (nmatches_out) *nmatches_out = nmatches;
+    return VSG_OK;
+}
+
+// ORBmatcher.cc:1667-1784 and :1856-1878
+vsg_status vsg_search_by_projection_last(vsg_matcher *m, const vsg_frame *Cur, const uint8_t *occupied, int n_last,
+                                         const vsg_proj_point *pts, const uint8_t *desc, float th, int mode,
+                                         int check_ori, int32_t *assign_out, int *nmatches_out) {
+    if (!m || !Cur || n_last < 0 || !assign_out || (n_last > 0 && (!pts || !desc)) || (Cur->n > 0 && !occupied)) return VSG_ERR_INVALID;
+    CK(cudaSetDevice(m->device));
+    std::vector<AreaQuery> qs;
+    std::vector<int> q_src;
+    for (int i = 0; i < n_last; ++i) {
+        const vsg_proj_point &p = pts[i];
+        if (!p.valid) continue;
+        if (p.octave < 0 || p.octave >= (int)Cur->scale.size()) { set_error("point %d: octave %d out of range", i, p.octave); return VSG_ERR_INVALID; }
+        const float radius = th * Cur->scale[p.octave];
+        int lo, hi;
+        if (mode == 1) { lo = p.octave; hi = -1; }                 // forward  (:1719-1720)
+        else if (mode == 2) { lo = 0; hi = p.octave; }             // backward (:1721-1722)
+        else { lo = p.octave - 1; hi = p.octave + 1; }             // :1723-1724
+        qs.push_back(AreaQuery{p.u, p.v, radius, lo, hi, p.ur, radius});
+        q_src.push_back(i);
+    }
+    std::vector<uint8_t> qdesc(qs.size() * 32);
+    for (size_t k = 0; k < qs.size(); ++k) memcpy(&qdesc[k * 32], desc + (size_t)q_src[k] * 32, 32);
+    std::vector<int> ptr;
+    std::vector<int2> ent;
+    vsg_status st = area_search(m, Cur, (int)qs.size(), qs.data(), qdesc.data(), ptr, ent);
+    if (st != VSG_OK) return st;
+    std::vector<uint8_t> blocked(occupied, occupied + Cur->n);
+    for (int i = 0; i < Cur->n; ++i) assign_out[i] = -1;
+    std::vector<int> rot_hist[HISTO_LENGTH];
+    int nmatches = 0;
+    for (size_t k = 0; k < qs.size(); ++k) {
+        int best = 256, best_idx = -1;
+        for (int c = ptr[k]; c < ptr[k + 1]; ++c) {
+            const int i2 = ent[c].x, dist = ent[c].y;
+            if (blocked[i2]) continue;
+            if (dist < best) { best = dist; best_idx = i2; }
+        }
+        if (best <= TH_HIGH) {
+            const vsg_proj_point &p = pts[q_src[k]];
+            assign_out[best_idx] = q_src[k];
+            blocked[best_idx] = p.blocks;
+            ++nmatches;
+            if (check_ori) rot_hist[rot_bin(p.angle, Cur->keys[best_idx].angle)].push_back(best_idx);
+        }
+    }
+    if (check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rot_hist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx : rot_hist[i]) { assign_out[idx] = -2; --nmatches; }
+        }
+    }
+    if (nmatches_out) *nmatches_out = nmatches;
+    return VSG_OK;
+}
+
+// ORBmatcher.cc:643-756
+vsg_status vsg_search_for_initialization(vsg_matcher *m, const vsg_frame_view *F1, const vsg_frame *F2,
+                                         float *prev_matched, int window_size, float nnratio, int check_ori,
+                                         int32_t *matches12_out, int *nmatches_out) {
+    if (!m || !F1 || !F2 || !matches12_out || (F1->n > 0 && (!prev_matched || !F1->keys || !F1->descriptors))) return VSG_ERR_INVALID;
+    CK(cudaSetDevice(m->device));
+    std::vector<AreaQuery> qs;
+    std::vector<int> q_src;
+    for (int i1 = 0; i1 < F1->n; ++i1) {
+        const int level1 = F1->keys[i1].octave;
+        if (level1 > 0) continue;                                   // :659-661
+        qs.push_back(AreaQuery{prev_matched[2 * i1], prev_matched[2 * i1 + 1], (float)window_size, level1, level1, 0.f, -1.f});
+        q_src.push_back(i1);
+    }
+    std::vector<uint8_t> qdesc(qs.size() * 32);
+    for (size_t k = 0; k < qs.size(); ++k) memcpy(&qdesc[k * 32], F1->descriptors + (size_t)q_src[k] * 32, 32);
+    std::vector<int> ptr;
+    std::vector<int2> ent;
+    vsg_status st = area_search(m, F2, (int)qs.size(), qs.data(), qdesc.data(), ptr, ent);
+    if (st != VSG_OK) return st;
+    int nmatches = 0;
+    for (int i = 0; i < F1->n; ++i) matches12_out[i] = -1;
+    std::vector<int> rot_hist[HISTO_LENGTH];
+    std::vector<int> matched_distance(F2->n, INT_MAX), matches21(F2->n, -1);
+    for (size_t k = 0; k < qs.size(); ++k) {
+        const int i1 = q_src[k];
+        int best = INT_MAX, best2 = INT_MAX, best_idx2 = -1;
+        for (int c = ptr[k]; c < ptr[k + 1]; ++c) {
+            const int i2 = ent[c].x, dist = ent[c].y;
+            if (matched_distance[i2] <= dist) continue;             // :682-683
+            if (dist < best) { best2 = best; best = dist; best_idx2 = i2; }
+            else if (dist < best2) best2 = dist;
+        }
+        if (best <= TH_LOW) {
+            if (best < (float)best2 * nnratio) {
+                if (matches21[best_idx2] >= 0) { matches12_out[matches21[best_idx2]] = -1; --nmatches; }
+                matches12_out[i1] = best_idx2;
+                matches21[best_idx2] = i1;
+                matched_distance[best_idx2] = best;
+                ++nmatches;
+                if (check_ori) rot_hist[rot_bin(F1->keys[i1].angle, F2->keys[best_idx2].angle)].push_back(i1);
+            }
+        }
+    }
+    if (check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rot_hist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx1 : rot_hist[i])
+                if (matches12_out[idx1] >= 0) { matches12_out[idx1] = -1; --nmatches; }
+        }
+    }
+    for (int i1 = 0; i1 < F1->n; ++i1)                              // :748-751
+        if (matches12_out[i1] >= 0) {
+            prev_matched[2 * i1] = F2->keys[matches12_out[i1]].x;
+            prev_matched[2 * i1 + 1] = F2->keys[matches12_out[i1]].y;
+        }
+    if (nmatches_out) *nmatches_out = nmatches;
+    return VSG_OK;
+}
+
+// ORBmatcher.cc:226-428
+vsg_status vsg_search_by_bow(vsg_matcher *m, const vsg_frame_view *KF, const uint8_t *kf_mp_valid,
+                             const vsg_frame_view *F, int kf_nnodes, const int32_t *kf_nodes, const int32_t *kf_ptr,
+                             const int32_t *kf_idx, int f_nnodes, const int32_t *f_nodes, const int32_t *f_ptr,
+                             const int32_t *f_idx, float nnratio, int check_ori, int32_t *matches_f_out,
+                             int *nmatches_out) {
+    if (!m || !KF || !F || !matches_f_out || kf_nnodes < 0 || f_nnodes < 0 || (KF->n > 0 && !kf_mp_valid)) return VSG_ERR_INVALID;
+    CK(cudaSetDevice(m->device));
+    // the merge walk over the two FeatureVectors (:248-376): one query per keyframe feature with a usable map
+    // point inside a common node; its candidates are the frame features of that node, in vIndicesF order
+    std::vector<int> q_kf, cptr(1, 0), cand;
+    int a = 0, b = 0;
+    while (a < kf_nnodes && b < f_nnodes) {
+        if (kf_nodes[a] == f_nodes[b]) {
+            for (int ik = kf_ptr[a]; ik < kf_ptr[a + 1]; ++ik) {
+                const int real_kf = kf_idx[ik];
+                if (real_kf < 0 || real_kf >= KF->n) { set_error("bow: keyframe index out of range"); return VSG_ERR_INVALID; }
+                if (!kf_mp_valid[real_kf]) continue;
+                q_kf.push_back(real_kf);
+                for (int jf = f_ptr[b]; jf < f_ptr[b + 1]; ++jf) {
+                    if (f_idx[jf] < 0 || f_idx[jf] >= F->n) { set_error("bow: frame index out of range"); return VSG_ERR_INVALID; }
+                    cand.push_back(f_idx[jf]);
+                }
+                cptr.push_back((int)cand.size());
+            }
+            ++a; ++b;
+        } else if (kf_nodes[a] < f_nodes[b]) {
+            while (a < kf_nnodes && kf_nodes[a] < f_nodes[b]) ++a;
+        } else {
+            while (b < f_nnodes && f_nodes[b] < kf_nodes[a]) ++b;
+        }
+    }
+    const int nq = (int)q_kf.size(), ncand = (int)cand.size();
+    std::vector<int> dist(ncand);
+    if (nq > 0 && ncand > 0) {
+        std::vector<uint8_t> qdesc((size_t)nq * 32);
+        for (int k = 0; k < nq; ++k) memcpy(&qdesc[(size_t)k * 32], KF->descriptors + (size_t)q_kf[k] * 32, 32);
+        vsg_status st;
+        if ((st = matcher_ensure(m, 1, (size_t)nq * 32)) || (st = matcher_ensure(m, 2, (size_t)std::max(F->n, 1) * 32)) ||
+            (st = matcher_ensure(m, 3, (size_t)(nq + 1) * 4)) || (st = matcher_ensure(m, 4, (size_t)ncand * 4)) ||
+            (st = matcher_ensure(m, 6, (size_t)ncand * 4)))
+            return st;
+        cudaStream_t s = m->stream;
+        CK(cudaMemcpyAsync(m->buf[1], qdesc.data(), (size_t)nq * 32, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(m->buf[2], F->descriptors, (size_t)F->n * 32, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(m->buf[3], cptr.data(), (size_t)(nq + 1) * 4, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(m->buf[4], cand.data(), (size_t)ncand * 4, cudaMemcpyHostToDevice, s));
+        launch_window_dists(m, (const uint8_t *)m->buf[1], nq, (const uint8_t *)m->buf[2], (const int *)m->buf[3],
+                            (const int *)m->buf[4], (int *)m->buf[6]);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(dist.data(), m->buf[6], (size_t)ncand * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    for (int i = 0; i < F->n; ++i) matches_f_out[i] = -1;
+    std::vector<int> rot_hist[HISTO_LENGTH];
+    int nmatches = 0;
+    for (int k = 0; k < nq; ++k) {                                   // :256-358 with the distances looked up
+        int best1 = 256, best_idx_f = -1, best2 = 256;
+        for (int c = cptr[k]; c < cptr[k + 1]; ++c) {
+            const int real_f = cand[c];
+            if (matches_f_out[real_f] >= 0) continue;                // :282-283
+            const int d = dist[c];
+            if (d < best1) { best2 = best1; best1 = d; best_idx_f = real_f; }
+            else if (d < best2) best2 = d;
+        }
+        if (best1 <= TH_LOW) {
+            if (static_cast<float>(best1) < nnratio * static_cast<float>(best2)) {
+                matches_f_out[best_idx_f] = q_kf[k];
+                if (check_ori) rot_hist[rot_bin(KF->keys[q_kf[k]].angle, F->keys[best_idx_f].angle)].push_back(best_idx_f);
+                ++nmatches;
+            }
+        }
+    }
+    if (check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rot_hist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx : rot_hist[i]) { matches_f_out[idx] = -1; --nmatches; }
+        }
+    }
+    if (nmatches_out) *nmatches_out = nmatches;
+    return VSG_OK;
+}
+
+}  // extern "C"

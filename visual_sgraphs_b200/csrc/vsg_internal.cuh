@@ -72,6 +72,25 @@ struct __align__(8) LevelKp {
     unsigned short pad;
 };
 
+}  // namespace vsg
+
+// Matcher workspace: a stream plus scratch buffers that grow on demand (defined here so that match.cu and
+// match_methods.cu share it).
+struct vsg_matcher {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    void *buf[12] = {};
+    size_t cap[12] = {};
+    int sm_count = 148;
+};
+
+namespace vsg {
+
+vsg_status matcher_ensure(vsg_matcher *m, int slot, size_t bytes);
+// distances of every CSR candidate: all_dist[c] = |query[q] xor train[cand[c]]| for c in [cand_ptr[q], cand_ptr[q+1])
+void launch_window_dists(vsg_matcher *m, const uint8_t *query_dev, int nq, const uint8_t *train_dev,
+                         const int *cand_ptr_dev, const int *cand_dev, int *all_dist_dev);
+
 void set_error(const char *fmt, ...);
 bool cuda_ok(cudaError_t e, const char *what);
 void count_launch(int n = 1);

@@ -6,7 +6,8 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import check, ptr
+from ._lib import PROJ_POINT_DTYPE, TRACK_POINT_DTYPE, check, ptr
+from .frame import DeviceFrame, FrameData
 
 TH_HIGH = 100     # ORBmatcher.cc:34
 TH_LOW = 50       # ORBmatcher.cc:35
@@ -82,3 +83,77 @@ class ORBmatcher:
                                        ptr(train_level), int(init_dist), ptr(out["best_idx"]), ptr(out["best_dist"]),
                                        ptr(out["second_dist"]), ptr(out["best_level"]), ptr(out["second_level"])))
         return out
+
+    # ---- Search* methods on flattened views (single-camera branches) ----
+    def frame(self, data):
+        """Upload a FrameData and build its grid (Frame::AssignFeaturesToGrid)."""
+        return DeviceFrame(self, data)
+
+    def area_search(self, frame, qx, qy, qr, min_level, max_level, qdesc):
+        """Frame::GetFeaturesInArea for many windows at once -> (cand_ptr, cand_idx, cand_dist)."""
+        qx, qy, qr = (np.ascontiguousarray(a, np.float32) for a in (qx, qy, qr))
+        min_level, max_level = (np.ascontiguousarray(a, np.int32) for a in (min_level, max_level))
+        qdesc = np.ascontiguousarray(qdesc, np.uint8).reshape(-1, 32)
+        nq = len(qx)
+        cand_ptr = np.zeros(nq + 1, np.int32)
+        cap = max(1024, nq * 64)
+        while True:
+            idx, dist, total = np.zeros(cap, np.int32), np.zeros(cap, np.int32), C.c_int(0)
+            st = self._L.vsg_area_search(self._h, frame._h, nq, ptr(qx), ptr(qy), ptr(qr), ptr(min_level),
+                                         ptr(max_level), ptr(qdesc), ptr(cand_ptr), ptr(idx), ptr(dist), cap,
+                                         C.byref(total))
+            if st == _lib.VSG_ERR_CAPACITY:
+                cap = total.value
+                continue
+            check(st)
+            return cand_ptr, idx[: total.value].copy(), dist[: total.value].copy()
+
+    def SearchByProjectionMap(self, frame, occupied, track_points, mp_desc, th=3.0, bFarPoints=False,
+                              thFarPoints=50.0):
+        """SearchByProjection(Frame&, vector<MapPoint*>&, th, bFarPoints, thFarPoints) (ORBmatcher.cc:42-144).
+        Returns (nmatches, assign[N])."""
+        pts = np.ascontiguousarray(track_points, TRACK_POINT_DTYPE)
+        mp_desc = np.ascontiguousarray(mp_desc, np.uint8).reshape(-1, 32)
+        occupied = np.ascontiguousarray(occupied, np.uint8)
+        assign = np.zeros(frame.data.n, np.int32)
+        nm = C.c_int(0)
+        check(self._L.vsg_search_by_projection_map(self._h, frame._h, ptr(occupied), len(pts), ptr(pts), ptr(mp_desc),
+                                                   float(th), int(bFarPoints), float(thFarPoints),
+                                                   float(self.mfNNratio), ptr(assign), C.byref(nm)))
+        return nm.value, assign
+
+    def SearchByProjectionLast(self, cur_frame, occupied, proj_points, desc, th, mode=0):
+        """SearchByProjection(Frame& Cur, const Frame& Last, th, bMono) (ORBmatcher.cc:1667-1878) with the
+        projection done by the caller. Returns (nmatches, assign[N])."""
+        pts = np.ascontiguousarray(proj_points, PROJ_POINT_DTYPE)
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        occupied = np.ascontiguousarray(occupied, np.uint8)
+        assign = np.zeros(cur_frame.data.n, np.int32)
+        nm = C.c_int(0)
+        check(self._L.vsg_search_by_projection_last(self._h, cur_frame._h, ptr(occupied), len(pts), ptr(pts), ptr(desc),
+                                                    float(th), int(mode), int(self.mbCheckOrientation), ptr(assign),
+                                                    C.byref(nm)))
+        return nm.value, assign
+
+    def SearchForInitialization(self, f1_data, f2_frame, prev_matched, windowSize=10):
+        """ORBmatcher.cc:643-756. prev_matched (n1, 2) float32 is updated in place. Returns (nmatches, matches12)."""
+        assert prev_matched.dtype == np.float32 and prev_matched.flags["C_CONTIGUOUS"]
+        m12 = np.zeros(f1_data.n, np.int32)
+        nm = C.c_int(0)
+        check(self._L.vsg_search_for_initialization(self._h, C.byref(f1_data.view), f2_frame._h, ptr(prev_matched),
+                                                    int(windowSize), float(self.mfNNratio),
+                                                    int(self.mbCheckOrientation), ptr(m12), C.byref(nm)))
+        return nm.value, m12
+
+    def SearchByBoW(self, kf_data, kf_mp_valid, f_data, kf_featvec, f_featvec):
+        """SearchByBoW(KeyFrame*, Frame&, ...) (ORBmatcher.cc:226-428). Feature vectors are (nodes, ptr, idx)
+        triples with sorted node ids. Returns (nmatches, matches_f[F.N])."""
+        kn, kp, ki = (np.ascontiguousarray(a, np.int32) for a in kf_featvec)
+        fn, fp, fi = (np.ascontiguousarray(a, np.int32) for a in f_featvec)
+        valid = np.ascontiguousarray(kf_mp_valid, np.uint8)
+        out = np.zeros(f_data.n, np.int32)
+        nm = C.c_int(0)
+        check(self._L.vsg_search_by_bow(self._h, C.byref(kf_data.view), ptr(valid), C.byref(f_data.view), len(kn),
+                                        ptr(kn), ptr(kp), ptr(ki), len(fn), ptr(fn), ptr(fp), ptr(fi),
+                                        float(self.mfNNratio), int(self.mbCheckOrientation), ptr(out), C.byref(nm)))
+        return nm.value, out
