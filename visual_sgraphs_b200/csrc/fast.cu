@@ -9,61 +9,85 @@
 //     response is strictly greater than the responses of its 8 neighbours, where non-corners and
 //     pixels outside the cell's interior ([3,w-3) x [3,h-3)) count as 0.
 //
-// One CTA per (cell, frame).  The cell window is staged in shared memory with aligned 32-bit loads,
-// the strength K of every interior pixel is computed once (it does not depend on the threshold), NMS
-// runs at iniThFAST and — only if the cell produced nothing — again at minThFAST, exactly the
-// reference's retry rule.  Survivors are appended to the (frame, level) candidate list with one
-// global atomic per CTA.  The list order is not the reference's cell-row-major order; the oct-tree
-// only depends on order through the first-max-wins tie break, which octree.cu reproduces from the
-// coordinates (see order_key there).
+// One CTA per (cell, frame).  The cell window is loaded straight into a pair-interleaved shared-memory layout
+// (see below), the strength K of every interior pixel is computed once (it does not depend on the threshold),
+// NMS runs at iniThFAST and — only if the cell produced nothing — again at minThFAST, exactly the reference's
+// retry rule.  Survivors are compacted with warp ballots and appended to the (frame, level) candidate list with
+// one global atomic per CTA.  The list order is not the reference's cell-row-major order; the oct-tree only
+// depends on order through the first-max-wins tie break, which octree.cu reproduces from the coordinates
+// (see order_key there).
 #include "vsg_internal.cuh"
 
 namespace vsg {
 
-// The 16-pixel Bresenham ring is read in OpenCV's order: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)
-// (1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3).
-// Strength K of the pixel at c (tile pitch tp): max over 16 circular 9-windows of the window minimum
-// of the ring (bright arcs) and of the negated window maximum (dark arcs), relative to the centre.
-__device__ __forceinline__ int fast_strength(const uint8_t *c, int tp) {
-    int p[16];
-    p[0] = c[3 * tp];      p[1] = c[3 * tp + 1];   p[2] = c[2 * tp + 2];   p[3] = c[tp + 3];
-    p[4] = c[3];           p[5] = c[-tp + 3];      p[6] = c[-2 * tp + 2];  p[7] = c[-3 * tp + 1];
-    p[8] = c[-3 * tp];     p[9] = c[-3 * tp - 1];  p[10] = c[-2 * tp - 2]; p[11] = c[-tp - 3];
-    p[12] = c[-3];         p[13] = c[tp - 3];      p[14] = c[2 * tp - 2];  p[15] = c[3 * tp - 1];
-    const int v = c[0];
-    // sliding-window min / max of width 9 by doubling: 2, 4, 8, then +1
-    int lo2[16], hi2[16], lo4[16], hi4[16];
+// Packed arithmetic: every thread scores TWO pixels of a row at once, lane 0 = interior column j, lane 1 =
+// column j + S (S = half the interior width), as 16-bit lanes of one 32-bit register.  sm_100a has native
+// two- and three-input packed min/max (VIMNMX.U16x2 / VIMNMX3.U16x2), so the sliding-window minima/maxima of
+// the 16-pixel ring cost half the instructions per pixel.  The cell window is re-laid out in shared memory as
+// such pairs (T2) so that one aligned 32-bit load fetches a ring position for both pixels.
+__device__ __forceinline__ uint32_t min2(uint32_t a, uint32_t b) { uint32_t d; asm("min.u16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) { uint32_t d; asm("max.u16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ uint32_t min3(uint32_t a, uint32_t b, uint32_t c) { return min2(min2(a, b), c); }   // fused to VIMNMX3
+__device__ __forceinline__ uint32_t max3(uint32_t a, uint32_t b, uint32_t c) { return max2(max2(a, b), c); }
+
+constexpr int kFastThreads = 128;
+constexpr int kT2Pitch = 48;      // words per pair-row: 3 (alignment) + lane offset S (<= 36, multiple of 4) + 6 halo columns, rounded to 4
+constexpr int kS2Pitch = 40;      // words per strength row: S + 2
+
+// The 16-pixel Bresenham ring in OpenCV's order: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)
+// (-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3).  Strength K of both pixels of the pair at c: max over the 16
+// circular 9-windows of the window minimum (bright arcs) / of the negated window maximum (dark arcs),
+// relative to the centre, clamped at 0.
+__device__ __forceinline__ uint32_t fast_strength2(const uint32_t *c) {
+    constexpr int P = kT2Pitch;
+    uint32_t p[16];
+    p[0] = c[3 * P];       p[1] = c[3 * P + 1];    p[2] = c[2 * P + 2];    p[3] = c[P + 3];
+    p[4] = c[3];           p[5] = c[-P + 3];       p[6] = c[-2 * P + 2];   p[7] = c[-3 * P + 1];
+    p[8] = c[-3 * P];      p[9] = c[-3 * P - 1];   p[10] = c[-2 * P - 2];  p[11] = c[-P - 3];
+    p[12] = c[-3];         p[13] = c[P - 3];       p[14] = c[2 * P - 2];   p[15] = c[3 * P - 1];
+    const uint32_t v = c[0];
+    uint32_t lo3[16], hi3[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        lo2[i] = min(p[i], p[(i + 1) & 15]);
-        hi2[i] = max(p[i], p[(i + 1) & 15]);
+        lo3[i] = min3(p[i], p[(i + 1) & 15], p[(i + 2) & 15]);
+        hi3[i] = max3(p[i], p[(i + 1) & 15], p[(i + 2) & 15]);
     }
+    uint32_t lo9[16], hi9[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        lo4[i] = min(lo2[i], lo2[(i + 2) & 15]);
-        hi4[i] = max(hi2[i], hi2[(i + 2) & 15]);
+        lo9[i] = min3(lo3[i], lo3[(i + 3) & 15], lo3[(i + 6) & 15]);
+        hi9[i] = max3(hi3[i], hi3[(i + 3) & 15], hi3[(i + 6) & 15]);
     }
-    int best_lo = 0, best_hi = 255;  // max over arcs of window-min, min over arcs of window-max
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const int lo9 = min(min(lo4[i], lo4[(i + 4) & 15]), p[(i + 8) & 15]);
-        const int hi9 = max(max(hi4[i], hi4[(i + 4) & 15]), p[(i + 8) & 15]);
-        best_lo = max(best_lo, lo9);
-        best_hi = min(best_hi, hi9);
-    }
-    return max(max(best_lo - v, v - best_hi), 0);
+    uint32_t best_lo = max3(max3(lo9[0], lo9[1], lo9[2]), max3(lo9[3], lo9[4], lo9[5]), max3(lo9[6], lo9[7], lo9[8]));
+    best_lo = max3(best_lo, max3(lo9[9], lo9[10], lo9[11]), max3(lo9[12], lo9[13], max2(lo9[14], lo9[15])));
+    uint32_t best_hi = min3(min3(hi9[0], hi9[1], hi9[2]), min3(hi9[3], hi9[4], hi9[5]), min3(hi9[6], hi9[7], hi9[8]));
+    best_hi = min3(best_hi, min3(hi9[9], hi9[10], hi9[11]), min3(hi9[12], hi9[13], min2(hi9[14], hi9[15])));
+    // per lane: max(best_lo - v, v - best_hi, 0); the max/min with v keeps both differences non-negative (no borrow)
+    return max2(max2(best_lo, v) - v, v - min2(best_hi, v));
 }
 
-__global__ void __launch_bounds__(256) fast_kernel(FrameGeom g, const Cell *__restrict__ cells,
-                                                   const uint8_t *__restrict__ lvl0_base, int lvl0_pitch,
-                                                   int64_t lvl0_stride, const uint8_t *__restrict__ pyr,
-                                                   Cand *__restrict__ cand, int *__restrict__ cand_count, int ini_th,
-                                                   int min_th, int tile_pitch, int tile_rows, int score_pitch,
-                                                   int list_cap) {
+// Flattened (row, pair) iteration without divisions: index i -> i + kFastThreads.
+struct PairIter {
+    int iy, j, di, dj, S;
+    __device__ PairIter(int tid, int S_) : S(S_) {
+        iy = tid / S_; j = tid - iy * S_;
+        di = kFastThreads / S_; dj = kFastThreads - di * S_;
+    }
+    __device__ __forceinline__ void next() {
+        j += dj; iy += di;
+        if (j >= S) { j -= S; ++iy; }
+    }
+};
+
+__global__ void __launch_bounds__(kFastThreads, 8) fast_kernel(FrameGeom g, const Cell *__restrict__ cells,
+                                                             const uint8_t *__restrict__ lvl0_base, int lvl0_pitch,
+                                                             int64_t lvl0_stride, const uint8_t *__restrict__ pyr,
+                                                             Cand *__restrict__ cand, int *__restrict__ cand_count,
+                                                             int ini_th, int min_th, int tile_rows, int list_cap) {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t *tile = smem;                                        // tile_rows x tile_pitch
-    uint8_t *score = tile + tile_rows * tile_pitch;              // (ih + 2) x score_pitch, zero apron
-    uint32_t *list = reinterpret_cast<uint32_t *>(score + (tile_rows - 4) * score_pitch);
+    uint32_t *t2 = reinterpret_cast<uint32_t *>(smem);                       // tile_rows x kT2Pitch pixel pairs
+    uint32_t *s2 = t2 + tile_rows * kT2Pitch;                                // (ih + 2) x kS2Pitch packed strengths
+    uint32_t *list = s2 + (tile_rows - 4) * kS2Pitch;
     __shared__ int s_count, s_base;
 
     const Cell cell = cells[blockIdx.x];
@@ -75,47 +99,89 @@ __global__ void __launch_bounds__(256) fast_kernel(FrameGeom g, const Cell *__re
     else { src = pyr + L.plane_offset + (int64_t)frame * L.plane_stride; spitch = L.pitch; }
 
     const int tid = threadIdx.x;
-    const int ax0 = cell.x0 & ~3;                 // 4-byte aligned tile origin
-    const int xoff = cell.x0 - ax0;
-    const int nwords = (xoff + cell.cw + 3) >> 2;
-    for (int i = tid; i < cell.ch * nwords; i += 256) {
-        const int r = i / nwords, wi = i - r * nwords;
-        const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(src + (int64_t)(cell.y0 + r) * spitch + ax0) + wi);
-        *reinterpret_cast<uint32_t *>(tile + r * tile_pitch + 4 * wi) = w;
-    }
     const int iw = cell.cw - 6, ih = cell.ch - 6;  // interior = FAST's [3,w-3) x [3,h-3)
-    for (int i = tid; i < (ih + 2) * score_pitch; i += 256) score[i] = 0;
+    // lane 0 of a pair holds window column b, lane 1 column b + S; S is a multiple of 4 so that both halves of
+    // four consecutive pairs come from two aligned 32-bit global loads
+    const int S = (((iw + 1) >> 1) + 3) & ~3;
+    const int ax0 = cell.x0 & ~3;                  // 4-byte aligned origin of the pair columns
+    const int xoff = cell.x0 - ax0;                // window column w sits at pair column xoff + w
+    {
+        const int nq = (xoff + S + 6 + 3) >> 2;    // quads of pair columns per row
+        const uint8_t *base = src + (int64_t)cell.y0 * spitch + ax0;
+        int r = tid / nq, q = tid - r * nq;
+        const int dr = kFastThreads / nq, dq = kFastThreads - dr * nq;
+        while (r < cell.ch) {
+            const uint8_t *row = base + (int64_t)r * spitch + 4 * q;
+            const uint32_t a = __ldg(reinterpret_cast<const uint32_t *>(row));
+            // the second half may reach past the window (never past the pitch: w + 16 <= pitch by construction)
+            const uint32_t b = __ldg(reinterpret_cast<const uint32_t *>(row + S));
+            uint4 o;
+            o.x = __byte_perm(a, b, 0x7470) & 0x00FF00FFu;   // [a0, -, b0, -]
+            o.y = __byte_perm(a, b, 0x7571) & 0x00FF00FFu;
+            o.z = __byte_perm(a, b, 0x7672) & 0x00FF00FFu;
+            o.w = __byte_perm(a, b, 0x7773) & 0x00FF00FFu;
+            *reinterpret_cast<uint4 *>(t2 + r * kT2Pitch + 4 * q) = o;
+            q += dq; r += dr;
+            if (q >= nq) { q -= nq; ++r; }
+        }
+    }
+    for (int i = tid; i < kS2Pitch; i += kFastThreads) {     // top and bottom apron rows of the strength plane
+        s2[i] = 0;
+        s2[(ih + 1) * kS2Pitch + i] = 0;
+    }
     if (tid == 0) s_count = 0;
     __syncthreads();
 
-    for (int i = tid; i < iw * ih; i += 256) {
-        const int iy = i / iw, ix = i - iy * iw;
-        const int K = fast_strength(tile + (iy + 3) * tile_pitch + xoff + ix + 3, tile_pitch);
-        score[(iy + 1) * score_pitch + ix + 1] = (uint8_t)K;
+    const uint32_t *t2c = t2 + 3 * kT2Pitch + xoff + 3;      // pair (row 0, interior column 0)
+    const int npairs = S * ih;
+    for (PairIter it(tid, S); it.iy < ih; it.next()) {
+        uint32_t K = fast_strength2(t2c + it.iy * kT2Pitch + it.j);
+        if (it.j + S >= iw) K &= 0x0000FFFFu;                // no second pixel in this pair
+        if (it.j >= iw) K = 0;
+        s2[(it.iy + 1) * kS2Pitch + it.j + 1] = K;
+    }
+    __syncthreads();
+    // the two halves meet in the middle: column S-1 (lane 0) and column S (lane 1) are neighbours
+    for (int iy = tid; iy < ih; iy += kFastThreads) {
+        uint32_t *row = s2 + (iy + 1) * kS2Pitch;
+        row[0] = row[S] << 16;          // left apron:  lane 0 = outside the cell (0), lane 1 = K(S-1)
+        row[S + 1] = row[1] >> 16;      // right apron: lane 0 = K(S), lane 1 = outside the cell (0)
     }
     __syncthreads();
 
+    const int lane = tid & 31;
     for (int pass = 0; pass < 2; ++pass) {
         const int t = pass == 0 ? ini_th : min_th;
-        for (int i = tid; i < iw * ih; i += 256) {
-            const int iy = i / iw, ix = i - iy * iw;
-            const uint8_t *s = score + (iy + 1) * score_pitch + ix + 1;
-            const int K = s[0];
-            if (K <= t) continue;
-            const int resp = K - 1;
-            bool is_max = true;
-#pragma unroll
-            for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-                for (int dx = -1; dx <= 1; ++dx) {
-                    if (dx == 0 && dy == 0) continue;
-                    const int kn = s[dy * score_pitch + dx];
-                    const int rn = kn > t ? kn - 1 : 0;
-                    is_max = is_max && (resp > rn);
+        const int tt = max(t, 1);       // a corner scoring 0 (K == 1, only possible at t == 0) never survives the NMS
+        PairIter it(tid, S);
+        for (int base = 0; base < npairs; base += kFastThreads, it.next()) {   // warp-uniform trip count
+            bool f0 = false, f1 = false;
+            int k0 = 0, k1 = 0;
+            if (it.iy < ih) {
+                const uint32_t *c = s2 + (it.iy + 1) * kS2Pitch + it.j + 1;
+                const uint32_t K = c[0];
+                k0 = K & 0xFFFF; k1 = K >> 16;
+                if (k0 > tt || k1 > tt) {
+                    // strict maximum over the 8 neighbours: neighbours that are not corners at t are below K anyway
+                    const uint32_t nb = max3(max3(c[-kS2Pitch - 1], c[-kS2Pitch], c[-kS2Pitch + 1]),
+                                             max3(c[-1], c[1], c[kS2Pitch - 1]), max2(c[kS2Pitch], c[kS2Pitch + 1]));
+                    f0 = k0 > tt && k0 > (int)(nb & 0xFFFF);
+                    f1 = k1 > tt && k1 > (int)(nb >> 16);
                 }
-            if (is_max) {
-                const int slot = atomicAdd(&s_count, 1);
-                if (slot < list_cap) list[slot] = (uint32_t)ix | ((uint32_t)iy << 8) | ((uint32_t)resp << 16);
+            }
+            const unsigned m0 = __ballot_sync(0xffffffffu, f0), m1 = __ballot_sync(0xffffffffu, f1);
+            if ((m0 | m1) == 0) continue;
+            int wbase = 0;
+            if (lane == 0) wbase = atomicAdd(&s_count, __popc(m0) + __popc(m1));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            const unsigned lt = (1u << lane) - 1;
+            if (f0) {
+                const int slot = wbase + __popc(m0 & lt);
+                if (slot < list_cap) list[slot] = (uint32_t)it.j | ((uint32_t)it.iy << 8) | ((uint32_t)(k0 - 1) << 16);
+            }
+            if (f1) {
+                const int slot = wbase + __popc(m0) + __popc(m1 & lt);
+                if (slot < list_cap) list[slot] = (uint32_t)(it.j + S) | ((uint32_t)it.iy << 8) | ((uint32_t)(k1 - 1) << 16);
             }
         }
         __syncthreads();
@@ -127,7 +193,7 @@ __global__ void __launch_bounds__(256) fast_kernel(FrameGeom g, const Cell *__re
     if (tid == 0) s_base = atomicAdd(&cand_count[slot_idx], n);
     __syncthreads();
     Cand *out = cand + L.cand_offset + (int64_t)frame * g.cand_total;
-    for (int i = tid; i < n; i += 256) {
+    for (int i = tid; i < n; i += kFastThreads) {
         const int dst = s_base + i;
         if (dst >= L.cand_cap) break;
         const uint32_t e = list[i];
@@ -144,19 +210,18 @@ void launch_fast(const FrameGeom &g, const Cell *cells, const uint8_t *lvl0_base
                  const uint8_t *pyr, Cand *cand, int *cand_count, int ini_th, int min_th, int max_cw, int max_ch,
                  int nframes, cudaStream_t s) {
     if (g.ncells == 0) return;
-    const int tile_pitch = ((max_cw + 3 + 3) & ~3) + 4;           // room for the alignment shift
+    const int max_S = ((((max_cw - 6) + 1) >> 1) + 3) & ~3;
+    if (3 + max_S + 6 + 3 > kT2Pitch || max_S + 2 > kS2Pitch) { set_error("FAST cell wider than the shared-memory tile"); return; }
     const int tile_rows = max_ch;
-    const int score_pitch = ((max_cw - 6 + 2) + 3) & ~3;
     const int list_cap = ((max_cw - 6 + 1) / 2) * ((max_ch - 6 + 1) / 2) + 1;
-    const size_t smem = (size_t)tile_rows * tile_pitch + (size_t)(tile_rows - 4) * score_pitch + (size_t)list_cap * 4 + 16;
+    const size_t smem = (size_t)tile_rows * kT2Pitch * 4 + (size_t)(tile_rows - 4) * kS2Pitch * 4 + (size_t)list_cap * 4 + 16;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         cudaFuncSetAttribute(fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    fast_kernel<<<dim3(g.ncells, nframes), 256, smem, s>>>(g, cells, lvl0_base, lvl0_pitch, lvl0_stride, pyr, cand,
-                                                          cand_count, ini_th, min_th, tile_pitch, tile_rows,
-                                                          score_pitch, list_cap);
+    fast_kernel<<<dim3(g.ncells, nframes), kFastThreads, smem, s>>>(g, cells, lvl0_base, lvl0_pitch, lvl0_stride, pyr, cand,
+                                                                  cand_count, ini_th, min_th, tile_rows, list_cap);
     count_launch();
 }
 
