@@ -52,12 +52,15 @@ void launch_resize_level(const FrameGeom &g, int level, const uint8_t *src_base,
 }
 
 // ------------------------------------------------------------------------------------------------
-// blur: CTA = 64 x 32 output tile; source tile (70 x 38) staged in shared memory with the
-// REFLECT_101 index map applied at load time (the blur reflects the level itself, not a padded
-// buffer — SURVEY App. A2), horizontal pass into a u16 plane, vertical pass from it.
-// One launch covers every level: blockIdx.x walks a flat tile table.
+// blur: no shared memory.  One thread owns a strip of 4 columns x 32 rows and walks down it with a
+// 7-row register window of horizontal sums: per source row three aligned 32-bit loads, the four
+// horizontal sums by funnel-shift + two IDP4A each (taps packed as bytes), then four vertical sums
+// and one 32-bit store.  REFLECT_101 reflects the level itself, not a padded buffer:
+// rows by index arithmetic, columns by giving the first and the last one or two 4-column groups of a
+// row to separate "edge" work items that assemble their 12 source bytes one by one — they are queued
+// after all interior items so that interior warps never diverge.  One launch covers every level.
 // ------------------------------------------------------------------------------------------------
-constexpr int kBlurTW = 64, kBlurTH = 32;
+constexpr int kBlurRows = 32, kBlurThreads = 128;
 
 __device__ __forceinline__ int reflect101(int i, int n) {
     if (i < 0) i = -i;
@@ -67,20 +70,67 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 
 struct BlurLevels {
     int nlevels;
-    int tile_begin[kMaxLevels + 1];  // prefix sums of tiles per level
-    int tiles_x[kMaxLevels];
+    int block_begin[kMaxLevels + 1];  // prefix sums of thread blocks per level
+    int n_int_cg[kMaxLevels];         // interior 4-column groups per row: cg = 1 .. n_int_cg
+    int n_edge_cg[kMaxLevels];        // edge groups per row: cg = 0 and cg > n_int_cg
+    int n_strips[kMaxLevels];
 };
 
-__global__ void __launch_bounds__(256) blur_kernel(FrameGeom g, BlurLevels bl, const uint8_t *__restrict__ lvl0_base,
-                                                   int lvl0_pitch, int64_t lvl0_stride, const uint8_t *__restrict__ pyr,
-                                                   uint8_t *__restrict__ blur) {
-    __shared__ uint8_t tile[kBlurTH + 6][kBlurTW + 8];
-    __shared__ uint16_t hbuf[kBlurTH + 6][kBlurTW];
+template <bool kEdge>
+__device__ __forceinline__ void blur_load_row(const uint8_t *__restrict__ row, int x, int w, uint32_t h[4]) {
+    uint32_t w0, w1, w2;
+    if (!kEdge) {
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(row + x);
+        w0 = __ldg(p - 1); w1 = __ldg(p); w2 = __ldg(p + 1);
+    } else {
+        uint32_t b[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) b[k] = __ldg(row + reflect101(min(x - 4 + k, w + 2), w));
+        w0 = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+        w1 = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+        w2 = b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24);
+    }
+    // output k: bytes x+k-3 .. x+k+3; taps {18,34,48,56 | 48,34,18,-} packed little-endian
+    const uint32_t kLo = 0x38302212u, kHi = 0x00122230u;
+    h[0] = __dp4a(__funnelshift_r(w0, w1, 8), kLo, __dp4a(__funnelshift_r(w1, w2, 8), kHi, 0u));
+    h[1] = __dp4a(__funnelshift_r(w0, w1, 16), kLo, __dp4a(__funnelshift_r(w1, w2, 16), kHi, 0u));
+    h[2] = __dp4a(__funnelshift_r(w0, w1, 24), kLo, __dp4a(__funnelshift_r(w1, w2, 24), kHi, 0u));
+    h[3] = __dp4a(w1, kLo, __dp4a(w2, kHi, 0u));
+}
+
+template <bool kEdge>
+__device__ __forceinline__ void blur_strip(const uint8_t *__restrict__ src, int spitch, uint8_t *__restrict__ dst,
+                                           int dpitch, int w, int h, int x, int y0) {
+    uint32_t hw[7][4];
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+        blur_load_row<kEdge>(src + (int64_t)reflect101(min(y0 - 3 + r, h + 2), h) * spitch, x, w, hw[r]);
+    const int yend = min(y0 + kBlurRows, h);
+    for (int base = 0; base < kBlurRows; base += 7) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            const int y = y0 + base + k;
+            if (y < yend) {
+                blur_load_row<kEdge>(src + (int64_t)reflect101(min(y + 3, h + 2), h) * spitch, x, w, hw[(k + 6) % 7]);
+                uint32_t v[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    v[c] = 18u * (hw[k % 7][c] + hw[(k + 6) % 7][c]) + 34u * (hw[(k + 1) % 7][c] + hw[(k + 5) % 7][c]) +
+                           48u * (hw[(k + 2) % 7][c] + hw[(k + 4) % 7][c]) + (56u * hw[(k + 3) % 7][c] + 32768u);
+                // (v + 32768) >> 16 is byte 2 of each sum
+                const uint32_t out = __byte_perm(__byte_perm(v[0], v[1], 0x0062), __byte_perm(v[2], v[3], 0x0062), 0x5410);
+                *reinterpret_cast<uint32_t *>(dst + (int64_t)y * dpitch + x) = out;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBlurThreads) blur_kernel(FrameGeom g, BlurLevels bl, const uint8_t *__restrict__ lvl0_base,
+                                                            int lvl0_pitch, int64_t lvl0_stride,
+                                                            const uint8_t *__restrict__ pyr, uint8_t *__restrict__ blur) {
     int level = 0;
-    while (level + 1 < bl.nlevels && (int)blockIdx.x >= bl.tile_begin[level + 1]) ++level;
+    while (level + 1 < bl.nlevels && (int)blockIdx.x >= bl.block_begin[level + 1]) ++level;
     const LevelGeom &L = g.lv[level];
-    const int t = blockIdx.x - bl.tile_begin[level];
-    const int tx0 = (t % bl.tiles_x[level]) * kBlurTW, ty0 = (t / bl.tiles_x[level]) * kBlurTH;
     const int frame = blockIdx.y;
     const uint8_t *src;
     int spitch;
@@ -88,35 +138,18 @@ __global__ void __launch_bounds__(256) blur_kernel(FrameGeom g, BlurLevels bl, c
     else { src = pyr + L.plane_offset + (int64_t)frame * L.plane_stride; spitch = L.pitch; }
     uint8_t *dst = blur + L.plane_offset + (int64_t)frame * L.plane_stride;
 
-    const int tid = threadIdx.x;
-    for (int i = tid; i < (kBlurTH + 6) * (kBlurTW + 6); i += 256) {
-        const int ly = i / (kBlurTW + 6), lx = i - ly * (kBlurTW + 6);
-        const int sy = reflect101(min(ty0 + ly - 3, L.h + 2), L.h);  // rows/cols past the image are never used
-        const int sx = reflect101(min(tx0 + lx - 3, L.w + 2), L.w);
-        tile[ly][lx] = __ldg(src + (int64_t)sy * spitch + sx);
-    }
-    __syncthreads();
-    for (int i = tid; i < (kBlurTH + 6) * kBlurTW; i += 256) {
-        const int ly = i / kBlurTW, lx = i - ly * kBlurTW;
-        const uint8_t *p = &tile[ly][lx];
-        const int h = 18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3];
-        hbuf[ly][lx] = (uint16_t)h;
-    }
-    __syncthreads();
-    // each thread: 4 adjacent columns x 2 rows -> two 32-bit stores
-    for (int i = tid; i < kBlurTH * (kBlurTW / 4); i += 256) {
-        const int ly = i / (kBlurTW / 4), lx = (i - ly * (kBlurTW / 4)) * 4;
-        const int y = ty0 + ly, x = tx0 + lx;
-        if (y >= L.h || x >= L.w) continue;
-        uint32_t packed = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t v = 18u * (hbuf[ly][lx + k] + hbuf[ly + 6][lx + k]) +
-                               34u * (hbuf[ly + 1][lx + k] + hbuf[ly + 5][lx + k]) +
-                               48u * (hbuf[ly + 2][lx + k] + hbuf[ly + 4][lx + k]) + 56u * hbuf[ly + 3][lx + k];
-            packed |= ((v + 32768u) >> 16) << (8 * k);
-        }
-        *reinterpret_cast<uint32_t *>(dst + (int64_t)y * L.pitch + x) = packed;
+    const int item = (blockIdx.x - bl.block_begin[level]) * kBlurThreads + threadIdx.x;
+    const int n_int = bl.n_int_cg[level], n_edge = bl.n_edge_cg[level];
+    const int items_int = bl.n_strips[level] * n_int;
+    if (item < items_int) {
+        const int strip = item / n_int, cg = 1 + (item - strip * n_int);
+        blur_strip<false>(src, spitch, dst, L.pitch, L.w, L.h, 4 * cg, strip * kBlurRows);
+    } else {
+        const int e = item - items_int;
+        if (e >= bl.n_strips[level] * n_edge) return;
+        const int strip = e / n_edge, k = e - strip * n_edge;
+        const int cg = k == 0 ? 0 : n_int + k;
+        blur_strip<true>(src, spitch, dst, L.pitch, L.w, L.h, 4 * cg, strip * kBlurRows);
     }
 }
 
@@ -126,12 +159,20 @@ void launch_blur(const FrameGeom &g, const uint8_t *lvl0_base, int lvl0_pitch, i
     bl.nlevels = g.nlevels;
     int total = 0;
     for (int l = 0; l < g.nlevels; ++l) {
-        bl.tile_begin[l] = total;
-        bl.tiles_x[l] = (g.lv[l].w + kBlurTW - 1) / kBlurTW;
-        total += bl.tiles_x[l] * ((g.lv[l].h + kBlurTH - 1) / kBlurTH);
+        const int w = g.lv[l].w, h = g.lv[l].h;
+        const int ncg = (w + 3) / 4;
+        // interior groups: x >= 4 and x + 7 <= w - 1 (the three aligned words lie inside the row)
+        int n_int = 0;
+        for (int cg = 1; cg < ncg; ++cg)
+            if (4 * cg + 7 <= w - 1) n_int = cg;
+        bl.block_begin[l] = total;
+        bl.n_int_cg[l] = n_int;
+        bl.n_edge_cg[l] = ncg - n_int;
+        bl.n_strips[l] = (h + kBlurRows - 1) / kBlurRows;
+        total += (bl.n_strips[l] * ncg + kBlurThreads - 1) / kBlurThreads;
     }
-    bl.tile_begin[g.nlevels] = total;
-    blur_kernel<<<dim3(total, nframes), 256, 0, s>>>(g, bl, lvl0_base, lvl0_pitch, lvl0_stride, pyr, blur);
+    bl.block_begin[g.nlevels] = total;
+    blur_kernel<<<dim3(total, nframes), kBlurThreads, 0, s>>>(g, bl, lvl0_base, lvl0_pitch, lvl0_stride, pyr, blur);
     count_launch();
 }
 
