@@ -9,8 +9,9 @@
 //
 // slot_kernel:     one CTA per frame; prefix counts over the level-major keypoint order give every
 //                  keypoint its output row, n and monoIndex.
-// describe_kernel: one warp per keypoint; lanes 0..30 are the 31 columns of the radius-15 disc for the
-//                  moments, then lane i produces descriptor byte i (8 point pairs).
+// describe_kernel: 64 keypoints per CTA; a warp per keypoint for the moments (lanes 0..30 = the 31 columns of
+//                  the radius-15 disc) and for the descriptor (lane i = byte i, 8 point pairs), one thread per
+//                  keypoint for the scalar angle / cos / sin in between.
 #include "vsg_internal.cuh"
 
 namespace vsg {
@@ -97,6 +98,11 @@ __global__ void __launch_bounds__(256) slot_kernel(FrameGeom g, const LevelKp *_
     }
 }
 
+// 64 keypoints per CTA (8 warps x 8 keypoints).  The warp-uniform scalar work — fastAtan2 and the
+// double-precision cos/sin — is done once per keypoint by 64 threads in between the two warp-parallel
+// phases instead of redundantly by all 32 lanes of a warp.
+constexpr int kDescKp = 64;
+
 __global__ void __launch_bounds__(256) describe_kernel(FrameGeom g, const uint8_t *__restrict__ lvl0_base,
                                                        int lvl0_pitch, int64_t lvl0_stride,
                                                        const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur,
@@ -104,85 +110,117 @@ __global__ void __launch_bounds__(256) describe_kernel(FrameGeom g, const uint8_
                                                        const int *__restrict__ level_kp_count,
                                                        const int *__restrict__ slot, vsg_keypoint *__restrict__ kps_out,
                                                        uint8_t *__restrict__ desc_out, int out_cap) {
+    __shared__ int s_x[kDescKp], s_y[kDescKp], s_level[kDescKp], s_row[kDescKp], s_score[kDescKp];
+    __shared__ int s_m01[kDescKp], s_m10[kDescKp];
+    __shared__ float s_angle[kDescKp], s_cos[kDescKp], s_sin[kDescKp];
     const int frame = blockIdx.y;
-    const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);  // keypoint index in level-major order
-    int level = 0, off = 0;
-    for (; level < g.nlevels; ++level) {
-        const int c = level_kp_count[frame * g.nlevels + level];
-        if (i < off + c) break;
-        off += c;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int first = blockIdx.x * kDescKp;             // keypoint index in level-major order
+
+    if (tid < kDescKp) {
+        const int i = first + tid;
+        int level = 0, off = 0;
+        for (; level < g.nlevels; ++level) {
+            const int c = level_kp_count[frame * g.nlevels + level];
+            if (i < off + c) break;
+            off += c;
+        }
+        int row = -1;
+        if (level < g.nlevels) {
+            const LevelKp kp = level_kps[(int64_t)frame * g.kp_total + g.lv[level].kp_offset + (i - off)];
+            row = slot[(int64_t)frame * g.kp_total + i];
+            s_x[tid] = kp.x; s_y[tid] = kp.y; s_score[tid] = kp.score;
+        }
+        s_level[tid] = level;
+        s_row[tid] = row;
     }
-    if (level == g.nlevels) return;
-    const LevelGeom &L = g.lv[level];
-    const LevelKp kp = level_kps[(int64_t)frame * g.kp_total + L.kp_offset + (i - off)];
-    const int out_row = slot[(int64_t)frame * g.kp_total + i];
-    if (out_row < 0) return;
+    __syncthreads();
+    if (s_row[0] < 0 && s_level[0] >= g.nlevels) return;   // whole CTA is past the last keypoint
 
-    const uint8_t *img;
-    int ipitch;
-    if (level == 0) { img = lvl0_base + (int64_t)frame * lvl0_stride; ipitch = lvl0_pitch; }
-    else { img = pyr + L.plane_offset + (int64_t)frame * L.plane_stride; ipitch = L.pitch; }
-
-    // ---- IC_Angle (:73-100): lanes = columns u = lane-15 of the disc ----
-    int m10 = 0, m01 = 0;
-    if (lane < 31) {
-        const int u = lane - kHalfPatch;
-        const int au = abs(u);
-        const uint8_t *c = img + (int64_t)kp.y * ipitch + kp.x + u;
-#pragma unroll 1
-        for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
-            if (au <= c_umax[abs(v)]) {
-                const int val = __ldg(c + v * ipitch);
-                m10 += u * val;
-                m01 += v * val;
+    // ---- IC_Angle moments (:73-100): lanes = columns u = lane-15 of the disc ----
+    for (int k = warp; k < kDescKp; k += 8) {
+        if (s_row[k] < 0) continue;
+        const int level = s_level[k];
+        const LevelGeom &L = g.lv[level];
+        const uint8_t *img;
+        int ipitch;
+        if (level == 0) { img = lvl0_base + (int64_t)frame * lvl0_stride; ipitch = lvl0_pitch; }
+        else { img = pyr + L.plane_offset + (int64_t)frame * L.plane_stride; ipitch = L.pitch; }
+        int m10 = 0, m01 = 0;
+        if (lane < 31) {
+            const int u = lane - kHalfPatch;
+            const int au = abs(u);
+            const uint8_t *c = img + (int64_t)s_y[k] * ipitch + s_x[k] + u;
+#pragma unroll
+            for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
+                if (au <= c_umax[v < 0 ? -v : v]) {
+                    const int val = __ldg(c + v * ipitch);
+                    m10 += u * val;
+                    m01 += v * val;
+                }
             }
         }
-    }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        m10 += __shfl_xor_sync(0xffffffffu, m10, d);
-        m01 += __shfl_xor_sync(0xffffffffu, m01, d);
+        for (int d = 16; d > 0; d >>= 1) {
+            m10 += __shfl_xor_sync(0xffffffffu, m10, d);
+            m01 += __shfl_xor_sync(0xffffffffu, m01, d);
+        }
+        if (lane == 0) { s_m10[k] = m10; s_m01[k] = m01; }
     }
-    const float angle = fast_atan2_deg((float)m01, (float)m10);
+    __syncthreads();
 
-    // ---- computeOrbDescriptor (:103-149) on the blurred level ----
-    const float factor_pi = (float)(3.14159265358979323846 / 180.0);  // (float)(CV_PI/180.f), :102
-    const float arad = __fmul_rn(angle, factor_pi);
-    // glibc's cosf/sinf are (all but) correctly rounded; double-precision cos/sin rounded to float
-    // reproduces that where CUDA's cosf (2 ulp) would not.  SURVEY A8 allows <=0.1 % differing bits.
-    const float a = (float)cos((double)arad), b = (float)sin((double)arad);
-    const uint8_t *bc = blur + L.plane_offset + (int64_t)frame * L.plane_stride + (int64_t)kp.y * L.pitch + kp.x;
-    const char4 *pat = reinterpret_cast<const char4 *>(d_pattern) + lane * 8;
-    int val = 0;
-#pragma unroll
-    for (int bit = 0; bit < 8; ++bit) {
-        const char4 p = pat[bit];
-        const float x0 = (float)p.x, y0 = (float)p.y, x1 = (float)p.z, y1 = (float)p.w;
-        const int ry0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
-        const int rx0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-        const int ry1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
-        const int rx1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-        const int t0 = __ldg(bc + ry0 * L.pitch + rx0);
-        const int t1 = __ldg(bc + ry1 * L.pitch + rx1);
-        val |= (t0 < t1) << bit;
-    }
-    desc_out[((int64_t)frame * out_cap + out_row) * 32 + lane] = (uint8_t)val;
-
-    if (lane == 0) {
+    // ---- one thread per keypoint: angle, steering coefficients, output record ----
+    if (tid < kDescKp && s_row[tid] >= 0) {
+        const float angle = fast_atan2_deg((float)s_m01[tid], (float)s_m10[tid]);
+        const float factor_pi = (float)(3.14159265358979323846 / 180.0);  // (float)(CV_PI/180.f), :102
+        const float arad = __fmul_rn(angle, factor_pi);
+        // glibc's cosf/sinf are (all but) correctly rounded; double-precision cos/sin rounded to float
+        // reproduces that where CUDA's cosf (2 ulp) would not.  SURVEY A8 allows <=0.1 % differing bits.
+        s_cos[tid] = (float)cos((double)arad);
+        s_sin[tid] = (float)sin((double)arad);
+        s_angle[tid] = angle;
+        const int level = s_level[tid];
+        const LevelGeom &L = g.lv[level];
         vsg_keypoint o;
-        o.x = (float)kp.x;
-        o.y = (float)kp.y;
+        o.x = (float)s_x[tid];
+        o.y = (float)s_y[tid];
         if (level != 0) {  // keypoint->pt *= scale (:1147-1150)
             o.x = __fmul_rn(o.x, L.scale);
             o.y = __fmul_rn(o.y, L.scale);
         }
         o.size = L.kp_size;
         o.angle = angle;
-        o.response = (float)kp.score;
+        o.response = (float)s_score[tid];
         o.octave = level;
         o.class_id = -1;
-        kps_out[(int64_t)frame * out_cap + out_row] = o;
+        kps_out[(int64_t)frame * out_cap + s_row[tid]] = o;
+    }
+    __syncthreads();
+
+    // ---- computeOrbDescriptor (:103-149) on the blurred level: lane i -> descriptor byte i ----
+    const char4 *pat = reinterpret_cast<const char4 *>(d_pattern) + lane * 8;
+    char4 p[8];
+#pragma unroll
+    for (int bit = 0; bit < 8; ++bit) p[bit] = pat[bit];
+    for (int k = warp; k < kDescKp; k += 8) {
+        const int out_row = s_row[k];
+        if (out_row < 0) continue;
+        const LevelGeom &L = g.lv[s_level[k]];
+        const float a = s_cos[k], b = s_sin[k];
+        const uint8_t *bc = blur + L.plane_offset + (int64_t)frame * L.plane_stride + (int64_t)s_y[k] * L.pitch + s_x[k];
+        int val = 0;
+#pragma unroll
+        for (int bit = 0; bit < 8; ++bit) {
+            const float x0 = (float)p[bit].x, y0 = (float)p[bit].y, x1 = (float)p[bit].z, y1 = (float)p[bit].w;
+            const int ry0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+            const int rx0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+            const int ry1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+            const int rx1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+            const int t0 = __ldg(bc + ry0 * L.pitch + rx0);
+            const int t1 = __ldg(bc + ry1 * L.pitch + rx1);
+            val |= (t0 < t1) << bit;
+        }
+        desc_out[((int64_t)frame * out_cap + out_row) * 32 + lane] = (uint8_t)val;
     }
 }
 
@@ -192,7 +230,7 @@ void launch_describe(const FrameGeom &g, const uint8_t *lvl0_base, int lvl0_pitc
                      int *mono_out, int *slot_scratch, int nframes, cudaStream_t s) {
     slot_kernel<<<nframes, 256, 0, s>>>(g, level_kps, level_kp_count, lap_x0, lap_x1, out_cap, n_out, mono_out,
                                        slot_scratch);
-    describe_kernel<<<dim3((g.kp_total + 7) / 8, nframes), 256, 0, s>>>(g, lvl0_base, lvl0_pitch, lvl0_stride, pyr,
+    describe_kernel<<<dim3((g.kp_total + kDescKp - 1) / kDescKp, nframes), 256, 0, s>>>(g, lvl0_base, lvl0_pitch, lvl0_stride, pyr,
                                                                        blur, level_kps, level_kp_count, slot_scratch,
                                                                        kps_out, desc_out, out_cap);
     count_launch(2);

@@ -31,6 +31,7 @@ __device__ __forceinline__ uint32_t min3(uint32_t a, uint32_t b, uint32_t c) { r
 __device__ __forceinline__ uint32_t max3(uint32_t a, uint32_t b, uint32_t c) { return max2(max2(a, b), c); }
 
 constexpr int kFastThreads = 128;
+constexpr int kLoadIters = 4;      // covers cells up to 4*128 quads (e.g. 8 quads x 64 rows) without a loop
 constexpr int kT2Pitch = 48;      // words per pair-row: 3 (alignment) + lane offset S (<= 36, multiple of 4) + 6 halo columns, rounded to 4
 constexpr int kS2Pitch = 40;      // words per strength row: S + 2
 
@@ -79,7 +80,7 @@ struct PairIter {
     }
 };
 
-__global__ void __launch_bounds__(kFastThreads, 8) fast_kernel(FrameGeom g, const Cell *__restrict__ cells,
+__global__ void __launch_bounds__(kFastThreads, 8) fast_kernel(FrameGeom g,
                                                              const uint8_t *__restrict__ lvl0_base, int lvl0_pitch,
                                                              int64_t lvl0_stride, const uint8_t *__restrict__ pyr,
                                                              Cand *__restrict__ cand, int *__restrict__ cand_count,
@@ -90,7 +91,21 @@ __global__ void __launch_bounds__(kFastThreads, 8) fast_kernel(FrameGeom g, cons
     uint32_t *list = s2 + (tile_rows - 4) * kS2Pitch;
     __shared__ int s_count, s_base;
 
-    const Cell cell = cells[blockIdx.x];
+    // cell geometry from the level tables (kernel parameters): no dependent global load at kernel start.
+    // Valid cells of a level form a rows_eff x cols_eff prefix of the reference's grid (:811-828).
+    Cell cell;
+    {
+        int level = 0;
+        while (level + 1 < g.nlevels && (int)blockIdx.x >= g.lv[level + 1].cell_begin) ++level;
+        const LevelGeom &G = g.lv[level];
+        const int local = blockIdx.x - G.cell_begin;
+        const int ci = local / G.cols_eff, cj = local - ci * G.cols_eff;
+        cell.level = (short)level;
+        cell.x0 = (short)(kBorderMin + cj * G.w_cell);
+        cell.y0 = (short)(kBorderMin + ci * G.h_cell);
+        cell.cw = (short)(min(cell.x0 + G.w_cell + 6, G.w - kBorderMin) - cell.x0);
+        cell.ch = (short)(min(cell.y0 + G.h_cell + 6, G.h - kBorderMin) - cell.y0);
+    }
     const int frame = blockIdx.y;
     const LevelGeom &L = g.lv[cell.level];
     const uint8_t *src;
@@ -108,21 +123,46 @@ __global__ void __launch_bounds__(kFastThreads, 8) fast_kernel(FrameGeom g, cons
     {
         const int nq = (xoff + S + 6 + 3) >> 2;    // quads of pair columns per row
         const uint8_t *base = src + (int64_t)cell.y0 * spitch + ax0;
-        int r = tid / nq, q = tid - r * nq;
-        const int dr = kFastThreads / nq, dq = kFastThreads - dr * nq;
-        while (r < cell.ch) {
+        const int total = cell.ch * nq;
+        const float inv = 1.0f / (float)nq;
+        // all global loads of the CTA are issued before the first one is consumed
+        uint32_t a[kLoadIters], b[kLoadIters];
+        int dst[kLoadIters];
+#pragma unroll
+        for (int it = 0; it < kLoadIters; ++it) {
+            const int i = tid + it * kFastThreads;
+            dst[it] = -1;
+            if (i < total) {
+                const int r = (int)(((float)i + 0.5f) * inv), q = i - r * nq;
+                const uint8_t *row = base + (int64_t)r * spitch + 4 * q;
+                a[it] = __ldg(reinterpret_cast<const uint32_t *>(row));
+                // the second half may reach past the window, never past the image row (x0 + cw <= W - 16)
+                b[it] = __ldg(reinterpret_cast<const uint32_t *>(row + S));
+                dst[it] = r * kT2Pitch + 4 * q;
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < kLoadIters; ++it) {
+            if (dst[it] >= 0) {
+                uint4 o;
+                o.x = __byte_perm(a[it], b[it], 0x7470) & 0x00FF00FFu;   // [a0, -, b0, -]
+                o.y = __byte_perm(a[it], b[it], 0x7571) & 0x00FF00FFu;
+                o.z = __byte_perm(a[it], b[it], 0x7672) & 0x00FF00FFu;
+                o.w = __byte_perm(a[it], b[it], 0x7773) & 0x00FF00FFu;
+                *reinterpret_cast<uint4 *>(t2 + dst[it]) = o;
+            }
+        }
+        for (int i = tid + kLoadIters * kFastThreads; i < total; i += kFastThreads) {   // oversized cells only
+            const int r = (int)(((float)i + 0.5f) * inv), q = i - r * nq;
             const uint8_t *row = base + (int64_t)r * spitch + 4 * q;
-            const uint32_t a = __ldg(reinterpret_cast<const uint32_t *>(row));
-            // the second half may reach past the window (never past the pitch: w + 16 <= pitch by construction)
-            const uint32_t b = __ldg(reinterpret_cast<const uint32_t *>(row + S));
+            const uint32_t aa = __ldg(reinterpret_cast<const uint32_t *>(row));
+            const uint32_t bb = __ldg(reinterpret_cast<const uint32_t *>(row + S));
             uint4 o;
-            o.x = __byte_perm(a, b, 0x7470) & 0x00FF00FFu;   // [a0, -, b0, -]
-            o.y = __byte_perm(a, b, 0x7571) & 0x00FF00FFu;
-            o.z = __byte_perm(a, b, 0x7672) & 0x00FF00FFu;
-            o.w = __byte_perm(a, b, 0x7773) & 0x00FF00FFu;
+            o.x = __byte_perm(aa, bb, 0x7470) & 0x00FF00FFu;
+            o.y = __byte_perm(aa, bb, 0x7571) & 0x00FF00FFu;
+            o.z = __byte_perm(aa, bb, 0x7672) & 0x00FF00FFu;
+            o.w = __byte_perm(aa, bb, 0x7773) & 0x00FF00FFu;
             *reinterpret_cast<uint4 *>(t2 + r * kT2Pitch + 4 * q) = o;
-            q += dq; r += dr;
-            if (q >= nq) { q -= nq; ++r; }
         }
     }
     for (int i = tid; i < kS2Pitch; i += kFastThreads) {     // top and bottom apron rows of the strength plane
@@ -155,34 +195,27 @@ __global__ void __launch_bounds__(kFastThreads, 8) fast_kernel(FrameGeom g, cons
         const int tt = max(t, 1);       // a corner scoring 0 (K == 1, only possible at t == 0) never survives the NMS
         PairIter it(tid, S);
         for (int base = 0; base < npairs; base += kFastThreads, it.next()) {   // warp-uniform trip count
-            bool f0 = false, f1 = false;
-            int k0 = 0, k1 = 0;
-            if (it.iy < ih) {
-                const uint32_t *c = s2 + (it.iy + 1) * kS2Pitch + it.j + 1;
-                const uint32_t K = c[0];
-                k0 = K & 0xFFFF; k1 = K >> 16;
-                if (k0 > tt || k1 > tt) {
-                    // strict maximum over the 8 neighbours: neighbours that are not corners at t are below K anyway
-                    const uint32_t nb = max3(max3(c[-kS2Pitch - 1], c[-kS2Pitch], c[-kS2Pitch + 1]),
-                                             max3(c[-1], c[1], c[kS2Pitch - 1]), max2(c[kS2Pitch], c[kS2Pitch + 1]));
-                    f0 = k0 > tt && k0 > (int)(nb & 0xFFFF);
-                    f1 = k1 > tt && k1 > (int)(nb >> 16);
-                }
-            }
+            // out-of-range lanes read the (zero) apron row 0: no branch around the loads
+            // lanes past the last pair read a harmless in-range location and are masked: no branch around the loads
+            const bool in = it.iy < ih;
+            const uint32_t *c = s2 + (in ? (it.iy + 1) * kS2Pitch + it.j + 1 : kS2Pitch + 1);
+            const uint32_t K = c[0];
+            // strict maximum over the 8 neighbours: neighbours that are not corners at t are below K anyway
+            const uint32_t nb = max3(max3(c[-kS2Pitch - 1], c[-kS2Pitch], c[-kS2Pitch + 1]),
+                                     max3(c[-1], c[1], c[kS2Pitch - 1]), max2(c[kS2Pitch], c[kS2Pitch + 1]));
+            const int k0 = K & 0xFFFF, k1 = K >> 16;
+            const bool f0 = in && k0 > tt && k0 > (int)(nb & 0xFFFF);
+            const bool f1 = in && k1 > tt && k1 > (int)(nb >> 16);
             const unsigned m0 = __ballot_sync(0xffffffffu, f0), m1 = __ballot_sync(0xffffffffu, f1);
-            if ((m0 | m1) == 0) continue;
+            if ((m0 | m1) == 0) continue;                                       // warp-uniform
+            const int n0 = __popc(m0);
             int wbase = 0;
-            if (lane == 0) wbase = atomicAdd(&s_count, __popc(m0) + __popc(m1));
+            if (lane == 0) wbase = atomicAdd(&s_count, n0 + __popc(m1));
             wbase = __shfl_sync(0xffffffffu, wbase, 0);
             const unsigned lt = (1u << lane) - 1;
-            if (f0) {
-                const int slot = wbase + __popc(m0 & lt);
-                if (slot < list_cap) list[slot] = (uint32_t)it.j | ((uint32_t)it.iy << 8) | ((uint32_t)(k0 - 1) << 16);
-            }
-            if (f1) {
-                const int slot = wbase + __popc(m0) + __popc(m1 & lt);
-                if (slot < list_cap) list[slot] = (uint32_t)(it.j + S) | ((uint32_t)it.iy << 8) | ((uint32_t)(k1 - 1) << 16);
-            }
+            const uint32_t pos = (uint32_t)it.j | ((uint32_t)it.iy << 8);
+            if (f0) list[wbase + __popc(m0 & lt)] = pos | ((uint32_t)(k0 - 1) << 16);
+            if (f1) list[wbase + n0 + __popc(m1 & lt)] = (pos + S) | ((uint32_t)(k1 - 1) << 16);
         }
         __syncthreads();
         if (s_count > 0) break;   // uniform: the retry happens only when the cell is empty (:842)
@@ -209,6 +242,7 @@ __global__ void __launch_bounds__(kFastThreads, 8) fast_kernel(FrameGeom g, cons
 void launch_fast(const FrameGeom &g, const Cell *cells, const uint8_t *lvl0_base, int lvl0_pitch, int64_t lvl0_stride,
                  const uint8_t *pyr, Cand *cand, int *cand_count, int ini_th, int min_th, int max_cw, int max_ch,
                  int nframes, cudaStream_t s) {
+    (void)cells;   // the kernel derives the cell geometry from the level tables
     if (g.ncells == 0) return;
     const int max_S = ((((max_cw - 6) + 1) >> 1) + 3) & ~3;
     if (3 + max_S + 6 + 3 > kT2Pitch || max_S + 2 > kS2Pitch) { set_error("FAST cell wider than the shared-memory tile"); return; }
@@ -220,7 +254,7 @@ void launch_fast(const FrameGeom &g, const Cell *cells, const uint8_t *lvl0_base
         cudaFuncSetAttribute(fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    fast_kernel<<<dim3(g.ncells, nframes), kFastThreads, smem, s>>>(g, cells, lvl0_base, lvl0_pitch, lvl0_stride, pyr, cand,
+    fast_kernel<<<dim3(g.ncells, nframes), kFastThreads, smem, s>>>(g, lvl0_base, lvl0_pitch, lvl0_stride, pyr, cand,
                                                                   cand_count, ini_th, min_th, tile_rows, list_cap);
     count_launch();
 }

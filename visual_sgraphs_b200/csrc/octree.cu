@@ -10,13 +10,13 @@
 //     by comparing its coordinates with the box midpoint only.  So keys never move in memory; each
 //     key carries the list position of its node (`node_of`) and every pass re-labels it.
 //   * One pass of the reference's main loop divides EVERY multi-key node.  All threads histogram
-//     their keys into the four children of their node (shared-memory atomics), then thread 0 rebuilds
-//     the list exactly as push_front/erase would leave it: children of the i-th divided node, in
-//     n1..n4 order, end up in front of everything pushed before them; single-key nodes keep their
-//     relative order behind.
+//     their keys into the four children of their node (shared-memory atomics); the list is then
+//     rebuilt in parallel exactly as push_front/erase would leave it — block-wide prefix sums over the
+//     list give every child its position: children of the i-th divided node, in n1..n4 order, end up
+//     in front of everything pushed before them; single-key nodes keep their relative order behind.
 //   * The "careful" phase (:696-759) sorts the expandable nodes with the libstdc++ introsort
-//     emulation (introsort.cuh — tie order is part of the result), expands from the back until the
-//     quota is reached, and rebuilds the list the same way.
+//     emulation (introsort.cuh — tie order is part of the result; one thread, a few hundred items),
+//     finds how many are divided before the quota is reached, and rebuilds the list the same way.
 //   * Final pick per node = highest response, FIRST in the reference's candidate order on ties
 //     (:766-782).  Candidate order is cell-row-major, then row-major inside the cell (:811-874), so
 //     the tie break is an atomicMax on (response, ~order_key(x, y)).
@@ -49,6 +49,31 @@ __device__ __forceinline__ ONode child_of(const ONode &n, int q, int count) {
     return c;
 }
 
+// Exclusive prefix sums of three per-thread values over the 256 threads of the CTA (thread order), in place;
+// the block totals are returned in ta, tb, tc.  Contains two barriers.
+__device__ __forceinline__ void block_scan3(int &a, int &b, int &c, int (*s_warp)[8], int &ta, int &tb, int &tc) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int ia = a, ib = b, ic = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int xa = __shfl_up_sync(0xffffffffu, ia, d), xb = __shfl_up_sync(0xffffffffu, ib, d),
+                  xc = __shfl_up_sync(0xffffffffu, ic, d);
+        if (lane >= d) { ia += xa; ib += xb; ic += xc; }
+    }
+    if (lane == 31) { s_warp[0][warp] = ia; s_warp[1][warp] = ib; s_warp[2][warp] = ic; }
+    __syncthreads();
+    int wa = 0, wb = 0, wc = 0;
+    ta = tb = tc = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const int va = s_warp[0][w], vb = s_warp[1][w], vc = s_warp[2][w];
+        if (w < warp) { wa += va; wb += vb; wc += vc; }
+        ta += va; tb += vb; tc += vc;
+    }
+    __syncthreads();
+    a = wa + ia - a; b = wb + ib - b; c = wc + ic - c;
+}
+
 __global__ void __launch_bounds__(256) octree_kernel(FrameGeom g, const Cand *__restrict__ cand,
                                                      const int *__restrict__ cand_count,
                                                      unsigned short *__restrict__ node_of,
@@ -64,7 +89,8 @@ __global__ void __launch_bounds__(256) octree_kernel(FrameGeom g, const Cand *__
     short *expanded = reinterpret_cast<short *>(stay_pos + cap);           // [cap] 1 if divided this round
     unsigned short *exp_list = reinterpret_cast<unsigned short *>(expanded + cap);  // [cap] expandable nodes, push order
     SortItem *sort_buf = reinterpret_cast<SortItem *>(exp_list + cap + (cap & 1));  // [cap]
-    __shared__ int s_size, s_nexp, s_state, s_flip;
+    __shared__ int s_size, s_nexp, s_state, s_E, s_T, s_X;
+    __shared__ int s_scan[3][8];
 
     const int level = blockIdx.x, frame = blockIdx.y;
     const LevelGeom &L = g.lv[level];
@@ -107,7 +133,6 @@ __global__ void __launch_bounds__(256) octree_kernel(FrameGeom g, const Cand *__
         }
         s_size = m;
         s_state = 0;  // 0 = main passes, 1 = careful phase, 2 = finished
-        s_flip = 0;
     }
     __syncthreads();
     for (int k = tid; k < n; k += 256) nof[k] = stay_pos[nof[k]];
@@ -127,82 +152,108 @@ __global__ void __launch_bounds__(256) octree_kernel(FrameGeom g, const Cand *__
             if (node.count > 1) atomicAdd(&cc[nd * 4 + quadrant(node, keys[k].x - kBorderMin, keys[k].y - kBorderMin)], 1);
         }
         __syncthreads();
-        if (tid == 0) {
-            int new_size, nexp = 0;
-            if (state == 0) {
-                // main pass (:626-684): every multi-key node is divided, walking the list front to back
-                int T = 0;
-                for (int i = 0; i < size; ++i)
-                    if (cur[i].count > 1)
-                        for (int q = 0; q < 4; ++q) T += cc[i * 4 + q] > 0;
-                int push = 0, stay = 0;
-                for (int i = 0; i < size; ++i) {
-                    if (cur[i].count == 1) {
-                        const int pos = T + stay++;
-                        nxt[pos] = cur[i];
-                        stay_pos[i] = (unsigned short)pos;
-                        expanded[i] = 0;
-                    } else {
-                        expanded[i] = 1;
-                        for (int q = 0; q < 4; ++q) {
-                            const int c = cc[i * 4 + q];
-                            if (c == 0) continue;
-                            const int pos = T - 1 - push++;
-                            nxt[pos] = child_of(cur[i], q, c);
-                            child_pos[i * 4 + q] = (unsigned short)pos;
-                            if (c > 1) exp_list[nexp++] = (unsigned short)pos;
-                        }
+
+        // every thread owns a contiguous chunk of the list so that prefix sums follow list order
+        const int chunk = (size + 255) / 256;
+        const int lo = min(tid * chunk, size), hi = min(lo + chunk, size);
+        if (state == 0) {
+            // main pass (:626-684): every multi-key node is divided, walking the list front to back; children
+            // are pushed to the FRONT in n1..n4 order, single-key nodes keep their relative order behind them
+            int kids = 0, stays = 0, exps = 0;
+            for (int i = lo; i < hi; ++i) {
+                if (cur[i].count == 1) { ++stays; continue; }
+                for (int q = 0; q < 4; ++q) { kids += cc[i * 4 + q] > 0; exps += cc[i * 4 + q] > 1; }
+            }
+            int T, S, X;
+            block_scan3(kids, stays, exps, s_scan, T, S, X);     // in: my sums, out: exclusive prefixes; totals in T,S,X
+            int push = kids, stay = stays, nexp = exps;
+            for (int i = lo; i < hi; ++i) {
+                if (cur[i].count == 1) {
+                    const int pos = T + stay++;
+                    nxt[pos] = cur[i];
+                    stay_pos[i] = (unsigned short)pos;
+                    expanded[i] = 0;
+                } else {
+                    expanded[i] = 1;
+                    for (int q = 0; q < 4; ++q) {
+                        const int c = cc[i * 4 + q];
+                        if (c == 0) continue;
+                        const int pos = T - 1 - push++;
+                        nxt[pos] = child_of(cur[i], q, c);
+                        child_pos[i * 4 + q] = (unsigned short)pos;
+                        if (c > 1) exp_list[nexp++] = (unsigned short)pos;
                     }
                 }
-                new_size = T + stay;
+            }
+            if (tid == 0) {
+                const int new_size = T + S;
                 if (new_size >= N || new_size == size) s_state = 2;           // :690-694
-                else if (new_size + nexp * 3 > N) s_state = 1;                // :696
-            } else {
-                // careful round (:698-759): sort expandable nodes, divide from the back until size >= N
-                const int m = s_nexp;
-                for (int j = 0; j < m; ++j) {
-                    const int pos = exp_list[j];
-                    sort_buf[j].count = cur[pos].count;
-                    sort_buf[j].ulx = cur[pos].x0;
-                    sort_buf[j].ref = pos;
-                }
+                else if (new_size + X * 3 > N) s_state = 1;                   // :696
+                s_size = new_size;
+                s_nexp = X;
+            }
+        } else {
+            // careful round (:698-759): sort the expandable nodes, divide from the back until size >= N
+            const int m = s_nexp;
+            for (int j = tid; j < m; j += 256) {
+                const int pos = exp_list[j];
+                sort_buf[j].count = cur[pos].count;
+                sort_buf[j].ulx = cur[pos].x0;
+                sort_buf[j].ref = pos;
+            }
+            for (int i = tid; i < size; i += 256) expanded[i] = 0;
+            __syncthreads();
+            if (tid == 0) {
                 libstdcxx_sort(sort_buf, m);
-                for (int i = 0; i < size; ++i) expanded[i] = 0;
-                int running = size, E = 0, T = 0;
+                // processing order r = 0.. : sort_buf[m-1-r]; push_off[r] / exp_off[r] = children / expandable children
+                // pushed before r.  They overwrite the (count, ulx) fields that are no longer needed.
+                int running = size, E = 0, T = 0, X = 0;
                 for (int j = m - 1; j >= 0; --j) {
                     const int pos = sort_buf[j].ref;
-                    int c = 0;
-                    for (int q = 0; q < 4; ++q) c += cc[pos * 4 + q] > 0;
+                    int c = 0, e = 0;
+                    for (int q = 0; q < 4; ++q) { c += cc[pos * 4 + q] > 0; e += cc[pos * 4 + q] > 1; }
+                    sort_buf[j].count = T;
+                    sort_buf[j].ulx = X;
                     expanded[pos] = 1;
                     running += c - 1;
-                    T += c;
+                    T += c; X += e;
                     ++E;
                     if (running >= N) break;
                 }
-                int push = 0;
-                for (int r = 0; r < E; ++r) {
-                    const int pos = sort_buf[m - 1 - r].ref;
-                    for (int q = 0; q < 4; ++q) {
-                        const int c = cc[pos * 4 + q];
-                        if (c == 0) continue;
-                        const int np = T - 1 - push++;
-                        nxt[np] = child_of(cur[pos], q, c);
-                        child_pos[pos * 4 + q] = (unsigned short)np;
-                        if (c > 1) exp_list[nexp++] = (unsigned short)np;   // safe: entry j < nexp already consumed
-                    }
-                }
-                int stay = 0;
-                for (int i = 0; i < size; ++i) {
-                    if (expanded[i]) continue;
-                    const int np = T + stay++;
-                    nxt[np] = cur[i];
-                    stay_pos[i] = (unsigned short)np;
-                }
-                new_size = T + stay;
-                if (new_size >= N || new_size == size) s_state = 2;           // :753-757
+                s_E = E; s_T = T; s_X = X;
             }
-            s_size = new_size;
-            s_nexp = nexp;
+            __syncthreads();
+            const int E = s_E, T = s_T;
+            for (int r = tid; r < E; r += 256) {
+                const SortItem it = sort_buf[m - 1 - r];
+                const int pos = it.ref;
+                int push = it.count, nexp = it.ulx;
+                for (int q = 0; q < 4; ++q) {
+                    const int c = cc[pos * 4 + q];
+                    if (c == 0) continue;
+                    const int np = T - 1 - push++;
+                    nxt[np] = child_of(cur[pos], q, c);
+                    child_pos[pos * 4 + q] = (unsigned short)np;
+                    if (c > 1) exp_list[nexp++] = (unsigned short)np;      // old entries were copied to sort_buf
+                }
+            }
+            int stays = 0;
+            for (int i = lo; i < hi; ++i) stays += expanded[i] ? 0 : 1;
+            int d0 = 0, d1 = 0, S, D0, D1;
+            block_scan3(stays, d0, d1, s_scan, S, D0, D1);
+            int stay = stays;
+            for (int i = lo; i < hi; ++i) {
+                if (expanded[i]) continue;
+                const int np = T + stay++;
+                nxt[np] = cur[i];
+                stay_pos[i] = (unsigned short)np;
+            }
+            if (tid == 0) {
+                const int new_size = T + S;
+                if (new_size >= N || new_size == size) s_state = 2;           // :753-757
+                s_size = new_size;
+                s_nexp = s_X;
+            }
         }
         __syncthreads();
         for (int k = tid; k < n; k += 256) {

@@ -13,41 +13,103 @@
 namespace vsg {
 
 // ------------------------------------------------------------------------------------------------
-// resize: one thread = 4 horizontally adjacent output pixels of one row (one 32-bit store).
-// grid (ceil(dw/128), ceil(dh/8), nframes), block (32, 8).
+// resize: one thread owns 4 output columns x kResizeRows output rows.  Its four
+// (sx0, sx1, a0, a1) column entries are loop invariant: the source bytes of a row come from three
+// aligned 32-bit loads and one byte-permute per column, the horizontal interpolation is one IDP2A
+// (a0*s0 + a1*s1).  The rows of a strip are independent, so all their loads are in flight together
+// (the source row shared by two consecutive output rows is simply re-read from L1).
+// Vertical: ((b*(h>>4))>>16) is a 32x32 high multiply by b<<16.
+// grid (ceil(ncg/128), ceil(dh/kResizeRows), nframes), block 128.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) resize_kernel(const uint8_t *__restrict__ src, int src_pitch, int64_t src_stride,
-                                                     uint8_t *__restrict__ dst, int dst_pitch, int64_t dst_stride,
-                                                     int dw, int dh, const short4 *__restrict__ xtab,
-                                                     const short4 *__restrict__ ytab) {
-    const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
-    const int y = blockIdx.y * 8 + threadIdx.y;
-    if (x4 >= dw || y >= dh) return;
+constexpr int kResizeRows = 4, kResizeThreads = 128;
+
+__global__ void __launch_bounds__(kResizeThreads) resize_kernel(const uint8_t *__restrict__ src, int src_pitch,
+                                                                int64_t src_stride, uint8_t *__restrict__ dst,
+                                                                int dst_pitch, int64_t dst_stride, int dw, int dh,
+                                                                int sw, const short4 *__restrict__ xtab,
+                                                                const short4 *__restrict__ ytab) {
+    const int x4 = (blockIdx.x * kResizeThreads + threadIdx.x) * 4;
+    if (x4 >= dw) return;
+    const int y0 = blockIdx.y * kResizeRows, y1 = min(y0 + kResizeRows, dh);
     const uint8_t *s = src + (int64_t)blockIdx.z * src_stride;
-    uint8_t *d = dst + (int64_t)blockIdx.z * dst_stride;
-    const short4 yt = __ldg(&ytab[y]);
-    const uint8_t *r0 = s + (int64_t)yt.x * src_pitch;
-    const uint8_t *r1 = s + (int64_t)yt.y * src_pitch;
-    const int b0 = yt.z, b1 = yt.w;
-    uint32_t packed = 0;
+    uint8_t *d = dst + (int64_t)blockIdx.z * dst_stride + x4;
+
+    // column setup: aligned base word, byte selectors relative to it, packed coefficients
+    short4 xt[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) xt[k] = __ldg(&xtab[x4 + k]);   // table is padded to a multiple of 4 entries
+    const int base = xt[0].x & ~3;                               // all 8 source columns lie in [base, base + 12)
+    uint32_t sel[4], coef[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const short4 xt = __ldg(&xtab[x4 + k]);  // table is padded to a multiple of 4 entries
-        const int h0 = (int)__ldg(r0 + xt.x) * xt.z + (int)__ldg(r0 + xt.y) * xt.w;
-        const int h1 = (int)__ldg(r1 + xt.x) * xt.z + (int)__ldg(r1 + xt.y) * xt.w;
-        const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
-        packed |= (uint32_t)min(max(v, 0), 255) << (8 * k);
+        const int o0 = xt[k].x - base, o1 = xt[k].y - base;      // 0..11
+        sel[k] = (uint32_t)o0 | ((uint32_t)o1 << 4);             // resolved against (w0,w1) or (w1,w2) below
+        coef[k] = (uint32_t)(uint16_t)xt[k].z | ((uint32_t)(uint16_t)xt[k].w << 16);
     }
-    *reinterpret_cast<uint32_t *>(d + (int64_t)y * dst_pitch + x4) = packed;  // pitch % 16 == 0: pad bytes are scratch
+    // bytes 0..7 come from (w0, w1), 4..11 from (w1, w2): pick per column which pair holds both taps
+    bool hi[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int o0 = sel[k] & 15, o1 = sel[k] >> 4;
+        hi[k] = o1 >= 8;
+        const int f = hi[k] ? 4 : 0;
+        sel[k] = (uint32_t)(o0 - f) | ((uint32_t)(o1 - f) << 4);
+    }
+    const bool need_w2 = hi[0] || hi[1] || hi[2] || hi[3];       // false only when all taps sit in the first 8 bytes
+
+    // words that would cross the end of the source row (only in the last column group) are assembled bytewise:
+    // level 0 may be a caller-owned buffer with no padding behind its last row
+    const bool tail = base + 12 > sw;
+    auto hrow = [&](int sy, uint32_t g[4]) {                    // g = (S[sx0]*a0 + S[sx1]*a1) >> 4 for the 4 columns
+        const uint8_t *row = s + (int64_t)sy * src_pitch;
+        uint32_t w0, w1, w2 = 0u;
+        if (!tail) {
+            const uint32_t *p = reinterpret_cast<const uint32_t *>(row + base);
+            w0 = __ldg(p); w1 = __ldg(p + 1);
+            if (need_w2) w2 = __ldg(p + 2);
+        } else {
+            uint32_t b[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) b[k] = __ldg(row + min(base + k, sw - 1));
+            w0 = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+            w1 = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+            w2 = b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t bytes = hi[k] ? __byte_perm(w1, w2, sel[k]) : __byte_perm(w0, w1, sel[k]);
+            g[k] = __dp2a_lo(coef[k], bytes, 0u) >> 4;
+        }
+    };
+
+    // kResizeRows independent output rows: all table and source loads are issued before any arithmetic
+    short4 yt[kResizeRows];
+#pragma unroll
+    for (int r = 0; r < kResizeRows; ++r) yt[r] = __ldg(&ytab[min(y0 + r, dh - 1)]);
+    uint32_t ga[kResizeRows][4], gb[kResizeRows][4];
+#pragma unroll
+    for (int r = 0; r < kResizeRows; ++r) {
+        hrow(yt[r].x, ga[r]);
+        hrow(yt[r].y, gb[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < kResizeRows; ++r) {
+        if (y0 + r >= y1) break;
+        const uint32_t b0 = (uint32_t)yt[r].z << 16, b1 = (uint32_t)yt[r].w << 16;
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (__umulhi(b0, ga[r][k]) + __umulhi(b1, gb[r][k]) + 2u) >> 2;
+        *reinterpret_cast<uint32_t *>(d + (int64_t)(y0 + r) * dst_pitch) = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+    }
 }
 
 void launch_resize_level(const FrameGeom &g, int level, const uint8_t *src_base, int src_pitch, int64_t src_stride,
                          uint8_t *pyr, int nframes, cudaStream_t s) {
     const LevelGeom &L = g.lv[level];
-    dim3 block(32, 8);
-    dim3 grid((L.w + 127) / 128, (L.h + 7) / 8, nframes);
-    resize_kernel<<<grid, block, 0, s>>>(src_base, src_pitch, src_stride, pyr + L.plane_offset, L.pitch, L.plane_stride,
-                                         L.w, L.h, L.xtab, L.ytab);
+    const int ncg = (L.w + 3) / 4;
+    dim3 grid((ncg + kResizeThreads - 1) / kResizeThreads, (L.h + kResizeRows - 1) / kResizeRows, nframes);
+    resize_kernel<<<grid, kResizeThreads, 0, s>>>(src_base, src_pitch, src_stride, pyr + L.plane_offset, L.pitch,
+                                                 L.plane_stride, L.w, L.h, g.lv[level - 1].w, L.xtab, L.ytab);
     count_launch();
 }
 

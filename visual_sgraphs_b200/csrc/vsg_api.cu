@@ -231,6 +231,16 @@ vsg_status configure_shape(vsg_extractor *ex, int w, int h) {
             }
         }
         L.cell_count = (int)ex->cells_h.size() - L.cell_begin;
+        L.cols_eff = L.rows_eff = 0;
+        for (int k = L.cell_begin; k < (int)ex->cells_h.size(); ++k) {
+            const Cell &c = ex->cells_h[k];
+            L.cols_eff = std::max(L.cols_eff, (c.x0 - min_b) / L.w_cell + 1);
+            L.rows_eff = std::max(L.rows_eff, (c.y0 - min_b) / L.h_cell + 1);
+        }
+        if (L.cols_eff * L.rows_eff != L.cell_count) {
+            set_error("internal: level %d cell table is not a prefix rectangle", l);
+            return VSG_ERR_INVALID;
+        }
         L.quota = ex->quota[l];
         L.n_ini = (int)std::round(static_cast<float>(max_bx - min_b) / (max_by - min_b));   // :566
         if (L.n_ini < 1) {
@@ -354,7 +364,8 @@ int64_t vsg_launch_count(void) { return g_launches.load(); }
 
 vsg_status vsg_extractor_create(const vsg_orb_params *params, int device, int max_batch, vsg_extractor **out) {
     if (!params || !out || max_batch < 1 || params->nlevels < 1 || params->nlevels > kMaxLevels ||
-        params->scale_factor <= 1.0f || params->nfeatures < 0) {
+        params->scale_factor <= 1.0f || params->scale_factor >= 2.0f || params->nfeatures < 0) {
+        // scale factors >= 2 take cv::resize's INTER_AREA shortcut in the reference and are not restated here
         set_error("vsg_extractor_create: invalid argument");
         return VSG_ERR_INVALID;
     }

@@ -27,6 +27,7 @@ struct LevelGeom {
     // cell grid of ComputeKeyPointsOctTree (:795-809)
     int n_cols, n_rows, w_cell, h_cell;
     int cell_begin, cell_count;  // slice of the flat cell table
+    int cols_eff, rows_eff;      // the cells that survive the skip rules (:816,825) form this prefix rectangle
     // oct-tree
     int quota;             // mnFeaturesPerLevel[level]
     int n_ini;             // round(width/height) root nodes (:566)
