@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(256) octree_kernel(FrameGeom g, const Cand *__
     const int tid = threadIdx.x;
     const int n = min(cand_count[frame * g.nlevels + level], L.cand_cap);
     const Cand *keys = cand + L.cand_offset + (int64_t)frame * g.cand_total;
+    const uint32_t *key_xy = reinterpret_cast<const uint32_t *>(keys);   // word 2k = x | y << 16 of candidate k
     unsigned short *nof = node_of + L.cand_offset + (int64_t)frame * g.cand_total;
     LevelKp *out = level_kps + (int64_t)frame * g.kp_total + L.kp_offset;
     int *out_count = level_kp_count + frame * g.nlevels + level;
@@ -146,10 +147,22 @@ __global__ void __launch_bounds__(256) octree_kernel(FrameGeom g, const Cand *__
         if (state == 2) break;
         for (int i = tid; i < size * 4; i += 256) cc[i] = 0;
         __syncthreads();
-        for (int k = tid; k < n; k += 256) {
-            const int nd = nof[k];
-            const ONode &node = cur[nd];
-            if (node.count > 1) atomicAdd(&cc[nd * 4 + quadrant(node, keys[k].x - kBorderMin, keys[k].y - kBorderMin)], 1);
+        for (int k0 = tid; k0 < n; k0 += 4 * 256) {       // 4 keys per thread in flight (global loads are L2 latency)
+            int nd[4];
+            uint32_t xy[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = k0 + u * 256;
+                nd[u] = k < n ? nof[k] : -1;
+                xy[u] = k < n ? key_xy[2 * k] : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (nd[u] < 0) continue;
+                const ONode &node = cur[nd[u]];
+                if (node.count > 1)
+                    atomicAdd(&cc[nd[u] * 4 + quadrant(node, (int)(xy[u] & 0xFFFF) - kBorderMin, (int)(xy[u] >> 16) - kBorderMin)], 1);
+            }
         }
         __syncthreads();
 
@@ -256,13 +269,25 @@ __global__ void __launch_bounds__(256) octree_kernel(FrameGeom g, const Cand *__
             }
         }
         __syncthreads();
-        for (int k = tid; k < n; k += 256) {
-            const int nd = nof[k];
-            if (expanded[nd]) {
-                const ONode &node = cur[nd];
-                nof[k] = child_pos[nd * 4 + quadrant(node, keys[k].x - kBorderMin, keys[k].y - kBorderMin)];
-            } else {
-                nof[k] = stay_pos[nd];
+        for (int k0 = tid; k0 < n; k0 += 4 * 256) {
+            int nd[4];
+            uint32_t xy[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = k0 + u * 256;
+                nd[u] = k < n ? nof[k] : -1;
+                xy[u] = k < n ? key_xy[2 * k] : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (nd[u] < 0) continue;
+                const int k = k0 + u * 256;
+                if (expanded[nd[u]]) {
+                    const ONode &node = cur[nd[u]];
+                    nof[k] = child_pos[nd[u] * 4 + quadrant(node, (int)(xy[u] & 0xFFFF) - kBorderMin, (int)(xy[u] >> 16) - kBorderMin)];
+                } else {
+                    nof[k] = stay_pos[nd[u]];
+                }
             }
         }
         { ONode *t = cur; cur = nxt; nxt = t; }
@@ -274,7 +299,7 @@ __global__ void __launch_bounds__(256) octree_kernel(FrameGeom g, const Cand *__
     for (int i = tid; i < size; i += 256) best[i] = 0ull;
     __syncthreads();
     for (int k = tid; k < n; k += 256) {
-        const Cand c = keys[k];
+        const Cand c = keys[k];                                // independent iterations: the loads pipeline
         const int rx = c.x - kEdge, ry = c.y - kEdge;          // offset inside the FAST-able area
         const int cx = rx / L.w_cell, cy = ry / L.h_cell;
         const unsigned order = ((unsigned)(cy * L.n_cols + cx) << 14) | ((unsigned)(ry - cy * L.h_cell) << 7) |

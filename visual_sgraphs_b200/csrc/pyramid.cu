@@ -26,7 +26,8 @@ constexpr int kResizeRows = 4, kResizeThreads = 128;
 __global__ void __launch_bounds__(kResizeThreads) resize_kernel(const uint8_t *__restrict__ src, int src_pitch,
                                                                 int64_t src_stride, uint8_t *__restrict__ dst,
                                                                 int dst_pitch, int64_t dst_stride, int dw, int dh,
-                                                                int sw, const short4 *__restrict__ xtab,
+                                                                int sw, const uint8_t *__restrict__ src_end,
+                                                                const short4 *__restrict__ xtab,
                                                                 const short4 *__restrict__ ytab) {
     const int x4 = (blockIdx.x * kResizeThreads + threadIdx.x) * 4;
     if (x4 >= dw) return;
@@ -57,13 +58,13 @@ __global__ void __launch_bounds__(kResizeThreads) resize_kernel(const uint8_t *_
     }
     const bool need_w2 = hi[0] || hi[1] || hi[2] || hi[3];       // false only when all taps sit in the first 8 bytes
 
-    // words that would cross the end of the source row (only in the last column group) are assembled bytewise:
-    // level 0 may be a caller-owned buffer with no padding behind its last row
-    const bool tail = base + 12 > sw;
+    // Words past the end of a source row only ever hold unused bytes (taps are clamped to sw-1), and reading
+    // them is harmless except at the very end of the source buffer (level 0 may be a caller-owned buffer with
+    // nothing behind its last row): only there the 12 bytes are assembled one by one.
     auto hrow = [&](int sy, uint32_t g[4]) {                    // g = (S[sx0]*a0 + S[sx1]*a1) >> 4 for the 4 columns
         const uint8_t *row = s + (int64_t)sy * src_pitch;
         uint32_t w0, w1, w2 = 0u;
-        if (!tail) {
+        if (row + base + 12 <= src_end) {
             const uint32_t *p = reinterpret_cast<const uint32_t *>(row + base);
             w0 = __ldg(p); w1 = __ldg(p + 1);
             if (need_w2) w2 = __ldg(p + 2);
@@ -105,11 +106,14 @@ __global__ void __launch_bounds__(kResizeThreads) resize_kernel(const uint8_t *_
 
 void launch_resize_level(const FrameGeom &g, int level, const uint8_t *src_base, int src_pitch, int64_t src_stride,
                          uint8_t *pyr, int nframes, cudaStream_t s) {
+    const LevelGeom &P = g.lv[level - 1];
+    // one past the last byte of the source batch (our own planes have slack behind them, but stay exact)
+    const uint8_t *src_end = src_base + (int64_t)(nframes - 1) * src_stride + (int64_t)(P.h - 1) * src_pitch + P.w;
     const LevelGeom &L = g.lv[level];
     const int ncg = (L.w + 3) / 4;
     dim3 grid((ncg + kResizeThreads - 1) / kResizeThreads, (L.h + kResizeRows - 1) / kResizeRows, nframes);
     resize_kernel<<<grid, kResizeThreads, 0, s>>>(src_base, src_pitch, src_stride, pyr + L.plane_offset, L.pitch,
-                                                 L.plane_stride, L.w, L.h, g.lv[level - 1].w, L.xtab, L.ytab);
+                                                 L.plane_stride, L.w, L.h, P.w, src_end, L.xtab, L.ytab);
     count_launch();
 }
 

@@ -446,15 +446,36 @@ vsg_status vsg_extract_batch(vsg_extractor *ex, const uint8_t *images, int nfram
     if (st != VSG_OK) return st;
     CK(cudaMemcpyAsync(ex->n_h, ex->n_d, nframes * sizeof(int), cudaMemcpyDeviceToHost, ex->stream));
     CK(cudaMemcpyAsync(ex->mono_h, ex->mono_d, nframes * sizeof(int), cudaMemcpyDeviceToHost, ex->stream));
-    CK(cudaMemcpyAsync(ex->kps_h, ex->kps_d, (size_t)nframes * g.out_cap * sizeof(vsg_keypoint), cudaMemcpyDeviceToHost,
-                       ex->stream));
-    CK(cudaMemcpyAsync(ex->desc_h, ex->desc_d, (size_t)nframes * g.out_cap * 32, cudaMemcpyDeviceToHost, ex->stream));
+    // Results go straight into the caller's arrays when those are page-locked (one strided D2H each, no
+    // host-side copy); otherwise through the handle's pinned staging buffers.
+    auto pinned = [](const void *p) {
+        if (!p) return false;
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeHost;
+    };
+    const bool direct = capacity >= g.out_cap && (!keypoints_out || pinned(keypoints_out)) &&
+                        (!descriptors_out || pinned(descriptors_out));
+    if (direct) {
+        if (keypoints_out)
+            CK(cudaMemcpy2DAsync(keypoints_out, (size_t)capacity * sizeof(vsg_keypoint), ex->kps_d,
+                                 (size_t)g.out_cap * sizeof(vsg_keypoint), (size_t)g.out_cap * sizeof(vsg_keypoint),
+                                 nframes, cudaMemcpyDeviceToHost, ex->stream));
+        if (descriptors_out)
+            CK(cudaMemcpy2DAsync(descriptors_out, (size_t)capacity * 32, ex->desc_d, (size_t)g.out_cap * 32,
+                                 (size_t)g.out_cap * 32, nframes, cudaMemcpyDeviceToHost, ex->stream));
+    } else {
+        CK(cudaMemcpyAsync(ex->kps_h, ex->kps_d, (size_t)nframes * g.out_cap * sizeof(vsg_keypoint),
+                           cudaMemcpyDeviceToHost, ex->stream));
+        CK(cudaMemcpyAsync(ex->desc_h, ex->desc_d, (size_t)nframes * g.out_cap * 32, cudaMemcpyDeviceToHost, ex->stream));
+    }
     CK(cudaStreamSynchronize(ex->stream));
     vsg_status ret = VSG_OK;
     for (int f = 0; f < nframes; ++f) {
         const int n = ex->n_h[f];
         if (n_out) n_out[f] = n;
         if (mono_index_out) mono_index_out[f] = ex->mono_h[f];
+        if (direct) continue;
         if (n > capacity) {
             set_error("vsg_extract_batch: frame %d has %d keypoints, capacity %d", f, n, capacity);
             ret = VSG_ERR_CAPACITY;
