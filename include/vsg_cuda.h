@@ -261,6 +261,17 @@ vsg_status vsg_search_by_bow(vsg_matcher *m, const vsg_frame_view *KF, const uin
                              const int32_t *f_idx, float nnratio, int check_ori, int32_t *matches_f_out,
                              int *nmatches_out);
 
+/* Frame::ComputeStereoMatches (Frame.cc:957-1127): for every left keypoint the best right keypoint in its row
+ * band (octave +-1, uR in [uL - mbf/mb, uL], Hamming < TH_HIGH), then — if the distance is below
+ * (TH_HIGH+TH_LOW)/2 — an 11x11 L1 patch correlation over 11 horizontal offsets on the un-blurred pyramid
+ * level of both extractors, parabola sub-pixel fit, disparity gate and the final 1.5*1.4*median rejection.
+ * `left` / `right` are the two extractor handles whose last call produced keys_l / keys_r (the device pyramids
+ * of that call are read in place; frame_l / frame_r select the frame of a batched call).  u_right_out and
+ * depth_out are mvuRight / mvDepth (n_l entries, -1 = no match). */
+vsg_status vsg_stereo_match(vsg_matcher *m, vsg_extractor *left, vsg_extractor *right, int frame_l, int frame_r,
+                            const vsg_keypoint *keys_l, const uint8_t *desc_l, int n_l, const vsg_keypoint *keys_r,
+                            const uint8_t *desc_r, int n_r, float mb, float mbf, float *u_right_out, float *depth_out);
+
 #ifdef __cplusplus
 }
 #endif

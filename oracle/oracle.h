@@ -150,6 +150,14 @@ int orc_search_by_bow(const orc_frame_view *KF, const uint8_t *kf_mp_valid, cons
                       const int32_t *f_nodes, const int32_t *f_ptr, const int32_t *f_idx, float nnratio, int check_ori,
                       int32_t *matches_f);
 
+/* Frame::ComputeStereoMatches (Frame.cc:957-1127): row-band Hamming search, 11x11 SAD refinement on the
+ * un-blurred pyramids of both extractors (their last orc_extract call), parabola fit, median-based outlier
+ * rejection.  keys/desc are the extractors' raw outputs (mvKeys / mvKeysRight).  Fills u_right[n_l], depth[n_l]
+ * (-1 = no match). */
+void orc_stereo_matches(const orc_extractor *left, const orc_extractor *right, const orc_keypoint *keys_l,
+                        const uint8_t *desc_l, int n_l, const orc_keypoint *keys_r, const uint8_t *desc_r, int n_r,
+                        float mb, float mbf, float *u_right, float *depth);
+
 /* ---- throughput harness for bench.py's cpu_baseline: extracts `nframes` frames (tightly packed
  * w*h each) with `threads` worker threads, one extractor instance per thread; returns seconds. ---- */
 double orc_bench_extract(const uint8_t *frames, int nframes, int width, int height, int nfeatures, float scale_factor,

@@ -77,6 +77,7 @@ def lib():
         L.orc_search_by_projection_last.argtypes = [vp, vp, C.c_int, vp, vp, C.c_float, C.c_int, C.c_int, vp]
         L.orc_search_for_initialization.argtypes = [vp, vp, vp, C.c_int, C.c_float, C.c_int, vp]
         L.orc_search_by_bow.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, C.c_float, C.c_int, vp]
+        L.orc_stereo_matches.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_float, C.c_float, vp, vp]
         L.orc_bench_extract.restype = C.c_double
         L.orc_bench_extract.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.POINTER(C.c_int64)]
@@ -286,3 +287,16 @@ def search_by_bow(kf_view, kf_mp_valid, f_view, kf_fv, f_fv, nnratio, check_ori)
     nm = lib().orc_search_by_bow(C.addressof(kf_view), _ptr(valid), C.addressof(f_view), len(kn), _ptr(kn), _ptr(kp),
                                  _ptr(ki), len(fn), _ptr(fn), _ptr(fp), _ptr(fi), nnratio, int(check_ori), _ptr(out))
     return nm, out
+
+
+def stereo_matches(ex_left, ex_right, keys_l, desc_l, keys_r, desc_r, mb, mbf):
+    """Frame::ComputeStereoMatches on two OracleExtractor objects (their last call's pyramids)."""
+    keys_l = np.ascontiguousarray(keys_l, KEYPOINT_DTYPE)
+    keys_r = np.ascontiguousarray(keys_r, KEYPOINT_DTYPE)
+    desc_l = np.ascontiguousarray(desc_l, np.uint8)
+    desc_r = np.ascontiguousarray(desc_r, np.uint8)
+    u_right = np.zeros(len(keys_l), np.float32)
+    depth = np.zeros(len(keys_l), np.float32)
+    lib().orc_stereo_matches(ex_left._h, ex_right._h, _ptr(keys_l), _ptr(desc_l), len(keys_l), _ptr(keys_r), _ptr(desc_r),
+                             len(keys_r), mb, mbf, _ptr(u_right), _ptr(depth))
+    return u_right, depth

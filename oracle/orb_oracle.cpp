@@ -20,6 +20,8 @@
 #include <chrono>
 #include <cmath>
 #include <cfloat>
+#include <climits>
+#include <cstdlib>
 #include <cstring>
 #include <list>
 #include <thread>
@@ -700,6 +702,95 @@ int orc_distribute_octree(const float *xyr, int n, int min_x, int max_x, int min
     int m = 0;
     for (const Cand &s : sel) { if (m < cap) selected_idx[m] = s.src; ++m; }
     return m;
+}
+
+// Frame::ComputeStereoMatches — orb_slam3/src/Frame.cc:957-1127
+void orc_stereo_matches(const orc_extractor *left, const orc_extractor *right, const orc_keypoint *keys_l,
+                        const uint8_t *desc_l, int n_l, const orc_keypoint *keys_r, const uint8_t *desc_r, int n_r,
+                        float mb, float mbf, float *u_right, float *depth) {
+    const int TH_HIGH = 100, TH_LOW = 50;
+    for (int i = 0; i < n_l; ++i) { u_right[i] = -1.0f; depth[i] = -1.0f; }
+    const int th_orb_dist = (TH_HIGH + TH_LOW) / 2;
+    const int n_rows = left->pyramid[0].h;
+    const std::vector<float> &scale = left->t.scale, &inv_scale = left->t.inv_scale;
+    std::vector<std::vector<int>> row_indices(n_rows);
+    for (int ir = 0; ir < n_r; ++ir) {                                       // :973-984
+        const float kp_y = keys_r[ir].y;
+        const float r = 2.0f * scale[keys_r[ir].octave];
+        const int maxr = (int)std::ceil(kp_y + r), minr = (int)std::floor(kp_y - r);
+        for (int yi = minr; yi <= maxr; ++yi)
+            if (yi >= 0 && yi < n_rows) row_indices[yi].push_back(ir);       // the reference has no bounds check
+    }
+    const float min_z = mb, min_d = 0, max_d = mbf / min_z;
+    std::vector<std::pair<int, int>> dist_idx;
+    for (int il = 0; il < n_l; ++il) {
+        const orc_keypoint &kpl = keys_l[il];
+        const int level_l = kpl.octave;
+        const float vl = kpl.y, ul = kpl.x;
+        const size_t row = (size_t)vl;
+        if (row >= (size_t)n_rows) continue;
+        const std::vector<int> &cands = row_indices[row];
+        if (cands.empty()) continue;
+        const float min_u = ul - max_d, max_u = ul - min_d;
+        if (max_u < 0) continue;
+        int best_dist = TH_HIGH;
+        size_t best_idx_r = 0;
+        for (int ir : cands) {                                               // :1017-1040
+            const orc_keypoint &kpr = keys_r[ir];
+            if (kpr.octave < level_l - 1 || kpr.octave > level_l + 1) continue;
+            const float ur = kpr.x;
+            if (ur >= min_u && ur <= max_u) {
+                const int dist = orc_descriptor_distance(desc_l + (size_t)il * 32, desc_r + (size_t)ir * 32);
+                if (dist < best_dist) { best_dist = dist; best_idx_r = ir; }
+            }
+        }
+        if (best_dist < th_orb_dist) {                                       // :1043-1111
+            const float ur0 = keys_r[best_idx_r].x;
+            const float scale_factor = inv_scale[kpl.octave];
+            const float scaled_ul = std::round(kpl.x * scale_factor);
+            const float scaled_vl = std::round(kpl.y * scale_factor);
+            const float scaled_ur0 = std::round(ur0 * scale_factor);
+            const int w = 5, L = 5;
+            const Image &PL = left->pyramid[kpl.octave], &PR = right->pyramid[kpl.octave];
+            int best_sad = INT_MAX, best_inc_r = 0;
+            float dists[2 * 5 + 1];
+            const float iniu = scaled_ur0 + L - w, endu = scaled_ur0 + L + w + 1;
+            if (iniu < 0 || endu >= PR.w) continue;
+            const int y0 = (int)(scaled_vl - w), xl0 = (int)(scaled_ul - w);
+            for (int inc = -L; inc <= +L; ++inc) {
+                const int xr0 = (int)(scaled_ur0 + inc - w);
+                long sad = 0;                                                // cv::norm(IL, IR, NORM_L1)
+                for (int dy = 0; dy < 2 * w + 1; ++dy) {
+                    const uint8_t *a = PL.row(y0 + dy) + xl0, *b = PR.row(y0 + dy) + xr0;
+                    for (int dx = 0; dx < 2 * w + 1; ++dx) sad += std::abs((int)a[dx] - (int)b[dx]);
+                }
+                const float dist = (float)(double)sad;
+                if (dist < best_sad) { best_sad = (int)dist; best_inc_r = inc; }
+                dists[L + inc] = dist;
+            }
+            if (best_inc_r == -L || best_inc_r == L) continue;
+            const float d1 = dists[L + best_inc_r - 1], d2 = dists[L + best_inc_r], d3 = dists[L + best_inc_r + 1];
+            const float delta_r = (d1 - d3) / (2.0f * (d1 + d3 - 2.0f * d2));
+            if (delta_r < -1 || delta_r > 1) continue;
+            float best_ur = scale[kpl.octave] * ((float)scaled_ur0 + (float)best_inc_r + delta_r);
+            float disparity = (ul - best_ur);
+            if (disparity >= min_d && disparity < max_d) {
+                if (disparity <= 0) { disparity = 0.01; best_ur = ul - 0.01; }
+                depth[il] = mbf / disparity;
+                u_right[il] = best_ur;
+                dist_idx.push_back(std::pair<int, int>(best_sad, il));
+            }
+        }
+    }
+    if (dist_idx.empty()) return;                                            // the reference reads [0] here (SURVEY C#12)
+    std::sort(dist_idx.begin(), dist_idx.end());
+    const float median = dist_idx[dist_idx.size() / 2].first;
+    const float th_dist = 1.5f * 1.4f * median;
+    for (int i = (int)dist_idx.size() - 1; i >= 0; --i) {
+        if (dist_idx[i].first < th_dist) break;
+        u_right[dist_idx[i].second] = -1;
+        depth[dist_idx[i].second] = -1;
+    }
 }
 
 double orc_bench_extract(const uint8_t *frames, int nframes, int w, int h, int nfeatures, float scale_factor,

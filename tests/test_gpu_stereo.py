@@ -1,0 +1,43 @@
+"""GPU parity test for Frame::ComputeStereoMatches (BASELINE config 2: 752x480 stereo, 1200 features per side):
+extraction of both images on the device + vsg_stereo_match on the device pyramids against the oracle."""
+import numpy as np
+import pytest
+
+from visual_sgraphs_b200.synth import synth_stereo_pair
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("seed,size,nfeat", [(42, (752, 480), 1200), (7, (376, 240), 500)])
+def test_stereo_matches_parity(oracle, seed, size, nfeat):
+    from visual_sgraphs_b200.extractor import ORBextractor
+    from visual_sgraphs_b200.matcher import ORBmatcher
+    left, right = synth_stereo_pair(seed, *size)
+    exl, exr = ORBextractor(nfeat), ORBextractor(nfeat)          # two instances, like Frame.cc:129-132
+    _, kl, dl = exl(left)
+    _, kr, dr = exr(right)
+    oxl, oxr = oracle.OracleExtractor(nfeat), oracle.OracleExtractor(nfeat)
+    _, okl, odl = oxl(left)
+    _, okr, odr = oxr(right)
+    assert kl.tobytes() == okl.tobytes() and np.array_equal(dl, odl) and kr.tobytes() == okr.tobytes()
+    mb, mbf = 0.11, 47.9
+    u, d = ORBmatcher().ComputeStereoMatches(exl, exr, kl, dl, kr, dr, mb, mbf)
+    wu, wd = oracle.stereo_matches(oxl, oxr, okl, odl, okr, odr, mb, mbf)
+    assert np.array_equal(u, wu)
+    assert np.array_equal(d, wd)
+    assert (u >= 0).sum() > 0.2 * len(kl)
+
+
+def test_stereo_inside_a_batch(oracle):
+    """Left and right images extracted as frames 0 and 1 of one batched call (pair i on one GPU)."""
+    from visual_sgraphs_b200.extractor import ORBextractor
+    from visual_sgraphs_b200.matcher import ORBmatcher
+    left, right = synth_stereo_pair(3, 752, 480)
+    ex = ORBextractor(1200, max_batch=2)
+    (_, kl, dl), (_, kr, dr) = ex.extract_batch(np.stack([left, right]))
+    u, d = ORBmatcher().ComputeStereoMatches(ex, ex, kl, dl, kr, dr, 0.11, 47.9, frame_l=0, frame_r=1)
+    oxl, oxr = oracle.OracleExtractor(1200), oracle.OracleExtractor(1200)
+    oxl(left)
+    oxr(right)
+    wu, wd = oracle.stereo_matches(oxl, oxr, kl, dl, kr, dr, 0.11, 47.9)
+    assert np.array_equal(u, wu) and np.array_equal(d, wd)

@@ -31,7 +31,7 @@ __device__ __forceinline__ uint32_t min3(uint32_t a, uint32_t b, uint32_t c) { r
 __device__ __forceinline__ uint32_t max3(uint32_t a, uint32_t b, uint32_t c) { return max2(max2(a, b), c); }
 
 constexpr int kFastThreads = 128;
-constexpr int kLoadIters = 4;      // covers cells up to 4*128 quads (e.g. 8 quads x 64 rows) without a loop
+constexpr int kLoadIters = 3;      // 3 x 16 rows of 8 quads cover the usual 44-row cell without a loop
 constexpr int kT2Pitch = 48;      // words per pair-row: 3 (alignment) + lane offset S (<= 36, multiple of 4) + 6 halo columns, rounded to 4
 constexpr int kS2Pitch = 40;      // words per strength row: S + 2
 
@@ -121,39 +121,37 @@ __global__ void __launch_bounds__(kFastThreads, 8) fast_kernel(FrameGeom g,
     const int ax0 = cell.x0 & ~3;                  // 4-byte aligned origin of the pair columns
     const int xoff = cell.x0 - ax0;                // window column w sits at pair column xoff + w
     {
-        const int nq = (xoff + S + 6 + 3) >> 2;    // quads of pair columns per row
+        const int nq = (xoff + S + 6 + 3) >> 2;    // quads of pair columns per row (7..9 typical, <= 12)
         const uint8_t *base = src + (int64_t)cell.y0 * spitch + ax0;
-        const int total = cell.ch * nq;
-        const float inv = 1.0f / (float)nq;
+        // thread -> (row, quad) by shift/mask: 8 (or 16) quad slots per row, threads beyond nq idle
+        const int lq = nq <= 8 ? 3 : 4;
+        const int q = tid & ((1 << lq) - 1), r0 = tid >> lq, rstep = kFastThreads >> lq;
+        const bool qok = q < nq;
         // all global loads of the CTA are issued before the first one is consumed
         uint32_t a[kLoadIters], b[kLoadIters];
-        int dst[kLoadIters];
 #pragma unroll
         for (int it = 0; it < kLoadIters; ++it) {
-            const int i = tid + it * kFastThreads;
-            dst[it] = -1;
-            if (i < total) {
-                const int r = (int)(((float)i + 0.5f) * inv), q = i - r * nq;
+            const int r = r0 + it * rstep;
+            if (qok && r < cell.ch) {
                 const uint8_t *row = base + (int64_t)r * spitch + 4 * q;
                 a[it] = __ldg(reinterpret_cast<const uint32_t *>(row));
                 // the second half may reach past the window, never past the image row (x0 + cw <= W - 16)
                 b[it] = __ldg(reinterpret_cast<const uint32_t *>(row + S));
-                dst[it] = r * kT2Pitch + 4 * q;
             }
         }
 #pragma unroll
         for (int it = 0; it < kLoadIters; ++it) {
-            if (dst[it] >= 0) {
+            const int r = r0 + it * rstep;
+            if (qok && r < cell.ch) {
                 uint4 o;
                 o.x = __byte_perm(a[it], b[it], 0x7470) & 0x00FF00FFu;   // [a0, -, b0, -]
                 o.y = __byte_perm(a[it], b[it], 0x7571) & 0x00FF00FFu;
                 o.z = __byte_perm(a[it], b[it], 0x7672) & 0x00FF00FFu;
                 o.w = __byte_perm(a[it], b[it], 0x7773) & 0x00FF00FFu;
-                *reinterpret_cast<uint4 *>(t2 + dst[it]) = o;
+                *reinterpret_cast<uint4 *>(t2 + r * kT2Pitch + 4 * q) = o;
             }
         }
-        for (int i = tid + kLoadIters * kFastThreads; i < total; i += kFastThreads) {   // oversized cells only
-            const int r = (int)(((float)i + 0.5f) * inv), q = i - r * nq;
+        for (int r = r0 + kLoadIters * rstep; qok && r < cell.ch; r += rstep) {   // taller cells
             const uint8_t *row = base + (int64_t)r * spitch + 4 * q;
             const uint32_t aa = __ldg(reinterpret_cast<const uint32_t *>(row));
             const uint32_t bb = __ldg(reinterpret_cast<const uint32_t *>(row + S));
@@ -210,7 +208,11 @@ __global__ void __launch_bounds__(kFastThreads, 8) fast_kernel(FrameGeom g,
             if ((m0 | m1) == 0) continue;                                       // warp-uniform
             const int n0 = __popc(m0);
             int wbase = 0;
-            if (lane == 0) wbase = atomicAdd(&s_count, n0 + __popc(m1));
+            // one shared-memory atomic per warp, issued by lane 0 under a predicate (no divergent region)
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %2, 0;\n\t@p atom.shared.add.u32 %0, [%1], %3;\n\t}"
+                         : "+r"(wbase)
+                         : "r"((uint32_t)__cvta_generic_to_shared(&s_count)), "r"(lane), "r"(n0 + __popc(m1))
+                         : "memory");
             wbase = __shfl_sync(0xffffffffu, wbase, 0);
             const unsigned lt = (1u << lane) - 1;
             const uint32_t pos = (uint32_t)it.j | ((uint32_t)it.iy << 8);

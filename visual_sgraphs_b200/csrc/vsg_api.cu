@@ -350,6 +350,23 @@ vsg_status run_pipeline(vsg_extractor *ex, const uint8_t *lvl0_base, int lvl0_pi
 
 }  // namespace
 
+namespace vsg {
+bool extractor_pyramid(vsg_extractor *ex, PyramidRef *out) {
+    if (!ex || ex->cur_w == 0 || ex->last_nframes == 0) return false;
+    out->device = ex->device;
+    out->nframes = ex->last_nframes;
+    out->geom = &ex->g;
+    out->lvl0_base = ex->lvl0_base;
+    out->lvl0_pitch = ex->lvl0_pitch;
+    out->lvl0_stride = ex->lvl0_stride;
+    out->pyr = ex->pyr;
+    out->scale = ex->scale.data();
+    out->inv_scale = ex->inv_scale.data();
+    out->stream = ex->stream;
+    return true;
+}
+}  // namespace vsg
+
 extern "C" {
 
 const char *vsg_last_error(void) { return g_err; }

@@ -92,6 +92,20 @@ vsg_status matcher_ensure(vsg_matcher *m, int slot, size_t bytes);
 void launch_window_dists(vsg_matcher *m, const uint8_t *query_dev, int nq, const uint8_t *train_dev,
                          const int *cand_ptr_dev, const int *cand_dev, int *all_dist_dev);
 
+// Read-only view of an extractor's device pyramid of its last call (for the stereo matcher).
+struct PyramidRef {
+    int device;
+    int nframes;
+    const FrameGeom *geom;
+    const uint8_t *lvl0_base;
+    int lvl0_pitch;
+    int64_t lvl0_stride;
+    const uint8_t *pyr;
+    const float *scale, *inv_scale;   // host tables, nlevels entries
+    cudaStream_t stream;
+};
+bool extractor_pyramid(vsg_extractor *ex, PyramidRef *out);
+
 void set_error(const char *fmt, ...);
 bool cuda_ok(cudaError_t e, const char *what);
 void count_launch(int n = 1);

@@ -157,3 +157,18 @@ class ORBmatcher:
                                         ptr(kn), ptr(kp), ptr(ki), len(fn), ptr(fn), ptr(fp), ptr(fi),
                                         float(self.mfNNratio), int(self.mbCheckOrientation), ptr(out), C.byref(nm)))
         return nm.value, out
+
+    def ComputeStereoMatches(self, ex_left, ex_right, keys_l, desc_l, keys_r, desc_r, mb, mbf, frame_l=0, frame_r=0):
+        """Frame::ComputeStereoMatches (Frame.cc:957-1127) on the device pyramids of the two extractors' last call.
+        Returns (mvuRight, mvDepth) float32 arrays."""
+        from ._lib import KEYPOINT_DTYPE
+        keys_l = np.ascontiguousarray(keys_l, KEYPOINT_DTYPE)
+        keys_r = np.ascontiguousarray(keys_r, KEYPOINT_DTYPE)
+        desc_l = np.ascontiguousarray(desc_l, np.uint8).reshape(-1, 32)
+        desc_r = np.ascontiguousarray(desc_r, np.uint8).reshape(-1, 32)
+        u_right = np.zeros(len(keys_l), np.float32)
+        depth = np.zeros(len(keys_l), np.float32)
+        check(self._L.vsg_stereo_match(self._h, ex_left._h, ex_right._h, frame_l, frame_r, ptr(keys_l), ptr(desc_l),
+                                       len(keys_l), ptr(keys_r), ptr(desc_r), len(keys_r), float(mb), float(mbf),
+                                       ptr(u_right), ptr(depth)))
+        return u_right, depth
