@@ -261,6 +261,73 @@ vsg_status vsg_search_by_bow(vsg_matcher *m, const vsg_frame_view *KF, const uin
                              const int32_t *f_idx, float nnratio, int check_ori, int32_t *matches_f_out,
                              int *nmatches_out);
 
+/* A map point already projected into the searched Frame / KeyFrame by the caller: the pose, Sim3 and
+ * camera-model arithmetic ahead of GetFeaturesInArea (e.g. ORBmatcher.cc:444-486, 1182-1238, 1904-1929) stays
+ * with the reference's Sophus / GeometricCamera classes; everything from the window query on runs here. */
+typedef struct vsg_search_point {
+    float u, v;                    /* uv = project(Tcw * p3Dw) */
+    float ur;                      /* uv(0) - bf * invz (Fuse's stereo reprojection gate; unused elsewhere) */
+    float angle;                   /* pKF->mvKeysUn[i].angle of the source observation (rotation histogram) */
+    int32_t level;                 /* nPredictedLevel = pMP->PredictScale(dist, pKF) */
+    uint8_t valid;                 /* the point passed every gate ahead of GetFeaturesInArea */
+    uint8_t pad[3];
+} vsg_search_point;
+
+/* SearchByProjection(Frame& Cur, KeyFrame*, const set<MapPoint*>& sAlreadyFound, th, ORBdist)
+ * (ORBmatcher.cc:1880-2000, relocalisation).  pts[i] = map point i of the keyframe (valid = present, not bad,
+ * not already found, projection inside the frame, depth inside the scale-invariance range).
+ * occupied[j] = Cur.mvpMapPoints[j] != NULL.  assign_out as in vsg_search_by_projection_last. */
+vsg_status vsg_search_by_projection_reloc(vsg_matcher *m, const vsg_frame *Cur, const uint8_t *occupied, int n,
+                                          const vsg_search_point *pts, const uint8_t *desc, float th, int orb_dist,
+                                          int check_ori, int32_t *assign_out, int *nmatches_out);
+
+/* SearchByProjection(KeyFrame*, Sim3f& Scw, vpPoints, vpMatched, th, ratioHamming) and the vpPointsKFs overload
+ * (ORBmatcher.cc:430-528, 530-641; loop closing / merging).  matched[j] = vpMatched[j] != NULL on entry.
+ * assign_out[j] = index of the point written to vpMatched[j] (and vpMatchedKF[j]), -1 untouched. */
+vsg_status vsg_search_by_projection_sim3(vsg_matcher *m, const vsg_frame *KF, const uint8_t *matched, int n,
+                                         const vsg_search_point *pts, const uint8_t *desc, int th,
+                                         float ratio_hamming, int32_t *assign_out, int *nmatches_out);
+
+/* The search of ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th, bRight) (ORBmatcher.cc:1148-1335, variant 0: chi2
+ * reprojection gates 5.99 / 7.8 against inv_level_sigma2 = pKF->mvInvLevelSigma2, initial distance 256) and of
+ * Fuse(KeyFrame*, Sim3f&, vpPoints, th, vpReplacePoint) (:1337-1446, variant 1: no gate, initial INT_MAX).
+ * best_idx_out[i] = the keyframe feature the reference picks for point i (bestDist <= TH_LOW), else -1.  The
+ * search of a point does not depend on the map-point bookkeeping of earlier points, so the caller applies
+ * Replace / AddObservation / AddMapPoint in order afterwards, re-checking isBad() / IsInKeyFrame() as the
+ * reference does at the top of each iteration.  *nfused_out counts the entries >= 0. */
+vsg_status vsg_fuse_search(vsg_matcher *m, const vsg_frame *KF, int n, const vsg_search_point *pts,
+                           const uint8_t *desc, float th, const float *inv_level_sigma2, int variant,
+                           int32_t *best_idx_out, int *nfused_out);
+
+/* SearchBySim3(pKF1, pKF2, vpMatches12, S12, th) (ORBmatcher.cc:1448-1665).  pts1[i1] (KF1.n entries): map point
+ * i1 of KF1 projected into KF2 (valid = present, not already matched, not bad, depth/image/distance gates);
+ * pts2[i2] likewise into KF1.  matches12_out[i1] = i2 where both directions agree, else -1. */
+vsg_status vsg_search_by_sim3(vsg_matcher *m, const vsg_frame *KF1, const vsg_frame *KF2, int n1,
+                              const vsg_search_point *pts1, const uint8_t *desc1, int n2,
+                              const vsg_search_point *pts2, const uint8_t *desc2, float th, int32_t *matches12_out,
+                              int *nfound_out);
+
+/* SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vpMatches12) (ORBmatcher.cc:758-900).  mp_valid1/2[i] = map point
+ * present and not bad.  matches12_out[i1] = i2 (the reference stores vpMapPoints2[i2]) or -1. */
+vsg_status vsg_search_by_bow_kf(vsg_matcher *m, const vsg_frame_view *KF1, const uint8_t *mp_valid1,
+                                const vsg_frame_view *KF2, const uint8_t *mp_valid2, int nnodes1,
+                                const int32_t *nodes1, const int32_t *ptr1, const int32_t *idx1, int nnodes2,
+                                const int32_t *nodes2, const int32_t *ptr2, const int32_t *idx2, float nnratio,
+                                int check_ori, int32_t *matches12_out, int *nmatches_out);
+
+/* SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse) (ORBmatcher.cc:902-1146), single
+ * pinhole camera per keyframe (mpCamera2 == NULL).  has_mp1/2[i] = GetMapPoint(i) != NULL.  f12 = the
+ * fundamental matrix of Pinhole::epipolarConstrain (Pinhole.cpp:118-141), row-major; ep = epipole of KF1 in KF2
+ * (:914).  level_sigma2_2 = pKF2->mvLevelSigma2.  matches12_out[i1] = i2 or -1 (vMatchedPairs = the pairs with
+ * i2 >= 0 in increasing i1). */
+vsg_status vsg_search_for_triangulation(vsg_matcher *m, const vsg_frame_view *KF1, const uint8_t *has_mp1,
+                                        const vsg_frame_view *KF2, const uint8_t *has_mp2, int nnodes1,
+                                        const int32_t *nodes1, const int32_t *ptr1, const int32_t *idx1, int nnodes2,
+                                        const int32_t *nodes2, const int32_t *ptr2, const int32_t *idx2,
+                                        int only_stereo, int coarse, const float *f12, const float *ep,
+                                        const float *level_sigma2_2, int check_ori, int32_t *matches12_out,
+                                        int *nmatches_out);
+
 /* Frame::ComputeStereoMatches (Frame.cc:957-1127): for every left keypoint the best right keypoint in its row
  * band (octave +-1, uR in [uL - mbf/mb, uL], Hamming < TH_HIGH), then — if the distance is below
  * (TH_HIGH+TH_LOW)/2 — an 11x11 L1 patch correlation over 11 horizontal offsets on the un-blurred pyramid

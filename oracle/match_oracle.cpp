@@ -314,4 +314,292 @@ int orc_search_by_bow(const orc_frame_view *KF, const uint8_t *kf_mp_valid, cons
     return nmatches;
 }
 
+// KeyFrame::GetFeaturesInArea (KeyFrame.cc:834-875): the Frame version without the level filter
+static void kf_features_in_area(const orc_frame_view *f, const Grid &g, float x, float y, float r, std::vector<int> &out) {
+    features_in_area(f, g, x, y, r, -1, -1, out);
+}
+
+// ORBmatcher.cc:1880-2000 (projection and the gates ahead of GetFeaturesInArea are the caller's: pts[i].valid)
+int orc_search_by_projection_reloc(const orc_frame_view *Cur, const uint8_t *occupied_in, int n,
+                                   const orc_search_point *pts, const uint8_t *desc, float th, int orb_dist,
+                                   int check_ori, int32_t *assign) {
+    Grid g(Cur);
+    std::vector<uint8_t> has_mp(occupied_in, occupied_in + Cur->n);
+    for (int i = 0; i < Cur->n; ++i) assign[i] = -1;
+    std::vector<int> rot_hist[HISTO_LENGTH];
+    int nmatches = 0;
+    std::vector<int> cand;
+    for (int i = 0; i < n; ++i) {
+        const orc_search_point &p = pts[i];
+        if (!p.valid) continue;
+        const int level = p.level;
+        const float radius = th * Cur->scale_factors[level];
+        features_in_area(Cur, g, p.u, p.v, radius, level - 1, level + 1, cand);
+        if (cand.empty()) continue;
+        int best = 256, best_idx2 = -1;
+        for (int i2 : cand) {
+            if (has_mp[i2]) continue;
+            const int dist = descriptor_distance(desc + (size_t)i * 32, Cur->descriptors + (size_t)i2 * 32);
+            if (dist < best) { best = dist; best_idx2 = i2; }
+        }
+        if (best <= orb_dist && best_idx2 >= 0) {
+            assign[best_idx2] = i;
+            has_mp[best_idx2] = 1;
+            ++nmatches;
+            if (check_ori) rot_hist[rot_bin(p.angle, Cur->keys[best_idx2].angle)].push_back(best_idx2);
+        }
+    }
+    if (check_ori) {
+        int sizes[HISTO_LENGTH], ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; ++i) sizes[i] = (int)rot_hist[i].size();
+        three_maxima(sizes, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; ++i)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (int idx : rot_hist[i]) { assign[idx] = -2; --nmatches; }
+    }
+    return nmatches;
+}
+
+// ORBmatcher.cc:430-528 / :530-641
+int orc_search_by_projection_sim3(const orc_frame_view *KF, const uint8_t *matched_in, int n, const orc_search_point *pts,
+                                  const uint8_t *desc, int th, float ratio_hamming, int32_t *assign) {
+    Grid g(KF);
+    std::vector<uint8_t> matched(matched_in, matched_in + KF->n);
+    for (int i = 0; i < KF->n; ++i) assign[i] = -1;
+    int nmatches = 0;
+    std::vector<int> cand;
+    for (int i = 0; i < n; ++i) {
+        const orc_search_point &p = pts[i];
+        if (!p.valid) continue;
+        const int level = p.level;
+        const float radius = th * KF->scale_factors[level];
+        kf_features_in_area(KF, g, p.u, p.v, radius, cand);
+        if (cand.empty()) continue;
+        int best = 256, best_idx = -1;
+        for (int idx : cand) {
+            if (matched[idx]) continue;
+            const int kp_level = KF->keys[idx].octave;
+            if (kp_level < level - 1 || kp_level > level) continue;
+            const int dist = descriptor_distance(desc + (size_t)i * 32, KF->descriptors + (size_t)idx * 32);
+            if (dist < best) { best = dist; best_idx = idx; }
+        }
+        if (best <= TH_LOW * ratio_hamming && best_idx >= 0) {
+            assign[best_idx] = i;
+            matched[best_idx] = 1;
+            ++nmatches;
+        }
+    }
+    return nmatches;
+}
+
+// the search of ORBmatcher.cc:1148-1335 (variant 0) / :1337-1446 (variant 1); the MapPoint bookkeeping is the caller's
+int orc_fuse_search(const orc_frame_view *KF, int n, const orc_search_point *pts, const uint8_t *desc, float th,
+                    const float *inv_level_sigma2, int variant, int32_t *best_idx_out) {
+    Grid g(KF);
+    int nfused = 0;
+    std::vector<int> cand;
+    for (int i = 0; i < n; ++i) {
+        best_idx_out[i] = -1;
+        const orc_search_point &p = pts[i];
+        if (!p.valid) continue;
+        const int level = p.level;
+        const float radius = th * KF->scale_factors[level];
+        kf_features_in_area(KF, g, p.u, p.v, radius, cand);
+        if (cand.empty()) continue;
+        int best = variant == 0 ? 256 : INT_MAX, best_idx = -1;
+        for (int idx : cand) {
+            const orc_keypoint &kp = KF->keys[idx];
+            const int kp_level = kp.octave;
+            if (kp_level < level - 1 || kp_level > level) continue;
+            if (variant == 0) {
+                if (KF->u_right && KF->u_right[idx] >= 0) {
+                    const float kpx = kp.x, kpy = kp.y, kpr = KF->u_right[idx];
+                    const float ex = p.u - kpx, ey = p.v - kpy, er = p.ur - kpr;
+                    const float e2 = ex * ex + ey * ey + er * er;
+                    if (e2 * inv_level_sigma2[kp_level] > 7.8) continue;
+                } else {
+                    const float kpx = kp.x, kpy = kp.y;
+                    const float ex = p.u - kpx, ey = p.v - kpy;
+                    const float e2 = ex * ex + ey * ey;
+                    if (e2 * inv_level_sigma2[kp_level] > 5.99) continue;
+                }
+            }
+            const int dist = descriptor_distance(desc + (size_t)i * 32, KF->descriptors + (size_t)idx * 32);
+            if (dist < best) { best = dist; best_idx = idx; }
+        }
+        if (best <= TH_LOW) {
+            best_idx_out[i] = best_idx;
+            ++nfused;
+        }
+    }
+    return nfused;
+}
+
+// ORBmatcher.cc:1448-1665
+int orc_search_by_sim3(const orc_frame_view *KF1, const orc_frame_view *KF2, const orc_search_point *pts1,
+                       const uint8_t *desc1, const orc_search_point *pts2, const uint8_t *desc2, float th,
+                       int32_t *matches12) {
+    const int n1 = KF1->n, n2 = KF2->n;
+    std::vector<int> match1(n1, -1), match2(n2, -1);
+    std::vector<int> cand;
+    for (int dir = 0; dir < 2; ++dir) {
+        const orc_frame_view *T = dir == 0 ? KF2 : KF1;
+        const orc_search_point *pts = dir == 0 ? pts1 : pts2;
+        const uint8_t *desc = dir == 0 ? desc1 : desc2;
+        std::vector<int> &out = dir == 0 ? match1 : match2;
+        Grid g(T);
+        for (int i = 0; i < (dir == 0 ? n1 : n2); ++i) {
+            if (!pts[i].valid) continue;
+            const int level = pts[i].level;
+            const float radius = th * T->scale_factors[level];
+            kf_features_in_area(T, g, pts[i].u, pts[i].v, radius, cand);
+            if (cand.empty()) continue;
+            int best = INT_MAX, best_idx = -1;
+            for (int idx : cand) {
+                const orc_keypoint &kp = T->keys[idx];
+                if (kp.octave < level - 1 || kp.octave > level) continue;
+                const int dist = descriptor_distance(desc + (size_t)i * 32, T->descriptors + (size_t)idx * 32);
+                if (dist < best) { best = dist; best_idx = idx; }
+            }
+            if (best <= TH_HIGH) out[i] = best_idx;
+        }
+    }
+    int nfound = 0;
+    for (int i1 = 0; i1 < n1; ++i1) {
+        matches12[i1] = -1;
+        const int idx2 = match1[i1];
+        if (idx2 >= 0) {
+            const int idx1 = match2[idx2];
+            if (idx1 == i1) { matches12[i1] = idx2; ++nfound; }
+        }
+    }
+    return nfound;
+}
+
+// ORBmatcher.cc:758-900 (NLeft == -1)
+int orc_search_by_bow_kf(const orc_frame_view *KF1, const uint8_t *mp_valid1, const orc_frame_view *KF2,
+                         const uint8_t *mp_valid2, int nn1, const int32_t *nodes1, const int32_t *ptr1,
+                         const int32_t *idx1v, int nn2, const int32_t *nodes2, const int32_t *ptr2, const int32_t *idx2v,
+                         float nnratio, int check_ori, int32_t *matches12) {
+    for (int i = 0; i < KF1->n; ++i) matches12[i] = -1;
+    std::vector<bool> matched2(KF2->n, false);
+    std::vector<int> rot_hist[HISTO_LENGTH];
+    int nmatches = 0, a = 0, b = 0;
+    while (a < nn1 && b < nn2) {
+        if (nodes1[a] == nodes2[b]) {
+            for (int k1 = ptr1[a]; k1 < ptr1[a + 1]; ++k1) {
+                const int idx1 = idx1v[k1];
+                if (!mp_valid1[idx1]) continue;
+                const uint8_t *d1 = KF1->descriptors + (size_t)idx1 * 32;
+                int best1 = 256, best_idx2 = -1, best2 = 256;
+                for (int k2 = ptr2[b]; k2 < ptr2[b + 1]; ++k2) {
+                    const int idx2 = idx2v[k2];
+                    if (matched2[idx2] || !mp_valid2[idx2]) continue;
+                    const int dist = descriptor_distance(d1, KF2->descriptors + (size_t)idx2 * 32);
+                    if (dist < best1) { best2 = best1; best1 = dist; best_idx2 = idx2; }
+                    else if (dist < best2) best2 = dist;
+                }
+                if (best1 < TH_LOW) {
+                    if (static_cast<float>(best1) < nnratio * static_cast<float>(best2)) {
+                        matches12[idx1] = best_idx2;
+                        matched2[best_idx2] = true;
+                        if (check_ori) rot_hist[rot_bin(KF1->keys[idx1].angle, KF2->keys[best_idx2].angle)].push_back(idx1);
+                        ++nmatches;
+                    }
+                }
+            }
+            ++a; ++b;
+        } else if (nodes1[a] < nodes2[b]) {
+            while (a < nn1 && nodes1[a] < nodes2[b]) ++a;
+        } else {
+            while (b < nn2 && nodes2[b] < nodes1[a]) ++b;
+        }
+    }
+    if (check_ori) {
+        int sizes[HISTO_LENGTH], ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; ++i) sizes[i] = (int)rot_hist[i].size();
+        three_maxima(sizes, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int i1 : rot_hist[i]) { matches12[i1] = -1; --nmatches; }
+        }
+    }
+    return nmatches;
+}
+
+// Pinhole::epipolarConstrain (Pinhole.cpp:118-141) with F12 precomputed by the caller
+static bool epipolar_constrain(const float *F12, const orc_keypoint &kp1, const orc_keypoint &kp2, float unc) {
+    const float a = kp1.x * F12[0] + kp1.y * F12[3] + F12[6];
+    const float b = kp1.x * F12[1] + kp1.y * F12[4] + F12[7];
+    const float c = kp1.x * F12[2] + kp1.y * F12[5] + F12[8];
+    const float num = a * kp2.x + b * kp2.y + c;
+    const float den = a * a + b * b;
+    if (den == 0) return false;
+    const float dsqr = num * num / den;
+    return dsqr < 3.84 * unc;
+}
+
+// ORBmatcher.cc:902-1146 (mpCamera2 == NULL)
+int orc_search_for_triangulation(const orc_frame_view *KF1, const uint8_t *has_mp1, const orc_frame_view *KF2,
+                                 const uint8_t *has_mp2, int nn1, const int32_t *nodes1, const int32_t *ptr1,
+                                 const int32_t *idx1v, int nn2, const int32_t *nodes2, const int32_t *ptr2,
+                                 const int32_t *idx2v, int only_stereo, int coarse, const float *f12, const float *ep,
+                                 const float *level_sigma2_2, int check_ori, int32_t *matches12) {
+    for (int i = 0; i < KF1->n; ++i) matches12[i] = -1;
+    std::vector<bool> matched2(KF2->n, false);   // declared and tested by the reference, never set (SURVEY C#3)
+    std::vector<int> rot_hist[HISTO_LENGTH];
+    int nmatches = 0, a = 0, b = 0;
+    while (a < nn1 && b < nn2) {
+        if (nodes1[a] == nodes2[b]) {
+            for (int k1 = ptr1[a]; k1 < ptr1[a + 1]; ++k1) {
+                const int idx1 = idx1v[k1];
+                if (has_mp1[idx1]) continue;
+                const bool stereo1 = KF1->u_right && KF1->u_right[idx1] >= 0;
+                if (only_stereo && !stereo1) continue;
+                const orc_keypoint &kp1 = KF1->keys[idx1];
+                const uint8_t *d1 = KF1->descriptors + (size_t)idx1 * 32;
+                int best = TH_LOW, best_idx2 = -1;
+                for (int k2 = ptr2[b]; k2 < ptr2[b + 1]; ++k2) {
+                    const int idx2 = idx2v[k2];
+                    if (matched2[idx2] || has_mp2[idx2]) continue;
+                    const bool stereo2 = KF2->u_right && KF2->u_right[idx2] >= 0;
+                    if (only_stereo && !stereo2) continue;
+                    const int dist = descriptor_distance(d1, KF2->descriptors + (size_t)idx2 * 32);
+                    if (dist > TH_LOW || dist > best) continue;
+                    const orc_keypoint &kp2 = KF2->keys[idx2];
+                    if (!stereo1 && !stereo2) {
+                        const float distex = ep[0] - kp2.x, distey = ep[1] - kp2.y;
+                        if (distex * distex + distey * distey < 100 * KF2->scale_factors[kp2.octave]) continue;
+                    }
+                    if (coarse || epipolar_constrain(f12, kp1, kp2, level_sigma2_2[kp2.octave])) {
+                        best_idx2 = idx2;
+                        best = dist;
+                    }
+                }
+                if (best_idx2 >= 0) {
+                    matches12[idx1] = best_idx2;
+                    ++nmatches;
+                    if (check_ori) rot_hist[rot_bin(kp1.angle, KF2->keys[best_idx2].angle)].push_back(idx1);
+                }
+            }
+            ++a; ++b;
+        } else if (nodes1[a] < nodes2[b]) {
+            while (a < nn1 && nodes1[a] < nodes2[b]) ++a;
+        } else {
+            while (b < nn2 && nodes2[b] < nodes1[a]) ++b;
+        }
+    }
+    if (check_ori) {
+        int sizes[HISTO_LENGTH], ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; ++i) sizes[i] = (int)rot_hist[i].size();
+        three_maxima(sizes, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int i1 : rot_hist[i]) { matches12[i1] = -1; --nmatches; }
+        }
+    }
+    return nmatches;
+}
+
+
 }  // extern "C"

@@ -150,6 +150,39 @@ int orc_search_by_bow(const orc_frame_view *KF, const uint8_t *kf_mp_valid, cons
                       const int32_t *f_nodes, const int32_t *f_ptr, const int32_t *f_idx, float nnratio, int check_ori,
                       int32_t *matches_f);
 
+/* A map point already projected into the searched Frame / KeyFrame (layout-identical to vsg_search_point). */
+typedef struct orc_search_point {
+    float u, v, ur, angle;
+    int32_t level;                 /* nPredictedLevel */
+    uint8_t valid;
+    uint8_t pad[3];
+} orc_search_point;
+
+/* SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1880-2000). */
+int orc_search_by_projection_reloc(const orc_frame_view *Cur, const uint8_t *occupied, int n, const orc_search_point *pts,
+                                   const uint8_t *desc, float th, int orb_dist, int check_ori, int32_t *assign);
+/* SearchByProjection(KeyFrame*, Sim3f&, vpPoints[, vpPointsKFs], vpMatched, th, ratioHamming) (:430-641). */
+int orc_search_by_projection_sim3(const orc_frame_view *KF, const uint8_t *matched, int n, const orc_search_point *pts,
+                                  const uint8_t *desc, int th, float ratio_hamming, int32_t *assign);
+/* The search of Fuse (variant 0: :1148-1335 with the chi2 gates; variant 1: :1337-1446). */
+int orc_fuse_search(const orc_frame_view *KF, int n, const orc_search_point *pts, const uint8_t *desc, float th,
+                    const float *inv_level_sigma2, int variant, int32_t *best_idx_out);
+/* SearchBySim3 (:1448-1665): pts1 has KF1->n entries, pts2 has KF2->n. */
+int orc_search_by_sim3(const orc_frame_view *KF1, const orc_frame_view *KF2, const orc_search_point *pts1,
+                       const uint8_t *desc1, const orc_search_point *pts2, const uint8_t *desc2, float th,
+                       int32_t *matches12);
+/* SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (:758-900). */
+int orc_search_by_bow_kf(const orc_frame_view *KF1, const uint8_t *mp_valid1, const orc_frame_view *KF2,
+                         const uint8_t *mp_valid2, int nn1, const int32_t *nodes1, const int32_t *ptr1,
+                         const int32_t *idx1, int nn2, const int32_t *nodes2, const int32_t *ptr2, const int32_t *idx2,
+                         float nnratio, int check_ori, int32_t *matches12);
+/* SearchForTriangulation (:902-1146, mpCamera2 == NULL, Pinhole::epipolarConstrain with F12 given row-major). */
+int orc_search_for_triangulation(const orc_frame_view *KF1, const uint8_t *has_mp1, const orc_frame_view *KF2,
+                                 const uint8_t *has_mp2, int nn1, const int32_t *nodes1, const int32_t *ptr1,
+                                 const int32_t *idx1, int nn2, const int32_t *nodes2, const int32_t *ptr2,
+                                 const int32_t *idx2, int only_stereo, int coarse, const float *f12, const float *ep,
+                                 const float *level_sigma2_2, int check_ori, int32_t *matches12);
+
 /* Frame::ComputeStereoMatches (Frame.cc:957-1127): row-band Hamming search, 11x11 SAD refinement on the
  * un-blurred pyramids of both extractors (their last orc_extract call), parabola fit, median-based outlier
  * rejection.  keys/desc are the extractors' raw outputs (mvKeys / mvKeysRight).  Fills u_right[n_l], depth[n_l]

@@ -77,6 +77,13 @@ def lib():
         L.orc_search_by_projection_last.argtypes = [vp, vp, C.c_int, vp, vp, C.c_float, C.c_int, C.c_int, vp]
         L.orc_search_for_initialization.argtypes = [vp, vp, vp, C.c_int, C.c_float, C.c_int, vp]
         L.orc_search_by_bow.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, C.c_float, C.c_int, vp]
+        L.orc_search_by_projection_reloc.argtypes = [vp, vp, C.c_int, vp, vp, C.c_float, C.c_int, C.c_int, vp]
+        L.orc_search_by_projection_sim3.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, C.c_float, vp]
+        L.orc_fuse_search.argtypes = [vp, C.c_int, vp, vp, C.c_float, vp, C.c_int, vp]
+        L.orc_search_by_sim3.argtypes = [vp, vp, vp, vp, vp, vp, C.c_float, vp]
+        L.orc_search_by_bow_kf.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, C.c_float, C.c_int, vp]
+        L.orc_search_for_triangulation.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int,
+                                                   C.c_int, vp, vp, vp, C.c_int, vp]
         L.orc_stereo_matches.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_float, C.c_float, vp, vp]
         L.orc_bench_extract.restype = C.c_double
         L.orc_bench_extract.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
@@ -300,3 +307,65 @@ def stereo_matches(ex_left, ex_right, keys_l, desc_l, keys_r, desc_r, mb, mbf):
     lib().orc_stereo_matches(ex_left._h, ex_right._h, _ptr(keys_l), _ptr(desc_l), len(keys_l), _ptr(keys_r), _ptr(desc_r),
                              len(keys_r), mb, mbf, _ptr(u_right), _ptr(depth))
     return u_right, depth
+
+
+def _u8(a):
+    return np.ascontiguousarray(a, np.uint8)
+
+
+def search_by_projection_reloc(view, occupied, pts, desc, th, orb_dist, check_ori):
+    occupied, desc = _u8(occupied), _u8(desc)
+    assign = np.zeros(view.n, np.int32)
+    nm = lib().orc_search_by_projection_reloc(C.addressof(view), _ptr(occupied), len(pts), _ptr(pts), _ptr(desc), th,
+                                              int(orb_dist), int(check_ori), _ptr(assign))
+    return nm, assign
+
+
+def search_by_projection_sim3(view, matched, pts, desc, th, ratio_hamming):
+    matched, desc = _u8(matched), _u8(desc)
+    assign = np.zeros(view.n, np.int32)
+    nm = lib().orc_search_by_projection_sim3(C.addressof(view), _ptr(matched), len(pts), _ptr(pts), _ptr(desc), int(th),
+                                             ratio_hamming, _ptr(assign))
+    return nm, assign
+
+
+def fuse_search(view, pts, desc, th, inv_level_sigma2, variant):
+    desc = _u8(desc)
+    sig = np.ascontiguousarray(inv_level_sigma2, np.float32)
+    best = np.zeros(max(len(pts), 1), np.int32)
+    nf = lib().orc_fuse_search(C.addressof(view), len(pts), _ptr(pts), _ptr(desc), th, _ptr(sig), int(variant), _ptr(best))
+    return nf, best[:len(pts)]
+
+
+def search_by_sim3(view1, view2, pts1, desc1, pts2, desc2, th):
+    desc1, desc2 = _u8(desc1), _u8(desc2)
+    m12 = np.zeros(max(view1.n, 1), np.int32)
+    nf = lib().orc_search_by_sim3(C.addressof(view1), C.addressof(view2), _ptr(pts1), _ptr(desc1), _ptr(pts2), _ptr(desc2),
+                                  th, _ptr(m12))
+    return nf, m12[:view1.n]
+
+
+def search_by_bow_kf(view1, valid1, view2, valid2, fv1, fv2, nnratio, check_ori):
+    n1, p1, i1 = (np.ascontiguousarray(a, np.int32) for a in fv1)
+    n2, p2, i2 = (np.ascontiguousarray(a, np.int32) for a in fv2)
+    valid1, valid2 = _u8(valid1), _u8(valid2)
+    out = np.zeros(max(view1.n, 1), np.int32)
+    nm = lib().orc_search_by_bow_kf(C.addressof(view1), _ptr(valid1), C.addressof(view2), _ptr(valid2), len(n1), _ptr(n1),
+                                    _ptr(p1), _ptr(i1), len(n2), _ptr(n2), _ptr(p2), _ptr(i2), nnratio, int(check_ori),
+                                    _ptr(out))
+    return nm, out[:view1.n]
+
+
+def search_for_triangulation(view1, has1, view2, has2, fv1, fv2, only_stereo, coarse, f12, ep, level_sigma2_2, check_ori):
+    n1, p1, i1 = (np.ascontiguousarray(a, np.int32) for a in fv1)
+    n2, p2, i2 = (np.ascontiguousarray(a, np.int32) for a in fv2)
+    has1, has2 = _u8(has1), _u8(has2)
+    f12 = np.ascontiguousarray(f12, np.float32).reshape(9)
+    ep = np.ascontiguousarray(ep, np.float32).reshape(2)
+    sig = np.ascontiguousarray(level_sigma2_2, np.float32)
+    out = np.zeros(max(view1.n, 1), np.int32)
+    nm = lib().orc_search_for_triangulation(C.addressof(view1), _ptr(has1), C.addressof(view2), _ptr(has2), len(n1),
+                                            _ptr(n1), _ptr(p1), _ptr(i1), len(n2), _ptr(n2), _ptr(p2), _ptr(i2),
+                                            int(only_stereo), int(coarse), _ptr(f12), _ptr(ep), _ptr(sig), int(check_ori),
+                                            _ptr(out))
+    return nm, out[:view1.n]

@@ -10,6 +10,74 @@
 #include <random>
 #include <vector>
 
+#include <set>
+#include <tuple>
+
+// ---- stand-ins for Eigen / Sophus (only what the shim's templates use) ----
+struct Vec3 {
+    float v[3];
+    float operator()(int i) const { return v[i]; }
+    Vec3 operator-(const Vec3 &o) const { return Vec3{{v[0] - o.v[0], v[1] - o.v[1], v[2] - o.v[2]}}; }
+    Vec3 operator+(const Vec3 &o) const { return Vec3{{v[0] + o.v[0], v[1] + o.v[1], v[2] + o.v[2]}}; }
+    Vec3 operator/(float s) const { return Vec3{{v[0] / s, v[1] / s, v[2] / s}}; }
+    Vec3 operator*(float s) const { return Vec3{{v[0] * s, v[1] * s, v[2] * s}}; }
+    float dot(const Vec3 &o) const { return v[0] * o.v[0] + v[1] * o.v[1] + v[2] * o.v[2]; }
+    float norm() const { return std::sqrt(dot(*this)); }
+};
+struct Vec2 {
+    float v[2];
+    float operator()(int i) const { return v[i]; }
+};
+struct Mat3 {
+    float m[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    int fill = 0;
+    float operator()(int r, int c) const { return m[3 * r + c]; }
+    Mat3 &operator<<(float x) { fill = 0; m[fill++] = x; return *this; }
+    Mat3 &operator,(float x) { m[fill++] = x; return *this; }
+    Mat3 transpose() const { Mat3 t; for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) t.m[3 * r + c] = m[3 * c + r]; return t; }
+    Mat3 operator*(const Mat3 &o) const {
+        Mat3 t;
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { float a = 0; for (int k = 0; k < 3; ++k) a += m[3 * r + k] * o.m[3 * k + c]; t.m[3 * r + c] = a; }
+        return t;
+    }
+    Vec3 operator*(const Vec3 &p) const { return Vec3{{m[0] * p.v[0] + m[1] * p.v[1] + m[2] * p.v[2], m[3] * p.v[0] + m[4] * p.v[1] + m[5] * p.v[2], m[6] * p.v[0] + m[7] * p.v[1] + m[8] * p.v[2]}}; }
+    Mat3 inverse() const {
+        const float *a = m;
+        const float det = a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * a[7] - a[4] * a[6]);
+        Mat3 t;
+        t.m[0] = (a[4] * a[8] - a[5] * a[7]) / det; t.m[1] = (a[2] * a[7] - a[1] * a[8]) / det; t.m[2] = (a[1] * a[5] - a[2] * a[4]) / det;
+        t.m[3] = (a[5] * a[6] - a[3] * a[8]) / det; t.m[4] = (a[0] * a[8] - a[2] * a[6]) / det; t.m[5] = (a[2] * a[3] - a[0] * a[5]) / det;
+        t.m[6] = (a[3] * a[7] - a[4] * a[6]) / det; t.m[7] = (a[1] * a[6] - a[0] * a[7]) / det; t.m[8] = (a[0] * a[4] - a[1] * a[3]) / det;
+        return t;
+    }
+};
+namespace Sophus {
+struct SE3f {   // rotation kept as a matrix; the tests use the identity rotation
+    Mat3 R;
+    Vec3 t{{0, 0, 0}};
+    SE3f() {}
+    SE3f(const Mat3 &R_, const Vec3 &t_) : R(R_), t(t_) {}
+    SE3f inverse() const { Mat3 Rt = R.transpose(); Vec3 nt = Rt * t; return SE3f(Rt, Vec3{{-nt.v[0], -nt.v[1], -nt.v[2]}}); }
+    Vec3 translation() const { return t; }
+    Mat3 rotationMatrix() const { return R; }
+    Vec3 operator*(const Vec3 &p) const { return R * p + t; }
+    SE3f operator*(const SE3f &o) const { return SE3f(R * o.R, R * o.t + t); }
+};
+template <class T>
+struct Sim3 {
+    Mat3 R;
+    Vec3 t{{0, 0, 0}};
+    T s = 1;
+    Mat3 rotationMatrix() const { return R; }
+    Vec3 translation() const { return t; }
+    T scale() const { return s; }
+    Sim3 inverse() const { Sim3 o; o.R = R.transpose(); o.s = 1 / s; Vec3 nt = o.R * t; o.t = Vec3{{-nt.v[0] / s, -nt.v[1] / s, -nt.v[2] / s}}; return o; }
+    Vec3 operator*(const Vec3 &p) const { return (R * p) * s + t; }
+};
+using Sim3f = Sim3<float>;
+}  // namespace Sophus
+#define SOPHUS_SIM3_HPP
+
 #include "../../oracle/oracle.h"
 #include "../../visual_sgraphs_b200/shim/ORBextractor.h"
 #include "../../visual_sgraphs_b200/shim/ORBmatcher.h"
@@ -21,24 +89,15 @@ static int g_fail = 0;
     } while (0)
 
 // ---- stand-ins for the reference's types (only what ORBmatcher reads) ----
-struct Vec3 {
-    float v[3];
-    float operator()(int i) const { return v[i]; }
-};
-struct Vec2 {
-    float v[2];
-    float operator()(int i) const { return v[i]; }
-};
-struct Pose {   // translation-only SE3
-    Vec3 t;
-    Pose inverse() const { return Pose{{{-t.v[0], -t.v[1], -t.v[2]}}}; }
-    Vec3 translation() const { return t; }
-    Vec3 operator*(const Vec3 &p) const { return Vec3{{p.v[0] + t.v[0], p.v[1] + t.v[1], p.v[2] + t.v[2]}}; }
-};
+using Pose = Sophus::SE3f;
+static Pose translation_pose(float x, float y, float z) { return Pose(Mat3(), Vec3{{x, y, z}}); }
 struct Camera {
     float fx = 500, fy = 500, cx = 320, cy = 240;
     Vec2 project(const Vec3 &p) const { return Vec2{{fx * p.v[0] / p.v[2] + cx, fy * p.v[1] / p.v[2] + cy}}; }
+    Mat3 toK_() const { Mat3 K; K << fx, 0.f, cx, 0.f, fy, cy, 0.f, 0.f, 1.f; return K; }
 };
+struct KeyFrame;
+struct Frame;
 struct MapPoint {
     bool mbTrackInView = false, mbTrackInViewR = false;
     float mTrackProjX = 0, mTrackProjY = 0, mTrackProjXR = 0, mTrackViewCos = 1, mTrackDepth = 1;
@@ -47,10 +106,29 @@ struct MapPoint {
     int obs = 1;
     cv::Mat desc;
     Vec3 pos{{0, 0, 1}};
+    Vec3 normal{{0, 0, 1}};
+    float max_dist = 1e4f, min_dist = 0.01f;
+    std::set<const void *> in_kf;
+    MapPoint *replaced_by = nullptr;
+    std::map<const void *, int> index_in;
     bool isBad() const { return bad; }
     int Observations() const { return obs; }
     cv::Mat GetDescriptor() const { return desc.clone(); }
     Vec3 GetWorldPos() const { return pos; }
+    Vec3 GetNormal() const { return normal; }
+    float GetMaxDistanceInvariance() const { return max_dist; }
+    float GetMinDistanceInvariance() const { return min_dist; }
+    template <class T> int PredictScale(float dist, T *pF) const {      // MapPoint.cc:533-565
+        const float ratio = max_dist / dist;
+        int nScale = std::ceil(std::log(ratio) / pF->mfLogScaleFactor);
+        if (nScale < 0) nScale = 0;
+        else if (nScale >= pF->mnScaleLevels) nScale = pF->mnScaleLevels - 1;
+        return nScale;
+    }
+    bool IsInKeyFrame(const void *kf) const { return in_kf.count(kf) != 0; }
+    void AddObservation(const void *kf, int idx) { in_kf.insert(kf); index_in[kf] = idx; ++obs; }
+    void Replace(MapPoint *o) { bad = true; replaced_by = o; o->in_kf.insert(in_kf.begin(), in_kf.end()); o->obs += obs; }
+    std::tuple<int, int> GetIndexInKeyFrame(const void *kf) const { auto it = index_in.find(kf); return std::make_tuple(it == index_in.end() ? -1 : it->second, -1); }
 };
 struct Frame {
     int N = 0, Nleft = -1;
@@ -64,11 +142,30 @@ struct Frame {
     float mnMinX = 0, mnMinY = 0, mnMaxX = 640, mnMaxY = 480;
     float mfGridElementWidthInv = 64.f / 640.f, mfGridElementHeightInv = 48.f / 480.f;
     float mb = 0.1f, mbf = 40.f;
-    Pose pose{{{0, 0, 0}}};
+    Pose pose;
     Camera cam;
     Camera *mpCamera = &cam;
+    float mfLogScaleFactor = std::log(1.2f);
+    int mnScaleLevels = 8;
     Pose GetPose() const { return pose; }
     std::vector<MapPoint *> GetMapPointMatches() const { return mvpMapPoints; }   // KeyFrame interface
+};
+struct KeyFrame : Frame {   // the members ORBmatcher reads from a KeyFrame (KeyFrame.h)
+    int NLeft = -1;
+    float fx = 500, fy = 500, cx = 320, cy = 240;
+    Camera *mpCamera2 = nullptr;
+    std::vector<float> mvLevelSigma2, mvInvLevelSigma2;
+    explicit KeyFrame(const Frame &f) : Frame(f) {
+        mpCamera = &cam;
+        for (float sc : mvScaleFactors) { mvLevelSigma2.push_back(sc * sc); mvInvLevelSigma2.push_back(1.0f / (sc * sc)); }
+    }
+    KeyFrame(const KeyFrame &) = delete;
+    MapPoint *GetMapPoint(size_t i) const { return mvpMapPoints[i]; }
+    void AddMapPoint(MapPoint *p, size_t i) { mvpMapPoints[i] = p; }
+    std::set<MapPoint *> GetMapPoints() const { std::set<MapPoint *> s; for (MapPoint *p : mvpMapPoints) if (p && !p->isBad()) s.insert(p); return s; }
+    bool IsInImage(float x, float y) const { return x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY; }
+    Vec3 GetCameraCenter() const { return pose.inverse().translation(); }
+    Pose GetPoseInverse() const { return pose.inverse(); }
 };
 
 static std::vector<unsigned char> read_raw(const char *path, size_t n) {
@@ -229,8 +326,8 @@ int main(int argc, char **argv) {
         Frame Cur = A, Last = B;
         Cur.mpCamera = &Cur.cam; Last.mpCamera = &Last.cam;
         Cur.mvpMapPoints.assign(Cur.N, nullptr);
-        Cur.pose = Pose{{{0.02f, -0.01f, -0.3f}}};    // tlc = Tlw * (-t): z = +0.3 > mb -> forward
-        Last.pose = Pose{{{0, 0, 0}}};
+        Cur.pose = translation_pose(0.02f, -0.01f, -0.3f);    // tlc = Tlw * (-t): z = +0.3 > mb -> forward
+        Last.pose = translation_pose(0, 0, 0);
         std::vector<MapPoint> store(Last.N);
         std::vector<orc_proj_point> pts(Last.N);
         std::vector<unsigned char> pdesc((size_t)Last.N * 32, 0);
@@ -240,7 +337,7 @@ int main(int argc, char **argv) {
             // a world point whose projection in Cur lands near the shifted keypoint
             const float u = Last.mvKeys[i].pt.x - 9, v = Last.mvKeys[i].pt.y - 5;
             const Vec3 xc{{(u - 320) * z / 500, (v - 240) * z / 500, z}};
-            mp.pos = Vec3{{xc.v[0] - Cur.pose.t.v[0], xc.v[1] - Cur.pose.t.v[1], xc.v[2] - Cur.pose.t.v[2]}};
+            mp.pos = xc - Cur.pose.t;
             mp.obs = rng() % 10 < 9 ? 1 : 0;
             mp.desc = Last.mDescriptors.row(i).clone();
             Last.mvpMapPoints[i] = rng() % 10 < 8 ? &mp : nullptr;
@@ -320,6 +417,309 @@ int main(int argc, char **argv) {
         for (int i = 0; i < A.N; ++i) {
             EXPECT(got12[i] == m12[i], "vnMatches12[%d]", i);
             EXPECT(prev[i].x == prev_o[2 * i] && prev[i].y == prev_o[2 * i + 1], "vbPrevMatched[%d]", i);
+        }
+    }
+
+    // ================= keyframe-side methods =================
+    // world points that project near B's keypoints shifted into A (camera at the given translation-only pose)
+    auto make_points = [&](const Frame &src, const Pose &pose, float dx, float dy, std::vector<MapPoint> &store) {
+        store.assign(src.N, MapPoint());
+        for (int i = 0; i < src.N; ++i) {
+            MapPoint &mp = store[i];
+            const float z = 2.f + (rng() % 100) / 10.f;
+            const float u = src.mvKeys[i].pt.x + dx + ((int)(rng() % 5) - 2) * 0.5f, v = src.mvKeys[i].pt.y + dy + ((int)(rng() % 5) - 2) * 0.5f;
+            const Vec3 xc{{(u - 320) * z / 500, (v - 240) * z / 500, z}};
+            mp.pos = xc - pose.t;
+            mp.desc = src.mDescriptors.row(i).clone();
+            mp.bad = rng() % 30 == 0;
+            mp.obs = 1 + rng() % 3;
+            // max distance so that PredictScale lands on the keypoint's octave (+-1)
+            mp.max_dist = z * std::pow(1.2f, (float)src.mvKeys[i].octave + ((int)(rng() % 3) - 1) * 0.6f) * 0.999f;
+            mp.min_dist = 0.05f;
+        }
+    };
+    auto flat_fv = [](const std::map<unsigned, std::vector<unsigned>> &fv, std::vector<int32_t> &n, std::vector<int32_t> &p, std::vector<int32_t> &x) {
+        p.push_back(0);
+        for (auto &kv : fv) { n.push_back(kv.first); for (unsigned v : kv.second) x.push_back(v); p.push_back((int32_t)x.size()); }
+    };
+    // the caller-side projection of the reference loops, restated for the oracle's inputs
+    auto project_points = [&](const std::vector<MapPoint *> &vp, const Pose &Tcw, const KeyFrame *kf, const Frame *fr, bool check_normal,
+                              bool frame_bounds, std::vector<orc_search_point> &pts, std::vector<unsigned char> &desc) {
+        pts.assign(vp.size(), orc_search_point());
+        desc.assign(vp.size() * 32, 0);
+        const Vec3 Ow = Tcw.inverse().translation();
+        for (size_t i = 0; i < vp.size(); ++i) {
+            orc_search_point &p = pts[i];
+            std::memset(&p, 0, sizeof(p));
+            MapPoint *mp = vp[i];
+            if (!mp) continue;
+            const Vec3 pc = Tcw * mp->pos;
+            if (!frame_bounds && pc(2) < 0.0f) continue;
+            const Vec2 uv = Camera().project(pc);
+            if (frame_bounds) { if (uv(0) < 0 || uv(0) > 640 || uv(1) < 0 || uv(1) > 480) continue; }
+            else if (!(uv(0) >= 0 && uv(0) < 640 && uv(1) >= 0 && uv(1) < 480)) continue;
+            const Vec3 PO = mp->pos - Ow;
+            const float dist = PO.norm();
+            if (dist < mp->min_dist || dist > mp->max_dist) continue;
+            if (check_normal && PO.dot(mp->normal) < 0.5 * dist) continue;
+            p.level = kf ? mp->PredictScale(dist, kf) : mp->PredictScale(dist, fr);
+            p.u = uv(0); p.v = uv(1); p.ur = uv(0) - 40.f * (1 / pc(2));
+            p.valid = 1;
+            std::memcpy(&desc[i * 32], mp->desc.ptr(0), 32);
+        }
+    };
+
+    // ---------------- SearchByProjection(Cur, KF, sAlreadyFound, th, ORBdist): relocalisation ----------------
+    {
+        Frame Cur = A;
+        Cur.mpCamera = &Cur.cam;
+        Cur.pose = translation_pose(0.01f, 0.02f, 0.05f);
+        Cur.mvpMapPoints.assign(Cur.N, nullptr);
+        KeyFrame KF(B);
+        std::vector<MapPoint> store;
+        make_points(B, Cur.pose, -9, -5, store);
+        for (MapPoint &mp : store) mp.normal = Vec3{{0, 0, 0}};
+        std::set<MapPoint *> found;
+        MapPoint pre;
+        for (int i = 0; i < KF.N; ++i) {
+            KF.mvpMapPoints[i] = rng() % 10 < 9 ? &store[i] : nullptr;
+            if (rng() % 15 == 0) found.insert(&store[i]);
+        }
+        std::vector<unsigned char> occupied(Cur.N, 0);
+        for (int i = 0; i < Cur.N; i += 13) { Cur.mvpMapPoints[i] = &pre; occupied[i] = 1; }
+        std::vector<MapPoint *> vp = KF.mvpMapPoints;
+        for (auto &q : vp) if (q && (q->bad || found.count(q))) q = nullptr;
+        std::vector<orc_search_point> pts;
+        std::vector<unsigned char> pdesc, dc;
+        project_points(vp, Cur.pose, nullptr, &Cur, false, true, pts, pdesc);
+        for (int i = 0; i < KF.N; ++i) pts[i].angle = KF.mvKeysUn[i].angle;
+        orc_frame_view vc = view_of(Cur, dc);
+        std::vector<int32_t> assign(Cur.N);
+        const int want = orc_search_by_projection_reloc(&vc, occupied.data(), KF.N, pts.data(), pdesc.data(), 10.f, 100, 1, assign.data());
+        VS_GRAPHS::ORBmatcher matcher(0.9f, true);
+        const int got = matcher.SearchByProjection(Cur, &KF, found, 10.f, 100);
+        EXPECT(got == want && got > 50, "SearchByProjection(reloc): %d vs %d", got, want);
+        for (int i = 0; i < Cur.N; ++i) {
+            MapPoint *expect = assign[i] >= 0 ? KF.mvpMapPoints[assign[i]] : (assign[i] == -2 ? nullptr : (occupied[i] ? &pre : nullptr));
+            EXPECT(Cur.mvpMapPoints[i] == expect, "reloc mvpMapPoints[%d]", i);
+        }
+    }
+
+    // ---------------- SearchByBoW(KF1, KF2) ----------------
+    {
+        KeyFrame K1(A), K2(B);
+        std::vector<MapPoint> s1(K1.N), s2(K2.N);
+        std::vector<unsigned char> v1(K1.N), v2(K2.N);
+        for (int i = 0; i < K1.N; ++i) { s1[i].bad = rng() % 25 == 0; K1.mvpMapPoints[i] = rng() % 10 < 9 ? &s1[i] : nullptr; v1[i] = K1.mvpMapPoints[i] && !s1[i].bad; }
+        for (int i = 0; i < K2.N; ++i) { s2[i].bad = rng() % 25 == 0; K2.mvpMapPoints[i] = rng() % 10 < 9 ? &s2[i] : nullptr; v2[i] = K2.mvpMapPoints[i] && !s2[i].bad; }
+        std::vector<int32_t> n1, p1, i1, n2, p2, i2;
+        flat_fv(K1.mFeatVec, n1, p1, i1);
+        flat_fv(K2.mFeatVec, n2, p2, i2);
+        std::vector<unsigned char> d1, d2;
+        orc_frame_view w1 = view_of(K1, d1), w2 = view_of(K2, d2);
+        std::vector<int32_t> m12(K1.N);
+        const int want = orc_search_by_bow_kf(&w1, v1.data(), &w2, v2.data(), (int)n1.size(), n1.data(), p1.data(), i1.data(),
+                                              (int)n2.size(), n2.data(), p2.data(), i2.data(), 0.8f, 1, m12.data());
+        VS_GRAPHS::ORBmatcher matcher(0.8f, true);
+        std::vector<MapPoint *> matches;
+        const int got = matcher.SearchByBoW(&K1, &K2, matches);
+        EXPECT(got == want && got > 10, "SearchByBoW(KF,KF): %d vs %d", got, want);
+        for (int i = 0; i < K1.N && i < (int)matches.size(); ++i)
+            EXPECT(matches[i] == (m12[i] >= 0 ? K2.mvpMapPoints[m12[i]] : nullptr), "vpMatches12[%d]", i);
+    }
+
+    // ---------------- Fuse(KF, vpMapPoints, th) ----------------
+    {
+        KeyFrame KF(A);
+        KF.pose = translation_pose(0.f, 0.01f, 0.02f);
+        std::vector<MapPoint> store, inkf(KF.N);
+        make_points(B, KF.pose, -9, -5, store);
+        for (int i = 0; i < KF.N; ++i) { inkf[i].obs = 1 + rng() % 4; inkf[i].bad = rng() % 20 == 0; KF.mvpMapPoints[i] = rng() % 3 == 0 ? &inkf[i] : nullptr; }
+        std::vector<MapPoint *> vp(store.size());
+        for (size_t i = 0; i < store.size(); ++i) vp[i] = rng() % 12 == 0 ? nullptr : &store[i];
+        for (size_t i = 0; i + 1 < vp.size(); i += 17) vp[i + 1] = vp[i];                    // duplicates: the second is skipped by IsInKeyFrame
+        std::vector<orc_search_point> pts;
+        std::vector<unsigned char> pdesc, dk;
+        project_points(vp, KF.pose, &KF, nullptr, true, false, pts, pdesc);
+        orc_frame_view vk = view_of(KF, dk);
+        std::vector<int32_t> best(vp.size());
+        orc_fuse_search(&vk, (int)vp.size(), pts.data(), pdesc.data(), 3.f, KF.mvInvLevelSigma2.data(), 0, best.data());
+        // expected bookkeeping, replayed on copies of the mock state
+        std::vector<MapPoint> e_store = store, e_inkf = inkf;
+        std::vector<MapPoint *> e_kfmp(KF.N);
+        for (int i = 0; i < KF.N; ++i) e_kfmp[i] = KF.mvpMapPoints[i] ? &e_inkf[KF.mvpMapPoints[i] - &inkf[0]] : nullptr;
+        int want = 0;
+        for (size_t i = 0; i < vp.size(); ++i) {
+            if (!vp[i]) continue;
+            MapPoint *mp = &e_store[vp[i] - &store[0]];
+            if (mp->bad || mp->IsInKeyFrame(&KF)) continue;
+            if (best[i] < 0) continue;
+            MapPoint *in = e_kfmp[best[i]];
+            if (in) { if (!in->bad) { if (in->obs > mp->obs) mp->Replace(in); else in->Replace(mp); } }
+            else { mp->AddObservation(&KF, best[i]); e_kfmp[best[i]] = mp; }
+            ++want;
+        }
+        VS_GRAPHS::ORBmatcher matcher;
+        const int got = matcher.Fuse(&KF, vp, 3.f);
+        EXPECT(got == want && got > 20, "Fuse: %d vs %d", got, want);
+        for (size_t i = 0; i < store.size(); ++i) EXPECT(store[i].bad == e_store[i].bad && store[i].obs == e_store[i].obs, "Fuse map point %zu state", i);
+        for (int i = 0; i < KF.N; ++i) {
+            const MapPoint *g = KF.mvpMapPoints[i], *e = e_kfmp[i];
+            const bool same = (!g && !e) || (g && e && ((g >= &store[0] && g < &store[0] + store.size()) ? (e == &e_store[g - &store[0]]) : (e == &e_inkf[g - &inkf[0]])));
+            EXPECT(same, "Fuse KF map point %d", i);
+        }
+    }
+
+    // ---------------- Sim3 family: SearchByProjection(KF, Scw, ...), SearchBySim3, Fuse(KF, Scw, ...) ----------------
+    {
+        KeyFrame KF(A);
+        Sophus::Sim3f Scw;
+        Scw.s = 2.f; Scw.t = Vec3{{0.02f, -0.02f, 0.04f}};                                  // Tcw = [I | t/s]
+        const Pose Tcw(Mat3(), Scw.t / Scw.s);
+        std::vector<MapPoint> store;
+        make_points(B, Tcw, -9, -5, store);
+        std::vector<MapPoint *> vp(store.size());
+        for (size_t i = 0; i < store.size(); ++i) vp[i] = &store[i];
+        std::vector<MapPoint *> vpMatched(KF.N, nullptr);
+        MapPoint pre;
+        for (int i = 0; i < KF.N; i += 9) vpMatched[i] = &pre;
+        for (int i = 4; i < KF.N; i += 31) vpMatched[i] = vp[i % vp.size()];                // already found points
+        std::set<MapPoint *> already(vpMatched.begin(), vpMatched.end());
+        std::vector<MapPoint *> vq = vp;
+        for (auto &q : vq) if (q->bad || already.count(q)) q = nullptr;
+        std::vector<orc_search_point> pts;
+        std::vector<unsigned char> pdesc, dk;
+        project_points(vq, Tcw, &KF, nullptr, true, false, pts, pdesc);
+        orc_frame_view vk = view_of(KF, dk);
+        std::vector<unsigned char> matched(KF.N);
+        for (int i = 0; i < KF.N; ++i) matched[i] = vpMatched[i] != nullptr;
+        std::vector<int32_t> assign(KF.N);
+        const int want = orc_search_by_projection_sim3(&vk, matched.data(), (int)vq.size(), pts.data(), pdesc.data(), 8, 1.5f, assign.data());
+        const std::vector<MapPoint *> before = vpMatched;
+        std::vector<KeyFrame *> pkfs(vp.size(), &KF), matched_kf(KF.N, nullptr);
+        std::vector<MapPoint *> vpMatched2 = vpMatched;
+        VS_GRAPHS::ORBmatcher matcher;
+        const int got = matcher.SearchByProjection(&KF, Scw, vp, vpMatched, 8, 1.5f);
+        const int got2 = matcher.SearchByProjection(&KF, Scw, vp, pkfs, vpMatched2, matched_kf, 8, 1.5f);
+        EXPECT(got == want && got2 == want && got > 50, "SearchByProjection(Sim3): %d / %d vs %d", got, got2, want);
+        for (int i = 0; i < KF.N; ++i) {
+            EXPECT(vpMatched[i] == (assign[i] >= 0 ? vp[assign[i]] : before[i]) && vpMatched2[i] == vpMatched[i], "vpMatched[%d]", i);
+            EXPECT(matched_kf[i] == (assign[i] >= 0 ? &KF : nullptr), "vpMatchedKF[%d]", i);
+        }
+        // Fuse(KF, Scw, vpPoints, th, vpReplacePoint)
+        std::vector<MapPoint> inkf(KF.N);
+        for (int i = 0; i < KF.N; ++i) { inkf[i].bad = rng() % 20 == 0; KF.mvpMapPoints[i] = rng() % 3 == 0 ? &inkf[i] : nullptr; }
+        std::vector<MapPoint *> vr = vp;
+        project_points(vr, Tcw, &KF, nullptr, true, false, pts, pdesc);
+        std::vector<int32_t> best(vr.size());
+        orc_fuse_search(&vk, (int)vr.size(), pts.data(), pdesc.data(), 4.f, nullptr, 1, best.data());
+        std::vector<MapPoint *> e_kfmp = KF.mvpMapPoints, e_replace(vr.size(), nullptr);
+        int wantf = 0;
+        for (size_t i = 0; i < vr.size(); ++i) {
+            if (vr[i]->bad || best[i] < 0) continue;
+            MapPoint *in = e_kfmp[best[i]];
+            if (in) { if (!in->bad) e_replace[i] = in; }
+            else e_kfmp[best[i]] = vr[i];
+            ++wantf;
+        }
+        std::vector<MapPoint *> replace(vr.size(), nullptr);
+        const int gotf = matcher.Fuse(&KF, Scw, vr, 4.f, replace);
+        EXPECT(gotf == wantf && gotf > 50, "Fuse(Sim3): %d vs %d", gotf, wantf);
+        EXPECT(replace == e_replace && KF.mvpMapPoints == e_kfmp, "Fuse(Sim3) outputs");
+    }
+    {
+        // SearchBySim3: K1 = A at the origin, K2 = B; S12 maps camera-2 coordinates to camera-1 (translation + scale 1)
+        KeyFrame K1(A), K2(B);
+        K1.pose = translation_pose(0, 0, 0);
+        K2.pose = translation_pose(0.03f, 0.01f, 0.f);
+        Sophus::Sim3f S12;
+        S12.t = Vec3{{-0.03f, -0.01f, 0.f}};
+        const Sophus::Sim3f S21 = S12.inverse();
+        std::vector<MapPoint> s1, s2;
+        make_points(A, translation_pose(0, 0, 0), 0, 0, s1);        // seen in K1 at A's keypoints
+        make_points(B, translation_pose(0, 0, 0), -9, -5, s2);      // K2's points: land at A's coordinates in camera 1
+        for (int i = 0; i < K1.N; ++i) K1.mvpMapPoints[i] = rng() % 10 < 8 ? &s1[i] : nullptr;
+        for (int i = 0; i < K2.N; ++i) K2.mvpMapPoints[i] = rng() % 10 < 8 ? &s2[i] : nullptr;
+        // make K1's points project into K2 where B's keypoints are: shift their world position
+        for (int i = 0; i < K1.N; ++i) {
+            const float z = s1[i].pos.v[2];
+            s1[i].pos = Vec3{{(A.mvKeys[i].pt.x + 9 - 320) * z / 500, (A.mvKeys[i].pt.y + 5 - 240) * z / 500, z}} - S21.t;
+        }
+        std::vector<MapPoint *> vpMatches12(K1.N, nullptr);
+        for (int i = 0; i < K1.N; i += 23) if (K2.mvpMapPoints[i % K2.N]) { vpMatches12[i] = K2.mvpMapPoints[i % K2.N]; vpMatches12[i]->index_in[&K2] = i % K2.N; }
+        std::vector<bool> am1(K1.N, false), am2(K2.N, false);
+        for (int i = 0; i < K1.N; ++i) if (vpMatches12[i]) { am1[i] = true; am2[std::get<0>(vpMatches12[i]->GetIndexInKeyFrame(&K2))] = true; }
+        auto proj = [&](const std::vector<MapPoint *> &vp, const std::vector<bool> &am, const Pose &Tw, const Sophus::Sim3f &S, KeyFrame *tgt,
+                        std::vector<orc_search_point> &pts, std::vector<unsigned char> &desc) {
+            pts.assign(vp.size(), orc_search_point());
+            desc.assign(vp.size() * 32, 0);
+            for (size_t i = 0; i < vp.size(); ++i) {
+                std::memset(&pts[i], 0, sizeof(orc_search_point));
+                MapPoint *mp = vp[i];
+                if (!mp || am[i] || mp->bad) continue;
+                const Vec3 pb = S * (Tw * mp->pos);
+                if (pb(2) < 0.0) continue;
+                const float invz = 1.0 / pb(2);
+                const float x = pb(0) * invz, y = pb(1) * invz;
+                const float u = 500 * x + 320, v = 500 * y + 240;
+                if (!tgt->IsInImage(u, v)) continue;
+                const float d = pb.norm();
+                if (d < mp->min_dist || d > mp->max_dist) continue;
+                pts[i].level = mp->PredictScale(d, tgt);
+                pts[i].u = u; pts[i].v = v; pts[i].valid = 1;
+                std::memcpy(&desc[i * 32], mp->desc.ptr(0), 32);
+            }
+        };
+        std::vector<orc_search_point> p1, p2;
+        std::vector<unsigned char> e1, e2, d1, d2;
+        proj(K1.mvpMapPoints, am1, K1.pose, S21, &K2, p1, e1);
+        proj(K2.mvpMapPoints, am2, K2.pose, S12, &K1, p2, e2);
+        orc_frame_view w1 = view_of(K1, d1), w2 = view_of(K2, d2);
+        std::vector<int32_t> m12(K1.N);
+        const int want = orc_search_by_sim3(&w1, &w2, p1.data(), e1.data(), p2.data(), e2.data(), 7.5f, m12.data());
+        const std::vector<MapPoint *> before = vpMatches12;
+        VS_GRAPHS::ORBmatcher matcher;
+        const int got = matcher.SearchBySim3(&K1, &K2, vpMatches12, S12, 7.5f);
+        EXPECT(got == want && got > 30, "SearchBySim3: %d vs %d", got, want);
+        for (int i = 0; i < K1.N; ++i) EXPECT(vpMatches12[i] == (m12[i] >= 0 ? K2.mvpMapPoints[m12[i]] : before[i]), "SearchBySim3 vpMatches12[%d]", i);
+    }
+
+    // ---------------- SearchForTriangulation ----------------
+    {
+        KeyFrame K1(A), K2(B);
+        K1.pose = translation_pose(0, 0, 0);
+        K2.pose = translation_pose(-0.09f, -0.05f, 0.f);      // pure sideways motion: epipolar lines along (9, 5)
+        std::vector<MapPoint> s1(K1.N), s2(K2.N);
+        std::vector<unsigned char> h1(K1.N), h2(K2.N);
+        for (int i = 0; i < K1.N; ++i) { K1.mvpMapPoints[i] = rng() % 10 < 3 ? &s1[i] : nullptr; h1[i] = K1.mvpMapPoints[i] != nullptr; }
+        for (int i = 0; i < K2.N; ++i) { K2.mvpMapPoints[i] = rng() % 10 < 3 ? &s2[i] : nullptr; h2[i] = K2.mvpMapPoints[i] != nullptr; }
+        std::vector<int32_t> n1, p1, i1, n2, p2, i2;
+        flat_fv(K1.mFeatVec, n1, p1, i1);
+        flat_fv(K2.mFeatVec, n2, p2, i2);
+        // the same F12 / epipole the shim derives (Pinhole.cpp:120-124, ORBmatcher.cc:908-914) with the stand-in algebra
+        const Pose T12 = K1.pose * K2.pose.inverse();
+        const Vec3 t12 = T12.translation();
+        Mat3 t12x;
+        t12x << 0, -t12(2), t12(1), t12(2), 0, -t12(0), -t12(1), t12(0), 0;
+        const Mat3 K = Camera().toK_();
+        const Mat3 F12 = K.transpose().inverse() * t12x * T12.rotationMatrix() * K.inverse();
+        const Vec3 C2 = K2.pose * K1.GetCameraCenter();
+        const Vec2 ep = Camera().project(C2);
+        const float epf[2] = {ep(0), ep(1)};
+        std::vector<unsigned char> d1, d2;
+        orc_frame_view w1 = view_of(K1, d1), w2 = view_of(K2, d2);
+        for (int coarse = 0; coarse < 2; ++coarse) {
+            std::vector<int32_t> m12(K1.N);
+            const int want = orc_search_for_triangulation(&w1, h1.data(), &w2, h2.data(), (int)n1.size(), n1.data(), p1.data(), i1.data(),
+                                                          (int)n2.size(), n2.data(), p2.data(), i2.data(), 0, coarse, F12.m, epf,
+                                                          K2.mvLevelSigma2.data(), 1, m12.data());
+            VS_GRAPHS::ORBmatcher matcher(0.6f, true);
+            std::vector<std::pair<size_t, size_t>> pairs;
+            const int got = matcher.SearchForTriangulation(&K1, &K2, pairs, false, coarse != 0);
+            EXPECT(got == want && got > 5 && (int)pairs.size() == got, "SearchForTriangulation(coarse=%d): %d vs %d (%zu pairs)", coarse, got, want, pairs.size());
+            size_t k = 0;
+            for (int i = 0; i < K1.N; ++i)
+                if (m12[i] >= 0) { EXPECT(k < pairs.size() && pairs[k].first == (size_t)i && pairs[k].second == (size_t)m12[i], "pair %zu", k); ++k; }
         }
     }
 

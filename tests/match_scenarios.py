@@ -79,3 +79,37 @@ def feature_vector(desc, nnodes=64):
         idx.extend(members.tolist())
         ptr.append(len(idx))
     return nodes.astype(np.int32), np.array(ptr, np.int32), np.array(idx, np.int32)
+
+
+def search_points(kb, shift, seed, sigma=1.0, size=(640, 480)):
+    """Map points observed in frame B (keys kb), projected into frame A by the caller: vsg_search_point records."""
+    from visual_sgraphs_b200._lib import SEARCH_POINT_DTYPE
+    rng = np.random.default_rng(seed)
+    n = len(kb)
+    pts = np.zeros(n, SEARCH_POINT_DTYPE)
+    pts["u"] = kb["x"] - shift[0] + rng.normal(0, sigma, n)
+    pts["v"] = kb["y"] - shift[1] + rng.normal(0, sigma, n)
+    pts["ur"] = pts["u"] - rng.uniform(2, 40, n)
+    pts["angle"] = kb["angle"]
+    pts["level"] = np.clip(kb["octave"] + rng.integers(-1, 2, n), 0, 7)
+    inside = (pts["u"] >= 0) & (pts["u"] < size[0]) & (pts["v"] >= 0) & (pts["v"] < size[1])
+    pts["valid"] = inside & (rng.random(n) < 0.9)
+    return pts
+
+
+def sigma_tables():
+    s = [np.float32(1.0)]
+    for _ in range(7):
+        s.append(np.float32(float(s[-1]) * float(np.float32(1.2))))
+    scale = np.array(s, np.float32)
+    sigma2 = (scale * scale).astype(np.float32)
+    return scale, sigma2, (np.float32(1.0) / sigma2).astype(np.float32)
+
+
+def translation_f12(shift):
+    """Fundamental matrix (row-major, Pinhole::epipolarConstrain's F12) of a pure image translation by `shift`:
+    the epipolar line of kp1 is the line through kp1 along the shift."""
+    sx, sy = float(shift[0]), float(shift[1])
+    nrm = np.hypot(sx, sy)
+    nx, ny = -sy / nrm, sx / nrm
+    return np.array([0, 0, -nx, 0, 0, -ny, nx, ny, 0], np.float32)

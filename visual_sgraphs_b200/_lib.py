@@ -41,7 +41,9 @@ TRACK_POINT_DTYPE = np.dtype([("proj_x", "<f4"), ("proj_y", "<f4"), ("proj_xr", 
                               ("pad", "u1")])
 PROJ_POINT_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("ur", "<f4"), ("angle", "<f4"), ("octave", "<i4"),
                              ("valid", "u1"), ("blocks", "u1"), ("pad", "u1", 2)])
-assert TRACK_POINT_DTYPE.itemsize == 28 and PROJ_POINT_DTYPE.itemsize == 24
+SEARCH_POINT_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("ur", "<f4"), ("angle", "<f4"), ("level", "<i4"),
+                               ("valid", "u1"), ("pad", "u1", 3)])
+assert TRACK_POINT_DTYPE.itemsize == 28 and PROJ_POINT_DTYPE.itemsize == 24 and SEARCH_POINT_DTYPE.itemsize == 24
 
 
 class VsgError(RuntimeError):
@@ -97,6 +99,21 @@ _SIGNATURES = {
     "vsg_search_by_bow": (C.c_int, [C.c_void_p, C.POINTER(FrameView), C.c_void_p, C.POINTER(FrameView), C.c_int,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_float, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
+    "vsg_search_by_projection_reloc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                                 C.c_float, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
+    "vsg_search_by_projection_sim3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                                C.c_int, C.c_float, C.c_void_p, C.POINTER(C.c_int)]),
+    "vsg_fuse_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
+                                  C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
+    "vsg_search_by_sim3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.POINTER(C.c_int)]),
+    "vsg_search_by_bow_kf": (C.c_int, [C.c_void_p, C.POINTER(FrameView), C.c_void_p, C.POINTER(FrameView), C.c_void_p,
+                                       C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
+    "vsg_search_for_triangulation": (C.c_int, [C.c_void_p, C.POINTER(FrameView), C.c_void_p, C.POINTER(FrameView),
+                                               C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                               C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
     "vsg_stereo_match": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
 }

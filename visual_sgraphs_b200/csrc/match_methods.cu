@@ -19,48 +19,9 @@
 #include <cmath>
 #include <vector>
 
-#include "vsg_internal.cuh"
-
-struct vsg_frame {
-    int device = 0;        // the frame may outlive the matcher that uploaded it
-    int n = 0, cols = 0, rows = 0, n_levels = 0;
-    float min_x = 0, min_y = 0, inv_w = 0, inv_h = 0;
-    bool has_right = false;
-    // device
-    float2 *xy = nullptr;
-    int *octave = nullptr;
-    float *u_right = nullptr;
-    uint8_t *desc = nullptr;
-    int *cell_ptr = nullptr, *cell_idx = nullptr;
-    // host copies the resolve loops read
-    std::vector<vsg_keypoint> keys;
-    std::vector<float> scale;
-};
+#include "match_internal.cuh"
 
 namespace vsg {
-
-#define CK(call)                                          \
-    do {                                                  \
-        if (!cuda_ok((call), #call)) return VSG_ERR_CUDA; \
-    } while (0)
-
-constexpr int TH_HIGH = 100, TH_LOW = 50, HISTO_LENGTH = 30;   // ORBmatcher.cc:34-36
-
-struct FrameDev {
-    int n, cols, rows;
-    float min_x, min_y, inv_w, inv_h;
-    const float2 *xy;
-    const int *octave;
-    const float *u_right;   // nullptr if monocular
-    const uint4 *desc;
-    const int *cell_ptr, *cell_idx;
-};
-
-struct AreaQuery {          // one GetFeaturesInArea call + the per-candidate stereo gate of the caller
-    float x, y, r;
-    int min_level, max_level;
-    float xr, rr;           // right-image gate: skip if u_right[idx] > 0 && |xr - u_right[idx]| > rr; rr < 0 disables it
-};
 
 __device__ __forceinline__ int hamming256(const uint4 &a0, const uint4 &a1, const uint4 &b0, const uint4 &b1) {
     return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
@@ -121,7 +82,7 @@ __global__ void area_search_kernel(FrameDev f, int nq, const AreaQuery *__restri
 }
 
 // Runs the area search for nq queries and brings the lists back: ptr[nq+1] and (idx, dist) pairs in query order.
-static vsg_status area_search(vsg_matcher *m, const vsg_frame *f, int nq, const AreaQuery *qs, const uint8_t *qdesc,
+vsg_status area_search(vsg_matcher *m, const vsg_frame *f, int nq, const AreaQuery *qs, const uint8_t *qdesc,
                               std::vector<int> &ptr, std::vector<int2> &ent) {
     ptr.assign(nq + 1, 0);
     ent.clear();
@@ -169,7 +130,7 @@ static vsg_status area_search(vsg_matcher *m, const vsg_frame *f, int nq, const 
 }
 
 // ORBmatcher::ComputeThreeMaxima (ORBmatcher.cc:2002-2043)
-static void three_maxima(const std::vector<int> *hist, int L, int &ind1, int &ind2, int &ind3) {
+void three_maxima(const std::vector<int> *hist, int L, int &ind1, int &ind2, int &ind3) {
     int max1 = 0, max2 = 0, max3 = 0;
     for (int i = 0; i < L; ++i) {
         const int s = (int)hist[i].size();
@@ -181,7 +142,7 @@ static void three_maxima(const std::vector<int> *hist, int L, int &ind1, int &in
     else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
 }
 
-static int rot_bin(float a1, float a2) {   // :351-358 — factor is 1/HISTO_LENGTH, C round()
+int rot_bin(float a1, float a2) {   // :351-358 — factor is 1/HISTO_LENGTH, C round()
     const float factor = 1.0f / HISTO_LENGTH;
     float rot = a1 - a2;
     if (rot < 0.0) rot += 360.0f;
@@ -206,6 +167,7 @@ vsg_status vsg_frame_create(vsg_matcher *m, const vsg_frame_view *v, vsg_frame *
     f->has_right = v->u_right != nullptr;
     f->keys.assign(v->keys, v->keys + v->n);
     if (v->scale_factors) f->scale.assign(v->scale_factors, v->scale_factors + v->n_levels);
+    if (v->u_right) f->u_right_h.assign(v->u_right, v->u_right + v->n);
     // AssignFeaturesToGrid (Frame.cc:521-553): keypoints appended to their cell in index order; PosInGrid uses round()
     const int ncell = f->cols * f->rows;
     std::vector<int> cell_of(v->n, -1), cptr(ncell + 1, 0), cidx;

@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import PROJ_POINT_DTYPE, TRACK_POINT_DTYPE, check, ptr
+from ._lib import PROJ_POINT_DTYPE, SEARCH_POINT_DTYPE, TRACK_POINT_DTYPE, check, ptr
 from .frame import DeviceFrame, FrameData
 
 TH_HIGH = 100     # ORBmatcher.cc:34
@@ -156,6 +156,84 @@ class ORBmatcher:
         check(self._L.vsg_search_by_bow(self._h, C.byref(kf_data.view), ptr(valid), C.byref(f_data.view), len(kn),
                                         ptr(kn), ptr(kp), ptr(ki), len(fn), ptr(fn), ptr(fp), ptr(fi),
                                         float(self.mfNNratio), int(self.mbCheckOrientation), ptr(out), C.byref(nm)))
+        return nm.value, out
+
+    def SearchByProjectionReloc(self, cur_frame, occupied, search_points, desc, th, ORBdist):
+        """SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1880-2000) with the
+        projection done by the caller. Returns (nmatches, assign[N])."""
+        pts = np.ascontiguousarray(search_points, SEARCH_POINT_DTYPE)
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        occupied = np.ascontiguousarray(occupied, np.uint8)
+        assign = np.zeros(cur_frame.data.n, np.int32)
+        nm = C.c_int(0)
+        check(self._L.vsg_search_by_projection_reloc(self._h, cur_frame._h, ptr(occupied), len(pts), ptr(pts), ptr(desc),
+                                                     float(th), int(ORBdist), int(self.mbCheckOrientation),
+                                                     ptr(assign), C.byref(nm)))
+        return nm.value, assign
+
+    def SearchByProjectionSim3(self, kf_frame, matched, search_points, desc, th, ratioHamming=1.0):
+        """SearchByProjection(KeyFrame*, Sim3f&, vpPoints[, vpPointsKFs], vpMatched, th, ratioHamming)
+        (ORBmatcher.cc:430-641). Returns (nmatches, assign[N])."""
+        pts = np.ascontiguousarray(search_points, SEARCH_POINT_DTYPE)
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        matched = np.ascontiguousarray(matched, np.uint8)
+        assign = np.zeros(kf_frame.data.n, np.int32)
+        nm = C.c_int(0)
+        check(self._L.vsg_search_by_projection_sim3(self._h, kf_frame._h, ptr(matched), len(pts), ptr(pts), ptr(desc),
+                                                    int(th), float(ratioHamming), ptr(assign), C.byref(nm)))
+        return nm.value, assign
+
+    def FuseSearch(self, kf_frame, search_points, desc, th, inv_level_sigma2=None, sim3_variant=False):
+        """The search of Fuse(KeyFrame*, vpMapPoints, th) (ORBmatcher.cc:1148-1335) or, with sim3_variant, of
+        Fuse(KeyFrame*, Sim3f&, ...) (:1337-1446). Returns (nFused, best_idx[n])."""
+        pts = np.ascontiguousarray(search_points, SEARCH_POINT_DTYPE)
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        sig = None if inv_level_sigma2 is None else np.ascontiguousarray(inv_level_sigma2, np.float32)
+        best = np.zeros(len(pts), np.int32)
+        nf = C.c_int(0)
+        check(self._L.vsg_fuse_search(self._h, kf_frame._h, len(pts), ptr(pts), ptr(desc), float(th), ptr(sig),
+                                      int(bool(sim3_variant)), ptr(best), C.byref(nf)))
+        return nf.value, best
+
+    def SearchBySim3(self, kf1_frame, kf2_frame, pts1, desc1, pts2, desc2, th):
+        """ORBmatcher.cc:1448-1665 with both projections done by the caller. Returns (nFound, matches12[N1])."""
+        pts1 = np.ascontiguousarray(pts1, SEARCH_POINT_DTYPE)
+        pts2 = np.ascontiguousarray(pts2, SEARCH_POINT_DTYPE)
+        desc1 = np.ascontiguousarray(desc1, np.uint8).reshape(-1, 32)
+        desc2 = np.ascontiguousarray(desc2, np.uint8).reshape(-1, 32)
+        m12 = np.zeros(len(pts1), np.int32)
+        nf = C.c_int(0)
+        check(self._L.vsg_search_by_sim3(self._h, kf1_frame._h, kf2_frame._h, len(pts1), ptr(pts1), ptr(desc1), len(pts2),
+                                         ptr(pts2), ptr(desc2), float(th), ptr(m12), C.byref(nf)))
+        return nf.value, m12
+
+    def SearchByBoWKF(self, kf1_data, mp_valid1, kf2_data, mp_valid2, featvec1, featvec2):
+        """SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (ORBmatcher.cc:758-900). Returns (nmatches, matches12[N1])."""
+        n1, p1, i1 = (np.ascontiguousarray(a, np.int32) for a in featvec1)
+        n2, p2, i2 = (np.ascontiguousarray(a, np.int32) for a in featvec2)
+        v1, v2 = np.ascontiguousarray(mp_valid1, np.uint8), np.ascontiguousarray(mp_valid2, np.uint8)
+        out = np.zeros(kf1_data.n, np.int32)
+        nm = C.c_int(0)
+        check(self._L.vsg_search_by_bow_kf(self._h, C.byref(kf1_data.view), ptr(v1), C.byref(kf2_data.view), ptr(v2),
+                                           len(n1), ptr(n1), ptr(p1), ptr(i1), len(n2), ptr(n2), ptr(p2), ptr(i2),
+                                           float(self.mfNNratio), int(self.mbCheckOrientation), ptr(out), C.byref(nm)))
+        return nm.value, out
+
+    def SearchForTriangulation(self, kf1_data, has_mp1, kf2_data, has_mp2, featvec1, featvec2, F12, ep, level_sigma2_2,
+                               bOnlyStereo=False, bCoarse=False):
+        """ORBmatcher.cc:902-1146 (single pinhole camera). Returns (nmatches, matches12[N1])."""
+        n1, p1, i1 = (np.ascontiguousarray(a, np.int32) for a in featvec1)
+        n2, p2, i2 = (np.ascontiguousarray(a, np.int32) for a in featvec2)
+        h1, h2 = np.ascontiguousarray(has_mp1, np.uint8), np.ascontiguousarray(has_mp2, np.uint8)
+        F12 = np.ascontiguousarray(F12, np.float32).reshape(9)
+        ep = np.ascontiguousarray(ep, np.float32).reshape(2)
+        sig = np.ascontiguousarray(level_sigma2_2, np.float32)
+        out = np.zeros(kf1_data.n, np.int32)
+        nm = C.c_int(0)
+        check(self._L.vsg_search_for_triangulation(self._h, C.byref(kf1_data.view), ptr(h1), C.byref(kf2_data.view), ptr(h2),
+                                                   len(n1), ptr(n1), ptr(p1), ptr(i1), len(n2), ptr(n2), ptr(p2), ptr(i2),
+                                                   int(bOnlyStereo), int(bCoarse), ptr(F12), ptr(ep), ptr(sig),
+                                                   int(self.mbCheckOrientation), ptr(out), C.byref(nm)))
         return nm.value, out
 
     def ComputeStereoMatches(self, ex_left, ex_right, keys_l, desc_l, keys_r, desc_r, mb, mbf, frame_l=0, frame_r=0):

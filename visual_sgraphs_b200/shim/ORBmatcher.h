@@ -20,6 +20,9 @@
 #include <cstdint>
 #include <cstring>
 #include <set>
+#include <tuple>
+#include <type_traits>
+#include <utility>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -67,6 +70,45 @@ public:
     template <class FrameT>
     int SearchForInitialization(FrameT &F1, FrameT &F2, std::vector<cv::Point2f> &vbPrevMatched,
                                 std::vector<int> &vnMatches12, int windowSize = 10);
+
+    // Project MapPoints seen in a KeyFrame into the Frame; relocalisation (ORBmatcher.cc:1880-2000).
+    template <class FrameT, class KeyFrameT, class MapPointT>
+    int SearchByProjection(FrameT &CurrentFrame, KeyFrameT *pKF, const std::set<MapPointT *> &sAlreadyFound, const float th,
+                           const int ORBdist);
+
+    // SearchByBoW between two keyframes; loop detection (ORBmatcher.cc:758-900).
+    template <class KeyFrameT, class MapPointT>
+    int SearchByBoW(KeyFrameT *pKF1, KeyFrameT *pKF2, std::vector<MapPointT *> &vpMatches12);
+
+    // Project MapPoints into a KeyFrame and search for duplicates (ORBmatcher.cc:1148-1335; bRight = false).
+    template <class KeyFrameT, class MapPointT>
+    int Fuse(KeyFrameT *pKF, const std::vector<MapPointT *> &vpMapPoints, const float th = 3.0, const bool bRight = false);
+
+#ifdef SOPHUS_SIM3_HPP   // the Sim3 overloads need Sophus' own SE3/Sim3 arithmetic (include sophus/sim3.hpp first, as
+                         // the reference's ORBmatcher.h does)
+    // Loop closing: project with a similarity transform (ORBmatcher.cc:430-528).
+    template <class KeyFrameT, class MapPointT>
+    int SearchByProjection(KeyFrameT *pKF, Sophus::Sim3<float> &Scw, const std::vector<MapPointT *> &vpPoints,
+                           std::vector<MapPointT *> &vpMatched, int th, float ratioHamming = 1.0);
+    // Place recognition (ORBmatcher.cc:530-641).
+    template <class KeyFrameT, class MapPointT>
+    int SearchByProjection(KeyFrameT *pKF, Sophus::Sim3<float> &Scw, const std::vector<MapPointT *> &vpPoints,
+                           const std::vector<KeyFrameT *> &vpPointsKFs, std::vector<MapPointT *> &vpMatched,
+                           std::vector<KeyFrameT *> &vpMatchedKF, int th, float ratioHamming = 1.0);
+    // ORBmatcher.cc:1448-1665
+    template <class KeyFrameT, class MapPointT>
+    int SearchBySim3(KeyFrameT *pKF1, KeyFrameT *pKF2, std::vector<MapPointT *> &vpMatches12, const Sophus::Sim3f &S12,
+                     const float th);
+    // ORBmatcher.cc:1337-1446
+    template <class KeyFrameT, class MapPointT>
+    int Fuse(KeyFrameT *pKF, Sophus::Sim3f &Scw, const std::vector<MapPointT *> &vpPoints, float th,
+             std::vector<MapPointT *> &vpReplacePoint);
+#endif
+
+    // Matching to triangulate new MapPoints, epipolar constraint (ORBmatcher.cc:902-1146; pinhole, mpCamera2 == NULL).
+    template <class KeyFrameT>
+    int SearchForTriangulation(KeyFrameT *pKF1, KeyFrameT *pKF2, std::vector<std::pair<size_t, size_t>> &vMatchedPairs,
+                               const bool bOnlyStereo, const bool bCoarse = false);
 
 public:
     static const int TH_LOW = 50;
@@ -120,6 +162,42 @@ protected:
         vsg_frame *h = nullptr;
         ~FrameGuard() { vsg_frame_destroy(h); }
     };
+    template <class FV>
+    static void FlattenFeatVec(const FV &fv, std::vector<int32_t> &nodes, std::vector<int32_t> &ptr, std::vector<int32_t> &idx) {
+        ptr.push_back(0);
+        for (const auto &kv : fv) {           // DBoW2::FeatureVector = std::map<NodeId, std::vector<unsigned>>
+            nodes.push_back((int32_t)kv.first);
+            for (unsigned v : kv.second) idx.push_back((int32_t)v);
+            ptr.push_back((int32_t)idx.size());
+        }
+    }
+    template <class MapPointT>
+    static void CopyDescriptor(MapPointT *pMP, std::vector<uint8_t> &desc, size_t i) {
+        const cv::Mat d = pMP->GetDescriptor();
+        std::memcpy(&desc[i * 32], d.ptr(0), 32);
+    }
+    template <class KeyFrameT>
+    static void RequireSingleCameraKF(const KeyFrameT &KF) {
+        if (KF.NLeft != -1)
+            throw std::runtime_error("vsg ORBmatcher: two-camera keyframes (NLeft != -1) are not supported by the CUDA path");
+    }
+    // The gates the Sim3 / Fuse projections share between the depth test and GetFeaturesInArea
+    // (e.g. ORBmatcher.cc:468-486): scale-invariance range, viewing angle, predicted level.
+    template <class MapPointT, class KeyFrameT, class Vec3T>
+    static bool DistanceAndNormalGates(MapPointT *pMP, KeyFrameT *pKF, const Vec3T &p3Dw, const Vec3T &Ow, bool bCheckNormal,
+                                       vsg_search_point &p) {
+        const float maxDistance = pMP->GetMaxDistanceInvariance();
+        const float minDistance = pMP->GetMinDistanceInvariance();
+        Vec3T PO = p3Dw - Ow;
+        const float dist = PO.norm();
+        if (dist < minDistance || dist > maxDistance) return false;
+        if (bCheckNormal) {
+            Vec3T Pn = pMP->GetNormal();
+            if (PO.dot(Pn) < 0.5 * dist) return false;
+        }
+        p.level = pMP->PredictScale(dist, pKF);
+        return true;
+    }
     template <class FrameT>
     static void RequireSingleCamera(const FrameT &F) {
         if (F.Nleft != -1)
@@ -265,6 +343,375 @@ int ORBmatcher::SearchForInitialization(FrameT &F1, FrameT &F2, std::vector<cv::
     Check(vsg_search_for_initialization(Workspace(), &f1.view, fr2.h, reinterpret_cast<float *>(vbPrevMatched.data()),
                                         windowSize, mfNNratio, mbCheckOrientation ? 1 : 0, vnMatches12.data(), &nmatches),
           "vsg_search_for_initialization");
+    return nmatches;
+}
+
+// ---- relocalisation (ORBmatcher.cc:1880-2000) ----
+template <class FrameT, class KeyFrameT, class MapPointT>
+int ORBmatcher::SearchByProjection(FrameT &CurrentFrame, KeyFrameT *pKF, const std::set<MapPointT *> &sAlreadyFound,
+                                   const float th, const int ORBdist) {
+    RequireSingleCamera(CurrentFrame);
+    Flat flat;
+    Flatten(CurrentFrame, flat);
+    FrameGuard fr;
+    Check(vsg_frame_create(Workspace(), &flat.view, &fr.h), "vsg_frame_create");
+    const auto Tcw = CurrentFrame.GetPose();
+    const auto Ow = Tcw.inverse().translation();
+    const std::vector<MapPointT *> vpMPs = pKF->GetMapPointMatches();
+    const int n = (int)vpMPs.size(), N = flat.view.n;
+    std::vector<vsg_search_point> pts(n);
+    std::vector<uint8_t> desc((size_t)n * 32, 0);
+    for (int i = 0; i < n; ++i) {
+        vsg_search_point &p = pts[i];
+        std::memset(&p, 0, sizeof(p));
+        MapPointT *pMP = vpMPs[i];
+        if (!pMP || pMP->isBad() || sAlreadyFound.count(pMP)) continue;               // :1898-1902
+        const auto x3Dw = pMP->GetWorldPos();
+        const auto x3Dc = Tcw * x3Dw;
+        const auto uv = CurrentFrame.mpCamera->project(x3Dc);
+        if (uv(0) < CurrentFrame.mnMinX || uv(0) > CurrentFrame.mnMaxX) continue;
+        if (uv(1) < CurrentFrame.mnMinY || uv(1) > CurrentFrame.mnMaxY) continue;
+        const auto PO = x3Dw - Ow;                                                     // :1915-1925
+        const float dist3D = PO.norm();
+        const float maxDistance = pMP->GetMaxDistanceInvariance();
+        const float minDistance = pMP->GetMinDistanceInvariance();
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        p.level = pMP->PredictScale(dist3D, &CurrentFrame);
+        p.u = uv(0); p.v = uv(1);
+        p.angle = pKF->mvKeysUn[i].angle;
+        p.valid = 1;
+        CopyDescriptor(pMP, desc, (size_t)i);
+    }
+    std::vector<uint8_t> occupied(N, 0);
+    for (int i = 0; i < N; ++i) occupied[i] = CurrentFrame.mvpMapPoints[i] ? 1 : 0;   // :1939
+    std::vector<int32_t> assign(N, -1);
+    int nmatches = 0;
+    Check(vsg_search_by_projection_reloc(Workspace(), fr.h, occupied.data(), n, pts.data(), desc.data(), th, ORBdist,
+                                         mbCheckOrientation ? 1 : 0, assign.data(), &nmatches), "vsg_search_by_projection_reloc");
+    for (int i = 0; i < N; ++i) {
+        if (assign[i] >= 0) CurrentFrame.mvpMapPoints[i] = vpMPs[assign[i]];           // :1954
+        else if (assign[i] == -2) CurrentFrame.mvpMapPoints[i] = nullptr;              // :1989
+    }
+    return nmatches;
+}
+
+// ---- SearchByBoW(KF, KF) (ORBmatcher.cc:758-900) ----
+template <class KeyFrameT, class MapPointT>
+int ORBmatcher::SearchByBoW(KeyFrameT *pKF1, KeyFrameT *pKF2, std::vector<MapPointT *> &vpMatches12) {
+    RequireSingleCameraKF(*pKF1);
+    RequireSingleCameraKF(*pKF2);
+    const std::vector<MapPointT *> vpMapPoints1 = pKF1->GetMapPointMatches();
+    const std::vector<MapPointT *> vpMapPoints2 = pKF2->GetMapPointMatches();
+    vpMatches12 = std::vector<MapPointT *>(vpMapPoints1.size(), static_cast<MapPointT *>(nullptr));
+    Flat k1, k2;
+    Flatten(*pKF1, k1);
+    Flatten(*pKF2, k2);
+    std::vector<uint8_t> v1(k1.view.n, 0), v2(k2.view.n, 0);
+    for (int i = 0; i < k1.view.n; ++i) v1[i] = vpMapPoints1[i] && !vpMapPoints1[i]->isBad();   // :800-804
+    for (int i = 0; i < k2.view.n; ++i) v2[i] = vpMapPoints2[i] && !vpMapPoints2[i]->isBad();   // :820-826
+    std::vector<int32_t> n1, p1, i1, n2, p2, i2;
+    FlattenFeatVec(pKF1->mFeatVec, n1, p1, i1);
+    FlattenFeatVec(pKF2->mFeatVec, n2, p2, i2);
+    std::vector<int32_t> m12(k1.view.n, -1);
+    int nmatches = 0;
+    Check(vsg_search_by_bow_kf(Workspace(), &k1.view, v1.data(), &k2.view, v2.data(), (int)n1.size(), n1.data(), p1.data(),
+                               i1.data(), (int)n2.size(), n2.data(), p2.data(), i2.data(), mfNNratio,
+                               mbCheckOrientation ? 1 : 0, m12.data(), &nmatches), "vsg_search_by_bow_kf");
+    for (int i = 0; i < k1.view.n; ++i)
+        if (m12[i] >= 0) vpMatches12[i] = vpMapPoints2[m12[i]];                           // :847
+    return nmatches;
+}
+
+// ---- Fuse(KF, vpMapPoints, th) (ORBmatcher.cc:1148-1335) ----
+template <class KeyFrameT, class MapPointT>
+int ORBmatcher::Fuse(KeyFrameT *pKF, const std::vector<MapPointT *> &vpMapPoints, const float th, const bool bRight) {
+    RequireSingleCameraKF(*pKF);
+    if (bRight) throw std::runtime_error("vsg ORBmatcher::Fuse: bRight needs a two-camera keyframe (not supported)");
+    Flat flat;
+    Flatten(*pKF, flat);
+    FrameGuard fr;
+    Check(vsg_frame_create(Workspace(), &flat.view, &fr.h), "vsg_frame_create");
+    const auto Tcw = pKF->GetPose();
+    const auto Ow = pKF->GetCameraCenter();
+    const float &bf = pKF->mbf;
+    const int nMPs = (int)vpMapPoints.size();
+    std::vector<vsg_search_point> pts(nMPs);
+    std::vector<uint8_t> desc((size_t)nMPs * 32, 0);
+    for (int i = 0; i < nMPs; ++i) {
+        vsg_search_point &p = pts[i];
+        std::memset(&p, 0, sizeof(p));
+        MapPointT *pMP = vpMapPoints[i];
+        if (!pMP) continue;
+        // isBad() / IsInKeyFrame() change while the reference's loop runs: they are evaluated in the replay below,
+        // at the same point of the iteration order; the search itself does not depend on them.
+        const auto p3Dw = pMP->GetWorldPos();
+        const auto p3Dc = Tcw * p3Dw;
+        if (p3Dc(2) < 0.0f) continue;
+        const float invz = 1 / p3Dc(2);
+        const auto uv = pKF->mpCamera->project(p3Dc);
+        if (!pKF->IsInImage(uv(0), uv(1))) continue;
+        p.ur = uv(0) - bf * invz;
+        if (!DistanceAndNormalGates(pMP, pKF, p3Dw, Ow, true, p)) continue;
+        p.u = uv(0); p.v = uv(1);
+        p.valid = 1;
+        CopyDescriptor(pMP, desc, (size_t)i);
+    }
+    std::vector<int32_t> best(nMPs, -1);
+    Check(vsg_fuse_search(Workspace(), fr.h, nMPs, pts.data(), desc.data(), th, pKF->mvInvLevelSigma2.data(), 0, best.data(),
+                          nullptr), "vsg_fuse_search");
+    int nFused = 0;
+    for (int i = 0; i < nMPs; ++i) {                                                        // :1173-1332 in order
+        MapPointT *pMP = vpMapPoints[i];
+        if (!pMP || pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;
+        if (best[i] < 0) continue;
+        MapPointT *pMPinKF = pKF->GetMapPoint(best[i]);
+        if (pMPinKF) {
+            if (!pMPinKF->isBad()) {
+                if (pMPinKF->Observations() > pMP->Observations()) pMP->Replace(pMPinKF);
+                else pMPinKF->Replace(pMP);
+            }
+        } else {
+            pMP->AddObservation(pKF, best[i]);
+            pKF->AddMapPoint(pMP, best[i]);
+        }
+        nFused++;
+    }
+    return nFused;
+}
+
+#ifdef SOPHUS_SIM3_HPP
+// ---- SearchByProjection(KF, Scw, vpPoints, vpMatched, th, ratioHamming) (ORBmatcher.cc:430-528) ----
+template <class KeyFrameT, class MapPointT>
+int ORBmatcher::SearchByProjection(KeyFrameT *pKF, Sophus::Sim3<float> &Scw, const std::vector<MapPointT *> &vpPoints,
+                                   std::vector<MapPointT *> &vpMatched, int th, float ratioHamming) {
+    std::vector<KeyFrameT *> none, none_out;
+    return SearchByProjection(pKF, Scw, vpPoints, none, vpMatched, none_out, th, ratioHamming);
+}
+
+// ---- ... with vpPointsKFs / vpMatchedKF (ORBmatcher.cc:530-641; the projection is the pinhole fx, fy, cx, cy one) ----
+template <class KeyFrameT, class MapPointT>
+int ORBmatcher::SearchByProjection(KeyFrameT *pKF, Sophus::Sim3<float> &Scw, const std::vector<MapPointT *> &vpPoints,
+                                   const std::vector<KeyFrameT *> &vpPointsKFs, std::vector<MapPointT *> &vpMatched,
+                                   std::vector<KeyFrameT *> &vpMatchedKF, int th, float ratioHamming) {
+    RequireSingleCameraKF(*pKF);
+    const bool bWithKFs = !vpPointsKFs.empty();
+    Flat flat;
+    Flatten(*pKF, flat);
+    FrameGuard fr;
+    Check(vsg_frame_create(Workspace(), &flat.view, &fr.h), "vsg_frame_create");
+    const float &fx = pKF->fx, &fy = pKF->fy, &cx = pKF->cx, &cy = pKF->cy;
+    Sophus::SE3f Tcw = Sophus::SE3f(Scw.rotationMatrix(), Scw.translation() / Scw.scale());
+    const auto Ow = Tcw.inverse().translation();
+    std::set<MapPointT *> spAlreadyFound(vpMatched.begin(), vpMatched.end());
+    spAlreadyFound.erase(static_cast<MapPointT *>(nullptr));
+    const int n = (int)vpPoints.size(), N = flat.view.n;
+    std::vector<vsg_search_point> pts(n);
+    std::vector<uint8_t> desc((size_t)n * 32, 0);
+    for (int iMP = 0; iMP < n; ++iMP) {
+        vsg_search_point &p = pts[iMP];
+        std::memset(&p, 0, sizeof(p));
+        MapPointT *pMP = vpPoints[iMP];
+        if (pMP->isBad() || spAlreadyFound.count(pMP)) continue;
+        const auto p3Dw = pMP->GetWorldPos();
+        const auto p3Dc = Tcw * p3Dw;
+        if (p3Dc(2) < 0.0) continue;
+        float u, v;
+        if (bWithKFs) {                                                                     // :567-573
+            const float invz = 1 / p3Dc(2);
+            const float x = p3Dc(0) * invz, y = p3Dc(1) * invz;
+            u = fx * x + cx; v = fy * y + cy;
+        } else {                                                                            // :461
+            const auto uv = pKF->mpCamera->project(p3Dc);
+            u = uv(0); v = uv(1);
+        }
+        if (!pKF->IsInImage(u, v)) continue;
+        if (!DistanceAndNormalGates(pMP, pKF, p3Dw, Ow, true, p)) continue;
+        p.u = u; p.v = v;
+        p.valid = 1;
+        CopyDescriptor(pMP, desc, (size_t)iMP);
+    }
+    std::vector<uint8_t> matched(N, 0);
+    for (int i = 0; i < N; ++i) matched[i] = vpMatched[i] ? 1 : 0;
+    std::vector<int32_t> assign(N, -1);
+    int nmatches = 0;
+    Check(vsg_search_by_projection_sim3(Workspace(), fr.h, matched.data(), n, pts.data(), desc.data(), th, ratioHamming,
+                                        assign.data(), &nmatches), "vsg_search_by_projection_sim3");
+    for (int i = 0; i < N; ++i)
+        if (assign[i] >= 0) {
+            vpMatched[i] = vpPoints[assign[i]];                                              // :522 / :634
+            if (bWithKFs) vpMatchedKF[i] = vpPointsKFs[assign[i]];                           // :635
+        }
+    return nmatches;
+}
+
+// ---- SearchBySim3 (ORBmatcher.cc:1448-1665) ----
+template <class KeyFrameT, class MapPointT>
+int ORBmatcher::SearchBySim3(KeyFrameT *pKF1, KeyFrameT *pKF2, std::vector<MapPointT *> &vpMatches12, const Sophus::Sim3f &S12,
+                             const float th) {
+    RequireSingleCameraKF(*pKF1);
+    RequireSingleCameraKF(*pKF2);
+    const float &fx = pKF1->fx, &fy = pKF1->fy, &cx = pKF1->cx, &cy = pKF1->cy;
+    Sophus::SE3f T1w = pKF1->GetPose();
+    Sophus::SE3f T2w = pKF2->GetPose();
+    Sophus::Sim3f S21 = S12.inverse();
+    const std::vector<MapPointT *> vpMapPoints1 = pKF1->GetMapPointMatches();
+    const std::vector<MapPointT *> vpMapPoints2 = pKF2->GetMapPointMatches();
+    const int N1 = (int)vpMapPoints1.size(), N2 = (int)vpMapPoints2.size();
+    std::vector<bool> vbAlreadyMatched1(N1, false), vbAlreadyMatched2(N2, false);
+    for (int i = 0; i < N1; i++) {                                                          // :1472-1482
+        MapPointT *pMP = vpMatches12[i];
+        if (pMP) {
+            vbAlreadyMatched1[i] = true;
+            int idx2 = std::get<0>(pMP->GetIndexInKeyFrame(pKF2));
+            if (idx2 >= 0 && idx2 < N2) vbAlreadyMatched2[idx2] = true;
+        }
+    }
+    Flat f1, f2;
+    Flatten(*pKF1, f1);
+    Flatten(*pKF2, f2);
+    FrameGuard fr1, fr2;
+    Check(vsg_frame_create(Workspace(), &f1.view, &fr1.h), "vsg_frame_create");
+    Check(vsg_frame_create(Workspace(), &f2.view, &fr2.h), "vsg_frame_create");
+    std::vector<vsg_search_point> pts1(N1), pts2(N2);
+    std::vector<uint8_t> desc1((size_t)N1 * 32, 0), desc2((size_t)N2 * 32, 0);
+    auto project = [&](const std::vector<MapPointT *> &vp, const std::vector<bool> &already, const Sophus::SE3f &Tw,
+                       const Sophus::Sim3f &S, KeyFrameT *pTarget, std::vector<vsg_search_point> &pts, std::vector<uint8_t> &desc) {
+        for (int i = 0; i < (int)vp.size(); ++i) {
+            vsg_search_point &p = pts[i];
+            std::memset(&p, 0, sizeof(p));
+            MapPointT *pMP = vp[i];
+            if (!pMP || already[i]) continue;
+            if (pMP->isBad()) continue;
+            const auto p3Dw = pMP->GetWorldPos();
+            const auto p3Dca = Tw * p3Dw;
+            const auto p3Dcb = S * p3Dca;
+            if (p3Dcb(2) < 0.0) continue;
+            const float invz = 1.0 / p3Dcb(2);
+            const float x = p3Dcb(0) * invz, y = p3Dcb(1) * invz;
+            const float u = fx * x + cx, v = fy * y + cy;
+            if (!pTarget->IsInImage(u, v)) continue;
+            const float maxDistance = pMP->GetMaxDistanceInvariance();
+            const float minDistance = pMP->GetMinDistanceInvariance();
+            const float dist3D = p3Dcb.norm();
+            if (dist3D < minDistance || dist3D > maxDistance) continue;
+            p.level = pMP->PredictScale(dist3D, pTarget);
+            p.u = u; p.v = v;
+            p.valid = 1;
+            CopyDescriptor(pMP, desc, (size_t)i);
+        }
+    };
+    project(vpMapPoints1, vbAlreadyMatched1, T1w, S21, pKF2, pts1, desc1);                  // :1488-1560
+    project(vpMapPoints2, vbAlreadyMatched2, T2w, S12, pKF1, pts2, desc2);                  // :1563-1635
+    std::vector<int32_t> m12(N1, -1);
+    int nFound = 0;
+    Check(vsg_search_by_sim3(Workspace(), fr1.h, fr2.h, N1, pts1.data(), desc1.data(), N2, pts2.data(), desc2.data(), th,
+                             m12.data(), &nFound), "vsg_search_by_sim3");
+    for (int i1 = 0; i1 < N1; ++i1)
+        if (m12[i1] >= 0) vpMatches12[i1] = vpMapPoints2[m12[i1]];                           // :1648
+    return nFound;
+}
+
+// ---- Fuse(KF, Scw, vpPoints, th, vpReplacePoint) (ORBmatcher.cc:1337-1446) ----
+template <class KeyFrameT, class MapPointT>
+int ORBmatcher::Fuse(KeyFrameT *pKF, Sophus::Sim3f &Scw, const std::vector<MapPointT *> &vpPoints, float th,
+                     std::vector<MapPointT *> &vpReplacePoint) {
+    RequireSingleCameraKF(*pKF);
+    Flat flat;
+    Flatten(*pKF, flat);
+    FrameGuard fr;
+    Check(vsg_frame_create(Workspace(), &flat.view, &fr.h), "vsg_frame_create");
+    Sophus::SE3f Tcw = Sophus::SE3f(Scw.rotationMatrix(), Scw.translation() / Scw.scale());
+    const auto Ow = Tcw.inverse().translation();
+    const std::set<MapPointT *> spAlreadyFound = pKF->GetMapPoints();
+    const int nPoints = (int)vpPoints.size();
+    std::vector<vsg_search_point> pts(nPoints);
+    std::vector<uint8_t> desc((size_t)nPoints * 32, 0);
+    for (int iMP = 0; iMP < nPoints; ++iMP) {
+        vsg_search_point &p = pts[iMP];
+        std::memset(&p, 0, sizeof(p));
+        MapPointT *pMP = vpPoints[iMP];
+        if (spAlreadyFound.count(pMP)) continue;            // isBad() is re-checked in order below
+        const auto p3Dw = pMP->GetWorldPos();
+        const auto p3Dc = Tcw * p3Dw;
+        if (p3Dc(2) < 0.0f) continue;
+        const auto uv = pKF->mpCamera->project(p3Dc);
+        if (!pKF->IsInImage(uv(0), uv(1))) continue;
+        if (!DistanceAndNormalGates(pMP, pKF, p3Dw, Ow, true, p)) continue;
+        p.u = uv(0); p.v = uv(1);
+        p.valid = 1;
+        CopyDescriptor(pMP, desc, (size_t)iMP);
+    }
+    std::vector<int32_t> best(nPoints, -1);
+    Check(vsg_fuse_search(Workspace(), fr.h, nPoints, pts.data(), desc.data(), th, nullptr, 1, best.data(), nullptr),
+          "vsg_fuse_search");
+    int nFused = 0;
+    for (int iMP = 0; iMP < nPoints; ++iMP) {                                               // :1353-1442 in order
+        MapPointT *pMP = vpPoints[iMP];
+        if (pMP->isBad() || best[iMP] < 0) continue;
+        MapPointT *pMPinKF = pKF->GetMapPoint(best[iMP]);
+        if (pMPinKF) {
+            if (!pMPinKF->isBad()) vpReplacePoint[iMP] = pMPinKF;
+        } else {
+            pMP->AddObservation(pKF, best[iMP]);
+            pKF->AddMapPoint(pMP, best[iMP]);
+        }
+        nFused++;
+    }
+    return nFused;
+}
+#endif  // SOPHUS_SIM3_HPP
+
+// ---- SearchForTriangulation (ORBmatcher.cc:902-1146) ----
+template <class KeyFrameT>
+int ORBmatcher::SearchForTriangulation(KeyFrameT *pKF1, KeyFrameT *pKF2, std::vector<std::pair<size_t, size_t>> &vMatchedPairs,
+                                       const bool bOnlyStereo, const bool bCoarse) {
+    RequireSingleCameraKF(*pKF1);
+    RequireSingleCameraKF(*pKF2);
+    if (pKF1->mpCamera2 || pKF2->mpCamera2)
+        throw std::runtime_error("vsg ORBmatcher::SearchForTriangulation: two-camera keyframes are not supported");
+    // epipole in the second image and the fundamental matrix of Pinhole::epipolarConstrain (Pinhole.cpp:120-124),
+    // built once with the reference's own Eigen expressions (it does not depend on the keypoints)
+    const auto T1w = pKF1->GetPose();
+    const auto T2w = pKF2->GetPose();
+    const auto Tw2 = pKF2->GetPoseInverse();
+    const auto Cw = pKF1->GetCameraCenter();
+    const auto C2 = T2w * Cw;
+    const auto ep = pKF2->mpCamera->project(C2);
+    const auto T12 = T1w * Tw2;
+    const auto R12 = T12.rotationMatrix();
+    const auto t12 = T12.translation();
+    float f12[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (!bCoarse) {
+        typename std::decay<decltype(R12)>::type t12x;
+        t12x << 0, -t12(2), t12(1), t12(2), 0, -t12(0), -t12(1), t12(0), 0;                 // Sophus::SO3f::hat(t12)
+        const auto K1 = pKF1->mpCamera->toK_();
+        const auto K2 = pKF2->mpCamera->toK_();
+        const typename std::decay<decltype(R12)>::type F12 = K1.transpose().inverse() * t12x * R12 * K2.inverse();
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) f12[3 * r + c] = F12(r, c);
+    }
+    const float epf[2] = {ep(0), ep(1)};
+    Flat k1, k2;
+    Flatten(*pKF1, k1);
+    Flatten(*pKF2, k2);
+    std::vector<uint8_t> h1(k1.view.n, 0), h2(k2.view.n, 0);
+    for (int i = 0; i < k1.view.n; ++i) h1[i] = pKF1->GetMapPoint(i) ? 1 : 0;               // :968
+    for (int i = 0; i < k2.view.n; ++i) h2[i] = pKF2->GetMapPoint(i) ? 1 : 0;               // :998
+    std::vector<int32_t> n1, p1, i1, n2, p2, i2;
+    FlattenFeatVec(pKF1->mFeatVec, n1, p1, i1);
+    FlattenFeatVec(pKF2->mFeatVec, n2, p2, i2);
+    std::vector<int32_t> m12(k1.view.n, -1);
+    int nmatches = 0;
+    Check(vsg_search_for_triangulation(Workspace(), &k1.view, h1.data(), &k2.view, h2.data(), (int)n1.size(), n1.data(),
+                                       p1.data(), i1.data(), (int)n2.size(), n2.data(), p2.data(), i2.data(),
+                                       bOnlyStereo ? 1 : 0, bCoarse ? 1 : 0, f12, epf, pKF2->mvLevelSigma2.data(),
+                                       mbCheckOrientation ? 1 : 0, m12.data(), &nmatches), "vsg_search_for_triangulation");
+    vMatchedPairs.clear();
+    vMatchedPairs.reserve(nmatches);
+    for (size_t i = 0, iend = m12.size(); i < iend; i++) {                                  // :1136-1143
+        if (m12[i] < 0) continue;
+        vMatchedPairs.push_back(std::make_pair(i, (size_t)m12[i]));
+    }
     return nmatches;
 }
 
