@@ -131,7 +131,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     cores = host_threads()
-    per_step = max(cores * 4, 32)
+    per_step = max(cores * 16, 64)
     from oracle import oracle as orc
     frames = make_frames(per_step, 9000)
     for _ in range(args.warmup):
@@ -153,6 +153,36 @@ def run_reference(args, rank):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def latency_extras(torch, lib, device):
+    """One frame per call through vsg_extract (the reference's per-frame operator() use): pinned frame in, pinned
+    keypoints/descriptors out, host clock around each call."""
+    from visual_sgraphs_b200._lib import check, ptr
+    from visual_sgraphs_b200.extractor import ORBextractor
+    import ctypes as C
+    ex = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=device, max_batch=1)
+    cap = ex.max_keypoints(W, H)
+    frames = torch.from_numpy(make_frames(8, 4000)).pin_memory()
+    kp = torch.zeros((cap, 28), dtype=torch.uint8).pin_memory()
+    de = torch.zeros((cap, 32), dtype=torch.uint8).pin_memory()
+    n, mono = C.c_int(0), C.c_int(0)
+    fn = frames.numpy()
+
+    def one(i):
+        check(lib.vsg_extract(ex._h, ptr(fn[i % 8]), W, H, W, 0, 0, ptr(kp), ptr(de), cap, C.byref(n), C.byref(mono)))
+
+    for i in range(20):
+        one(i)
+    ts = []
+    for i in range(200):
+        t0 = time.perf_counter()
+        one(i)
+        ts.append(time.perf_counter() - t0)
+    ex.close()
+    ts = np.array(ts) * 1e3
+    return {"ms_median": float(np.median(ts)), "ms_p95": float(np.percentile(ts, 95)),
+            "frames_per_s": float(1e3 / np.mean(ts)), "calls": 200}
 
 
 def matching_extras(torch, device):
@@ -193,6 +223,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=512, help="frames per step per GPU")
     ap.add_argument("--no-extras", action="store_true", help="skip the matching and cpu-baseline extras")
+    ap.add_argument("--no-stage-profile", action="store_true", help="(experiments) no per-stage events in the timed region")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -236,7 +267,7 @@ def main():
         ex.extract_batch_dev(dev_frames, kps_d, desc_d, n_d, mono_d)
     ex.sync()
     sampler = ClockSampler(local_rank)
-    ex.profile(True)
+    ex.profile(not args.no_stage_profile)
     launches0 = lib.vsg_launch_count()
     barrier()
     sampler.start()
@@ -274,20 +305,23 @@ def main():
         check(lib.vsg_extract_batch(handles[i]._h, ptr(host_np[b:e]), e - b, W, H, W, W * H, 0, 0, ptr(kp), ptr(de), cap,
                                     ptr(nn), ptr(mm)))
 
-    def e2e_step():
-        ths = [threading.Thread(target=e2e_part, args=(i,)) for i in range(len(parts))]
+    def e2e_worker(i, steps):
+        for _ in range(steps):
+            e2e_part(i)
+
+    def e2e_run(steps):
+        # each handle streams its half of every step back to back; the halves are not re-synchronised between steps
+        ths = [threading.Thread(target=e2e_worker, args=(i, steps)) for i in range(len(parts))]
         for t in ths:
             t.start()
         for t in ths:
             t.join()
 
-    for _ in range(2):
-        e2e_step()
+    e2e_run(2)
     barrier()
     launches_e2e0 = lib.vsg_launch_count()
     t0 = time.perf_counter()
-    for _ in range(K):
-        e2e_step()
+    e2e_run(K)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
@@ -308,7 +342,7 @@ def main():
         peak, peak_src = measured_peaks()
         dominant = max(stage_ms, key=lambda k: stage_ms[k])
         roof_stage = dominant if stages_bytes[dominant] > 0 else "fast"
-        dur_ms = stage_ms[roof_stage] / max(runs, 1)
+        dur_ms = stage_ms[roof_stage] / max(runs, 1) if runs else elapsed_ms / K
         achieved = stages_bytes[roof_stage] * B / (dur_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
@@ -335,13 +369,14 @@ def main():
         }
         if world == 1 and not args.no_extras:
             cores = host_threads()
-            nfr = max(4 * cores, 64)
+            nfr = 256 * cores                       # ~10 s of CPU work on all host threads
             v_all, secs_all, _ = cpu_port_throughput(nfr, cores)
-            v_one, _, _ = cpu_port_throughput(32, 1)
+            v_one, _, _ = cpu_port_throughput(96, 1)
             line["cpu_baseline"] = {"value": v_all, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "%d frames of the same workload, %d threads (one extractor per thread), %.1f s" %
                                               (nfr, cores, secs_all),
                                     "single_thread_value": v_one}
+            line["single_frame_latency"] = latency_extras(torch, lib, local_rank)
             line["matching"] = matching_extras(torch, local_rank)
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -174,3 +174,37 @@ def test_full_size_properties_without_oracle():
         lx = k1["x"] / scale[k1["octave"]]
         assert (lx >= 18.99).all()
         assert (k1["size"] == np.floor(31 * scale[k1["octave"]])).all()
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_chunked_pipeline_matches_single_stream(oracle, monkeypatch, pinned):
+    """vsg_extract_batch cuts large host batches into chunks that rotate over three CUDA streams (H2D / kernels / D2H
+    overlap).  Every frame must come out exactly as from a one-frame call, whatever chunk it lands in."""
+    torch = pytest.importorskip("torch")
+    monkeypatch.setenv("VSG_CHUNK_FRAMES", "3")          # read when the handle is created
+    base = synth_sequence(4, 640, 480, first_seed=7000)
+    frames = np.stack([np.roll(base[i % 4], 5 * (i // 4), 1) for i in range(11)])   # chunks of 3, 3, 3, 2
+    ex = _extractor(1000, max_batch=11)
+    if pinned:
+        from visual_sgraphs_b200._lib import check, ptr
+        cap = ex.max_keypoints(640, 480)
+        t_frames = torch.from_numpy(frames).pin_memory()
+        kps = torch.zeros((11, cap + 5, 28), dtype=torch.uint8).pin_memory()       # capacity > out_cap: strided D2H
+        desc = torch.zeros((11, cap + 5, 32), dtype=torch.uint8).pin_memory()
+        n, mono = np.zeros(11, np.int32), np.zeros(11, np.int32)
+        check(ex._L.vsg_extract_batch(ex._h, ptr(t_frames), 11, 640, 480, 640, 640 * 480, 0, 0, ptr(kps), ptr(desc), cap + 5,
+                                      ptr(n), ptr(mono)))
+        from visual_sgraphs_b200._lib import KEYPOINT_DTYPE
+        res = [(int(mono[f]), kps[f, :n[f]].numpy().copy().view(KEYPOINT_DTYPE).reshape(-1), desc[f, :n[f]].numpy().copy())
+               for f in range(11)]
+    else:
+        res = ex.extract_batch(frames)
+    single = _extractor(1000)
+    orc = oracle.OracleExtractor(1000)
+    for f in range(11):
+        m, k, d = single(frames[f])
+        assert res[f][0] == m and res[f][1].tobytes() == k.tobytes() and np.array_equal(res[f][2], d), f
+    for f in (0, 4, 10):
+        _compare_outputs(res[f], orc(frames[f]), "chunked frame %d" % f)
+    orc(frames[7])
+    assert np.array_equal(ex.pyramid_level(3, frame=7), orc.level(3))

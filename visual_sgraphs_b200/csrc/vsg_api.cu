@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -49,6 +50,13 @@ struct vsg_extractor {
     int device = 0;
     int max_batch = 1;
     cudaStream_t stream = nullptr;
+    // Host-pointer batches are cut into chunks that rotate over `stream` and these two, so that one chunk's H2D,
+    // another's kernels and a third's D2H overlap (each chunk works on its own frame range of the scratch buffers).
+    static constexpr int kAuxStreams = 2;
+    cudaStream_t aux[kAuxStreams] = {nullptr, nullptr};
+    int chunk_frames = 64;
+    int dev_chunk_frames = 0;          // device-resident batches: 0 = one pass on `stream`
+    cudaEvent_t fork_ev = nullptr, join_ev[kAuxStreams] = {nullptr, nullptr};
     vsg_orb_params p{};
     std::vector<float> scale, inv_scale, sigma2, inv_sigma2;
     std::vector<int> quota;
@@ -305,16 +313,24 @@ vsg_status configure_shape(vsg_extractor *ex, int w, int h) {
     return VSG_OK;
 }
 
-// The device pipeline for `nframes` frames whose level 0 is at (lvl0_base, lvl0_pitch, lvl0_stride).
-vsg_status run_pipeline(vsg_extractor *ex, const uint8_t *lvl0_base, int lvl0_pitch, int64_t lvl0_stride, int nframes,
-                        int lap_x0, int lap_x1, vsg_keypoint *kps_dev, uint8_t *desc_dev, int out_cap, int *n_dev,
-                        int *mono_dev) {
-    const FrameGeom &g = ex->g;
-    cudaStream_t s = ex->stream;
-    ex->lvl0_base = lvl0_base; ex->lvl0_pitch = lvl0_pitch; ex->lvl0_stride = lvl0_stride; ex->last_nframes = nframes;
-    CK(cudaMemsetAsync(ex->cand_count, 0, (size_t)nframes * g.nlevels * sizeof(int), s));
+// The device pipeline for frames [f0, f0 + nframes) of the handle's scratch buffers, on stream `s`.  Level 0 of frame
+// f0 is at lvl0_base; the output pointers address frame f0 as well.  Chunks of one batch run this concurrently on
+// different streams: every per-frame array is addressed through a geometry whose offsets are shifted to frame f0.
+vsg_status run_pipeline(vsg_extractor *ex, cudaStream_t s, int f0, const uint8_t *lvl0_base, int lvl0_pitch,
+                        int64_t lvl0_stride, int nframes, int lap_x0, int lap_x1, vsg_keypoint *kps_dev,
+                        uint8_t *desc_dev, int out_cap, int *n_dev, int *mono_dev) {
+    FrameGeom g = ex->g;
+    for (int l = 0; l < g.nlevels; ++l) {
+        g.lv[l].plane_offset += (int64_t)f0 * g.lv[l].plane_stride;
+        g.lv[l].cand_offset += (int64_t)f0 * g.cand_total;
+    }
+    int *cand_count = ex->cand_count + (size_t)f0 * g.nlevels;
+    int *level_kp_count = ex->level_kp_count + (size_t)f0 * g.nlevels;
+    LevelKp *level_kps = ex->level_kps + (size_t)f0 * g.kp_total;
+    int *slot = ex->slot + (size_t)f0 * g.kp_total;
+    CK(cudaMemsetAsync(cand_count, 0, (size_t)nframes * g.nlevels * sizeof(int), s));
     cudaEvent_t *ev = nullptr;
-    if (ex->profile) {
+    if (ex->profile && s == ex->stream) {
         if (!ex->ev_created) {
             for (int i = 0; i < vsg_extractor::kEvRing; ++i)
                 for (int k = 0; k <= VSG_NUM_STAGES; ++k) CK(cudaEventCreate(&ex->ev[i][k]));
@@ -333,15 +349,15 @@ vsg_status run_pipeline(vsg_extractor *ex, const uint8_t *lvl0_base, int lvl0_pi
         else launch_resize_level(g, l, ex->pyr + P.plane_offset, P.pitch, P.plane_stride, ex->pyr, nframes, s);
     }
     STAGE_MARK(1);
-    launch_fast(g, ex->cells_d, lvl0_base, lvl0_pitch, lvl0_stride, ex->pyr, ex->cand, ex->cand_count, ex->p.ini_th_fast,
+    launch_fast(g, ex->cells_d, lvl0_base, lvl0_pitch, lvl0_stride, ex->pyr, ex->cand, cand_count, ex->p.ini_th_fast,
                 ex->p.min_th_fast, ex->max_cw, ex->max_ch, nframes, s);
     STAGE_MARK(2);
-    launch_octree(g, ex->cand, ex->cand_count, ex->node_of, ex->level_kps, ex->level_kp_count, ex->max_nodes, nframes, s);
+    launch_octree(g, ex->cand, cand_count, ex->node_of, level_kps, level_kp_count, ex->max_nodes, nframes, s);
     STAGE_MARK(3);
     launch_blur(g, lvl0_base, lvl0_pitch, lvl0_stride, ex->pyr, ex->blur, nframes, s);
     STAGE_MARK(4);
-    launch_describe(g, lvl0_base, lvl0_pitch, lvl0_stride, ex->pyr, ex->blur, ex->level_kps, ex->level_kp_count, lap_x0,
-                    lap_x1, kps_dev, desc_dev, out_cap, n_dev, mono_dev, ex->slot, nframes, s);
+    launch_describe(g, lvl0_base, lvl0_pitch, lvl0_stride, ex->pyr, ex->blur, level_kps, level_kp_count, lap_x0,
+                    lap_x1, kps_dev, desc_dev, out_cap, n_dev, mono_dev, slot, nframes, s);
     STAGE_MARK(5);
 #undef STAGE_MARK
     CK(cudaGetLastError());
@@ -396,10 +412,16 @@ vsg_status vsg_extractor_create(const vsg_orb_params *params, int device, int ma
     ex->p = *params;
     build_tables(ex);
     if (!cuda_ok(cudaSetDevice(device), "cudaSetDevice") ||
-        !cuda_ok(cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
+        !cuda_ok(cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking), "cudaStreamCreate") ||
+        !cuda_ok(cudaStreamCreateWithFlags(&ex->aux[0], cudaStreamNonBlocking), "cudaStreamCreate") ||
+        !cuda_ok(cudaStreamCreateWithFlags(&ex->aux[1], cudaStreamNonBlocking), "cudaStreamCreate")) {
         delete ex;
         return VSG_ERR_CUDA;
     }
+    if (const char *e = getenv("VSG_CHUNK_FRAMES")) ex->chunk_frames = std::max(1, atoi(e));
+    if (const char *e = getenv("VSG_DEV_CHUNK_FRAMES")) ex->dev_chunk_frames = std::max(0, atoi(e));
+    cudaEventCreateWithFlags(&ex->fork_ev, cudaEventDisableTiming);
+    for (cudaEvent_t &e : ex->join_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     *out = ex;
     return VSG_OK;
 }
@@ -408,6 +430,11 @@ void vsg_extractor_destroy(vsg_extractor *ex) {
     if (!ex) return;
     cudaSetDevice(ex->device);
     if (ex->stream) { cudaStreamSynchronize(ex->stream); cudaStreamDestroy(ex->stream); }
+    for (cudaStream_t a : ex->aux)
+        if (a) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
+    if (ex->fork_ev) cudaEventDestroy(ex->fork_ev);
+    for (cudaEvent_t e : ex->join_ev)
+        if (e) cudaEventDestroy(e);
     if (ex->ev_created)
         for (int i = 0; i < vsg_extractor::kEvRing; ++i)
             for (int k = 0; k <= VSG_NUM_STAGES; ++k) cudaEventDestroy(ex->ev[i][k]);
@@ -450,19 +477,7 @@ vsg_status vsg_extract_batch(vsg_extractor *ex, const uint8_t *images, int nfram
     const FrameGeom &g = ex->g;
     const LevelGeom &L0 = g.lv[0];
     uint8_t *lvl0 = ex->pyr + L0.plane_offset;
-    if (frame_stride == (size_t)pitch * height && (int64_t)L0.pitch * L0.h == L0.plane_stride) {
-        CK(cudaMemcpy2DAsync(lvl0, L0.pitch, images, pitch, width, (size_t)height * nframes, cudaMemcpyHostToDevice,
-                             ex->stream));
-    } else {
-        for (int f = 0; f < nframes; ++f)
-            CK(cudaMemcpy2DAsync(lvl0 + f * L0.plane_stride, L0.pitch, images + f * frame_stride, pitch, width, height,
-                                 cudaMemcpyHostToDevice, ex->stream));
-    }
-    st = run_pipeline(ex, lvl0, L0.pitch, L0.plane_stride, nframes, lap_x0, lap_x1, ex->kps_d, ex->desc_d, g.out_cap,
-                      ex->n_d, ex->mono_d);
-    if (st != VSG_OK) return st;
-    CK(cudaMemcpyAsync(ex->n_h, ex->n_d, nframes * sizeof(int), cudaMemcpyDeviceToHost, ex->stream));
-    CK(cudaMemcpyAsync(ex->mono_h, ex->mono_d, nframes * sizeof(int), cudaMemcpyDeviceToHost, ex->stream));
+    ex->lvl0_base = lvl0; ex->lvl0_pitch = L0.pitch; ex->lvl0_stride = L0.plane_stride; ex->last_nframes = nframes;
     // Results go straight into the caller's arrays when those are page-locked (one strided D2H each, no
     // host-side copy); otherwise through the handle's pinned staging buffers.
     auto pinned = [](const void *p) {
@@ -473,19 +488,47 @@ vsg_status vsg_extract_batch(vsg_extractor *ex, const uint8_t *images, int nfram
     };
     const bool direct = capacity >= g.out_cap && (!keypoints_out || pinned(keypoints_out)) &&
                         (!descriptors_out || pinned(descriptors_out));
-    if (direct) {
-        if (keypoints_out)
-            CK(cudaMemcpy2DAsync(keypoints_out, (size_t)capacity * sizeof(vsg_keypoint), ex->kps_d,
-                                 (size_t)g.out_cap * sizeof(vsg_keypoint), (size_t)g.out_cap * sizeof(vsg_keypoint),
-                                 nframes, cudaMemcpyDeviceToHost, ex->stream));
-        if (descriptors_out)
-            CK(cudaMemcpy2DAsync(descriptors_out, (size_t)capacity * 32, ex->desc_d, (size_t)g.out_cap * 32,
-                                 (size_t)g.out_cap * 32, nframes, cudaMemcpyDeviceToHost, ex->stream));
-    } else {
-        CK(cudaMemcpyAsync(ex->kps_h, ex->kps_d, (size_t)nframes * g.out_cap * sizeof(vsg_keypoint),
-                           cudaMemcpyDeviceToHost, ex->stream));
-        CK(cudaMemcpyAsync(ex->desc_h, ex->desc_d, (size_t)nframes * g.out_cap * 32, cudaMemcpyDeviceToHost, ex->stream));
+    // Chunked software pipeline: chunk c runs H2D -> kernels -> D2H on stream c mod 3, on its own frame range.
+    const bool chunked = !ex->profile && nframes >= 2 * ex->chunk_frames;
+    const int chunk = chunked ? ex->chunk_frames : nframes;
+    const bool tight = frame_stride == (size_t)pitch * height && (int64_t)L0.pitch * L0.h == L0.plane_stride;
+    int nstreams_used = 0;
+    for (int f0 = 0, c = 0; f0 < nframes; f0 += chunk, ++c) {
+        const int nf = std::min(chunk, nframes - f0);
+        cudaStream_t s = (c % 3 == 0) ? ex->stream : ex->aux[c % 3 - 1];
+        nstreams_used = std::min(3, c + 1);
+        uint8_t *dst0 = lvl0 + (int64_t)f0 * L0.plane_stride;
+        const uint8_t *src0 = images + (size_t)f0 * frame_stride;
+        if (tight) {
+            CK(cudaMemcpy2DAsync(dst0, L0.pitch, src0, pitch, width, (size_t)height * nf, cudaMemcpyHostToDevice, s));
+        } else {
+            for (int f = 0; f < nf; ++f)
+                CK(cudaMemcpy2DAsync(dst0 + f * L0.plane_stride, L0.pitch, src0 + f * frame_stride, pitch, width, height,
+                                     cudaMemcpyHostToDevice, s));
+        }
+        vsg_keypoint *kd = ex->kps_d + (size_t)f0 * g.out_cap;
+        uint8_t *dd = ex->desc_d + (size_t)f0 * g.out_cap * 32;
+        st = run_pipeline(ex, s, f0, dst0, L0.pitch, L0.plane_stride, nf, lap_x0, lap_x1, kd, dd, g.out_cap, ex->n_d + f0,
+                          ex->mono_d + f0);
+        if (st != VSG_OK) return st;
+        CK(cudaMemcpyAsync(ex->n_h + f0, ex->n_d + f0, nf * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(ex->mono_h + f0, ex->mono_d + f0, nf * sizeof(int), cudaMemcpyDeviceToHost, s));
+        if (direct) {
+            if (keypoints_out)
+                CK(cudaMemcpy2DAsync(keypoints_out + (size_t)f0 * capacity, (size_t)capacity * sizeof(vsg_keypoint), kd,
+                                     (size_t)g.out_cap * sizeof(vsg_keypoint), (size_t)g.out_cap * sizeof(vsg_keypoint), nf,
+                                     cudaMemcpyDeviceToHost, s));
+            if (descriptors_out)
+                CK(cudaMemcpy2DAsync(descriptors_out + (size_t)f0 * capacity * 32, (size_t)capacity * 32, dd,
+                                     (size_t)g.out_cap * 32, (size_t)g.out_cap * 32, nf, cudaMemcpyDeviceToHost, s));
+        } else {
+            CK(cudaMemcpyAsync(ex->kps_h + (size_t)f0 * g.out_cap, kd, (size_t)nf * g.out_cap * sizeof(vsg_keypoint),
+                               cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(ex->desc_h + (size_t)f0 * g.out_cap * 32, dd, (size_t)nf * g.out_cap * 32,
+                               cudaMemcpyDeviceToHost, s));
+        }
     }
+    for (int k = 1; k < nstreams_used; ++k) CK(cudaStreamSynchronize(ex->aux[k - 1]));
     CK(cudaStreamSynchronize(ex->stream));
     vsg_status ret = VSG_OK;
     for (int f = 0; f < nframes; ++f) {
@@ -529,8 +572,29 @@ vsg_status vsg_extract_batch_dev(vsg_extractor *ex, const uint8_t *images_dev, i
         set_error("vsg_extract_batch_dev: capacity %d < vsg_extractor_max_keypoints() = %d", capacity, ex->g.out_cap);
         return VSG_ERR_CAPACITY;
     }
-    return run_pipeline(ex, images_dev, pitch, (int64_t)frame_stride, nframes, lap_x0, lap_x1, keypoints_dev,
-                        descriptors_dev, capacity, n_dev, mono_dev);
+    ex->lvl0_base = images_dev; ex->lvl0_pitch = pitch; ex->lvl0_stride = (int64_t)frame_stride; ex->last_nframes = nframes;
+    const int chunk = ex->dev_chunk_frames;
+    if (ex->profile || chunk <= 0 || nframes < 2 * chunk)
+        return run_pipeline(ex, ex->stream, 0, images_dev, pitch, (int64_t)frame_stride, nframes, lap_x0, lap_x1,
+                            keypoints_dev, descriptors_dev, capacity, n_dev, mono_dev);
+    // Chunks rotate over the handle's three streams so that kernels of different stages (ALU-bound FAST next to
+    // latency-bound resize / blur / describe) share the SMs; the handle's stream forks and joins the other two, so
+    // the call keeps its stream-ordered contract.
+    CK(cudaEventRecord(ex->fork_ev, ex->stream));
+    for (cudaStream_t a : ex->aux) CK(cudaStreamWaitEvent(a, ex->fork_ev, 0));
+    for (int f0 = 0, c = 0; f0 < nframes; f0 += chunk, ++c) {
+        const int nf = std::min(chunk, nframes - f0);
+        cudaStream_t s = (c % 3 == 0) ? ex->stream : ex->aux[c % 3 - 1];
+        st = run_pipeline(ex, s, f0, images_dev + (size_t)f0 * frame_stride, pitch, (int64_t)frame_stride, nf, lap_x0, lap_x1,
+                          keypoints_dev + (size_t)f0 * capacity, descriptors_dev + (size_t)f0 * capacity * 32, capacity,
+                          n_dev + f0, mono_dev + f0);
+        if (st != VSG_OK) return st;
+    }
+    for (int k = 0; k < vsg_extractor::kAuxStreams; ++k) {
+        CK(cudaEventRecord(ex->join_ev[k], ex->aux[k]));
+        CK(cudaStreamWaitEvent(ex->stream, ex->join_ev[k], 0));
+    }
+    return VSG_OK;
 }
 
 vsg_status vsg_extractor_sync(vsg_extractor *ex) {
