@@ -238,6 +238,21 @@ vsg_status vsg_search_by_projection_map(vsg_matcher *m, const vsg_frame *F, cons
                                         const vsg_track_point *pts, const uint8_t *mp_desc, float th, int far_points,
                                         float th_far, float nnratio, int32_t *assign_out, int *nmatches_out);
 
+/* The same method in two halves, for map points sharded over GPUs (BASELINE config 3): every rank runs
+ * vsg_projection_map_candidates on its contiguous shard of the map points — the window query and the Hamming distance
+ * of every candidate, in the reference's candidate order (cand_ptr has n_mp + 1 entries, VSG_ERR_CAPACITY and
+ * *total_out = needed size if the lists do not fit) — the lists are all-gathered in shard order, and
+ * vsg_projection_map_resolve replays the order-dependent part of the loop (:76-141: claimed keypoints are skipped by
+ * later map points, best / second-best with their octaves, TH_HIGH and ratio gates) over all of them.  The resolve is
+ * host code and needs no device. */
+vsg_status vsg_projection_map_candidates(vsg_matcher *m, const vsg_frame *F, int n_mp, const vsg_track_point *pts,
+                                         const uint8_t *mp_desc, float th, int far_points, float th_far,
+                                         int32_t *cand_ptr, int32_t *cand_idx, int32_t *cand_dist, int capacity,
+                                         int *total_out);
+vsg_status vsg_projection_map_resolve(const vsg_frame_view *F, const uint8_t *occupied, int n_mp,
+                                      const vsg_track_point *pts, const int32_t *cand_ptr, const int32_t *cand_idx,
+                                      const int32_t *cand_dist, float nnratio, int32_t *assign_out, int *nmatches_out);
+
 /* SearchByProjection(Frame& Cur, const Frame& Last, th, bMono) (ORBmatcher.cc:1667-1878).  mode: 0 = octaves
  * [o-1, o+1], 1 = forward (>= o), 2 = backward ([0, o]) (:1719-1724).  assign_out[i] = index of the last-frame
  * point written to Cur.mvpMapPoints[i], -1 untouched, -2 written and then cleared by the rotation check. */

@@ -126,3 +126,27 @@ def test_empty_inputs(oracle):
     pts, desc, occ = sc.track_points(fd, kb, db, (9, 5), 1)
     nm, assign = m.SearchByProjectionMap(efr, np.zeros(0, np.uint8), pts, desc)
     assert nm == 0 and len(assign) == 0
+
+
+def test_projection_map_in_two_halves(oracle):
+    """vsg_projection_map_candidates (GPU) + vsg_projection_map_resolve (host) == the one-call method == the oracle;
+    with the map points split into shards the concatenated lists give the same answer (the multi-GPU C3 path)."""
+    from visual_sgraphs_b200 import sharded
+    ka, da, kb, db = sc.two_frames(oracle)
+    fd = sc.frame_data(ka, da, stereo_seed=5)
+    kb2, db2 = np.concatenate([kb] * 6), np.concatenate([db] * 6)
+    pts, desc, occ = sc.track_points(fd, kb2, db2, (9, 5), 21, True)
+    m = _matcher(0.8)
+    fr = m.frame(fd)
+    wnm, wassign = oracle.search_by_projection_map(fd.view, occ, pts, desc, 3.0, False, 50.0, float(np.float32(0.8)))
+    cp, ci, cd = m.ProjectionMapCandidates(fr, pts, desc, 3.0)
+    nm, assign = m.ProjectionMapResolve(fd, occ, pts, cp, ci, cd)
+    assert nm == wnm and np.array_equal(assign, wassign)
+    ptrs, idxs, dists = [np.zeros(1, np.int32)], [], []
+    for b, e in sharded.shard_bounds(len(pts), 3):
+        p, i, d = m.ProjectionMapCandidates(fr, pts[b:e], desc[b:e], 3.0)
+        ptrs.append(p[1:] + ptrs[-1][-1])
+        idxs.append(i)
+        dists.append(d)
+    nm3, assign3 = m.ProjectionMapResolve(fd, occ, pts, np.concatenate(ptrs), np.concatenate(idxs), np.concatenate(dists))
+    assert nm3 == wnm and np.array_equal(assign3, wassign)

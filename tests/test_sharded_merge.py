@@ -81,3 +81,60 @@ def test_train_sharded_knn2_over_gloo(tmp_path, nt):
         assert np.array_equal(got["dist"], want_d)
     if nt > 7:
         assert want_i[0, 0] == 7 and want_i[0, 1] == nt - 3 and want_d[0, 0] == 0 and want_d[0, 1] == 0
+
+
+# ---- map-point-sharded SearchByProjection (BASELINE config 3) ----
+def _proj_scenario(oracle):
+    from tests import match_scenarios as sc
+    ka, da, kb, db = sc.two_frames(oracle, size=(322, 243), nfeat=400)
+    fd = sc.frame_data(ka, da, size=(322, 243), stereo_seed=5)
+    reps = 5
+    kb2, db2 = np.concatenate([kb] * reps), np.concatenate([db] * reps)
+    pts, desc, occ = sc.track_points(fd, kb2, db2, (9, 5), 21, True)
+    return fd, pts, desc, occ
+
+
+def _cpu_candidates(oracle, fd, pts, desc, th):
+    """CPU stand-in for vsg_projection_map_candidates built from the oracle's GetFeaturesInArea restatement."""
+    f32 = np.float32
+    ptr, idx, dist = [0], [], []
+    for i, mp in enumerate(pts):
+        if mp["in_view"] and not mp["bad"]:
+            lvl = int(mp["level"])
+            r = f32(2.5) if float(mp["view_cos"]) > 0.998 else f32(4.0)
+            if th != 1.0:
+                r = f32(r * f32(th))
+            win = f32(r * fd.scale_factors[lvl])
+            for j in oracle.get_features_in_area(fd.view, float(mp["proj_x"]), float(mp["proj_y"]), float(win), lvl - 1, lvl):
+                if fd.u_right is not None and fd.u_right[j] > 0 and abs(f32(mp["proj_xr"] - fd.u_right[j])) > win:
+                    continue
+                idx.append(j)
+                dist.append(oracle.descriptor_distance(desc[i], fd.descriptors[j]))
+        ptr.append(len(idx))
+    return np.array(ptr, np.int32), np.array(idx, np.int32), np.array(dist, np.int32)
+
+
+def _proj_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as orc
+    from visual_sgraphs_b200.matcher import projection_map_resolve
+    fd, pts, desc, occ = _proj_scenario(orc)
+    b, e = sharded.shard_bounds(len(pts), world)[rank]
+    nm, assign = sharded.search_by_projection_map_sharded(
+        dist, len(pts), pts[b:e], lambda: _cpu_candidates(orc, fd, pts[b:e], desc[b:e], 3.0),
+        lambda pa, cp, ci, cd: projection_map_resolve(fd, occ, pa, cp, ci, cd, 0.8))
+    np.savez(os.path.join(out_dir, "proj%d.npz" % rank), nm=nm, assign=assign)
+    dist.destroy_process_group()
+
+
+def test_map_sharded_search_by_projection_over_gloo(tmp_path, oracle):
+    world = 2
+    mp.spawn(_proj_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    fd, pts, desc, occ = _proj_scenario(oracle)
+    wnm, wassign = oracle.search_by_projection_map(fd.view, occ, pts, desc, 3.0, False, 50.0, float(np.float32(0.8)))
+    assert wnm > 50
+    for r in range(world):
+        got = np.load(str(tmp_path / ("proj%d.npz" % r)))
+        assert int(got["nm"]) == wnm and np.array_equal(got["assign"], wassign)

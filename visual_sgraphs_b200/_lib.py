@@ -92,6 +92,10 @@ _SIGNATURES = {
     "vsg_search_by_projection_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                                C.c_float, C.c_int, C.c_float, C.c_float, C.c_void_p,
                                                C.POINTER(C.c_int)]),
+    "vsg_projection_map_candidates": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_int,
+                                                C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
+    "vsg_projection_map_resolve": (C.c_int, [C.POINTER(FrameView), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_float, C.c_void_p, C.POINTER(C.c_int)]),
     "vsg_search_by_projection_last": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                                 C.c_float, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
     "vsg_search_for_initialization": (C.c_int, [C.c_void_p, C.POINTER(FrameView), C.c_void_p, C.c_void_p, C.c_int,

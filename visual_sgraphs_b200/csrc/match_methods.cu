@@ -240,58 +240,129 @@ vsg_status vsg_area_search(vsg_matcher *m, const vsg_frame *f, int nq, const flo
     return VSG_OK;
 }
 
-// ORBmatcher.cc:42-144
-vsg_status vsg_search_by_projection_map(vsg_matcher *m, const vsg_frame *F, const uint8_t *occupied, int n_mp,
-                                        const vsg_track_point *pts, const uint8_t *mp_desc, float th, int far_points,
-                                        float th_far, float nnratio, int32_t *assign_out, int *nmatches_out) {
-    if (!m || !F || n_mp < 0 || !assign_out || (n_mp > 0 && (!pts || !mp_desc)) || (F->n > 0 && !occupied)) return VSG_ERR_INVALID;
-    CK(cudaSetDevice(m->device));
+// ORBmatcher.cc:48-74: the map points that reach GetFeaturesInArea, as window queries
+static vsg_status projection_map_queries(const std::vector<float> &scale, int n_mp, const vsg_track_point *pts, float th,
+                                         int far_points, float th_far, std::vector<AreaQuery> &qs, std::vector<int> &q_mp) {
     const bool b_factor = th != 1.0;
-    // queries = the map points that reach GetFeaturesInArea (:48-74)
-    std::vector<AreaQuery> qs;
-    std::vector<int> q_mp;
-    std::vector<uint8_t> qdesc;
+    qs.clear(); q_mp.clear();
     qs.reserve(n_mp); q_mp.reserve(n_mp);
     for (int i = 0; i < n_mp; ++i) {
         const vsg_track_point &mp = pts[i];
         if (!mp.in_view) continue;
         if (far_points && mp.depth > th_far) continue;
         if (mp.bad) continue;
-        if (mp.level < 0 || mp.level >= (int)F->scale.size()) { set_error("map point %d: level %d out of range", i, mp.level); return VSG_ERR_INVALID; }
+        if (mp.level < 0 || mp.level >= (int)scale.size()) { set_error("map point %d: level %d out of range", i, mp.level); return VSG_ERR_INVALID; }
         float r = (mp.view_cos > 0.998) ? 2.5f : 4.0f;    // RadiusByViewingCos (:218-224)
         if (b_factor) r *= th;
-        const float win = r * F->scale[mp.level];
+        const float win = r * scale[mp.level];
         qs.push_back(AreaQuery{mp.proj_x, mp.proj_y, win, mp.level - 1, mp.level, mp.proj_xr, win});
         q_mp.push_back(i);
     }
-    qdesc.resize(qs.size() * 32);
-    for (size_t k = 0; k < qs.size(); ++k) memcpy(&qdesc[k * 32], mp_desc + (size_t)q_mp[k] * 32, 32);
-    std::vector<int> ptr;
-    std::vector<int2> ent;
-    vsg_status st = area_search(m, F, (int)qs.size(), qs.data(), qdesc.data(), ptr, ent);
-    if (st != VSG_OK) return st;
-    // sequential replay of :76-141
-    std::vector<uint8_t> blocked(occupied, occupied + F->n);
-    for (int i = 0; i < F->n; ++i) assign_out[i] = -1;
+    return VSG_OK;
+}
+
+// ORBmatcher.cc:76-141: the sequential replay over per-map-point candidate lists (ptr has n_mp + 1 entries; map points
+// that never reached GetFeaturesInArea have empty lists)
+static int projection_map_resolve(int n_kp, const vsg_keypoint *keys, const uint8_t *occupied, int n_mp,
+                                  const vsg_track_point *pts, const int32_t *ptr, const int32_t *cand_idx,
+                                  const int32_t *cand_dist, float nnratio, int32_t *assign_out) {
+    std::vector<uint8_t> blocked(occupied, occupied + n_kp);
+    for (int i = 0; i < n_kp; ++i) assign_out[i] = -1;
     int nmatches = 0;
-    for (size_t k = 0; k < qs.size(); ++k) {
+    for (int k = 0; k < n_mp; ++k) {
+        if (ptr[k] == ptr[k + 1]) continue;
         int best = 256, best_level = -1, best2 = 256, best_level2 = -1, best_idx = -1;
         for (int c = ptr[k]; c < ptr[k + 1]; ++c) {
-            const int idx = ent[c].x, dist = ent[c].y;
+            const int idx = cand_idx[c], dist = cand_dist[c];
             if (blocked[idx]) continue;
-            if (dist < best) { best2 = best; best = dist; best_level2 = best_level; best_level = F->keys[idx].octave; best_idx = idx; }
-            else if (dist < best2) { best_level2 = F->keys[idx].octave; best2 = dist; }
+            if (dist < best) { best2 = best; best = dist; best_level2 = best_level; best_level = keys[idx].octave; best_idx = idx; }
+            else if (dist < best2) { best_level2 = keys[idx].octave; best2 = dist; }
         }
         if (best <= TH_HIGH) {
             if (best_level == best_level2 && best > nnratio * best2) continue;
             if (best_level != best_level2 || best <= nnratio * best2) {
-                assign_out[best_idx] = q_mp[k];
-                blocked[best_idx] = pts[q_mp[k]].blocks;
+                assign_out[best_idx] = k;
+                blocked[best_idx] = pts[k].blocks;
                 ++nmatches;
             }
         }
     }
-    if (nmatches_out) *nmatches_out = nmatches;
+    return nmatches;
+}
+
+// GPU half of SearchByProjection(Frame&, vector<MapPoint*>&): candidate lists of every map point
+vsg_status vsg_projection_map_candidates(vsg_matcher *m, const vsg_frame *F, int n_mp, const vsg_track_point *pts,
+                                         const uint8_t *mp_desc, float th, int far_points, float th_far,
+                                         int32_t *cand_ptr, int32_t *cand_idx, int32_t *cand_dist, int capacity,
+                                         int *total_out) {
+    if (!m || !F || n_mp < 0 || !cand_ptr || (n_mp > 0 && (!pts || !mp_desc))) return VSG_ERR_INVALID;
+    CK(cudaSetDevice(m->device));
+    std::vector<AreaQuery> qs;
+    std::vector<int> q_mp;
+    vsg_status st = projection_map_queries(F->scale, n_mp, pts, th, far_points, th_far, qs, q_mp);
+    if (st != VSG_OK) return st;
+    std::vector<uint8_t> qdesc(qs.size() * 32);
+    for (size_t k = 0; k < qs.size(); ++k) memcpy(&qdesc[k * 32], mp_desc + (size_t)q_mp[k] * 32, 32);
+    std::vector<int> ptr;
+    std::vector<int2> ent;
+    if ((st = area_search(m, F, (int)qs.size(), qs.data(), qdesc.data(), ptr, ent)) != VSG_OK) return st;
+    if (total_out) *total_out = (int)ent.size();
+    // expand to one list per map point
+    size_t q = 0;
+    for (int i = 0; i < n_mp; ++i) {
+        cand_ptr[i] = q < qs.size() ? ptr[q] : (int)ent.size();
+        if (q < qs.size() && q_mp[q] == i) ++q;
+    }
+    cand_ptr[n_mp] = (int)ent.size();
+    if ((int)ent.size() > capacity) return VSG_ERR_CAPACITY;
+    for (size_t k = 0; k < ent.size(); ++k) {
+        if (cand_idx) cand_idx[k] = ent[k].x;
+        if (cand_dist) cand_dist[k] = ent[k].y;
+    }
+    return VSG_OK;
+}
+
+// host half: the order-dependent replay (no device needed; runs on every rank after the all-gather when the map
+// points are sharded over GPUs)
+vsg_status vsg_projection_map_resolve(const vsg_frame_view *F, const uint8_t *occupied, int n_mp,
+                                      const vsg_track_point *pts, const int32_t *cand_ptr, const int32_t *cand_idx,
+                                      const int32_t *cand_dist, float nnratio, int32_t *assign_out, int *nmatches_out) {
+    if (!F || n_mp < 0 || !cand_ptr || (F->n > 0 && (!occupied || !assign_out || !F->keys)) ||
+        (n_mp > 0 && !pts) || (cand_ptr[n_mp] > 0 && (!cand_idx || !cand_dist)))
+        return VSG_ERR_INVALID;
+    for (int c = 0; c < cand_ptr[n_mp]; ++c)
+        if (cand_idx[c] < 0 || cand_idx[c] >= F->n) { set_error("resolve: candidate index out of range"); return VSG_ERR_INVALID; }
+    const int nm = projection_map_resolve(F->n, F->keys, occupied, n_mp, pts, cand_ptr, cand_idx, cand_dist, nnratio, assign_out);
+    if (nmatches_out) *nmatches_out = nm;
+    return VSG_OK;
+}
+
+// ORBmatcher.cc:42-144
+vsg_status vsg_search_by_projection_map(vsg_matcher *m, const vsg_frame *F, const uint8_t *occupied, int n_mp,
+                                        const vsg_track_point *pts, const uint8_t *mp_desc, float th, int far_points,
+                                        float th_far, float nnratio, int32_t *assign_out, int *nmatches_out) {
+    if (!m || !F || n_mp < 0 || !assign_out || (n_mp > 0 && (!pts || !mp_desc)) || (F->n > 0 && !occupied)) return VSG_ERR_INVALID;
+    CK(cudaSetDevice(m->device));
+    std::vector<AreaQuery> qs;
+    std::vector<int> q_mp;
+    vsg_status st = projection_map_queries(F->scale, n_mp, pts, th, far_points, th_far, qs, q_mp);
+    if (st != VSG_OK) return st;
+    std::vector<uint8_t> qdesc(qs.size() * 32);
+    for (size_t k = 0; k < qs.size(); ++k) memcpy(&qdesc[k * 32], mp_desc + (size_t)q_mp[k] * 32, 32);
+    std::vector<int> ptr;
+    std::vector<int2> ent;
+    if ((st = area_search(m, F, (int)qs.size(), qs.data(), qdesc.data(), ptr, ent)) != VSG_OK) return st;
+    // per-map-point lists for the replay
+    std::vector<int32_t> mp_ptr(n_mp + 1), ci(ent.size()), cd(ent.size());
+    size_t q = 0;
+    for (int i = 0; i < n_mp; ++i) {
+        mp_ptr[i] = q < qs.size() ? ptr[q] : (int)ent.size();
+        if (q < qs.size() && q_mp[q] == i) ++q;
+    }
+    mp_ptr[n_mp] = (int)ent.size();
+    for (size_t k = 0; k < ent.size(); ++k) { ci[k] = ent[k].x; cd[k] = ent[k].y; }
+    const int nm = projection_map_resolve(F->n, F->keys.data(), occupied, n_mp, pts, mp_ptr.data(), ci.data(), cd.data(), nnratio, assign_out);
+    if (nmatches_out) *nmatches_out = nm;
     return VSG_OK;
 }
 

@@ -14,6 +14,19 @@ TH_LOW = 50       # ORBmatcher.cc:35
 HISTO_LENGTH = 30  # ORBmatcher.cc:36
 
 
+def projection_map_resolve(frame_data, occupied, track_points, cand_ptr, cand_idx, cand_dist, nnratio):
+    """vsg_projection_map_resolve: host code, needs no CUDA device (every rank runs it after the all-gather)."""
+    L = _lib.load()
+    pts = np.ascontiguousarray(track_points, TRACK_POINT_DTYPE)
+    occupied = np.ascontiguousarray(occupied, np.uint8)
+    cand_ptr, cand_idx, cand_dist = (np.ascontiguousarray(a, np.int32) for a in (cand_ptr, cand_idx, cand_dist))
+    assign = np.zeros(frame_data.n, np.int32)
+    nm = C.c_int(0)
+    check(L.vsg_projection_map_resolve(C.byref(frame_data.view), ptr(occupied), len(pts), ptr(pts), ptr(cand_ptr),
+                                       ptr(cand_idx), ptr(cand_dist), float(np.float32(nnratio)), ptr(assign), C.byref(nm)))
+    return nm.value, assign
+
+
 class ORBmatcher:
     def __init__(self, nnratio=0.6, checkOri=True, device=0):
         self._L = _lib.load()
@@ -121,6 +134,28 @@ class ORBmatcher:
                                                    float(th), int(bFarPoints), float(thFarPoints),
                                                    float(self.mfNNratio), ptr(assign), C.byref(nm)))
         return nm.value, assign
+
+    def ProjectionMapCandidates(self, frame, track_points, mp_desc, th=3.0, bFarPoints=False, thFarPoints=50.0):
+        """GPU half of SearchByProjection(Frame&, vector<MapPoint*>&): per-map-point candidate lists
+        (cand_ptr [n+1], cand_idx, cand_dist) in the reference's order (vsg_projection_map_candidates)."""
+        pts = np.ascontiguousarray(track_points, TRACK_POINT_DTYPE)
+        mp_desc = np.ascontiguousarray(mp_desc, np.uint8).reshape(-1, 32)
+        cand_ptr = np.zeros(len(pts) + 1, np.int32)
+        cap = max(1024, len(pts) * 16)
+        while True:
+            idx, dist, total = np.zeros(cap, np.int32), np.zeros(cap, np.int32), C.c_int(0)
+            st = self._L.vsg_projection_map_candidates(self._h, frame._h, len(pts), ptr(pts), ptr(mp_desc), float(th),
+                                                       int(bFarPoints), float(thFarPoints), ptr(cand_ptr), ptr(idx),
+                                                       ptr(dist), cap, C.byref(total))
+            if st == _lib.VSG_ERR_CAPACITY:
+                cap = total.value
+                continue
+            check(st)
+            return cand_ptr, idx[: total.value].copy(), dist[: total.value].copy()
+
+    def ProjectionMapResolve(self, frame_data, occupied, track_points, cand_ptr, cand_idx, cand_dist):
+        """Host half: the order-dependent replay of ORBmatcher.cc:76-141 (vsg_projection_map_resolve)."""
+        return projection_map_resolve(frame_data, occupied, track_points, cand_ptr, cand_idx, cand_dist, self.mfNNratio)
 
     def SearchByProjectionLast(self, cur_frame, occupied, proj_points, desc, th, mode=0):
         """SearchByProjection(Frame& Cur, const Frame& Last, th, bMono) (ORBmatcher.cc:1667-1878) with the

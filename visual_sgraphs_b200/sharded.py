@@ -53,3 +53,61 @@ def merge_top2_numpy(idx_parts, dist_parts):
     out_i = np.take_along_axis(flat_i, order, 1).astype(np.int32)
     out_d = np.take_along_axis(flat_d, order, 1).astype(np.int32)
     return out_i, out_d
+
+
+def _all_gather_rows(dist, rows, counts, device):
+    """All-gather variable-length 2-D arrays (same trailing shape/dtype on every rank): pad to the longest, gather,
+    trim.  `counts` = row count of every rank (already known to all).  Returns the list of per-rank arrays."""
+    import torch
+    world = dist.get_world_size()
+    longest = max(max(counts), 1)
+    rows = np.ascontiguousarray(rows)
+    pad = np.zeros((longest,) + rows.shape[1:], rows.dtype)
+    pad[: rows.shape[0]] = rows
+    mine = torch.from_numpy(pad).to(device)
+    out = torch.empty((world,) + tuple(mine.shape), dtype=mine.dtype, device=device)
+    if mine.is_cuda:
+        dist.all_gather_into_tensor(out, mine)
+    else:
+        dist.all_gather(list(out.unbind(0)), mine)
+    out = out.cpu().numpy()
+    return [out[r, : counts[r]] for r in range(world)]
+
+
+def search_by_projection_map_sharded(dist, n_mp_total, pts_shard, local_candidates, resolve, device="cpu"):
+    """SearchByProjection(Frame&, vector<MapPoint*>&) (ORBmatcher.cc:42-144) with the MAP POINTS sharded contiguously
+    over ranks (BASELINE config 3) and the frame replicated.
+
+    local_candidates() -> (cand_ptr [n_local + 1], cand_idx, cand_dist) int32 arrays for this rank's shard
+        (vsg_projection_map_candidates: GPU window query + Hamming distances, reference candidate order);
+    pts_shard: this rank's vsg_track_point records (their `blocks` flag is needed by every rank's replay);
+    resolve(pts_all, cand_ptr, cand_idx, cand_dist) -> (nmatches, assign) replays ORBmatcher.cc:76-141 over all lists
+        (vsg_projection_map_resolve, host code).
+    One exchange step: per-rank list sizes (one int each), then the padded lists and point records.  Every rank ends
+    with the identical (nmatches, assign) of the single-process call."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    bounds = shard_bounds(n_mp_total, world)
+    n_local = bounds[rank][1] - bounds[rank][0]
+    ptr, idx, d = local_candidates()
+    ptr = np.asarray(ptr, np.int32)
+    assert len(ptr) == n_local + 1 and len(pts_shard) == n_local
+    total = torch.tensor([int(ptr[-1])], dtype=torch.int64, device=device)
+    totals = torch.zeros(world, dtype=torch.int64, device=device)
+    if total.is_cuda:
+        dist.all_gather_into_tensor(totals, total)
+    else:
+        dist.all_gather(list(totals.unbind(0)), total[0])
+    totals = [int(t) for t in totals.cpu()]
+    n_locals = [e - b for b, e in bounds]
+    lens = np.diff(ptr).astype(np.int32).reshape(-1, 1)
+    cand = np.stack([np.asarray(idx, np.int32)[: ptr[-1]], np.asarray(d, np.int32)[: ptr[-1]]], 1)
+    all_lens = _all_gather_rows(dist, lens, n_locals, device)
+    all_cand = _all_gather_rows(dist, cand, totals, device)
+    all_pts = _all_gather_rows(dist, np.ascontiguousarray(pts_shard).view(np.uint8).reshape(n_local, -1), n_locals, device)
+    lens = np.concatenate([a.reshape(-1) for a in all_lens]) if n_mp_total else np.zeros(0, np.int32)
+    gptr = np.zeros(n_mp_total + 1, np.int32)
+    np.cumsum(lens, out=gptr[1:])
+    cand = np.concatenate(all_cand) if sum(totals) else np.zeros((0, 2), np.int32)
+    pts_all = np.concatenate(all_pts).reshape(-1).view(pts_shard.dtype)
+    return resolve(pts_all, gptr, np.ascontiguousarray(cand[:, 0]), np.ascontiguousarray(cand[:, 1]))
