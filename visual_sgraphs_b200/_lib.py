@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvsg_cuda.so")
+LIB_PATH = os.environ.get("VSG_LIB_PATH") or os.path.join(_HERE, "libvsg_cuda.so")   # override: kernel-variant experiments
 
 KEYPOINT_DTYPE = np.dtype(
     [("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4"),

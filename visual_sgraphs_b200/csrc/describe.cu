@@ -101,9 +101,12 @@ __global__ void __launch_bounds__(256) slot_kernel(FrameGeom g, const LevelKp *_
 // 64 keypoints per CTA (8 warps x 8 keypoints).  The warp-uniform scalar work — fastAtan2 and the
 // double-precision cos/sin — is done once per keypoint by 64 threads in between the two warp-parallel
 // phases instead of redundantly by all 32 lanes of a warp.
+#ifndef VSG_DESC_MINB
+#define VSG_DESC_MINB 4
+#endif
 constexpr int kDescKp = 64;
 
-__global__ void __launch_bounds__(256) describe_kernel(FrameGeom g, const uint8_t *__restrict__ lvl0_base,
+__global__ void __launch_bounds__(256, VSG_DESC_MINB) describe_kernel(FrameGeom g, const uint8_t *__restrict__ lvl0_base,
                                                        int lvl0_pitch, int64_t lvl0_stride,
                                                        const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur,
                                                        const LevelKp *__restrict__ level_kps,

@@ -191,9 +191,12 @@ __global__ void __launch_bounds__(kFastThreads, 8) fast_kernel(FrameGeom g,
     for (int pass = 0; pass < 2; ++pass) {
         const int t = pass == 0 ? ini_th : min_th;
         const int tt = max(t, 1);       // a corner scoring 0 (K == 1, only possible at t == 0) never survives the NMS
+        // Survivors are only flagged inside the loop (bit `iter` of m0 / m1 for the two pixels of the pair); the
+        // compaction runs once per pass after it: one warp scan, one shared-memory atomic per warp.
+        uint32_t m0 = 0, m1 = 0;
         PairIter it(tid, S);
-        for (int base = 0; base < npairs; base += kFastThreads, it.next()) {   // warp-uniform trip count
-            // out-of-range lanes read the (zero) apron row 0: no branch around the loads
+        int iter = 0;
+        for (int base = 0; base < npairs; base += kFastThreads, it.next(), ++iter) {
             // lanes past the last pair read a harmless in-range location and are masked: no branch around the loads
             const bool in = it.iy < ih;
             const uint32_t *c = s2 + (in ? (it.iy + 1) * kS2Pitch + it.j + 1 : kS2Pitch + 1);
@@ -204,20 +207,36 @@ __global__ void __launch_bounds__(kFastThreads, 8) fast_kernel(FrameGeom g,
             const int k0 = K & 0xFFFF, k1 = K >> 16;
             const bool f0 = in && k0 > tt && k0 > (int)(nb & 0xFFFF);
             const bool f1 = in && k1 > tt && k1 > (int)(nb >> 16);
-            const unsigned m0 = __ballot_sync(0xffffffffu, f0), m1 = __ballot_sync(0xffffffffu, f1);
-            if ((m0 | m1) == 0) continue;                                       // warp-uniform
-            const int n0 = __popc(m0);
+            m0 |= (uint32_t)f0 << iter;
+            m1 |= (uint32_t)f1 << iter;
+        }
+        const int cnt = __popc(m0) + __popc(m1);
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total > 0) {                                                    // warp-uniform
             int wbase = 0;
-            // one shared-memory atomic per warp, issued by lane 0 under a predicate (no divergent region)
-            asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %2, 0;\n\t@p atom.shared.add.u32 %0, [%1], %3;\n\t}"
-                         : "+r"(wbase)
-                         : "r"((uint32_t)__cvta_generic_to_shared(&s_count)), "r"(lane), "r"(n0 + __popc(m1))
-                         : "memory");
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            const unsigned lt = (1u << lane) - 1;
-            const uint32_t pos = (uint32_t)it.j | ((uint32_t)it.iy << 8);
-            if (f0) list[wbase + __popc(m0 & lt)] = pos | ((uint32_t)(k0 - 1) << 16);
-            if (f1) list[wbase + n0 + __popc(m1 & lt)] = (pos + S) | ((uint32_t)(k1 - 1) << 16);
+            if (lane == 31) wbase = atomicAdd(&s_count, total);
+            wbase = __shfl_sync(0xffffffffu, wbase, 31);
+            int pos = wbase + incl - cnt;
+            while (m0) {
+                const int i = __ffs(m0) - 1;
+                m0 &= m0 - 1;
+                const int p = tid + i * kFastThreads, iy = p / S, j = p - iy * S;
+                const uint32_t K = s2[(iy + 1) * kS2Pitch + j + 1] & 0xFFFFu;
+                list[pos++] = (uint32_t)j | ((uint32_t)iy << 8) | ((K - 1) << 16);
+            }
+            while (m1) {
+                const int i = __ffs(m1) - 1;
+                m1 &= m1 - 1;
+                const int p = tid + i * kFastThreads, iy = p / S, j = p - iy * S;
+                const uint32_t K = s2[(iy + 1) * kS2Pitch + j + 1] >> 16;
+                list[pos++] = (uint32_t)(j + S) | ((uint32_t)iy << 8) | ((K - 1) << 16);
+            }
         }
         __syncthreads();
         if (s_count > 0) break;   // uniform: the retry happens only when the cell is empty (:842)
@@ -247,7 +266,10 @@ void launch_fast(const FrameGeom &g, const Cell *cells, const uint8_t *lvl0_base
     (void)cells;   // the kernel derives the cell geometry from the level tables
     if (g.ncells == 0) return;
     const int max_S = ((((max_cw - 6) + 1) >> 1) + 3) & ~3;
-    if (3 + max_S + 6 + 3 > kT2Pitch || max_S + 2 > kS2Pitch) { set_error("FAST cell wider than the shared-memory tile"); return; }
+    if (3 + max_S + 6 + 3 > kT2Pitch || max_S + 2 > kS2Pitch || max_S * (max_ch - 6) > 32 * kFastThreads) {
+        set_error("FAST cell larger than the shared-memory tile / the 32-iteration survivor masks");
+        return;
+    }
     const int tile_rows = max_ch;
     const int list_cap = ((max_cw - 6 + 1) / 2) * ((max_ch - 6 + 1) / 2) + 1;
     const size_t smem = (size_t)tile_rows * kT2Pitch * 4 + (size_t)(tile_rows - 4) * kS2Pitch * 4 + (size_t)list_cap * 4 + 16;

@@ -21,9 +21,18 @@ namespace vsg {
 // Vertical: ((b*(h>>4))>>16) is a 32x32 high multiply by b<<16.
 // grid (ceil(ncg/128), ceil(dh/kResizeRows), nframes), block 128.
 // ------------------------------------------------------------------------------------------------
-constexpr int kResizeRows = 4, kResizeThreads = 128;
+#ifndef VSG_RESIZE_ROWS
+#define VSG_RESIZE_ROWS 4
+#endif
+#ifndef VSG_RESIZE_MINB
+#define VSG_RESIZE_MINB 12
+#endif
+#ifndef VSG_BLUR_MINB
+#define VSG_BLUR_MINB 10
+#endif
+constexpr int kResizeRows = VSG_RESIZE_ROWS, kResizeThreads = 128;
 
-__global__ void __launch_bounds__(kResizeThreads) resize_kernel(const uint8_t *__restrict__ src, int src_pitch,
+__global__ void __launch_bounds__(kResizeThreads, VSG_RESIZE_MINB) resize_kernel(const uint8_t *__restrict__ src, int src_pitch,
                                                                 int64_t src_stride, uint8_t *__restrict__ dst,
                                                                 int dst_pitch, int64_t dst_stride, int dw, int dh,
                                                                 int sw, const uint8_t *__restrict__ src_end,
@@ -191,7 +200,7 @@ __device__ __forceinline__ void blur_strip(const uint8_t *__restrict__ src, int 
     }
 }
 
-__global__ void __launch_bounds__(kBlurThreads) blur_kernel(FrameGeom g, BlurLevels bl, const uint8_t *__restrict__ lvl0_base,
+__global__ void __launch_bounds__(kBlurThreads, VSG_BLUR_MINB) blur_kernel(FrameGeom g, BlurLevels bl, const uint8_t *__restrict__ lvl0_base,
                                                             int lvl0_pitch, int64_t lvl0_stride,
                                                             const uint8_t *__restrict__ pyr, uint8_t *__restrict__ blur) {
     int level = 0;
