@@ -40,14 +40,16 @@ def level_sizes(w, h):
     return [(int(np.rint(np.float32(w) * i)), int(np.rint(np.float32(h) * i))) for i in inv]
 
 
-def algorithmic_bytes(w, h, n_kp):
-    """per-stage compulsory bytes per frame. P = sum of level pixels."""
+def algorithmic_bytes(w, h, n_kp, fused):
+    """per-stage compulsory bytes per frame. P = sum of level pixels.  With the fused FAST + blur grid
+    (the default) the "fast" stage is that one kernel: it reads every level for FAST (P) and reads + writes every level
+    for the blur (2P); the "blur" stage is then empty."""
     px = [a * b for a, b in level_sizes(w, h)]
     P, p0, p7 = sum(px), px[0], px[-1]
     stages = {
         "pyramid": (P - p7) + (P - p0),   # read L0..L6, write L1..L7
-        "fast": P,                        # read every level once
-        "blur": 2 * P,                    # read + write every level
+        "fast": 3 * P if fused else P,    # read every level once (+ blur: read + write every level)
+        "blur": 0 if fused else 2 * P,
         "describe": 60 * n_kp,            # 28 B keypoint + 32 B descriptor per keypoint
         "octree": 0,                      # latency-bound bookkeeping; no roofline claim
     }
@@ -183,6 +185,97 @@ def latency_extras(torch, lib, device):
     ts = np.array(ts) * 1e3
     return {"ms_median": float(np.median(ts)), "ms_p95": float(np.percentile(ts, 95)),
             "frames_per_s": float(1e3 / np.mean(ts)), "calls": 200}
+
+
+def other_config_extras(torch, lib, device):
+    """The other BASELINE configs as reported extras (they are parity-test cases, not bench lines): C4 1280x720 / 2000
+    features (device-resident batch), C2 EuRoC-shaped stereo pairs through the host API (extraction of both images in
+    one batched call + vsg_stereo_match on the device pyramids), C3 SearchByProjection of a 200k-point map into a
+    1000-keypoint frame (one call, host arrays in and out)."""
+    from visual_sgraphs_b200._lib import KEYPOINT_DTYPE, TRACK_POINT_DTYPE
+    from visual_sgraphs_b200.extractor import ORBextractor
+    from visual_sgraphs_b200.frame import FrameData
+    from visual_sgraphs_b200.matcher import ORBmatcher
+    from visual_sgraphs_b200.synth import synth_frame, synth_stereo_pair
+    out = {}
+    # ---- C4 ----
+    B4 = 128
+    base = [synth_frame(6000 + i, 1280, 720) for i in range(8)]
+    fr = np.stack([np.roll(base[i % 8], (5 * (i // 8), 11 * (i // 8)), (0, 1)) for i in range(B4)])
+    d_frames = torch.from_numpy(fr).cuda()
+    ex = ORBextractor(2000, SCALE, NLEVELS, INI_TH, MIN_TH, device=device, max_batch=B4)
+    cap = ex.max_keypoints(1280, 720)
+    kps = torch.zeros((B4, cap, 28), dtype=torch.uint8, device="cuda")
+    desc = torch.zeros((B4, cap, 32), dtype=torch.uint8, device="cuda")
+    n = torch.zeros(B4, dtype=torch.int32, device="cuda")
+    mono = torch.zeros(B4, dtype=torch.int32, device="cuda")
+    st = torch.cuda.ExternalStream(ex.stream(), device=device)
+    torch.cuda.synchronize()
+    for _ in range(2):
+        ex.extract_batch_dev(d_frames, kps, desc, n, mono)
+    ex.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(5):
+        ex.extract_batch_dev(d_frames, kps, desc, n, mono)
+    e1.record(st)
+    ex.sync()
+    ms = e0.elapsed_time(e1) / 5
+    out["c4_1280x720_2000f"] = {"frames_per_s": B4 / (ms * 1e-3), "ms_per_128_frames": ms,
+                                "keypoints_per_frame": float(n.float().mean().item())}
+    ex.close()
+    del d_frames, kps, desc
+    # ---- C2 ----
+    npairs = 16
+    pairs = [synth_stereo_pair(8000 + i) for i in range(npairs)]
+    stack = torch.from_numpy(np.stack([im for pr in pairs for im in pr])).pin_memory()   # L0 R0 L1 R1 ...
+    ex2 = ORBextractor(1200, SCALE, NLEVELS, INI_TH, MIN_TH, device=device, max_batch=2 * npairs)
+    m = ORBmatcher(device=device)
+
+    def stereo_step():
+        res = ex2.extract_batch(stack.numpy())
+        matched = 0
+        for i in range(npairs):
+            (_, kl, dl), (_, kr, dr) = res[2 * i], res[2 * i + 1]
+            u, _ = m.ComputeStereoMatches(ex2, ex2, kl, dl, kr, dr, 0.11, 47.9, frame_l=2 * i, frame_r=2 * i + 1)
+            matched += int((u >= 0).sum())
+        return matched
+
+    stereo_step()
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        matched = stereo_step()
+    dt = (time.perf_counter() - t0) / reps
+    out["c2_stereo_752x480_1200f"] = {"pairs_per_s": npairs / dt, "ms_per_pair": 1e3 * dt / npairs,
+                                      "stereo_matches_per_pair": matched / npairs}
+    ex2.close()
+    # ---- C3 ----
+    rng = np.random.default_rng(3)
+    n_kp, n_map = 1000, 200_000
+    keys = np.zeros(n_kp, KEYPOINT_DTYPE)
+    keys["x"], keys["y"] = rng.uniform(20, 620, n_kp), rng.uniform(20, 460, n_kp)
+    keys["octave"] = rng.integers(0, 8, n_kp)
+    kdesc = rng.integers(0, 256, (n_kp, 32), dtype=np.uint8)
+    fdata = FrameData(keys, kdesc)
+    src = rng.integers(0, n_kp, n_map)
+    pts = np.zeros(n_map, TRACK_POINT_DTYPE)
+    pts["proj_x"] = keys["x"][src] + rng.normal(0, 2, n_map)
+    pts["proj_y"] = keys["y"][src] + rng.normal(0, 2, n_map)
+    pts["view_cos"] = rng.uniform(0.99, 1.0, n_map)
+    pts["level"] = np.clip(keys["octave"][src] + rng.integers(0, 2, n_map), 0, 7)
+    pts["in_view"], pts["blocks"] = True, rng.random(n_map) < 0.9
+    mp_desc = kdesc[src] ^ np.packbits(rng.random((n_map, 32, 8)) < 0.08, axis=2).reshape(n_map, 32)
+    occ = np.zeros(n_kp, np.uint8)
+    frame = m.frame(fdata)
+    m.SearchByProjectionMap(frame, occ, pts, mp_desc, 3.0)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        nm, _ = m.SearchByProjectionMap(frame, occ, pts, mp_desc, 3.0)
+    dt = (time.perf_counter() - t0) / 5
+    out["c3_projection_1000kp_x_200k_map"] = {"ms_per_call": dt * 1e3, "map_points_per_s": n_map / dt, "nmatches": nm}
+    m.close()
+    return out
 
 
 def matching_extras(torch, device):
@@ -338,7 +431,8 @@ def main():
     if rank == 0:
         frames_total = world * B * K
         value = frames_total / (elapsed_ms * 1e-3)
-        stages_bytes, b_frame = algorithmic_bytes(W, H, n_kp_mean)
+        fused = os.environ.get("VSG_FUSE_FAST_BLUR", "1") != "0"
+        stages_bytes, b_frame = algorithmic_bytes(W, H, n_kp_mean, fused)
         peak, peak_src = measured_peaks()
         dominant = max(stage_ms, key=lambda k: stage_ms[k])
         roof_stage = dominant if stages_bytes[dominant] > 0 else "fast"
@@ -357,7 +451,8 @@ def main():
             "e2e": {"value": frames_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * W * H,
                     "d2h_bytes_per_step": B * cap * 60 + 8 * B, "ms_per_step": e2e_ms / K},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": roof_stage, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "fast_blur_kernel (FAST cells + Gaussian blur in one grid)" if fused and roof_stage == "fast" else roof_stage,
+                         "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_frame": stages_bytes[roof_stage], "launch_ms": dur_ms,
                          "dominant_stage_by_time": dominant,
@@ -378,6 +473,7 @@ def main():
                                     "single_thread_value": v_one}
             line["single_frame_latency"] = latency_extras(torch, lib, local_rank)
             line["matching"] = matching_extras(torch, local_rank)
+            line["other_configs"] = other_config_extras(torch, lib, local_rank)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

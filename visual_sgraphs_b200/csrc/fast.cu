@@ -16,6 +16,7 @@
 // one global atomic per CTA.  The list order is not the reference's cell-row-major order; the oct-tree only
 // depends on order through the first-max-wins tie break, which octree.cu reproduces from the coordinates
 // (see order_key there).
+#include "blur_device.cuh"
 #include "vsg_internal.cuh"
 
 namespace vsg {
@@ -80,11 +81,11 @@ struct PairIter {
     }
 };
 
-__global__ void __launch_bounds__(kFastThreads, 8) fast_kernel(FrameGeom g,
-                                                             const uint8_t *__restrict__ lvl0_base, int lvl0_pitch,
-                                                             int64_t lvl0_stride, const uint8_t *__restrict__ pyr,
-                                                             Cand *__restrict__ cand, int *__restrict__ cand_count,
-                                                             int ini_th, int min_th, int tile_rows, int list_cap) {
+// One FAST cell (kFastThreads threads): cell `cell_block` of the frame's flat cell table.
+__device__ __forceinline__ void fast_cell_body(const FrameGeom &g, const uint8_t *__restrict__ lvl0_base, int lvl0_pitch,
+                                               int64_t lvl0_stride, const uint8_t *__restrict__ pyr,
+                                               Cand *__restrict__ cand, int *__restrict__ cand_count, int ini_th,
+                                               int min_th, int tile_rows, int list_cap, int cell_block, int frame) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t *t2 = reinterpret_cast<uint32_t *>(smem);                       // tile_rows x kT2Pitch pixel pairs
     uint32_t *s2 = t2 + tile_rows * kT2Pitch;                                // (ih + 2) x kS2Pitch packed strengths
@@ -96,9 +97,9 @@ __global__ void __launch_bounds__(kFastThreads, 8) fast_kernel(FrameGeom g,
     Cell cell;
     {
         int level = 0;
-        while (level + 1 < g.nlevels && (int)blockIdx.x >= g.lv[level + 1].cell_begin) ++level;
+        while (level + 1 < g.nlevels && cell_block >= g.lv[level + 1].cell_begin) ++level;
         const LevelGeom &G = g.lv[level];
-        const int local = blockIdx.x - G.cell_begin;
+        const int local = cell_block - G.cell_begin;
         const int ci = local / G.cols_eff, cj = local - ci * G.cols_eff;
         cell.level = (short)level;
         cell.x0 = (short)(kBorderMin + cj * G.w_cell);
@@ -106,7 +107,6 @@ __global__ void __launch_bounds__(kFastThreads, 8) fast_kernel(FrameGeom g,
         cell.cw = (short)(min(cell.x0 + G.w_cell + 6, G.w - kBorderMin) - cell.x0);
         cell.ch = (short)(min(cell.y0 + G.h_cell + 6, G.h - kBorderMin) - cell.y0);
     }
-    const int frame = blockIdx.y;
     const LevelGeom &L = g.lv[cell.level];
     const uint8_t *src;
     int spitch;
@@ -260,11 +260,54 @@ __global__ void __launch_bounds__(kFastThreads, 8) fast_kernel(FrameGeom g,
     }
 }
 
+__global__ void __launch_bounds__(kFastThreads, 8) fast_kernel(FrameGeom g,
+                                                             const uint8_t *__restrict__ lvl0_base, int lvl0_pitch,
+                                                             int64_t lvl0_stride, const uint8_t *__restrict__ pyr,
+                                                             Cand *__restrict__ cand, int *__restrict__ cand_count,
+                                                             int ini_th, int min_th, int tile_rows, int list_cap) {
+    fast_cell_body(g, lvl0_base, lvl0_pitch, lvl0_stride, pyr, cand, cand_count, ini_th, min_th, tile_rows, list_cap,
+                   blockIdx.x, blockIdx.y);
+}
+
+// FAST cells and Gaussian-blur blocks of the same frames in ONE grid.  The two are independent (both only read the
+// pyramid) and stress different units — FAST is bound by the ALU pipe (packed min/max), the blur by load latency and
+// the FMA pipe (IDP4A / IMAD) — so blur blocks are interleaved between FAST cells, `ratio` cells then one blur block,
+// and every SM holds a mix of both.  blockIdx.x -> role:
+//   x < nblur * (ratio + 1):  group x / (ratio + 1); position x % (ratio + 1) < ratio is cell group*ratio + position,
+//                             position == ratio is blur block `group`;
+//   beyond that:              the remaining cells.
+static_assert(kFastThreads == kBlurThreads, "the fused kernel runs both roles with the same block size");
+__global__ void __launch_bounds__(kFastThreads, 8) fast_blur_kernel(FrameGeom g, BlurLevels bl,
+                                                                  const uint8_t *__restrict__ lvl0_base, int lvl0_pitch,
+                                                                  int64_t lvl0_stride, const uint8_t *__restrict__ pyr,
+                                                                  uint8_t *__restrict__ blur, Cand *__restrict__ cand,
+                                                                  int *__restrict__ cand_count, int ini_th, int min_th,
+                                                                  int tile_rows, int list_cap, int nblur, int ratio) {
+    const int x = blockIdx.x, group = ratio + 1;
+    int cell;
+    if (x < nblur * group) {
+        const int gi = x / group, pos = x - gi * group;
+        if (pos == ratio) {
+            blur_block_body(g, bl, lvl0_base, lvl0_pitch, lvl0_stride, pyr, blur, gi, blockIdx.y);
+            return;
+        }
+        cell = gi * ratio + pos;
+    } else {
+        cell = nblur * ratio + (x - nblur * group);
+    }
+    fast_cell_body(g, lvl0_base, lvl0_pitch, lvl0_stride, pyr, cand, cand_count, ini_th, min_th, tile_rows, list_cap, cell,
+                   blockIdx.y);
+}
+
+// blur == nullptr: FAST alone; otherwise the fused FAST + blur grid.
 void launch_fast(const FrameGeom &g, const Cell *cells, const uint8_t *lvl0_base, int lvl0_pitch, int64_t lvl0_stride,
-                 const uint8_t *pyr, Cand *cand, int *cand_count, int ini_th, int min_th, int max_cw, int max_ch,
-                 int nframes, cudaStream_t s) {
+                 const uint8_t *pyr, uint8_t *blur, Cand *cand, int *cand_count, int ini_th, int min_th, int max_cw,
+                 int max_ch, int nframes, cudaStream_t s) {
     (void)cells;   // the kernel derives the cell geometry from the level tables
-    if (g.ncells == 0) return;
+    if (g.ncells == 0) {
+        if (blur) launch_blur(g, lvl0_base, lvl0_pitch, lvl0_stride, pyr, blur, nframes, s);
+        return;
+    }
     const int max_S = ((((max_cw - 6) + 1) >> 1) + 3) & ~3;
     if (3 + max_S + 6 + 3 > kT2Pitch || max_S + 2 > kS2Pitch || max_S * (max_ch - 6) > 32 * kFastThreads) {
         set_error("FAST cell larger than the shared-memory tile / the 32-iteration survivor masks");
@@ -276,10 +319,20 @@ void launch_fast(const FrameGeom &g, const Cell *cells, const uint8_t *lvl0_base
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         cudaFuncSetAttribute(fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(fast_blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    fast_kernel<<<dim3(g.ncells, nframes), kFastThreads, smem, s>>>(g, lvl0_base, lvl0_pitch, lvl0_stride, pyr, cand,
-                                                                  cand_count, ini_th, min_th, tile_rows, list_cap);
+    if (!blur) {
+        fast_kernel<<<dim3(g.ncells, nframes), kFastThreads, smem, s>>>(g, lvl0_base, lvl0_pitch, lvl0_stride, pyr, cand,
+                                                                      cand_count, ini_th, min_th, tile_rows, list_cap);
+    } else {
+        const BlurLevels bl = make_blur_levels(g);
+        const int nblur = bl.block_begin[g.nlevels];
+        const int ratio = g.ncells / nblur;
+        fast_blur_kernel<<<dim3(g.ncells + nblur, nframes), kFastThreads, smem, s>>>(
+            g, bl, lvl0_base, lvl0_pitch, lvl0_stride, pyr, blur, cand, cand_count, ini_th, min_th, tile_rows, list_cap, nblur,
+            ratio);
+    }
     count_launch();
 }
 

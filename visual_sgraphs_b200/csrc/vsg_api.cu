@@ -56,6 +56,7 @@ struct vsg_extractor {
     cudaStream_t aux[kAuxStreams] = {nullptr, nullptr};
     int chunk_frames = 64;
     int dev_chunk_frames = 0;          // device-resident batches: 0 = one pass on `stream`
+    bool fuse_fast_blur = true;
     cudaEvent_t fork_ev = nullptr, join_ev[kAuxStreams] = {nullptr, nullptr};
     vsg_orb_params p{};
     std::vector<float> scale, inv_scale, sigma2, inv_sigma2;
@@ -349,12 +350,13 @@ vsg_status run_pipeline(vsg_extractor *ex, cudaStream_t s, int f0, const uint8_t
         else launch_resize_level(g, l, ex->pyr + P.plane_offset, P.pitch, P.plane_stride, ex->pyr, nframes, s);
     }
     STAGE_MARK(1);
-    launch_fast(g, ex->cells_d, lvl0_base, lvl0_pitch, lvl0_stride, ex->pyr, ex->cand, cand_count, ex->p.ini_th_fast,
-                ex->p.min_th_fast, ex->max_cw, ex->max_ch, nframes, s);
+    // FAST cells and the Gaussian blur share one grid (fast.cu) unless VSG_FUSE_FAST_BLUR=0
+    launch_fast(g, ex->cells_d, lvl0_base, lvl0_pitch, lvl0_stride, ex->pyr, ex->fuse_fast_blur ? ex->blur : nullptr, ex->cand,
+                cand_count, ex->p.ini_th_fast, ex->p.min_th_fast, ex->max_cw, ex->max_ch, nframes, s);
     STAGE_MARK(2);
     launch_octree(g, ex->cand, cand_count, ex->node_of, level_kps, level_kp_count, ex->max_nodes, nframes, s);
     STAGE_MARK(3);
-    launch_blur(g, lvl0_base, lvl0_pitch, lvl0_stride, ex->pyr, ex->blur, nframes, s);
+    if (!ex->fuse_fast_blur) launch_blur(g, lvl0_base, lvl0_pitch, lvl0_stride, ex->pyr, ex->blur, nframes, s);
     STAGE_MARK(4);
     launch_describe(g, lvl0_base, lvl0_pitch, lvl0_stride, ex->pyr, ex->blur, level_kps, level_kp_count, lap_x0,
                     lap_x1, kps_dev, desc_dev, out_cap, n_dev, mono_dev, slot, nframes, s);
@@ -420,6 +422,7 @@ vsg_status vsg_extractor_create(const vsg_orb_params *params, int device, int ma
     }
     if (const char *e = getenv("VSG_CHUNK_FRAMES")) ex->chunk_frames = std::max(1, atoi(e));
     if (const char *e = getenv("VSG_DEV_CHUNK_FRAMES")) ex->dev_chunk_frames = std::max(0, atoi(e));
+    if (const char *e = getenv("VSG_FUSE_FAST_BLUR")) ex->fuse_fast_blur = atoi(e) != 0;
     cudaEventCreateWithFlags(&ex->fork_ev, cudaEventDisableTiming);
     for (cudaEvent_t &e : ex->join_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     *out = ex;

@@ -115,9 +115,10 @@ void launch_resize_level(const FrameGeom &g, int level, const uint8_t *src_base,
                          uint8_t *pyr, int nframes, cudaStream_t s);
 void launch_blur(const FrameGeom &g, const uint8_t *lvl0_base, int lvl0_pitch, int64_t lvl0_stride, const uint8_t *pyr,
                  uint8_t *blur, int nframes, cudaStream_t s);
+// blur != nullptr: the Gaussian blur of the same frames runs inside the same grid (fast_blur_kernel)
 void launch_fast(const FrameGeom &g, const Cell *cells, const uint8_t *lvl0_base, int lvl0_pitch, int64_t lvl0_stride,
-                 const uint8_t *pyr, Cand *cand, int *cand_count, int ini_th, int min_th, int max_cw, int max_ch,
-                 int nframes, cudaStream_t s);
+                 const uint8_t *pyr, uint8_t *blur, Cand *cand, int *cand_count, int ini_th, int min_th, int max_cw,
+                 int max_ch, int nframes, cudaStream_t s);
 void launch_octree(const FrameGeom &g, const Cand *cand, const int *cand_count, unsigned short *node_of,
                    LevelKp *level_kps, int *level_kp_count, int max_quota_nodes, int nframes, cudaStream_t s);
 void launch_describe(const FrameGeom &g, const uint8_t *lvl0_base, int lvl0_pitch, int64_t lvl0_stride,
