@@ -98,6 +98,15 @@ vsg_status vsg_extract_batch(vsg_extractor *ex, const uint8_t *images, int nfram
                              size_t frame_stride, int lap_x0, int lap_x1, vsg_keypoint *keypoints_out,
                              uint8_t *descriptors_out, int capacity, int *n_out, int *mono_index_out);
 
+/* Batched operator() on interleaved 8-bit colour frames (`channels` = 3 or 4; r_first != 0: RGB / RGBA order, else
+ * BGR / BGRA): the cv::cvtColor(..., COLOR_*2GRAY) that Tracking::GrabImage{RGBD,Monocular,Stereo} runs ahead of the
+ * extractor (Tracking.cc:1526-1551, 1595-1608, 1646-1660) is done on the device, bit-exact with OpenCV's 8-bit path,
+ * and the gray frames feed the same pipeline.  `pitch` is the byte pitch of a colour row. */
+vsg_status vsg_extract_batch_color(vsg_extractor *ex, const uint8_t *images, int nframes, int width, int height, int pitch,
+                                   size_t frame_stride, int channels, int r_first, int lap_x0, int lap_x1,
+                                   vsg_keypoint *keypoints_out, uint8_t *descriptors_out, int capacity, int *n_out,
+                                   int *mono_index_out);
+
 /* Same, but the frames already live in device memory (frame f at images_dev + f*frame_stride; pitch
  * and base 16-byte aligned) and the results stay on the device: keypoints_dev / descriptors_dev /
  * n_dev / mono_dev are device pointers sized as above.  Asynchronous on the handle's stream; call
@@ -157,6 +166,19 @@ vsg_status vsg_knn2_dev(vsg_matcher *m, const uint8_t *query_dev, int nq, const 
  * lexicographic order — the step after the all-gather when the train set is sharded over GPUs. */
 vsg_status vsg_knn2_merge_dev(vsg_matcher *m, const int32_t *idx_parts_dev, const int32_t *dist_parts_dev, int nparts,
                               int nq, int32_t *out_idx_dev, int32_t *out_dist_dev);
+
+/* MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:340-417) for `npoints` map points at once: point p's observed
+ * descriptors are rows ptr[p] .. ptr[p+1]-1 of `descriptors` (in the reference's vDescriptors order).  best_out[p] =
+ * the row (relative to ptr[p]) with the smallest median Hamming distance to the others (median = sorted row entry
+ * 0.5*(N-1), first row wins ties), or -1 for a point without descriptors (the reference leaves mDescriptor alone). */
+vsg_status vsg_distinctive_descriptors(vsg_matcher *m, const uint8_t *descriptors, const int32_t *ptr, int npoints,
+                                       int32_t *best_out);
+
+/* The descriptor part of Frame::ComputeStereoFishEyeMatches (Frame.cc:1200-1208): knnMatch(k = 2) and Lowe's ratio
+ * test matches[0].distance < matches[1].distance * ratio (0.7 in the reference).  match_out[i] = train index or -1;
+ * dist_out (may be NULL) = best distance.  The KannalaBrandt8 triangulation gate that follows stays with the caller. */
+vsg_status vsg_knn2_ratio(vsg_matcher *m, const uint8_t *query, int nq, const uint8_t *train, int nt, float ratio,
+                          int32_t *match_out, int32_t *dist_out);
 
 /* Candidate-list ("windowed") search shared by the SearchByProjection family, SearchForInitialization,
  * Fuse and SearchBySim3: for each query i, scan its candidate train rows cand[cand_ptr[i]..cand_ptr[i+1])
@@ -342,6 +364,24 @@ vsg_status vsg_search_for_triangulation(vsg_matcher *m, const vsg_frame_view *KF
                                         int only_stereo, int coarse, const float *f12, const float *ep,
                                         const float *level_sigma2_2, int check_ori, int32_t *matches12_out,
                                         int *nmatches_out);
+
+/* ------------------------------------------------------------------------------------------------
+ * BoW transform — the per-feature tree walk of DBoW2::TemplatedVocabulary::transform as called by Frame::ComputeBoW /
+ * KeyFrame::ComputeBoW (Frame.cc:882-889, KeyFrame.cc:99-108 -> Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1139-1265).
+ * The vocabulary tree is uploaded once, flattened: node 0 is the root, the children of node i are
+ * child_idx[child_ptr[i] .. child_ptr[i+1]) in the order of m_nodes[i].children (ties go to the first child), leaves
+ * have no children; node_descriptors is nnodes x 32 bytes (the root's row is unused); levels = m_L.
+ * vsg_bow_transform returns, per descriptor, the leaf reached (the caller maps it to word_id / weight from its own
+ * vocabulary object) and the node passed at level m_L - levelsup (the FeatureVector node; 0 = root when that level is
+ * <= 0 or the leaf is reached earlier).  BowVector::addWeight, FeatureVector::addFeature and the L1 normalisation are
+ * O(N) double-precision bookkeeping in feature order and stay with the caller (INTEGRATION.md shows the loop).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct vsg_vocabulary vsg_vocabulary;
+vsg_status vsg_vocabulary_create(vsg_matcher *m, int nnodes, const int32_t *child_ptr, const int32_t *child_idx,
+                                 const uint8_t *node_descriptors, int levels, vsg_vocabulary **out);
+void vsg_vocabulary_destroy(vsg_vocabulary *v);
+vsg_status vsg_bow_transform(vsg_matcher *m, const vsg_vocabulary *voc, const uint8_t *descriptors, int n, int levelsup,
+                             int32_t *leaf_node_out, int32_t *feature_node_out);
 
 /* Frame::ComputeStereoMatches (Frame.cc:957-1127): for every left keypoint the best right keypoint in its row
  * band (octave +-1, uR in [uL - mbf/mb, uL], Hamming < TH_HIGH), then — if the distance is below

@@ -7,6 +7,7 @@
  */
 #include "oracle.h"
 
+#include <algorithm>
 #include <climits>
 #include <cmath>
 #include <cstring>
@@ -601,5 +602,54 @@ int orc_search_for_triangulation(const orc_frame_view *KF1, const uint8_t *has_m
     return nmatches;
 }
 
+
+// MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:383-409) for one point: N descriptors -> BestIdx
+int orc_distinctive_descriptor(const uint8_t *desc, int n) {
+    if (n <= 0) return -1;
+    std::vector<float> distances((size_t)n * n);
+    for (int i = 0; i < n; ++i) {
+        distances[(size_t)i * n + i] = 0;
+        for (int j = i + 1; j < n; ++j) {
+            const int distij = descriptor_distance(desc + (size_t)i * 32, desc + (size_t)j * 32);
+            distances[(size_t)i * n + j] = (float)distij;
+            distances[(size_t)j * n + i] = (float)distij;
+        }
+    }
+    int best_median = INT_MAX, best_idx = 0;
+    for (int i = 0; i < n; ++i) {
+        std::vector<int> v(distances.begin() + (size_t)i * n, distances.begin() + (size_t)(i + 1) * n);
+        std::sort(v.begin(), v.end());
+        const int median = v[(size_t)(0.5 * (n - 1))];
+        if (median < best_median) { best_median = median; best_idx = i; }
+    }
+    return best_idx;
+}
+
+// TemplatedVocabulary::transform(feature, word_id, weight, nid, levelsup) (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:
+// 1225-1265) on a flattened tree (children of node i = child_idx[child_ptr[i] .. child_ptr[i+1]), FORB::distance =
+// the 256-bit Hamming distance, FORB.cpp:81-101).  leaf[i] = final node, nid[i] = node at level L - levelsup.
+void orc_bow_transform(const int32_t *child_ptr, const int32_t *child_idx, const uint8_t *node_desc, int levels,
+                       const uint8_t *desc, int n, int levelsup, int32_t *leaf, int32_t *nid_out) {
+    for (int f = 0; f < n; ++f) {
+        const uint8_t *feature = desc + (size_t)f * 32;
+        const int nid_level = levels - levelsup;
+        int nid = 0;                                  // `if (nid_level <= 0 && nid != NULL) *nid = 0;  // root`
+        int final_id = 0, current_level = 0;
+        do {
+            ++current_level;
+            const int cb = child_ptr[final_id], ce = child_ptr[final_id + 1];
+            final_id = child_idx[cb];
+            double best_d = (double)descriptor_distance(feature, node_desc + (size_t)final_id * 32);
+            for (int c = cb + 1; c < ce; ++c) {
+                const int id = child_idx[c];
+                const double d = (double)descriptor_distance(feature, node_desc + (size_t)id * 32);
+                if (d < best_d) { best_d = d; final_id = id; }
+            }
+            if (current_level == nid_level) nid = final_id;
+        } while (child_ptr[final_id] != child_ptr[final_id + 1]);   // !isLeaf()
+        leaf[f] = final_id;
+        nid_out[f] = nid;
+    }
+}
 
 }  // extern "C"

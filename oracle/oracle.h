@@ -81,6 +81,9 @@ void orc_orb_descriptor(const uint8_t *img, int pitch, int x, int y, float angle
 int orc_distribute_octree(const float *xyr, int n, int min_x, int max_x, int min_y, int max_y, int quota,
                           int32_t *selected_idx, int cap);
 
+/* cv::cvtColor(..., COLOR_{RGB,BGR,RGBA,BGRA}2GRAY) on 8-bit images (Tracking.cc:1595-1608) */
+void orc_cvt_gray(const uint8_t *src, int w, int h, int pitch, int channels, int r_first, uint8_t *dst, int dst_pitch);
+
 /* ---- matcher arithmetic (ORBmatcher.cc) on flattened views ---- */
 int orc_descriptor_distance(const uint8_t *a, const uint8_t *b);
 
@@ -182,6 +185,13 @@ int orc_search_for_triangulation(const orc_frame_view *KF1, const uint8_t *has_m
                                  const int32_t *idx1, int nn2, const int32_t *nodes2, const int32_t *ptr2,
                                  const int32_t *idx2, int only_stereo, int coarse, const float *f12, const float *ep,
                                  const float *level_sigma2_2, int check_ori, int32_t *matches12);
+
+/* DBoW2 TemplatedVocabulary::transform tree walk (TemplatedVocabulary.h:1225-1265) on a flattened tree. */
+void orc_bow_transform(const int32_t *child_ptr, const int32_t *child_idx, const uint8_t *node_desc, int levels,
+                       const uint8_t *desc, int n, int levelsup, int32_t *leaf, int32_t *nid);
+
+/* MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:340-417) for one point with n observed descriptors. */
+int orc_distinctive_descriptor(const uint8_t *desc, int n);
 
 /* Frame::ComputeStereoMatches (Frame.cc:957-1127): row-band Hamming search, 11x11 SAD refinement on the
  * un-blurred pyramids of both extractors (their last orc_extract call), parabola fit, median-based outlier

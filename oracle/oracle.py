@@ -70,6 +70,7 @@ def lib():
         L.orc_ic_angle.argtypes = [vp, C.c_int, C.c_int, C.c_int]
         L.orc_orb_descriptor.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_float, vp]
         L.orc_distribute_octree.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int]
+        L.orc_cvt_gray.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int]
         L.orc_descriptor_distance.argtypes = [vp, vp]
         L.orc_get_features_in_area.argtypes = [vp, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, vp, C.c_int]
         L.orc_three_maxima.argtypes = [vp, C.c_int, i32p, i32p, i32p]
@@ -84,6 +85,8 @@ def lib():
         L.orc_search_by_bow_kf.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, C.c_float, C.c_int, vp]
         L.orc_search_for_triangulation.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int,
                                                    C.c_int, vp, vp, vp, C.c_int, vp]
+        L.orc_distinctive_descriptor.argtypes = [vp, C.c_int]
+        L.orc_bow_transform.argtypes = [vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, vp, vp]
         L.orc_stereo_matches.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_float, C.c_float, vp, vp]
         L.orc_bench_extract.restype = C.c_double
         L.orc_bench_extract.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
@@ -229,6 +232,15 @@ def distribute_octree(xyr, min_x, max_x, min_y, max_y, quota):
     return out[:m].copy()
 
 
+def cvt_gray(img, rgb=True):
+    """cv::cvtColor(img, COLOR_{RGB,BGR}[A]2GRAY) for an (h, w, 3|4) uint8 image."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w, ch = img.shape
+    out = np.zeros((h, w), np.uint8)
+    lib().orc_cvt_gray(_ptr(img), w, h, img.strides[0], ch, int(bool(rgb)), _ptr(out), w)
+    return out
+
+
 def descriptor_distance(a, b):
     a = np.ascontiguousarray(a, np.uint8)
     b = np.ascontiguousarray(b, np.uint8)
@@ -369,3 +381,21 @@ def search_for_triangulation(view1, has1, view2, has2, fv1, fv2, only_stereo, co
                                             int(only_stereo), int(coarse), _ptr(f12), _ptr(ep), _ptr(sig), int(check_ori),
                                             _ptr(out))
     return nm, out[:view1.n]
+
+
+def distinctive_descriptor(desc):
+    """MapPoint::ComputeDistinctiveDescriptors for one point: (n, 32) uint8 -> BestIdx (-1 if n == 0)."""
+    desc = _u8(desc).reshape(-1, 32)
+    return lib().orc_distinctive_descriptor(_ptr(desc), len(desc))
+
+
+def bow_transform(child_ptr, child_idx, node_desc, levels, desc, levelsup=4):
+    """DBoW2 tree walk per descriptor -> (leaf node, FeatureVector node)."""
+    child_ptr = np.ascontiguousarray(child_ptr, np.int32)
+    child_idx = np.ascontiguousarray(child_idx, np.int32)
+    node_desc, desc = _u8(node_desc).reshape(-1, 32), _u8(desc).reshape(-1, 32)
+    leaf = np.zeros(max(len(desc), 1), np.int32)
+    nid = np.zeros(max(len(desc), 1), np.int32)
+    lib().orc_bow_transform(_ptr(child_ptr), _ptr(child_idx), _ptr(node_desc), int(levels), _ptr(desc), len(desc),
+                            int(levelsup), _ptr(leaf), _ptr(nid))
+    return leaf[:len(desc)], nid[:len(desc)]

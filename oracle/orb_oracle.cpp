@@ -793,6 +793,19 @@ void orc_stereo_matches(const orc_extractor *left, const orc_extractor *right, c
     }
 }
 
+// cv::cvtColor(src, dst, COLOR_{RGB,BGR,RGBA,BGRA}2GRAY) for 8-bit images, as run by Tracking::GrabImageRGBD /
+// GrabImageMonocular / GrabImageStereo ahead of the extractor (Tracking.cc:1526-1551, 1595-1608, 1646-1660).
+// OpenCV's fixed-point path: 15-bit coefficients R 9798, G 19235, B 3735, round to nearest (pinned against cv2 4.13).
+void orc_cvt_gray(const uint8_t *src, int w, int h, int pitch, int channels, int r_first, uint8_t *dst, int dst_pitch) {
+    const int ri = r_first ? 0 : 2, bi = r_first ? 2 : 0;
+    for (int y = 0; y < h; ++y) {
+        const uint8_t *s = src + (size_t)y * pitch;
+        uint8_t *d = dst + (size_t)y * dst_pitch;
+        for (int x = 0; x < w; ++x, s += channels)
+            d[x] = (uint8_t)((s[ri] * 9798 + s[1] * 19235 + s[bi] * 3735 + (1 << 14)) >> 15);
+    }
+}
+
 double orc_bench_extract(const uint8_t *frames, int nframes, int w, int h, int nfeatures, float scale_factor,
                          int nlevels, int ini_th, int min_th, int threads, int64_t *total_keypoints) {
     if (threads < 1) threads = 1;

@@ -113,3 +113,43 @@ def translation_f12(shift):
     nrm = np.hypot(sx, sy)
     nx, ny = -sy / nrm, sx / nrm
     return np.array([0, 0, -nx, 0, 0, -ny, nx, ny, 0], np.float32)
+
+
+def synthetic_vocabulary(seed, k=10, levels=4, prune=0.08):
+    """A stand-in for ORBvoc (the blob is not in the checkout): a k-ary tree of depth `levels` whose node descriptors
+    are their parent's descriptor with random bit flips (fewer flips deeper down, like k-majority cluster centres).
+    A few inner nodes are pruned to leaves so that the tree is unbalanced, like DBoW2's HKmeans can leave it.
+    Returns dict(child_ptr, child_idx, node_desc, word_id, weight, levels); node 0 is the root."""
+    rng = np.random.default_rng(seed)
+    desc = [np.zeros(32, np.uint8)]
+    children = [[]]
+    depth = [0]
+    frontier = [0]
+    for lvl in range(1, levels + 1):
+        nxt = []
+        for parent in frontier:
+            if lvl > 1 and rng.random() < prune:
+                continue                                   # stays a leaf
+            for _ in range(k):
+                flips = np.packbits(rng.random(256) < (0.5 if lvl == 1 else 0.25 / lvl))
+                desc.append(desc[parent] ^ flips if lvl > 1 else rng.integers(0, 256, 32, dtype=np.uint8))
+                children.append([])
+                depth.append(lvl)
+                children[parent].append(len(desc) - 1)
+                nxt.append(len(desc) - 1)
+        frontier = nxt
+    if len(children[1]) > 2:
+        desc[children[1][2]] = desc[children[1][0]].copy()  # equal distances: the first child must win
+    child_ptr, child_idx = [0], []
+    for c in children:
+        child_idx.extend(c)
+        child_ptr.append(len(child_idx))
+    n = len(desc)
+    word_id = np.full(n, -1, np.int64)
+    leaves = [i for i in range(n) if not children[i]]
+    word_id[leaves] = np.arange(len(leaves))
+    weight = np.zeros(n)
+    weight[leaves] = rng.uniform(0.2, 8.0, len(leaves))
+    weight[leaves[::37]] = 0.0                             # stopped words (weight 0)
+    return dict(child_ptr=np.array(child_ptr, np.int32), child_idx=np.array(child_idx, np.int32),
+                node_desc=np.stack(desc), word_id=word_id, weight=weight, levels=levels)

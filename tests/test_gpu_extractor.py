@@ -208,3 +208,24 @@ def test_chunked_pipeline_matches_single_stream(oracle, monkeypatch, pinned):
         _compare_outputs(res[f], orc(frames[f]), "chunked frame %d" % f)
     orc(frames[7])
     assert np.array_equal(ex.pyramid_level(3, frame=7), orc.level(3))
+
+
+@pytest.mark.parametrize("channels,rgb", [(3, True), (3, False), (4, True), (4, False)])
+def test_colour_ingest_matches_gray_path(oracle, channels, rgb):
+    """vsg_extract_batch_color: cvtColor on the device (Tracking.cc:1595-1608) then the same pipeline; must equal the
+    gray path fed with the oracle's (cv2-pinned) conversion, including a width that is not a multiple of 4."""
+    rng = np.random.default_rng(17 + channels + rgb)
+    for w, h, nf in ((640, 480, 3), (322, 243, 2)):
+        gray = synth_sequence(nf, w, h, first_seed=9100)
+        col = np.empty((nf, h, w, channels), np.uint8)
+        # a colour image whose luma has structure: gray plus per-channel offsets and noise
+        for c in range(channels):
+            col[..., c] = np.clip(gray.astype(np.int16) + rng.integers(-20, 21, gray.shape), 0, 255)
+        ex = _extractor(700, max_batch=nf)
+        got = ex.extract_batch_color(col, rgb=rgb)
+        ref = _extractor(700)
+        for f in range(nf):
+            g = oracle.cvt_gray(col[f], rgb)
+            m, k, d = ref(g)
+            assert got[f][0] == m and got[f][1].tobytes() == k.tobytes() and np.array_equal(got[f][2], d), (w, f)
+            assert np.array_equal(ex.pyramid_level(0, frame=f), g)

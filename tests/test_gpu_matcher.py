@@ -121,3 +121,70 @@ def test_match_window_matches_sequential_scan(init):
     want2 = window_ref(q, t, cand_ptr, cand, None, None, init)
     for k in want2:
         assert np.array_equal(got2[k], want2[k]), k
+
+
+def test_distinctive_descriptors_batch(oracle):
+    """vsg_distinctive_descriptors against the oracle's MapPoint::ComputeDistinctiveDescriptors restatement, for a batch
+    of map points with 0 .. 1500 observations (1500 > the shared-memory staging limit)."""
+    from visual_sgraphs_b200.matcher import ORBmatcher
+    rng = np.random.default_rng(5)
+    sizes = [0, 1, 2, 3, 5, 8, 13, 31, 32, 33, 64, 100, 257, 1500] + rng.integers(1, 40, 300).tolist()
+    descs, ptr = [], [0]
+    for n in sizes:
+        base = rng.integers(0, 256, 32, dtype=np.uint8)
+        d = np.stack([base ^ np.packbits(rng.random(256) < rng.uniform(0.02, 0.3)) for _ in range(n)]) if n else \
+            np.zeros((0, 32), np.uint8)
+        if n > 3:
+            d[3] = d[1]
+        descs.append(d)
+        ptr.append(ptr[-1] + n)
+    got = ORBmatcher().ComputeDistinctiveDescriptors(np.concatenate(descs), ptr)
+    want = [oracle.distinctive_descriptor(d) for d in descs]
+    assert got.tolist() == want
+
+
+def test_knn2_ratio_filter(oracle):
+    from visual_sgraphs_b200.matcher import ORBmatcher
+    from visual_sgraphs_b200.synth import synth_query_train
+    q, t = synth_query_train(9, 300, 2000)
+    m = ORBmatcher()
+    match, dist = m.knn2_ratio(q, t, 0.7)
+    idx, d = m.knn2(q, t)
+    want = np.where(d[:, 0].astype(np.float32) < d[:, 1].astype(np.float32).astype(np.float64) * np.float64(np.float32(0.7)), idx[:, 0], -1)
+    assert np.array_equal(match, want) and np.array_equal(dist, d[:, 0])
+    assert (match >= 0).sum() > 10
+    one, _ = m.knn2_ratio(q[:5], t[:1], 0.7)          # fewer than two neighbours: (*it).size() >= 2 fails
+    assert (one == -1).all()
+
+
+def test_bow_transform(oracle):
+    """vsg_bow_transform (GPU tree walk) against the oracle's restatement of DBoW2's transform, and the BowVector /
+    FeatureVector bookkeeping of Vocabulary.transform against a direct restatement of TemplatedVocabulary.h:1139-1205."""
+    from tests import match_scenarios as sc
+    from visual_sgraphs_b200.matcher import ORBmatcher
+    from visual_sgraphs_b200.vocabulary import Vocabulary
+    voc = sc.synthetic_vocabulary(4, k=10, levels=4)
+    m = ORBmatcher()
+    V = Vocabulary(m, voc["child_ptr"], voc["child_idx"], voc["node_desc"], voc["word_id"], voc["weight"], voc["levels"])
+    rng = np.random.default_rng(2)
+    nd = voc["node_desc"]
+    feats = np.stack([nd[rng.integers(1, len(nd))] ^ np.packbits(rng.random(256) < 0.08) for _ in range(2000)])
+    feats[0] = nd[voc["child_idx"][voc["child_ptr"][1]]]
+    for levelsup in (4, 2, 1, 0, 6):
+        leaf, nid = V.walk(feats, levelsup)
+        wleaf, wnid = oracle.bow_transform(voc["child_ptr"], voc["child_idx"], nd, voc["levels"], feats, levelsup)
+        assert np.array_equal(leaf, wleaf) and np.array_equal(nid, wnid), levelsup
+    bow, (nodes, ptr_, idx) = V.transform(feats, 2)
+    wleaf, wnid = oracle.bow_transform(voc["child_ptr"], voc["child_idx"], nd, voc["levels"], feats, 2)
+    want_v, want_fv = {}, {}
+    for i in range(len(feats)):
+        w = voc["weight"][wleaf[i]]
+        if w > 0:
+            want_v[int(voc["word_id"][wleaf[i]])] = want_v.get(int(voc["word_id"][wleaf[i]]), 0.0) + w
+            want_fv.setdefault(int(wnid[i]), []).append(i)
+    s = sum(abs(want_v[k]) for k in sorted(want_v))
+    assert bow == {k: v / s for k, v in want_v.items()}
+    assert nodes.tolist() == sorted(want_fv) and idx.tolist() == [i for k in sorted(want_fv) for i in want_fv[k]]
+    assert len(nodes) > 5 and abs(sum(bow.values()) - 1.0) < 1e-9
+    walk0, _ = V.walk(np.zeros((0, 32), np.uint8))
+    assert len(walk0) == 0

@@ -164,3 +164,19 @@ def test_blur_and_angles_and_descriptors_match_cv2(oracle):
             assert np.array_equal(d, desc[row + i]), (level, i)
         row += len(lk)
     assert row == len(kps) and mono == len(kps)
+
+
+@pytest.mark.parametrize("channels", [3, 4])
+@pytest.mark.parametrize("rgb", [True, False])
+def test_cvt_gray_matches_cv2(oracle, channels, rgb):
+    """Tracking::GrabImageRGBD's cvtColor (Tracking.cc:1595-1608) for RGB / BGR / RGBA / BGRA inputs."""
+    rng = np.random.default_rng(channels * 2 + rgb)
+    code = {(3, True): cv2.COLOR_RGB2GRAY, (3, False): cv2.COLOR_BGR2GRAY, (4, True): cv2.COLOR_RGBA2GRAY,
+            (4, False): cv2.COLOR_BGRA2GRAY}[(channels, rgb)]
+    for shape in ((480, 640), (97, 131), (5, 3)):
+        img = rng.integers(0, 256, shape + (channels,), dtype=np.uint8)
+        assert np.array_equal(oracle.cvt_gray(img, rgb), cv2.cvtColor(img, code))
+    ramp = np.stack(list(np.meshgrid(np.arange(256), np.arange(256), indexing="ij")) + [np.full((256, 256), 77)], -1).astype(np.uint8)
+    if channels == 4:
+        ramp = np.concatenate([ramp, ramp[..., :1]], -1)
+    assert np.array_equal(oracle.cvt_gray(ramp, rgb), cv2.cvtColor(np.ascontiguousarray(ramp), code))

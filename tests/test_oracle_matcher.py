@@ -128,3 +128,39 @@ def test_search_by_projection_map_matches_python_restatement(oracle):
             wnm, wassign = py_search_by_projection_map(fd, occ, pts, desc, th, far, 40.0, 0.8)
             assert nm == wnm and np.array_equal(assign, wassign)
             assert nm > 20
+
+
+def test_distinctive_descriptor_matches_python_restatement(oracle):
+    """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:383-409): least median distance, first row on ties."""
+    rng = np.random.default_rng(31)
+    assert oracle.distinctive_descriptor(np.zeros((0, 32), np.uint8)) == -1
+    for n in (1, 2, 3, 4, 7, 16, 33):
+        for trial in range(6):
+            base = rng.integers(0, 256, 32, dtype=np.uint8)
+            d = np.stack([base ^ np.packbits(rng.random(256) < rng.uniform(0.02, 0.3)) for _ in range(n)])
+            if trial == 0 and n > 2:
+                d[2] = d[0]                     # identical observations: ties in the medians
+            dm = np.array([[hamming(a, b) for b in d] for a in d])
+            med = [sorted(row)[int(0.5 * (n - 1))] for row in dm]
+            assert oracle.distinctive_descriptor(d) == int(np.argmin(med))
+
+
+def test_bow_tree_walk_matches_python_restatement(oracle):
+    """TemplatedVocabulary::transform(feature, ...) (TemplatedVocabulary.h:1225-1265) on a synthetic unbalanced tree."""
+    voc = sc.synthetic_vocabulary(4, k=6, levels=3)
+    rng = np.random.default_rng(8)
+    nd = voc["node_desc"]
+    feats = np.stack([nd[rng.integers(1, len(nd))] ^ np.packbits(rng.random(256) < 0.1) for _ in range(150)])
+    feats[0] = nd[voc["child_idx"][voc["child_ptr"][1]]]      # sits exactly on the duplicated child: tie -> first child
+    for levelsup in (1, 2, 3, 5):
+        leaf, nid = oracle.bow_transform(voc["child_ptr"], voc["child_idx"], nd, voc["levels"], feats, levelsup)
+        for f in range(len(feats)):
+            node, lvl, want_nid = 0, 0, 0
+            while voc["child_ptr"][node] != voc["child_ptr"][node + 1]:
+                lvl += 1
+                kids = voc["child_idx"][voc["child_ptr"][node]:voc["child_ptr"][node + 1]]
+                d = [hamming(feats[f], nd[c]) for c in kids]
+                node = int(kids[int(np.argmin(d))])
+                if lvl == voc["levels"] - levelsup:
+                    want_nid = node
+            assert leaf[f] == node and nid[f] == want_nid, (levelsup, f)

@@ -126,6 +126,52 @@ void launch_resize_level(const FrameGeom &g, int level, const uint8_t *src_base,
     count_launch();
 }
 
+// ------------------------------------------------------------------------------------------------
+// colour ingest: cv::cvtColor(RGB|BGR|RGBA|BGRA -> GRAY) as Tracking::GrabImageRGBD / GrabImageMonocular /
+// GrabImageStereo run it ahead of the extractor (orb_slam3/src/Tracking.cc:1526-1551, 1595-1608, 1646-1660).
+// OpenCV's 8-bit path: gray = (R*9798 + G*19235 + B*3735 + (1 << 14)) >> 15 (verified bit-exact against cv2 4.13).
+// One thread converts 4 pixels: 3 (or 4) aligned 32-bit loads, one 32-bit store into the level-0 plane.
+// ------------------------------------------------------------------------------------------------
+template <int kChannels>
+__global__ void __launch_bounds__(128) cvt_gray_kernel(const uint8_t *__restrict__ src, int src_pitch, int64_t src_stride,
+                                                       uint8_t *__restrict__ dst, int dst_pitch, int64_t dst_stride, int w,
+                                                       int h, int r_first) {
+    const int x4 = (blockIdx.x * 128 + threadIdx.x) * 4, y = blockIdx.y;
+    if (x4 >= w) return;
+    const uint8_t *row = src + (int64_t)blockIdx.z * src_stride + (int64_t)y * src_pitch + (int64_t)x4 * kChannels;
+    uint8_t px[4][4];
+    if (x4 + 4 <= w) {
+        uint32_t words[kChannels];
+#pragma unroll
+        for (int k = 0; k < kChannels; ++k) words[k] = __ldg(reinterpret_cast<const uint32_t *>(row) + k);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int byte = i * kChannels + c;
+                px[i][c] = (uint8_t)(words[byte >> 2] >> (8 * (byte & 3)));
+            }
+    } else {
+        for (int i = 0; i < 4; ++i)
+            for (int c = 0; c < 3; ++c) px[i][c] = x4 + i < w ? __ldg(row + i * kChannels + c) : 0;
+    }
+    const uint32_t c0 = r_first ? 9798u : 3735u, c2 = r_first ? 3735u : 9798u;
+    uint32_t out = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out |= ((px[i][0] * c0 + px[i][1] * 19235u + px[i][2] * c2 + (1u << 14)) >> 15) << (8 * i);
+    uint8_t *d = dst + (int64_t)blockIdx.z * dst_stride + (int64_t)y * dst_pitch + x4;
+    if (x4 + 4 <= w) *reinterpret_cast<uint32_t *>(d) = out;   // level-0 planes have a pitch that is a multiple of 64
+    else for (int i = 0; x4 + i < w; ++i) d[i] = (uint8_t)(out >> (8 * i));
+}
+
+void launch_cvt_gray(const uint8_t *src, int src_pitch, int64_t src_stride, int channels, int r_first, uint8_t *dst,
+                     int dst_pitch, int64_t dst_stride, int w, int h, int nframes, cudaStream_t s) {
+    dim3 grid(((w + 3) / 4 + 127) / 128, h, nframes);
+    if (channels == 3) cvt_gray_kernel<3><<<grid, 128, 0, s>>>(src, src_pitch, src_stride, dst, dst_pitch, dst_stride, w, h, r_first);
+    else cvt_gray_kernel<4><<<grid, 128, 0, s>>>(src, src_pitch, src_stride, dst, dst_pitch, dst_stride, w, h, r_first);
+    count_launch();
+}
+
 }  // namespace vsg
 
 #include "blur_device.cuh"

@@ -57,6 +57,8 @@ struct vsg_extractor {
     int chunk_frames = 64;
     int dev_chunk_frames = 0;          // device-resident batches: 0 = one pass on `stream`
     bool fuse_fast_blur = true;
+    uint8_t *color_d = nullptr;        // device staging of colour frames (vsg_extract_batch_color), allocated on first use
+    size_t color_bytes = 0;
     cudaEvent_t fork_ev = nullptr, join_ev[kAuxStreams] = {nullptr, nullptr};
     vsg_orb_params p{};
     std::vector<float> scale, inv_scale, sigma2, inv_sigma2;
@@ -116,7 +118,8 @@ struct vsg_extractor {
     void free_shape() {
         cudaFree(cells_d); cudaFree(tabs_d); cudaFree(pyr); cudaFree(blur); cudaFree(cand); cudaFree(node_of);
         cudaFree(cand_count); cudaFree(level_kps); cudaFree(level_kp_count); cudaFree(slot); cudaFree(kps_d);
-        cudaFree(desc_d); cudaFree(n_d); cudaFree(mono_d);
+        cudaFree(desc_d); cudaFree(n_d); cudaFree(mono_d); cudaFree(color_d);
+        color_d = nullptr; color_bytes = 0;
         cudaFreeHost(kps_h); cudaFreeHost(desc_h); cudaFreeHost(n_h); cudaFreeHost(mono_h);
         cells_d = nullptr; tabs_d = nullptr; pyr = blur = nullptr; cand = nullptr; node_of = nullptr;
         cand_count = nullptr; level_kps = nullptr; level_kp_count = nullptr; slot = nullptr; kps_d = nullptr;
@@ -465,18 +468,29 @@ int vsg_extractor_max_keypoints(vsg_extractor *ex, int width, int height) {
     return ex->g.out_cap;
 }
 
-vsg_status vsg_extract_batch(vsg_extractor *ex, const uint8_t *images, int nframes, int width, int height, int pitch,
-                             size_t frame_stride, int lap_x0, int lap_x1, vsg_keypoint *keypoints_out,
-                             uint8_t *descriptors_out, int capacity, int *n_out, int *mono_index_out) {
+// channels == 1: 8-bit gray frames; 3 / 4: interleaved colour frames converted on the device (r_first: the first channel
+// is red, i.e. COLOR_RGB2GRAY / COLOR_RGBA2GRAY, else the BGR variants)
+static vsg_status extract_batch_host(vsg_extractor *ex, const uint8_t *images, int nframes, int width, int height, int pitch,
+                                     size_t frame_stride, int channels, int r_first, int lap_x0, int lap_x1,
+                                     vsg_keypoint *keypoints_out, uint8_t *descriptors_out, int capacity, int *n_out,
+                                     int *mono_index_out) {
     if (!ex) return VSG_ERR_INVALID;
     if (!images || width <= 0 || height <= 0 || nframes <= 0) return VSG_EMPTY_IMAGE;   // :1087-1088
-    if (nframes > ex->max_batch || pitch < width || capacity < 0) {
-        set_error("vsg_extract_batch: nframes %d > max_batch %d, or bad pitch/capacity", nframes, ex->max_batch);
+    if (nframes > ex->max_batch || pitch < width * channels || capacity < 0 || (channels != 1 && channels != 3 && channels != 4)) {
+        set_error("vsg_extract_batch: nframes %d > max_batch %d, or bad pitch/capacity/channels", nframes, ex->max_batch);
         return VSG_ERR_INVALID;
     }
     CK(cudaSetDevice(ex->device));
     vsg_status st = configure_shape(ex, width, height);
     if (st != VSG_OK) return st;
+    const int cpitch = (width * channels + 63) & ~63;                   // staging pitch of a colour row
+    const size_t cstride = (size_t)cpitch * height;
+    if (channels != 1 && ex->color_bytes < cstride * ex->max_batch) {
+        cudaFree(ex->color_d);
+        ex->color_d = nullptr; ex->color_bytes = 0;
+        CK(cudaMalloc(&ex->color_d, cstride * ex->max_batch));
+        ex->color_bytes = cstride * ex->max_batch;
+    }
     const FrameGeom &g = ex->g;
     const LevelGeom &L0 = g.lv[0];
     uint8_t *lvl0 = ex->pyr + L0.plane_offset;
@@ -502,7 +516,18 @@ vsg_status vsg_extract_batch(vsg_extractor *ex, const uint8_t *images, int nfram
         nstreams_used = std::min(3, c + 1);
         uint8_t *dst0 = lvl0 + (int64_t)f0 * L0.plane_stride;
         const uint8_t *src0 = images + (size_t)f0 * frame_stride;
-        if (tight) {
+        if (channels != 1) {
+            uint8_t *c0 = ex->color_d + (size_t)f0 * cstride;
+            if (frame_stride == (size_t)pitch * height) {
+                CK(cudaMemcpy2DAsync(c0, cpitch, src0, pitch, (size_t)width * channels, (size_t)height * nf,
+                                     cudaMemcpyHostToDevice, s));
+            } else {
+                for (int f = 0; f < nf; ++f)
+                    CK(cudaMemcpy2DAsync(c0 + f * cstride, cpitch, src0 + f * frame_stride, pitch, (size_t)width * channels,
+                                         height, cudaMemcpyHostToDevice, s));
+            }
+            launch_cvt_gray(c0, cpitch, (int64_t)cstride, channels, r_first, dst0, L0.pitch, L0.plane_stride, width, height, nf, s);
+        } else if (tight) {
             CK(cudaMemcpy2DAsync(dst0, L0.pitch, src0, pitch, width, (size_t)height * nf, cudaMemcpyHostToDevice, s));
         } else {
             for (int f = 0; f < nf; ++f)
@@ -550,6 +575,22 @@ vsg_status vsg_extract_batch(vsg_extractor *ex, const uint8_t *images, int nfram
             memcpy(descriptors_out + (size_t)f * capacity * 32, ex->desc_h + (size_t)f * g.out_cap * 32, (size_t)n * 32);
     }
     return ret;
+}
+
+vsg_status vsg_extract_batch(vsg_extractor *ex, const uint8_t *images, int nframes, int width, int height, int pitch,
+                             size_t frame_stride, int lap_x0, int lap_x1, vsg_keypoint *keypoints_out,
+                             uint8_t *descriptors_out, int capacity, int *n_out, int *mono_index_out) {
+    return extract_batch_host(ex, images, nframes, width, height, pitch, frame_stride, 1, 0, lap_x0, lap_x1, keypoints_out,
+                              descriptors_out, capacity, n_out, mono_index_out);
+}
+
+vsg_status vsg_extract_batch_color(vsg_extractor *ex, const uint8_t *images, int nframes, int width, int height, int pitch,
+                                   size_t frame_stride, int channels, int r_first, int lap_x0, int lap_x1,
+                                   vsg_keypoint *keypoints_out, uint8_t *descriptors_out, int capacity, int *n_out,
+                                   int *mono_index_out) {
+    if (channels != 3 && channels != 4) { set_error("vsg_extract_batch_color: channels must be 3 or 4"); return VSG_ERR_INVALID; }
+    return extract_batch_host(ex, images, nframes, width, height, pitch, frame_stride, channels, r_first, lap_x0, lap_x1,
+                              keypoints_out, descriptors_out, capacity, n_out, mono_index_out);
 }
 
 vsg_status vsg_extract(vsg_extractor *ex, const uint8_t *image, int width, int height, int pitch, int lap_x0,

@@ -113,6 +113,9 @@ void count_launch(int n = 1);
 // --- kernel launchers (each file documents the reference lines it implements) ---
 void launch_resize_level(const FrameGeom &g, int level, const uint8_t *src_base, int src_pitch, int64_t src_stride,
                          uint8_t *pyr, int nframes, cudaStream_t s);
+// cv::cvtColor(..., COLOR_{RGB,BGR,RGBA,BGRA}2GRAY) of `nframes` device frames into 8-bit planes (src 4-byte aligned)
+void launch_cvt_gray(const uint8_t *src, int src_pitch, int64_t src_stride, int channels, int r_first, uint8_t *dst,
+                     int dst_pitch, int64_t dst_stride, int w, int h, int nframes, cudaStream_t s);
 void launch_blur(const FrameGeom &g, const uint8_t *lvl0_base, int lvl0_pitch, int64_t lvl0_stride, const uint8_t *pyr,
                  uint8_t *blur, int nframes, cudaStream_t s);
 // blur != nullptr: the Gaussian blur of the same frames runs inside the same grid (fast_blur_kernel)

@@ -90,6 +90,22 @@ class ORBextractor:
                                         int(lapping[0]), int(lapping[1]), ptr(kps), ptr(desc), cap, ptr(n), ptr(mono)))
         return [(int(mono[f]), kps[f, : n[f]].copy(), desc[f, : n[f]].copy()) for f in range(nf)]
 
+    def extract_batch_color(self, frames, rgb=True, lapping=(0, 0)):
+        """frames: (n, h, w, 3|4) uint8 interleaved colour frames; rgb: channel order as Tracking's mbRGB flag.
+        cvtColor(..., COLOR_{RGB,BGR}[A]2GRAY) runs on the device. Returns list of (mono, kps, desc)."""
+        assert frames.dtype == np.uint8 and frames.ndim == 4 and frames.shape[3] in (3, 4) and frames.strides[3] == 1
+        nf, h, w, ch = frames.shape
+        assert frames.strides[2] == ch
+        cap = self.max_keypoints(w, h)
+        kps = np.zeros((nf, cap), KEYPOINT_DTYPE)
+        desc = np.zeros((nf, cap, 32), np.uint8)
+        n = np.zeros(nf, np.int32)
+        mono = np.zeros(nf, np.int32)
+        check(self._L.vsg_extract_batch_color(self._h, ptr(frames), nf, w, h, frames.strides[1], frames.strides[0], ch,
+                                              int(bool(rgb)), int(lapping[0]), int(lapping[1]), ptr(kps), ptr(desc), cap,
+                                              ptr(n), ptr(mono)))
+        return [(int(mono[f]), kps[f, : n[f]].copy(), desc[f, : n[f]].copy()) for f in range(nf)]
+
     def extract_batch_dev(self, frames_dev, kps_dev, desc_dev, n_dev, mono_dev, lapping=(0, 0)):
         """Device-resident variant: torch uint8 CUDA tensors. frames (n,h,w); kps (n,cap,28) u8; desc (n,cap,32)
         u8; n/mono int32 (n). Asynchronous on the handle's stream."""

@@ -78,6 +78,25 @@ class ORBmatcher:
         check(self._L.vsg_knn2_merge_dev(self._h, ptr(idx_parts_dev), ptr(dist_parts_dev), nparts, nq,
                                          ptr(out_idx_dev), ptr(out_dist_dev)))
 
+    def ComputeDistinctiveDescriptors(self, descriptors, ptr_):
+        """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:340-417) for many map points: descriptors (total, 32),
+        ptr_ (npoints + 1) CSR offsets. Returns best row per point (relative to its first row; -1 if it has none)."""
+        descriptors = np.ascontiguousarray(descriptors, np.uint8).reshape(-1, 32)
+        ptr_ = np.ascontiguousarray(ptr_, np.int32)
+        best = np.zeros(len(ptr_) - 1, np.int32)
+        check(self._L.vsg_distinctive_descriptors(self._h, ptr(descriptors), ptr(ptr_), len(best), ptr(best)))
+        return best
+
+    def knn2_ratio(self, query, train, ratio=0.7):
+        """knnMatch(k=2) + Lowe ratio of Frame::ComputeStereoFishEyeMatches (Frame.cc:1200-1208) -> (match, dist)."""
+        query = np.ascontiguousarray(query, np.uint8).reshape(-1, 32)
+        train = np.ascontiguousarray(train, np.uint8).reshape(-1, 32)
+        match = np.zeros(len(query), np.int32)
+        dist = np.zeros(len(query), np.int32)
+        check(self._L.vsg_knn2_ratio(self._h, ptr(query), len(query), ptr(train), len(train), float(ratio), ptr(match),
+                                     ptr(dist)))
+        return match, dist
+
     def match_window(self, query, train, cand_ptr, cand, skip=None, train_level=None, init_dist=256):
         """Best / second-best over per-query candidate lists (ORBmatcher.cc:77-120 idiom).
         Returns dict(best_idx, best_dist, second_dist, best_level, second_level)."""
