@@ -67,6 +67,18 @@ def make_frames(n, seed0):
     return out
 
 
+def ncu_traffic(kernel, frames):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture
+    (profiles/ncu_traffic.json), scaled from the captured frames per launch to this run's."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    if kernel not in d:
+        return None
+    return d[kernel]["dram_bytes_per_launch"] / d["frames_per_launch"] * frames
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -453,7 +465,10 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "fast_blur_kernel (FAST cells + Gaussian blur in one grid)" if fused and roof_stage == "fast" else roof_stage,
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak,
+                         "traffic": ncu_traffic("fast_blur_kernel", B) if fused and roof_stage == "fast" else None,
+                         "traffic_note": "bytes per launch; ncu capture at 64 frames per launch scaled to this batch",
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_frame": stages_bytes[roof_stage], "launch_ms": dur_ms,
                          "dominant_stage_by_time": dominant,
                          "note": "FAST/pyramid/blur are HBM-bound by bytes but issue-bound in practice (see DESIGN.md)"},
