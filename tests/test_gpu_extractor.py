@@ -229,3 +229,26 @@ def test_colour_ingest_matches_gray_path(oracle, channels, rgb):
             m, k, d = ref(g)
             assert got[f][0] == m and got[f][1].tobytes() == k.tobytes() and np.array_equal(got[f][2], d), (w, f)
             assert np.array_equal(ex.pyramid_level(0, frame=f), g)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_configurations(oracle, seed):
+    """Randomised extractor parameters and frame shapes (incl. KITTI's 1241x376 and widths that are not multiples of
+    4): every output must equal the oracle's — the constructor tables, cell grids, quotas and nIni all change."""
+    rng = np.random.default_rng(500 + seed)
+    shapes = [(1241, 376), (641, 479), (322, 243), (752, 480), (517, 389), (960, 540), (400, 400), (480, 640)]
+    w, h = shapes[seed % len(shapes)]
+    nfeat = int(rng.integers(200, 2500))
+    scale = float(np.float32(rng.choice([1.1, 1.2, 1.25, 1.3, 1.44])))
+    nlevels = int(rng.integers(3, 9))
+    while min(w, h) / (scale ** (nlevels - 1)) < 70:       # the smallest level must still hold one 35-px cell
+        nlevels -= 1
+    ini, mn = int(rng.integers(10, 40)), int(rng.integers(3, 10))
+    frame = synth_frame(7000 + seed, w, h)
+    if seed % 3 == 0:
+        frame = (frame // 4 + 96).astype(np.uint8)          # low contrast: many cells take the minThFAST retry
+    lap = (0, 0) if seed % 2 else (int(w * 0.3), int(w * 0.6))
+    from visual_sgraphs_b200.extractor import ORBextractor
+    got = ORBextractor(nfeat, scale, nlevels, ini, mn)(frame, lap)
+    want = oracle.OracleExtractor(nfeat, scale, nlevels, ini, mn)(frame, lap)
+    _compare_outputs(got, want, "seed %d: %dx%d nfeat %d scale %.2f levels %d th %d/%d" % (seed, w, h, nfeat, scale, nlevels, ini, mn))
