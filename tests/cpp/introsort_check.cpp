@@ -27,12 +27,12 @@ static long run_case(const std::vector<int> &counts, const std::vector<int> &ulx
     for (int i = 0; i < n; ++i) {
         nodes[i] = {ulx[i], i};
         ref[i] = std::make_pair(counts[i], &nodes[i]);
-        mine[i] = {counts[i], ulx[i], i};
+        mine[i] = vsg::make_sort_item(counts[i], ulx[i], i);
     }
     std::sort(ref.begin(), ref.end(), entry_less);
     vsg::libstdcxx_sort(mine.data(), n);
     for (int i = 0; i < n; ++i)
-        if (ref[i].second->id != mine[i].ref) return i + 1;
+        if (ref[i].second->id != vsg::sort_item_ref(mine[i])) return i + 1;
     return 0;
 }
 

@@ -19,16 +19,23 @@
 
 namespace vsg {
 
+// One sort element packed into 64 bits so that a compare is one load and a move one load + one store (the sort runs
+// on a single thread of the CTA over shared memory): count (pair.first = node key count, 24 bits) | ulx
+// (pair.second->UL.x, 16 bits) | ref (which node; NOT part of the ordering, 24 bits).
 struct SortItem {
-    int count;  // pair.first  = node key count
-    int ulx;    // pair.second->UL.x
-    int ref;    // which node (list position); not part of the ordering
+    unsigned long long v;
 };
 
-VSG_HD bool item_less(const SortItem &a, const SortItem &b) {  // compareNodes, ORBextractor.cc:539-560
-    if (a.count < b.count) return true;
-    if (a.count > b.count) return false;
-    return a.ulx < b.ulx;
+VSG_HD SortItem make_sort_item(int count, int ulx, int ref) {
+    SortItem it;
+    it.v = ((unsigned long long)(unsigned)count << 40) | ((unsigned long long)((unsigned)ulx & 0xFFFFu) << 24) |
+           (unsigned long long)((unsigned)ref & 0xFFFFFFu);
+    return it;
+}
+VSG_HD int sort_item_ref(const SortItem &it) { return (int)(it.v & 0xFFFFFFull); }
+
+VSG_HD bool item_less(const SortItem &a, const SortItem &b) {  // compareNodes, ORBextractor.cc:539-560: (count, UL.x)
+    return (a.v >> 24) < (b.v >> 24);
 }
 
 VSG_HD void item_swap(SortItem &a, SortItem &b) { SortItem t = a; a = b; b = t; }
@@ -139,7 +146,7 @@ VSG_HD void libstdcxx_sort(SortItem *v, int n) {
     for (int t = n; t > 1; t >>= 1) ++lg;
     // __introsort_loop with an explicit stack instead of the recursion on the right part (the two
     // parts are disjoint, so the processing order does not change the outcome)
-    int stack_first[64], stack_last[64], stack_depth[64];
+    int stack_first[40], stack_last[40], stack_depth[40];   // at most one push per level of the 2*lg(n) depth budget
     int sp = 0;
     stack_first[0] = 0; stack_last[0] = n; stack_depth[0] = 2 * lg; sp = 1;
     while (sp > 0) {

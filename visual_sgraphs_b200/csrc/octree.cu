@@ -15,15 +15,28 @@
 //     list give every child its position: children of the i-th divided node, in n1..n4 order, end up
 //     in front of everything pushed before them; single-key nodes keep their relative order behind.
 //   * The "careful" phase (:696-759) sorts the expandable nodes with the libstdc++ introsort
-//     emulation (introsort.cuh — tie order is part of the result; one thread, a few hundred items),
-//     finds how many are divided before the quota is reached, and rebuilds the list the same way.
+//     emulation (introsort.cuh — tie order is part of the result; one thread, 64-bit packed items);
+//     how many of them are divided before the quota is reached, and where their children land, is a
+//     block-wide prefix sum over the sorted order; the list is then rebuilt the same way.
 //   * Final pick per node = highest response, FIRST in the reference's candidate order on ties
 //     (:766-782).  Candidate order is cell-row-major, then row-major inside the cell (:811-874), so
 //     the tie break is an atomicMax on (response, ~order_key(x, y)).
+#include <cstdio>
+
 #include "introsort.cuh"
 #include "vsg_internal.cuh"
 
 namespace vsg {
+
+#ifdef VSG_OCTREE_TIMING
+#define OT_DECL long long ot_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long ot_last = clock64(); int ot_rounds = 0;
+#define OT_MARK(i) do { const long long now = clock64(); ot_t[i] += now - ot_last; ot_last = now; } while (0)
+#else
+#define OT_DECL
+#define OT_MARK(i) do { } while (0)
+#endif
+
+constexpr int kInFlight = 8;
 
 struct ONode {
     short x0, y0, x1, y1;  // UL.x, UL.y, UR.x (== BR.x), BR.y (== BL.y), relative to minBorder
@@ -49,9 +62,10 @@ __device__ __forceinline__ ONode child_of(const ONode &n, int q, int count) {
     return c;
 }
 
-// Exclusive prefix sums of three per-thread values over the 256 threads of the CTA (thread order), in place;
+// Exclusive prefix sums of three per-thread values over the kThreads threads of the CTA (thread order), in place;
 // the block totals are returned in ta, tb, tc.  Contains two barriers.
-__device__ __forceinline__ void block_scan3(int &a, int &b, int &c, int (*s_warp)[8], int &ta, int &tb, int &tc) {
+template <int kThreads>
+__device__ __forceinline__ void block_scan3(int &a, int &b, int &c, int (*s_warp)[32], int &ta, int &tb, int &tc) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int ia = a, ib = b, ic = c;
 #pragma unroll
@@ -65,7 +79,7 @@ __device__ __forceinline__ void block_scan3(int &a, int &b, int &c, int (*s_warp
     int wa = 0, wb = 0, wc = 0;
     ta = tb = tc = 0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
+    for (int w = 0; w < kThreads / 32; ++w) {
         const int va = s_warp[0][w], vb = s_warp[1][w], vc = s_warp[2][w];
         if (w < warp) { wa += va; wb += vb; wc += vc; }
         ta += va; tb += vb; tc += vc;
@@ -74,7 +88,8 @@ __device__ __forceinline__ void block_scan3(int &a, int &b, int &c, int (*s_warp
     a = wa + ia - a; b = wb + ib - b; c = wc + ic - c;
 }
 
-__global__ void __launch_bounds__(256) octree_kernel(FrameGeom g, const Cand *__restrict__ cand,
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads) octree_kernel(FrameGeom g, const Cand *__restrict__ cand,
                                                      const int *__restrict__ cand_count,
                                                      unsigned short *__restrict__ node_of,
                                                      LevelKp *__restrict__ level_kps,
@@ -83,14 +98,15 @@ __global__ void __launch_bounds__(256) octree_kernel(FrameGeom g, const Cand *__
     ONode *list_a = reinterpret_cast<ONode *>(smem);
     ONode *list_b = list_a + cap;
     int *cc = reinterpret_cast<int *>(list_b + cap);                       // [cap][4] child key counts
-    unsigned long long *best = reinterpret_cast<unsigned long long *>(cc); // reused after the tree is final
     unsigned short *child_pos = reinterpret_cast<unsigned short *>(cc + 4 * cap);  // [cap][4]
     unsigned short *stay_pos = child_pos + 4 * cap;                        // [cap]
     short *expanded = reinterpret_cast<short *>(stay_pos + cap);           // [cap] 1 if divided this round
     unsigned short *exp_list = reinterpret_cast<unsigned short *>(expanded + cap);  // [cap] expandable nodes, push order
-    SortItem *sort_buf = reinterpret_cast<SortItem *>(exp_list + cap + (cap & 1));  // [cap]
+    unsigned short *push_off = exp_list + cap;                             // [cap] careful phase: children pushed before r
+    unsigned short *exp_off = push_off + cap;                              // [cap] expandable children pushed before r
+    SortItem *sort_buf = reinterpret_cast<SortItem *>(exp_off + cap);      // [cap] (cap is a multiple of 4: 8-byte aligned)
     __shared__ int s_size, s_nexp, s_state, s_E, s_T, s_X;
-    __shared__ int s_scan[3][8];
+    __shared__ int s_scan[3][32];
 
     const int level = blockIdx.x, frame = blockIdx.y;
     const LevelGeom &L = g.lv[level];
@@ -107,10 +123,11 @@ __global__ void __launch_bounds__(256) octree_kernel(FrameGeom g, const Cand *__
     }
     const int N = L.quota;
     const int max_y = L.h - 2 * kBorderMin;  // maxBorderY - minBorderY
+    OT_DECL
 
     // ---- roots (:566-593) ----
     ONode *cur = list_a, *nxt = list_b;
-    for (int i = tid; i < L.n_ini; i += 256) {
+    for (int i = tid; i < L.n_ini; i += kThreads) {
         ONode r;
         r.x0 = (short)(int)__fmul_rn(L.h_x, (float)i);
         r.x1 = (short)(int)__fmul_rn(L.h_x, (float)(i + 1));
@@ -120,10 +137,28 @@ __global__ void __launch_bounds__(256) octree_kernel(FrameGeom g, const Cand *__
         cur[i] = r;
     }
     __syncthreads();
-    for (int k = tid; k < n; k += 256) {
-        const int r = (int)__fdiv_rn((float)(keys[k].x - kBorderMin), L.h_x);
-        nof[k] = (unsigned short)r;
-        atomicAdd(&cur[r].count, 1);
+    // every key goes to root int(x / hX) (:589-592); the per-root counts are warp ballots + one atomic per warp and
+    // root (nIni is 1 .. 4 for real images), not one atomic per key on the same counter
+    if (L.n_ini == 1) {
+        for (int k = tid; k < n; k += kThreads) nof[k] = 0;
+        if (tid == 0) cur[0].count = n;
+    } else {
+        for (int k0 = 0; k0 < n; k0 += kThreads) {
+            const int k = k0 + tid;
+            int r = -1;
+            if (k < n) {
+                r = (int)__fdiv_rn((float)((int)(key_xy[2 * k] & 0xFFFF) - kBorderMin), L.h_x);
+                nof[k] = (unsigned short)r;
+            }
+            if (L.n_ini <= 8) {
+                for (int j = 0; j < L.n_ini; ++j) {
+                    const unsigned mj = __ballot_sync(0xffffffffu, r == j);
+                    if ((tid & 31) == 0 && mj) atomicAdd(&cur[j].count, __popc(mj));
+                }
+            } else if (r >= 0) {
+                atomicAdd(&cur[r].count, 1);
+            }
+        }
     }
     __syncthreads();
     if (tid == 0) {  // drop empty roots, keep order (:597-608)
@@ -136,28 +171,29 @@ __global__ void __launch_bounds__(256) octree_kernel(FrameGeom g, const Cand *__
         s_state = 0;  // 0 = main passes, 1 = careful phase, 2 = finished
     }
     __syncthreads();
-    for (int k = tid; k < n; k += 256) nof[k] = stay_pos[nof[k]];
+    for (int k = tid; k < n; k += kThreads) nof[k] = stay_pos[nof[k]];
     { ONode *t = cur; cur = nxt; nxt = t; }
     __syncthreads();
 
+    OT_MARK(0);
     // ---- subdivision rounds ----
     while (true) {
         const int size = s_size;
         const int state = s_state;
         if (state == 2) break;
-        for (int i = tid; i < size * 4; i += 256) cc[i] = 0;
+        for (int i = tid; i < size * 4; i += kThreads) cc[i] = 0;
         __syncthreads();
-        for (int k0 = tid; k0 < n; k0 += 4 * 256) {       // 4 keys per thread in flight (global loads are L2 latency)
-            int nd[4];
-            uint32_t xy[4];
+        for (int k0 = tid; k0 < n; k0 += kInFlight * kThreads) {   // kInFlight keys per thread in flight (L2 latency)
+            int nd[kInFlight];
+            uint32_t xy[kInFlight];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int k = k0 + u * 256;
+            for (int u = 0; u < kInFlight; ++u) {
+                const int k = k0 + u * kThreads;
                 nd[u] = k < n ? nof[k] : -1;
                 xy[u] = k < n ? key_xy[2 * k] : 0u;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < kInFlight; ++u) {
                 if (nd[u] < 0) continue;
                 const ONode &node = cur[nd[u]];
                 if (node.count > 1)
@@ -165,9 +201,10 @@ __global__ void __launch_bounds__(256) octree_kernel(FrameGeom g, const Cand *__
             }
         }
         __syncthreads();
+        OT_MARK(1);
 
         // every thread owns a contiguous chunk of the list so that prefix sums follow list order
-        const int chunk = (size + 255) / 256;
+        const int chunk = (size + kThreads - 1) / kThreads;
         const int lo = min(tid * chunk, size), hi = min(lo + chunk, size);
         if (state == 0) {
             // main pass (:626-684): every multi-key node is divided, walking the list front to back; children
@@ -178,7 +215,7 @@ __global__ void __launch_bounds__(256) octree_kernel(FrameGeom g, const Cand *__
                 for (int q = 0; q < 4; ++q) { kids += cc[i * 4 + q] > 0; exps += cc[i * 4 + q] > 1; }
             }
             int T, S, X;
-            block_scan3(kids, stays, exps, s_scan, T, S, X);     // in: my sums, out: exclusive prefixes; totals in T,S,X
+            block_scan3<kThreads>(kids, stays, exps, s_scan, T, S, X);     // in: my sums, out: exclusive prefixes; totals in T,S,X
             int push = kids, stay = stays, nexp = exps;
             for (int i = lo; i < hi; ++i) {
                 if (cur[i].count == 1) {
@@ -208,39 +245,61 @@ __global__ void __launch_bounds__(256) octree_kernel(FrameGeom g, const Cand *__
         } else {
             // careful round (:698-759): sort the expandable nodes, divide from the back until size >= N
             const int m = s_nexp;
-            for (int j = tid; j < m; j += 256) {
+            for (int j = tid; j < m; j += kThreads) {
                 const int pos = exp_list[j];
-                sort_buf[j].count = cur[pos].count;
-                sort_buf[j].ulx = cur[pos].x0;
-                sort_buf[j].ref = pos;
+                sort_buf[j] = make_sort_item(cur[pos].count, cur[pos].x0, pos);
             }
-            for (int i = tid; i < size; i += 256) expanded[i] = 0;
+            for (int i = tid; i < size; i += kThreads) expanded[i] = 0;
+            if (tid == 0) s_E = m;
             __syncthreads();
-            if (tid == 0) {
-                libstdcxx_sort(sort_buf, m);
-                // processing order r = 0.. : sort_buf[m-1-r]; push_off[r] / exp_off[r] = children / expandable children
-                // pushed before r.  They overwrite the (count, ulx) fields that are no longer needed.
-                int running = size, E = 0, T = 0, X = 0;
-                for (int j = m - 1; j >= 0; --j) {
-                    const int pos = sort_buf[j].ref;
-                    int c = 0, e = 0;
-                    for (int q = 0; q < 4; ++q) { c += cc[pos * 4 + q] > 0; e += cc[pos * 4 + q] > 1; }
-                    sort_buf[j].count = T;
-                    sort_buf[j].ulx = X;
-                    expanded[pos] = 1;
-                    running += c - 1;
-                    T += c; X += e;
-                    ++E;
-                    if (running >= N) break;
+            OT_MARK(2);
+            if (tid == 0) libstdcxx_sort(sort_buf, m);
+            __syncthreads();
+            // processing order r = 0 .. m-1 is sort_buf[m-1-r] (:709 walks the sorted vector from the back).  Node r
+            // contributes c_r non-empty children (e_r of them expandable); the list has size + sum_{i<=r}(c_i - 1)
+            // nodes after it, and the walk stops after the first r where that reaches N (:753-754).  c_r >= 1, so
+            // the running size is monotone: the stop index is a block-wide minimum, the landing positions of the
+            // children are exclusive prefix sums over r.
+            const int mchunk = (m + kThreads - 1) / kThreads;
+            const int rlo = min(tid * mchunk, m), rhi = min(rlo + mchunk, m);
+            int csum = 0, esum = 0, zero = 0;
+            for (int r = rlo; r < rhi; ++r) {
+                const int pos = sort_item_ref(sort_buf[m - 1 - r]);
+                for (int q = 0; q < 4; ++q) { csum += cc[pos * 4 + q] > 0; esum += cc[pos * 4 + q] > 1; }
+            }
+            int Tall, Xall, Zall;
+            block_scan3<kThreads>(csum, esum, zero, s_scan, Tall, Xall, Zall);   // csum / esum are now exclusive prefixes
+            {
+                int run_c = csum, run_e = esum;
+                for (int r = rlo; r < rhi; ++r) {
+                    const int pos = sort_item_ref(sort_buf[m - 1 - r]);
+                    push_off[r] = (unsigned short)run_c;
+                    exp_off[r] = (unsigned short)run_e;
+                    for (int q = 0; q < 4; ++q) { run_c += cc[pos * 4 + q] > 0; run_e += cc[pos * 4 + q] > 1; }
+                    if (size + run_c - (r + 1) >= N) { atomicMin(&s_E, r + 1); break; }
                 }
-                s_E = E; s_T = T; s_X = X;
             }
             __syncthreads();
-            const int E = s_E, T = s_T;
-            for (int r = tid; r < E; r += 256) {
-                const SortItem it = sort_buf[m - 1 - r];
-                const int pos = it.ref;
-                int push = it.count, nexp = it.ulx;
+            const int E = s_E;
+            // totals over the E divided nodes: the prefix at r = E, recomputed by the one thread whose chunk holds r = E
+            // (it may have stopped before reaching it), or the block totals when every node is divided
+            if (E == m) {
+                if (tid == 0) { s_T = Tall; s_X = Xall; }
+            } else if (E >= rlo && E < rhi) {
+                int run_c = csum, run_e = esum;
+                for (int r = rlo; r < E; ++r) {
+                    const int pos = sort_item_ref(sort_buf[m - 1 - r]);
+                    for (int q = 0; q < 4; ++q) { run_c += cc[pos * 4 + q] > 0; run_e += cc[pos * 4 + q] > 1; }
+                }
+                s_T = run_c; s_X = run_e;
+            }
+            __syncthreads();
+            OT_MARK(3);
+            const int T = s_T;
+            for (int r = tid; r < E; r += kThreads) {
+                const int pos = sort_item_ref(sort_buf[m - 1 - r]);
+                expanded[pos] = 1;
+                int push = push_off[r], nexp = exp_off[r];
                 for (int q = 0; q < 4; ++q) {
                     const int c = cc[pos * 4 + q];
                     if (c == 0) continue;
@@ -250,10 +309,11 @@ __global__ void __launch_bounds__(256) octree_kernel(FrameGeom g, const Cand *__
                     if (c > 1) exp_list[nexp++] = (unsigned short)np;      // old entries were copied to sort_buf
                 }
             }
+            __syncthreads();
             int stays = 0;
             for (int i = lo; i < hi; ++i) stays += expanded[i] ? 0 : 1;
             int d0 = 0, d1 = 0, S, D0, D1;
-            block_scan3(stays, d0, d1, s_scan, S, D0, D1);
+            block_scan3<kThreads>(stays, d0, d1, s_scan, S, D0, D1);
             int stay = stays;
             for (int i = lo; i < hi; ++i) {
                 if (expanded[i]) continue;
@@ -269,19 +329,20 @@ __global__ void __launch_bounds__(256) octree_kernel(FrameGeom g, const Cand *__
             }
         }
         __syncthreads();
-        for (int k0 = tid; k0 < n; k0 += 4 * 256) {
-            int nd[4];
-            uint32_t xy[4];
+        OT_MARK(4);
+        for (int k0 = tid; k0 < n; k0 += kInFlight * kThreads) {
+            int nd[kInFlight];
+            uint32_t xy[kInFlight];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int k = k0 + u * 256;
+            for (int u = 0; u < kInFlight; ++u) {
+                const int k = k0 + u * kThreads;
                 nd[u] = k < n ? nof[k] : -1;
                 xy[u] = k < n ? key_xy[2 * k] : 0u;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < kInFlight; ++u) {
                 if (nd[u] < 0) continue;
-                const int k = k0 + u * 256;
+                const int k = k0 + u * kThreads;
                 if (expanded[nd[u]]) {
                     const ONode &node = cur[nd[u]];
                     nof[k] = child_pos[nd[u] * 4 + quadrant(node, (int)(xy[u] & 0xFFFF) - kBorderMin, (int)(xy[u] >> 16) - kBorderMin)];
@@ -292,49 +353,68 @@ __global__ void __launch_bounds__(256) octree_kernel(FrameGeom g, const Cand *__
         }
         { ONode *t = cur; cur = nxt; nxt = t; }
         __syncthreads();
+        OT_MARK(5);
+#ifdef VSG_OCTREE_TIMING
+        ++ot_rounds;
+#endif
     }
 
-    // ---- best key per node (:766-782) ----
+    // ---- best key per node (:766-782): highest response, first in the reference's candidate order on ties ----
+    // two passes of native 32-bit shared-memory atomics: the maximum response per node, then the smallest order key
+    // among the keys that carry it
     const int size = s_size;
-    for (int i = tid; i < size; i += 256) best[i] = 0ull;
+    unsigned *best_score = reinterpret_cast<unsigned *>(cc);            // [size]  (cc is free once the tree is final)
+    unsigned *best_order = best_score + cap;                            // [size]
+    for (int i = tid; i < size; i += kThreads) { best_score[i] = 0u; best_order[i] = 0xFFFFFFFFu; }
     __syncthreads();
-    for (int k = tid; k < n; k += 256) {
+    for (int k = tid; k < n; k += kThreads) atomicMax(&best_score[nof[k]], (unsigned)keys[k].score + 1u);
+    __syncthreads();
+    for (int k = tid; k < n; k += kThreads) {
         const Cand c = keys[k];                                // independent iterations: the loads pipeline
+        const int node = nof[k];
+        if ((unsigned)c.score + 1u != best_score[node]) continue;
         const int rx = c.x - kEdge, ry = c.y - kEdge;          // offset inside the FAST-able area
         const int cx = rx / L.w_cell, cy = ry / L.h_cell;
         const unsigned order = ((unsigned)(cy * L.n_cols + cx) << 14) | ((unsigned)(ry - cy * L.h_cell) << 7) |
                                (unsigned)(rx - cx * L.w_cell);
-        const unsigned long long key = ((unsigned long long)c.score << 32) | (unsigned long long)(0xFFFFFFFFu - order);
-        atomicMax(&best[nof[k]], key);
+        atomicMin(&best_order[node], order);
     }
     __syncthreads();
-    for (int i = tid; i < size && i < L.kp_cap; i += 256) {
-        const unsigned long long b = best[i];
-        const unsigned order = 0xFFFFFFFFu - (unsigned)(b & 0xFFFFFFFFull);
+    for (int i = tid; i < size && i < L.kp_cap; i += kThreads) {
+        const unsigned order = best_order[i];
         const int cell = order >> 14, ly = (order >> 7) & 127, lx = order & 127;
         const int cy = cell / L.n_cols, cx = cell - cy * L.n_cols;
         LevelKp kp;
         kp.x = (unsigned short)(kEdge + cx * L.w_cell + lx);
         kp.y = (unsigned short)(kEdge + cy * L.h_cell + ly);
-        kp.score = (unsigned short)(b >> 32);
+        kp.score = (unsigned short)(best_score[i] - 1u);
         kp.pad = 0;
         out[i] = kp;
     }
     if (tid == 0) *out_count = min(size, L.kp_cap);
+    OT_MARK(6);
+#ifdef VSG_OCTREE_TIMING
+    if (tid == 0 && frame == 0)
+        printf("octree level %d n %d rounds %d: roots %lld | passA %lld | careful-prep %lld | sort+scan %lld | rebuild %lld | passB %lld | best %lld cycles\n",
+               level, n, ot_rounds, ot_t[0], ot_t[1], ot_t[2], ot_t[3], ot_t[4], ot_t[5], ot_t[6]);
+#endif
 }
 
 void launch_octree(const FrameGeom &g, const Cand *cand, const int *cand_count, unsigned short *node_of,
                    LevelKp *level_kps, int *level_kp_count, int max_nodes, int nframes, cudaStream_t s) {
     const int cap = (max_nodes + 3) & ~3;
-    // list_a, list_b (12 B each), cc (16 B), child_pos (8 B), stay_pos, expanded, exp_list (2 B each), sort_buf (12 B)
-    const size_t smem = (size_t)cap * (12 + 12 + 16 + 8 + 2 + 2 + 2 + 12) + 64;
+    // list_a, list_b (12 B each), cc (16 B), child_pos (8 B), stay_pos, expanded, exp_list, push_off, exp_off (2 B
+    // each), sort_buf (8 B)
+    const size_t smem = (size_t)cap * (12 + 12 + 16 + 8 + 2 + 2 + 2 + 2 + 2 + 8) + 64;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(octree_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    octree_kernel<<<dim3(g.nlevels, nframes), 256, smem, s>>>(g, cand, cand_count, node_of, level_kps, level_kp_count,
-                                                             cap);
+    // (a 1024-thread variant for single frames was measured: the passes over the keys get faster, the block-wide scans
+    // and barriers slower — 69.7 us vs 67.0 us for one 640x480 frame — so every batch size uses 8-warp CTAs)
+    octree_kernel<256><<<dim3(g.nlevels, nframes), 256, smem, s>>>(g, cand, cand_count, node_of, level_kps,
+                                                                  level_kp_count, cap);
     count_launch();
 }
 
