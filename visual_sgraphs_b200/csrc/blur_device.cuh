@@ -15,7 +15,7 @@ namespace vsg {
 // row to separate "edge" work items that assemble their 12 source bytes one by one — they are queued
 // after all interior items so that interior warps never diverge.  One launch covers every level.
 // ------------------------------------------------------------------------------------------------
-constexpr int kBlurRows = 32, kBlurThreads = 128;
+constexpr int kBlurRows = 32, kBlurRowsSmallBatch = 8, kBlurThreads = 128;   // strip height: large batches / few frames
 
 __device__ __forceinline__ int reflect101(int i, int n) {
     if (i < 0) i = -i;
@@ -25,6 +25,7 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 
 struct BlurLevels {
     int nlevels;
+    int rows;                         // rows per strip (one thread walks a strip top to bottom)
     int block_begin[kMaxLevels + 1];  // prefix sums of thread blocks per level
     int n_int_cg[kMaxLevels];         // interior 4-column groups per row: cg = 1 .. n_int_cg
     int n_edge_cg[kMaxLevels];        // edge groups per row: cg = 0 and cg > n_int_cg
@@ -55,13 +56,13 @@ __device__ __forceinline__ void blur_load_row(const uint8_t *__restrict__ row, i
 
 template <bool kEdge>
 __device__ __forceinline__ void blur_strip(const uint8_t *__restrict__ src, int spitch, uint8_t *__restrict__ dst,
-                                           int dpitch, int w, int h, int x, int y0) {
+                                           int dpitch, int w, int h, int x, int y0, int rows) {
     uint32_t hw[7][4];
 #pragma unroll
     for (int r = 0; r < 6; ++r)
         blur_load_row<kEdge>(src + (int64_t)reflect101(min(y0 - 3 + r, h + 2), h) * spitch, x, w, hw[r]);
-    const int yend = min(y0 + kBlurRows, h);
-    for (int base = 0; base < kBlurRows; base += 7) {
+    const int yend = min(y0 + rows, h);
+    for (int base = 0; base < rows; base += 7) {
 #pragma unroll
         for (int k = 0; k < 7; ++k) {
             const int y = y0 + base + k;
@@ -98,20 +99,23 @@ __device__ __forceinline__ void blur_block_body(const FrameGeom &g, const BlurLe
     const int items_int = bl.n_strips[level] * n_int;
     if (item < items_int) {
         const int strip = item / n_int, cg = 1 + (item - strip * n_int);
-        blur_strip<false>(src, spitch, dst, L.pitch, L.w, L.h, 4 * cg, strip * kBlurRows);
+        blur_strip<false>(src, spitch, dst, L.pitch, L.w, L.h, 4 * cg, strip * bl.rows, bl.rows);
     } else {
         const int e = item - items_int;
         if (e >= bl.n_strips[level] * n_edge) return;
         const int strip = e / n_edge, k = e - strip * n_edge;
         const int cg = k == 0 ? 0 : n_int + k;
-        blur_strip<true>(src, spitch, dst, L.pitch, L.w, L.h, 4 * cg, strip * kBlurRows);
+        blur_strip<true>(src, spitch, dst, L.pitch, L.w, L.h, 4 * cg, strip * bl.rows, bl.rows);
     }
 }
 
 // Block table of one launch (host side).
-inline BlurLevels make_blur_levels(const FrameGeom &g) {
+// Few frames in flight: the GPU is not full and a strip is a serial chain of row loads, so strips are kept short (more,
+// shorter threads); large batches amortise the 6-row prologue of a strip over 32 rows.
+inline BlurLevels make_blur_levels(const FrameGeom &g, int nframes) {
     BlurLevels bl;
     bl.nlevels = g.nlevels;
+    bl.rows = nframes <= 8 ? kBlurRowsSmallBatch : kBlurRows;
     int total = 0;
     for (int l = 0; l < g.nlevels; ++l) {
         const int w = g.lv[l].w, h = g.lv[l].h;
@@ -123,7 +127,7 @@ inline BlurLevels make_blur_levels(const FrameGeom &g) {
         bl.block_begin[l] = total;
         bl.n_int_cg[l] = n_int;
         bl.n_edge_cg[l] = ncg - n_int;
-        bl.n_strips[l] = (h + kBlurRows - 1) / kBlurRows;
+        bl.n_strips[l] = (h + bl.rows - 1) / bl.rows;
         total += (bl.n_strips[l] * ncg + kBlurThreads - 1) / kBlurThreads;
     }
     bl.block_begin[g.nlevels] = total;

@@ -51,6 +51,8 @@ __global__ void __launch_bounds__(256) slot_kernel(FrameGeom g, const LevelKp *_
                                                    int *__restrict__ slot) {
     __shared__ int s_off[kMaxLevels + 1];
     __shared__ int s_part[256];
+    pdl_launch_dependents();
+    pdl_wait();
     const int frame = blockIdx.x, tid = threadIdx.x;
     if (tid == 0) {
         int acc = 0;
@@ -104,8 +106,9 @@ __global__ void __launch_bounds__(256) slot_kernel(FrameGeom g, const LevelKp *_
 #ifndef VSG_DESC_MINB
 #define VSG_DESC_MINB 4
 #endif
-constexpr int kDescKp = 64;
+// (few frames in flight: 16 keypoints per CTA — four times the CTAs, a quarter of the serial keypoints per warp)
 
+template <int kDescKp>
 __global__ void __launch_bounds__(256, VSG_DESC_MINB) describe_kernel(FrameGeom g, const uint8_t *__restrict__ lvl0_base,
                                                        int lvl0_pitch, int64_t lvl0_stride,
                                                        const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur,
@@ -116,6 +119,8 @@ __global__ void __launch_bounds__(256, VSG_DESC_MINB) describe_kernel(FrameGeom 
     __shared__ int s_x[kDescKp], s_y[kDescKp], s_level[kDescKp], s_row[kDescKp], s_score[kDescKp];
     __shared__ int s_m01[kDescKp], s_m10[kDescKp];
     __shared__ float s_angle[kDescKp], s_cos[kDescKp], s_sin[kDescKp];
+    pdl_launch_dependents();
+    pdl_wait();
     const int frame = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int first = blockIdx.x * kDescKp;             // keypoint index in level-major order
@@ -231,11 +236,14 @@ void launch_describe(const FrameGeom &g, const uint8_t *lvl0_base, int lvl0_pitc
                      const uint8_t *pyr, const uint8_t *blur, const LevelKp *level_kps, const int *level_kp_count,
                      int lap_x0, int lap_x1, vsg_keypoint *kps_out, uint8_t *desc_out, int out_cap, int *n_out,
                      int *mono_out, int *slot_scratch, int nframes, cudaStream_t s) {
-    slot_kernel<<<nframes, 256, 0, s>>>(g, level_kps, level_kp_count, lap_x0, lap_x1, out_cap, n_out, mono_out,
-                                       slot_scratch);
-    describe_kernel<<<dim3((g.kp_total + kDescKp - 1) / kDescKp, nframes), 256, 0, s>>>(g, lvl0_base, lvl0_pitch, lvl0_stride, pyr,
-                                                                       blur, level_kps, level_kp_count, slot_scratch,
-                                                                       kps_out, desc_out, out_cap);
+    launch_kernel(slot_kernel, dim3(nframes), dim3(256), 0, s, true, g, level_kps, level_kp_count, lap_x0, lap_x1, out_cap,
+                  n_out, mono_out, slot_scratch);
+    if (nframes <= 8)
+        launch_kernel(describe_kernel<16>, dim3((g.kp_total + 15) / 16, nframes), dim3(256), 0, s, true, g, lvl0_base, lvl0_pitch,
+                      lvl0_stride, pyr, blur, level_kps, level_kp_count, (const int *)slot_scratch, kps_out, desc_out, out_cap);
+    else
+        launch_kernel(describe_kernel<64>, dim3((g.kp_total + 63) / 64, nframes), dim3(256), 0, s, true, g, lvl0_base, lvl0_pitch,
+                      lvl0_stride, pyr, blur, level_kps, level_kp_count, (const int *)slot_scratch, kps_out, desc_out, out_cap);
     count_launch(2);
 }
 

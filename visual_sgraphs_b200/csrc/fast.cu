@@ -265,6 +265,8 @@ __global__ void __launch_bounds__(kFastThreads, 8) fast_kernel(FrameGeom g,
                                                              int64_t lvl0_stride, const uint8_t *__restrict__ pyr,
                                                              Cand *__restrict__ cand, int *__restrict__ cand_count,
                                                              int ini_th, int min_th, int tile_rows, int list_cap) {
+    pdl_launch_dependents();
+    pdl_wait();
     fast_cell_body(g, lvl0_base, lvl0_pitch, lvl0_stride, pyr, cand, cand_count, ini_th, min_th, tile_rows, list_cap,
                    blockIdx.x, blockIdx.y);
 }
@@ -283,6 +285,8 @@ __global__ void __launch_bounds__(kFastThreads, 8) fast_blur_kernel(FrameGeom g,
                                                                   uint8_t *__restrict__ blur, Cand *__restrict__ cand,
                                                                   int *__restrict__ cand_count, int ini_th, int min_th,
                                                                   int tile_rows, int list_cap, int nblur, int ratio) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int x = blockIdx.x, group = ratio + 1;
     int cell;
     if (x < nblur * group) {
@@ -323,15 +327,14 @@ void launch_fast(const FrameGeom &g, const Cell *cells, const uint8_t *lvl0_base
         configured = smem;
     }
     if (!blur) {
-        fast_kernel<<<dim3(g.ncells, nframes), kFastThreads, smem, s>>>(g, lvl0_base, lvl0_pitch, lvl0_stride, pyr, cand,
-                                                                      cand_count, ini_th, min_th, tile_rows, list_cap);
+        launch_kernel(fast_kernel, dim3(g.ncells, nframes), dim3(kFastThreads), smem, s, true, g, lvl0_base, lvl0_pitch,
+                      lvl0_stride, pyr, cand, cand_count, ini_th, min_th, tile_rows, list_cap);
     } else {
-        const BlurLevels bl = make_blur_levels(g);
+        const BlurLevels bl = make_blur_levels(g, nframes);
         const int nblur = bl.block_begin[g.nlevels];
         const int ratio = g.ncells / nblur;
-        fast_blur_kernel<<<dim3(g.ncells + nblur, nframes), kFastThreads, smem, s>>>(
-            g, bl, lvl0_base, lvl0_pitch, lvl0_stride, pyr, blur, cand, cand_count, ini_th, min_th, tile_rows, list_cap, nblur,
-            ratio);
+        launch_kernel(fast_blur_kernel, dim3(g.ncells + nblur, nframes), dim3(kFastThreads), smem, s, true, g, bl, lvl0_base,
+                      lvl0_pitch, lvl0_stride, pyr, blur, cand, cand_count, ini_th, min_th, tile_rows, list_cap, nblur, ratio);
     }
     count_launch();
 }

@@ -108,9 +108,11 @@ __global__ void __launch_bounds__(kThreads) octree_kernel(FrameGeom g, const Can
     __shared__ int s_size, s_nexp, s_state, s_E, s_T, s_X;
     __shared__ int s_scan[3][32];
 
+    pdl_launch_dependents();
     const int level = blockIdx.x, frame = blockIdx.y;
     const LevelGeom &L = g.lv[level];
     const int tid = threadIdx.x;
+    pdl_wait();
     const int n = min(cand_count[frame * g.nlevels + level], L.cand_cap);
     const Cand *keys = cand + L.cand_offset + (int64_t)frame * g.cand_total;
     const uint32_t *key_xy = reinterpret_cast<const uint32_t *>(keys);   // word 2k = x | y << 16 of candidate k
@@ -413,8 +415,8 @@ void launch_octree(const FrameGeom &g, const Cand *cand, const int *cand_count, 
     }
     // (a 1024-thread variant for single frames was measured: the passes over the keys get faster, the block-wide scans
     // and barriers slower — 69.7 us vs 67.0 us for one 640x480 frame — so every batch size uses 8-warp CTAs)
-    octree_kernel<256><<<dim3(g.nlevels, nframes), 256, smem, s>>>(g, cand, cand_count, node_of, level_kps,
-                                                                  level_kp_count, cap);
+    launch_kernel(octree_kernel<256>, dim3(g.nlevels, nframes), dim3(256), smem, s, true, g, cand, cand_count, node_of,
+                  level_kps, level_kp_count, cap);
     count_launch();
 }
 

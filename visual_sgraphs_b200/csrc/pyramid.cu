@@ -38,6 +38,8 @@ __global__ void __launch_bounds__(kResizeThreads, VSG_RESIZE_MINB) resize_kernel
                                                                 int sw, const uint8_t *__restrict__ src_end,
                                                                 const short4 *__restrict__ xtab,
                                                                 const short4 *__restrict__ ytab) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int x4 = (blockIdx.x * kResizeThreads + threadIdx.x) * 4;
     if (x4 >= dw) return;
     const int y0 = blockIdx.y * kResizeRows, y1 = min(y0 + kResizeRows, dh);
@@ -121,8 +123,8 @@ void launch_resize_level(const FrameGeom &g, int level, const uint8_t *src_base,
     const LevelGeom &L = g.lv[level];
     const int ncg = (L.w + 3) / 4;
     dim3 grid((ncg + kResizeThreads - 1) / kResizeThreads, (L.h + kResizeRows - 1) / kResizeRows, nframes);
-    resize_kernel<<<grid, kResizeThreads, 0, s>>>(src_base, src_pitch, src_stride, pyr + L.plane_offset, L.pitch,
-                                                 L.plane_stride, L.w, L.h, P.w, src_end, L.xtab, L.ytab);
+    launch_kernel(resize_kernel, grid, dim3(kResizeThreads), 0, s, true, src_base, src_pitch, src_stride, pyr + L.plane_offset,
+                  L.pitch, L.plane_stride, L.w, L.h, P.w, src_end, L.xtab, L.ytab);
     count_launch();
 }
 
@@ -181,13 +183,16 @@ namespace vsg {
 __global__ void __launch_bounds__(kBlurThreads, VSG_BLUR_MINB) blur_kernel(FrameGeom g, BlurLevels bl, const uint8_t *__restrict__ lvl0_base,
                                                             int lvl0_pitch, int64_t lvl0_stride,
                                                             const uint8_t *__restrict__ pyr, uint8_t *__restrict__ blur) {
+    pdl_launch_dependents();
+    pdl_wait();
     blur_block_body(g, bl, lvl0_base, lvl0_pitch, lvl0_stride, pyr, blur, blockIdx.x, blockIdx.y);
 }
 
 void launch_blur(const FrameGeom &g, const uint8_t *lvl0_base, int lvl0_pitch, int64_t lvl0_stride, const uint8_t *pyr,
                  uint8_t *blur, int nframes, cudaStream_t s) {
-    const BlurLevels bl = make_blur_levels(g);
-    blur_kernel<<<dim3(bl.block_begin[g.nlevels], nframes), kBlurThreads, 0, s>>>(g, bl, lvl0_base, lvl0_pitch, lvl0_stride, pyr, blur);
+    const BlurLevels bl = make_blur_levels(g, nframes);
+    launch_kernel(blur_kernel, dim3(bl.block_begin[g.nlevels], nframes), dim3(kBlurThreads), 0, s, true, g, bl, lvl0_base,
+                  lvl0_pitch, lvl0_stride, pyr, blur);
     count_launch();
 }
 

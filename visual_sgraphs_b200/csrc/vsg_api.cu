@@ -37,6 +37,10 @@ bool cuda_ok(cudaError_t e, const char *what) {
     return false;
 }
 void count_launch(int n) { g_launches += n; }
+bool pdl_enabled() {
+    static const bool on = [] { const char *e = getenv("VSG_PDL"); return !e || atoi(e) != 0; }();
+    return on;
+}
 
 static inline int cv_round(float v) { return (int)lrintf(v); }
 static inline int cv_round(double v) { return (int)lrint(v); }

@@ -106,6 +106,31 @@ struct PyramidRef {
 };
 bool extractor_pyramid(vsg_extractor *ex, PyramidRef *out);
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the attribute may be scheduled while the previous
+// kernel of the stream is still draining; it must execute pdl_wait() before touching anything that kernel wrote.
+// Every pipeline kernel calls pdl_launch_dependents() first thing (the next kernel's blocks can be made resident as
+// soon as all of this kernel's blocks have started) and pdl_wait() ahead of its first dependent access; both are no-ops
+// for ordinary launches.  VSG_PDL=0 disables the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl,
+                                 Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 void set_error(const char *fmt, ...);
 bool cuda_ok(cudaError_t e, const char *what);
 void count_launch(int n = 1);
