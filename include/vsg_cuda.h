@@ -394,6 +394,14 @@ vsg_status vsg_stereo_match(vsg_matcher *m, vsg_extractor *left, vsg_extractor *
                             const vsg_keypoint *keys_l, const uint8_t *desc_l, int n_l, const vsg_keypoint *keys_r,
                             const uint8_t *desc_r, int n_r, float mb, float mbf, float *u_right_out, float *depth_out);
 
+/* Batched ComputeStereoMatches: frames 2p / 2p+1 of the extractor's last vsg_extract_batch[_color] call are the left /
+ * right image of stereo pair p (BASELINE config 2; SURVEY 8e: both images of a pair on one GPU).  Keypoints,
+ * descriptors and pyramids are read where that call left them in device memory — nothing is uploaded — and the
+ * median-based rejection (:1113-1126) runs on the device too.  u_right_out / depth_out are [npairs][capacity] floats
+ * (capacity >= vsg_extractor_max_keypoints); entries beyond a pair's left keypoint count are -1. */
+vsg_status vsg_stereo_match_batch(vsg_matcher *m, vsg_extractor *ex, int npairs, float mb, float mbf,
+                                  float *u_right_out, float *depth_out, int capacity);
+
 #ifdef __cplusplus
 }
 #endif

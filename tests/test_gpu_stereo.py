@@ -41,3 +41,28 @@ def test_stereo_inside_a_batch(oracle):
     oxr(right)
     wu, wd = oracle.stereo_matches(oxl, oxr, kl, dl, kr, dr, 0.11, 47.9)
     assert np.array_equal(u, wu) and np.array_equal(d, wd)
+
+
+def test_stereo_batch_matches_per_pair_and_oracle(oracle):
+    """vsg_stereo_match_batch (pairs 2p / 2p+1 of one extractor batch, device-resident inputs, median rejection on the
+    device) against the per-pair entry point and the oracle."""
+    from visual_sgraphs_b200.extractor import ORBextractor
+    from visual_sgraphs_b200.matcher import ORBmatcher
+    pairs = [synth_stereo_pair(20 + i, 752, 480) for i in range(3)]
+    pairs.append((pairs[0][0], np.full_like(pairs[0][1], 128)))        # a right image without keypoints: no matches at all
+    stack = np.stack([im for pr in pairs for im in pr])
+    ex = ORBextractor(1200, max_batch=len(stack))
+    res = ex.extract_batch(stack)
+    m = ORBmatcher()
+    ub, db = m.ComputeStereoMatchesBatch(ex, len(pairs), 0.11, 47.9)
+    for p, (left, right) in enumerate(pairs):
+        (_, kl, dl), (_, kr, dr) = res[2 * p], res[2 * p + 1]
+        u1, d1 = m.ComputeStereoMatches(ex, ex, kl, dl, kr, dr, 0.11, 47.9, frame_l=2 * p, frame_r=2 * p + 1)
+        assert np.array_equal(ub[p, :len(kl)], u1) and np.array_equal(db[p, :len(kl)], d1), p
+        assert (ub[p, len(kl):] == -1).all() and (db[p, len(kl):] == -1).all()
+        oxl, oxr = oracle.OracleExtractor(1200), oracle.OracleExtractor(1200)
+        oxl(left)
+        oxr(right)
+        wu, wd = oracle.stereo_matches(oxl, oxr, kl, dl, kr, dr, 0.11, 47.9)
+        assert np.array_equal(u1, wu) and np.array_equal(d1, wd), p
+    assert (ub[0] >= 0).sum() > 200 and (ub[3] >= 0).sum() == 0

@@ -135,6 +135,156 @@ __global__ void stereo_sad_kernel(StereoPlanes P, const vsg_keypoint *__restrict
     }
 }
 
+// ---- batched variant: pairs (2p, 2p+1) of one extractor batch, everything device-resident ----
+struct BatchPlanes {          // frame-0 base of every level + strides; frame f of level l = base[l] + f * stride[l]
+    const uint8_t *base[kMaxLevels];
+    int64_t stride[kMaxLevels];
+    int pitch[kMaxLevels], w[kMaxLevels];
+    float scale[kMaxLevels], inv_scale[kMaxLevels];
+    int n_rows;
+};
+
+__global__ void stereo_search_batch_kernel(BatchPlanes P, const vsg_keypoint *__restrict__ kps, const uint4 *__restrict__ desc,
+                                           const int *__restrict__ n_kp, int out_cap, float max_d,
+                                           int *__restrict__ best_dist, int *__restrict__ best_idx) {
+    extern __shared__ RightKp s_right[];
+    const int pair = blockIdx.y;
+    const vsg_keypoint *keys_l = kps + (size_t)(2 * pair) * out_cap, *keys_r = keys_l + out_cap;
+    const uint4 *desc_l = desc + (size_t)(2 * pair) * out_cap * 2, *desc_r = desc_l + (size_t)out_cap * 2;
+    const int n_l = min(n_kp[2 * pair], out_cap), n_r = min(n_kp[2 * pair + 1], out_cap);
+    for (int i = threadIdx.x; i < n_r; i += blockDim.x) {                       // :973-984
+        const vsg_keypoint k = keys_r[i];
+        const float r = __fmul_rn(2.0f, P.scale[k.octave]);
+        RightKp rk;
+        rk.x = k.x;
+        rk.maxr = (int)ceilf(__fadd_rn(k.y, r));
+        rk.minr = (int)floorf(__fsub_rn(k.y, r));
+        rk.octave = k.octave;
+        s_right[i] = rk;
+    }
+    __syncthreads();
+    const int il = blockIdx.x * blockDim.x + threadIdx.x;
+    if (il >= n_l) return;
+    const vsg_keypoint kpl = keys_l[il];
+    int bd = 100, bi = 0;
+    const int row = (int)kpl.y;
+    const float min_u = kpl.x - max_d, max_u = kpl.x;
+    if (row >= 0 && row < P.n_rows && !(max_u < 0)) {
+        const uint4 la = __ldg(desc_l + 2 * il), lb = __ldg(desc_l + 2 * il + 1);
+        for (int ir = 0; ir < n_r; ++ir) {
+            const RightKp k = s_right[ir];
+            if (row < k.minr || row > k.maxr) continue;
+            if (k.octave < kpl.octave - 1 || k.octave > kpl.octave + 1) continue;
+            if (k.x >= min_u && k.x <= max_u) {
+                const int d = hamming256(la, lb, __ldg(desc_r + 2 * ir), __ldg(desc_r + 2 * ir + 1));
+                if (d < bd) { bd = d; bi = ir; }
+            }
+        }
+    }
+    best_dist[(size_t)pair * out_cap + il] = bd;
+    best_idx[(size_t)pair * out_cap + il] = bi;
+}
+
+__global__ void stereo_sad_batch_kernel(BatchPlanes P, const vsg_keypoint *__restrict__ kps, const int *__restrict__ n_kp,
+                                        int out_cap, const int *__restrict__ best_dist, const int *__restrict__ best_idx,
+                                        float max_d, float mbf, int *__restrict__ sad_out, float *__restrict__ u_right,
+                                        float *__restrict__ depth) {
+    const int pair = blockIdx.y;
+    const int il = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (il >= out_cap) return;
+    const size_t o = (size_t)pair * out_cap + il;
+    if (lane == 0) { sad_out[o] = -1; u_right[o] = -1.0f; depth[o] = -1.0f; }
+    if (il >= min(n_kp[2 * pair], out_cap)) return;
+    if (best_dist[o] >= 75) return;
+    const vsg_keypoint *keys_l = kps + (size_t)(2 * pair) * out_cap, *keys_r = keys_l + out_cap;
+    const vsg_keypoint kpl = keys_l[il];
+    const int oct = kpl.octave;
+    const float ur0 = keys_r[best_idx[o]].x;
+    const float sf = P.inv_scale[oct];
+    const float sul = roundf(__fmul_rn(kpl.x, sf)), svl = roundf(__fmul_rn(kpl.y, sf)), sur0 = roundf(__fmul_rn(ur0, sf));
+    const int w = 5, L = 5;
+    const float iniu = sur0 + L - w, endu = sur0 + L + w + 1;
+    if (iniu < 0 || endu >= P.w[oct]) return;
+    const uint8_t *pl = P.base[oct] + (int64_t)(2 * pair) * P.stride[oct], *pr = pl + P.stride[oct];
+    const int pitch = P.pitch[oct];
+    const int y0 = (int)(svl - w), xl0 = (int)(sul - w), xr0 = (int)(sur0 - L - w);
+    int sad[11];
+#pragma unroll
+    for (int k = 0; k < 11; ++k) sad[k] = 0;
+    for (int p = lane; p < 121; p += 32) {
+        const int dy = p / 11, dx = p - dy * 11;
+        const int a = __ldg(pl + (int64_t)(y0 + dy) * pitch + xl0 + dx);
+        const uint8_t *rrow = pr + (int64_t)(y0 + dy) * pitch + xr0 + dx;
+#pragma unroll
+        for (int k = 0; k < 11; ++k) sad[k] += abs(a - (int)__ldg(rrow + k));
+    }
+#pragma unroll
+    for (int k = 0; k < 11; ++k)
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) sad[k] += __shfl_xor_sync(0xffffffffu, sad[k], d);
+    if (lane != 0) return;
+    int best = INT_MAX, best_inc = 0;
+#pragma unroll
+    for (int k = 0; k < 11; ++k)
+        if (sad[k] < best) { best = sad[k]; best_inc = k - L; }
+    if (best_inc == -L || best_inc == L) return;
+    float d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+    for (int k = 1; k < 10; ++k)
+        if (k - L == best_inc) { d1 = (float)sad[k - 1]; d2 = (float)sad[k]; d3 = (float)sad[k + 1]; }
+    const float delta = __fdiv_rn(__fsub_rn(d1, d3), __fmul_rn(2.0f, __fsub_rn(__fadd_rn(d1, d3), __fmul_rn(2.0f, d2))));
+    if (delta < -1 || delta > 1) return;
+    float best_ur = __fmul_rn(P.scale[oct], __fadd_rn(__fadd_rn(sur0, (float)best_inc), delta));
+    float disparity = __fsub_rn(kpl.x, best_ur);
+    if (disparity >= 0.f && disparity < max_d) {
+        if (disparity <= 0) {
+            disparity = 0.01f;
+            best_ur = (float)((double)kpl.x - 0.01);
+        }
+        depth[o] = __fdiv_rn(mbf, disparity);
+        u_right[o] = best_ur;
+        sad_out[o] = best;
+    }
+}
+
+// :1113-1126 per pair: median = the (count / 2)-th smallest SAD of the accepted matches (0-based, as in the sorted
+// vDistIdx), found by bisection on the integer SAD value; every match with SAD >= 1.5f * 1.4f * median is dropped
+// (the reference walks the sorted vector from the back until the first SAD below the threshold: the same set).
+__global__ void __launch_bounds__(256) stereo_median_kernel(int out_cap, const int *__restrict__ sad, float *__restrict__ u_right,
+                                                            float *__restrict__ depth) {
+    __shared__ int s_cnt;
+    const int pair = blockIdx.x, tid = threadIdx.x;
+    const int *s = sad + (size_t)pair * out_cap;
+    int valid = 0;
+    for (int i = tid; i < out_cap; i += 256) valid += s[i] >= 0;
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    atomicAdd(&s_cnt, valid);
+    __syncthreads();
+    const int total = s_cnt;
+    if (total == 0) return;
+    const int k = total / 2;
+    int lo = 0, hi = 121 * 255;                                 // smallest v with #{sad <= v} >= k + 1
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        __syncthreads();
+        if (tid == 0) s_cnt = 0;
+        __syncthreads();
+        int c = 0;
+        for (int i = tid; i < out_cap; i += 256) c += (s[i] >= 0 && s[i] <= mid);
+        atomicAdd(&s_cnt, c);
+        __syncthreads();
+        if (s_cnt >= k + 1) hi = mid; else lo = mid + 1;
+    }
+    const float th = __fmul_rn(__fmul_rn(1.5f, 1.4f), (float)lo);
+    for (int i = tid; i < out_cap; i += 256)
+        if (s[i] >= 0 && !((float)s[i] < th)) {
+            u_right[(size_t)pair * out_cap + i] = -1.0f;
+            depth[(size_t)pair * out_cap + i] = -1.0f;
+        }
+}
+
 }  // namespace vsg
 
 using namespace vsg;
@@ -228,5 +378,54 @@ extern "C" vsg_status vsg_stereo_match(vsg_matcher *m, vsg_extractor *left, vsg_
         u_right_out[dist_idx[i].second] = -1;
         depth_out[dist_idx[i].second] = -1;
     }
+    return VSG_OK;
+}
+
+extern "C" vsg_status vsg_stereo_match_batch(vsg_matcher *m, vsg_extractor *ex, int npairs, float mb, float mbf,
+                                             float *u_right_out, float *depth_out, int capacity) {
+    if (!m || !ex || npairs < 0 || (npairs > 0 && (!u_right_out || !depth_out))) return VSG_ERR_INVALID;
+    PyramidRef pr;
+    if (!extractor_pyramid(ex, &pr) || !pr.kps_dev || pr.device != m->device || 2 * npairs > pr.nframes) {
+        set_error("vsg_stereo_match_batch: the extractor's last call must be a host-pointer batch of >= 2 * npairs frames on the "
+                  "matcher's device (frames 2p / 2p+1 = left / right image of pair p)");
+        return VSG_ERR_INVALID;
+    }
+    if (capacity < pr.out_cap) {
+        set_error("vsg_stereo_match_batch: capacity %d < vsg_extractor_max_keypoints() = %d", capacity, pr.out_cap);
+        return VSG_ERR_CAPACITY;
+    }
+    if (npairs == 0) return VSG_OK;
+    CK(cudaSetDevice(m->device));
+    CK(cudaStreamSynchronize(pr.stream));
+    const int nl = pr.geom->nlevels, cap = pr.out_cap;
+    BatchPlanes P;
+    for (int l = 0; l < nl; ++l) {
+        const LevelGeom &G = pr.geom->lv[l];
+        if (l == 0) { P.base[l] = pr.lvl0_base; P.stride[l] = pr.lvl0_stride; P.pitch[l] = pr.lvl0_pitch; }
+        else { P.base[l] = pr.pyr + G.plane_offset; P.stride[l] = G.plane_stride; P.pitch[l] = G.pitch; }
+        P.w[l] = G.w;
+        P.scale[l] = pr.scale[l];
+        P.inv_scale[l] = pr.inv_scale[l];
+    }
+    P.n_rows = pr.geom->lv[0].h;
+    vsg_status st;
+    const size_t n = (size_t)npairs * cap;
+    if ((st = matcher_ensure(m, 6, n * 12)) || (st = matcher_ensure(m, 7, n * 8))) return st;
+    int *bd = (int *)m->buf[6], *bi = bd + n, *sad = bi + n;
+    float *ur = (float *)m->buf[7], *dp = ur + n;
+    cudaStream_t s = m->stream;
+    const float max_d = mbf / mb;
+    const size_t smem = (size_t)cap * sizeof(RightKp);
+    if (smem > 200 * 1024) { set_error("vsg_stereo_match_batch: too many keypoints per image (%d)", cap); return VSG_ERR_INVALID; }
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(stereo_search_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stereo_search_batch_kernel<<<dim3((cap + 127) / 128, npairs), 128, smem, s>>>(P, pr.kps_dev, (const uint4 *)pr.desc_dev, pr.n_dev,
+                                                                                 cap, max_d, bd, bi);
+    stereo_sad_batch_kernel<<<dim3((cap + 7) / 8, npairs), 256, 0, s>>>(P, pr.kps_dev, pr.n_dev, cap, bd, bi, max_d, mbf, sad, ur, dp);
+    stereo_median_kernel<<<npairs, 256, 0, s>>>(cap, sad, ur, dp);
+    count_launch(3);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy2DAsync(u_right_out, (size_t)capacity * 4, ur, (size_t)cap * 4, (size_t)cap * 4, npairs, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpy2DAsync(depth_out, (size_t)capacity * 4, dp, (size_t)cap * 4, (size_t)cap * 4, npairs, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
     return VSG_OK;
 }

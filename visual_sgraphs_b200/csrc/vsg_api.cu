@@ -118,6 +118,7 @@ struct vsg_extractor {
     int lvl0_pitch = 0;
     int64_t lvl0_stride = 0;
     int last_nframes = 0;
+    bool results_on_handle = false;    // kps_d / desc_d / n_d hold the last call's results (host-pointer API)
 
     void free_shape() {
         cudaFree(cells_d); cudaFree(tabs_d); cudaFree(pyr); cudaFree(blur); cudaFree(cand); cudaFree(node_of);
@@ -388,6 +389,10 @@ bool extractor_pyramid(vsg_extractor *ex, PyramidRef *out) {
     out->scale = ex->scale.data();
     out->inv_scale = ex->inv_scale.data();
     out->stream = ex->stream;
+    out->kps_dev = ex->results_on_handle ? ex->kps_d : nullptr;
+    out->desc_dev = ex->results_on_handle ? ex->desc_d : nullptr;
+    out->n_dev = ex->results_on_handle ? ex->n_d : nullptr;
+    out->out_cap = ex->g.out_cap;
     return true;
 }
 }  // namespace vsg
@@ -499,6 +504,7 @@ static vsg_status extract_batch_host(vsg_extractor *ex, const uint8_t *images, i
     const LevelGeom &L0 = g.lv[0];
     uint8_t *lvl0 = ex->pyr + L0.plane_offset;
     ex->lvl0_base = lvl0; ex->lvl0_pitch = L0.pitch; ex->lvl0_stride = L0.plane_stride; ex->last_nframes = nframes;
+    ex->results_on_handle = true;
     // Results go straight into the caller's arrays when those are page-locked (one strided D2H each, no
     // host-side copy); otherwise through the handle's pinned staging buffers.
     auto pinned = [](const void *p) {
@@ -621,6 +627,7 @@ vsg_status vsg_extract_batch_dev(vsg_extractor *ex, const uint8_t *images_dev, i
         return VSG_ERR_CAPACITY;
     }
     ex->lvl0_base = images_dev; ex->lvl0_pitch = pitch; ex->lvl0_stride = (int64_t)frame_stride; ex->last_nframes = nframes;
+    ex->results_on_handle = false;
     const int chunk = ex->dev_chunk_frames;
     if (ex->profile || chunk <= 0 || nframes < 2 * chunk)
         return run_pipeline(ex, ex->stream, 0, images_dev, pitch, (int64_t)frame_stride, nframes, lap_x0, lap_x1,

@@ -103,6 +103,11 @@ struct PyramidRef {
     const uint8_t *pyr;
     const float *scale, *inv_scale;   // host tables, nlevels entries
     cudaStream_t stream;
+    // device-resident results of the last host-pointer batch call (null after a device-resident call)
+    const vsg_keypoint *kps_dev;
+    const uint8_t *desc_dev;
+    const int *n_dev;
+    int out_cap;
 };
 bool extractor_pyramid(vsg_extractor *ex, PyramidRef *out);
 

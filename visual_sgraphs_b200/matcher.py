@@ -304,3 +304,12 @@ class ORBmatcher:
                                        len(keys_l), ptr(keys_r), ptr(desc_r), len(keys_r), float(mb), float(mbf),
                                        ptr(u_right), ptr(depth)))
         return u_right, depth
+
+    def ComputeStereoMatchesBatch(self, ex, npairs, mb, mbf):
+        """Frame::ComputeStereoMatches for pairs (2p, 2p+1) of the extractor's last extract_batch call, on its
+        device-resident results. Returns (u_right, depth) float32 arrays of shape (npairs, cap)."""
+        cap = self._L.vsg_extractor_max_keypoints(ex._h, *ex.level_size(0))
+        u = np.zeros((npairs, cap), np.float32)
+        d = np.zeros((npairs, cap), np.float32)
+        check(self._L.vsg_stereo_match_batch(self._h, ex._h, int(npairs), float(mb), float(mbf), ptr(u), ptr(d), cap))
+        return u, d
