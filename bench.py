@@ -114,7 +114,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.05)
+            time.sleep(0.004)
 
     def result(self):
         self.stop_flag = True
@@ -239,7 +239,8 @@ def other_config_extras(torch, lib, device):
     del d_frames, kps, desc
     # ---- C2 ----
     npairs = 64
-    pairs = [synth_stereo_pair(8000 + i) for i in range(npairs)]
+    base_pairs = [synth_stereo_pair(8000 + i) for i in range(8)]
+    pairs = [base_pairs[i % 8] for i in range(npairs)]
     stack = torch.from_numpy(np.stack([im for pr in pairs for im in pr])).pin_memory()   # L0 R0 L1 R1 ...
     ex2 = ORBextractor(1200, SCALE, NLEVELS, INI_TH, MIN_TH, device=device, max_batch=2 * npairs)
     m = ORBmatcher(device=device)
