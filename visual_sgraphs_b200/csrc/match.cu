@@ -31,6 +31,16 @@ vsg_status matcher_ensure(vsg_matcher *m, int slot, size_t bytes) {
     m->cap[slot] = want;
     return VSG_OK;
 }
+vsg_status matcher_ensure_host(vsg_matcher *m, int slot, size_t bytes) {
+    if (m->hcap[slot] >= bytes) return VSG_OK;
+    if (m->hbuf[slot]) cudaFreeHost(m->hbuf[slot]);
+    m->hbuf[slot] = nullptr;
+    m->hcap[slot] = 0;
+    const size_t want = bytes + bytes / 4 + 256;
+    CK(cudaMallocHost(&m->hbuf[slot], want));
+    m->hcap[slot] = want;
+    return VSG_OK;
+}
 static vsg_status ensure(vsg_matcher *m, int slot, size_t bytes) { return matcher_ensure(m, slot, bytes); }
 
 __device__ __forceinline__ int hamming256(const uint4 &a0, const uint4 &a1, const uint4 &b0, const uint4 &b1) {
@@ -264,6 +274,7 @@ void vsg_matcher_destroy(vsg_matcher *m) {
     cudaSetDevice(m->device);
     if (m->stream) { cudaStreamSynchronize(m->stream); cudaStreamDestroy(m->stream); }
     for (int i = 0; i < 12; ++i) cudaFree(m->buf[i]);
+    for (int i = 0; i < 6; ++i) cudaFreeHost(m->hbuf[i]);
     delete m;
 }
 

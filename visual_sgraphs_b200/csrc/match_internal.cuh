@@ -46,6 +46,15 @@ struct AreaQuery {          // one GetFeaturesInArea call + the per-candidate st
     float x, y, r;
     int min_level, max_level;
     float xr, rr;           // right-image gate: skip if u_right[idx] > 0 && |xr - u_right[idx]| > rr; rr < 0 disables it
+    int max_dist = 256;     // candidates farther than this are not listed: the caller proved they cannot change its result
+    int desc_idx = -1;      // row of the uploaded query descriptors (-1: the query's own index)
+};
+
+// Candidate lists as the kernel left them: query q's (idx, dist) pairs are raw[off[q] .. off[q] + cnt[q]) (segments in
+// arbitrary order).  The arrays live in the matcher's pinned staging and stay valid until its next search.
+struct AreaLists {
+    const int2 *raw = nullptr;
+    const int *off = nullptr, *cnt = nullptr;
 };
 
 
@@ -53,6 +62,9 @@ struct AreaQuery {          // one GetFeaturesInArea call + the per-candidate st
 // the lists back: ptr[nq+1] and (idx, dist) pairs in query order, each list in the reference's candidate order.
 vsg_status area_search(vsg_matcher *m, const vsg_frame *f, int nq, const AreaQuery *qs, const uint8_t *qdesc,
                        std::vector<int> &ptr, std::vector<int2> &ent);
+// the same without the re-pack into query order; n_qdesc rows of qdesc are uploaded (queries pick theirs by desc_idx)
+vsg_status area_search_raw(vsg_matcher *m, const vsg_frame *f, int nq, const AreaQuery *qs, const uint8_t *qdesc,
+                           int n_qdesc, AreaLists *out);
 // ORBmatcher::ComputeThreeMaxima (ORBmatcher.cc:2002-2043)
 void three_maxima(const std::vector<int> *hist, int L, int &ind1, int &ind2, int &ind3);
 // rotation-histogram bin (ORBmatcher.cc:351-358)

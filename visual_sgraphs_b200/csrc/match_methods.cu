@@ -15,7 +15,10 @@
 // is skipped by later ones, vMatchedDistance stealing, the rotation histogram) is sequential by
 // definition; it is replayed on the host over those lists, which is O(#candidates) integer work.
 #include <algorithm>
+#include <chrono>
 #include <climits>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <vector>
 
@@ -43,7 +46,11 @@ __global__ void area_search_kernel(FrameDev f, int nq, const AreaQuery *__restri
     const bool ok = !(min_cx >= f.cols || max_cx < 0 || min_cy >= f.rows || max_cy < 0) && a.r == a.r;
     const bool check_levels = (a.min_level > 0) || (a.max_level >= 0);
     uint4 qa, qb;
-    if (ok) { qa = __ldg(qdesc + 2 * q); qb = __ldg(qdesc + 2 * q + 1); }
+    if (ok) {
+        const int di = a.desc_idx >= 0 ? a.desc_idx : q;
+        qa = __ldg(qdesc + 2 * di);
+        qb = __ldg(qdesc + 2 * di + 1);
+    }
     for (int pass = 0; pass < 2 && ok; ++pass) {
         int w = 0;
         for (int ix = min_cx; ix <= max_cx; ++ix)
@@ -63,10 +70,10 @@ __global__ void area_search_kernel(FrameDev f, int nq, const AreaQuery *__restri
                         if (ur > 0 && fabsf(a.xr - ur) > a.rr) continue;
                     }
                     if (pass == 1) {
-                        if (off + w < cap) {
-                            const int d = hamming256(qa, qb, __ldg(f.desc + 2 * idx), __ldg(f.desc + 2 * idx + 1));
-                            out[off + w] = make_int2(idx, d);
-                        }
+                        // the segment was sized for every window hit; hits farther than max_dist are not stored
+                        const int d = hamming256(qa, qb, __ldg(f.desc + 2 * idx), __ldg(f.desc + 2 * idx + 1));
+                        if (d > a.max_dist) continue;
+                        if (off + w < cap) out[off + w] = make_int2(idx, d);
                     }
                     ++w;
                 }
@@ -75,6 +82,8 @@ __global__ void area_search_kernel(FrameDev f, int nq, const AreaQuery *__restri
             cnt = w;
             if (cnt == 0) break;
             off = atomicAdd(total, cnt);
+        } else {
+            cnt = w;                       // stored entries (<= the segment size)
         }
     }
     q_off[q] = off;
@@ -82,51 +91,84 @@ __global__ void area_search_kernel(FrameDev f, int nq, const AreaQuery *__restri
 }
 
 // Runs the area search for nq queries and brings the lists back: ptr[nq+1] and (idx, dist) pairs in query order.
-vsg_status area_search(vsg_matcher *m, const vsg_frame *f, int nq, const AreaQuery *qs, const uint8_t *qdesc,
-                              std::vector<int> &ptr, std::vector<int2> &ent) {
-    ptr.assign(nq + 1, 0);
-    ent.clear();
+static bool timing_on() { static const bool on = getenv("VSG_TIMING") != nullptr; return on; }
+struct PhaseTimer {
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    const char *what;
+    explicit PhaseTimer(const char *w) : what(w) {}
+    void mark(const char *phase) {
+        if (!timing_on()) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[vsg timing] %s: %s %.3f ms\n", what, phase, std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
+};
+
+vsg_status area_search_raw(vsg_matcher *m, const vsg_frame *f, int nq, const AreaQuery *qs, const uint8_t *qdesc,
+                           int n_qdesc, AreaLists *out) {
+    PhaseTimer pt("area_search");
+    *out = AreaLists();
     if (nq == 0) return VSG_OK;
     cudaStream_t s = m->stream;
     vsg_status st;
-    // slots: 7 queries, 8 qdesc, 9 off/cnt/total, 10 out entries
-    if ((st = matcher_ensure(m, 7, (size_t)nq * sizeof(AreaQuery))) || (st = matcher_ensure(m, 8, (size_t)nq * 32)) ||
-        (st = matcher_ensure(m, 9, (size_t)(2 * nq + 1) * sizeof(int))))
+    // device slots: 7 queries, 8 qdesc, 9 off/cnt/total, 10 out entries; pinned host slots: 0 off/cnt/total, 1 entries
+    if ((st = matcher_ensure(m, 7, (size_t)nq * sizeof(AreaQuery))) || (st = matcher_ensure(m, 8, (size_t)n_qdesc * 32)) ||
+        (st = matcher_ensure(m, 9, (size_t)(2 * nq + 1) * sizeof(int))) ||
+        (st = matcher_ensure_host(m, 0, (size_t)(2 * nq + 1) * sizeof(int))))
         return st;
     CK(cudaMemcpyAsync(m->buf[7], qs, (size_t)nq * sizeof(AreaQuery), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(m->buf[8], qdesc, (size_t)nq * 32, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(m->buf[8], qdesc, (size_t)n_qdesc * 32, cudaMemcpyHostToDevice, s));
     int *off_d = (int *)m->buf[9], *cnt_d = off_d + nq, *total_d = off_d + 2 * nq;
+    int *host = (int *)m->hbuf[0];
     FrameDev fd{f->n, f->cols, f->rows, f->min_x, f->min_y, f->inv_w, f->inv_h, f->xy, f->octave,
                 f->has_right ? f->u_right : nullptr, (const uint4 *)f->desc, f->cell_ptr, f->cell_idx};
     size_t cap = std::max<size_t>(m->cap[10] / sizeof(int2), (size_t)nq * 32);
-    std::vector<int> off(nq), cnt(nq);
     for (int attempt = 0; attempt < 2; ++attempt) {
         if ((st = matcher_ensure(m, 10, cap * sizeof(int2)))) return st;
         CK(cudaMemsetAsync(total_d, 0, sizeof(int), s));
         area_search_kernel<<<(nq + 127) / 128, 128, 0, s>>>(fd, nq, (const AreaQuery *)m->buf[7], (const uint4 *)m->buf[8],
                                                            off_d, cnt_d, (int2 *)m->buf[10], (int)cap, total_d);
         count_launch();
-        int total = 0;
-        CK(cudaMemcpyAsync(&total, total_d, sizeof(int), cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(off.data(), off_d, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(cnt.data(), cnt_d, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(host, off_d, (size_t)(2 * nq + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
+        pt.mark("H2D + kernel + D2H of offsets");
+        const int total = host[2 * nq];
         if ((size_t)total <= cap) {
-            std::vector<int2> raw(total);
-            if (total) CK(cudaMemcpy(raw.data(), m->buf[10], (size_t)total * sizeof(int2), cudaMemcpyDeviceToHost));
-            ent.resize(total);
-            int w = 0;
-            for (int q = 0; q < nq; ++q) {      // segments were allocated in arbitrary order: re-pack by query
-                ptr[q] = w;
-                for (int k = 0; k < cnt[q]; ++k) ent[w++] = raw[off[q] + k];
+            if ((st = matcher_ensure_host(m, 1, (size_t)std::max(total, 1) * sizeof(int2)))) return st;
+            if (total) {
+                CK(cudaMemcpyAsync(m->hbuf[1], m->buf[10], (size_t)total * sizeof(int2), cudaMemcpyDeviceToHost, s));
+                CK(cudaStreamSynchronize(s));
             }
-            ptr[nq] = w;
+            pt.mark("D2H of entries");
+            out->raw = (const int2 *)m->hbuf[1];
+            out->off = host;
+            out->cnt = host + nq;
             return VSG_OK;
         }
         cap = (size_t)total + 1024;             // retry once with the exact size
     }
     set_error("area_search: candidate buffer overflow");
     return VSG_ERR_CAPACITY;
+}
+
+// Runs the area search for nq queries and brings the lists back: ptr[nq+1] and (idx, dist) pairs in query order.
+vsg_status area_search(vsg_matcher *m, const vsg_frame *f, int nq, const AreaQuery *qs, const uint8_t *qdesc,
+                       std::vector<int> &ptr, std::vector<int2> &ent) {
+    ptr.assign(nq + 1, 0);
+    ent.clear();
+    AreaLists L;
+    vsg_status st = area_search_raw(m, f, nq, qs, qdesc, nq, &L);
+    if (st != VSG_OK || nq == 0) return st;
+    int total = 0;
+    for (int q = 0; q < nq; ++q) total += L.cnt[q];
+    ent.resize(total);
+    int w = 0;
+    for (int q = 0; q < nq; ++q) {              // segments were allocated in arbitrary order: re-pack by query
+        ptr[q] = w;
+        for (int k = 0; k < L.cnt[q]; ++k) ent[w++] = L.raw[L.off[q] + k];
+    }
+    ptr[nq] = w;
+    return VSG_OK;
 }
 
 // ORBmatcher::ComputeThreeMaxima (ORBmatcher.cc:2002-2043)
@@ -241,8 +283,18 @@ vsg_status vsg_area_search(vsg_matcher *m, const vsg_frame *f, int nq, const flo
 }
 
 // ORBmatcher.cc:48-74: the map points that reach GetFeaturesInArea, as window queries
+// Candidates at distance d > TH_HIGH with nnratio * d >= TH_HIGH can neither become the best match (:123) nor, as the
+// second best, trigger the ratio rejection (:125: best <= TH_HIGH <= nnratio * d), and every candidate that stays is
+// closer than every one dropped — so the replay over the pruned lists gives the identical result.
+static int projection_map_max_dist(float nnratio) {
+    int d = TH_HIGH + 1;
+    while (d < 256 && !(nnratio * (float)d >= (float)TH_HIGH)) ++d;
+    return d - 1;
+}
+
 static vsg_status projection_map_queries(const std::vector<float> &scale, int n_mp, const vsg_track_point *pts, float th,
-                                         int far_points, float th_far, std::vector<AreaQuery> &qs, std::vector<int> &q_mp) {
+                                         int far_points, float th_far, int max_dist, std::vector<AreaQuery> &qs,
+                                         std::vector<int> &q_mp) {
     const bool b_factor = th != 1.0;
     qs.clear(); q_mp.clear();
     qs.reserve(n_mp); q_mp.reserve(n_mp);
@@ -255,7 +307,7 @@ static vsg_status projection_map_queries(const std::vector<float> &scale, int n_
         float r = (mp.view_cos > 0.998) ? 2.5f : 4.0f;    // RadiusByViewingCos (:218-224)
         if (b_factor) r *= th;
         const float win = r * scale[mp.level];
-        qs.push_back(AreaQuery{mp.proj_x, mp.proj_y, win, mp.level - 1, mp.level, mp.proj_xr, win});
+        qs.push_back(AreaQuery{mp.proj_x, mp.proj_y, win, mp.level - 1, mp.level, mp.proj_xr, win, max_dist});
         q_mp.push_back(i);
     }
     return VSG_OK;
@@ -299,8 +351,8 @@ vsg_status vsg_projection_map_candidates(vsg_matcher *m, const vsg_frame *F, int
     CK(cudaSetDevice(m->device));
     std::vector<AreaQuery> qs;
     std::vector<int> q_mp;
-    vsg_status st = projection_map_queries(F->scale, n_mp, pts, th, far_points, th_far, qs, q_mp);
-    if (st != VSG_OK) return st;
+    vsg_status st = projection_map_queries(F->scale, n_mp, pts, th, far_points, th_far, 256, qs, q_mp);   // full lists: the
+    if (st != VSG_OK) return st;                                                           // resolve's nnratio is not known here
     std::vector<uint8_t> qdesc(qs.size() * 32);
     for (size_t k = 0; k < qs.size(); ++k) memcpy(&qdesc[k * 32], mp_desc + (size_t)q_mp[k] * 32, 32);
     std::vector<int> ptr;
@@ -343,26 +395,59 @@ vsg_status vsg_search_by_projection_map(vsg_matcher *m, const vsg_frame *F, cons
                                         float th_far, float nnratio, int32_t *assign_out, int *nmatches_out) {
     if (!m || !F || n_mp < 0 || !assign_out || (n_mp > 0 && (!pts || !mp_desc)) || (F->n > 0 && !occupied)) return VSG_ERR_INVALID;
     CK(cudaSetDevice(m->device));
-    std::vector<AreaQuery> qs;
-    std::vector<int> q_mp;
-    vsg_status st = projection_map_queries(F->scale, n_mp, pts, th, far_points, th_far, qs, q_mp);
-    if (st != VSG_OK) return st;
-    std::vector<uint8_t> qdesc(qs.size() * 32);
-    for (size_t k = 0; k < qs.size(); ++k) memcpy(&qdesc[k * 32], mp_desc + (size_t)q_mp[k] * 32, 32);
-    std::vector<int> ptr;
-    std::vector<int2> ent;
-    if ((st = area_search(m, F, (int)qs.size(), qs.data(), qdesc.data(), ptr, ent)) != VSG_OK) return st;
-    // per-map-point lists for the replay
-    std::vector<int32_t> mp_ptr(n_mp + 1), ci(ent.size()), cd(ent.size());
-    size_t q = 0;
-    for (int i = 0; i < n_mp; ++i) {
-        mp_ptr[i] = q < qs.size() ? ptr[q] : (int)ent.size();
-        if (q < qs.size() && q_mp[q] == i) ++q;
+    PhaseTimer pt("search_by_projection_map");
+    // query list in the matcher's reusable scratch (a 200k-point map is 8 MB of queries: no fresh pages per call)
+    m->scratch[0].resize((size_t)std::max(n_mp, 1) * sizeof(AreaQuery));
+    m->scratch[1].resize((size_t)std::max(n_mp, 1) * sizeof(int));
+    AreaQuery *qs = reinterpret_cast<AreaQuery *>(m->scratch[0].data());
+    int *q_mp = reinterpret_cast<int *>(m->scratch[1].data());
+    int nq = 0;
+    {
+        const bool b_factor = th != 1.0;
+        const int max_dist = projection_map_max_dist(nnratio);
+        for (int i = 0; i < n_mp; ++i) {                      // :48-74
+            const vsg_track_point &mp = pts[i];
+            if (!mp.in_view) continue;
+            if (far_points && mp.depth > th_far) continue;
+            if (mp.bad) continue;
+            if (mp.level < 0 || mp.level >= (int)F->scale.size()) { set_error("map point %d: level %d out of range", i, mp.level); return VSG_ERR_INVALID; }
+            float r = (mp.view_cos > 0.998) ? 2.5f : 4.0f;    // RadiusByViewingCos (:218-224)
+            if (b_factor) r *= th;
+            const float win = r * F->scale[mp.level];
+            qs[nq] = AreaQuery{mp.proj_x, mp.proj_y, win, mp.level - 1, mp.level, mp.proj_xr, win, max_dist, i};   // desc row i
+            q_mp[nq++] = i;
+        }
     }
-    mp_ptr[n_mp] = (int)ent.size();
-    for (size_t k = 0; k < ent.size(); ++k) { ci[k] = ent[k].x; cd[k] = ent[k].y; }
-    const int nm = projection_map_resolve(F->n, F->keys.data(), occupied, n_mp, pts, mp_ptr.data(), ci.data(), cd.data(), nnratio, assign_out);
-    if (nmatches_out) *nmatches_out = nm;
+    pt.mark("queries");
+    AreaLists L;
+    vsg_status st;
+    if ((st = area_search_raw(m, F, nq, qs, mp_desc, n_mp, &L)) != VSG_OK) return st;
+    pt.mark("area_search total");
+    // sequential replay of :76-141 straight over the kernel's segments (query k = map point q_mp[k], in map order)
+    std::vector<uint8_t> blocked(occupied, occupied + F->n);
+    for (int i = 0; i < F->n; ++i) assign_out[i] = -1;
+    const vsg_keypoint *keys = F->keys.data();
+    int nmatches = 0;
+    for (int k = 0; k < nq; ++k) {
+        int best = 256, best_level = -1, best2 = 256, best_level2 = -1, best_idx = -1;
+        const int2 *c = L.raw + L.off[k], *ce = c + L.cnt[k];
+        for (; c < ce; ++c) {
+            const int idx = c->x, dist = c->y;
+            if (blocked[idx]) continue;
+            if (dist < best) { best2 = best; best = dist; best_level2 = best_level; best_level = keys[idx].octave; best_idx = idx; }
+            else if (dist < best2) { best_level2 = keys[idx].octave; best2 = dist; }
+        }
+        if (best <= TH_HIGH) {
+            if (best_level == best_level2 && best > nnratio * best2) continue;
+            if (best_level != best_level2 || best <= nnratio * best2) {
+                assign_out[best_idx] = q_mp[k];
+                blocked[best_idx] = pts[q_mp[k]].blocks;
+                ++nmatches;
+            }
+        }
+    }
+    pt.mark("resolve");
+    if (nmatches_out) *nmatches_out = nmatches;
     return VSG_OK;
 }
 

@@ -8,6 +8,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "../../include/vsg_cuda.h"
 
 namespace vsg {
@@ -82,12 +84,16 @@ struct vsg_matcher {
     cudaStream_t stream = nullptr;
     void *buf[12] = {};
     size_t cap[12] = {};
+    void *hbuf[6] = {};      // pinned host staging (grows on demand): results come back without page faults
+    size_t hcap[6] = {};
+    std::vector<char> scratch[2];   // reusable host scratch of the search methods (query lists), kept across calls
     int sm_count = 148;
 };
 
 namespace vsg {
 
 vsg_status matcher_ensure(vsg_matcher *m, int slot, size_t bytes);
+vsg_status matcher_ensure_host(vsg_matcher *m, int slot, size_t bytes);
 // distances of every CSR candidate: all_dist[c] = |query[q] xor train[cand[c]]| for c in [cand_ptr[q], cand_ptr[q+1])
 void launch_window_dists(vsg_matcher *m, const uint8_t *query_dev, int nq, const uint8_t *train_dev,
                          const int *cand_ptr_dev, const int *cand_dev, int *all_dist_dev);
