@@ -252,3 +252,35 @@ def test_random_configurations(oracle, seed):
     got = ORBextractor(nfeat, scale, nlevels, ini, mn)(frame, lap)
     want = oracle.OracleExtractor(nfeat, scale, nlevels, ini, mn)(frame, lap)
     _compare_outputs(got, want, "seed %d: %dx%d nfeat %d scale %.2f levels %d th %d/%d" % (seed, w, h, nfeat, scale, nlevels, ini, mn))
+
+
+def test_error_conventions_of_the_c_abi():
+    """Status codes at the boundary: bad arguments are VSG_ERR_INVALID, too-small outputs VSG_ERR_CAPACITY, an empty
+    image the reference's -1 (VSG_EMPTY_IMAGE, ORBextractor.cc:1087-1088); a failed call leaves the handle usable."""
+    import ctypes as C
+    from visual_sgraphs_b200 import _lib
+    from visual_sgraphs_b200._lib import KEYPOINT_DTYPE, ptr
+    L = _lib.load()
+    ex = _extractor(1000, max_batch=2)
+    frame = synth_frame(77, 640, 480)
+    cap = ex.max_keypoints(640, 480)
+    kps, desc = np.zeros(cap, KEYPOINT_DTYPE), np.zeros((cap, 32), np.uint8)
+    n, mono = C.c_int(0), C.c_int(0)
+    args = lambda img, w, h, pitch, c: (ex._h, ptr(img), w, h, pitch, 0, 0, ptr(kps), ptr(desc), c, C.byref(n), C.byref(mono))
+    assert L.vsg_extract(*args(None, 640, 480, 640, cap)) == _lib.VSG_EMPTY_IMAGE
+    assert L.vsg_extract(*args(frame, 0, 480, 640, cap)) == _lib.VSG_EMPTY_IMAGE
+    assert L.vsg_extract(*args(frame, 640, 480, 320, cap)) == _lib.VSG_ERR_INVALID          # pitch < width
+    assert L.vsg_extract(*args(frame, 60, 60, 640, cap)) == _lib.VSG_ERR_INVALID            # too small for one 35-px cell
+    assert b"too small" in L.vsg_last_error()
+    assert L.vsg_extract(*args(frame, 640, 480, 640, 10)) == _lib.VSG_ERR_CAPACITY          # 10 slots for ~1000 keypoints
+    three = np.stack([frame] * 3)
+    kb, db = np.zeros((3, cap), KEYPOINT_DTYPE), np.zeros((3, cap, 32), np.uint8)
+    nb, mb = np.zeros(3, np.int32), np.zeros(3, np.int32)
+    assert L.vsg_extract_batch(ex._h, ptr(three), 3, 640, 480, 640, 640 * 480, 0, 0, ptr(kb), ptr(db), cap, ptr(nb),
+                               ptr(mb)) == _lib.VSG_ERR_INVALID                              # 3 frames > max_batch 2
+    assert L.vsg_extract_batch_color(ex._h, ptr(three), 1, 640, 480, 640 * 2, 640 * 480 * 2, 2, 1, 0, 0, ptr(kb), ptr(db),
+                                     cap, ptr(nb), ptr(mb)) == _lib.VSG_ERR_INVALID          # 2 channels
+    assert L.vsg_extractor_create(C.byref(_lib.OrbParams(1000, 2.5, 8, 20, 7)), 0, 1, C.byref(C.c_void_p())) == _lib.VSG_ERR_INVALID
+    assert L.vsg_extractor_create(C.byref(_lib.OrbParams(1000, 1.2, 8, 20, 7)), 99, 1, C.byref(C.c_void_p())) == _lib.VSG_ERR_CUDA
+    m, k, d = ex(frame)                                                                      # the handle still works
+    assert m == len(k) > 900

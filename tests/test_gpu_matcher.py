@@ -188,3 +188,24 @@ def test_bow_transform(oracle):
     assert len(nodes) > 5 and abs(sum(bow.values()) - 1.0) < 1e-9
     walk0, _ = V.walk(np.zeros((0, 32), np.uint8))
     assert len(walk0) == 0
+
+
+def test_matcher_error_conventions():
+    import ctypes as C
+    from visual_sgraphs_b200 import _lib
+    from visual_sgraphs_b200._lib import ptr
+    from visual_sgraphs_b200.matcher import ORBmatcher
+    L = _lib.load()
+    m = ORBmatcher()
+    q = np.zeros((4, 32), np.uint8)
+    out = np.zeros((4, 2), np.int32)
+    assert L.vsg_knn2(m._h, ptr(q), -1, ptr(q), 4, 0, ptr(out), ptr(out)) == _lib.VSG_ERR_INVALID
+    assert L.vsg_knn2(None, ptr(q), 4, ptr(q), 4, 0, ptr(out), ptr(out)) == _lib.VSG_ERR_INVALID
+    idx, dist = m.knn2(q, np.zeros((0, 32), np.uint8))                     # empty train set: no neighbours
+    assert (idx == -1).all() and (dist == np.iinfo(np.int32).max).all()
+    bad_ptr = np.array([0, 3, 2], np.int32)                                # decreasing CSR offsets
+    assert L.vsg_distinctive_descriptors(m._h, ptr(q), ptr(bad_ptr), 2, ptr(out)) == _lib.VSG_ERR_INVALID
+    assert L.vsg_matcher_create(99, C.byref(C.c_void_p())) == _lib.VSG_ERR_CUDA
+    # a vocabulary whose child lists do not cover every node exactly once is rejected
+    assert L.vsg_vocabulary_create(m._h, 3, ptr(np.array([0, 1, 1, 1], np.int32)), ptr(np.array([1], np.int32)),
+                                   ptr(np.zeros((3, 32), np.uint8)), 2, C.byref(C.c_void_p())) == _lib.VSG_ERR_INVALID
