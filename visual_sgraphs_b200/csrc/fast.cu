@@ -279,7 +279,10 @@ __global__ void __launch_bounds__(kFastThreads, 8) fast_kernel(FrameGeom g,
 //                             position == ratio is blur block `group`;
 //   beyond that:              the remaining cells.
 static_assert(kFastThreads == kBlurThreads, "the fused kernel runs both roles with the same block size");
-__global__ void __launch_bounds__(kFastThreads, 8) fast_blur_kernel(FrameGeom g, BlurLevels bl,
+#ifndef VSG_FAST_MINB
+#define VSG_FAST_MINB 8
+#endif
+__global__ void __launch_bounds__(kFastThreads, VSG_FAST_MINB) fast_blur_kernel(FrameGeom g, BlurLevels bl,
                                                                   const uint8_t *__restrict__ lvl0_base, int lvl0_pitch,
                                                                   int64_t lvl0_stride, const uint8_t *__restrict__ pyr,
                                                                   uint8_t *__restrict__ blur, Cand *__restrict__ cand,
