@@ -322,8 +322,12 @@ def matching_extras(torch, device):
         m.sync()
         ms = e0.elapsed_time(e1) / reps
         pairs = nq * nt
+        sms = torch.cuda.get_device_properties(device).multi_processor_count
+        peak = 16.0 * sms * 1965e6          # POPC: 16 results / clk / SM on the XU pipe (measured: ncu pipe_xu 97 % active)
         out[name] = {"ms": ms, "pairs_per_s": pairs / (ms * 1e-3), "matches_per_s": nq / (ms * 1e-3),
-                     "popc_per_s": 8 * pairs / (ms * 1e-3)}
+                     "popc_per_s": 8 * pairs / (ms * 1e-3),
+                     "roofline": {"bound": "popc (xu pipe)", "achieved": 8 * pairs / (ms * 1e-3), "peak": peak,
+                                  "unit": "POPC/s", "frac": 8 * pairs / (ms * 1e-3) / peak}}
     m.close()
     return out
 
