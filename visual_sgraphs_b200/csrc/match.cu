@@ -265,6 +265,15 @@ vsg_status vsg_matcher_create(int device, vsg_matcher **out) {
         return VSG_ERR_CUDA;
     }
     cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device);
+    {   // frame uploads use the stream-ordered allocator: keep freed blocks in the pool instead of returning them to the OS
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = 256ull << 20;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        } else {
+            cudaGetLastError();
+        }
+    }
     *out = m;
     return VSG_OK;
 }

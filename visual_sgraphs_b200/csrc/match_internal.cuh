@@ -9,7 +9,8 @@ struct vsg_frame {
     int n = 0, cols = 0, rows = 0, n_levels = 0;
     float min_x = 0, min_y = 0, inv_w = 0, inv_h = 0;
     bool has_right = false;
-    // device
+    // device: one stream-ordered allocation (`block`), carved into the arrays below
+    void *block = nullptr;
     float2 *xy = nullptr;
     int *octave = nullptr;
     float *u_right = nullptr;

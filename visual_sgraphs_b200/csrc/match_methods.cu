@@ -16,6 +16,7 @@
 // definition; it is replayed on the host over those lists, which is O(#candidates) integer work.
 #include <algorithm>
 #include <chrono>
+#include <cstring>
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
@@ -31,32 +32,59 @@ __device__ __forceinline__ int hamming256(const uint4 &a0, const uint4 &a1, cons
            __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
 }
 
-// One thread per query: walk the cell range twice (count, then fill).  Frame.cc:802-868.
-__global__ void area_search_kernel(FrameDev f, int nq, const AreaQuery *__restrict__ qs,
-                                   const uint4 *__restrict__ qdesc, int *__restrict__ q_off, int *__restrict__ q_cnt,
-                                   int2 *__restrict__ out, int cap, int *__restrict__ total) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per query (Frame.cc:802-868).  The cells of the query window, flattened in the reference's walk order
+// (ix outer, iy inner), are dealt to the lanes 32 at a time; every lane filters the keypoints of its cell (level range,
+// |dx|, |dy| < r, the caller's stereo gate) and measures their Hamming distance to the query descriptor.  A warp prefix
+// sum over the per-lane hit counts gives every hit its position in the query's list, so the list comes out in exactly
+// the order the reference's three nested loops produce.  Two sweeps: the first only counts (the query's segment of the
+// output is then reserved with one atomic), the second stores.
+__global__ void __launch_bounds__(256) area_search_kernel(FrameDev f, int nq, const AreaQuery *__restrict__ qs,
+                                                          const uint4 *__restrict__ qdesc, int *__restrict__ q_off,
+                                                          int *__restrict__ q_cnt, int2 *__restrict__ out, int cap,
+                                                          int *__restrict__ total) {
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (q >= nq) return;
     const AreaQuery a = qs[q];
-    int cnt = 0, off = 0;
     const int min_cx = max(0, (int)floorf((a.x - f.min_x - a.r) * f.inv_w));
     const int max_cx = min(f.cols - 1, (int)ceilf((a.x - f.min_x + a.r) * f.inv_w));
     const int min_cy = max(0, (int)floorf((a.y - f.min_y - a.r) * f.inv_h));
     const int max_cy = min(f.rows - 1, (int)ceilf((a.y - f.min_y + a.r) * f.inv_h));
     const bool ok = !(min_cx >= f.cols || max_cx < 0 || min_cy >= f.rows || max_cy < 0) && a.r == a.r;
-    const bool check_levels = (a.min_level > 0) || (a.max_level >= 0);
-    uint4 qa, qb;
-    if (ok) {
-        const int di = a.desc_idx >= 0 ? a.desc_idx : q;
-        qa = __ldg(qdesc + 2 * di);
-        qb = __ldg(qdesc + 2 * di + 1);
+    if (!ok) {
+        if (lane == 0) { q_off[q] = 0; q_cnt[q] = 0; }
+        return;
     }
-    for (int pass = 0; pass < 2 && ok; ++pass) {
-        int w = 0;
-        for (int ix = min_cx; ix <= max_cx; ++ix)
-            for (int iy = min_cy; iy <= max_cy; ++iy) {
+    const bool check_levels = (a.min_level > 0) || (a.max_level >= 0);
+    const int di = a.desc_idx >= 0 ? a.desc_idx : q;
+    const uint4 qa = __ldg(qdesc + 2 * di), qb = __ldg(qdesc + 2 * di + 1);
+    const int ncy = max_cy - min_cy + 1, ncell = (max_cx - min_cx + 1) * ncy;
+    int off = 0, stored = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        int before = 0;                                   // hits of the cells ahead of this round
+        for (int base = 0; base < ncell; base += 32) {
+            const int k = base + lane;
+            int jb = 0, je = 0;
+            if (k < ncell) {
+                const int ix = min_cx + k / ncy, iy = min_cy + k % ncy;
                 const int c = ix * f.rows + iy;
-                for (int j = f.cell_ptr[c]; j < f.cell_ptr[c + 1]; ++j) {
+                jb = f.cell_ptr[c];
+                je = f.cell_ptr[c + 1];
+            }
+            // sweep 0 counts this lane's hits; sweep 1 needs the count first for the positions, so it filters twice
+            int mine = 0;
+            for (int rep = 0; rep <= pass; ++rep) {
+                int w = 0, pos = 0;
+                if (rep == 1) {                           // positions: exclusive prefix of `mine` over the lanes
+                    int incl = mine;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += v;
+                    }
+                    pos = off + before + incl - mine;
+                    before += __shfl_sync(0xffffffffu, incl, 31);
+                }
+                for (int j = jb; j < je; ++j) {
                     const int idx = f.cell_idx[j];
                     if (check_levels) {
                         const int o = f.octave[idx];
@@ -69,28 +97,28 @@ __global__ void area_search_kernel(FrameDev f, int nq, const AreaQuery *__restri
                         const float ur = f.u_right[idx];
                         if (ur > 0 && fabsf(a.xr - ur) > a.rr) continue;
                     }
-                    if (pass == 1) {
-                        // the segment was sized for every window hit; hits farther than max_dist are not stored
-                        const int d = hamming256(qa, qb, __ldg(f.desc + 2 * idx), __ldg(f.desc + 2 * idx + 1));
-                        if (d > a.max_dist) continue;
-                        if (off + w < cap) out[off + w] = make_int2(idx, d);
-                    }
+                    const int d = hamming256(qa, qb, __ldg(f.desc + 2 * idx), __ldg(f.desc + 2 * idx + 1));
+                    if (d > a.max_dist) continue;         // farther than the caller can use: not listed
+                    if (rep == 1 && pos + w < cap) out[pos + w] = make_int2(idx, d);
                     ++w;
                 }
+                mine = w;
             }
+            if (pass == 0) {
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
+                stored += mine;
+            }
+        }
         if (pass == 0) {
-            cnt = w;
-            if (cnt == 0) break;
-            off = atomicAdd(total, cnt);
-        } else {
-            cnt = w;                       // stored entries (<= the segment size)
+            if (stored == 0) break;
+            if (lane == 0) off = atomicAdd(total, stored);
+            off = __shfl_sync(0xffffffffu, off, 0);
         }
     }
-    q_off[q] = off;
-    q_cnt[q] = cnt;
+    if (lane == 0) { q_off[q] = off; q_cnt[q] = stored; }
 }
 
-// Runs the area search for nq queries and brings the lists back: ptr[nq+1] and (idx, dist) pairs in query order.
 static bool timing_on() { static const bool on = getenv("VSG_TIMING") != nullptr; return on; }
 struct PhaseTimer {
     std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
@@ -126,8 +154,8 @@ vsg_status area_search_raw(vsg_matcher *m, const vsg_frame *f, int nq, const Are
     for (int attempt = 0; attempt < 2; ++attempt) {
         if ((st = matcher_ensure(m, 10, cap * sizeof(int2)))) return st;
         CK(cudaMemsetAsync(total_d, 0, sizeof(int), s));
-        area_search_kernel<<<(nq + 127) / 128, 128, 0, s>>>(fd, nq, (const AreaQuery *)m->buf[7], (const uint4 *)m->buf[8],
-                                                           off_d, cnt_d, (int2 *)m->buf[10], (int)cap, total_d);
+        area_search_kernel<<<(nq + 7) / 8, 256, 0, s>>>(fd, nq, (const AreaQuery *)m->buf[7], (const uint4 *)m->buf[8],
+                                                       off_d, cnt_d, (int2 *)m->buf[10], (int)cap, total_d);
         count_launch();
         CK(cudaMemcpyAsync(host, off_d, (size_t)(2 * nq + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
@@ -225,29 +253,32 @@ vsg_status vsg_frame_create(vsg_matcher *m, const vsg_frame_view *v, vsg_frame *
     std::vector<int> fill(cptr.begin(), cptr.end() - 1);
     for (int i = 0; i < v->n; ++i)
         if (cell_of[i] >= 0) cidx[fill[cell_of[i]]++] = i;
-    std::vector<float2> xy(v->n);
-    std::vector<int> oct(v->n);
-    for (int i = 0; i < v->n; ++i) { xy[i] = make_float2(v->keys[i].x, v->keys[i].y); oct[i] = v->keys[i].octave; }
+    // One pinned staging block, one stream-ordered device allocation, one H2D copy (a Search* call of the drop-in
+    // classes uploads a frame every time: six cudaMalloc / cudaFree pairs per call cost more than the search itself).
     const size_t n1 = std::max(v->n, 1);
-    bool ok = cuda_ok(cudaMalloc(&f->xy, n1 * sizeof(float2)), "cudaMalloc") &&
-              cuda_ok(cudaMalloc(&f->octave, n1 * sizeof(int)), "cudaMalloc") &&
-              cuda_ok(cudaMalloc(&f->u_right, n1 * sizeof(float)), "cudaMalloc") &&
-              cuda_ok(cudaMalloc(&f->desc, n1 * 32), "cudaMalloc") &&
-              cuda_ok(cudaMalloc(&f->cell_ptr, (size_t)(ncell + 1) * sizeof(int)), "cudaMalloc") &&
-              cuda_ok(cudaMalloc(&f->cell_idx, std::max<size_t>(cidx.size(), 1) * sizeof(int)), "cudaMalloc");
+    auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    const size_t o_xy = 0, o_oct = o_xy + up16(n1 * sizeof(float2)), o_ur = o_oct + up16(n1 * sizeof(int)),
+                 o_desc = o_ur + up16(n1 * sizeof(float)), o_cptr = o_desc + up16(n1 * 32),
+                 o_cidx = o_cptr + up16((size_t)(ncell + 1) * sizeof(int)),
+                 total = o_cidx + up16(std::max<size_t>(cidx.size(), 1) * sizeof(int));
+    vsg_status st = matcher_ensure_host(m, 2, total);
+    if (st != VSG_OK) { delete f; return st; }
+    uint8_t *h = (uint8_t *)m->hbuf[2];
+    float2 *hxy = (float2 *)(h + o_xy);
+    int *hoct = (int *)(h + o_oct);
+    for (int i = 0; i < v->n; ++i) { hxy[i] = make_float2(v->keys[i].x, v->keys[i].y); hoct[i] = v->keys[i].octave; }
+    if (v->u_right) memcpy(h + o_ur, v->u_right, (size_t)v->n * sizeof(float));
+    if (v->n) memcpy(h + o_desc, v->descriptors, (size_t)v->n * 32);
+    memcpy(h + o_cptr, cptr.data(), (size_t)(ncell + 1) * sizeof(int));
+    if (!cidx.empty()) memcpy(h + o_cidx, cidx.data(), cidx.size() * sizeof(int));
     cudaStream_t s = m->stream;
-    if (ok && v->n) {
-        ok = cuda_ok(cudaMemcpyAsync(f->xy, xy.data(), v->n * sizeof(float2), cudaMemcpyHostToDevice, s), "H2D") &&
-             cuda_ok(cudaMemcpyAsync(f->octave, oct.data(), v->n * sizeof(int), cudaMemcpyHostToDevice, s), "H2D") &&
-             cuda_ok(cudaMemcpyAsync(f->desc, v->descriptors, (size_t)v->n * 32, cudaMemcpyHostToDevice, s), "H2D");
-        if (ok && v->u_right)
-            ok = cuda_ok(cudaMemcpyAsync(f->u_right, v->u_right, v->n * sizeof(float), cudaMemcpyHostToDevice, s), "H2D");
-        if (ok && !cidx.empty())
-            ok = cuda_ok(cudaMemcpyAsync(f->cell_idx, cidx.data(), cidx.size() * sizeof(int), cudaMemcpyHostToDevice, s), "H2D");
-    }
-    if (ok) ok = cuda_ok(cudaMemcpyAsync(f->cell_ptr, cptr.data(), (size_t)(ncell + 1) * sizeof(int), cudaMemcpyHostToDevice, s), "H2D") &&
-                 cuda_ok(cudaStreamSynchronize(s), "sync");
+    bool ok = cuda_ok(cudaMallocAsync(&f->block, total, s), "cudaMallocAsync") &&
+              cuda_ok(cudaMemcpyAsync(f->block, h, total, cudaMemcpyHostToDevice, s), "H2D") &&
+              cuda_ok(cudaStreamSynchronize(s), "sync");
     if (!ok) { vsg_frame_destroy(f); return VSG_ERR_CUDA; }
+    uint8_t *d = (uint8_t *)f->block;
+    f->xy = (float2 *)(d + o_xy); f->octave = (int *)(d + o_oct); f->u_right = (float *)(d + o_ur);
+    f->desc = d + o_desc; f->cell_ptr = (int *)(d + o_cptr); f->cell_idx = (int *)(d + o_cidx);
     *out = f;
     return VSG_OK;
 }
@@ -255,7 +286,9 @@ vsg_status vsg_frame_create(vsg_matcher *m, const vsg_frame_view *v, vsg_frame *
 void vsg_frame_destroy(vsg_frame *f) {
     if (!f) return;
     cudaSetDevice(f->device);
-    cudaFree(f->xy); cudaFree(f->octave); cudaFree(f->u_right); cudaFree(f->desc); cudaFree(f->cell_ptr); cudaFree(f->cell_idx);
+    // every search returns only after its kernels have finished, so the block can go back to the pool right away;
+    // the frame may outlive the matcher whose stream allocated it, hence the per-thread stream
+    if (f->block) cudaFreeAsync(f->block, cudaStreamPerThread);
     delete f;
 }
 
