@@ -284,3 +284,39 @@ def test_error_conventions_of_the_c_abi():
     assert L.vsg_extractor_create(C.byref(_lib.OrbParams(1000, 1.2, 8, 20, 7)), 99, 1, C.byref(C.c_void_p())) == _lib.VSG_ERR_CUDA
     m, k, d = ex(frame)                                                                      # the handle still works
     assert m == len(k) > 900
+
+
+def test_baseline_batch_size_properties(oracle):
+    """The bench's batch shape (512 frames of 640x480 through the chunked host-pointer pipeline): every frame is
+    independent of its position in the batch (the 32 distinct frames repeat 16 times and must repeat their results),
+    the first and the last frame equal the oracle, the device-resident path gives the same bytes."""
+    torch = pytest.importorskip("torch")
+    from visual_sgraphs_b200._lib import KEYPOINT_DTYPE, check, ptr
+    base = synth_sequence(32, 640, 480, first_seed=12000)
+    frames = torch.from_numpy(np.concatenate([base] * 16)).pin_memory()
+    ex = _extractor(1000, max_batch=512)
+    cap = ex.max_keypoints(640, 480)
+    kps = torch.zeros((512, cap, 28), dtype=torch.uint8).pin_memory()
+    desc = torch.zeros((512, cap, 32), dtype=torch.uint8).pin_memory()
+    n, mono = np.zeros(512, np.int32), np.zeros(512, np.int32)
+    check(ex._L.vsg_extract_batch(ex._h, ptr(frames), 512, 640, 480, 640, 640 * 480, 0, 0, ptr(kps), ptr(desc), cap, ptr(n),
+                                  ptr(mono)))
+    kn, dn = kps.numpy(), desc.numpy()
+    for f in range(32, 512):
+        b = f % 32
+        assert n[f] == n[b] and kn[f, :n[f]].tobytes() == kn[b, :n[b]].tobytes() and dn[f, :n[f]].tobytes() == dn[b, :n[b]].tobytes(), f
+    orc = oracle.OracleExtractor(1000)
+    for f in (0, 31):
+        k = kn[f, :n[f]].copy().view(KEYPOINT_DTYPE).reshape(-1)
+        _compare_outputs((int(mono[f]), k, dn[f, :n[f]]), orc(base[f]), "frame %d of 512" % f)
+    d_frames = frames.cuda()
+    kd = torch.zeros((512, cap, 28), dtype=torch.uint8, device="cuda")
+    dd = torch.zeros((512, cap, 32), dtype=torch.uint8, device="cuda")
+    nd = torch.zeros(512, dtype=torch.int32, device="cuda")
+    md = torch.zeros(512, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ex.extract_batch_dev(d_frames, kd, dd, nd, md)
+    ex.sync()
+    assert np.array_equal(nd.cpu().numpy(), n)
+    for f in (0, 100, 511):
+        assert kd[f, :n[f]].cpu().numpy().tobytes() == kn[f, :n[f]].tobytes() and dd[f, :n[f]].cpu().numpy().tobytes() == dn[f, :n[f]].tobytes()

@@ -209,3 +209,50 @@ def test_matcher_error_conventions():
     # a vocabulary whose child lists do not cover every node exactly once is rejected
     assert L.vsg_vocabulary_create(m._h, 3, ptr(np.array([0, 1, 1, 1], np.int32)), ptr(np.array([1], np.int32)),
                                    ptr(np.zeros((3, 32), np.uint8)), 2, C.byref(C.c_void_p())) == _lib.VSG_ERR_INVALID
+
+
+def test_knn2_full_size_properties():
+    """BASELINE config 5 at its full size (100k x 1M descriptors, device-resident): size-independent properties —
+    sampled queries against a numpy brute force over the whole train set, planted exact and near duplicates found at
+    the right indices, the answer for a query equal to the answer for the same query placed elsewhere in the batch,
+    and the train set split into two shards + merge equal to the one-shot result."""
+    torch = pytest.importorskip("torch")
+    m = _matcher()
+    nq, nt = 100_000, 1_000_000
+    g = torch.Generator(device="cuda").manual_seed(11)
+    q = torch.randint(0, 256, (nq, 32), dtype=torch.uint8, device="cuda", generator=g)
+    t = torch.randint(0, 256, (nt, 32), dtype=torch.uint8, device="cuda", generator=g)
+    t[999_999] = t[123]                       # exact duplicates across the two halves: the lower index must come first
+    q[5] = t[123]
+    q[77_777] = t[654_321] ^ torch.tensor([1] + [0] * 31, dtype=torch.uint8, device="cuda")   # one bit away
+    q[99_999] = q[42]                         # the same query twice
+    idx = torch.zeros((nq, 2), dtype=torch.int32, device="cuda")
+    dist = torch.zeros((nq, 2), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    m.knn2_dev(q, t, idx, dist)
+    m.sync()
+    idx_h, dist_h = idx.cpu().numpy(), dist.cpu().numpy()
+    assert tuple(idx_h[5]) == (123, 999_999) and tuple(dist_h[5]) == (0, 0)
+    assert idx_h[77_777, 0] == 654_321 and dist_h[77_777, 0] == 1
+    assert np.array_equal(idx_h[99_999], idx_h[42]) and np.array_equal(dist_h[99_999], dist_h[42])
+    assert (dist_h[:, 0] <= dist_h[:, 1]).all() and (idx_h >= 0).all() and (idx_h < nt).all()
+    t_h = t.cpu().numpy()
+    sample = np.array([0, 5, 42, 31_337, 77_777, 99_999])
+    qs = q[torch.from_numpy(sample).cuda()].cpu().numpy()
+    for s, qq in zip(sample, qs):
+        d = POP[np.bitwise_xor(t_h, qq[None, :])].sum(1)
+        order = np.argsort(d.astype(np.int64) * (1 << 32) + np.arange(nt), kind="stable")[:2]
+        assert np.array_equal(idx_h[s], order) and np.array_equal(dist_h[s], d[order]), s
+    # two shards + merge == one shot
+    half = nt // 2
+    parts_i = torch.zeros((2, nq, 2), dtype=torch.int32, device="cuda")
+    parts_d = torch.zeros((2, nq, 2), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    m.knn2_dev(q, t[:half].contiguous(), parts_i[0], parts_d[0], 0)
+    m.knn2_dev(q, t[half:].contiguous(), parts_i[1], parts_d[1], half)
+    mi = torch.zeros((nq, 2), dtype=torch.int32, device="cuda")
+    md = torch.zeros((nq, 2), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    m.knn2_merge_dev(parts_i, parts_d, mi, md)
+    m.sync()
+    assert torch.equal(mi, idx) and torch.equal(md, dist)
