@@ -307,27 +307,25 @@ __global__ void __launch_bounds__(kFastThreads, VSG_FAST_MINB) fast_blur_kernel(
 }
 
 // blur == nullptr: FAST alone; otherwise the fused FAST + blur grid.
-void launch_fast(const FrameGeom &g, const Cell *cells, const uint8_t *lvl0_base, int lvl0_pitch, int64_t lvl0_stride,
+vsg_status launch_fast(const FrameGeom &g, const Cell *cells, const uint8_t *lvl0_base, int lvl0_pitch, int64_t lvl0_stride,
                  const uint8_t *pyr, uint8_t *blur, Cand *cand, int *cand_count, int ini_th, int min_th, int max_cw,
                  int max_ch, int nframes, cudaStream_t s) {
     (void)cells;   // the kernel derives the cell geometry from the level tables
     if (g.ncells == 0) {
         if (blur) launch_blur(g, lvl0_base, lvl0_pitch, lvl0_stride, pyr, blur, nframes, s);
-        return;
+        return VSG_OK;
     }
     const int max_S = ((((max_cw - 6) + 1) >> 1) + 3) & ~3;
     if (3 + max_S + 6 + 3 > kT2Pitch || max_S + 2 > kS2Pitch || max_S * (max_ch - 6) > 32 * kFastThreads) {
         set_error("FAST cell larger than the shared-memory tile / the 32-iteration survivor masks");
-        return;
+        return VSG_ERR_INVALID;
     }
     const int tile_rows = max_ch;
     const int list_cap = ((max_cw - 6 + 1) / 2) * ((max_ch - 6 + 1) / 2) + 1;
     const size_t smem = (size_t)tile_rows * kT2Pitch * 4 + (size_t)(tile_rows - 4) * kS2Pitch * 4 + (size_t)list_cap * 4 + 16;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    if (smem > 48 * 1024) {   // per device and cheap: set on every launch rather than caching it in a (racy) static
         cudaFuncSetAttribute(fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(fast_blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
     }
     if (!blur) {
         launch_kernel(fast_kernel, dim3(g.ncells, nframes), dim3(kFastThreads), smem, s, true, g, lvl0_base, lvl0_pitch,
@@ -340,6 +338,7 @@ void launch_fast(const FrameGeom &g, const Cell *cells, const uint8_t *lvl0_base
                       lvl0_pitch, lvl0_stride, pyr, blur, cand, cand_count, ini_th, min_th, tile_rows, list_cap, nblur, ratio);
     }
     count_launch();
+    return VSG_OK;
 }
 
 }  // namespace vsg

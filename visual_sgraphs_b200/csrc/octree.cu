@@ -408,11 +408,7 @@ void launch_octree(const FrameGeom &g, const Cand *cand, const int *cand_count, 
     // list_a, list_b (12 B each), cc (16 B), child_pos (8 B), stay_pos, expanded, exp_list, push_off, exp_off (2 B
     // each), sort_buf (8 B)
     const size_t smem = (size_t)cap * (12 + 12 + 16 + 8 + 2 + 2 + 2 + 2 + 2 + 8) + 64;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(octree_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    if (smem > 48 * 1024) cudaFuncSetAttribute(octree_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     // (a 1024-thread variant for single frames was measured: the passes over the keys get faster, the block-wide scans
     // and barriers slower — 69.7 us vs 67.0 us for one 640x480 frame — so every batch size uses 8-warp CTAs)
     launch_kernel(octree_kernel<256>, dim3(g.nlevels, nframes), dim3(256), smem, s, true, g, cand, cand_count, node_of,

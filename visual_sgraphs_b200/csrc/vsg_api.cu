@@ -365,8 +365,10 @@ vsg_status run_pipeline(vsg_extractor *ex, cudaStream_t s, int f0, const uint8_t
     }
     STAGE_MARK(1);
     // FAST cells and the Gaussian blur share one grid (fast.cu) unless VSG_FUSE_FAST_BLUR=0
-    launch_fast(g, ex->cells_d, lvl0_base, lvl0_pitch, lvl0_stride, ex->pyr, ex->fuse_fast_blur ? ex->blur : nullptr, ex->cand,
-                cand_count, ex->p.ini_th_fast, ex->p.min_th_fast, ex->max_cw, ex->max_ch, nframes, s);
+    const vsg_status fst = launch_fast(g, ex->cells_d, lvl0_base, lvl0_pitch, lvl0_stride, ex->pyr,
+                                       ex->fuse_fast_blur ? ex->blur : nullptr, ex->cand, cand_count, ex->p.ini_th_fast,
+                                       ex->p.min_th_fast, ex->max_cw, ex->max_ch, nframes, s);
+    if (fst != VSG_OK) return fst;
     STAGE_MARK(2);
     launch_octree(g, ex->cand, cand_count, ex->node_of, level_kps, level_kp_count, ex->max_nodes, nframes, s);
     STAGE_MARK(3);

@@ -155,7 +155,7 @@ void launch_cvt_gray(const uint8_t *src, int src_pitch, int64_t src_stride, int 
 void launch_blur(const FrameGeom &g, const uint8_t *lvl0_base, int lvl0_pitch, int64_t lvl0_stride, const uint8_t *pyr,
                  uint8_t *blur, int nframes, cudaStream_t s);
 // blur != nullptr: the Gaussian blur of the same frames runs inside the same grid (fast_blur_kernel)
-void launch_fast(const FrameGeom &g, const Cell *cells, const uint8_t *lvl0_base, int lvl0_pitch, int64_t lvl0_stride,
+vsg_status launch_fast(const FrameGeom &g, const Cell *cells, const uint8_t *lvl0_base, int lvl0_pitch, int64_t lvl0_stride,
                  const uint8_t *pyr, uint8_t *blur, Cand *cand, int *cand_count, int ini_th, int min_th, int max_cw,
                  int max_ch, int nframes, cudaStream_t s);
 void launch_octree(const FrameGeom &g, const Cand *cand, const int *cand_count, unsigned short *node_of,
