@@ -48,22 +48,21 @@ __device__ __forceinline__ uint32_t fast_strength2(const uint32_t *c) {
     p[8] = c[-3 * P];      p[9] = c[-3 * P - 1];   p[10] = c[-2 * P - 2];  p[11] = c[-P - 3];
     p[12] = c[-3];         p[13] = c[P - 3];       p[14] = c[2 * P - 2];   p[15] = c[3 * P - 1];
     const uint32_t v = c[0];
-    uint32_t lo3[16], hi3[16];
+    // max over the 16 windows of the window minimum, four windows at a time: the windows starting at b..b+3 share
+    // the six pixels p[b+3..b+8]; what is left of them are the four 3-windows of (p[b], p[b+1], p[b+2], p[b+9],
+    // p[b+10], p[b+11]), and max(min(s0,s1,s2), min(s1,s2,s3)) = min(s1, s2, max(s0,s3)).  8 operations per group,
+    // 34 per polarity (the plain two-level sliding minimum needs 40).
+    uint32_t glo[4], ghi[4];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        lo3[i] = min3(p[i], p[(i + 1) & 15], p[(i + 2) & 15]);
-        hi3[i] = max3(p[i], p[(i + 1) & 15], p[(i + 2) & 15]);
+    for (int g = 0; g < 4; ++g) {
+        const int b = 4 * g;
+        const uint32_t s0 = p[b], s1 = p[b + 1], s2 = p[b + 2], s3 = p[(b + 9) & 15], s4 = p[(b + 10) & 15], s5 = p[(b + 11) & 15];
+        const uint32_t q0 = p[b + 3], q1 = p[(b + 4) & 15], q2 = p[(b + 5) & 15], q3 = p[(b + 6) & 15], q4 = p[(b + 7) & 15], q5 = p[(b + 8) & 15];
+        glo[g] = min3(max2(min3(max2(s0, s3), s1, s2), min3(max2(s2, s5), s3, s4)), min3(q0, q1, q2), min3(q3, q4, q5));
+        ghi[g] = max3(min2(max3(min2(s0, s3), s1, s2), max3(min2(s2, s5), s3, s4)), max3(q0, q1, q2), max3(q3, q4, q5));
     }
-    uint32_t lo9[16], hi9[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        lo9[i] = min3(lo3[i], lo3[(i + 3) & 15], lo3[(i + 6) & 15]);
-        hi9[i] = max3(hi3[i], hi3[(i + 3) & 15], hi3[(i + 6) & 15]);
-    }
-    uint32_t best_lo = max3(max3(lo9[0], lo9[1], lo9[2]), max3(lo9[3], lo9[4], lo9[5]), max3(lo9[6], lo9[7], lo9[8]));
-    best_lo = max3(best_lo, max3(lo9[9], lo9[10], lo9[11]), max3(lo9[12], lo9[13], max2(lo9[14], lo9[15])));
-    uint32_t best_hi = min3(min3(hi9[0], hi9[1], hi9[2]), min3(hi9[3], hi9[4], hi9[5]), min3(hi9[6], hi9[7], hi9[8]));
-    best_hi = min3(best_hi, min3(hi9[9], hi9[10], hi9[11]), min3(hi9[12], hi9[13], min2(hi9[14], hi9[15])));
+    const uint32_t best_lo = max3(glo[0], glo[1], max2(glo[2], glo[3]));
+    const uint32_t best_hi = min3(ghi[0], ghi[1], min2(ghi[2], ghi[3]));
     // per lane: max(best_lo - v, v - best_hi, 0); the max/min with v keeps both differences non-negative (no borrow)
     return max2(max2(best_lo, v) - v, v - min2(best_hi, v));
 }
@@ -193,23 +192,29 @@ __device__ __forceinline__ void fast_cell_body(const FrameGeom &g, const uint8_t
         const int tt = max(t, 1);       // a corner scoring 0 (K == 1, only possible at t == 0) never survives the NMS
         // Survivors are only flagged inside the loop (bit `iter` of m0 / m1 for the two pixels of the pair); the
         // compaction runs once per pass after it: one warp scan, one shared-memory atomic per warp.
-        uint32_t m0 = 0, m1 = 0;
+        // Per iteration the pair's two survivor flags are produced in packed form — K - min(K, max(nb, tt)) is
+        // non-zero in a lane iff that pixel beats the threshold and all 8 neighbours — and accumulated as bit `iter`
+        // of the two 16-bit lanes of acc[iter / 16] by a multiply-add (FMA pipe, not the ALU pipe the min/max use).
+        const uint32_t tt2 = (uint32_t)tt * 0x00010001u;
+        uint32_t acc[2] = {0, 0};
         PairIter it(tid, S);
-        int iter = 0;
-        for (int base = 0; base < npairs; base += kFastThreads, it.next(), ++iter) {
-            // lanes past the last pair read a harmless in-range location and are masked: no branch around the loads
-            const bool in = it.iy < ih;
-            const uint32_t *c = s2 + (in ? (it.iy + 1) * kS2Pitch + it.j + 1 : kS2Pitch + 1);
-            const uint32_t K = c[0];
-            // strict maximum over the 8 neighbours: neighbours that are not corners at t are below K anyway
-            const uint32_t nb = max3(max3(c[-kS2Pitch - 1], c[-kS2Pitch], c[-kS2Pitch + 1]),
-                                     max3(c[-1], c[1], c[kS2Pitch - 1]), max2(c[kS2Pitch], c[kS2Pitch + 1]));
-            const int k0 = K & 0xFFFF, k1 = K >> 16;
-            const bool f0 = in && k0 > tt && k0 > (int)(nb & 0xFFFF);
-            const bool f1 = in && k1 > tt && k1 > (int)(nb >> 16);
-            m0 |= (uint32_t)f0 << iter;
-            m1 |= (uint32_t)f1 << iter;
+        int base = 0;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t pw = 1;
+            for (int iter = 0; iter < 16 && base < npairs; ++iter, base += kFastThreads, it.next(), pw <<= 1) {
+                // lanes past the last pair read the (all-zero) top apron row and flag nothing: no branch around the loads
+                const uint32_t *c = s2 + (it.iy < ih ? (it.iy + 1) * kS2Pitch + it.j + 1 : 1);
+                const uint32_t K = c[0];
+                // strict maximum over the 8 neighbours: neighbours that are not corners at t are below K anyway
+                const uint32_t nb = max3(max3(c[-kS2Pitch - 1], c[-kS2Pitch], c[-kS2Pitch + 1]),
+                                         max3(c[-1], c[1], c[kS2Pitch - 1]), max2(c[kS2Pitch], c[kS2Pitch + 1]));
+                const uint32_t e = K - min2(K, max2(nb, tt2));
+                acc[half] += min2(e, 0x00010001u) * pw;
+            }
         }
+        uint32_t m0 = (acc[0] & 0xFFFFu) | (acc[1] << 16);
+        uint32_t m1 = (acc[0] >> 16) | (acc[1] & 0xFFFF0000u);
         const int cnt = __popc(m0) + __popc(m1);
         int incl = cnt;
 #pragma unroll
