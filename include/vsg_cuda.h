@@ -402,6 +402,22 @@ vsg_status vsg_stereo_match(vsg_matcher *m, vsg_extractor *left, vsg_extractor *
 vsg_status vsg_stereo_match_batch(vsg_matcher *m, vsg_extractor *ex, int npairs, float mb, float mbf,
                                   float *u_right_out, float *depth_out, int capacity);
 
+/* ---- per-keypoint steps of Frame's constructors right after the extractor ---- */
+
+/* Frame::UndistortKeyPoints (Frame.cc:891-922) and the corner call of Frame::ComputeImageBounds (:924-955):
+ * cv::undistortPoints(xy, xy, mK, mDistCoef, cv::Mat(), mK) on n (x, y) float pairs.  fx, fy, cx, cy are mK's entries and
+ * dist the dist_n (0, 4, 5, 8 or 12) entries of mDistCoef (k1 k2 p1 p2 [k3 [k4 k5 k6 [s1 s2 s3 s4]]]) widened to double
+ * as OpenCV does.  dist_n == 0 or dist[0] == 0 copies the input, the reference's own shortcut (:893-897).  Results are
+ * bit-identical to OpenCV's (double arithmetic, five iterations).  xy_out may alias xy_in. */
+vsg_status vsg_undistort_keypoints(vsg_matcher *m, int n, const float *xy_in, double fx, double fy, double cx, double cy,
+                                   const double *dist, int dist_n, float *xy_out);
+
+/* The same for the keypoints of the first nframes frames of the extractor's last vsg_extract_batch[_color] call, read where
+ * that call left them in device memory: xy_out is [nframes][capacity][2] floats (capacity >=
+ * vsg_extractor_max_keypoints); rows past a frame's keypoint count are (-1, -1). */
+vsg_status vsg_undistort_keypoints_batch(vsg_matcher *m, vsg_extractor *ex, int nframes, double fx, double fy, double cx,
+                                         double cy, const double *dist, int dist_n, float *xy_out, int capacity);
+
 #ifdef __cplusplus
 }
 #endif

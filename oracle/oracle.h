@@ -84,6 +84,13 @@ int orc_distribute_octree(const float *xyr, int n, int min_x, int max_x, int min
 /* cv::cvtColor(..., COLOR_{RGB,BGR,RGBA,BGRA}2GRAY) on 8-bit images (Tracking.cc:1595-1608) */
 void orc_cvt_gray(const uint8_t *src, int w, int h, int pitch, int channels, int r_first, uint8_t *dst, int dst_pitch);
 
+/* Frame::UndistortKeyPoints / ComputeImageBounds = cv::undistortPoints(pts, K, dist, R = I, P = K) (Frame.cc:891-955) */
+void orc_undistort_points(int n, const float *xy_in, double fx, double fy, double cx, double cy, const double *dist,
+                          int dist_n, float *xy_out);
+/* Frame::ComputeStereoFromRGBD (Frame.cc:1129-1150) */
+void orc_stereo_from_rgbd(int n, const float *xy, const float *xy_un, const float *depth, int depth_pitch_floats, float bf,
+                          float *u_right, float *depth_out);
+
 /* ---- matcher arithmetic (ORBmatcher.cc) on flattened views ---- */
 int orc_descriptor_distance(const uint8_t *a, const uint8_t *b);
 

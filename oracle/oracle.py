@@ -71,6 +71,10 @@ def lib():
         L.orc_orb_descriptor.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_float, vp]
         L.orc_distribute_octree.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int]
         L.orc_cvt_gray.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int]
+        L.orc_undistort_points.argtypes = [C.c_int, vp, C.c_double, C.c_double, C.c_double, C.c_double, vp, C.c_int, vp]
+        L.orc_undistort_points.restype = None
+        L.orc_stereo_from_rgbd.argtypes = [C.c_int, vp, vp, vp, C.c_int, C.c_float, vp, vp]
+        L.orc_stereo_from_rgbd.restype = None
         L.orc_descriptor_distance.argtypes = [vp, vp]
         L.orc_get_features_in_area.argtypes = [vp, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, vp, C.c_int]
         L.orc_three_maxima.argtypes = [vp, C.c_int, i32p, i32p, i32p]
@@ -239,6 +243,26 @@ def cvt_gray(img, rgb=True):
     out = np.zeros((h, w), np.uint8)
     lib().orc_cvt_gray(_ptr(img), w, h, img.strides[0], ch, int(bool(rgb)), _ptr(out), w)
     return out
+
+
+def undistort_points(xy, fx, fy, cx, cy, dist):
+    """Frame::UndistortKeyPoints: cv::undistortPoints(xy, K, dist, R=I, P=K) on (n, 2) float32 points."""
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    dist = np.ascontiguousarray(dist, np.float64).ravel()
+    out = np.zeros_like(xy)
+    lib().orc_undistort_points(xy.shape[0], _ptr(xy), fx, fy, cx, cy, _ptr(dist), dist.size, _ptr(out))
+    return out
+
+
+def stereo_from_rgbd(xy, xy_un, depth, bf):
+    """Frame::ComputeStereoFromRGBD: (u_right, depth) per keypoint from a float32 depth image."""
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    xy_un = np.ascontiguousarray(xy_un, np.float32).reshape(-1, 2)
+    depth = np.ascontiguousarray(depth, np.float32)
+    ur = np.zeros(xy.shape[0], np.float32)
+    dz = np.zeros(xy.shape[0], np.float32)
+    lib().orc_stereo_from_rgbd(xy.shape[0], _ptr(xy), _ptr(xy_un), _ptr(depth), depth.shape[1], bf, _ptr(ur), _ptr(dz))
+    return ur, dz
 
 
 def descriptor_distance(a, b):

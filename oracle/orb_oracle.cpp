@@ -806,6 +806,61 @@ void orc_cvt_gray(const uint8_t *src, int w, int h, int pitch, int channels, int
     }
 }
 
+// Frame::UndistortKeyPoints (Frame.cc:891-922) = cv::undistortPoints(mat, mat, mK, mDistCoef, cv::Mat(), mK) on the N x 2
+// float keypoint coordinates; also what Frame::ComputeImageBounds (:924-955) runs on the four image corners.
+// OpenCV (un-vendored; calib3d cvUndistortPointsInternal, restated from its published algorithm and pinned against
+// cv2 4.13 in tests/test_oracle_cv2.py): all arithmetic in double, normalise with 1/fx and 1/fy, five fixed-point
+// iterations of the Brown-Conrady model (the C++ wrapper's default TermCriteria(MAX_ITER, 5, 0.01)), k[0..13] =
+// (k1 k2 p1 p2 k3 k4 k5 k6 s1 s2 s3 s4 tx ty) zero-padded (the tilt terms must be zero here), a negative icdist
+// falls back to the normalised input, re-projection with P = K, results stored as float.  dist_n == 0 or k1 == 0
+// follows the reference's shortcut (:893-897): the coordinates are copied.
+void orc_undistort_points(int n, const float *xy_in, double fx, double fy, double cx, double cy, const double *dist,
+                          int dist_n, float *xy_out) {
+    if (dist_n <= 0 || dist[0] == 0.0) {
+        for (int i = 0; i < 2 * n; ++i) xy_out[i] = xy_in[i];
+        return;
+    }
+    double k[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < dist_n && i < 12; ++i) k[i] = dist[i];
+    const double ifx = 1. / fx, ify = 1. / fy;
+    for (int i = 0; i < n; ++i) {
+        const double u = xy_in[2 * i], v = xy_in[2 * i + 1];
+        double x = (u - cx) * ifx, y = (v - cy) * ify;
+        const double x0 = x, y0 = y;
+        for (int j = 0; j < 5; ++j) {
+            const double r2 = x * x + y * y;
+            const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+            if (icdist < 0) {
+                x = (u - cx) * ifx;
+                y = (v - cy) * ify;
+                break;
+            }
+            const double dx = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+            const double dy = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+            x = (x0 - dx) * icdist;
+            y = (y0 - dy) * icdist;
+        }
+        const double xx = fx * x + 0. * y + cx, yy = 0. * x + fy * y + cy, ww = 1. / (0. * x + 0. * y + 1.);
+        xy_out[2 * i] = (float)(xx * ww);
+        xy_out[2 * i + 1] = (float)(yy * ww);
+    }
+}
+
+// Frame::ComputeStereoFromRGBD (Frame.cc:1129-1150): depth at the (truncated) distorted keypoint position; where it is
+// positive, mvDepth = d and mvuRight = undistorted x - bf / d; -1 elsewhere.
+void orc_stereo_from_rgbd(int n, const float *xy, const float *xy_un, const float *depth, int depth_pitch_floats, float bf,
+                          float *u_right, float *depth_out) {
+    for (int i = 0; i < n; ++i) {
+        u_right[i] = -1.f;
+        depth_out[i] = -1.f;
+        const float d = depth[(size_t)(int)xy[2 * i + 1] * depth_pitch_floats + (int)xy[2 * i]];
+        if (d > 0) {
+            depth_out[i] = d;
+            u_right[i] = xy_un[2 * i] - bf / d;
+        }
+    }
+}
+
 double orc_bench_extract(const uint8_t *frames, int nframes, int w, int h, int nfeatures, float scale_factor,
                          int nlevels, int ini_th, int min_th, int threads, int64_t *total_keypoints) {
     if (threads < 1) threads = 1;

@@ -79,6 +79,7 @@ using Sim3f = Sim3<float>;
 #define SOPHUS_SIM3_HPP
 
 #include "../../oracle/oracle.h"
+#include "../../visual_sgraphs_b200/shim/FrameOps.h"
 #include "../../visual_sgraphs_b200/shim/ORBextractor.h"
 #include "../../visual_sgraphs_b200/shim/ORBmatcher.h"
 
@@ -721,6 +722,48 @@ int main(int argc, char **argv) {
             for (int i = 0; i < K1.N; ++i)
                 if (m12[i] >= 0) { EXPECT(k < pairs.size() && pairs[k].first == (size_t)i && pairs[k].second == (size_t)m12[i], "pair %zu", k); ++k; }
         }
+    }
+
+    // ---------------- FrameOps: UndistortKeyPoints, ComputeImageBounds, ComputeStereoFromRGBD (Frame.cc:891-955, 1129-1150) ----
+    {
+        float Kdata[9] = {517.306408f, 0.f, 318.643040f, 0.f, 516.469215f, 255.313989f, 0.f, 0.f, 1.f};   // TUM1.yaml
+        float Ddata[5] = {0.262383f, -0.953104f, -0.005358f, 0.002628f, 1.163314f};
+        cv::Mat mK(3, 3, CV_8UC1, Kdata, 3 * sizeof(float)), mDist(5, 1, CV_8UC1, Ddata, sizeof(float));
+        cv::Mat m(480, 640, CV_8UC1, img_a.data(), 640);
+        std::vector<cv::KeyPoint> keys, keysUn;
+        cv::Mat desc;
+        std::vector<int> lap = {0, 0};
+        ex(m, cv::noArray(), keys, desc, lap);
+        VS_GRAPHS::frame_ops::UndistortKeyPoints(keys, mK, mDist, keysUn);
+        const int n = (int)keys.size();
+        std::vector<float> xy(2 * (size_t)n), want(2 * (size_t)n);
+        for (int i = 0; i < n; ++i) { xy[2 * i] = keys[i].pt.x; xy[2 * i + 1] = keys[i].pt.y; }
+        const double dist[5] = {Ddata[0], Ddata[1], Ddata[2], Ddata[3], Ddata[4]};
+        orc_undistort_points(n, xy.data(), Kdata[0], Kdata[4], Kdata[2], Kdata[5], dist, 5, want.data());
+        int bad = 0, moved = 0;
+        for (int i = 0; i < n; ++i) {
+            bad += keysUn[i].pt.x != want[2 * i] || keysUn[i].pt.y != want[2 * i + 1] || keysUn[i].octave != keys[i].octave ||
+                   keysUn[i].angle != keys[i].angle;
+            moved += keysUn[i].pt.x != keys[i].pt.x;
+        }
+        EXPECT((int)keysUn.size() == n && bad == 0 && moved > n / 2, "UndistortKeyPoints: %d of %d differ (%d moved)", bad, n, moved);
+        float c[8] = {0.f, 0.f, 640.f, 0.f, 0.f, 480.f, 640.f, 480.f}, wc[8];
+        orc_undistort_points(4, c, Kdata[0], Kdata[4], Kdata[2], Kdata[5], dist, 5, wc);
+        float minx, maxx, miny, maxy;
+        VS_GRAPHS::frame_ops::ComputeImageBounds(640, 480, mK, mDist, minx, maxx, miny, maxy);
+        EXPECT(minx == std::min(wc[0], wc[4]) && maxx == std::max(wc[2], wc[6]) && miny == std::min(wc[1], wc[3]) &&
+                   maxy == std::max(wc[5], wc[7]), "ComputeImageBounds %f %f %f %f", minx, maxx, miny, maxy);
+        float Zdata[4] = {0.f, 0.f, 0.f, 0.f};
+        cv::Mat mZero(4, 1, CV_8UC1, Zdata, sizeof(float));
+        VS_GRAPHS::frame_ops::ComputeImageBounds(640, 480, mK, mZero, minx, maxx, miny, maxy);
+        EXPECT(minx == 0.f && maxx == 640.f && miny == 0.f && maxy == 480.f, "ComputeImageBounds without distortion");
+        std::vector<float> depth(640 * 480);
+        std::uniform_real_distribution<float> du(-0.5f, 6.f);
+        for (auto &d : depth) d = du(rng);
+        std::vector<float> ur, dz, wur(n), wdz(n);
+        VS_GRAPHS::frame_ops::ComputeStereoFromRGBD(keys, keysUn, depth.data(), 640, 40.f, ur, dz);
+        orc_stereo_from_rgbd(n, xy.data(), want.data(), depth.data(), 640, 40.f, wur.data(), wdz.data());
+        EXPECT(ur == wur && dz == wdz, "ComputeStereoFromRGBD");
     }
 
     orc_extractor_destroy(orc);

@@ -180,3 +180,45 @@ def test_cvt_gray_matches_cv2(oracle, channels, rgb):
     if channels == 4:
         ramp = np.concatenate([ramp, ramp[..., :1]], -1)
     assert np.array_equal(oracle.cvt_gray(ramp, rgb), cv2.cvtColor(np.ascontiguousarray(ramp), code))
+
+
+# Calibrations of the reference's own configs: TUM1 (config/RGB-D/TUM1.yaml:9-19), EuRoC (config/Stereo/EuRoC.yaml), and an
+# 8-coefficient rational model; values are float32 like the reference's mK / mDistCoef (Tracking.cc ParseCamParamFile).
+CALIBRATIONS = [
+    ((517.306408, 516.469215, 318.643040, 255.313989), (0.262383, -0.953104, -0.005358, 0.002628, 1.163314)),
+    ((458.654, 457.296, 367.215, 248.375), (-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05)),
+    ((600.0, 601.5, 320.25, 239.75), (0.1, -0.2, 0.001, 0.002, 0.05, 0.01, -0.02, 0.003)),
+    ((300.0, 300.0, 320.0, 240.0), (-2.5, 6.0, 0.0, 0.0, -5.0)),       # icdist < 0 far from the centre (regression_14583)
+]
+
+
+@pytest.mark.parametrize("calib", range(len(CALIBRATIONS)))
+def test_undistort_points_matches_cv2(oracle, calib):
+    """Frame::UndistortKeyPoints (Frame.cc:891-922): cv::undistortPoints(mat, mat, mK, mDistCoef, cv::Mat(), mK)."""
+    (fx, fy, cx, cy), dist = CALIBRATIONS[calib]
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float32).astype(np.float64)
+    dist = np.array(dist, np.float32).astype(np.float64)
+    rng = np.random.default_rng(40 + calib)
+    pts = np.stack([rng.uniform(-20, 780, 20000), rng.uniform(-20, 520, 20000)], 1).astype(np.float32)
+    pts[:4] = [[0, 0], [640, 0], [0, 480], [640, 480]]          # ComputeImageBounds' corners (:928-931)
+    ref = cv2.undistortPoints(pts.reshape(-1, 1, 2), K, dist, None, K).reshape(-1, 2)
+    got = oracle.undistort_points(pts, K[0, 0], K[1, 1], K[0, 2], K[1, 2], dist)
+    assert np.array_equal(ref, got)
+
+
+def test_undistort_points_shortcut_and_rgbd_association(oracle):
+    """k1 == 0 copies the keypoints (Frame.cc:893-897); ComputeStereoFromRGBD (:1129-1150) against a direct restatement."""
+    rng = np.random.default_rng(9)
+    pts = rng.uniform(0, 640, (100, 2)).astype(np.float32)
+    assert np.array_equal(oracle.undistort_points(pts, 500, 500, 320, 240, [0.0, 0.3, 0.0, 0.0]), pts)
+    assert np.array_equal(oracle.undistort_points(pts, 500, 500, 320, 240, []), pts)
+    xy = np.stack([rng.uniform(0, 639.9, 500), rng.uniform(0, 479.9, 500)], 1).astype(np.float32)
+    xy_un = (xy + rng.normal(0, 1, xy.shape)).astype(np.float32)
+    depth = rng.uniform(-0.5, 6.0, (480, 640)).astype(np.float32)
+    ur, dz = oracle.stereo_from_rgbd(xy, xy_un, depth, 40.0)
+    for i in range(len(xy)):
+        d = depth[int(xy[i, 1]), int(xy[i, 0])]
+        if d > 0:
+            assert dz[i] == d and ur[i] == np.float32(xy_un[i, 0] - np.float32(40.0) / d)
+        else:
+            assert dz[i] == -1 and ur[i] == -1

@@ -126,6 +126,9 @@ _SIGNATURES = {
                                         C.POINTER(C.c_void_p)]),
     "vsg_vocabulary_destroy": (None, [C.c_void_p]),
     "vsg_bow_transform": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "vsg_undistort_keypoints": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p] + [C.c_double] * 4 + [C.c_void_p, C.c_int, C.c_void_p]),
+    "vsg_undistort_keypoints_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int] + [C.c_double] * 4 +
+                                      [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "vsg_stereo_match_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int]),
     "vsg_stereo_match": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),

@@ -26,11 +26,6 @@ struct vsg_vocabulary {
 
 namespace vsg {
 
-#define CK(call)                                          \
-    do {                                                  \
-        if (!cuda_ok((call), #call)) return VSG_ERR_CUDA; \
-    } while (0)
-
 __global__ void __launch_bounds__(128) bow_transform_kernel(const int *__restrict__ child_ptr,
                                                             const int *__restrict__ child_idx,
                                                             const uint4 *__restrict__ node_desc,

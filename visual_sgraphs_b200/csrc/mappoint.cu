@@ -19,11 +19,6 @@
 
 namespace vsg {
 
-#define CK(call)                                          \
-    do {                                                  \
-        if (!cuda_ok((call), #call)) return VSG_ERR_CUDA; \
-    } while (0)
-
 constexpr int kDistinctThreads = 128;
 constexpr int kDistinctSmemRows = 1024;   // descriptors staged in shared memory (32 KB); longer lists are read from L2
 

@@ -16,11 +16,6 @@
 
 namespace vsg {
 
-#define CK(call)                                          \
-    do {                                                  \
-        if (!cuda_ok((call), #call)) return VSG_ERR_CUDA; \
-    } while (0)
-
 vsg_status matcher_ensure(vsg_matcher *m, int slot, size_t bytes) {
     if (m->cap[slot] >= bytes) return VSG_OK;
     if (m->buf[slot]) cudaFree(m->buf[slot]);

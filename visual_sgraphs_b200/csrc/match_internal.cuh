@@ -25,10 +25,6 @@ struct vsg_frame {
 namespace vsg {
 
 #ifndef CK
-#define CK(call)                                          \
-    do {                                                  \
-        if (!cuda_ok((call), #call)) return VSG_ERR_CUDA; \
-    } while (0)
 #endif
 
 constexpr int TH_HIGH = 100, TH_LOW = 50, HISTO_LENGTH = 30;   // ORBmatcher.cc:34-36

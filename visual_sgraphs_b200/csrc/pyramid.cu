@@ -19,7 +19,7 @@ namespace vsg {
 // (a0*s0 + a1*s1).  The rows of a strip are independent, so all their loads are in flight together
 // (the source row shared by two consecutive output rows is simply re-read from L1).
 // Vertical: ((b*(h>>4))>>16) is a 32x32 high multiply by b<<16.
-// grid (ceil(ncg/128), ceil(dh/kResizeRows), nframes), block 128.
+// grid (ceil(ncg * nstrips / 128), 1, nframes), block 128.
 // ------------------------------------------------------------------------------------------------
 #ifndef VSG_RESIZE_ROWS
 #define VSG_RESIZE_ROWS 4
@@ -40,9 +40,13 @@ __global__ void __launch_bounds__(kResizeThreads, VSG_RESIZE_MINB) resize_kernel
                                                                 const short4 *__restrict__ ytab) {
     pdl_launch_dependents();
     pdl_wait();
-    const int x4 = (blockIdx.x * kResizeThreads + threadIdx.x) * 4;
-    if (x4 >= dw) return;
-    const int y0 = blockIdx.y * kResizeRows, y1 = min(y0 + kResizeRows, dh);
+    // (row strip, column group) flattened over the grid's x dimension: no idle lanes at the right edge of narrow levels
+    const int ncg = (dw + 3) >> 2;
+    const int idx = blockIdx.x * kResizeThreads + threadIdx.x;
+    const int strip = idx / ncg;
+    const int x4 = (idx - strip * ncg) * 4;
+    const int y0 = strip * kResizeRows, y1 = min(y0 + kResizeRows, dh);
+    if (y0 >= dh) return;
     const uint8_t *s = src + (int64_t)blockIdx.z * src_stride;
     uint8_t *d = dst + (int64_t)blockIdx.z * dst_stride + x4;
 
@@ -122,7 +126,8 @@ void launch_resize_level(const FrameGeom &g, int level, const uint8_t *src_base,
     const uint8_t *src_end = src_base + (int64_t)(nframes - 1) * src_stride + (int64_t)(P.h - 1) * src_pitch + P.w;
     const LevelGeom &L = g.lv[level];
     const int ncg = (L.w + 3) / 4;
-    dim3 grid((ncg + kResizeThreads - 1) / kResizeThreads, (L.h + kResizeRows - 1) / kResizeRows, nframes);
+    const int nstrips = (L.h + kResizeRows - 1) / kResizeRows;
+    dim3 grid((ncg * nstrips + kResizeThreads - 1) / kResizeThreads, 1, nframes);
     launch_kernel(resize_kernel, grid, dim3(kResizeThreads), 0, s, true, src_base, src_pitch, src_stride, pyr + L.plane_offset,
                   L.pitch, L.plane_stride, L.w, L.h, P.w, src_end, L.xtab, L.ytab);
     count_launch();

@@ -22,11 +22,6 @@
 
 namespace vsg {
 
-#define CK(call)                                          \
-    do {                                                  \
-        if (!cuda_ok((call), #call)) return VSG_ERR_CUDA; \
-    } while (0)
-
 struct RightKp {          // what the row-band test needs of a right keypoint
     float x;
     int minr, maxr;       // floor(y - r), ceil(y + r)

@@ -193,11 +193,6 @@ void build_resize_tables(int sw, int sh, int dw, int dh, int dw_pad, std::vector
     }
 }
 
-#define CK(call)                                 \
-    do {                                         \
-        if (!cuda_ok((call), #call)) return VSG_ERR_CUDA; \
-    } while (0)
-
 vsg_status configure_shape(vsg_extractor *ex, int w, int h) {
     if (ex->cur_w == w && ex->cur_h == h) return VSG_OK;
     ex->free_shape();

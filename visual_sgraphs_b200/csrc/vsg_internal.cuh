@@ -144,6 +144,11 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
 
 void set_error(const char *fmt, ...);
 bool cuda_ok(cudaError_t e, const char *what);
+// In functions returning vsg_status: record the CUDA error text (vsg_last_error) and return VSG_ERR_CUDA.
+#define CK(call)                                          \
+    do {                                                  \
+        if (!cuda_ok((call), #call)) return VSG_ERR_CUDA; \
+    } while (0)
 void count_launch(int n = 1);
 
 // --- kernel launchers (each file documents the reference lines it implements) ---

@@ -305,6 +305,41 @@ class ORBmatcher:
                                        ptr(u_right), ptr(depth)))
         return u_right, depth
 
+    def UndistortKeyPoints(self, xy, K, dist):
+        """Frame::UndistortKeyPoints (Frame.cc:891-922): cv::undistortPoints(xy, mK, mDistCoef, cv::Mat(), mK) on an
+        (n, 2) float32 array; K is the 3x3 calibration matrix, dist the distortion coefficients (float32 values, as
+        the reference stores them)."""
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        K = np.asarray(K, np.float64)
+        dist = np.ascontiguousarray(np.asarray(dist, np.float64).ravel())
+        out = np.empty_like(xy)
+        check(self._L.vsg_undistort_keypoints(self._h, xy.shape[0], ptr(xy), float(K[0, 0]), float(K[1, 1]), float(K[0, 2]),
+                                              float(K[1, 2]), ptr(dist), dist.size, ptr(out)))
+        return out
+
+    def UndistortKeyPointsBatch(self, ex, nframes, K, dist):
+        """The same on the device-resident keypoints of the extractor's last extract_batch call: (nframes, cap, 2)."""
+        cap = self._L.vsg_extractor_max_keypoints(ex._h, *ex.level_size(0))
+        K = np.asarray(K, np.float64)
+        dist = np.ascontiguousarray(np.asarray(dist, np.float64).ravel())
+        out = np.empty((nframes, cap, 2), np.float32)
+        check(self._L.vsg_undistort_keypoints_batch(self._h, ex._h, int(nframes), float(K[0, 0]), float(K[1, 1]),
+                                                    float(K[0, 2]), float(K[1, 2]), ptr(dist), dist.size, ptr(out), cap))
+        return out
+
+    @staticmethod
+    def ComputeStereoFromRGBD(xy, xy_un, depth, bf):
+        """Frame::ComputeStereoFromRGBD (Frame.cc:1129-1150): a gather of one depth value per keypoint — host glue,
+        no device work.  Returns (mvuRight, mvDepth), -1 where the depth is not positive."""
+        xy = np.asarray(xy, np.float32).reshape(-1, 2)
+        xy_un = np.asarray(xy_un, np.float32).reshape(-1, 2)
+        depth = np.asarray(depth, np.float32)
+        d = depth[xy[:, 1].astype(np.int32), xy[:, 0].astype(np.int32)]
+        ok = d > 0
+        safe = np.where(ok, d, np.float32(1))
+        u_right = np.where(ok, xy_un[:, 0] - np.float32(bf) / safe, np.float32(-1)).astype(np.float32)
+        return u_right, np.where(ok, d, np.float32(-1)).astype(np.float32)
+
     def ComputeStereoMatchesBatch(self, ex, npairs, mb, mbf):
         """Frame::ComputeStereoMatches for pairs (2p, 2p+1) of the extractor's last extract_batch call, on its
         device-resident results. Returns (u_right, depth) float32 arrays of shape (npairs, cap)."""
