@@ -29,10 +29,14 @@ static long run_case(const std::vector<int> &counts, const std::vector<int> &ulx
         ref[i] = std::make_pair(counts[i], &nodes[i]);
         mine[i] = vsg::make_sort_item(counts[i], ulx[i], i);
     }
+    std::vector<vsg::SortItem> two(mine), ranked(n);
     std::sort(ref.begin(), ref.end(), entry_less);
     vsg::libstdcxx_sort(mine.data(), n);
+    // the device's two-phase form: sequential partition phase, then every element placed by its stable rank
+    vsg::introsort_loop(two.data(), n);
+    for (int j = 0; j < n; ++j) ranked[vsg::stable_rank(two.data(), n, j)] = two[j];
     for (int i = 0; i < n; ++i)
-        if (ref[i].second->id != vsg::sort_item_ref(mine[i])) return i + 1;
+        if (ref[i].second->id != vsg::sort_item_ref(mine[i]) || ref[i].second->id != vsg::sort_item_ref(ranked[i])) return i + 1;
     return 0;
 }
 

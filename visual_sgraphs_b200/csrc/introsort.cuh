@@ -9,7 +9,8 @@
 // need the very same permutation libstdc++ produces.  tests/test_introsort.py compiles this header
 // with g++ and checks it against std::sort on tie-heavy inputs.
 //
-// Usable from host and device code (one thread runs it; n is a few hundred at most).
+// Usable from host and device code.  On the device one thread runs the partition phase (introsort_loop) and the
+// whole CTA the final stable pass (stable_rank); n is a few hundred at most.
 #pragma once
 #if defined(__CUDACC__)
 #define VSG_HD __host__ __device__ __forceinline__
@@ -139,13 +140,14 @@ VSG_HD int partition_unguarded(SortItem *v, int first, int last, int pivot) {
     }
 }
 
-// std::sort(v, v + n, compareNodes)
-VSG_HD void libstdcxx_sort(SortItem *v, int n) {
+// __introsort_loop(v, v + n, 2 * lg(n)): median-of-3 quicksort partitions (heapsort below the depth limit) until every
+// unsorted run is at most 16 long.  The first half of std::sort; inherently sequential (data-dependent swaps).
+VSG_HD void introsort_loop(SortItem *v, int n) {
     if (n <= 0) return;
     int lg = 0;
     for (int t = n; t > 1; t >>= 1) ++lg;
-    // __introsort_loop with an explicit stack instead of the recursion on the right part (the two
-    // parts are disjoint, so the processing order does not change the outcome)
+    // explicit stack instead of the recursion on the right part (the two parts are disjoint, so the processing order
+    // does not change the outcome)
     int stack_first[40], stack_last[40], stack_depth[40];   // at most one push per level of the 2*lg(n) depth budget
     int sp = 0;
     stack_first[0] = 0; stack_last[0] = n; stack_depth[0] = 2 * lg; sp = 1;
@@ -167,13 +169,36 @@ VSG_HD void libstdcxx_sort(SortItem *v, int n) {
             last = cut;
         }
     }
-    // __final_insertion_sort
+}
+
+// __final_insertion_sort, the second half of std::sort.  Both of its loops only ever move an element in front of
+// strictly greater ones, i.e. it is a STABLE sort of whatever arrangement introsort_loop left — so any stable sort
+// produces the same permutation, e.g. the rank of every element computed independently (stable_rank below).
+VSG_HD void final_insertion_sort(SortItem *v, int n) {
     if (n > 16) {
         insertion_sort(v, 0, 16);
         for (int i = 16; i < n; ++i) linear_insert_unguarded(v, i);
     } else {
         insertion_sort(v, 0, n);
     }
+}
+
+// Position of v[j] after a stable sort of v[0..n): elements ordered before it plus equivalent ones in front of it.
+VSG_HD int stable_rank(const SortItem *v, int n, int j) {
+    const unsigned long long key = v[j].v >> 24;
+    int rank = 0;
+    for (int i = 0; i < n; ++i) {
+        const unsigned long long ki = v[i].v >> 24;
+        rank += (ki < key) || (ki == key && i < j);
+    }
+    return rank;
+}
+
+// std::sort(v, v + n, compareNodes), one thread
+VSG_HD void libstdcxx_sort(SortItem *v, int n) {
+    if (n <= 0) return;
+    introsort_loop(v, n);
+    final_insertion_sort(v, n);
 }
 
 }  // namespace vsg

@@ -15,7 +15,8 @@
 //     list give every child its position: children of the i-th divided node, in n1..n4 order, end up
 //     in front of everything pushed before them; single-key nodes keep their relative order behind.
 //   * The "careful" phase (:696-759) sorts the expandable nodes with the libstdc++ introsort
-//     emulation (introsort.cuh — tie order is part of the result; one thread, 64-bit packed items);
+//     emulation (introsort.cuh — tie order is part of the result; 64-bit packed items; the partition phase
+//     on one thread, the final insertion sort as a parallel stable rank sort);
 //     how many of them are divided before the quota is reached, and where their children land, is a
 //     block-wide prefix sum over the sorted order; the list is then rebuilt the same way.
 //   * Final pick per node = highest response, FIRST in the reference's candidate order on ties
@@ -255,7 +256,17 @@ __global__ void __launch_bounds__(kThreads) octree_kernel(FrameGeom g, const Can
             if (tid == 0) s_E = m;
             __syncthreads();
             OT_MARK(2);
-            if (tid == 0) libstdcxx_sort(sort_buf, m);
+            // std::sort in its two halves (introsort.cuh): the partition phase on one thread, then the final insertion
+            // sort — a stable sort of what the partitions left — as one rank computation per element by the whole CTA
+            // (child_pos is free until this round's rebuild and serves as the second buffer)
+            if (tid == 0) introsort_loop(sort_buf, m);
+            __syncthreads();
+            {
+                SortItem *ranked = reinterpret_cast<SortItem *>(child_pos);
+                for (int j = tid; j < m; j += kThreads) ranked[stable_rank(sort_buf, m, j)] = sort_buf[j];
+                __syncthreads();
+                for (int j = tid; j < m; j += kThreads) sort_buf[j] = ranked[j];
+            }
             __syncthreads();
             // processing order r = 0 .. m-1 is sort_buf[m-1-r] (:709 walks the sorted vector from the back).  Node r
             // contributes c_r non-empty children (e_r of them expandable); the list has size + sum_{i<=r}(c_i - 1)
