@@ -130,10 +130,11 @@ VSG_HD void median_to_first(SortItem *v, int result, int a, int b, int c) {
 
 // __unguarded_partition(first, last, pivot)
 VSG_HD int partition_unguarded(SortItem *v, int first, int last, int pivot) {
+    const SortItem pv = v[pivot];   // the pivot sits in front of [first, last) and is never swapped: read it once
     while (true) {
-        while (item_less(v[first], v[pivot])) ++first;
+        while (item_less(v[first], pv)) ++first;
         --last;
-        while (item_less(v[pivot], v[last])) --last;
+        while (item_less(pv, v[last])) --last;
         if (!(first < last)) return first;
         item_swap(v[first], v[last]);
         ++first;

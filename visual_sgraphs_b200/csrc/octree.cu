@@ -44,11 +44,15 @@ struct ONode {
     int count;             // vKeys.size(); bNoMore <=> count == 1
 };
 
-__device__ __forceinline__ int quadrant(const ONode &n, int kx, int ky) {
-    const int mx = n.x0 + ((n.x1 - n.x0 + 1) >> 1);  // UL.x + ceil((UR.x-UL.x)/2)
-    const int my = n.y0 + ((n.y1 - n.y0 + 1) >> 1);
-    // n1: left/top, n2: right/top, n3: left/bottom, n4: right/bottom   (:514-527)
-    return (kx < mx ? 0 : 1) + (ky < my ? 0 : 2);
+// Everything a key pass needs to know about a node in one shared-memory word: the split point (15 bits each) and, in
+// bit 31, whether the node is divided (in the histogram pass: whether it holds more than one key).
+constexpr uint32_t kDivided = 0x80000000u;
+__device__ __forceinline__ uint32_t split_word(const ONode &n) {
+    const int mx = n.x0 + ((n.x1 - n.x0 + 1) >> 1), my = n.y0 + ((n.y1 - n.y0 + 1) >> 1);
+    return (uint32_t)mx | ((uint32_t)my << 15) | (n.count > 1 ? kDivided : 0u);
+}
+__device__ __forceinline__ int quadrant(uint32_t split, int kx, int ky) {
+    return (kx < (int)(split & 0x7FFFu) ? 0 : 1) + (ky < (int)((split >> 15) & 0x7FFFu) ? 0 : 2);
 }
 
 __device__ __forceinline__ ONode child_of(const ONode &n, int q, int count) {
@@ -101,11 +105,11 @@ __global__ void __launch_bounds__(kThreads) octree_kernel(FrameGeom g, const Can
     int *cc = reinterpret_cast<int *>(list_b + cap);                       // [cap][4] child key counts
     unsigned short *child_pos = reinterpret_cast<unsigned short *>(cc + 4 * cap);  // [cap][4]
     unsigned short *stay_pos = child_pos + 4 * cap;                        // [cap]
-    short *expanded = reinterpret_cast<short *>(stay_pos + cap);           // [cap] 1 if divided this round
-    unsigned short *exp_list = reinterpret_cast<unsigned short *>(expanded + cap);  // [cap] expandable nodes, push order
+    unsigned short *exp_list = stay_pos + cap;                             // [cap] expandable nodes, push order
     unsigned short *push_off = exp_list + cap;                             // [cap] careful phase: children pushed before r
     unsigned short *exp_off = push_off + cap;                              // [cap] expandable children pushed before r
     SortItem *sort_buf = reinterpret_cast<SortItem *>(exp_off + cap);      // [cap] (cap is a multiple of 4: 8-byte aligned)
+    uint32_t *split = reinterpret_cast<uint32_t *>(sort_buf + cap);        // [cap] split_word of every node of the list
     __shared__ int s_size, s_nexp, s_state, s_E, s_T, s_X;
     __shared__ int s_scan[3][32];
 
@@ -185,6 +189,7 @@ __global__ void __launch_bounds__(kThreads) octree_kernel(FrameGeom g, const Can
         const int state = s_state;
         if (state == 2) break;
         for (int i = tid; i < size * 4; i += kThreads) cc[i] = 0;
+        for (int i = tid; i < size; i += kThreads) split[i] = split_word(cur[i]);
         __syncthreads();
         for (int k0 = tid; k0 < n; k0 += kInFlight * kThreads) {   // kInFlight keys per thread in flight (L2 latency)
             int nd[kInFlight];
@@ -198,9 +203,9 @@ __global__ void __launch_bounds__(kThreads) octree_kernel(FrameGeom g, const Can
 #pragma unroll
             for (int u = 0; u < kInFlight; ++u) {
                 if (nd[u] < 0) continue;
-                const ONode &node = cur[nd[u]];
-                if (node.count > 1)
-                    atomicAdd(&cc[nd[u] * 4 + quadrant(node, (int)(xy[u] & 0xFFFF) - kBorderMin, (int)(xy[u] >> 16) - kBorderMin)], 1);
+                const uint32_t w = split[nd[u]];
+                if (w & kDivided)
+                    atomicAdd(&cc[nd[u] * 4 + quadrant(w, (int)(xy[u] & 0xFFFF) - kBorderMin, (int)(xy[u] >> 16) - kBorderMin)], 1);
             }
         }
         __syncthreads();
@@ -225,9 +230,7 @@ __global__ void __launch_bounds__(kThreads) octree_kernel(FrameGeom g, const Can
                     const int pos = T + stay++;
                     nxt[pos] = cur[i];
                     stay_pos[i] = (unsigned short)pos;
-                    expanded[i] = 0;
-                } else {
-                    expanded[i] = 1;
+                } else {                                   // divided: split[i] already carries kDivided (count > 1)
                     for (int q = 0; q < 4; ++q) {
                         const int c = cc[i * 4 + q];
                         if (c == 0) continue;
@@ -252,7 +255,7 @@ __global__ void __launch_bounds__(kThreads) octree_kernel(FrameGeom g, const Can
                 const int pos = exp_list[j];
                 sort_buf[j] = make_sort_item(cur[pos].count, cur[pos].x0, pos);
             }
-            for (int i = tid; i < size; i += kThreads) expanded[i] = 0;
+            for (int i = tid; i < size; i += kThreads) split[i] &= ~kDivided;   // from here on: divided in THIS round
             if (tid == 0) s_E = m;
             __syncthreads();
             OT_MARK(2);
@@ -311,7 +314,7 @@ __global__ void __launch_bounds__(kThreads) octree_kernel(FrameGeom g, const Can
             const int T = s_T;
             for (int r = tid; r < E; r += kThreads) {
                 const int pos = sort_item_ref(sort_buf[m - 1 - r]);
-                expanded[pos] = 1;
+                split[pos] |= kDivided;
                 int push = push_off[r], nexp = exp_off[r];
                 for (int q = 0; q < 4; ++q) {
                     const int c = cc[pos * 4 + q];
@@ -324,12 +327,12 @@ __global__ void __launch_bounds__(kThreads) octree_kernel(FrameGeom g, const Can
             }
             __syncthreads();
             int stays = 0;
-            for (int i = lo; i < hi; ++i) stays += expanded[i] ? 0 : 1;
+            for (int i = lo; i < hi; ++i) stays += (split[i] & kDivided) ? 0 : 1;
             int d0 = 0, d1 = 0, S, D0, D1;
             block_scan3<kThreads>(stays, d0, d1, s_scan, S, D0, D1);
             int stay = stays;
             for (int i = lo; i < hi; ++i) {
-                if (expanded[i]) continue;
+                if (split[i] & kDivided) continue;
                 const int np = T + stay++;
                 nxt[np] = cur[i];
                 stay_pos[i] = (unsigned short)np;
@@ -356,12 +359,11 @@ __global__ void __launch_bounds__(kThreads) octree_kernel(FrameGeom g, const Can
             for (int u = 0; u < kInFlight; ++u) {
                 if (nd[u] < 0) continue;
                 const int k = k0 + u * kThreads;
-                if (expanded[nd[u]]) {
-                    const ONode &node = cur[nd[u]];
-                    nof[k] = child_pos[nd[u] * 4 + quadrant(node, (int)(xy[u] & 0xFFFF) - kBorderMin, (int)(xy[u] >> 16) - kBorderMin)];
-                } else {
+                const uint32_t w = split[nd[u]];
+                if (w & kDivided)
+                    nof[k] = child_pos[nd[u] * 4 + quadrant(w, (int)(xy[u] & 0xFFFF) - kBorderMin, (int)(xy[u] >> 16) - kBorderMin)];
+                else
                     nof[k] = stay_pos[nd[u]];
-                }
             }
         }
         { ONode *t = cur; cur = nxt; nxt = t; }
@@ -416,9 +418,9 @@ __global__ void __launch_bounds__(kThreads) octree_kernel(FrameGeom g, const Can
 void launch_octree(const FrameGeom &g, const Cand *cand, const int *cand_count, unsigned short *node_of,
                    LevelKp *level_kps, int *level_kp_count, int max_nodes, int nframes, cudaStream_t s) {
     const int cap = (max_nodes + 3) & ~3;
-    // list_a, list_b (12 B each), cc (16 B), child_pos (8 B), stay_pos, expanded, exp_list, push_off, exp_off (2 B
-    // each), sort_buf (8 B)
-    const size_t smem = (size_t)cap * (12 + 12 + 16 + 8 + 2 + 2 + 2 + 2 + 2 + 8) + 64;
+    // list_a, list_b (12 B each), cc (16 B), child_pos (8 B), stay_pos, exp_list, push_off, exp_off (2 B each),
+    // sort_buf (8 B), split (4 B)
+    const size_t smem = (size_t)cap * (12 + 12 + 16 + 8 + 2 + 2 + 2 + 2 + 8 + 4) + 64;
     if (smem > 48 * 1024) cudaFuncSetAttribute(octree_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     // (a 1024-thread variant for single frames was measured: the passes over the keys get faster, the block-wide scans
     // and barriers slower — 69.7 us vs 67.0 us for one 640x480 frame — so every batch size uses 8-warp CTAs)

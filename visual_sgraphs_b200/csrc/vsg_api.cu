@@ -195,6 +195,10 @@ void build_resize_tables(int sw, int sh, int dw, int dh, int dw_pad, std::vector
 
 vsg_status configure_shape(vsg_extractor *ex, int w, int h) {
     if (ex->cur_w == w && ex->cur_h == h) return VSG_OK;
+    if (w > kMaxImageDim || h > kMaxImageDim) {   // candidate / node coordinates and the resize tables are 16-bit (15 in the oct-tree)
+        set_error("image %dx%d too large: at most %d pixels per side", w, h, kMaxImageDim);
+        return VSG_ERR_INVALID;
+    }
     ex->free_shape();
     const int nl = ex->p.nlevels;
     FrameGeom &g = ex->g;

@@ -17,6 +17,7 @@ namespace vsg {
 constexpr int kMaxLevels = 16;
 constexpr int kEdge = 19;        // EDGE_THRESHOLD
 constexpr int kBorderMin = 16;   // minBorderX/Y = EDGE_THRESHOLD - 3
+constexpr int kMaxImageDim = 16384;   // packed 15/16-bit pixel coordinates (oct-tree midpoints, candidates, resize tables)
 constexpr int kHalfPatch = 15;   // HALF_PATCH_SIZE
 constexpr int kPatch = 31;       // PATCH_SIZE
 
