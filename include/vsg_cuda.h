@@ -402,6 +402,22 @@ vsg_status vsg_stereo_match(vsg_matcher *m, vsg_extractor *left, vsg_extractor *
 vsg_status vsg_stereo_match_batch(vsg_matcher *m, vsg_extractor *ex, int npairs, float mb, float mbf,
                                   float *u_right_out, float *depth_out, int capacity);
 
+/* Rectification ahead of the extractor: System::TrackStereo / TrackMonocular run cv::remap(im, imToFeed, M1, M2,
+ * cv::INTER_LINEAR) on every incoming image when the settings ask for it (System.cc:284-292; float maps from
+ * cv::initUndistortRectifyMap, Settings.cc:571-574 — BASELINE config 2's EuRoC.yaml does).
+ * vsg_extractor_set_rectify_map stores the CV_32FC1 map pair of camera `slot` (0 = left / only camera, 1 = right) in
+ * OpenCV's 1/32-pixel fixed-point form on the device; width x height is the size of the rectified image (newImSize).
+ * vsg_extract_batch_rectify is vsg_extract_batch on unrectified gray frames of src_width x src_height pixels: frame f is
+ * remapped with the map of camera f % ncameras (ncameras = 2: left / right images interleaved, as
+ * vsg_stereo_match_batch expects them) on the device, bit-exact with OpenCV's 8-bit remap (BORDER_CONSTANT, 0), and
+ * extracted at the maps' size. */
+vsg_status vsg_extractor_set_rectify_map(vsg_extractor *ex, int slot, const float *map_x, const float *map_y, int width,
+                                         int height);
+vsg_status vsg_extract_batch_rectify(vsg_extractor *ex, const uint8_t *images, int nframes, int src_width, int src_height,
+                                     int pitch, size_t frame_stride, int ncameras, int lap_x0, int lap_x1,
+                                     vsg_keypoint *keypoints_out, uint8_t *descriptors_out, int capacity, int *n_out,
+                                     int *mono_index_out);
+
 /* ---- per-keypoint steps of Frame's constructors right after the extractor ---- */
 
 /* Frame::UndistortKeyPoints (Frame.cc:891-922) and the corner call of Frame::ComputeImageBounds (:924-955):

@@ -84,6 +84,9 @@ int orc_distribute_octree(const float *xyr, int n, int min_x, int max_x, int min
 /* cv::cvtColor(..., COLOR_{RGB,BGR,RGBA,BGRA}2GRAY) on 8-bit images (Tracking.cc:1595-1608) */
 void orc_cvt_gray(const uint8_t *src, int w, int h, int pitch, int channels, int r_first, uint8_t *dst, int dst_pitch);
 
+/* cv::remap(src, dst, map_x, map_y, INTER_LINEAR) with CV_32FC1 maps, 8UC1 images, BORDER_CONSTANT 0 (System.cc:284-292) */
+void orc_remap_bilinear(const uint8_t *src, int sw, int sh, int spitch, const float *map_x, const float *map_y, int w, int h,
+                        uint8_t *dst, int dst_pitch);
 /* Frame::UndistortKeyPoints / ComputeImageBounds = cv::undistortPoints(pts, K, dist, R = I, P = K) (Frame.cc:891-955) */
 void orc_undistort_points(int n, const float *xy_in, double fx, double fy, double cx, double cy, const double *dist,
                           int dist_n, float *xy_out);

@@ -71,6 +71,8 @@ def lib():
         L.orc_orb_descriptor.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_float, vp]
         L.orc_distribute_octree.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int]
         L.orc_cvt_gray.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int]
+        L.orc_remap_bilinear.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, vp, C.c_int]
+        L.orc_remap_bilinear.restype = None
         L.orc_undistort_points.argtypes = [C.c_int, vp, C.c_double, C.c_double, C.c_double, C.c_double, vp, C.c_int, vp]
         L.orc_undistort_points.restype = None
         L.orc_stereo_from_rgbd.argtypes = [C.c_int, vp, vp, vp, C.c_int, C.c_float, vp, vp]
@@ -242,6 +244,17 @@ def cvt_gray(img, rgb=True):
     h, w, ch = img.shape
     out = np.zeros((h, w), np.uint8)
     lib().orc_cvt_gray(_ptr(img), w, h, img.strides[0], ch, int(bool(rgb)), _ptr(out), w)
+    return out
+
+
+def remap_bilinear(img, map_x, map_y):
+    """cv::remap(img, map_x, map_y, INTER_LINEAR) for an 8-bit gray image and float32 maps (System.cc:284-292)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    map_x = np.ascontiguousarray(map_x, np.float32)
+    map_y = np.ascontiguousarray(map_y, np.float32)
+    h, w = map_x.shape
+    out = np.zeros((h, w), np.uint8)
+    lib().orc_remap_bilinear(_ptr(img), img.shape[1], img.shape[0], img.strides[0], _ptr(map_x), _ptr(map_y), w, h, _ptr(out), w)
     return out
 
 

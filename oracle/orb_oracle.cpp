@@ -806,6 +806,29 @@ void orc_cvt_gray(const uint8_t *src, int w, int h, int pitch, int channels, int
     }
 }
 
+// cv::remap(src, dst, map1, map2, cv::INTER_LINEAR) with CV_32FC1 maps, 8-bit single-channel images and the default
+// BORDER_CONSTANT / 0 border, as System::TrackStereo / TrackMonocular run it on every incoming image when the settings
+// ask for rectification (System.cc:284-292, 352-…; maps from cv::initUndistortRectifyMap, Settings.cc:571-574).
+// OpenCV (un-vendored; imgproc remap, restated from its published algorithm and pinned against cv2 4.13 in
+// tests/test_oracle_cv2.py): the map is quantised to 1/32 pixel, sx = cvRound(mapx * 32), integer part sx >> 5
+// (saturated to short), fraction sx & 31; the four bilinear weights are the exact products (32-fy)(32-fx) * 32 ... of the
+// 15-bit table; dst = (sum of tap * weight + 2^14) >> 15; taps outside the source count as 0.
+void orc_remap_bilinear(const uint8_t *src, int sw, int sh, int spitch, const float *map_x, const float *map_y, int w, int h,
+                        uint8_t *dst, int dst_pitch) {
+    auto sat_short = [](int v) { return v < -32768 ? -32768 : (v > 32767 ? 32767 : v); };
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const int sx = cv_round(map_x[(size_t)y * w + x] * 32.f), sy = cv_round(map_y[(size_t)y * w + x] * 32.f);
+            const int ix = sat_short(sx >> 5), iy = sat_short(sy >> 5), fx = sx & 31, fy = sy & 31;
+            const int w00 = (32 - fy) * (32 - fx) * 32, w01 = (32 - fy) * fx * 32, w10 = fy * (32 - fx) * 32, w11 = fy * fx * 32;
+            auto tap = [&](int px, int py) -> int {
+                return (px >= 0 && px < sw && py >= 0 && py < sh) ? src[(size_t)py * spitch + px] : 0;
+            };
+            const int v = tap(ix, iy) * w00 + tap(ix + 1, iy) * w01 + tap(ix, iy + 1) * w10 + tap(ix + 1, iy + 1) * w11;
+            dst[(size_t)y * dst_pitch + x] = (uint8_t)((v + (1 << 14)) >> 15);
+        }
+}
+
 // Frame::UndistortKeyPoints (Frame.cc:891-922) = cv::undistortPoints(mat, mat, mK, mDistCoef, cv::Mat(), mK) on the N x 2
 // float keypoint coordinates; also what Frame::ComputeImageBounds (:924-955) runs on the four image corners.
 // OpenCV (un-vendored; calib3d cvUndistortPointsInternal, restated from its published algorithm and pinned against

@@ -80,3 +80,54 @@ def test_rgbd_frame_chain(oracle):
     assert len(res[-1][1]) == 0
     with pytest.raises(Exception):
         m.UndistortKeyPointsBatch(ex, len(frames) + 1, K, dist)
+
+
+def _rectify_maps(w, h, sw, sh, k1, shift):
+    """Smooth float32 maps of the kind cv::initUndistortRectifyMap produces (radial term + a small rotation / shift),
+    partly pointing outside the source so that the constant border is exercised."""
+    ys, xs = np.meshgrid(np.arange(h, dtype=np.float64), np.arange(w, dtype=np.float64), indexing="ij")
+    xn, yn = (xs - w / 2) / (0.6 * w), (ys - h / 2) / (0.6 * w)
+    r2 = xn * xn + yn * yn
+    f = 1 + k1 * r2
+    mx = (xn * f * np.cos(0.01) - yn * f * np.sin(0.01)) * 0.6 * w + sw / 2 + shift
+    my = (xn * f * np.sin(0.01) + yn * f * np.cos(0.01)) * 0.6 * w + sh / 2 - shift / 2
+    return mx.astype(np.float32), my.astype(np.float32)
+
+
+def test_rectified_stereo_chain(oracle):
+    """BASELINE config 2 with the rectification System::TrackStereo runs first (System.cc:284-292): unrectified left /
+    right frames interleaved in one batch, remapped on the device with each camera's map, extracted, stereo-matched —
+    against oracle remap + oracle extraction + oracle stereo matching."""
+    from visual_sgraphs_b200.extractor import ORBextractor
+    from visual_sgraphs_b200.matcher import ORBmatcher
+    from visual_sgraphs_b200.synth import synth_stereo_pair
+    sw, sh, w, h = 752, 480, 736, 464                     # the rectified size may differ from the sensor's (newImSize)
+    maps = [_rectify_maps(w, h, sw, sh, 0.12, 2.5), _rectify_maps(w, h, sw, sh, 0.10, -1.5)]
+    pairs = [synth_stereo_pair(70 + i, sw, sh) for i in range(2)]
+    stack = np.stack([im for pr in pairs for im in pr])
+    ex = ORBextractor(1200, max_batch=len(stack))
+    for slot, (mx, my) in enumerate(maps):
+        ex.set_rectify_map(slot, mx, my)
+    res = ex.extract_batch_rectify(stack, ncameras=2)
+    m = ORBmatcher()
+    ub, db = m.ComputeStereoMatchesBatch(ex, len(pairs), 0.11, 47.9)
+    for p, pr in enumerate(pairs):
+        rect = [oracle.remap_bilinear(im, *maps[c]) for c, im in enumerate(pr)]
+        assert (rect[0] == 0).any() and rect[0].std() > 10           # border pixels present, content preserved
+        oxl, oxr = oracle.OracleExtractor(1200), oracle.OracleExtractor(1200)
+        _, okl, odl = oxl(rect[0])
+        _, okr, odr = oxr(rect[1])
+        (_, kl, dl), (_, kr, dr) = res[2 * p], res[2 * p + 1]
+        assert kl.tobytes() == okl.tobytes() and np.array_equal(dl, odl)
+        assert kr.tobytes() == okr.tobytes() and np.array_equal(dr, odr)
+        wu, wd = oracle.stereo_matches(oxl, oxr, okl, odl, okr, odr, 0.11, 47.9)
+        assert np.array_equal(ub[p, :len(kl)], wu) and np.array_equal(db[p, :len(kl)], wd)
+    # one camera (monocular / RGB-D rectification), a chunk boundary inside the batch is covered by the extractor tests
+    ex1 = ORBextractor(1000, max_batch=3)
+    ex1.set_rectify_map(0, *maps[1])
+    frames = np.stack([pairs[0][0], pairs[1][1], pairs[0][1]])
+    for (_, k, d), im in zip(ex1.extract_batch_rectify(frames), frames):
+        _, ok, od = oracle.OracleExtractor(1000)(oracle.remap_bilinear(im, *maps[1]))
+        assert k.tobytes() == ok.tobytes() and np.array_equal(d, od)
+    with pytest.raises(Exception):
+        ex1.extract_batch_rectify(frames, ncameras=2)                 # no map for the second camera

@@ -222,3 +222,39 @@ def test_undistort_points_shortcut_and_rgbd_association(oracle):
             assert dz[i] == d and ur[i] == np.float32(xy_un[i, 0] - np.float32(40.0) / d)
         else:
             assert dz[i] == -1 and ur[i] == -1
+
+
+def _euroc_rectify_maps(right=False):
+    """cv::initUndistortRectifyMap maps like Settings.cc:571-574 builds them for config/Stereo/EuRoC.yaml (cam0 / cam1
+    intrinsics of that file; a small rectifying rotation and a common new projection)."""
+    if right:
+        K = np.array([[457.587, 0, 379.999], [0, 456.134, 255.238], [0, 0, 1]])
+        D = np.array([-0.28368365, 0.07451284, -0.00010473, -3.55590700e-05])
+        rvec = np.array([-0.004, 0.012, -0.002])
+    else:
+        K = np.array([[458.654, 0, 367.215], [0, 457.296, 248.375], [0, 0, 1]])
+        D = np.array([-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05])
+        rvec = np.array([0.003, -0.011, 0.0015])
+    R = cv2.Rodrigues(rvec)[0]
+    P = np.array([[435.2046959714599, 0, 367.4517211914062], [0, 435.2046959714599, 252.2008514404297], [0, 0, 1]])
+    return cv2.initUndistortRectifyMap(K, D, R, P, (752, 480), cv2.CV_32F)
+
+
+def test_remap_bilinear_matches_cv2(oracle):
+    """cv::remap(im, imToFeed, M1, M2, INTER_LINEAR) of System::TrackStereo (System.cc:284-292) on 8-bit frames."""
+    from visual_sgraphs_b200.synth import synth_frame
+    img = synth_frame(5, 752, 480)
+    for right in (False, True):
+        mx, my = _euroc_rectify_maps(right)
+        assert np.array_equal(oracle.remap_bilinear(img, mx, my), cv2.remap(img, mx, my, cv2.INTER_LINEAR))
+    rng = np.random.default_rng(3)
+    mx = rng.uniform(-5, 760, (300, 400)).astype(np.float32)          # taps outside the source on every side
+    my = rng.uniform(-5, 490, (300, 400)).astype(np.float32)
+    assert np.array_equal(oracle.remap_bilinear(img, mx, my), cv2.remap(img, mx, my, cv2.INTER_LINEAR))
+    mx = (np.arange(641)[None, :] * 1.171875 + 1 / 64).astype(np.float32).repeat(361, 0)    # exact ties of the 1/32 quantiser
+    my = (np.arange(361)[:, None] * 1.3 + 0.015625).astype(np.float32).repeat(641, 1)
+    assert np.array_equal(oracle.remap_bilinear(img, mx, my), cv2.remap(img, mx, my, cv2.INTER_LINEAR))
+    noise = rng.integers(0, 256, (97, 131), dtype=np.uint8)
+    mx = rng.uniform(-40000, 40000, (50, 60)).astype(np.float32)      # saturation of the integer part
+    my = rng.uniform(-3, 100, (50, 60)).astype(np.float32)
+    assert np.array_equal(oracle.remap_bilinear(noise, mx, my), cv2.remap(noise, mx, my, cv2.INTER_LINEAR))

@@ -126,6 +126,9 @@ _SIGNATURES = {
                                         C.POINTER(C.c_void_p)]),
     "vsg_vocabulary_destroy": (None, [C.c_void_p]),
     "vsg_bow_transform": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "vsg_extractor_set_rectify_map": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "vsg_extract_batch_rectify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int,
+                                            C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "vsg_undistort_keypoints": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p] + [C.c_double] * 4 + [C.c_void_p, C.c_int, C.c_void_p]),
     "vsg_undistort_keypoints_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int] + [C.c_double] * 4 +
                                       [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),

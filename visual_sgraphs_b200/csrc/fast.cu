@@ -33,8 +33,14 @@ __device__ __forceinline__ uint32_t max3(uint32_t a, uint32_t b, uint32_t c) { r
 
 constexpr int kFastThreads = 128;
 constexpr int kLoadIters = 3;      // 3 x 16 rows of 8 quads cover the usual 44-row cell without a loop
-constexpr int kT2Pitch = 48;      // words per pair-row: 3 (alignment) + lane offset S (<= 36, multiple of 4) + 6 halo columns, rounded to 4
-constexpr int kS2Pitch = 40;      // words per strength row: S + 2
+// Row pitches of the two shared-memory planes, in words.  A warp's 32 consecutive pairs p = iy * S + j sit at word
+// iy * pitch + j + const = p + iy * (pitch - S) + const: with pitch = S + 32 every ring / neighbour read of a warp is
+// bank-conflict free.  S = 20 for every full cell of the usual 35..40-pixel grids, so the pitch is the constant 52 (a
+// run-time pitch costs more address arithmetic than the conflicts); other S only see the usual
+// two-way conflicts.  Minimum sizes: 3 (alignment) + S + 6 halo columns rounded to 4 for the pixel pairs, S + 2 for
+// the strengths.
+constexpr int kT2Pitch = 52;
+constexpr int kS2Pitch = 52;
 
 // The 16-pixel Bresenham ring in OpenCV's order: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)
 // (-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3).  Strength K of both pixels of the pair at c: max over the 16

@@ -171,6 +171,50 @@ __global__ void __launch_bounds__(128) cvt_gray_kernel(const uint8_t *__restrict
     else for (int i = 0; x4 + i < w; ++i) d[i] = (uint8_t)(out >> (8 * i));
 }
 
+// ------------------------------------------------------------------------------------------------
+// rectification ingest: cv::remap(src, dst, M1, M2, INTER_LINEAR) as System::TrackStereo / TrackMonocular run it on
+// every incoming image when the settings ask for it (orb_slam3/src/System.cc:284-292; float maps from
+// cv::initUndistortRectifyMap, Settings.cc:571-574).  OpenCV's 8-bit path: map quantised to 1/32 pixel (done once on
+// the host when the map is set: integer part as two shorts, fraction as fy * 32 + fx), weights (32-fy)(32-fx)*32 ...
+// summing to 2^15, dst = (sum + 2^14) >> 15, taps outside the source are 0 (BORDER_CONSTANT).  One thread = 4 output
+// pixels, one 32-bit store into the level-0 plane; the map of a camera is shared by every frame of the batch (L2).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) remap_kernel(const uint8_t *__restrict__ src, int src_pitch, int64_t src_stride, int sw,
+                                                    int sh, RectifyMaps maps, int first_frame, uint8_t *__restrict__ dst,
+                                                    int dst_pitch, int64_t dst_stride, int w, int h) {
+    const int x4 = (blockIdx.x * 128 + threadIdx.x) * 4, y = blockIdx.y;
+    if (x4 >= w) return;
+    const int slot = (first_frame + (int)blockIdx.z) % maps.nslots;
+    const uint32_t *mxy = maps.xy[slot] + (size_t)y * w + x4;
+    const uint16_t *mf = maps.frac[slot] + (size_t)y * w + x4;
+    const uint8_t *s = src + (int64_t)blockIdx.z * src_stride;
+    uint32_t out = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (x4 + i >= w) break;
+        const uint32_t xy = __ldg(mxy + i);
+        const int f = __ldg(mf + i);
+        const int ix = (short)(xy & 0xFFFF), iy = (short)(xy >> 16), fx = f & 31, fy = f >> 5;
+        const uint8_t *p = s + (int64_t)iy * src_pitch + ix;
+        const bool x0 = (unsigned)ix < (unsigned)sw, x1 = (unsigned)(ix + 1) < (unsigned)sw;
+        const bool y0 = (unsigned)iy < (unsigned)sh, y1 = (unsigned)(iy + 1) < (unsigned)sh;
+        const int t00 = (x0 && y0) ? __ldg(p) : 0, t01 = (x1 && y0) ? __ldg(p + 1) : 0;
+        const int t10 = (x0 && y1) ? __ldg(p + src_pitch) : 0, t11 = (x1 && y1) ? __ldg(p + src_pitch + 1) : 0;
+        const int v = t00 * ((32 - fy) * (32 - fx) * 32) + t01 * ((32 - fy) * fx * 32) + t10 * (fy * (32 - fx) * 32) + t11 * (fy * fx * 32);
+        out |= (uint32_t)((v + (1 << 14)) >> 15) << (8 * i);
+    }
+    uint8_t *d = dst + (int64_t)blockIdx.z * dst_stride + (int64_t)y * dst_pitch + x4;
+    if (x4 + 4 <= w) *reinterpret_cast<uint32_t *>(d) = out;   // level-0 planes have a pitch that is a multiple of 64
+    else for (int i = 0; x4 + i < w; ++i) d[i] = (uint8_t)(out >> (8 * i));
+}
+
+void launch_remap(const uint8_t *src, int src_pitch, int64_t src_stride, int sw, int sh, const RectifyMaps &maps, int first_frame,
+                  uint8_t *dst, int dst_pitch, int64_t dst_stride, int w, int h, int nframes, cudaStream_t s) {
+    dim3 grid(((w + 3) / 4 + 127) / 128, h, nframes);
+    remap_kernel<<<grid, 128, 0, s>>>(src, src_pitch, src_stride, sw, sh, maps, first_frame, dst, dst_pitch, dst_stride, w, h);
+    count_launch();
+}
+
 void launch_cvt_gray(const uint8_t *src, int src_pitch, int64_t src_stride, int channels, int r_first, uint8_t *dst,
                      int dst_pitch, int64_t dst_stride, int w, int h, int nframes, cudaStream_t s) {
     dim3 grid(((w + 3) / 4 + 127) / 128, h, nframes);

@@ -63,6 +63,11 @@ struct vsg_extractor {
     bool fuse_fast_blur = true;
     uint8_t *color_d = nullptr;        // device staging of colour frames (vsg_extract_batch_color), allocated on first use
     size_t color_bytes = 0;
+    // rectification maps (vsg_extractor_set_rectify_map): quantised on the host, resident on the device; independent of the
+    // configured shape (the map size IS the shape the rectified frames are extracted at)
+    uint32_t *rect_xy[2] = {nullptr, nullptr};
+    uint16_t *rect_frac[2] = {nullptr, nullptr};
+    int rect_w = 0, rect_h = 0;
     cudaEvent_t fork_ev = nullptr, join_ev[kAuxStreams] = {nullptr, nullptr};
     // Completion of a chunked host-pointer batch can be awaited on blocking-sync events: the calling thread sleeps instead of
     // spinning in cudaStreamSynchronize, which matters when several handles / ranks share the host's cores
@@ -465,6 +470,7 @@ void vsg_extractor_destroy(vsg_extractor *ex) {
         for (int i = 0; i < vsg_extractor::kEvRing; ++i)
             for (int k = 0; k <= VSG_NUM_STAGES; ++k) cudaEventDestroy(ex->ev[i][k]);
     ex->free_shape();
+    for (int k = 0; k < 2; ++k) { cudaFree(ex->rect_xy[k]); cudaFree(ex->rect_frac[k]); }
     delete ex;
 }
 
@@ -490,22 +496,27 @@ int vsg_extractor_max_keypoints(vsg_extractor *ex, int width, int height) {
 
 // channels == 1: 8-bit gray frames; 3 / 4: interleaved colour frames converted on the device (r_first: the first channel
 // is red, i.e. COLOR_RGB2GRAY / COLOR_RGBA2GRAY, else the BGR variants)
-static vsg_status extract_batch_host(vsg_extractor *ex, const uint8_t *images, int nframes, int width, int height, int pitch,
-                                     size_t frame_stride, int channels, int r_first, int lap_x0, int lap_x1,
+// How the frames of a host-pointer batch reach the level-0 planes: copied as they are (gray), through cvtColor (3 / 4
+// channels) or through cv::remap with the handle's rectification maps (rect_slots = 1 or 2 cameras; gray input of
+// src_w x src_h pixels, the extraction runs at the maps' size).
+static vsg_status extract_batch_host(vsg_extractor *ex, const uint8_t *images, int nframes, int src_w, int src_h, int pitch,
+                                     size_t frame_stride, int channels, int r_first, int rect_slots, int lap_x0, int lap_x1,
                                      vsg_keypoint *keypoints_out, uint8_t *descriptors_out, int capacity, int *n_out,
                                      int *mono_index_out) {
     if (!ex) return VSG_ERR_INVALID;
-    if (!images || width <= 0 || height <= 0 || nframes <= 0) return VSG_EMPTY_IMAGE;   // :1087-1088
-    if (nframes > ex->max_batch || pitch < width * channels || capacity < 0 || (channels != 1 && channels != 3 && channels != 4)) {
+    if (!images || src_w <= 0 || src_h <= 0 || nframes <= 0) return VSG_EMPTY_IMAGE;   // :1087-1088
+    if (nframes > ex->max_batch || pitch < src_w * channels || capacity < 0 || (channels != 1 && channels != 3 && channels != 4)) {
         set_error("vsg_extract_batch: nframes %d > max_batch %d, or bad pitch/capacity/channels", nframes, ex->max_batch);
         return VSG_ERR_INVALID;
     }
+    const bool staged = channels != 1 || rect_slots > 0;               // frames land in the staging buffer first
+    const int width = rect_slots > 0 ? ex->rect_w : src_w, height = rect_slots > 0 ? ex->rect_h : src_h;
     CK(cudaSetDevice(ex->device));
     vsg_status st = configure_shape(ex, width, height);
     if (st != VSG_OK) return st;
-    const int cpitch = (width * channels + 63) & ~63;                   // staging pitch of a colour row
-    const size_t cstride = (size_t)cpitch * height;
-    if (channels != 1 && ex->color_bytes < cstride * ex->max_batch) {
+    const int cpitch = (src_w * channels + 63) & ~63;                   // staging pitch of a colour / unrectified row
+    const size_t cstride = (size_t)cpitch * src_h;
+    if (staged && ex->color_bytes < cstride * ex->max_batch) {
         cudaFree(ex->color_d);
         ex->color_d = nullptr; ex->color_bytes = 0;
         CK(cudaMalloc(&ex->color_d, cstride * ex->max_batch));
@@ -530,6 +541,7 @@ static vsg_status extract_batch_host(vsg_extractor *ex, const uint8_t *images, i
     const bool chunked = !ex->profile && nframes >= 2 * ex->chunk_frames;
     const int chunk = chunked ? ex->chunk_frames : nframes;
     const bool tight = frame_stride == (size_t)pitch * height && (int64_t)L0.pitch * L0.h == L0.plane_stride;
+    RectifyMaps maps = {{ex->rect_xy[0], ex->rect_xy[1]}, {ex->rect_frac[0], ex->rect_frac[1]}, rect_slots};
     int nstreams_used = 0;
     for (int f0 = 0, c = 0; f0 < nframes; f0 += chunk, ++c) {
         const int nf = std::min(chunk, nframes - f0);
@@ -537,17 +549,20 @@ static vsg_status extract_batch_host(vsg_extractor *ex, const uint8_t *images, i
         nstreams_used = std::min(3, c + 1);
         uint8_t *dst0 = lvl0 + (int64_t)f0 * L0.plane_stride;
         const uint8_t *src0 = images + (size_t)f0 * frame_stride;
-        if (channels != 1) {
+        if (staged) {
             uint8_t *c0 = ex->color_d + (size_t)f0 * cstride;
-            if (frame_stride == (size_t)pitch * height) {
-                CK(cudaMemcpy2DAsync(c0, cpitch, src0, pitch, (size_t)width * channels, (size_t)height * nf,
+            if (frame_stride == (size_t)pitch * src_h) {
+                CK(cudaMemcpy2DAsync(c0, cpitch, src0, pitch, (size_t)src_w * channels, (size_t)src_h * nf,
                                      cudaMemcpyHostToDevice, s));
             } else {
                 for (int f = 0; f < nf; ++f)
-                    CK(cudaMemcpy2DAsync(c0 + f * cstride, cpitch, src0 + f * frame_stride, pitch, (size_t)width * channels,
-                                         height, cudaMemcpyHostToDevice, s));
+                    CK(cudaMemcpy2DAsync(c0 + f * cstride, cpitch, src0 + f * frame_stride, pitch, (size_t)src_w * channels,
+                                         src_h, cudaMemcpyHostToDevice, s));
             }
-            launch_cvt_gray(c0, cpitch, (int64_t)cstride, channels, r_first, dst0, L0.pitch, L0.plane_stride, width, height, nf, s);
+            if (rect_slots > 0)
+                launch_remap(c0, cpitch, (int64_t)cstride, src_w, src_h, maps, f0, dst0, L0.pitch, L0.plane_stride, width, height, nf, s);
+            else
+                launch_cvt_gray(c0, cpitch, (int64_t)cstride, channels, r_first, dst0, L0.pitch, L0.plane_stride, width, height, nf, s);
         } else if (tight) {
             CK(cudaMemcpy2DAsync(dst0, L0.pitch, src0, pitch, width, (size_t)height * nf, cudaMemcpyHostToDevice, s));
         } else {
@@ -606,7 +621,7 @@ static vsg_status extract_batch_host(vsg_extractor *ex, const uint8_t *images, i
 vsg_status vsg_extract_batch(vsg_extractor *ex, const uint8_t *images, int nframes, int width, int height, int pitch,
                              size_t frame_stride, int lap_x0, int lap_x1, vsg_keypoint *keypoints_out,
                              uint8_t *descriptors_out, int capacity, int *n_out, int *mono_index_out) {
-    return extract_batch_host(ex, images, nframes, width, height, pitch, frame_stride, 1, 0, lap_x0, lap_x1, keypoints_out,
+    return extract_batch_host(ex, images, nframes, width, height, pitch, frame_stride, 1, 0, 0, lap_x0, lap_x1, keypoints_out,
                               descriptors_out, capacity, n_out, mono_index_out);
 }
 
@@ -615,7 +630,52 @@ vsg_status vsg_extract_batch_color(vsg_extractor *ex, const uint8_t *images, int
                                    vsg_keypoint *keypoints_out, uint8_t *descriptors_out, int capacity, int *n_out,
                                    int *mono_index_out) {
     if (channels != 3 && channels != 4) { set_error("vsg_extract_batch_color: channels must be 3 or 4"); return VSG_ERR_INVALID; }
-    return extract_batch_host(ex, images, nframes, width, height, pitch, frame_stride, channels, r_first, lap_x0, lap_x1,
+    return extract_batch_host(ex, images, nframes, width, height, pitch, frame_stride, channels, r_first, 0, lap_x0, lap_x1,
+                              keypoints_out, descriptors_out, capacity, n_out, mono_index_out);
+}
+
+vsg_status vsg_extractor_set_rectify_map(vsg_extractor *ex, int slot, const float *map_x, const float *map_y, int width,
+                                         int height) {
+    if (!ex || slot < 0 || slot > 1 || !map_x || !map_y || width <= 0 || height <= 0) {
+        set_error("vsg_extractor_set_rectify_map: slot must be 0 or 1, maps non-null, size positive");
+        return VSG_ERR_INVALID;
+    }
+    if (ex->rect_w != 0 && (ex->rect_w != width || ex->rect_h != height) && ex->rect_xy[1 - slot]) {
+        set_error("vsg_extractor_set_rectify_map: both maps of a handle must have the same size (%dx%d vs %dx%d)", width, height,
+                  ex->rect_w, ex->rect_h);
+        return VSG_ERR_INVALID;
+    }
+    // cv::remap's fixed-point form of a CV_32FC1 map pair: sx = cvRound(x * INTER_TAB_SIZE), integer part saturated to short
+    const size_t n = (size_t)width * height;
+    std::vector<uint32_t> xy(n);
+    std::vector<uint16_t> frac(n);
+    auto sat_short = [](int v) { return v < -32768 ? -32768 : (v > 32767 ? 32767 : v); };
+    for (size_t i = 0; i < n; ++i) {
+        const int sx = cv_round(map_x[i] * 32.f), sy = cv_round(map_y[i] * 32.f);
+        xy[i] = (uint32_t)(uint16_t)(short)sat_short(sx >> 5) | ((uint32_t)(uint16_t)(short)sat_short(sy >> 5) << 16);
+        frac[i] = (uint16_t)(((sy & 31) << 5) | (sx & 31));
+    }
+    CK(cudaSetDevice(ex->device));
+    CK(cudaStreamSynchronize(ex->stream));
+    cudaFree(ex->rect_xy[slot]); cudaFree(ex->rect_frac[slot]);
+    ex->rect_xy[slot] = nullptr; ex->rect_frac[slot] = nullptr;
+    CK(cudaMalloc(&ex->rect_xy[slot], n * sizeof(uint32_t)));
+    CK(cudaMalloc(&ex->rect_frac[slot], n * sizeof(uint16_t)));
+    CK(cudaMemcpy(ex->rect_xy[slot], xy.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ex->rect_frac[slot], frac.data(), n * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    ex->rect_w = width; ex->rect_h = height;
+    return VSG_OK;
+}
+
+vsg_status vsg_extract_batch_rectify(vsg_extractor *ex, const uint8_t *images, int nframes, int src_width, int src_height,
+                                     int pitch, size_t frame_stride, int ncameras, int lap_x0, int lap_x1,
+                                     vsg_keypoint *keypoints_out, uint8_t *descriptors_out, int capacity, int *n_out,
+                                     int *mono_index_out) {
+    if (!ex || ncameras < 1 || ncameras > 2 || !ex->rect_xy[0] || (ncameras == 2 && !ex->rect_xy[1])) {
+        set_error("vsg_extract_batch_rectify: ncameras must be 1 or 2 and their maps set (vsg_extractor_set_rectify_map)");
+        return VSG_ERR_INVALID;
+    }
+    return extract_batch_host(ex, images, nframes, src_width, src_height, pitch, frame_stride, 1, 0, ncameras, lap_x0, lap_x1,
                               keypoints_out, descriptors_out, capacity, n_out, mono_index_out);
 }
 

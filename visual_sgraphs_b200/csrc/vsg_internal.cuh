@@ -158,6 +158,15 @@ void launch_resize_level(const FrameGeom &g, int level, const uint8_t *src_base,
 // cv::cvtColor(..., COLOR_{RGB,BGR,RGBA,BGRA}2GRAY) of `nframes` device frames into 8-bit planes (src 4-byte aligned)
 void launch_cvt_gray(const uint8_t *src, int src_pitch, int64_t src_stride, int channels, int r_first, uint8_t *dst,
                      int dst_pitch, int64_t dst_stride, int w, int h, int nframes, cudaStream_t s);
+// Quantised rectification maps of up to two cameras (frame f of a batch uses slot f % nslots): per output pixel the
+// integer source position (x | y << 16, two shorts) and the 1/32-pixel fraction (fy * 32 + fx).
+struct RectifyMaps {
+    const uint32_t *xy[2];
+    const uint16_t *frac[2];
+    int nslots;
+};
+void launch_remap(const uint8_t *src, int src_pitch, int64_t src_stride, int sw, int sh, const RectifyMaps &maps, int first_frame,
+                  uint8_t *dst, int dst_pitch, int64_t dst_stride, int w, int h, int nframes, cudaStream_t s);
 void launch_blur(const FrameGeom &g, const uint8_t *lvl0_base, int lvl0_pitch, int64_t lvl0_stride, const uint8_t *pyr,
                  uint8_t *blur, int nframes, cudaStream_t s);
 // blur != nullptr: the Gaussian blur of the same frames runs inside the same grid (fast_blur_kernel)

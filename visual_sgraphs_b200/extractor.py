@@ -106,6 +106,31 @@ class ORBextractor:
                                               ptr(n), ptr(mono)))
         return [(int(mono[f]), kps[f, : n[f]].copy(), desc[f, : n[f]].copy()) for f in range(nf)]
 
+    def set_rectify_map(self, slot, map_x, map_y):
+        """Rectification map of camera `slot` (0 = left / only, 1 = right): the CV_32FC1 pair of
+        cv::initUndistortRectifyMap (Settings.cc:571-574); the maps' shape is the rectified image size."""
+        map_x = np.ascontiguousarray(map_x, np.float32)
+        map_y = np.ascontiguousarray(map_y, np.float32)
+        assert map_x.ndim == 2 and map_x.shape == map_y.shape
+        check(self._L.vsg_extractor_set_rectify_map(self._h, int(slot), ptr(map_x), ptr(map_y), map_x.shape[1], map_x.shape[0]))
+        self._rect_shape = map_x.shape
+
+    def extract_batch_rectify(self, frames, ncameras=1, lapping=(0, 0)):
+        """frames: (n, h, w) uint8 unrectified gray frames; frame f is remapped (cv::remap INTER_LINEAR, System.cc:284-292)
+        with the map of camera f % ncameras on the device and extracted. Returns list of (mono, kps, desc)."""
+        assert frames.dtype == np.uint8 and frames.ndim == 3 and frames.strides[2] == 1
+        nf, h, w = frames.shape
+        rh, rw = self._rect_shape
+        cap = self.max_keypoints(rw, rh)
+        kps = np.zeros((nf, cap), KEYPOINT_DTYPE)
+        desc = np.zeros((nf, cap, 32), np.uint8)
+        n = np.zeros(nf, np.int32)
+        mono = np.zeros(nf, np.int32)
+        check(self._L.vsg_extract_batch_rectify(self._h, ptr(frames), nf, w, h, frames.strides[1], frames.strides[0],
+                                                int(ncameras), int(lapping[0]), int(lapping[1]), ptr(kps), ptr(desc), cap,
+                                                ptr(n), ptr(mono)))
+        return [(int(mono[f]), kps[f, : n[f]].copy(), desc[f, : n[f]].copy()) for f in range(nf)]
+
     def extract_batch_dev(self, frames_dev, kps_dev, desc_dev, n_dev, mono_dev, lapping=(0, 0)):
         """Device-resident variant: torch uint8 CUDA tensors. frames (n,h,w); kps (n,cap,28) u8; desc (n,cap,32)
         u8; n/mono int32 (n). Asynchronous on the handle's stream."""
