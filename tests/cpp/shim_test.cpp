@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <random>
 #include <vector>
@@ -764,6 +765,43 @@ int main(int argc, char **argv) {
         VS_GRAPHS::frame_ops::ComputeStereoFromRGBD(keys, keysUn, depth.data(), 640, 40.f, ur, dz);
         orc_stereo_from_rgbd(n, xy.data(), want.data(), depth.data(), 640, 40.f, wur.data(), wdz.data());
         EXPECT(ur == wur && dz == wdz, "ComputeStereoFromRGBD");
+    }
+
+    // ---------------- rectification ahead of the extractor (System.cc:284-292) ----------------
+    {
+        const int w = 624, h = 464;
+        std::vector<float> mx((size_t)w * h), my((size_t)w * h);
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x) {
+                const float xn = (x - w / 2.f) / 400.f, yn = (y - h / 2.f) / 400.f, f = 1.f + 0.15f * (xn * xn + yn * yn);
+                mx[(size_t)y * w + x] = xn * f * 400.f + 320.f + 1.25f;
+                my[(size_t)y * w + x] = yn * f * 400.f + 240.f - 0.75f;
+            }
+        VS_GRAPHS::ORBextractor exr(1000, 1.2f, 8, 20, 7);
+        exr.SetRectification(mx.data(), my.data(), w, h);
+        cv::Mat m(480, 640, CV_8UC1, img_a.data(), 640);
+        std::vector<cv::KeyPoint> kps;
+        cv::Mat desc;
+        std::vector<int> lap = {0, 0};
+        exr(m, cv::noArray(), kps, desc, lap);
+        std::vector<unsigned char> rect((size_t)w * h);
+        orc_remap_bilinear(img_a.data(), 640, 480, 640, mx.data(), my.data(), w, h, rect.data(), w);
+        orc_extractor *orc2 = orc_extractor_create(1000, 1.2f, 8, 20, 7);
+        orc_extract(orc2, rect.data(), w, h, w, 0, 0);
+        const int n = orc_num_keypoints(orc2);
+        std::vector<orc_keypoint> okps(n);
+        std::vector<unsigned char> odesc((size_t)n * 32);
+        orc_get_keypoints(orc2, okps.data(), odesc.data());
+        int bad = (int)kps.size() != n;
+        for (int i = 0; i < n && i < (int)kps.size(); ++i)
+            bad += kps[i].pt.x != okps[i].x || kps[i].pt.y != okps[i].y || kps[i].octave != okps[i].octave ||
+                   std::memcmp(desc.ptr(i), &odesc[(size_t)i * 32], 32) != 0;
+        long diff = 0;
+        const cv::Mat &L0 = exr.mvImagePyramid[0];
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x) diff += L0.ptr(y)[x] != rect[(size_t)y * w + x];
+        EXPECT(bad == 0 && n > 500 && diff == 0 && L0.cols == w && L0.rows == h, "rectified extraction: %d bad of %d, %ld level-0 pixels differ", bad, n, diff);
+        orc_extractor_destroy(orc2);
     }
 
     orc_extractor_destroy(orc);

@@ -49,6 +49,12 @@ void ORBextractor::SetDevice(int device) {
     EnsureHandle();
 }
 
+void ORBextractor::SetRectification(const float *map1, const float *map2, int width, int height) {
+    Check(vsg_extractor_set_rectify_map(mpHandle, 0, map1, map2, width, height), "vsg_extractor_set_rectify_map");
+    mnRectWidth = width;
+    mnRectHeight = height;
+}
+
 static inline int Reflect101(int i, int n) {
     if (n == 1) return 0;
     while (i < 0 || i >= n) i = (i < 0) ? -i : 2 * n - 2 - i;
@@ -61,15 +67,22 @@ int ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*_mask*/, st
     cv::Mat image = _image.getMat();
     assert(image.type() == CV_8UC1);
 
-    const int cap = vsg_extractor_max_keypoints(mpHandle, image.cols, image.rows);
+    const bool rectify = mnRectWidth > 0;
+    const int cap = vsg_extractor_max_keypoints(mpHandle, rectify ? mnRectWidth : image.cols, rectify ? mnRectHeight : image.rows);
     if (cap < 0) Check(cap, "vsg_extractor_max_keypoints");
     static_assert(sizeof(cv::KeyPoint) == sizeof(vsg_keypoint), "cv::KeyPoint layout");
     std::vector<cv::KeyPoint> kps(cap);
     std::vector<unsigned char> desc((size_t)cap * 32);
     int n = 0, mono = 0;
     const int lap0 = vLappingArea.size() > 0 ? vLappingArea[0] : 0, lap1 = vLappingArea.size() > 1 ? vLappingArea[1] : 0;
-    Check(vsg_extract(mpHandle, image.ptr(0), image.cols, image.rows, (int)image.step, lap0, lap1,
-                      reinterpret_cast<vsg_keypoint *>(kps.data()), desc.data(), cap, &n, &mono), "vsg_extract");
+    if (rectify)
+        Check(vsg_extract_batch_rectify(mpHandle, image.ptr(0), 1, image.cols, image.rows, (int)image.step,
+                                        (size_t)image.step * image.rows, 1, lap0, lap1,
+                                        reinterpret_cast<vsg_keypoint *>(kps.data()), desc.data(), cap, &n, &mono),
+              "vsg_extract_batch_rectify");
+    else
+        Check(vsg_extract(mpHandle, image.ptr(0), image.cols, image.rows, (int)image.step, lap0, lap1,
+                          reinterpret_cast<vsg_keypoint *>(kps.data()), desc.data(), cap, &n, &mono), "vsg_extract");
 
     if (n == 0) {
         _descriptors.release();

@@ -48,6 +48,11 @@ public:
     void SetPyramidDownload(bool on) { mbDownloadPyramid = on; }
     void SetDevice(int device);                 // before the first call; default 0
     vsg_extractor *Handle() { return mpHandle; }  // for callers that want the device-side pyramid (stereo)
+    // Rectification on the device: map1 / map2 are this camera's CV_32FC1 maps of cv::initUndistortRectifyMap
+    // (Settings.cc:571-574, width x height = the rectified size).  From then on operator() takes the UNRECTIFIED image
+    // and does what System::TrackStereo's cv::remap(im, imToFeed, M1, M2, cv::INTER_LINEAR) (System.cc:284-292) plus the
+    // reference's operator() would; mvImagePyramid[0] is the rectified image.
+    void SetRectification(const float *map1, const float *map2, int width, int height);
 
 protected:
     void EnsureHandle();
@@ -67,6 +72,7 @@ protected:
     vsg_extractor *mpHandle = nullptr;
     int mnDevice = 0;
     bool mbDownloadPyramid = true;
+    int mnRectWidth = 0, mnRectHeight = 0;   // > 0: SetRectification was called
     std::vector<cv::Mat> mvPyramidStorage;   // padded buffers the mvImagePyramid ROIs point into
 };
 
