@@ -95,6 +95,8 @@ struct vsg_extractor {
     LevelKp *level_kps = nullptr;
     int *level_kp_count = nullptr;
     int *slot = nullptr;
+    uint8_t *out_block_d = nullptr, *out_block_h = nullptr;   // kps / desc / n / mono below are sub-ranges of these
+    size_t out_block_bytes = 0;
     vsg_keypoint *kps_d = nullptr;
     uint8_t *desc_d = nullptr;
     int *n_d = nullptr, *mono_d = nullptr;
@@ -133,10 +135,11 @@ struct vsg_extractor {
 
     void free_shape() {
         cudaFree(cells_d); cudaFree(tabs_d); cudaFree(pyr); cudaFree(blur); cudaFree(cand); cudaFree(node_of);
-        cudaFree(cand_count); cudaFree(level_kps); cudaFree(level_kp_count); cudaFree(slot); cudaFree(kps_d);
-        cudaFree(desc_d); cudaFree(n_d); cudaFree(mono_d); cudaFree(color_d);
+        cudaFree(cand_count); cudaFree(level_kps); cudaFree(level_kp_count); cudaFree(slot); cudaFree(out_block_d);
+        cudaFree(color_d);
         color_d = nullptr; color_bytes = 0;
-        cudaFreeHost(kps_h); cudaFreeHost(desc_h); cudaFreeHost(n_h); cudaFreeHost(mono_h);
+        cudaFreeHost(out_block_h);
+        out_block_d = out_block_h = nullptr; out_block_bytes = 0;
         cells_d = nullptr; tabs_d = nullptr; pyr = blur = nullptr; cand = nullptr; node_of = nullptr;
         cand_count = nullptr; level_kps = nullptr; level_kp_count = nullptr; slot = nullptr; kps_d = nullptr;
         desc_d = nullptr; n_d = mono_d = nullptr; kps_h = nullptr; desc_h = nullptr; n_h = mono_h = nullptr;
@@ -319,14 +322,26 @@ vsg_status configure_shape(vsg_extractor *ex, int w, int h) {
     CK(cudaMalloc(&ex->level_kps, (size_t)g.kp_total * B * sizeof(LevelKp)));
     CK(cudaMalloc(&ex->level_kp_count, (size_t)B * nl * sizeof(int)));
     CK(cudaMalloc(&ex->slot, (size_t)g.kp_total * B * sizeof(int)));
-    CK(cudaMalloc(&ex->kps_d, (size_t)g.out_cap * B * sizeof(vsg_keypoint)));
-    CK(cudaMalloc(&ex->desc_d, (size_t)g.out_cap * B * 32));
-    CK(cudaMalloc(&ex->n_d, (size_t)B * sizeof(int)));
-    CK(cudaMalloc(&ex->mono_d, (size_t)B * sizeof(int)));
-    CK(cudaMallocHost(&ex->kps_h, (size_t)g.out_cap * B * sizeof(vsg_keypoint)));
-    CK(cudaMallocHost(&ex->desc_h, (size_t)g.out_cap * B * 32));
-    CK(cudaMallocHost(&ex->n_h, (size_t)B * sizeof(int)));
-    CK(cudaMallocHost(&ex->mono_h, (size_t)B * sizeof(int)));
+    // The four result arrays are sub-ranges of ONE device block and of ONE pinned host block with the same layout, so a
+    // call that fills the whole handle (a single frame on a max_batch = 1 handle, above all) brings everything back with
+    // a single device-to-host copy instead of four.
+    {
+        auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+        const size_t off_desc = up((size_t)g.out_cap * B * sizeof(vsg_keypoint));
+        const size_t off_n = off_desc + up((size_t)g.out_cap * B * 32);
+        const size_t off_mono = off_n + up((size_t)B * sizeof(int));
+        ex->out_block_bytes = off_mono + up((size_t)B * sizeof(int));
+        CK(cudaMalloc(&ex->out_block_d, ex->out_block_bytes));
+        CK(cudaMallocHost(&ex->out_block_h, ex->out_block_bytes));
+        ex->kps_d = reinterpret_cast<vsg_keypoint *>(ex->out_block_d);
+        ex->desc_d = ex->out_block_d + off_desc;
+        ex->n_d = reinterpret_cast<int *>(ex->out_block_d + off_n);
+        ex->mono_d = reinterpret_cast<int *>(ex->out_block_d + off_mono);
+        ex->kps_h = reinterpret_cast<vsg_keypoint *>(ex->out_block_h);
+        ex->desc_h = ex->out_block_h + off_desc;
+        ex->n_h = reinterpret_cast<int *>(ex->out_block_h + off_n);
+        ex->mono_h = reinterpret_cast<int *>(ex->out_block_h + off_mono);
+    }
     ex->cur_w = w;
     ex->cur_h = h;
     return VSG_OK;
@@ -575,6 +590,10 @@ static vsg_status extract_batch_host(vsg_extractor *ex, const uint8_t *images, i
         st = run_pipeline(ex, s, f0, dst0, L0.pitch, L0.plane_stride, nf, lap_x0, lap_x1, kd, dd, g.out_cap, ex->n_d + f0,
                           ex->mono_d + f0);
         if (st != VSG_OK) return st;
+        if (!direct && nf == ex->max_batch) {     // the call fills the handle: one copy of the whole result block
+            CK(cudaMemcpyAsync(ex->out_block_h, ex->out_block_d, ex->out_block_bytes, cudaMemcpyDeviceToHost, s));
+            continue;
+        }
         CK(cudaMemcpyAsync(ex->n_h + f0, ex->n_d + f0, nf * sizeof(int), cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(ex->mono_h + f0, ex->mono_d + f0, nf * sizeof(int), cudaMemcpyDeviceToHost, s));
         if (direct) {
