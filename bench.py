@@ -269,6 +269,28 @@ def other_config_extras(torch, lib, device):
     out["c2_stereo_752x480_1200f"] = {"pairs_per_s": npairs / dt, "ms_per_pair": 1e3 * dt / npairs, "pairs_per_call": npairs,
                                       "stereo_matches_per_pair": matched / npairs,
                                       "api": "vsg_extract_batch (pinned frames in) + vsg_stereo_match_batch (u_right / depth out)"}
+    # the same with the rectification System::TrackStereo runs first (System.cc:284-292; EuRoC.yaml needs it): unrectified
+    # frames in, cv::remap on the device with one map per camera, then extraction + stereo matching
+    ys, xs = np.meshgrid(np.arange(480, dtype=np.float64), np.arange(752, dtype=np.float64), indexing="ij")
+    for slot, (k1, shift) in enumerate(((-0.05, 1.5), (-0.045, -1.0))):
+        xn, yn = (xs - 376) / 450.0, (ys - 240) / 450.0
+        f = 1 + k1 * (xn * xn + yn * yn)
+        ex2.set_rectify_map(slot, (xn * f * 450 + 376 + shift).astype(np.float32), (yn * f * 450 + 240 - shift).astype(np.float32))
+
+    def rectified_step():
+        check(lib.vsg_extract_batch_rectify(ex2._h, ptr(stack_np), 2 * npairs, 752, 480, 752, 752 * 480, 2, 0, 0, ptr(kp2), ptr(de2),
+                                            cap2, ptr(n2), ptr(mono2)))
+        check(lib.vsg_stereo_match_batch(m._h, ex2._h, npairs, 0.11, 47.9, ptr(u2), ptr(d2), cap2))
+        return int((u2 >= 0).sum())
+
+    rectified_step()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        matched_r = rectified_step()
+    dtr = (time.perf_counter() - t0) / reps
+    out["c2_stereo_752x480_1200f"]["rectified_on_device"] = {"pairs_per_s": npairs / dtr, "ms_per_pair": 1e3 * dtr / npairs,
+                                                              "stereo_matches_per_pair": matched_r / npairs,
+                                                              "api": "vsg_extract_batch_rectify (cv::remap per camera) + vsg_stereo_match_batch"}
     ex2.close()
     # ---- C3 ----
     rng = np.random.default_rng(3)
