@@ -425,14 +425,16 @@ def main():
     n_kp_mean = float(n_d.float().mean().item())
 
     # ---- end to end through the host-pointer C-ABI call (pinned frames in, pinned results out) ----
-    # Four handles driven by four host threads, each taking a quarter of the step's frames (every call is itself a
-    # chunked three-stream pipeline), so that the copies of one call overlap the kernels of the others — the way a
-    # sequence driver would run it.  Measured on the B200: 1 / 2 / 3 / 4 handles -> 93 / 106 / 115 / 117 k frames/s.
+    # Two handles driven by two host threads, each taking half of the step's frames (every call is itself a chunked
+    # three-stream pipeline of 128-frame chunks), so that the copies of one call overlap the kernels of the other — the
+    # way a sequence driver would run it.  Measured on the B200 (chunk 128): 1 / 2 / 4 handles -> 102 / 124 / 121 k
+    # frames/s; 64-frame chunks cap the rate at 117 k whatever the number of handles (small launches are less efficient).
     from visual_sgraphs_b200._lib import check, ptr
     host_np = host_frames.numpy()
-    nh = max(1, min(int(os.environ.get("VSG_E2E_HANDLES", "4")), B))       # handles (= host threads) sharing a step
+    nh = max(1, min(int(os.environ.get("VSG_E2E_HANDLES", "2")), B))       # handles (= host threads) sharing a step
+    alternate = os.environ.get("VSG_E2E_MODE", "split") == "alternate"      # whole steps round-robin over the handles
     cuts = [B * i // nh for i in range(nh + 1)]
-    parts = [(cuts[i], cuts[i + 1]) for i in range(nh)]
+    parts = [(0, B)] * nh if alternate else [(cuts[i], cuts[i + 1]) for i in range(nh)]
     handles = [ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_batch=e - b) for b, e in parts]
     outs = []
     for b, e in parts:
@@ -447,8 +449,9 @@ def main():
                                     ptr(nn), ptr(mm)))
 
     def e2e_worker(i, steps):
-        for _ in range(steps):
-            e2e_part(i)
+        for k in range(steps):
+            if not alternate or k % nh == i:
+                e2e_part(i)
 
     def e2e_run(steps):
         # each handle streams its half of every step back to back; the halves are not re-synchronised between steps

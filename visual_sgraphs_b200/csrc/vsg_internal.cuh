@@ -126,6 +126,7 @@ bool extractor_pyramid(vsg_extractor *ex, PyramidRef *out);
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 bool pdl_enabled();
+void pdl_scope(int nframes);   // run_pipeline: decides per batch size (thread-local)
 
 template <class... KArgs, class... Args>
 inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl,
