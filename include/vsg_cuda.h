@@ -260,6 +260,19 @@ vsg_status vsg_search_by_projection_map(vsg_matcher *m, const vsg_frame *F, cons
                                         const vsg_track_point *pts, const uint8_t *mp_desc, float th, int far_points,
                                         float th_far, float nnratio, int32_t *assign_out, int *nmatches_out);
 
+/* The same method on a two-camera frame (F.Nleft != -1, the stereo-fisheye rigs; ORBmatcher.cc:42-216 with the
+ * right-camera branch :146-213).  FL / FR are the two cameras' keypoints as separate frames (FL: mvKeys and rows
+ * [0, Nleft) of mDescriptors, FR: mvKeysRight and rows [Nleft, N); no u_right).  occupied and assign_out have N = Nleft +
+ * Nright entries in the reference's slot order (left slots first); left_to_right / right_to_left are
+ * mvLeftToRightMatch / mvRightToLeftMatch (-1 = none).  pts_left[i] holds mbTrackInView, mTrackProjX/Y, mTrackViewCos,
+ * mnTrackScaleLevel plus the shared mTrackDepth / isBad / Observations() > 0; pts_right[i] the R members
+ * (mbTrackInViewR, mTrackProjXR/YR in proj_x / proj_y, mTrackViewCosR, mnTrackScaleLevelR, -1 allowed). */
+vsg_status vsg_search_by_projection_map_2cam(vsg_matcher *m, const vsg_frame *FL, const vsg_frame *FR, const uint8_t *occupied,
+                                             const int32_t *left_to_right, const int32_t *right_to_left, int n_mp,
+                                             const vsg_track_point *pts_left, const vsg_track_point *pts_right,
+                                             const uint8_t *mp_desc, float th, int far_points, float th_far, float nnratio,
+                                             int32_t *assign_out, int *nmatches_out);
+
 /* The same method in two halves, for map points sharded over GPUs (BASELINE config 3): every rank runs
  * vsg_projection_map_candidates on its contiguous shard of the map points — the window query and the Hamming distance
  * of every candidate, in the reference's candidate order (cand_ptr has n_mp + 1 entries, VSG_ERR_CAPACITY and

@@ -165,6 +165,87 @@ int orc_search_by_projection_map(const orc_frame_view *F, const uint8_t *occupie
     return nmatches;
 }
 
+// ORBmatcher.cc:42-216 on a two-camera frame (F.Nleft != -1): FL / FR are the two cameras' keypoints with their own
+// grids (Frame::GetFeaturesInArea(..., bRight) reads mGrid + mvKeys or mGridRight + mvKeysRight, Frame.cc:840-848);
+// slots [0, nL) of occupied / assign are the left keypoints, [nL, nL + nR) the right ones.  pl[i] / pr[i] are the map
+// point's left / right tracking members; depth, bad and blocks are read from pl[i].
+int orc_search_by_projection_map_2cam(const orc_frame_view *FL, const orc_frame_view *FR, const uint8_t *occupied_in,
+                                      const int32_t *left_to_right, const int32_t *right_to_left, int n_mp,
+                                      const orc_track_point *pl, const orc_track_point *pr, const uint8_t *mp_desc, float th,
+                                      int far_points, float th_far, float nnratio, int32_t *assign) {
+    Grid gl(FL), gr(FR);
+    const int nL = FL->n, N = FL->n + FR->n;
+    std::vector<uint8_t> blocked(occupied_in, occupied_in + N);
+    for (int i = 0; i < N; ++i) assign[i] = -1;
+    int nmatches = 0;
+    const bool b_factor = th != 1.0;
+    std::vector<int> cand;
+    for (int i = 0; i < n_mp; ++i) {
+        const orc_track_point &l = pl[i], &rp = pr[i];
+        if (!l.in_view && !rp.in_view) continue;
+        if (far_points && l.depth > th_far) continue;
+        if (l.bad) continue;
+        const uint8_t *d_mp = mp_desc + (size_t)i * 32;
+        if (l.in_view) {
+            const int level = l.level;
+            float r = (l.view_cos > 0.998) ? 2.5f : 4.0f;
+            if (b_factor) r *= th;
+            features_in_area(FL, gl, l.proj_x, l.proj_y, r * FL->scale_factors[level], level - 1, level, cand);
+            if (!cand.empty()) {
+                int best = 256, best_level = -1, best2 = 256, best_level2 = -1, best_idx = -1;
+                for (int idx : cand) {
+                    if (blocked[idx]) continue;
+                    const int dist = descriptor_distance(d_mp, FL->descriptors + (size_t)idx * 32);
+                    if (dist < best) {
+                        best2 = best; best = dist; best_level2 = best_level; best_level = FL->keys[idx].octave; best_idx = idx;
+                    } else if (dist < best2) {
+                        best_level2 = FL->keys[idx].octave; best2 = dist;
+                    }
+                }
+                if (best <= TH_HIGH) {
+                    if (best_level == best_level2 && best > nnratio * best2) continue;      // also skips the right camera
+                    if (best_level != best_level2 || best <= nnratio * best2) {
+                        assign[best_idx] = i; blocked[best_idx] = l.blocks;
+                        if (left_to_right[best_idx] != -1) {
+                            assign[left_to_right[best_idx] + nL] = i; blocked[left_to_right[best_idx] + nL] = l.blocks;
+                            ++nmatches;
+                        }
+                        ++nmatches;
+                    }
+                }
+            }
+        }
+        if (rp.in_view) {
+            const int level = rp.level;
+            if (level != -1) {
+                const float r = (rp.view_cos > 0.998) ? 2.5f : 4.0f;
+                features_in_area(FR, gr, rp.proj_x, rp.proj_y, r * FR->scale_factors[level], level - 1, level, cand);
+                if (cand.empty()) continue;
+                int best = 256, best_level = -1, best2 = 256, best_level2 = -1, best_idx = -1;
+                for (int idx : cand) {
+                    if (blocked[idx + nL]) continue;
+                    const int dist = descriptor_distance(d_mp, FR->descriptors + (size_t)idx * 32);
+                    if (dist < best) {
+                        best2 = best; best = dist; best_level2 = best_level; best_level = FR->keys[idx].octave; best_idx = idx;
+                    } else if (dist < best2) {
+                        best_level2 = FR->keys[idx].octave; best2 = dist;
+                    }
+                }
+                if (best <= TH_HIGH) {
+                    if (best_level == best_level2 && best > nnratio * best2) continue;
+                    if (right_to_left[best_idx] != -1) {
+                        assign[right_to_left[best_idx]] = i; blocked[right_to_left[best_idx]] = l.blocks;
+                        ++nmatches;
+                    }
+                    assign[best_idx + nL] = i; blocked[best_idx + nL] = l.blocks;
+                    ++nmatches;
+                }
+            }
+        }
+    }
+    return nmatches;
+}
+
 // ORBmatcher.cc:1667-1784, 1856-1878 (single-camera branch)
 int orc_search_by_projection_last(const orc_frame_view *Cur, const uint8_t *occupied_in, int n_last,
                                   const orc_proj_point *pts, const uint8_t *desc, float th, int mode, int check_ori,

@@ -146,6 +146,11 @@ void orc_three_maxima(const int32_t *sizes, int L, int32_t *ind1, int32_t *ind2,
 int orc_search_by_projection_map(const orc_frame_view *F, const uint8_t *occupied, int n_mp, const orc_track_point *pts,
                                  const uint8_t *mp_desc, float th, int far_points, float th_far, float nnratio,
                                  int32_t *assign);
+/* the same on a two-camera frame (F.Nleft != -1), ORBmatcher.cc:42-216 incl. the right-camera branch :146-213 */
+int orc_search_by_projection_map_2cam(const orc_frame_view *FL, const orc_frame_view *FR, const uint8_t *occupied,
+                                      const int32_t *left_to_right, const int32_t *right_to_left, int n_mp,
+                                      const orc_track_point *pl, const orc_track_point *pr, const uint8_t *mp_desc, float th,
+                                      int far_points, float th_far, float nnratio, int32_t *assign);
 /* SearchByProjection(Frame& Cur, const Frame& Last, th, bMono) (ORBmatcher.cc:1667-1878, Nleft==-1).
  * mode: 0 = octave-1..octave+1, 1 = forward (>= octave), 2 = backward (0..octave).  assign[i] = index of the
  * last-frame point written to Cur.mvpMapPoints[i], -1 untouched, -2 written and then cleared by the rotation check. */

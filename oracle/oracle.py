@@ -81,6 +81,8 @@ def lib():
         L.orc_get_features_in_area.argtypes = [vp, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, vp, C.c_int]
         L.orc_three_maxima.argtypes = [vp, C.c_int, i32p, i32p, i32p]
         L.orc_search_by_projection_map.argtypes = [vp, vp, C.c_int, vp, vp, C.c_float, C.c_int, C.c_float, C.c_float, vp]
+        L.orc_search_by_projection_map_2cam.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, C.c_float, C.c_int, C.c_float,
+                                                         C.c_float, vp]
         L.orc_search_by_projection_last.argtypes = [vp, vp, C.c_int, vp, vp, C.c_float, C.c_int, C.c_int, vp]
         L.orc_search_for_initialization.argtypes = [vp, vp, vp, C.c_int, C.c_float, C.c_int, vp]
         L.orc_search_by_bow.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, C.c_float, C.c_int, vp]
@@ -316,6 +318,19 @@ def search_by_projection_map(view, occupied, pts, mp_desc, th, far_points, th_fa
     assign = np.zeros(view.n, np.int32)
     nm = lib().orc_search_by_projection_map(C.addressof(view), _ptr(occupied), len(pts), _ptr(pts), _ptr(mp_desc), th,
                                             int(far_points), th_far, nnratio, _ptr(assign))
+    return nm, assign
+
+
+def search_by_projection_map_2cam(view_l, view_r, occupied, l2r, r2l, pts_l, pts_r, mp_desc, th, far_points, th_far, nnratio):
+    """ORBmatcher.cc:42-216 on a two-camera frame; slots [0, nL) are the left keypoints, [nL, nL + nR) the right ones."""
+    occupied = np.ascontiguousarray(occupied, np.uint8)
+    mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
+    l2r = np.ascontiguousarray(l2r, np.int32)
+    r2l = np.ascontiguousarray(r2l, np.int32)
+    assign = np.zeros(view_l.n + view_r.n, np.int32)
+    nm = lib().orc_search_by_projection_map_2cam(C.addressof(view_l), C.addressof(view_r), _ptr(occupied), _ptr(l2r), _ptr(r2l),
+                                                 len(pts_l), _ptr(pts_l), _ptr(pts_r), _ptr(mp_desc), th, int(far_points),
+                                                 th_far, nnratio, _ptr(assign))
     return nm, assign
 
 

@@ -103,7 +103,8 @@ struct Frame;
 struct MapPoint {
     bool mbTrackInView = false, mbTrackInViewR = false;
     float mTrackProjX = 0, mTrackProjY = 0, mTrackProjXR = 0, mTrackViewCos = 1, mTrackDepth = 1;
-    int mnTrackScaleLevel = 0;
+    float mTrackProjYR = 0, mTrackViewCosR = 1;
+    int mnTrackScaleLevel = 0, mnTrackScaleLevelR = -1;
     bool bad = false;
     int obs = 1;
     cv::Mat desc;
@@ -134,7 +135,8 @@ struct MapPoint {
 };
 struct Frame {
     int N = 0, Nleft = -1;
-    std::vector<cv::KeyPoint> mvKeys, mvKeysUn;
+    std::vector<cv::KeyPoint> mvKeys, mvKeysUn, mvKeysRight;
+    std::vector<int> mvLeftToRightMatch, mvRightToLeftMatch;
     cv::Mat mDescriptors;
     std::vector<float> mvuRight;
     std::vector<float> mvScaleFactors;
@@ -321,6 +323,71 @@ int main(int argc, char **argv) {
             MapPoint *expect = assign[i] >= 0 ? vp[assign[i]] : (occupied[i] ? &pre : nullptr);
             EXPECT(A.mvpMapPoints[i] == expect, "mvpMapPoints[%d]", i);
         }
+    }
+
+    // ---------------- SearchByProjection(F, vpMapPoints) on a two-camera frame (Nleft != -1) ----------------
+    {
+        Frame F2;                                   // left camera = A's keypoints, right camera = B's
+        F2.Nleft = A.N;
+        F2.mvKeys = A.mvKeys; F2.mvKeysRight = B.mvKeys;
+        F2.N = A.N + B.N;
+        F2.mvScaleFactors = A.mvScaleFactors;
+        F2.mDescriptors.create(F2.N, 32, CV_8U);
+        for (int i = 0; i < A.N; ++i) std::memcpy(F2.mDescriptors.ptr(i), A.mDescriptors.ptr(i), 32);
+        for (int i = 0; i < B.N; ++i) std::memcpy(F2.mDescriptors.ptr(A.N + i), B.mDescriptors.ptr(i), 32);
+        F2.mvpMapPoints.assign(F2.N, nullptr);
+        F2.mvLeftToRightMatch.assign(A.N, -1);
+        F2.mvRightToLeftMatch.assign(B.N, -1);
+        for (int k = 0; k < 200; ++k) {
+            const int l = rng() % A.N, r = rng() % B.N;
+            if (F2.mvLeftToRightMatch[l] == -1 && F2.mvRightToLeftMatch[r] == -1) { F2.mvLeftToRightMatch[l] = r; F2.mvRightToLeftMatch[r] = l; }
+        }
+        const int nMP = A.N + B.N;
+        std::vector<MapPoint> store(nMP);
+        std::vector<MapPoint *> vp(nMP);
+        std::vector<orc_track_point> pl(nMP), pr(nMP);
+        std::vector<unsigned char> mpdesc((size_t)nMP * 32);
+        for (int i = 0; i < nMP; ++i) {
+            MapPoint &mp = store[i];
+            const bool from_left = i % 2 == 0;
+            const int src = from_left ? (i / 2) % A.N : (i / 2) % B.N;
+            const cv::KeyPoint &kl = A.mvKeys[from_left ? src : rng() % A.N], &kr = B.mvKeys[from_left ? rng() % B.N : src];
+            mp.mbTrackInView = rng() % 10 < 7; mp.mbTrackInViewR = rng() % 10 < 7;
+            mp.mTrackProjX = kl.pt.x + (int)(rng() % 5) - 2; mp.mTrackProjY = kl.pt.y + (int)(rng() % 5) - 2;
+            mp.mTrackProjXR = kr.pt.x + (int)(rng() % 5) - 2; mp.mTrackProjYR = kr.pt.y + (int)(rng() % 5) - 2;
+            mp.mTrackViewCos = 0.99f + (rng() % 100) / 10000.f; mp.mTrackViewCosR = 0.99f + (rng() % 100) / 10000.f;
+            mp.mnTrackScaleLevel = kl.octave; mp.mnTrackScaleLevelR = rng() % 20 == 0 ? -1 : kr.octave;
+            mp.mTrackDepth = 1 + rng() % 60;
+            mp.bad = rng() % 30 == 0;
+            mp.obs = rng() % 10 < 9 ? 2 : 0;
+            mp.desc = (from_left ? A.mDescriptors.row(src) : B.mDescriptors.row(src)).clone();
+            vp[i] = &mp;
+            std::memset(&pl[i], 0, sizeof(orc_track_point)); std::memset(&pr[i], 0, sizeof(orc_track_point));
+            pl[i].proj_x = mp.mTrackProjX; pl[i].proj_y = mp.mTrackProjY; pl[i].view_cos = mp.mTrackViewCos; pl[i].level = mp.mnTrackScaleLevel;
+            pl[i].in_view = mp.mbTrackInView; pl[i].depth = mp.mTrackDepth; pl[i].bad = mp.bad; pl[i].blocks = mp.obs > 0;
+            pr[i].proj_x = mp.mTrackProjXR; pr[i].proj_y = mp.mTrackProjYR; pr[i].view_cos = mp.mTrackViewCosR; pr[i].level = mp.mnTrackScaleLevelR;
+            pr[i].in_view = mp.mbTrackInViewR;
+            std::memcpy(&mpdesc[(size_t)i * 32], mp.desc.ptr(0), 32);
+        }
+        MapPoint pre;
+        pre.obs = 3;
+        std::vector<unsigned char> occupied(F2.N, 0);
+        for (int i = 0; i < F2.N; i += 13) { F2.mvpMapPoints[i] = &pre; occupied[i] = 1; }
+        orc_frame_view vl = va, vr = vb;
+        vl.u_right = nullptr; vr.u_right = nullptr;
+        std::vector<int32_t> assign(F2.N);
+        const int want = orc_search_by_projection_map_2cam(&vl, &vr, occupied.data(), F2.mvLeftToRightMatch.data(), F2.mvRightToLeftMatch.data(),
+                                                           nMP, pl.data(), pr.data(), mpdesc.data(), 3.f, 1, 45.f, 0.8f, assign.data());
+        VS_GRAPHS::ORBmatcher matcher(0.8f);
+        const int got = matcher.SearchByProjection(F2, vp, 3.f, true, 45.f);
+        EXPECT(got == want && got > 200, "SearchByProjection(map, two cameras): %d vs %d", got, want);
+        int right_hits = 0;
+        for (int i = 0; i < F2.N; ++i) {
+            MapPoint *expect = assign[i] >= 0 ? vp[assign[i]] : (occupied[i] ? &pre : nullptr);
+            EXPECT(F2.mvpMapPoints[i] == expect, "two cameras: mvpMapPoints[%d]", i);
+            right_hits += i >= A.N && assign[i] >= 0;
+        }
+        EXPECT(right_hits > 50, "two cameras: right-camera matches %d", right_hits);
     }
 
     // ---------------- SearchByProjection(Cur, Last) ----------------

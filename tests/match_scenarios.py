@@ -153,3 +153,40 @@ def synthetic_vocabulary(seed, k=10, levels=4, prune=0.08):
     weight[leaves[::37]] = 0.0                             # stopped words (weight 0)
     return dict(child_ptr=np.array(child_ptr, np.int32), child_idx=np.array(child_idx, np.int32),
                 node_desc=np.stack(desc), word_id=word_id, weight=weight, levels=levels)
+
+
+def two_camera_scene(oracle, seed=61, size=(640, 480), nfeat=800):
+    """A two-camera frame (F.Nleft != -1): left / right keypoints are the two related frames of two_frames; map points are
+    seen by the left camera, the right camera, or both, with their own projections and predicted levels;
+    mvLeftToRightMatch / mvRightToLeftMatch pair up a third of the keypoints.  Returns a dict."""
+    ka, da, kb, db = two_frames(oracle, seed=seed, size=size, nfeat=nfeat)
+    fl, fr = frame_data(ka, da, size=size), frame_data(kb, db, size=size)
+    rng = np.random.default_rng(seed + 7)
+    nl, nr = len(ka), len(kb)
+    # map points: one per left keypoint and one per right keypoint, each also projected (noisily) into the other camera
+    n = nl + nr
+    src_left = np.concatenate([np.arange(nl), rng.integers(0, nl, nr)])
+    src_right = np.concatenate([rng.integers(0, nr, nl), np.arange(nr)])
+    pl, pr = np.zeros(n, TRACK_POINT_DTYPE), np.zeros(n, TRACK_POINT_DTYPE)
+    for pts, keys, src in ((pl, ka, src_left), (pr, kb, src_right)):
+        pts["proj_x"] = keys["x"][src] + rng.normal(0, 1.5, n)
+        pts["proj_y"] = keys["y"][src] + rng.normal(0, 1.5, n)
+        pts["view_cos"] = rng.uniform(0.99, 1.0, n)
+        pts["level"] = np.clip(keys["octave"][src] + rng.integers(-1, 2, n), 0, 7)
+    pl["in_view"] = rng.random(n) < 0.7
+    pr["in_view"] = rng.random(n) < 0.7
+    pr["level"][rng.random(n) < 0.05] = -1                   # mnTrackScaleLevelR == -1 (:149)
+    pl["depth"] = rng.uniform(1, 80, n)
+    pl["bad"] = rng.random(n) < 0.03
+    pl["blocks"] = rng.random(n) < 0.9
+    desc = np.where((np.arange(n) < nl)[:, None], da[src_left], db[src_right]).astype(np.uint8)
+    flip = rng.random((n, 32)) < 0.02
+    desc = desc ^ (flip * rng.integers(1, 256, (n, 32))).astype(np.uint8)
+    l2r, r2l = np.full(nl, -1, np.int32), np.full(nr, -1, np.int32)
+    pairs = min(nl, nr) // 3
+    li, ri = rng.permutation(nl)[:pairs], rng.permutation(nr)[:pairs]
+    l2r[li], r2l[ri] = ri, li
+    occupied = (rng.random(nl + nr) < 0.1).astype(np.uint8)
+    order = rng.permutation(n)
+    return dict(fl=fl, fr=fr, pl=pl[order].copy(), pr=pr[order].copy(), desc=desc[order].copy(), l2r=l2r, r2l=r2l,
+                occupied=occupied)

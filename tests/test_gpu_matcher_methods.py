@@ -52,6 +52,21 @@ def test_search_by_projection_map(oracle, stereo, th, far):
     assert nm > 100
 
 
+@pytest.mark.parametrize("th,far", [(3.0, False), (1.0, True), (5.0, False)])
+def test_search_by_projection_map_two_cameras(oracle, th, far):
+    """F.Nleft != -1 (stereo-fisheye rigs): left- and right-camera searches incl. the cross assignments through
+    mvLeftToRightMatch / mvRightToLeftMatch (ORBmatcher.cc:42-216)."""
+    sc2 = sc.two_camera_scene(oracle)
+    m = _matcher(0.8)
+    nm, assign = m.SearchByProjectionMap2Cam(m.frame(sc2["fl"]), m.frame(sc2["fr"]), sc2["occupied"], sc2["l2r"], sc2["r2l"],
+                                             sc2["pl"], sc2["pr"], sc2["desc"], th, far, 40.0)
+    wnm, wassign = oracle.search_by_projection_map_2cam(sc2["fl"].view, sc2["fr"].view, sc2["occupied"], sc2["l2r"], sc2["r2l"],
+                                                        sc2["pl"], sc2["pr"], sc2["desc"], th, far, 40.0, float(np.float32(0.8)))
+    assert nm == wnm and np.array_equal(assign, wassign)
+    nl = sc2["fl"].n
+    assert (assign[:nl] >= 0).sum() > 100 and (assign[nl:] >= 0).sum() > 100
+
+
 def test_search_by_projection_map_large_map(oracle):
     """Many more map points than keypoints (the C3 shape, scaled): long claim chains on every keypoint."""
     ka, da, kb, db = sc.two_frames(oracle)

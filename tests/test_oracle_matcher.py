@@ -130,6 +130,81 @@ def test_search_by_projection_map_matches_python_restatement(oracle):
             assert nm > 20
 
 
+def py_search_by_projection_map_2cam(sc2, th, far, th_far, nnratio):
+    """Independent restatement of ORBmatcher.cc:42-216 for F.Nleft != -1."""
+    f32 = np.float32
+    fl, fr, pl, pr, desc = sc2["fl"], sc2["fr"], sc2["pl"], sc2["pr"], sc2["desc"]
+    nl = fl.n
+    blocked = sc2["occupied"].astype(bool).copy()
+    assign = np.full(fl.n + fr.n, -1, np.int32)
+    nm = 0
+
+    def scan(fd, cand, i, offset):
+        best, bl, best2, bl2, bi = 256, -1, 256, -1, -1
+        for idx in cand:
+            if blocked[idx + offset]:
+                continue
+            d = hamming(desc[i], fd.descriptors[idx])
+            if d < best:
+                best2, best, bl2, bl, bi = best, d, bl, int(fd.keys[idx]["octave"]), idx
+            elif d < best2:
+                bl2, best2 = int(fd.keys[idx]["octave"]), d
+        return best, bl, best2, bl2, bi
+
+    for i in range(len(pl)):
+        l, r = pl[i], pr[i]
+        if (not l["in_view"] and not r["in_view"]) or (far and l["depth"] > th_far) or l["bad"]:
+            continue
+        blocks = bool(l["blocks"])
+        if l["in_view"]:
+            lvl = int(l["level"])
+            rad = f32(2.5) if float(l["view_cos"]) > 0.998 else f32(4.0)
+            if th != 1.0:
+                rad = f32(rad * f32(th))
+            cand = py_features_in_area(fl, l["proj_x"], l["proj_y"], f32(rad * fl.scale_factors[lvl]), lvl - 1, lvl)
+            if cand:
+                best, bl, best2, bl2, bi = scan(fl, cand, i, 0)
+                if best <= 100:
+                    if bl == bl2 and f32(best) > f32(nnratio) * f32(best2):
+                        continue                                   # the reference's `continue` also skips the right camera
+                    assign[bi] = i
+                    blocked[bi] = blocks
+                    if sc2["l2r"][bi] != -1:
+                        assign[sc2["l2r"][bi] + nl] = i
+                        blocked[sc2["l2r"][bi] + nl] = blocks
+                        nm += 1
+                    nm += 1
+        if r["in_view"] and int(r["level"]) != -1:
+            lvl = int(r["level"])
+            rad = f32(2.5) if float(r["view_cos"]) > 0.998 else f32(4.0)
+            cand = py_features_in_area(fr, r["proj_x"], r["proj_y"], f32(rad * fr.scale_factors[lvl]), lvl - 1, lvl)
+            if not cand:
+                continue
+            best, bl, best2, bl2, bi = scan(fr, cand, i, nl)
+            if best <= 100:
+                if bl == bl2 and f32(best) > f32(nnratio) * f32(best2):
+                    continue
+                if sc2["r2l"][bi] != -1:
+                    assign[sc2["r2l"][bi]] = i
+                    blocked[sc2["r2l"][bi]] = blocks
+                    nm += 1
+                assign[bi + nl] = i
+                blocked[bi + nl] = blocks
+                nm += 1
+    return nm, assign
+
+
+def test_search_by_projection_map_two_cameras_matches_python_restatement(oracle):
+    sc2 = sc.two_camera_scene(oracle, size=(322, 243), nfeat=300)
+    for th, far in ((3.0, False), (1.0, True)):
+        nm, assign = oracle.search_by_projection_map_2cam(sc2["fl"].view, sc2["fr"].view, sc2["occupied"], sc2["l2r"], sc2["r2l"],
+                                                          sc2["pl"], sc2["pr"], sc2["desc"], th, far, 40.0, 0.8)
+        wnm, wassign = py_search_by_projection_map_2cam(sc2, th, far, 40.0, 0.8)
+        assert nm == wnm and np.array_equal(assign, wassign)
+        nl = sc2["fl"].n
+        assert (assign[:nl] >= 0).sum() > 20 and (assign[nl:] >= 0).sum() > 20
+
+
 def test_distinctive_descriptor_matches_python_restatement(oracle):
     """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:383-409): least median distance, first row on ties."""
     rng = np.random.default_rng(31)

@@ -484,6 +484,114 @@ vsg_status vsg_search_by_projection_map(vsg_matcher *m, const vsg_frame *F, cons
     return VSG_OK;
 }
 
+// ORBmatcher.cc:42-216 for a two-camera frame (F.Nleft != -1): per map point the left-camera search (:60-144) and the
+// right-camera search (:146-213), both window queries on the device, replayed in map order on the host.
+vsg_status vsg_search_by_projection_map_2cam(vsg_matcher *m, const vsg_frame *FL, const vsg_frame *FR, const uint8_t *occupied,
+                                             const int32_t *left_to_right, const int32_t *right_to_left, int n_mp,
+                                             const vsg_track_point *pts_left, const vsg_track_point *pts_right,
+                                             const uint8_t *mp_desc, float th, int far_points, float th_far, float nnratio,
+                                             int32_t *assign_out, int *nmatches_out) {
+    if (!m || !FL || !FR || n_mp < 0 || !assign_out || (n_mp > 0 && (!pts_left || !pts_right || !mp_desc)) ||
+        (FL->n + FR->n > 0 && !occupied) || (FL->n > 0 && !left_to_right) || (FR->n > 0 && !right_to_left))
+        return VSG_ERR_INVALID;
+    if (FL->has_right || FR->has_right) {
+        set_error("vsg_search_by_projection_map_2cam: the per-camera frames of a two-camera rig carry no uRight");
+        return VSG_ERR_INVALID;
+    }
+    CK(cudaSetDevice(m->device));
+    const int nL = FL->n, nR = FR->n, N = nL + nR;
+    const bool b_factor = th != 1.0;
+    const int max_dist = projection_map_max_dist(nnratio);
+    const int nlev = (int)FL->scale.size();
+    // queries of both cameras; q_of[cam][i] = query number of map point i or -1
+    std::vector<AreaQuery> qs[2];
+    std::vector<int> q_of[2];
+    for (int cam = 0; cam < 2; ++cam) q_of[cam].assign(std::max(n_mp, 1), -1);
+    for (int i = 0; i < n_mp; ++i) {
+        const vsg_track_point &l = pts_left[i], &r = pts_right[i];
+        if (!l.in_view && !r.in_view) continue;                                 // :52-53
+        if (far_points && l.depth > th_far) continue;                           // :55-56
+        if (l.bad) continue;                                                    // :58-59
+        if (l.in_view) {
+            if (l.level < 0 || l.level >= nlev) { set_error("map point %d: level %d out of range", i, l.level); return VSG_ERR_INVALID; }
+            float rad = (l.view_cos > 0.998) ? 2.5f : 4.0f;
+            if (b_factor) rad *= th;
+            const float win = rad * FL->scale[l.level];
+            q_of[0][i] = (int)qs[0].size();
+            qs[0].push_back(AreaQuery{l.proj_x, l.proj_y, win, l.level - 1, l.level, 0.f, win, max_dist, i});
+        }
+        if (r.in_view && r.level != -1) {                                       // :146-150
+            if (r.level < 0 || r.level >= nlev) { set_error("map point %d: right level %d out of range", i, r.level); return VSG_ERR_INVALID; }
+            const float rad = (r.view_cos > 0.998) ? 2.5f : 4.0f;              // no th factor on this side (:151)
+            const float win = rad * FR->scale[r.level];
+            q_of[1][i] = (int)qs[1].size();
+            qs[1].push_back(AreaQuery{r.proj_x, r.proj_y, win, r.level - 1, r.level, 0.f, win, max_dist, i});
+        }
+    }
+    // the two searches share the matcher's staging: the left lists are copied out before the right search runs
+    std::vector<int2> raw_l;
+    std::vector<int> off_l, cnt_l;
+    AreaLists L;
+    vsg_status st;
+    if ((st = area_search_raw(m, FL, (int)qs[0].size(), qs[0].data(), mp_desc, n_mp, &L)) != VSG_OK) return st;
+    {
+        const int nq = (int)qs[0].size();
+        off_l.assign(L.off, L.off + nq);
+        cnt_l.assign(L.cnt, L.cnt + nq);
+        int total = 0;
+        for (int k = 0; k < nq; ++k) total = std::max(total, off_l[k] + cnt_l[k]);
+        if (total) raw_l.assign(L.raw, L.raw + total);
+    }
+    AreaLists R;
+    if ((st = area_search_raw(m, FR, (int)qs[1].size(), qs[1].data(), mp_desc, n_mp, &R)) != VSG_OK) return st;
+
+    std::vector<uint8_t> blocked(occupied, occupied + N);
+    for (int i = 0; i < N; ++i) assign_out[i] = -1;
+    int nmatches = 0;
+    auto claim = [&](int slot, int mp) { assign_out[slot] = mp; blocked[slot] = pts_left[mp].blocks; };
+    for (int i = 0; i < n_mp; ++i) {
+        if (q_of[0][i] < 0 && q_of[1][i] < 0) continue;
+        bool skip_right = false;
+        if (q_of[0][i] >= 0) {
+            const int k = q_of[0][i];
+            int best = 256, best_level = -1, best2 = 256, best_level2 = -1, best_idx = -1;
+            const int2 *c = raw_l.data() + off_l[k], *ce = c + cnt_l[k];
+            for (; c < ce; ++c) {
+                const int idx = c->x, dist = c->y;
+                if (blocked[idx]) continue;
+                if (dist < best) { best2 = best; best = dist; best_level2 = best_level; best_level = FL->keys[idx].octave; best_idx = idx; }
+                else if (dist < best2) { best_level2 = FL->keys[idx].octave; best2 = dist; }
+            }
+            if (best <= TH_HIGH) {
+                if (best_level == best_level2 && best > nnratio * best2) skip_right = true;   // `continue` at :124-125
+                else {
+                    claim(best_idx, i);
+                    if (left_to_right[best_idx] != -1) { claim(left_to_right[best_idx] + nL, i); ++nmatches; }   // :131-136
+                    ++nmatches;
+                }
+            }
+        }
+        if (skip_right || q_of[1][i] < 0) continue;
+        const int k = q_of[1][i];
+        int best = 256, best_level = -1, best2 = 256, best_level2 = -1, best_idx = -1;
+        const int2 *c = R.raw + R.off[k], *ce = c + R.cnt[k];
+        for (; c < ce; ++c) {
+            const int idx = c->x, dist = c->y;
+            if (blocked[idx + nL]) continue;                                    // :176-178
+            if (dist < best) { best2 = best; best = dist; best_level2 = best_level; best_level = FR->keys[idx].octave; best_idx = idx; }
+            else if (dist < best2) { best_level2 = FR->keys[idx].octave; best2 = dist; }
+        }
+        if (best <= TH_HIGH) {
+            if (best_level == best_level2 && best > nnratio * best2) continue;
+            if (right_to_left[best_idx] != -1) { claim(right_to_left[best_idx], i); ++nmatches; }   // :203-208
+            claim(best_idx + nL, i);
+            ++nmatches;
+        }
+    }
+    if (nmatches_out) *nmatches_out = nmatches;
+    return VSG_OK;
+}
+
 // ORBmatcher.cc:1667-1784 and :1856-1878
 vsg_status vsg_search_by_projection_last(vsg_matcher *m, const vsg_frame *Cur, const uint8_t *occupied, int n_last,
                                          const vsg_proj_point *pts, const uint8_t *desc, float th, int mode,

@@ -154,6 +154,25 @@ class ORBmatcher:
                                                    float(self.mfNNratio), ptr(assign), C.byref(nm)))
         return nm.value, assign
 
+    def SearchByProjectionMap2Cam(self, frame_l, frame_r, occupied, left_to_right, right_to_left, pts_left, pts_right,
+                                  mp_desc, th=3.0, bFarPoints=False, thFarPoints=50.0):
+        """The same method on a two-camera frame (F.Nleft != -1; ORBmatcher.cc:42-216 incl. the right-camera branch):
+        frame_l / frame_r hold mvKeys / mvKeysRight with their descriptor rows, occupied and the returned assign have
+        Nleft + Nright slots (left first).  Returns (nmatches, assign)."""
+        pl = np.ascontiguousarray(pts_left, TRACK_POINT_DTYPE)
+        pr = np.ascontiguousarray(pts_right, TRACK_POINT_DTYPE)
+        assert len(pl) == len(pr)
+        mp_desc = np.ascontiguousarray(mp_desc, np.uint8).reshape(-1, 32)
+        occupied = np.ascontiguousarray(occupied, np.uint8)
+        l2r = np.ascontiguousarray(left_to_right, np.int32)
+        r2l = np.ascontiguousarray(right_to_left, np.int32)
+        assign = np.zeros(frame_l.data.n + frame_r.data.n, np.int32)
+        nm = C.c_int(0)
+        check(self._L.vsg_search_by_projection_map_2cam(self._h, frame_l._h, frame_r._h, ptr(occupied), ptr(l2r), ptr(r2l),
+                                                        len(pl), ptr(pl), ptr(pr), ptr(mp_desc), float(th), int(bFarPoints),
+                                                        float(thFarPoints), float(self.mfNNratio), ptr(assign), C.byref(nm)))
+        return nm.value, assign
+
     def ProjectionMapCandidates(self, frame, track_points, mp_desc, th=3.0, bFarPoints=False, thFarPoints=50.0):
         """GPU half of SearchByProjection(Frame&, vector<MapPoint*>&): per-map-point candidate lists
         (cand_ptr [n+1], cand_idx, cand_dist) in the reference's order (vsg_projection_map_candidates)."""

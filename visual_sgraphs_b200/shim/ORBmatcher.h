@@ -12,8 +12,9 @@
 // Each template flattens those members into the C ABI's view structs, calls the library and writes the
 // results back exactly where the reference does.
 //
-// Scope: single-camera frames (Frame::Nleft == -1).  For two-camera fisheye rigs (Nleft != -1) these
-// methods throw — keep the reference's CPU ORBmatcher for that configuration.
+// Scope: single-camera frames (Frame::Nleft == -1), plus the two-camera branch (Nleft != -1, stereo-fisheye rigs) of
+// SearchByProjection(Frame&, vector<MapPoint*>&).  The other methods throw for two-camera frames — keep the reference's
+// CPU ORBmatcher for them in that configuration.
 #ifndef VSG_SHIM_ORBMATCHER_H
 #define VSG_SHIM_ORBMATCHER_H
 
@@ -119,6 +120,10 @@ protected:
     float mfNNratio;
     bool mbCheckOrientation;
 
+    template <class FrameT, class MapPointT>
+    int SearchByProjectionTwoCameras(FrameT &F, const std::vector<MapPointT *> &vpMapPoints, const float th,
+                                     const bool bFarPoints, const float thFarPoints);
+
     // ---- plumbing ----
     vsg_matcher *mpWorkspace = nullptr;
     int mnDevice = 0;
@@ -206,10 +211,72 @@ protected:
 };
 
 // ---------------------------------------------------------------------------------------------------
+// Two-camera frames (F.Nleft != -1, ORBmatcher.cc:42-216 incl. the right-camera branch :146-213): the two cameras'
+// keypoints are uploaded as two frames, the library runs both window searches and replays the loop in map order.
+template <class FrameT, class MapPointT>
+int ORBmatcher::SearchByProjectionTwoCameras(FrameT &F, const std::vector<MapPointT *> &vpMapPoints, const float th,
+                                             const bool bFarPoints, const float thFarPoints) {
+    static_assert(sizeof(cv::KeyPoint) == sizeof(vsg_keypoint), "cv::KeyPoint layout");
+    const int nL = F.Nleft, nR = (int)F.mvKeysRight.size(), N = nL + nR, nMP = (int)vpMapPoints.size();
+    Flat cam[2];
+    FrameGuard fr[2];
+    for (int c = 0; c < 2; ++c) {
+        Flat &o = cam[c];
+        const std::vector<cv::KeyPoint> &keys = c == 0 ? F.mvKeys : F.mvKeysRight;     // Frame.cc:846-848
+        const int n = c == 0 ? nL : nR, row0 = c == 0 ? 0 : nL;
+        o.keys.resize(n);
+        if (n) std::memcpy(o.keys.data(), keys.data(), (size_t)n * sizeof(vsg_keypoint));
+        o.desc.resize((size_t)n * 32);
+        for (int i = 0; i < n; ++i) std::memcpy(&o.desc[(size_t)i * 32], F.mDescriptors.ptr(row0 + i), 32);
+        o.scale.assign(F.mvScaleFactors.begin(), F.mvScaleFactors.end());
+        vsg_frame_view &v = o.view;
+        v.n = n; v.keys = o.keys.data(); v.descriptors = o.desc.data(); v.u_right = nullptr;
+        v.min_x = F.mnMinX; v.min_y = F.mnMinY; v.max_x = F.mnMaxX; v.max_y = F.mnMaxY;
+        v.grid_inv_w = F.mfGridElementWidthInv; v.grid_inv_h = F.mfGridElementHeightInv;
+        v.grid_cols = FRAME_GRID_COLS; v.grid_rows = FRAME_GRID_ROWS;
+        v.scale_factors = o.scale.data(); v.n_levels = (int)o.scale.size();
+        Check(vsg_frame_create(Workspace(), &v, &fr[c].h), "vsg_frame_create");
+    }
+    std::vector<uint8_t> occupied(N, 0);
+    for (int i = 0; i < N; ++i)
+        if (F.mvpMapPoints[i] && F.mvpMapPoints[i]->Observations() > 0) occupied[i] = 1;
+    std::vector<int32_t> l2r(F.mvLeftToRightMatch.begin(), F.mvLeftToRightMatch.end());
+    std::vector<int32_t> r2l(F.mvRightToLeftMatch.begin(), F.mvRightToLeftMatch.end());
+    l2r.resize(nL, -1);
+    r2l.resize(nR, -1);
+    std::vector<vsg_track_point> pl(nMP), pr(nMP);
+    std::vector<uint8_t> desc((size_t)nMP * 32, 0);
+    for (int i = 0; i < nMP; ++i) {
+        MapPointT *pMP = vpMapPoints[i];
+        std::memset(&pl[i], 0, sizeof(vsg_track_point));
+        std::memset(&pr[i], 0, sizeof(vsg_track_point));
+        if (!pMP->mbTrackInView && !pMP->mbTrackInViewR) continue;
+        pl[i].in_view = pMP->mbTrackInView ? 1 : 0;
+        pl[i].proj_x = pMP->mTrackProjX; pl[i].proj_y = pMP->mTrackProjY; pl[i].view_cos = pMP->mTrackViewCos;
+        pl[i].level = pMP->mnTrackScaleLevel; pl[i].depth = pMP->mTrackDepth;
+        pl[i].bad = pMP->isBad() ? 1 : 0;
+        pl[i].blocks = pMP->Observations() > 0 ? 1 : 0;
+        pr[i].in_view = pMP->mbTrackInViewR ? 1 : 0;
+        pr[i].proj_x = pMP->mTrackProjXR; pr[i].proj_y = pMP->mTrackProjYR; pr[i].view_cos = pMP->mTrackViewCosR;
+        pr[i].level = pMP->mnTrackScaleLevelR;
+        const cv::Mat d = pMP->GetDescriptor();
+        std::memcpy(&desc[(size_t)i * 32], d.ptr(0), 32);
+    }
+    std::vector<int32_t> assign(N, -1);
+    int nmatches = 0;
+    Check(vsg_search_by_projection_map_2cam(Workspace(), fr[0].h, fr[1].h, occupied.data(), l2r.data(), r2l.data(), nMP, pl.data(),
+                                            pr.data(), desc.data(), th, bFarPoints ? 1 : 0, thFarPoints, mfNNratio, assign.data(),
+                                            &nmatches),
+          "vsg_search_by_projection_map_2cam");
+    for (int i = 0; i < N; ++i)
+        if (assign[i] >= 0) F.mvpMapPoints[i] = vpMapPoints[assign[i]];
+    return nmatches;
+}
+
 template <class FrameT, class MapPointT>
 int ORBmatcher::SearchByProjection(FrameT &F, const std::vector<MapPointT *> &vpMapPoints, const float th,
                                    const bool bFarPoints, const float thFarPoints) {
-    RequireSingleCamera(F);
+    if (F.Nleft != -1) return SearchByProjectionTwoCameras(F, vpMapPoints, th, bFarPoints, thFarPoints);
     Flat flat;
     Flatten(F, flat);
     FrameGuard fr;
