@@ -295,6 +295,15 @@ vsg_status vsg_search_by_projection_last(vsg_matcher *m, const vsg_frame *Cur, c
                                          const vsg_proj_point *pts, const uint8_t *desc, float th, int mode,
                                          int check_ori, int32_t *assign_out, int *nmatches_out);
 
+/* The same with a two-camera current frame (CurrentFrame.Nleft != -1; ORBmatcher.cc:1667-1878 incl. the right-camera
+ * search :1785-1852).  CurL / CurR as in vsg_search_by_projection_map_2cam; occupied and assign_out have Nleft + Nright
+ * slots.  pts_left[i] is the last-frame point projected with the left camera (valid, u, v, the last keypoint's angle and
+ * octave, blocks); pts_right[i].u / .v its projection into the right camera (mpCamera->project(Trl * x3Dc)). */
+vsg_status vsg_search_by_projection_last_2cam(vsg_matcher *m, const vsg_frame *CurL, const vsg_frame *CurR,
+                                              const uint8_t *occupied, int n_last, const vsg_proj_point *pts_left,
+                                              const vsg_proj_point *pts_right, const uint8_t *desc, float th, int mode,
+                                              int check_ori, int32_t *assign_out, int *nmatches_out);
+
 /* SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (ORBmatcher.cc:643-756).
  * prev_matched: F1.n x 2 floats, updated in place like vbPrevMatched.  matches12_out: F1.n entries. */
 vsg_status vsg_search_for_initialization(vsg_matcher *m, const vsg_frame_view *F1, const vsg_frame *F2,

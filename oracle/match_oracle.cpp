@@ -295,6 +295,67 @@ int orc_search_by_projection_last(const orc_frame_view *Cur, const uint8_t *occu
     return nmatches;
 }
 
+// ORBmatcher.cc:1667-1878 with a two-camera current frame: pl[i] = the point projected with the left camera (valid, u, v,
+// angle of the last-frame keypoint, its octave, blocks), pr[i].u / .v = its projection into the right camera (:1787-1788).
+int orc_search_by_projection_last_2cam(const orc_frame_view *CurL, const orc_frame_view *CurR, const uint8_t *occupied_in,
+                                       int n_last, const orc_proj_point *pl, const orc_proj_point *pr, const uint8_t *desc,
+                                       float th, int mode, int check_ori, int32_t *assign) {
+    Grid gl(CurL), gr(CurR);
+    const int nL = CurL->n, N = CurL->n + CurR->n;
+    std::vector<uint8_t> blocked(occupied_in, occupied_in + N);
+    for (int i = 0; i < N; ++i) assign[i] = -1;
+    std::vector<int> rot_hist[HISTO_LENGTH];
+    int nmatches = 0;
+    std::vector<int> cand;
+    auto window = [&](const orc_frame_view *F, const Grid &g, float u, float v, float radius, int oct) {
+        if (mode == 1) features_in_area(F, g, u, v, radius, oct, -1, cand);
+        else if (mode == 2) features_in_area(F, g, u, v, radius, 0, oct, cand);
+        else features_in_area(F, g, u, v, radius, oct - 1, oct + 1, cand);
+    };
+    for (int i = 0; i < n_last; ++i) {
+        const orc_proj_point &p = pl[i];
+        if (!p.valid) continue;
+        const int oct = p.octave;
+        const float radius = th * CurL->scale_factors[oct];
+        const uint8_t *d_mp = desc + (size_t)i * 32;
+        window(CurL, gl, p.u, p.v, radius, oct);
+        if (cand.empty()) continue;
+        {
+            int best = 256, best_idx = -1;
+            for (int i2 : cand) {
+                if (blocked[i2]) continue;
+                const int dist = descriptor_distance(d_mp, CurL->descriptors + (size_t)i2 * 32);
+                if (dist < best) { best = dist; best_idx = i2; }
+            }
+            if (best <= TH_HIGH) {
+                assign[best_idx] = i; blocked[best_idx] = p.blocks; ++nmatches;
+                if (check_ori) rot_hist[rot_bin(p.angle, CurL->keys[best_idx].angle)].push_back(best_idx);
+            }
+        }
+        window(CurR, gr, pr[i].u, pr[i].v, radius, oct);
+        int best = 256, best_idx = -1;
+        for (int i2 : cand) {
+            if (blocked[i2 + nL]) continue;
+            const int dist = descriptor_distance(d_mp, CurR->descriptors + (size_t)i2 * 32);
+            if (dist < best) { best = dist; best_idx = i2; }
+        }
+        if (best <= TH_HIGH) {
+            assign[best_idx + nL] = i; blocked[best_idx + nL] = p.blocks; ++nmatches;
+            if (check_ori) rot_hist[rot_bin(p.angle, CurR->keys[best_idx].angle)].push_back(best_idx + nL);
+        }
+    }
+    if (check_ori) {
+        int sizes[HISTO_LENGTH], ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; ++i) sizes[i] = (int)rot_hist[i].size();
+        three_maxima(sizes, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx : rot_hist[i]) { assign[idx] = -2; --nmatches; }
+        }
+    }
+    return nmatches;
+}
+
 // ORBmatcher.cc:643-756
 int orc_search_for_initialization(const orc_frame_view *F1, const orc_frame_view *F2, float *prev_matched,
                                   int window_size, float nnratio, int check_ori, int32_t *matches12) {

@@ -157,6 +157,10 @@ int orc_search_by_projection_map_2cam(const orc_frame_view *FL, const orc_frame_
 int orc_search_by_projection_last(const orc_frame_view *Cur, const uint8_t *occupied, int n_last,
                                   const orc_proj_point *pts, const uint8_t *desc, float th, int mode, int check_ori,
                                   int32_t *assign);
+/* the same with a two-camera current frame (CurrentFrame.Nleft != -1), ORBmatcher.cc:1785-1852 */
+int orc_search_by_projection_last_2cam(const orc_frame_view *CurL, const orc_frame_view *CurR, const uint8_t *occupied,
+                                       int n_last, const orc_proj_point *pl, const orc_proj_point *pr, const uint8_t *desc,
+                                       float th, int mode, int check_ori, int32_t *assign);
 /* SearchForInitialization (ORBmatcher.cc:643-756). prev_matched: n1 x 2 floats, updated in place. */
 int orc_search_for_initialization(const orc_frame_view *F1, const orc_frame_view *F2, float *prev_matched,
                                   int window_size, float nnratio, int check_ori, int32_t *matches12);

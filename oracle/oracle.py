@@ -81,6 +81,7 @@ def lib():
         L.orc_get_features_in_area.argtypes = [vp, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, vp, C.c_int]
         L.orc_three_maxima.argtypes = [vp, C.c_int, i32p, i32p, i32p]
         L.orc_search_by_projection_map.argtypes = [vp, vp, C.c_int, vp, vp, C.c_float, C.c_int, C.c_float, C.c_float, vp]
+        L.orc_search_by_projection_last_2cam.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_float, C.c_int, C.c_int, vp]
         L.orc_search_by_projection_map_2cam.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, C.c_float, C.c_int, C.c_float,
                                                          C.c_float, vp]
         L.orc_search_by_projection_last.argtypes = [vp, vp, C.c_int, vp, vp, C.c_float, C.c_int, C.c_int, vp]
@@ -331,6 +332,15 @@ def search_by_projection_map_2cam(view_l, view_r, occupied, l2r, r2l, pts_l, pts
     nm = lib().orc_search_by_projection_map_2cam(C.addressof(view_l), C.addressof(view_r), _ptr(occupied), _ptr(l2r), _ptr(r2l),
                                                  len(pts_l), _ptr(pts_l), _ptr(pts_r), _ptr(mp_desc), th, int(far_points),
                                                  th_far, nnratio, _ptr(assign))
+    return nm, assign
+
+
+def search_by_projection_last_2cam(view_l, view_r, occupied, pts_l, pts_r, desc, th, mode, check_ori):
+    occupied = np.ascontiguousarray(occupied, np.uint8)
+    desc = np.ascontiguousarray(desc, np.uint8)
+    assign = np.zeros(view_l.n + view_r.n, np.int32)
+    nm = lib().orc_search_by_projection_last_2cam(C.addressof(view_l), C.addressof(view_r), _ptr(occupied), len(pts_l),
+                                                  _ptr(pts_l), _ptr(pts_r), _ptr(desc), th, mode, int(check_ori), _ptr(assign))
     return nm, assign
 
 

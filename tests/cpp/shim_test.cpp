@@ -152,6 +152,8 @@ struct Frame {
     float mfLogScaleFactor = std::log(1.2f);
     int mnScaleLevels = 8;
     Pose GetPose() const { return pose; }
+    Pose Trl;                                        // right-from-left camera transform of a two-camera rig
+    Pose GetRelativePoseTrl() const { return Trl; }
     std::vector<MapPoint *> GetMapPointMatches() const { return mvpMapPoints; }   // KeyFrame interface
 };
 struct KeyFrame : Frame {   // the members ORBmatcher reads from a KeyFrame (KeyFrame.h)
@@ -438,6 +440,71 @@ int main(int argc, char **argv) {
                 MapPoint *expect = assign[i] >= 0 ? Last.mvpMapPoints[assign[i]] : nullptr;
                 EXPECT(Cur.mvpMapPoints[i] == expect, "Cur.mvpMapPoints[%d]", i);
             }
+        }
+    }
+
+    // ---------------- SearchByProjection(Cur, Last) with a two-camera current frame ----------------
+    {
+        Frame Cur, Last = B;                       // Cur: left camera = A's keypoints, right camera = A's shifted by the baseline
+        Cur.Nleft = A.N;
+        Cur.mvKeys = A.mvKeys; Cur.mvKeysRight = A.mvKeys;
+        for (cv::KeyPoint &k : Cur.mvKeysRight) k.pt.x -= 12.f;
+        Cur.N = 2 * A.N;
+        Cur.mvScaleFactors = A.mvScaleFactors;
+        Cur.mDescriptors.create(Cur.N, 32, CV_8U);
+        for (int i = 0; i < A.N; ++i) { std::memcpy(Cur.mDescriptors.ptr(i), A.mDescriptors.ptr(i), 32); std::memcpy(Cur.mDescriptors.ptr(A.N + i), A.mDescriptors.ptr(i), 32); }
+        Cur.mpCamera = &Cur.cam; Last.mpCamera = &Last.cam;
+        Cur.pose = translation_pose(0.02f, -0.01f, -0.3f);
+        Cur.Trl = translation_pose(-0.06f, 0.f, 0.f);
+        Last.pose = translation_pose(0, 0, 0);
+        std::vector<MapPoint> store(Last.N);
+        std::vector<orc_proj_point> pl(Last.N), pr(Last.N);
+        std::vector<unsigned char> pdesc((size_t)Last.N * 32, 0);
+        for (int i = 0; i < Last.N; ++i) {
+            MapPoint &mp = store[i];
+            const float z = 2.5f;                  // -0.06 * 500 / 2.5 = -12 px: the right projection lands on the shifted keypoint
+            const float u = Last.mvKeys[i].pt.x - 9, v = Last.mvKeys[i].pt.y - 5;
+            const Vec3 xc{{(u - 320) * z / 500, (v - 240) * z / 500, z}};
+            mp.pos = xc - Cur.pose.t;
+            mp.obs = rng() % 10 < 9 ? 1 : 0;
+            mp.desc = Last.mDescriptors.row(i).clone();
+            Last.mvpMapPoints[i] = rng() % 10 < 8 ? &mp : nullptr;
+            Last.mvbOutlier[i] = rng() % 20 == 0;
+            std::memset(&pl[i], 0, sizeof(orc_proj_point)); std::memset(&pr[i], 0, sizeof(orc_proj_point));
+            if (!Last.mvpMapPoints[i] || Last.mvbOutlier[i]) continue;
+            const Vec3 x3Dc = Cur.pose * mp.pos;
+            const float invzc = 1.0 / x3Dc(2);
+            if (invzc < 0) continue;
+            const Vec2 uv = Cur.cam.project(x3Dc);
+            if (uv(0) < Cur.mnMinX || uv(0) > Cur.mnMaxX || uv(1) < Cur.mnMinY || uv(1) > Cur.mnMaxY) continue;
+            orc_proj_point &p = pl[i];
+            p.valid = 1; p.u = uv(0); p.v = uv(1); p.ur = uv(0) - Cur.mbf * invzc;
+            p.octave = Last.mvKeys[i].octave; p.angle = Last.mvKeysUn[i].angle; p.blocks = mp.obs > 0;
+            const Vec2 uvr = Cur.cam.project(Cur.Trl * x3Dc);
+            pr[i].u = uvr(0); pr[i].v = uvr(1);
+            std::memcpy(&pdesc[(size_t)i * 32], mp.desc.ptr(0), 32);
+        }
+        std::vector<unsigned char> dl, dr;
+        Frame camL = A, camR = A;
+        camR.mvKeys = Cur.mvKeysRight; camR.mvKeysUn = Cur.mvKeysRight;
+        orc_frame_view vl = view_of(camL, dl), vr = view_of(camR, dr);
+        vl.u_right = nullptr; vr.u_right = nullptr;
+        std::vector<unsigned char> occupied(Cur.N, 0);
+        std::vector<int32_t> assign(Cur.N);
+        for (bool mono : {true, false}) {
+            Cur.mvpMapPoints.assign(Cur.N, nullptr);
+            const int want = orc_search_by_projection_last_2cam(&vl, &vr, occupied.data(), Last.N, pl.data(), pr.data(), pdesc.data(), 15.f,
+                                                                mono ? 0 : 1, 1, assign.data());
+            VS_GRAPHS::ORBmatcher matcher(0.9f, true);
+            const int got = matcher.SearchByProjection(Cur, Last, 15.f, mono);
+            EXPECT(got == want && got > 100, "SearchByProjection(last, two cameras, mono=%d): %d vs %d", (int)mono, got, want);
+            int right_hits = 0;
+            for (int i = 0; i < Cur.N; ++i) {
+                MapPoint *expect = assign[i] >= 0 ? Last.mvpMapPoints[assign[i]] : nullptr;
+                EXPECT(Cur.mvpMapPoints[i] == expect, "two cameras: Cur.mvpMapPoints[%d]", i);
+                right_hits += i >= A.N && assign[i] >= 0;
+            }
+            EXPECT(right_hits > 30, "two cameras (last): right-camera matches %d", right_hits);
         }
     }
 

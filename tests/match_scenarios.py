@@ -190,3 +190,33 @@ def two_camera_scene(oracle, seed=61, size=(640, 480), nfeat=800):
     order = rng.permutation(n)
     return dict(fl=fl, fr=fr, pl=pl[order].copy(), pr=pr[order].copy(), desc=desc[order].copy(), l2r=l2r, r2l=r2l,
                 occupied=occupied)
+
+
+def two_camera_last_scene(oracle, seed=61, size=(640, 480), nfeat=800):
+    """SearchByProjection(Cur, Last) with a two-camera current frame: every last-frame point comes with its projection
+    into the left camera (near a left keypoint) and into the right camera (near a right keypoint or far off)."""
+    ka, da, kb, db = two_frames(oracle, seed=seed, size=size, nfeat=nfeat)
+    fl, fr = frame_data(ka, da, size=size), frame_data(kb, db, size=size)
+    rng = np.random.default_rng(seed + 11)
+    nl, nr = len(ka), len(kb)
+    n = nl + nr
+    src_l = np.concatenate([np.arange(nl), rng.integers(0, nl, nr)])
+    src_r = np.concatenate([rng.integers(0, nr, nl), np.arange(nr)])
+    pl, pr = np.zeros(n, PROJ_POINT_DTYPE), np.zeros(n, PROJ_POINT_DTYPE)
+    pl["u"] = ka["x"][src_l] + rng.normal(0, 1.0, n)
+    pl["v"] = ka["y"][src_l] + rng.normal(0, 1.0, n)
+    pr["u"] = kb["x"][src_r] + rng.normal(0, 1.0, n)
+    pr["v"] = kb["y"][src_r] + rng.normal(0, 1.0, n)
+    far = rng.random(n) < 0.1                                 # the right projection may land outside the image
+    pr["u"][far] += 900
+    lonely = rng.random(n) < 0.1                              # ... and the left window may be empty (skips the right search)
+    pl["u"][lonely] = -200
+    from_left = np.arange(n) < nl
+    pl["angle"] = np.where(from_left, ka["angle"][src_l], kb["angle"][src_r])
+    pl["octave"] = np.where(from_left, ka["octave"][src_l], kb["octave"][src_r])
+    pl["valid"] = rng.random(n) < 0.9
+    pl["blocks"] = rng.random(n) < 0.9
+    desc = np.where(from_left[:, None], da[src_l], db[src_r]).astype(np.uint8)
+    occupied = (rng.random(nl + nr) < 0.05).astype(np.uint8)
+    order = rng.permutation(n)
+    return dict(fl=fl, fr=fr, pl=pl[order].copy(), pr=pr[order].copy(), desc=desc[order].copy(), occupied=occupied)

@@ -100,6 +100,21 @@ def test_search_by_projection_last(oracle, mode, check_ori):
         assert (assign == -2).any() or mode != 0 or True
 
 
+@pytest.mark.parametrize("check_ori", [True, False])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_search_by_projection_last_two_cameras(oracle, mode, check_ori):
+    """CurrentFrame.Nleft != -1: the right-camera search of ORBmatcher.cc:1785-1852, skipped when the left window is empty."""
+    sc2 = sc.two_camera_last_scene(oracle)
+    m = _matcher(0.9, check_ori)
+    nm, assign = m.SearchByProjectionLast2Cam(m.frame(sc2["fl"]), m.frame(sc2["fr"]), sc2["occupied"], sc2["pl"], sc2["pr"],
+                                              sc2["desc"], 15.0, mode)
+    wnm, wassign = oracle.search_by_projection_last_2cam(sc2["fl"].view, sc2["fr"].view, sc2["occupied"], sc2["pl"], sc2["pr"],
+                                                         sc2["desc"], 15.0, mode, check_ori)
+    assert nm == wnm and np.array_equal(assign, wassign)
+    nl = sc2["fl"].n
+    assert (assign[:nl] >= 0).sum() > 100 and (assign[nl:] >= 0).sum() > 100
+
+
 @pytest.mark.parametrize("window", [10, 100])
 def test_search_for_initialization(oracle, window):
     ka, da, kb, db = sc.two_frames(oracle, nfeat=2000)

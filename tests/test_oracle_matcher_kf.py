@@ -280,3 +280,50 @@ def test_bow_kf_and_triangulation(oracle):
         wnm -= rot_filter(hist, drop)
         assert nm == wnm and np.array_equal(m12, want), (only_stereo, coarse)
         assert nm > 3
+
+
+def test_search_by_projection_last_two_cameras(oracle):
+    """ORBmatcher.cc:1667-1878 with CurrentFrame.Nleft != -1 against an independent restatement."""
+    from tests.test_oracle_matcher import py_features_in_area
+    sc2 = sc.two_camera_last_scene(oracle, size=(322, 243), nfeat=300)
+    fl, fr, pl, pr, desc = sc2["fl"], sc2["fr"], sc2["pl"], sc2["pr"], sc2["desc"]
+    nl = fl.n
+    for mode in (0, 1, 2):
+        for check_ori in (True, False):
+            blocked = sc2["occupied"].astype(bool).copy()
+            assign = np.full(fl.n + fr.n, -1, np.int32)
+            hist = [[] for _ in range(30)]
+            nm = 0
+            for i in range(len(pl)):
+                p = pl[i]
+                if not p["valid"]:
+                    continue
+                oct_ = int(p["octave"])
+                radius = f32(f32(15.0) * fl.scale_factors[oct_])
+                lo, hi = {0: (oct_ - 1, oct_ + 1), 1: (oct_, -1), 2: (0, oct_)}[mode]
+                cand = py_features_in_area(fl, p["u"], p["v"], radius, lo, hi)
+                if not cand:
+                    continue                                     # skips the right camera as well
+                for fd, cands, off in ((fl, cand, 0), (fr, None, nl)):
+                    if cands is None:
+                        cands = py_features_in_area(fr, pr[i]["u"], pr[i]["v"], radius, lo, hi)
+                    best, bi = 256, -1
+                    for i2 in cands:
+                        if blocked[i2 + off]:
+                            continue
+                        d = hamming(desc[i], fd.descriptors[i2])
+                        if d < best:
+                            best, bi = d, i2
+                    if best <= 100:
+                        assign[bi + off] = i
+                        blocked[bi + off] = bool(p["blocks"])
+                        nm += 1
+                        if check_ori:
+                            hist[py_rot_bin(p["angle"], fd.keys[bi]["angle"])].append(bi + off)
+            if check_ori:
+                def drop(idx):
+                    assign[idx] = -2
+                nm -= rot_filter(hist, drop)
+            got_nm, got = oracle.search_by_projection_last_2cam(fl.view, fr.view, sc2["occupied"], pl, pr, desc, 15.0, mode, check_ori)
+            assert got_nm == nm and np.array_equal(got, assign)
+            assert (assign[:nl] >= 0).sum() > 20 and (assign[nl:] >= 0).sum() > 20

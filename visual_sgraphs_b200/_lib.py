@@ -93,6 +93,8 @@ _SIGNATURES = {
     "vsg_frame_create": (C.c_int, [C.c_void_p, C.POINTER(FrameView), C.POINTER(C.c_void_p)]),
     "vsg_frame_destroy": (None, [C.c_void_p]),
     "vsg_area_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 9 + [C.c_int, C.POINTER(C.c_int)]),
+    "vsg_search_by_projection_last_2cam": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                                                     C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
     "vsg_search_by_projection_map_2cam": (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
                                                     C.c_int, C.c_float, C.c_float, C.c_void_p, C.POINTER(C.c_int)]),
     "vsg_search_by_projection_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,

@@ -649,6 +649,81 @@ vsg_status vsg_search_by_projection_last(vsg_matcher *m, const vsg_frame *Cur, c
     return VSG_OK;
 }
 
+// ORBmatcher.cc:1667-1878 with a two-camera current frame (CurrentFrame.Nleft != -1): per last-frame point the left-camera
+// search (:1709-1784) and — unless the left window was empty, whose `continue` (:1727-1728) skips it — the right-camera
+// search around its projection through mTrl (:1785-1852).
+vsg_status vsg_search_by_projection_last_2cam(vsg_matcher *m, const vsg_frame *CurL, const vsg_frame *CurR,
+                                              const uint8_t *occupied, int n_last, const vsg_proj_point *pts_left,
+                                              const vsg_proj_point *pts_right, const uint8_t *desc, float th, int mode,
+                                              int check_ori, int32_t *assign_out, int *nmatches_out) {
+    if (!m || !CurL || !CurR || n_last < 0 || !assign_out || (n_last > 0 && (!pts_left || !pts_right || !desc)) ||
+        (CurL->n + CurR->n > 0 && !occupied))
+        return VSG_ERR_INVALID;
+    if (CurL->has_right || CurR->has_right) {
+        set_error("vsg_search_by_projection_last_2cam: the per-camera frames of a two-camera rig carry no uRight");
+        return VSG_ERR_INVALID;
+    }
+    CK(cudaSetDevice(m->device));
+    const int nL = CurL->n, N = CurL->n + CurR->n, nlev = (int)CurL->scale.size();
+    std::vector<AreaQuery> qs[2];
+    std::vector<int> q_src;
+    for (int i = 0; i < n_last; ++i) {
+        const vsg_proj_point &p = pts_left[i];
+        if (!p.valid) continue;
+        if (p.octave < 0 || p.octave >= nlev) { set_error("point %d: octave %d out of range", i, p.octave); return VSG_ERR_INVALID; }
+        const float radius = th * CurL->scale[p.octave];
+        int lo, hi;
+        if (mode == 1) { lo = p.octave; hi = -1; }
+        else if (mode == 2) { lo = 0; hi = p.octave; }
+        else { lo = p.octave - 1; hi = p.octave + 1; }
+        qs[0].push_back(AreaQuery{p.u, p.v, radius, lo, hi, 0.f, radius, 256, (int)q_src.size()});
+        qs[1].push_back(AreaQuery{pts_right[i].u, pts_right[i].v, radius, lo, hi, 0.f, radius, 256, (int)q_src.size()});
+        q_src.push_back(i);
+    }
+    const int nq = (int)q_src.size();
+    std::vector<uint8_t> qdesc((size_t)std::max(nq, 1) * 32);
+    for (int k = 0; k < nq; ++k) memcpy(&qdesc[(size_t)k * 32], desc + (size_t)q_src[k] * 32, 32);
+    std::vector<int> ptr[2];
+    std::vector<int2> ent[2];
+    vsg_status st;
+    if ((st = area_search(m, CurL, nq, qs[0].data(), qdesc.data(), ptr[0], ent[0])) != VSG_OK) return st;
+    if ((st = area_search(m, CurR, nq, qs[1].data(), qdesc.data(), ptr[1], ent[1])) != VSG_OK) return st;
+    std::vector<uint8_t> blocked(occupied, occupied + N);
+    for (int i = 0; i < N; ++i) assign_out[i] = -1;
+    std::vector<int> rot_hist[HISTO_LENGTH];
+    int nmatches = 0;
+    for (int k = 0; k < nq; ++k) {
+        const vsg_proj_point &p = pts_left[q_src[k]];
+        if (ptr[0][k] == ptr[0][k + 1]) continue;                  // vIndices2.empty() -> continue: no right-camera search either
+        for (int cam = 0; cam < 2; ++cam) {
+            const vsg_frame *F = cam == 0 ? CurL : CurR;
+            const int offset = cam == 0 ? 0 : nL;
+            int best = 256, best_idx = -1;
+            for (int c = ptr[cam][k]; c < ptr[cam][k + 1]; ++c) {
+                const int i2 = ent[cam][c].x, dist = ent[cam][c].y;
+                if (blocked[i2 + offset]) continue;
+                if (dist < best) { best = dist; best_idx = i2; }
+            }
+            if (best <= TH_HIGH) {
+                assign_out[best_idx + offset] = q_src[k];
+                blocked[best_idx + offset] = p.blocks;
+                ++nmatches;
+                if (check_ori) rot_hist[rot_bin(p.angle, F->keys[best_idx].angle)].push_back(best_idx + offset);
+            }
+        }
+    }
+    if (check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rot_hist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx : rot_hist[i]) { assign_out[idx] = -2; --nmatches; }
+        }
+    }
+    if (nmatches_out) *nmatches_out = nmatches;
+    return VSG_OK;
+}
+
 // ORBmatcher.cc:643-756
 vsg_status vsg_search_for_initialization(vsg_matcher *m, const vsg_frame_view *F1, const vsg_frame *F2,
                                          float *prev_matched, int window_size, float nnratio, int check_ori,

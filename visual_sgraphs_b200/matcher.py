@@ -208,6 +208,21 @@ class ORBmatcher:
                                                     C.byref(nm)))
         return nm.value, assign
 
+    def SearchByProjectionLast2Cam(self, cur_l, cur_r, occupied, pts_left, pts_right, desc, th, mode=0):
+        """The same with a two-camera current frame (CurrentFrame.Nleft != -1; ORBmatcher.cc:1667-1878 incl. :1785-1852):
+        pts_right carries the projections into the right camera (u, v). Returns (nmatches, assign[Nleft + Nright])."""
+        pl = np.ascontiguousarray(pts_left, PROJ_POINT_DTYPE)
+        pr = np.ascontiguousarray(pts_right, PROJ_POINT_DTYPE)
+        assert len(pl) == len(pr)
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        occupied = np.ascontiguousarray(occupied, np.uint8)
+        assign = np.zeros(cur_l.data.n + cur_r.data.n, np.int32)
+        nm = C.c_int(0)
+        check(self._L.vsg_search_by_projection_last_2cam(self._h, cur_l._h, cur_r._h, ptr(occupied), len(pl), ptr(pl), ptr(pr),
+                                                         ptr(desc), float(th), int(mode), int(self.mbCheckOrientation),
+                                                         ptr(assign), C.byref(nm)))
+        return nm.value, assign
+
     def SearchForInitialization(self, f1_data, f2_frame, prev_matched, windowSize=10):
         """ORBmatcher.cc:643-756. prev_matched (n1, 2) float32 is updated in place. Returns (nmatches, matches12)."""
         assert prev_matched.dtype == np.float32 and prev_matched.flags["C_CONTIGUOUS"]

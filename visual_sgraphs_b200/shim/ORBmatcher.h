@@ -12,8 +12,9 @@
 // Each template flattens those members into the C ABI's view structs, calls the library and writes the
 // results back exactly where the reference does.
 //
-// Scope: single-camera frames (Frame::Nleft == -1), plus the two-camera branch (Nleft != -1, stereo-fisheye rigs) of
-// SearchByProjection(Frame&, vector<MapPoint*>&).  The other methods throw for two-camera frames — keep the reference's
+// Scope: single-camera frames (Frame::Nleft == -1), plus the two-camera branches (Nleft != -1, stereo-fisheye rigs) of the
+// two per-frame tracking calls SearchByProjection(Frame&, vector<MapPoint*>&) and SearchByProjection(Frame&, const Frame&).
+// The other methods throw for two-camera frames — keep the reference's
 // CPU ORBmatcher for them in that configuration.
 #ifndef VSG_SHIM_ORBMATCHER_H
 #define VSG_SHIM_ORBMATCHER_H
@@ -203,6 +204,30 @@ protected:
         p.level = pMP->PredictScale(dist, pKF);
         return true;
     }
+    // The two cameras of a two-camera frame as separate frames: mvKeys + descriptor rows [0, Nleft) and mvKeysRight +
+    // rows [Nleft, N), the layout Frame::GetFeaturesInArea(..., bRight) works on (Frame.cc:840-848).
+    template <class FrameT>
+    void UploadCameras(const FrameT &F, Flat cam[2], FrameGuard fr[2]) {
+        static_assert(sizeof(cv::KeyPoint) == sizeof(vsg_keypoint), "cv::KeyPoint layout");
+        const int nL = F.Nleft, nR = (int)F.mvKeysRight.size();
+        for (int c = 0; c < 2; ++c) {
+            Flat &o = cam[c];
+            const std::vector<cv::KeyPoint> &keys = c == 0 ? F.mvKeys : F.mvKeysRight;
+            const int n = c == 0 ? nL : nR, row0 = c == 0 ? 0 : nL;
+            o.keys.resize(n);
+            if (n) std::memcpy(o.keys.data(), keys.data(), (size_t)n * sizeof(vsg_keypoint));
+            o.desc.resize((size_t)n * 32);
+            for (int i = 0; i < n; ++i) std::memcpy(&o.desc[(size_t)i * 32], F.mDescriptors.ptr(row0 + i), 32);
+            o.scale.assign(F.mvScaleFactors.begin(), F.mvScaleFactors.end());
+            vsg_frame_view &v = o.view;
+            v.n = n; v.keys = o.keys.data(); v.descriptors = o.desc.data(); v.u_right = nullptr;
+            v.min_x = F.mnMinX; v.min_y = F.mnMinY; v.max_x = F.mnMaxX; v.max_y = F.mnMaxY;
+            v.grid_inv_w = F.mfGridElementWidthInv; v.grid_inv_h = F.mfGridElementHeightInv;
+            v.grid_cols = FRAME_GRID_COLS; v.grid_rows = FRAME_GRID_ROWS;
+            v.scale_factors = o.scale.data(); v.n_levels = (int)o.scale.size();
+            Check(vsg_frame_create(Workspace(), &v, &fr[c].h), "vsg_frame_create");
+        }
+    }
     template <class FrameT>
     static void RequireSingleCamera(const FrameT &F) {
         if (F.Nleft != -1)
@@ -216,27 +241,10 @@ protected:
 template <class FrameT, class MapPointT>
 int ORBmatcher::SearchByProjectionTwoCameras(FrameT &F, const std::vector<MapPointT *> &vpMapPoints, const float th,
                                              const bool bFarPoints, const float thFarPoints) {
-    static_assert(sizeof(cv::KeyPoint) == sizeof(vsg_keypoint), "cv::KeyPoint layout");
     const int nL = F.Nleft, nR = (int)F.mvKeysRight.size(), N = nL + nR, nMP = (int)vpMapPoints.size();
     Flat cam[2];
     FrameGuard fr[2];
-    for (int c = 0; c < 2; ++c) {
-        Flat &o = cam[c];
-        const std::vector<cv::KeyPoint> &keys = c == 0 ? F.mvKeys : F.mvKeysRight;     // Frame.cc:846-848
-        const int n = c == 0 ? nL : nR, row0 = c == 0 ? 0 : nL;
-        o.keys.resize(n);
-        if (n) std::memcpy(o.keys.data(), keys.data(), (size_t)n * sizeof(vsg_keypoint));
-        o.desc.resize((size_t)n * 32);
-        for (int i = 0; i < n; ++i) std::memcpy(&o.desc[(size_t)i * 32], F.mDescriptors.ptr(row0 + i), 32);
-        o.scale.assign(F.mvScaleFactors.begin(), F.mvScaleFactors.end());
-        vsg_frame_view &v = o.view;
-        v.n = n; v.keys = o.keys.data(); v.descriptors = o.desc.data(); v.u_right = nullptr;
-        v.min_x = F.mnMinX; v.min_y = F.mnMinY; v.max_x = F.mnMaxX; v.max_y = F.mnMaxY;
-        v.grid_inv_w = F.mfGridElementWidthInv; v.grid_inv_h = F.mfGridElementHeightInv;
-        v.grid_cols = FRAME_GRID_COLS; v.grid_rows = FRAME_GRID_ROWS;
-        v.scale_factors = o.scale.data(); v.n_levels = (int)o.scale.size();
-        Check(vsg_frame_create(Workspace(), &v, &fr[c].h), "vsg_frame_create");
-    }
+    UploadCameras(F, cam, fr);
     std::vector<uint8_t> occupied(N, 0);
     for (int i = 0; i < N; ++i)
         if (F.mvpMapPoints[i] && F.mvpMapPoints[i]->Observations() > 0) occupied[i] = 1;
@@ -312,12 +320,15 @@ int ORBmatcher::SearchByProjection(FrameT &F, const std::vector<MapPointT *> &vp
 
 template <class FrameT>
 int ORBmatcher::SearchByProjection(FrameT &CurrentFrame, const FrameT &LastFrame, const float th, const bool bMono) {
-    RequireSingleCamera(CurrentFrame);
-    RequireSingleCamera(LastFrame);
-    Flat flat;
-    Flatten(CurrentFrame, flat);
-    FrameGuard fr;
-    Check(vsg_frame_create(Workspace(), &flat.view, &fr.h), "vsg_frame_create");
+    const bool bTwoCameras = CurrentFrame.Nleft != -1;
+    Flat flat, cam[2];
+    FrameGuard fr, frc[2];
+    if (bTwoCameras) {
+        UploadCameras(CurrentFrame, cam, frc);
+    } else {
+        Flatten(CurrentFrame, flat);
+        Check(vsg_frame_create(Workspace(), &flat.view, &fr.h), "vsg_frame_create");
+    }
     // pose arithmetic stays with the reference's Sophus / camera classes (:1677-1716)
     const auto Tcw = CurrentFrame.GetPose();
     const auto twc = Tcw.inverse().translation();
@@ -325,12 +336,13 @@ int ORBmatcher::SearchByProjection(FrameT &CurrentFrame, const FrameT &LastFrame
     const auto tlc = Tlw * twc;
     const bool bForward = tlc(2) > CurrentFrame.mb && !bMono;
     const bool bBackward = -tlc(2) > CurrentFrame.mb && !bMono;
-    const int nLast = LastFrame.N, N = flat.view.n;
-    std::vector<vsg_proj_point> pts(nLast);
+    const int nLast = LastFrame.N, N = bTwoCameras ? cam[0].view.n + cam[1].view.n : flat.view.n;
+    std::vector<vsg_proj_point> pts(nLast), ptsR(bTwoCameras ? nLast : 0);
     std::vector<uint8_t> desc((size_t)nLast * 32, 0);
     for (int i = 0; i < nLast; ++i) {
         vsg_proj_point &p = pts[i];
         std::memset(&p, 0, sizeof(p));
+        if (bTwoCameras) std::memset(&ptsR[i], 0, sizeof(vsg_proj_point));
         auto *pMP = LastFrame.mvpMapPoints[i];
         if (!pMP || LastFrame.mvbOutlier[i]) continue;
         const auto x3Dw = pMP->GetWorldPos();
@@ -343,9 +355,18 @@ int ORBmatcher::SearchByProjection(FrameT &CurrentFrame, const FrameT &LastFrame
         p.valid = 1;
         p.u = uv(0); p.v = uv(1);
         p.ur = uv(0) - CurrentFrame.mbf * invzc;                                           // :1747
-        p.octave = LastFrame.mvKeys[i].octave;
-        p.angle = LastFrame.mvKeysUn[i].angle;
+        // last-frame keypoint by camera (:1711-1712, :1768-1770)
+        const bool lastLeft = LastFrame.Nleft == -1 || i < LastFrame.Nleft;
+        p.octave = lastLeft ? LastFrame.mvKeys[i].octave : LastFrame.mvKeysRight[i - LastFrame.Nleft].octave;
+        p.angle = LastFrame.Nleft == -1 ? LastFrame.mvKeysUn[i].angle
+                  : lastLeft            ? LastFrame.mvKeys[i].angle
+                                        : LastFrame.mvKeysRight[i - LastFrame.Nleft].angle;
         p.blocks = pMP->Observations() > 0 ? 1 : 0;
+        if (bTwoCameras) {                                                                 // :1787-1788
+            const auto x3Dr = CurrentFrame.GetRelativePoseTrl() * x3Dc;
+            const auto uvr = CurrentFrame.mpCamera->project(x3Dr);
+            ptsR[i].u = uvr(0); ptsR[i].v = uvr(1);
+        }
         const cv::Mat d = pMP->GetDescriptor();
         std::memcpy(&desc[(size_t)i * 32], d.ptr(0), 32);
     }
@@ -354,9 +375,15 @@ int ORBmatcher::SearchByProjection(FrameT &CurrentFrame, const FrameT &LastFrame
         if (CurrentFrame.mvpMapPoints[i] && CurrentFrame.mvpMapPoints[i]->Observations() > 0) occupied[i] = 1;
     std::vector<int32_t> assign(N, -1);
     int nmatches = 0;
-    Check(vsg_search_by_projection_last(Workspace(), fr.h, occupied.data(), nLast, pts.data(), desc.data(), th,
-                                        bForward ? 1 : (bBackward ? 2 : 0), mbCheckOrientation ? 1 : 0, assign.data(),
-                                        &nmatches), "vsg_search_by_projection_last");
+    const int mode = bForward ? 1 : (bBackward ? 2 : 0);
+    if (bTwoCameras)
+        Check(vsg_search_by_projection_last_2cam(Workspace(), frc[0].h, frc[1].h, occupied.data(), nLast, pts.data(), ptsR.data(),
+                                                 desc.data(), th, mode, mbCheckOrientation ? 1 : 0, assign.data(), &nmatches),
+              "vsg_search_by_projection_last_2cam");
+    else
+        Check(vsg_search_by_projection_last(Workspace(), fr.h, occupied.data(), nLast, pts.data(), desc.data(), th, mode,
+                                            mbCheckOrientation ? 1 : 0, assign.data(), &nmatches),
+              "vsg_search_by_projection_last");
     for (int i = 0; i < N; ++i) {
         if (assign[i] >= 0) CurrentFrame.mvpMapPoints[i] = LastFrame.mvpMapPoints[assign[i]];   // :1763
         else if (assign[i] == -2) CurrentFrame.mvpMapPoints[i] = nullptr;                     // :1870
