@@ -37,7 +37,7 @@ if os.path.exists(launch_csv):
     with open(os.path.join(out_dir, "%s_launches.md" % tag), "w") as f:
         f.write("# ncu launch list summary (%s)\n\n" % tag)
         f.write("Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py "
-                "--steps 1 --warmup 1 --batch 64 --no-extras` (per-launch times are cold-cache and serialised: "
+                "--steps 2 --warmup 1 --no-extras` (512 frames per device-resident launch, 128 per launch in the end-to-end part; per-launch times are cold-cache and serialised: "
                 "compare SHARES).\n\n| kernel | launches | total us | share |\n|---|---:|---:|---:|\n")
         for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write("| %s | %d | %.1f | %.1f%% |\n" % (k, n, us, 100 * us / total))
