@@ -350,6 +350,27 @@ def matching_extras(torch, device):
                      "popc_per_s": 8 * pairs / (ms * 1e-3),
                      "roofline": {"bound": "popc (xu pipe)", "achieved": 8 * pairs / (ms * 1e-3), "peak": peak,
                                   "unit": "POPC/s", "frac": 8 * pairs / (ms * 1e-3) / peak}}
+    # CPU baseline beside it: the reference's brute-force loop with its bit-hack DescriptorDistance
+    # (ORBmatcher.cc:2047-2063) and a __builtin_popcountll variant, built with the reference's flags (-O3, no -march),
+    # all host threads, bounded sample; the GPU result on the same sample must be identical
+    from oracle import oracle as orc
+    cores = host_threads()
+    nq, nt = 512, 200_000
+    q = torch.randint(0, 256, (nq, 32), dtype=torch.uint8, device="cuda", generator=g)
+    t = torch.randint(0, 256, (nt, 32), dtype=torch.uint8, device="cuda", generator=g)
+    idx = torch.zeros((nq, 2), dtype=torch.int32, device="cuda")
+    dist = torch.zeros((nq, 2), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    m.knn2_dev(q, t, idx, dist)
+    m.sync()
+    qh, th = q.cpu().numpy(), t.cpu().numpy()
+    cpu = {}
+    for variant, label in ((0, "bit_hack"), (1, "popcountll")):
+        secs, ci, cd = orc.bench_knn2(qh, th, cores, variant)
+        assert np.array_equal(ci, idx.cpu().numpy()) and np.array_equal(cd, dist.cpu().numpy())
+        cpu[label + "_pairs_per_s"] = nq * nt / secs
+    cpu.update({"cores": cores, "kind": "port", "sample": "%d x %d descriptors, %d threads" % (nq, nt, cores)})
+    out["cpu_baseline"] = cpu
     m.close()
     return out
 

@@ -11,6 +11,8 @@
 #include <climits>
 #include <cmath>
 #include <cstring>
+#include <chrono>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -102,6 +104,42 @@ int rot_bin(float a1, float a2) {
 extern "C" {
 
 int orc_descriptor_distance(const uint8_t *a, const uint8_t *b) { return descriptor_distance(a, b); }
+
+// Brute-force kNN-2 on the host cores (cv::BFMatcher(NORM_HAMMING).knnMatch(k = 2), Frame.cc:43,1200): the CPU baseline of
+// the matching benchmark.  variant 0: the reference's bit-hack DescriptorDistance (ORBmatcher.cc:2047-2063);
+// variant 1: the same loop with __builtin_popcountll, labelled as such.  Ties -> lower train index first.  Returns seconds.
+double orc_bench_knn2(const uint8_t *query, int nq, const uint8_t *train, int nt, int threads, int variant, int32_t *idx_out,
+                      int32_t *dist_out) {
+    if (threads < 1) threads = 1;
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> pool;
+    for (int tid = 0; tid < threads; ++tid) {
+        pool.emplace_back([=]() {
+            for (int q = tid; q < nq; q += threads) {
+                const uint8_t *a = query + (size_t)q * 32;
+                int b0 = 257, b1 = 257, i0 = -1, i1 = -1;
+                for (int t = 0; t < nt; ++t) {
+                    const uint8_t *b = train + (size_t)t * 32;
+                    int d;
+                    if (variant == 0) {
+                        d = descriptor_distance(a, b);
+                    } else {
+                        uint64_t wa[4], wb[4];
+                        std::memcpy(wa, a, 32); std::memcpy(wb, b, 32);
+                        d = __builtin_popcountll(wa[0] ^ wb[0]) + __builtin_popcountll(wa[1] ^ wb[1]) +
+                            __builtin_popcountll(wa[2] ^ wb[2]) + __builtin_popcountll(wa[3] ^ wb[3]);
+                    }
+                    if (d < b0) { b1 = b0; i1 = i0; b0 = d; i0 = t; }
+                    else if (d < b1) { b1 = d; i1 = t; }
+                }
+                if (idx_out) { idx_out[2 * q] = i0; idx_out[2 * q + 1] = i1; }
+                if (dist_out) { dist_out[2 * q] = i0 >= 0 ? b0 : -1; dist_out[2 * q + 1] = i1 >= 0 ? b1 : -1; }
+            }
+        });
+    }
+    for (auto &th : pool) th.join();
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
 
 int orc_get_features_in_area(const orc_frame_view *f, float x, float y, float r, int min_level, int max_level,
                              int32_t *out, int cap) {

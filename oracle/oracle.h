@@ -96,6 +96,10 @@ void orc_stereo_from_rgbd(int n, const float *xy, const float *xy_un, const floa
 
 /* ---- matcher arithmetic (ORBmatcher.cc) on flattened views ---- */
 int orc_descriptor_distance(const uint8_t *a, const uint8_t *b);
+/* CPU baseline of the brute-force kNN-2 (knnMatch k = 2): variant 0 = the reference's bit-hack distance, 1 = popcount
+ * instructions; all `threads` host threads; returns seconds, fills idx / dist (nq x 2) when non-null */
+double orc_bench_knn2(const uint8_t *query, int nq, const uint8_t *train, int nt, int threads, int variant, int32_t *idx_out,
+                      int32_t *dist_out);
 
 /* What the Search* methods read from a Frame / KeyFrame (Frame.h:254-290,363-381). Layout-identical to
  * vsg_frame_view in include/vsg_cuda.h so tests can hand the same buffers to both. */

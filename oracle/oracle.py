@@ -81,6 +81,8 @@ def lib():
         L.orc_get_features_in_area.argtypes = [vp, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, vp, C.c_int]
         L.orc_three_maxima.argtypes = [vp, C.c_int, i32p, i32p, i32p]
         L.orc_search_by_projection_map.argtypes = [vp, vp, C.c_int, vp, vp, C.c_float, C.c_int, C.c_float, C.c_float, vp]
+        L.orc_bench_knn2.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp]
+        L.orc_bench_knn2.restype = C.c_double
         L.orc_search_by_projection_last_2cam.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_float, C.c_int, C.c_int, vp]
         L.orc_search_by_projection_map_2cam.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, C.c_float, C.c_int, C.c_float,
                                                          C.c_float, vp]
@@ -285,6 +287,16 @@ def descriptor_distance(a, b):
     a = np.ascontiguousarray(a, np.uint8)
     b = np.ascontiguousarray(b, np.uint8)
     return lib().orc_descriptor_distance(_ptr(a), _ptr(b))
+
+
+def bench_knn2(query, train, threads=1, variant=0):
+    """CPU brute-force kNN-2 (seconds, idx (nq, 2), dist (nq, 2)); variant 0 = bit-hack distance, 1 = popcount."""
+    query = np.ascontiguousarray(query, np.uint8)
+    train = np.ascontiguousarray(train, np.uint8)
+    idx = np.zeros((len(query), 2), np.int32)
+    dist = np.zeros((len(query), 2), np.int32)
+    secs = lib().orc_bench_knn2(_ptr(query), len(query), _ptr(train), len(train), threads, variant, _ptr(idx), _ptr(dist))
+    return secs, idx, dist
 
 
 def bench_extract(frames, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, threads=1):

@@ -239,3 +239,20 @@ def test_bow_tree_walk_matches_python_restatement(oracle):
                 if lvl == voc["levels"] - levelsup:
                     want_nid = node
             assert leaf[f] == node and nid[f] == want_nid, (levelsup, f)
+
+
+def test_cpu_knn2_baseline_matches_numpy(oracle):
+    """The CPU baseline of the brute-force matcher (both distance variants, threaded) is the lexicographic (dist, idx)
+    top-2 cv::BFMatcher::knnMatch returns."""
+    from visual_sgraphs_b200.synth import synth_query_train
+    q, t = synth_query_train(9, 60, 900)
+    t[100] = t[7]                                           # exact ties between train rows
+    d = np.unpackbits(q[:, None, :] ^ t[None, :, :], axis=2).sum(2).astype(np.int64)
+    order = np.lexsort((np.broadcast_to(np.arange(t.shape[0]), d.shape), d), axis=1)[:, :2]
+    for variant in (0, 1):
+        for threads in (1, 3):
+            _, idx, dist = oracle.bench_knn2(q, t, threads, variant)
+            assert np.array_equal(idx, order)
+            assert np.array_equal(dist, np.take_along_axis(d, order, 1))
+    _, idx, dist = oracle.bench_knn2(q, t[:1], 2, 0)        # a single train row: no second neighbour
+    assert (idx[:, 1] == -1).all() and (dist[:, 1] == -1).all() and (idx[:, 0] == 0).all()
