@@ -320,6 +320,15 @@ vsg_status vsg_search_by_bow(vsg_matcher *m, const vsg_frame_view *KF, const uin
                              const int32_t *f_idx, float nnratio, int check_ori, int32_t *matches_f_out,
                              int *nmatches_out);
 
+/* The same with a two-camera frame (F.Nleft = f_nleft != -1; ORBmatcher.cc:298-322, :362-390): F (and KF, if it has a
+ * second camera) list the left camera's keypoints / descriptor rows first, then the right camera's, as mDescriptors does;
+ * best and second-best are kept per camera.  f_nleft == -1 is vsg_search_by_bow. */
+vsg_status vsg_search_by_bow_2cam(vsg_matcher *m, const vsg_frame_view *KF, const uint8_t *kf_mp_valid,
+                                  const vsg_frame_view *F, int f_nleft, int kf_nnodes, const int32_t *kf_nodes,
+                                  const int32_t *kf_ptr, const int32_t *kf_idx, int f_nnodes, const int32_t *f_nodes,
+                                  const int32_t *f_ptr, const int32_t *f_idx, float nnratio, int check_ori,
+                                  int32_t *matches_f_out, int *nmatches_out);
+
 /* A map point already projected into the searched Frame / KeyFrame by the caller: the pose, Sim3 and
  * camera-model arithmetic ahead of GetFeaturesInArea (e.g. ORBmatcher.cc:444-486, 1182-1238, 1904-1929) stays
  * with the reference's Sophus / GeometricCamera classes; everything from the window query on runs here. */

@@ -450,6 +450,16 @@ int orc_search_by_bow(const orc_frame_view *KF, const uint8_t *kf_mp_valid, cons
                       const int32_t *kf_nodes, const int32_t *kf_ptr, const int32_t *kf_idx, int f_nnodes,
                       const int32_t *f_nodes, const int32_t *f_ptr, const int32_t *f_idx, float nnratio, int check_ori,
                       int32_t *matches_f) {
+    return orc_search_by_bow_2cam(KF, kf_mp_valid, F, -1, kf_nnodes, kf_nodes, kf_ptr, kf_idx, f_nnodes, f_nodes, f_ptr, f_idx,
+                                  nnratio, check_ori, matches_f);
+}
+
+// ORBmatcher.cc:226-428 incl. the F.Nleft != -1 branch (:298-322, :362-390): keys / descriptors of F are the left
+// camera's [0, f_nleft) followed by the right camera's; f_nleft == -1 is the single-camera method.
+int orc_search_by_bow_2cam(const orc_frame_view *KF, const uint8_t *kf_mp_valid, const orc_frame_view *F, int f_nleft,
+                           int kf_nnodes, const int32_t *kf_nodes, const int32_t *kf_ptr, const int32_t *kf_idx, int f_nnodes,
+                           const int32_t *f_nodes, const int32_t *f_ptr, const int32_t *f_idx, float nnratio, int check_ori,
+                           int32_t *matches_f) {
     for (int i = 0; i < F->n; ++i) matches_f[i] = -1;
     int nmatches = 0;
     std::vector<int> rot_hist[HISTO_LENGTH];
@@ -461,18 +471,33 @@ int orc_search_by_bow(const orc_frame_view *KF, const uint8_t *kf_mp_valid, cons
                 if (!kf_mp_valid[real_kf]) continue;
                 const uint8_t *d_kf = KF->descriptors + (size_t)real_kf * 32;
                 int best1 = 256, best_idx_f = -1, best2 = 256;
+                int best1r = 256, best_idx_fr = -1, best2r = 256;
                 for (int jf = f_ptr[b]; jf < f_ptr[b + 1]; ++jf) {
                     const int real_f = f_idx[jf];
                     if (matches_f[real_f] >= 0) continue;
                     const int dist = descriptor_distance(d_kf, F->descriptors + (size_t)real_f * 32);
-                    if (dist < best1) { best2 = best1; best1 = dist; best_idx_f = real_f; }
-                    else if (dist < best2) best2 = dist;
+                    if (f_nleft == -1) {
+                        if (dist < best1) { best2 = best1; best1 = dist; best_idx_f = real_f; }
+                        else if (dist < best2) best2 = dist;
+                    } else {
+                        if (real_f < f_nleft && dist < best1) { best2 = best1; best1 = dist; best_idx_f = real_f; }
+                        else if (real_f < f_nleft && dist < best2) best2 = dist;
+                        if (real_f >= f_nleft && dist < best1r) { best2r = best1r; best1r = dist; best_idx_fr = real_f; }
+                        else if (real_f >= f_nleft && dist < best2r) best2r = dist;
+                    }
                 }
                 if (best1 <= TH_LOW) {
                     if (static_cast<float>(best1) < nnratio * static_cast<float>(best2)) {
                         matches_f[best_idx_f] = real_kf;
                         if (check_ori) rot_hist[rot_bin(KF->keys[real_kf].angle, F->keys[best_idx_f].angle)].push_back(best_idx_f);
                         ++nmatches;
+                    }
+                    if (best1r <= TH_LOW) {
+                        if (static_cast<float>(best1r) < nnratio * static_cast<float>(best2r) || true) {
+                            matches_f[best_idx_fr] = real_kf;
+                            if (check_ori) rot_hist[rot_bin(KF->keys[real_kf].angle, F->keys[best_idx_fr].angle)].push_back(best_idx_fr);
+                            ++nmatches;
+                        }
                     }
                 }
             }

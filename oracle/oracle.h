@@ -175,6 +175,11 @@ int orc_search_by_bow(const orc_frame_view *KF, const uint8_t *kf_mp_valid, cons
                       const int32_t *kf_nodes, const int32_t *kf_ptr, const int32_t *kf_idx, int f_nnodes,
                       const int32_t *f_nodes, const int32_t *f_ptr, const int32_t *f_idx, float nnratio, int check_ori,
                       int32_t *matches_f);
+/* the same with a two-camera frame: F's features [0, f_nleft) belong to the left camera (f_nleft == -1: single camera) */
+int orc_search_by_bow_2cam(const orc_frame_view *KF, const uint8_t *kf_mp_valid, const orc_frame_view *F, int f_nleft,
+                           int kf_nnodes, const int32_t *kf_nodes, const int32_t *kf_ptr, const int32_t *kf_idx, int f_nnodes,
+                           const int32_t *f_nodes, const int32_t *f_ptr, const int32_t *f_idx, float nnratio, int check_ori,
+                           int32_t *matches_f);
 
 /* A map point already projected into the searched Frame / KeyFrame (layout-identical to vsg_search_point). */
 typedef struct orc_search_point {

@@ -89,6 +89,7 @@ def lib():
         L.orc_search_by_projection_last.argtypes = [vp, vp, C.c_int, vp, vp, C.c_float, C.c_int, C.c_int, vp]
         L.orc_search_for_initialization.argtypes = [vp, vp, vp, C.c_int, C.c_float, C.c_int, vp]
         L.orc_search_by_bow.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, C.c_float, C.c_int, vp]
+        L.orc_search_by_bow_2cam.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, C.c_float, C.c_int, vp]
         L.orc_search_by_projection_reloc.argtypes = [vp, vp, C.c_int, vp, vp, C.c_float, C.c_int, C.c_int, vp]
         L.orc_search_by_projection_sim3.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, C.c_float, vp]
         L.orc_fuse_search.argtypes = [vp, C.c_int, vp, vp, C.c_float, vp, C.c_int, vp]
@@ -372,13 +373,15 @@ def search_for_initialization(view1, view2, prev_matched, window, nnratio, check
     return nm, m12
 
 
-def search_by_bow(kf_view, kf_mp_valid, f_view, kf_fv, f_fv, nnratio, check_ori):
+def search_by_bow(kf_view, kf_mp_valid, f_view, kf_fv, f_fv, nnratio, check_ori, f_nleft=-1):
+    """f_nleft != -1: F is a two-camera frame whose first f_nleft features belong to the left camera."""
     kn, kp, ki = (np.ascontiguousarray(a, np.int32) for a in kf_fv)
     fn, fp, fi = (np.ascontiguousarray(a, np.int32) for a in f_fv)
     valid = np.ascontiguousarray(kf_mp_valid, np.uint8)
     out = np.zeros(f_view.n, np.int32)
-    nm = lib().orc_search_by_bow(C.addressof(kf_view), _ptr(valid), C.addressof(f_view), len(kn), _ptr(kn), _ptr(kp),
-                                 _ptr(ki), len(fn), _ptr(fn), _ptr(fp), _ptr(fi), nnratio, int(check_ori), _ptr(out))
+    nm = lib().orc_search_by_bow_2cam(C.addressof(kf_view), _ptr(valid), C.addressof(f_view), int(f_nleft), len(kn), _ptr(kn),
+                                      _ptr(kp), _ptr(ki), len(fn), _ptr(fn), _ptr(fp), _ptr(fi), nnratio, int(check_ori),
+                                      _ptr(out))
     return nm, out
 
 

@@ -149,6 +149,7 @@ struct Frame {
     Pose pose;
     Camera cam;
     Camera *mpCamera = &cam;
+    Camera *mpCamera2 = nullptr;
     float mfLogScaleFactor = std::log(1.2f);
     int mnScaleLevels = 8;
     Pose GetPose() const { return pose; }
@@ -159,7 +160,6 @@ struct Frame {
 struct KeyFrame : Frame {   // the members ORBmatcher reads from a KeyFrame (KeyFrame.h)
     int NLeft = -1;
     float fx = 500, fy = 500, cx = 320, cy = 240;
-    Camera *mpCamera2 = nullptr;
     std::vector<float> mvLevelSigma2, mvInvLevelSigma2;
     explicit KeyFrame(const Frame &f) : Frame(f) {
         mpCamera = &cam;
@@ -537,6 +537,53 @@ int main(int argc, char **argv) {
         EXPECT((int)matches.size() == F.N, "SearchByBoW output size");
         for (int j = 0; j < F.N && j < (int)matches.size(); ++j)
             EXPECT(matches[j] == (mf[j] >= 0 ? KF.mvpMapPoints[mf[j]] : nullptr), "vpMapPointMatches[%d]", j);
+    }
+
+    // ---------------- SearchByBoW(KF, F) with a two-camera frame ----------------
+    {
+        Frame KF = B, F2;                           // F2: left camera = A's keypoints, right camera = B's
+        F2.Nleft = A.N;
+        F2.mvKeys = A.mvKeys; F2.mvKeysRight = B.mvKeys;
+        F2.N = A.N + B.N;
+        F2.mvScaleFactors = A.mvScaleFactors;
+        F2.mDescriptors.create(F2.N, 32, CV_8U);
+        for (int i = 0; i < A.N; ++i) std::memcpy(F2.mDescriptors.ptr(i), A.mDescriptors.ptr(i), 32);
+        for (int i = 0; i < B.N; ++i) std::memcpy(F2.mDescriptors.ptr(A.N + i), B.mDescriptors.ptr(i), 32);
+        for (int i = 0; i < F2.N; ++i) F2.mFeatVec[(F2.mDescriptors.ptr(i)[0] * 7u + 3u) % 24u].push_back(i);
+        std::vector<MapPoint> store(KF.N);
+        std::vector<unsigned char> valid(KF.N, 0);
+        for (int i = 0; i < KF.N; ++i) {
+            store[i].bad = rng() % 25 == 0;
+            KF.mvpMapPoints[i] = rng() % 10 < 9 ? &store[i] : nullptr;
+            valid[i] = KF.mvpMapPoints[i] && !store[i].bad;
+        }
+        auto flat = [](const std::map<unsigned, std::vector<unsigned>> &fv, std::vector<int32_t> &n, std::vector<int32_t> &p, std::vector<int32_t> &x) {
+            p.push_back(0);
+            for (auto &kv : fv) { n.push_back(kv.first); for (unsigned v : kv.second) x.push_back(v); p.push_back((int32_t)x.size()); }
+        };
+        std::vector<int32_t> kn, kp, ki, fn, fp, fi;
+        flat(KF.mFeatVec, kn, kp, ki);
+        flat(F2.mFeatVec, fn, fp, fi);
+        std::vector<unsigned char> dk, df((size_t)F2.N * 32);
+        orc_frame_view vk = view_of(KF, dk);
+        std::vector<cv::KeyPoint> allkeys(F2.mvKeys);
+        allkeys.insert(allkeys.end(), F2.mvKeysRight.begin(), F2.mvKeysRight.end());
+        for (int i = 0; i < F2.N; ++i) std::memcpy(&df[(size_t)i * 32], F2.mDescriptors.ptr(i), 32);
+        orc_frame_view vf = vk;
+        vf.n = F2.N; vf.keys = reinterpret_cast<const orc_keypoint *>(allkeys.data()); vf.descriptors = df.data(); vf.u_right = nullptr;
+        std::vector<int32_t> mf(F2.N);
+        const int want = orc_search_by_bow_2cam(&vk, valid.data(), &vf, F2.Nleft, (int)kn.size(), kn.data(), kp.data(), ki.data(),
+                                                (int)fn.size(), fn.data(), fp.data(), fi.data(), 0.7f, 1, mf.data());
+        VS_GRAPHS::ORBmatcher matcher(0.7f, true);
+        std::vector<MapPoint *> matches;
+        const int got = matcher.SearchByBoW(&KF, F2, matches);
+        EXPECT(got == want && got > 20, "SearchByBoW(two cameras): %d vs %d", got, want);
+        int right_hits = 0;
+        for (int j = 0; j < F2.N && j < (int)matches.size(); ++j) {
+            EXPECT(matches[j] == (mf[j] >= 0 ? KF.mvpMapPoints[mf[j]] : nullptr), "two cameras: vpMapPointMatches[%d]", j);
+            right_hits += j >= A.N && mf[j] >= 0;
+        }
+        EXPECT((int)matches.size() == F2.N && right_hits > 10, "SearchByBoW(two cameras): right-camera matches %d", right_hits);
     }
 
     // ---------------- SearchForInitialization ----------------

@@ -143,6 +143,23 @@ def test_search_by_bow(oracle, check_ori):
     assert nm > 20
 
 
+@pytest.mark.parametrize("check_ori", [True, False])
+def test_search_by_bow_two_cameras(oracle, check_ori):
+    """F.Nleft != -1: best / second-best per camera, the right-camera match nested in the left one's threshold block with
+    its ratio test disabled (ORBmatcher.cc:298-322, :362-390)."""
+    ka, da, kb, db = sc.two_frames(oracle, shift=(3, 2))
+    keys, desc = np.concatenate([ka, kb]), np.concatenate([da, db])
+    kf, f = sc.frame_data(kb, db), sc.frame_data(keys, desc)
+    rng = np.random.default_rng(6)
+    valid = (rng.random(kf.n) < 0.85).astype(np.uint8)
+    kfv, ffv = sc.feature_vector(db, 24), sc.feature_vector(desc, 24)
+    m = _matcher(0.7, check_ori)
+    nm, mf = m.SearchByBoW(kf, valid, f, kfv, ffv, f_nleft=len(ka))
+    wnm, wmf = oracle.search_by_bow(kf.view, valid, f.view, kfv, ffv, float(np.float32(0.7)), check_ori, len(ka))
+    assert nm == wnm and np.array_equal(mf, wmf)
+    assert (mf[:len(ka)] >= 0).sum() > 20 and (mf[len(ka):] >= 0).sum() > 20
+
+
 def test_empty_inputs(oracle):
     from visual_sgraphs_b200._lib import KEYPOINT_DTYPE, TRACK_POINT_DTYPE
     ka, da, kb, db = sc.two_frames(oracle)

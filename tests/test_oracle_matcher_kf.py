@@ -327,3 +327,65 @@ def test_search_by_projection_last_two_cameras(oracle):
             got_nm, got = oracle.search_by_projection_last_2cam(fl.view, fr.view, sc2["occupied"], pl, pr, desc, 15.0, mode, check_ori)
             assert got_nm == nm and np.array_equal(got, assign)
             assert (assign[:nl] >= 0).sum() > 20 and (assign[nl:] >= 0).sum() > 20
+
+
+def py_search_by_bow(kf, valid, f, kfv, ffv, nnratio, check_ori, f_nleft):
+    """Independent restatement of ORBmatcher.cc:226-428 incl. the two-camera branch (f_nleft != -1)."""
+    kn, kp, ki = kfv
+    fn, fp, fi = ffv
+    fbucket = {int(n): fi[fp[j]:fp[j + 1]] for j, n in enumerate(fn)}
+    matches = np.full(f.n, -1, np.int32)
+    hist = [[] for _ in range(30)]
+    nm = 0
+    for a, node in enumerate(kn):
+        if int(node) not in fbucket:
+            continue
+        for real_kf in ki[kp[a]:kp[a + 1]]:
+            if not valid[real_kf]:
+                continue
+            b = {False: [256, -1, 256], True: [256, -1, 256]}       # per camera: best, idx, second
+            for real_f in fbucket[int(node)]:
+                if matches[real_f] >= 0:
+                    continue
+                d = hamming(kf.descriptors[real_kf], f.descriptors[real_f])
+                cam = f_nleft != -1 and real_f >= f_nleft
+                if d < b[cam][0]:
+                    b[cam] = [d, int(real_f), b[cam][0]]
+                elif d < b[cam][2]:
+                    b[cam][2] = d
+            if b[False][0] <= 50:
+                if f32(b[False][0]) < f32(nnratio) * f32(b[False][2]):
+                    matches[b[False][1]] = real_kf
+                    nm += 1
+                    if check_ori:
+                        hist[py_rot_bin(kf.keys[real_kf]["angle"], f.keys[b[False][1]]["angle"])].append(b[False][1])
+                if b[True][0] <= 50:                                  # nested in the left block, ratio test `|| true`
+                    matches[b[True][1]] = real_kf
+                    nm += 1
+                    if check_ori:
+                        hist[py_rot_bin(kf.keys[real_kf]["angle"], f.keys[b[True][1]]["angle"])].append(b[True][1])
+    if check_ori:
+        def drop(idx):
+            matches[idx] = -1
+        nm -= rot_filter(hist, drop)
+    return nm, matches
+
+
+def test_search_by_bow_single_and_two_cameras(oracle):
+    ka, da, kb, db = _frames(oracle, shift=(3, 2))
+    # F: a two-camera frame whose left camera sees frame A and whose right camera sees frame B
+    keys = np.concatenate([ka, kb])
+    desc = np.concatenate([da, db])
+    f = sc.frame_data(keys, desc, size=(322, 243))
+    kf = sc.frame_data(kb, db, size=(322, 243))
+    rng = np.random.default_rng(12)
+    valid = (rng.random(kf.n) < 0.85).astype(np.uint8)
+    kfv, ffv = sc.feature_vector(db, 12), sc.feature_vector(desc, 12)
+    for f_nleft in (-1, len(ka)):
+        for check_ori in (True, False):
+            nm, mf = oracle.search_by_bow(kf.view, valid, f.view, kfv, ffv, float(f32(0.7)), check_ori, f_nleft)
+            wnm, wmf = py_search_by_bow(kf, valid, f, kfv, ffv, 0.7, check_ori, f_nleft)
+            assert nm == wnm and np.array_equal(mf, wmf)
+            assert nm > 10
+            if f_nleft != -1:
+                assert (mf[f_nleft:] >= 0).sum() > 5 and (mf[:f_nleft] >= 0).sum() > 5

@@ -792,7 +792,21 @@ vsg_status vsg_search_by_bow(vsg_matcher *m, const vsg_frame_view *KF, const uin
                              const int32_t *kf_idx, int f_nnodes, const int32_t *f_nodes, const int32_t *f_ptr,
                              const int32_t *f_idx, float nnratio, int check_ori, int32_t *matches_f_out,
                              int *nmatches_out) {
-    if (!m || !KF || !F || !matches_f_out || kf_nnodes < 0 || f_nnodes < 0 || (KF->n > 0 && !kf_mp_valid)) return VSG_ERR_INVALID;
+    return vsg_search_by_bow_2cam(m, KF, kf_mp_valid, F, -1, kf_nnodes, kf_nodes, kf_ptr, kf_idx, f_nnodes, f_nodes, f_ptr, f_idx,
+                                  nnratio, check_ori, matches_f_out, nmatches_out);
+}
+
+// The same with a two-camera frame (F.Nleft = f_nleft != -1): F's features [0, f_nleft) are the left camera's, the rest
+// the right camera's; best / second-best are kept per camera (:298-322) and the right-camera match is taken inside the
+// left one's `bestDist1 <= TH_LOW` block with its ratio test disabled (`|| true`, :364-366).  f_nleft == -1: single camera.
+vsg_status vsg_search_by_bow_2cam(vsg_matcher *m, const vsg_frame_view *KF, const uint8_t *kf_mp_valid,
+                                  const vsg_frame_view *F, int f_nleft, int kf_nnodes, const int32_t *kf_nodes,
+                                  const int32_t *kf_ptr, const int32_t *kf_idx, int f_nnodes, const int32_t *f_nodes,
+                                  const int32_t *f_ptr, const int32_t *f_idx, float nnratio, int check_ori,
+                                  int32_t *matches_f_out, int *nmatches_out) {
+    if (!m || !KF || !F || !matches_f_out || kf_nnodes < 0 || f_nnodes < 0 || (KF->n > 0 && !kf_mp_valid) || f_nleft < -1 ||
+        f_nleft > F->n)
+        return VSG_ERR_INVALID;
     CK(cudaSetDevice(m->device));
     // the merge walk over the two FeatureVectors (:248-376): one query per keyframe feature with a usable map
     // point inside a common node; its candidates are the frame features of that node, in vIndicesF order
@@ -842,19 +856,31 @@ vsg_status vsg_search_by_bow(vsg_matcher *m, const vsg_frame_view *KF, const uin
     for (int i = 0; i < F->n; ++i) matches_f_out[i] = -1;
     std::vector<int> rot_hist[HISTO_LENGTH];
     int nmatches = 0;
-    for (int k = 0; k < nq; ++k) {                                   // :256-358 with the distances looked up
+    const int nleft = f_nleft < 0 ? F->n : f_nleft;                  // single camera: every feature is a "left" one
+    for (int k = 0; k < nq; ++k) {                                   // :256-392 with the distances looked up
         int best1 = 256, best_idx_f = -1, best2 = 256;
+        int best1r = 256, best_idx_fr = -1, best2r = 256;
         for (int c = cptr[k]; c < cptr[k + 1]; ++c) {
             const int real_f = cand[c];
-            if (matches_f_out[real_f] >= 0) continue;                // :282-283
+            if (matches_f_out[real_f] >= 0) continue;                // :282-283, :303-304
             const int d = dist[c];
-            if (d < best1) { best2 = best1; best1 = d; best_idx_f = real_f; }
-            else if (d < best2) best2 = d;
+            if (real_f < nleft) {
+                if (d < best1) { best2 = best1; best1 = d; best_idx_f = real_f; }
+                else if (d < best2) best2 = d;
+            } else {
+                if (d < best1r) { best2r = best1r; best1r = d; best_idx_fr = real_f; }
+                else if (d < best2r) best2r = d;
+            }
         }
         if (best1 <= TH_LOW) {
             if (static_cast<float>(best1) < nnratio * static_cast<float>(best2)) {
                 matches_f_out[best_idx_f] = q_kf[k];
                 if (check_ori) rot_hist[rot_bin(KF->keys[q_kf[k]].angle, F->keys[best_idx_f].angle)].push_back(best_idx_f);
+                ++nmatches;
+            }
+            if (best1r <= TH_LOW) {                                  // ratio test `|| true` (:366)
+                matches_f_out[best_idx_fr] = q_kf[k];
+                if (check_ori) rot_hist[rot_bin(KF->keys[q_kf[k]].angle, F->keys[best_idx_fr].angle)].push_back(best_idx_fr);
                 ++nmatches;
             }
         }

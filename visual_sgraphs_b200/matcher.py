@@ -233,17 +233,18 @@ class ORBmatcher:
                                                     int(self.mbCheckOrientation), ptr(m12), C.byref(nm)))
         return nm.value, m12
 
-    def SearchByBoW(self, kf_data, kf_mp_valid, f_data, kf_featvec, f_featvec):
+    def SearchByBoW(self, kf_data, kf_mp_valid, f_data, kf_featvec, f_featvec, f_nleft=-1):
         """SearchByBoW(KeyFrame*, Frame&, ...) (ORBmatcher.cc:226-428). Feature vectors are (nodes, ptr, idx)
-        triples with sorted node ids. Returns (nmatches, matches_f[F.N])."""
+        triples with sorted node ids; f_nleft != -1: F is a two-camera frame (left features first).
+        Returns (nmatches, matches_f[F.N])."""
         kn, kp, ki = (np.ascontiguousarray(a, np.int32) for a in kf_featvec)
         fn, fp, fi = (np.ascontiguousarray(a, np.int32) for a in f_featvec)
         valid = np.ascontiguousarray(kf_mp_valid, np.uint8)
         out = np.zeros(f_data.n, np.int32)
         nm = C.c_int(0)
-        check(self._L.vsg_search_by_bow(self._h, C.byref(kf_data.view), ptr(valid), C.byref(f_data.view), len(kn),
-                                        ptr(kn), ptr(kp), ptr(ki), len(fn), ptr(fn), ptr(fp), ptr(fi),
-                                        float(self.mfNNratio), int(self.mbCheckOrientation), ptr(out), C.byref(nm)))
+        check(self._L.vsg_search_by_bow_2cam(self._h, C.byref(kf_data.view), ptr(valid), C.byref(f_data.view), int(f_nleft),
+                                             len(kn), ptr(kn), ptr(kp), ptr(ki), len(fn), ptr(fn), ptr(fp), ptr(fi),
+                                             float(self.mfNNratio), int(self.mbCheckOrientation), ptr(out), C.byref(nm)))
         return nm.value, out
 
     def SearchByProjectionReloc(self, cur_frame, occupied, search_points, desc, th, ORBdist):

@@ -13,8 +13,8 @@
 // results back exactly where the reference does.
 //
 // Scope: single-camera frames (Frame::Nleft == -1), plus the two-camera branches (Nleft != -1, stereo-fisheye rigs) of the
-// two per-frame tracking calls SearchByProjection(Frame&, vector<MapPoint*>&) and SearchByProjection(Frame&, const Frame&).
-// The other methods throw for two-camera frames — keep the reference's
+// tracking calls SearchByProjection(Frame&, vector<MapPoint*>&), SearchByProjection(Frame&, const Frame&) and
+// SearchByBoW(KeyFrame*, Frame&, ...).  The other methods throw for two-camera frames — keep the reference's
 // CPU ORBmatcher for them in that configuration.
 #ifndef VSG_SHIM_ORBMATCHER_H
 #define VSG_SHIM_ORBMATCHER_H
@@ -203,6 +203,24 @@ protected:
         }
         p.level = pMP->PredictScale(dist, pKF);
         return true;
+    }
+    // A two-camera frame / keyframe as one feature list: mvKeys then mvKeysRight, all rows of mDescriptors (no grid use).
+    template <class FrameT>
+    static void FlattenBothCameras(const FrameT &F, Flat &out) {
+        static_assert(sizeof(cv::KeyPoint) == sizeof(vsg_keypoint), "cv::KeyPoint layout");
+        const int nL = (int)F.mvKeys.size(), nR = (int)F.mvKeysRight.size(), n = nL + nR;
+        out.keys.resize(n);
+        if (nL) std::memcpy(out.keys.data(), F.mvKeys.data(), (size_t)nL * sizeof(vsg_keypoint));
+        if (nR) std::memcpy(out.keys.data() + nL, F.mvKeysRight.data(), (size_t)nR * sizeof(vsg_keypoint));
+        out.desc.resize((size_t)n * 32);
+        for (int i = 0; i < n; ++i) std::memcpy(&out.desc[(size_t)i * 32], F.mDescriptors.ptr(i), 32);
+        out.scale.assign(F.mvScaleFactors.begin(), F.mvScaleFactors.end());
+        vsg_frame_view &v = out.view;
+        v.n = n; v.keys = out.keys.data(); v.descriptors = out.desc.data(); v.u_right = nullptr;
+        v.min_x = F.mnMinX; v.min_y = F.mnMinY; v.max_x = F.mnMaxX; v.max_y = F.mnMaxY;
+        v.grid_inv_w = F.mfGridElementWidthInv; v.grid_inv_h = F.mfGridElementHeightInv;
+        v.grid_cols = FRAME_GRID_COLS; v.grid_rows = FRAME_GRID_ROWS;
+        v.scale_factors = out.scale.data(); v.n_levels = (int)out.scale.size();
     }
     // The two cameras of a two-camera frame as separate frames: mvKeys + descriptor rows [0, Nleft) and mvKeysRight +
     // rows [Nleft, N), the layout Frame::GetFeaturesInArea(..., bRight) works on (Frame.cc:840-848).
@@ -393,12 +411,13 @@ int ORBmatcher::SearchByProjection(FrameT &CurrentFrame, const FrameT &LastFrame
 
 template <class KeyFrameT, class FrameT, class MapPointT>
 int ORBmatcher::SearchByBoW(KeyFrameT *pKF, FrameT &F, std::vector<MapPointT *> &vpMapPointMatches) {
-    RequireSingleCamera(F);
     const std::vector<MapPointT *> vpMapPointsKF = pKF->GetMapPointMatches();
     vpMapPointMatches = std::vector<MapPointT *>(F.N, static_cast<MapPointT *>(nullptr));
     Flat kf, fr;
-    Flatten(*pKF, kf);
-    Flatten(F, fr);
+    // two-camera frames / keyframes: the left camera's keypoints followed by the right camera's, the order of
+    // mDescriptors and of the indices in mFeatVec (:298-322, :341-343, :348-350)
+    if (pKF->mpCamera2) FlattenBothCameras(*pKF, kf); else Flatten(*pKF, kf);
+    if (F.Nleft != -1) FlattenBothCameras(F, fr); else Flatten(F, fr);
     std::vector<uint8_t> valid(kf.view.n, 0);
     for (int i = 0; i < kf.view.n; ++i)
         if (vpMapPointsKF[i] && !vpMapPointsKF[i]->isBad()) valid[i] = 1;                    // :262-266
@@ -415,9 +434,9 @@ int ORBmatcher::SearchByBoW(KeyFrameT *pKF, FrameT &F, std::vector<MapPointT *> 
     flatten_fv(F.mFeatVec, fn, fp, fi);
     std::vector<int32_t> matches(fr.view.n, -1);
     int nmatches = 0;
-    Check(vsg_search_by_bow(Workspace(), &kf.view, valid.data(), &fr.view, (int)kn.size(), kn.data(), kp.data(), ki.data(),
-                            (int)fn.size(), fn.data(), fp.data(), fi.data(), mfNNratio, mbCheckOrientation ? 1 : 0,
-                            matches.data(), &nmatches), "vsg_search_by_bow");
+    Check(vsg_search_by_bow_2cam(Workspace(), &kf.view, valid.data(), &fr.view, F.Nleft, (int)kn.size(), kn.data(), kp.data(),
+                                 ki.data(), (int)fn.size(), fn.data(), fp.data(), fi.data(), mfNNratio,
+                                 mbCheckOrientation ? 1 : 0, matches.data(), &nmatches), "vsg_search_by_bow");
     for (int j = 0; j < fr.view.n; ++j)
         if (matches[j] >= 0) vpMapPointMatches[j] = vpMapPointsKF[matches[j]];               // :339
     return nmatches;
