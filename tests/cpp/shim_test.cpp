@@ -709,6 +709,17 @@ int main(int argc, char **argv) {
         EXPECT(got == want && got > 10, "SearchByBoW(KF,KF): %d vs %d", got, want);
         for (int i = 0; i < K1.N && i < (int)matches.size(); ++i)
             EXPECT(matches[i] == (m12[i] >= 0 ? K2.mvpMapPoints[m12[i]] : nullptr), "vpMatches12[%d]", i);
+        // two-camera keyframes (NLeft != -1): features past mvKeysUn (the right camera's) are skipped (:793-796, :814-817),
+        // so right-camera entries in the FeatureVectors and map-point lists must not change the result
+        K1.NLeft = K1.N; K2.NLeft = K2.N;
+        for (auto &kv : K1.mFeatVec) kv.second.push_back(K1.N + kv.first % 7);
+        for (auto &kv : K2.mFeatVec) kv.second.push_back(K2.N + kv.first % 5);
+        K1.mvpMapPoints.resize(K1.N + 7, &s1[0]);
+        K2.mvpMapPoints.resize(K2.N + 5, &s2[0]);
+        const int got2 = matcher.SearchByBoW(&K1, &K2, matches);
+        EXPECT(got2 == want && (int)matches.size() == K1.N + 7, "SearchByBoW(KF,KF) with two-camera keyframes: %d vs %d", got2, want);
+        for (int i = 0; i < K1.N && i < (int)matches.size(); ++i)
+            EXPECT(matches[i] == (m12[i] >= 0 ? K2.mvpMapPoints[m12[i]] : nullptr), "two cameras: vpMatches12[%d]", i);
     }
 
     // ---------------- Fuse(KF, vpMapPoints, th) ----------------

@@ -14,7 +14,7 @@
 //
 // Scope: single-camera frames (Frame::Nleft == -1), plus the two-camera branches (Nleft != -1, stereo-fisheye rigs) of the
 // tracking calls SearchByProjection(Frame&, vector<MapPoint*>&), SearchByProjection(Frame&, const Frame&) and
-// SearchByBoW(KeyFrame*, Frame&, ...).  The other methods throw for two-camera frames — keep the reference's
+// SearchByBoW(KeyFrame*, Frame&, ...), and SearchByBoW(KeyFrame*, KeyFrame*, ...).  The other methods throw for two-camera frames — keep the reference's
 // CPU ORBmatcher for them in that configuration.
 #ifndef VSG_SHIM_ORBMATCHER_H
 #define VSG_SHIM_ORBMATCHER_H
@@ -169,11 +169,13 @@ protected:
         ~FrameGuard() { vsg_frame_destroy(h); }
     };
     template <class FV>
-    static void FlattenFeatVec(const FV &fv, std::vector<int32_t> &nodes, std::vector<int32_t> &ptr, std::vector<int32_t> &idx) {
+    static void FlattenFeatVec(const FV &fv, std::vector<int32_t> &nodes, std::vector<int32_t> &ptr, std::vector<int32_t> &idx,
+                               size_t limit = (size_t)-1) {   // features >= limit are skipped (two-camera keyframes, :793-796)
         ptr.push_back(0);
         for (const auto &kv : fv) {           // DBoW2::FeatureVector = std::map<NodeId, std::vector<unsigned>>
             nodes.push_back((int32_t)kv.first);
-            for (unsigned v : kv.second) idx.push_back((int32_t)v);
+            for (unsigned v : kv.second)
+                if ((size_t)v < limit) idx.push_back((int32_t)v);
             ptr.push_back((int32_t)idx.size());
         }
     }
@@ -511,8 +513,10 @@ int ORBmatcher::SearchByProjection(FrameT &CurrentFrame, KeyFrameT *pKF, const s
 // ---- SearchByBoW(KF, KF) (ORBmatcher.cc:758-900) ----
 template <class KeyFrameT, class MapPointT>
 int ORBmatcher::SearchByBoW(KeyFrameT *pKF1, KeyFrameT *pKF2, std::vector<MapPointT *> &vpMatches12) {
-    RequireSingleCameraKF(*pKF1);
-    RequireSingleCameraKF(*pKF2);
+    // two-camera keyframes: only the features with an entry in mvKeysUn take part (`idx >= mvKeysUn.size()` -> continue,
+    // :793-796, :814-817); they are dropped from the flattened FeatureVectors
+    const size_t lim1 = pKF1->NLeft != -1 ? pKF1->mvKeysUn.size() : (size_t)-1;
+    const size_t lim2 = pKF2->NLeft != -1 ? pKF2->mvKeysUn.size() : (size_t)-1;
     const std::vector<MapPointT *> vpMapPoints1 = pKF1->GetMapPointMatches();
     const std::vector<MapPointT *> vpMapPoints2 = pKF2->GetMapPointMatches();
     vpMatches12 = std::vector<MapPointT *>(vpMapPoints1.size(), static_cast<MapPointT *>(nullptr));
@@ -523,8 +527,8 @@ int ORBmatcher::SearchByBoW(KeyFrameT *pKF1, KeyFrameT *pKF2, std::vector<MapPoi
     for (int i = 0; i < k1.view.n; ++i) v1[i] = vpMapPoints1[i] && !vpMapPoints1[i]->isBad();   // :800-804
     for (int i = 0; i < k2.view.n; ++i) v2[i] = vpMapPoints2[i] && !vpMapPoints2[i]->isBad();   // :820-826
     std::vector<int32_t> n1, p1, i1, n2, p2, i2;
-    FlattenFeatVec(pKF1->mFeatVec, n1, p1, i1);
-    FlattenFeatVec(pKF2->mFeatVec, n2, p2, i2);
+    FlattenFeatVec(pKF1->mFeatVec, n1, p1, i1, lim1);
+    FlattenFeatVec(pKF2->mFeatVec, n2, p2, i2, lim2);
     std::vector<int32_t> m12(k1.view.n, -1);
     int nmatches = 0;
     Check(vsg_search_by_bow_kf(Workspace(), &k1.view, v1.data(), &k2.view, v2.data(), (int)n1.size(), n1.data(), p1.data(),
