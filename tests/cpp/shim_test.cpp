@@ -171,6 +171,9 @@ struct KeyFrame : Frame {   // the members ORBmatcher reads from a KeyFrame (Key
     std::set<MapPoint *> GetMapPoints() const { std::set<MapPoint *> s; for (MapPoint *p : mvpMapPoints) if (p && !p->isBad()) s.insert(p); return s; }
     bool IsInImage(float x, float y) const { return x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY; }
     Vec3 GetCameraCenter() const { return pose.inverse().translation(); }
+    Pose right_pose;                                  // two-camera rigs: pose of the right camera
+    Pose GetRightPose() const { return right_pose; }
+    Vec3 GetRightCameraCenter() const { return right_pose.inverse().translation(); }
     Pose GetPoseInverse() const { return pose.inverse(); }
 };
 
@@ -761,6 +764,61 @@ int main(int argc, char **argv) {
             const MapPoint *g = KF.mvpMapPoints[i], *e = e_kfmp[i];
             const bool same = (!g && !e) || (g && e && ((g >= &store[0] && g < &store[0] + store.size()) ? (e == &e_store[g - &store[0]]) : (e == &e_inkf[g - &inkf[0]])));
             EXPECT(same, "Fuse KF map point %d", i);
+        }
+    }
+
+    // ---------------- Fuse(KF, vpMapPoints, th, bRight = true) on a two-camera keyframe ----------------
+    {
+        Frame F2 = A;                               // left camera = A's keypoints, right camera = B's
+        F2.mvKeysRight = B.mvKeys;
+        F2.N = A.N + B.N;
+        F2.mDescriptors.create(F2.N, 32, CV_8U);
+        for (int i = 0; i < A.N; ++i) std::memcpy(F2.mDescriptors.ptr(i), A.mDescriptors.ptr(i), 32);
+        for (int i = 0; i < B.N; ++i) std::memcpy(F2.mDescriptors.ptr(A.N + i), B.mDescriptors.ptr(i), 32);
+        F2.mvuRight.assign(F2.N, -1.f);
+        F2.mvpMapPoints.assign(F2.N, nullptr);
+        KeyFrame KF(F2);
+        KF.NLeft = A.N;
+        Camera cam2;
+        KF.mpCamera2 = &cam2;
+        KF.pose = translation_pose(0.3f, 0.2f, 0.1f);                                        // the left pose must not be used
+        KF.right_pose = translation_pose(0.f, 0.01f, 0.02f);
+        std::vector<MapPoint> store, inkf(F2.N);
+        make_points(B, KF.right_pose, 0, 0, store);                                          // points in front of the right camera
+        for (int i = 0; i < F2.N; ++i) { inkf[i].obs = 1 + rng() % 4; inkf[i].bad = rng() % 20 == 0; KF.mvpMapPoints[i] = rng() % 3 == 0 ? &inkf[i] : nullptr; }
+        std::vector<MapPoint *> vp(store.size());
+        for (size_t i = 0; i < store.size(); ++i) vp[i] = rng() % 12 == 0 ? nullptr : &store[i];
+        std::vector<orc_search_point> pts;
+        std::vector<unsigned char> pdesc, dk;
+        project_points(vp, KF.right_pose, &KF, nullptr, true, false, pts, pdesc);
+        Frame camR = B;
+        camR.mvuRight.assign(B.N, -1.f);
+        orc_frame_view vr = view_of(camR, dk);
+        std::vector<int32_t> best(vp.size());
+        orc_fuse_search(&vr, (int)vp.size(), pts.data(), pdesc.data(), 3.f, KF.mvInvLevelSigma2.data(), 0, best.data());
+        std::vector<MapPoint> e_store = store, e_inkf = inkf;
+        std::vector<MapPoint *> e_kfmp(F2.N);
+        for (int i = 0; i < F2.N; ++i) e_kfmp[i] = KF.mvpMapPoints[i] ? &e_inkf[KF.mvpMapPoints[i] - &inkf[0]] : nullptr;
+        int want = 0, right_slots = 0;
+        for (size_t i = 0; i < vp.size(); ++i) {
+            if (!vp[i]) continue;
+            MapPoint *mp = &e_store[vp[i] - &store[0]];
+            if (mp->bad || mp->IsInKeyFrame(&KF)) continue;
+            if (best[i] < 0) continue;
+            const int slot = best[i] + A.N;                                                  // idx += pKF->NLeft (:1295-1296)
+            MapPoint *in = e_kfmp[slot];
+            if (in) { if (!in->bad) { if (in->obs > mp->obs) mp->Replace(in); else in->Replace(mp); } }
+            else { mp->AddObservation(&KF, slot); e_kfmp[slot] = mp; ++right_slots; }
+            ++want;
+        }
+        VS_GRAPHS::ORBmatcher matcher;
+        const int got = matcher.Fuse(&KF, vp, 3.f, true);
+        EXPECT(got == want && got > 20 && right_slots > 5, "Fuse(bRight): %d vs %d (%d new right slots)", got, want, right_slots);
+        for (size_t i = 0; i < store.size(); ++i) EXPECT(store[i].bad == e_store[i].bad && store[i].obs == e_store[i].obs, "Fuse(bRight) map point %zu state", i);
+        for (int i = 0; i < F2.N; ++i) {
+            const MapPoint *g = KF.mvpMapPoints[i], *e = e_kfmp[i];
+            const bool same = (!g && !e) || (g && e && ((g >= &store[0] && g < &store[0] + store.size()) ? (e == &e_store[g - &store[0]]) : (e == &e_inkf[g - &inkf[0]])));
+            EXPECT(same, "Fuse(bRight) KF map point %d", i);
         }
     }
 

@@ -14,7 +14,8 @@
 //
 // Scope: single-camera frames (Frame::Nleft == -1), plus the two-camera branches (Nleft != -1, stereo-fisheye rigs) of the
 // tracking calls SearchByProjection(Frame&, vector<MapPoint*>&), SearchByProjection(Frame&, const Frame&) and
-// SearchByBoW(KeyFrame*, Frame&, ...), and SearchByBoW(KeyFrame*, KeyFrame*, ...).  The other methods throw for two-camera frames — keep the reference's
+// SearchByBoW(KeyFrame*, Frame&, ...), and of SearchByBoW(KeyFrame*, KeyFrame*, ...) and Fuse(KeyFrame*, vpMapPoints, th,
+// bRight).  The other methods throw for two-camera frames — keep the reference's
 // CPU ORBmatcher for them in that configuration.
 #ifndef VSG_SHIM_ORBMATCHER_H
 #define VSG_SHIM_ORBMATCHER_H
@@ -542,14 +543,36 @@ int ORBmatcher::SearchByBoW(KeyFrameT *pKF1, KeyFrameT *pKF2, std::vector<MapPoi
 // ---- Fuse(KF, vpMapPoints, th) (ORBmatcher.cc:1148-1335) ----
 template <class KeyFrameT, class MapPointT>
 int ORBmatcher::Fuse(KeyFrameT *pKF, const std::vector<MapPointT *> &vpMapPoints, const float th, const bool bRight) {
-    RequireSingleCameraKF(*pKF);
-    if (bRight) throw std::runtime_error("vsg ORBmatcher::Fuse: bRight needs a two-camera keyframe (not supported)");
+    const bool bTwoCameras = pKF->NLeft != -1;
+    if (bRight && !bTwoCameras) throw std::runtime_error("vsg ORBmatcher::Fuse: bRight needs a two-camera keyframe");
     Flat flat;
-    Flatten(*pKF, flat);
+    if (bTwoCameras) {
+        // the camera searched: mvKeys / mvKeysRight with their descriptor rows and grid (KeyFrame::GetFeaturesInArea(...,
+        // bRight)); the stereo gate reads mvuRight[idx] with the camera-local index on both sides (:1266)
+        static_assert(sizeof(cv::KeyPoint) == sizeof(vsg_keypoint), "cv::KeyPoint layout");
+        const std::vector<cv::KeyPoint> &keys = bRight ? pKF->mvKeysRight : pKF->mvKeys;
+        const int n = (int)keys.size(), row0 = bRight ? pKF->NLeft : 0;
+        flat.keys.resize(n);
+        if (n) std::memcpy(flat.keys.data(), keys.data(), (size_t)n * sizeof(vsg_keypoint));
+        flat.desc.resize((size_t)n * 32);
+        for (int i = 0; i < n; ++i) std::memcpy(&flat.desc[(size_t)i * 32], pKF->mDescriptors.ptr(row0 + i), 32);
+        flat.scale.assign(pKF->mvScaleFactors.begin(), pKF->mvScaleFactors.end());
+        vsg_frame_view &v = flat.view;
+        v.n = n; v.keys = flat.keys.data(); v.descriptors = flat.desc.data();
+        v.u_right = (int)pKF->mvuRight.size() >= n && n > 0 ? pKF->mvuRight.data() : nullptr;
+        v.min_x = pKF->mnMinX; v.min_y = pKF->mnMinY; v.max_x = pKF->mnMaxX; v.max_y = pKF->mnMaxY;
+        v.grid_inv_w = pKF->mfGridElementWidthInv; v.grid_inv_h = pKF->mfGridElementHeightInv;
+        v.grid_cols = FRAME_GRID_COLS; v.grid_rows = FRAME_GRID_ROWS;
+        v.scale_factors = flat.scale.data(); v.n_levels = (int)flat.scale.size();
+    } else {
+        Flatten(*pKF, flat);
+    }
     FrameGuard fr;
     Check(vsg_frame_create(Workspace(), &flat.view, &fr.h), "vsg_frame_create");
-    const auto Tcw = pKF->GetPose();
-    const auto Ow = pKF->GetCameraCenter();
+    const auto Tcw = bRight ? pKF->GetRightPose() : pKF->GetPose();                          // :1154-1165
+    const auto Ow = bRight ? pKF->GetRightCameraCenter() : pKF->GetCameraCenter();
+    auto *pCamera = bRight ? pKF->mpCamera2 : pKF->mpCamera;
+    const int idxOffset = bRight ? pKF->NLeft : 0;                                            // :1295-1296
     const float &bf = pKF->mbf;
     const int nMPs = (int)vpMapPoints.size();
     std::vector<vsg_search_point> pts(nMPs);
@@ -565,7 +588,7 @@ int ORBmatcher::Fuse(KeyFrameT *pKF, const std::vector<MapPointT *> &vpMapPoints
         const auto p3Dc = Tcw * p3Dw;
         if (p3Dc(2) < 0.0f) continue;
         const float invz = 1 / p3Dc(2);
-        const auto uv = pKF->mpCamera->project(p3Dc);
+        const auto uv = pCamera->project(p3Dc);
         if (!pKF->IsInImage(uv(0), uv(1))) continue;
         p.ur = uv(0) - bf * invz;
         if (!DistanceAndNormalGates(pMP, pKF, p3Dw, Ow, true, p)) continue;
@@ -581,6 +604,7 @@ int ORBmatcher::Fuse(KeyFrameT *pKF, const std::vector<MapPointT *> &vpMapPoints
         MapPointT *pMP = vpMapPoints[i];
         if (!pMP || pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;
         if (best[i] < 0) continue;
+        best[i] += idxOffset;
         MapPointT *pMPinKF = pKF->GetMapPoint(best[i]);
         if (pMPinKF) {
             if (!pMPinKF->isBad()) {
