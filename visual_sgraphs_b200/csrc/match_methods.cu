@@ -429,10 +429,14 @@ vsg_status vsg_search_by_projection_map(vsg_matcher *m, const vsg_frame *F, cons
     if (!m || !F || n_mp < 0 || !assign_out || (n_mp > 0 && (!pts || !mp_desc)) || (F->n > 0 && !occupied)) return VSG_ERR_INVALID;
     CK(cudaSetDevice(m->device));
     PhaseTimer pt("search_by_projection_map");
-    // query list in the matcher's reusable scratch (a 200k-point map is 8 MB of queries: no fresh pages per call)
-    m->scratch[0].resize((size_t)std::max(n_mp, 1) * sizeof(AreaQuery));
+    // query list in the matcher's pinned staging (a 200k-point map is 7 MB of queries: no fresh pages per call, and the
+    // upload runs at the PCIe rate instead of the pageable-memory rate)
+    {
+        vsg_status qst = matcher_ensure_host(m, 3, (size_t)std::max(n_mp, 1) * sizeof(AreaQuery));
+        if (qst != VSG_OK) return qst;
+    }
     m->scratch[1].resize((size_t)std::max(n_mp, 1) * sizeof(int));
-    AreaQuery *qs = reinterpret_cast<AreaQuery *>(m->scratch[0].data());
+    AreaQuery *qs = reinterpret_cast<AreaQuery *>(m->hbuf[3]);
     int *q_mp = reinterpret_cast<int *>(m->scratch[1].data());
     int nq = 0;
     {
