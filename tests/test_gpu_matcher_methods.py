@@ -72,7 +72,7 @@ def test_search_by_projection_map_large_map(oracle):
     ka, da, kb, db = sc.two_frames(oracle)
     fd = sc.frame_data(ka, da)
     rng = np.random.default_rng(2)
-    reps = 20
+    reps = 30                                   # > 20 000 queries: the device-ordered lists + entry-walk replay
     kb2 = np.concatenate([kb] * reps)
     db2 = np.concatenate([db] * reps)
     flip = rng.integers(0, 256, db2.shape, dtype=np.uint8) & rng.integers(0, 256, db2.shape, dtype=np.uint8) & \

@@ -179,6 +179,123 @@ vsg_status area_search_raw(vsg_matcher *m, const vsg_frame *f, int nq, const Are
     return VSG_ERR_CAPACITY;
 }
 
+// Exclusive prefix sum of the per-query counts by one CTA (tiles of 1024 with a running carry): ptr[q] = position of query
+// q's list in query order, ptr[n] = number of entries.
+__global__ void __launch_bounds__(1024) scan_counts_kernel(const int *__restrict__ cnt, int n, int *__restrict__ ptr) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + tid;
+        const int v = i < n ? cnt[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int x = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += x;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        int wsum = lane < 32 ? s_warp[lane] : 0, wincl = wsum;   // every warp scans the 32 warp totals
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int x = __shfl_up_sync(0xffffffffu, wincl, d);
+            if (lane >= d) wincl += x;
+        }
+        const int warp_before = __shfl_sync(0xffffffffu, wincl - wsum, warp);
+        const int tile_total = __shfl_sync(0xffffffffu, wincl, 31);
+        const int carry = s_carry;
+        if (i < n) ptr[i] = carry + warp_before + incl - v;
+        __syncthreads();
+        if (tid == 0) s_carry = carry + tile_total;
+        __syncthreads();
+    }
+    if (tid == 0) ptr[n] = s_carry;
+}
+
+// Copies every query's segment to its place in query order and tags each entry with its query.
+__global__ void __launch_bounds__(256) order_segments_kernel(const int2 *__restrict__ raw, const int *__restrict__ off,
+                                                             const int *__restrict__ cnt, const int *__restrict__ ptr, int nq,
+                                                             int2 *__restrict__ ent, int *__restrict__ qid) {
+    const int q = blockIdx.x * 256 + threadIdx.x;
+    if (q >= nq) return;
+    const int n = cnt[q], src = off[q], dst = ptr[q];
+    for (int c = 0; c < n; ++c) {
+        ent[dst + c] = raw[src + c];
+        qid[dst + c] = q;
+    }
+}
+
+// area_search_raw with the lists re-ordered on the device: entries of query 0, then of query 1, ... (each list still in
+// the reference's candidate order), ptr[nq + 1], and the query of every entry.  For callers whose replay wants to walk
+// ALL entries front to back (a map much larger than the frame: most entries are skipped by a one-byte test).
+constexpr int kOrderedReplayMinQueries = 20000;   // below this the two extra kernels cost more than the replay saves
+struct OrderedLists {
+    const int2 *ent = nullptr;
+    const int *qid = nullptr, *ptr = nullptr;
+    int total = 0;
+};
+vsg_status area_search_ordered(vsg_matcher *m, const vsg_frame *f, int nq, const AreaQuery *qs, const uint8_t *qdesc,
+                               int n_qdesc, OrderedLists *out) {
+    PhaseTimer pt("area_search");
+    *out = OrderedLists();
+    if (nq == 0) return VSG_OK;
+    cudaStream_t s = m->stream;
+    vsg_status st;
+    // device slots: 7 queries, 8 qdesc, 9 off/cnt/total, 10 raw entries, 11 ptr + qid, 6 ordered entries;
+    // pinned host slots: 0 ptr, 1 entries, 4 qid
+    if ((st = matcher_ensure(m, 7, (size_t)nq * sizeof(AreaQuery))) || (st = matcher_ensure(m, 8, (size_t)n_qdesc * 32)) ||
+        (st = matcher_ensure(m, 9, (size_t)(2 * nq + 1) * sizeof(int))) ||
+        (st = matcher_ensure_host(m, 0, (size_t)(nq + 2) * sizeof(int))))
+        return st;
+    CK(cudaMemcpyAsync(m->buf[7], qs, (size_t)nq * sizeof(AreaQuery), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(m->buf[8], qdesc, (size_t)n_qdesc * 32, cudaMemcpyHostToDevice, s));
+    int *off_d = (int *)m->buf[9], *cnt_d = off_d + nq, *total_d = off_d + 2 * nq;
+    int *host = (int *)m->hbuf[0];
+    FrameDev fd{f->n, f->cols, f->rows, f->min_x, f->min_y, f->inv_w, f->inv_h, f->xy, f->octave,
+                f->has_right ? f->u_right : nullptr, (const uint4 *)f->desc, f->cell_ptr, f->cell_idx};
+    size_t cap = std::max<size_t>(m->cap[10] / sizeof(int2), (size_t)nq * 4);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if ((st = matcher_ensure(m, 10, cap * sizeof(int2)))) return st;
+        CK(cudaMemsetAsync(total_d, 0, sizeof(int), s));
+        area_search_kernel<<<(nq + 7) / 8, 256, 0, s>>>(fd, nq, (const AreaQuery *)m->buf[7], (const uint4 *)m->buf[8],
+                                                       off_d, cnt_d, (int2 *)m->buf[10], (int)cap, total_d);
+        count_launch();
+        CK(cudaMemcpyAsync(host, total_d, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        pt.mark("H2D + kernel + D2H of the total");
+        const int total = host[0];
+        if ((size_t)total > cap) { cap = (size_t)total + 1024; continue; }   // retry once with the exact size
+        if ((st = matcher_ensure(m, 11, ((size_t)nq + 1 + std::max(total, 1)) * sizeof(int))) ||
+            (st = matcher_ensure(m, 6, (size_t)std::max(total, 1) * sizeof(int2))) ||
+            (st = matcher_ensure_host(m, 1, (size_t)std::max(total, 1) * sizeof(int2))) ||
+            (st = matcher_ensure_host(m, 4, (size_t)std::max(total, 1) * sizeof(int))))
+            return st;
+        int *ptr_d = (int *)m->buf[11], *qid_d = ptr_d + nq + 1;
+        scan_counts_kernel<<<1, 1024, 0, s>>>(cnt_d, nq, ptr_d);
+        order_segments_kernel<<<(nq + 255) / 256, 256, 0, s>>>((const int2 *)m->buf[10], off_d, cnt_d, ptr_d, nq, (int2 *)m->buf[6],
+                                                               qid_d);
+        count_launch(2);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(host, ptr_d, (size_t)(nq + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
+        if (total) {
+            CK(cudaMemcpyAsync(m->hbuf[1], m->buf[6], (size_t)total * sizeof(int2), cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(m->hbuf[4], qid_d, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, s));
+        }
+        CK(cudaStreamSynchronize(s));
+        pt.mark("ordering + D2H of the lists");
+        out->ent = (const int2 *)m->hbuf[1];
+        out->qid = (const int *)m->hbuf[4];
+        out->ptr = host;
+        out->total = total;
+        return VSG_OK;
+    }
+    set_error("area_search: candidate buffer overflow");
+    return VSG_ERR_CAPACITY;
+}
+
 // Runs the area search for nq queries and brings the lists back: ptr[nq+1] and (idx, dist) pairs in query order.
 vsg_status area_search(vsg_matcher *m, const vsg_frame *f, int nq, const AreaQuery *qs, const uint8_t *qdesc,
                        std::vector<int> &ptr, std::vector<int2> &ent) {
@@ -456,18 +573,52 @@ vsg_status vsg_search_by_projection_map(vsg_matcher *m, const vsg_frame *F, cons
         }
     }
     pt.mark("queries");
-    AreaLists L;
-    vsg_status st;
-    if ((st = area_search_raw(m, F, nq, qs, mp_desc, n_mp, &L)) != VSG_OK) return st;
-    pt.mark("area_search total");
-    // sequential replay of :76-141 straight over the kernel's segments (query k = map point q_mp[k], in map order)
     std::vector<uint8_t> blocked(occupied, occupied + F->n);
     for (int i = 0; i < F->n; ++i) assign_out[i] = -1;
     const vsg_keypoint *keys = F->keys.data();
     int nmatches = 0;
-    for (int k = 0; k < nq; ++k) {
+    vsg_status st;
+    if (nq < kOrderedReplayMinQueries) {
+        // tracking-sized calls (a local map of a few thousand points): the lists come back as the kernel left them and
+        // the replay of :76-141 visits them query by query — two kernels and a copy less than the ordered form below
+        AreaLists R;
+        if ((st = area_search_raw(m, F, nq, qs, mp_desc, n_mp, &R)) != VSG_OK) return st;
+        pt.mark("area_search total");
+        for (int k = 0; k < nq; ++k) {
+            int best = 256, best_level = -1, best2 = 256, best_level2 = -1, best_idx = -1;
+            const int2 *c = R.raw + R.off[k], *ce = c + R.cnt[k];
+            for (; c < ce; ++c) {
+                const int idx = c->x, dist = c->y;
+                if (blocked[idx]) continue;
+                if (dist < best) { best2 = best; best = dist; best_level2 = best_level; best_level = keys[idx].octave; best_idx = idx; }
+                else if (dist < best2) { best_level2 = keys[idx].octave; best2 = dist; }
+            }
+            if (best <= TH_HIGH) {
+                if (best_level == best_level2 && best > nnratio * best2) continue;
+                if (best_level != best_level2 || best <= nnratio * best2) {
+                    assign_out[best_idx] = q_mp[k];
+                    blocked[best_idx] = pts[q_mp[k]].blocks;
+                    ++nmatches;
+                }
+            }
+        }
+        pt.mark("resolve");
+        if (nmatches_out) *nmatches_out = nmatches;
+        return VSG_OK;
+    }
+    OrderedLists L;
+    if ((st = area_search_ordered(m, F, nq, qs, mp_desc, n_mp, &L)) != VSG_OK) return st;
+    pt.mark("area_search total");
+    // Sequential replay of :76-141 (query k = map point q_mp[k], in map order) as ONE walk over all entries in query
+    // order: an entry whose keypoint is already claimed is skipped by a one-byte test — with a map much larger than
+    // the frame that is nearly every entry — and only the first unclaimed entry of a query triggers the scan of that
+    // query's list.  (Claims only ever appear, so an entry found claimed stays irrelevant for its query.)
+    for (int e = 0; e < L.total;) {
+        if (blocked[L.ent[e].x]) { ++e; continue; }
+        const int k = L.qid[e];
         int best = 256, best_level = -1, best2 = 256, best_level2 = -1, best_idx = -1;
-        const int2 *c = L.raw + L.off[k], *ce = c + L.cnt[k];
+        const int2 *c = L.ent + e, *ce = L.ent + L.ptr[k + 1];
+        e = L.ptr[k + 1];
         for (; c < ce; ++c) {
             const int idx = c->x, dist = c->y;
             if (blocked[idx]) continue;
