@@ -258,3 +258,23 @@ def test_remap_bilinear_matches_cv2(oracle):
     mx = rng.uniform(-40000, 40000, (50, 60)).astype(np.float32)      # saturation of the integer part
     my = rng.uniform(-3, 100, (50, 60)).astype(np.float32)
     assert np.array_equal(oracle.remap_bilinear(noise, mx, my), cv2.remap(noise, mx, my, cv2.INTER_LINEAR))
+
+
+def test_primitives_match_cv2_on_random_shapes(oracle):
+    """Randomised sweep over image sizes and scale factors (seeded): resize at the extractor's level ratios 1.1 .. 1.9,
+    the 7x7 blur, the colour conversion and remap, all against cv2 — the shapes the fixed parametrisations do not hit
+    (odd sizes, widths that are not multiples of 4, very small levels)."""
+    rng = np.random.default_rng(2026)
+    for trial in range(40):
+        w, h = int(rng.integers(67, 400)), int(rng.integers(67, 300))
+        kind = ("uniform", "binary")[trial % 2]
+        src = _rand_img(1000 + trial, w, h, kind)
+        scale = float(rng.uniform(1.1, 1.9))
+        dw, dh = int(round(w / scale)), int(round(h / scale))
+        assert np.array_equal(oracle.resize_linear(src, dw, dh), cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LINEAR)), (w, h, dw, dh)
+        assert np.array_equal(oracle.gaussian_blur7(src), cv2_ref.blur(src)), (w, h)
+        rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        assert np.array_equal(oracle.cvt_gray(rgb, True), cv2.cvtColor(rgb, cv2.COLOR_RGB2GRAY))
+        mx = (np.arange(dw)[None, :] * scale + rng.uniform(-3, 3)).astype(np.float32).repeat(dh, 0) + rng.normal(0, 0.3, (dh, dw)).astype(np.float32)
+        my = (np.arange(dh)[:, None] * scale + rng.uniform(-3, 3)).astype(np.float32).repeat(dw, 1) + rng.normal(0, 0.3, (dh, dw)).astype(np.float32)
+        assert np.array_equal(oracle.remap_bilinear(src, mx, my), cv2.remap(src, mx, my, cv2.INTER_LINEAR)), (w, h)
