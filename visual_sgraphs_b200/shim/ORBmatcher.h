@@ -207,46 +207,40 @@ protected:
         p.level = pMP->PredictScale(dist, pKF);
         return true;
     }
-    // A two-camera frame / keyframe as one feature list: mvKeys then mvKeysRight, all rows of mDescriptors (no grid use).
+    // Keys (one or two lists back to back) + descriptor rows [row0, row0 + n) of a frame / keyframe as a view.
     template <class FrameT>
-    static void FlattenBothCameras(const FrameT &F, Flat &out) {
+    static void FlattenKeys(const FrameT &F, const std::vector<cv::KeyPoint> &keysA, const std::vector<cv::KeyPoint> *keysB,
+                            int row0, const float *u_right, Flat &out) {
         static_assert(sizeof(cv::KeyPoint) == sizeof(vsg_keypoint), "cv::KeyPoint layout");
-        const int nL = (int)F.mvKeys.size(), nR = (int)F.mvKeysRight.size(), n = nL + nR;
+        const int nA = (int)keysA.size(), nB = keysB ? (int)keysB->size() : 0, n = nA + nB;
         out.keys.resize(n);
-        if (nL) std::memcpy(out.keys.data(), F.mvKeys.data(), (size_t)nL * sizeof(vsg_keypoint));
-        if (nR) std::memcpy(out.keys.data() + nL, F.mvKeysRight.data(), (size_t)nR * sizeof(vsg_keypoint));
+        if (nA) std::memcpy(out.keys.data(), keysA.data(), (size_t)nA * sizeof(vsg_keypoint));
+        if (nB) std::memcpy(out.keys.data() + nA, keysB->data(), (size_t)nB * sizeof(vsg_keypoint));
         out.desc.resize((size_t)n * 32);
-        for (int i = 0; i < n; ++i) std::memcpy(&out.desc[(size_t)i * 32], F.mDescriptors.ptr(i), 32);
+        for (int i = 0; i < n; ++i) std::memcpy(&out.desc[(size_t)i * 32], F.mDescriptors.ptr(row0 + i), 32);
         out.scale.assign(F.mvScaleFactors.begin(), F.mvScaleFactors.end());
         vsg_frame_view &v = out.view;
-        v.n = n; v.keys = out.keys.data(); v.descriptors = out.desc.data(); v.u_right = nullptr;
+        v.n = n; v.keys = out.keys.data(); v.descriptors = out.desc.data(); v.u_right = u_right;
         v.min_x = F.mnMinX; v.min_y = F.mnMinY; v.max_x = F.mnMaxX; v.max_y = F.mnMaxY;
         v.grid_inv_w = F.mfGridElementWidthInv; v.grid_inv_h = F.mfGridElementHeightInv;
         v.grid_cols = FRAME_GRID_COLS; v.grid_rows = FRAME_GRID_ROWS;
         v.scale_factors = out.scale.data(); v.n_levels = (int)out.scale.size();
     }
-    // The two cameras of a two-camera frame as separate frames: mvKeys + descriptor rows [0, Nleft) and mvKeysRight +
-    // rows [Nleft, N), the layout Frame::GetFeaturesInArea(..., bRight) works on (Frame.cc:840-848).
+    // A two-camera frame / keyframe as one feature list: mvKeys then mvKeysRight, all rows of mDescriptors (the order of
+    // the indices in mFeatVec; no grid use).
+    template <class FrameT>
+    static void FlattenBothCameras(const FrameT &F, Flat &out) { FlattenKeys(F, F.mvKeys, &F.mvKeysRight, 0, nullptr, out); }
+    // One camera of a two-camera frame / keyframe: mvKeys + descriptor rows [0, Nleft) or mvKeysRight + rows [Nleft, N),
+    // the layout GetFeaturesInArea(..., bRight) works on (Frame.cc:840-848, KeyFrame.cc:834-875).
+    template <class FrameT>
+    static void FlattenCamera(const FrameT &F, bool bRight, int nLeft, const float *u_right, Flat &out) {
+        FlattenKeys(F, bRight ? F.mvKeysRight : F.mvKeys, nullptr, bRight ? nLeft : 0, u_right, out);
+    }
     template <class FrameT>
     void UploadCameras(const FrameT &F, Flat cam[2], FrameGuard fr[2]) {
-        static_assert(sizeof(cv::KeyPoint) == sizeof(vsg_keypoint), "cv::KeyPoint layout");
-        const int nL = F.Nleft, nR = (int)F.mvKeysRight.size();
         for (int c = 0; c < 2; ++c) {
-            Flat &o = cam[c];
-            const std::vector<cv::KeyPoint> &keys = c == 0 ? F.mvKeys : F.mvKeysRight;
-            const int n = c == 0 ? nL : nR, row0 = c == 0 ? 0 : nL;
-            o.keys.resize(n);
-            if (n) std::memcpy(o.keys.data(), keys.data(), (size_t)n * sizeof(vsg_keypoint));
-            o.desc.resize((size_t)n * 32);
-            for (int i = 0; i < n; ++i) std::memcpy(&o.desc[(size_t)i * 32], F.mDescriptors.ptr(row0 + i), 32);
-            o.scale.assign(F.mvScaleFactors.begin(), F.mvScaleFactors.end());
-            vsg_frame_view &v = o.view;
-            v.n = n; v.keys = o.keys.data(); v.descriptors = o.desc.data(); v.u_right = nullptr;
-            v.min_x = F.mnMinX; v.min_y = F.mnMinY; v.max_x = F.mnMaxX; v.max_y = F.mnMaxY;
-            v.grid_inv_w = F.mfGridElementWidthInv; v.grid_inv_h = F.mfGridElementHeightInv;
-            v.grid_cols = FRAME_GRID_COLS; v.grid_rows = FRAME_GRID_ROWS;
-            v.scale_factors = o.scale.data(); v.n_levels = (int)o.scale.size();
-            Check(vsg_frame_create(Workspace(), &v, &fr[c].h), "vsg_frame_create");
+            FlattenCamera(F, c == 1, F.Nleft, nullptr, cam[c]);
+            Check(vsg_frame_create(Workspace(), &cam[c].view, &fr[c].h), "vsg_frame_create");
         }
     }
     template <class FrameT>
@@ -549,21 +543,8 @@ int ORBmatcher::Fuse(KeyFrameT *pKF, const std::vector<MapPointT *> &vpMapPoints
     if (bTwoCameras) {
         // the camera searched: mvKeys / mvKeysRight with their descriptor rows and grid (KeyFrame::GetFeaturesInArea(...,
         // bRight)); the stereo gate reads mvuRight[idx] with the camera-local index on both sides (:1266)
-        static_assert(sizeof(cv::KeyPoint) == sizeof(vsg_keypoint), "cv::KeyPoint layout");
-        const std::vector<cv::KeyPoint> &keys = bRight ? pKF->mvKeysRight : pKF->mvKeys;
-        const int n = (int)keys.size(), row0 = bRight ? pKF->NLeft : 0;
-        flat.keys.resize(n);
-        if (n) std::memcpy(flat.keys.data(), keys.data(), (size_t)n * sizeof(vsg_keypoint));
-        flat.desc.resize((size_t)n * 32);
-        for (int i = 0; i < n; ++i) std::memcpy(&flat.desc[(size_t)i * 32], pKF->mDescriptors.ptr(row0 + i), 32);
-        flat.scale.assign(pKF->mvScaleFactors.begin(), pKF->mvScaleFactors.end());
-        vsg_frame_view &v = flat.view;
-        v.n = n; v.keys = flat.keys.data(); v.descriptors = flat.desc.data();
-        v.u_right = (int)pKF->mvuRight.size() >= n && n > 0 ? pKF->mvuRight.data() : nullptr;
-        v.min_x = pKF->mnMinX; v.min_y = pKF->mnMinY; v.max_x = pKF->mnMaxX; v.max_y = pKF->mnMaxY;
-        v.grid_inv_w = pKF->mfGridElementWidthInv; v.grid_inv_h = pKF->mfGridElementHeightInv;
-        v.grid_cols = FRAME_GRID_COLS; v.grid_rows = FRAME_GRID_ROWS;
-        v.scale_factors = flat.scale.data(); v.n_levels = (int)flat.scale.size();
+        const int n = (int)(bRight ? pKF->mvKeysRight : pKF->mvKeys).size();
+        FlattenCamera(*pKF, bRight, pKF->NLeft, (int)pKF->mvuRight.size() >= n && n > 0 ? pKF->mvuRight.data() : nullptr, flat);
     } else {
         Flatten(*pKF, flat);
     }
