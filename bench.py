@@ -11,8 +11,8 @@ scaling).  One JSON line is printed by rank 0:
   value      frames/s with the batch already resident in HBM (device pointers in, device results out)
   e2e        frames/s through the host-pointer C-ABI call (pinned host frames -> H2D -> kernels -> D2H)
   roofline   the dominant kernel group's algorithmic bytes / its CUDA-event time vs the measured HBM peak
-  cpu_baseline  the CPU oracle (a port of the reference algorithm) on this box's host cores, bounded sample
-`--impl reference` times that CPU port alone (all host threads) and prints the same line shape.
+  cpu_baseline  the reference's own ORBextractor.cc (oracle/_ref, compiled unmodified) on this box's host cores, bounded sample
+`--impl reference` times that CPU build alone (all host threads) and prints the same line shape.
 """
 import argparse
 import json
@@ -124,12 +124,36 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.sm)}
 
 
-def cpu_port_throughput(nframes, threads):
-    """The CPU oracle (port of ORBextractor.cc) over `nframes` frames on `threads` host threads."""
+def workload_config(B):
+    """The `config` object — identical in the repo arm and the reference arm (the driver compares them)."""
+    return {"workload": "C1: ORBextractor 640x480, 1000 features, 8 levels, scale 1.2, FAST 20/7",
+            "frames_per_step_per_gpu": B, "sharding": "frames by rank, no collective",
+            "l2": "inputs larger than L2: %d MB of frames + %d MB of pyramid/blur planes per step" %
+                  (B * W * H >> 20, (2 * B * 1158012) >> 20)}
+
+
+def cpu_reference():
+    """(kind, bench_extract(frames, threads) -> (seconds, keypoints)).  kind "reference" = oracle/_ref/libvsg_ref.so, the
+    reference's own ORBextractor.cc compiled unmodified (oracle/ref_build/Makefile); "port" = the oracle restatement,
+    only when that library is neither prebuilt nor buildable."""
+    try:
+        from oracle import ref
+        if ref.available():
+            ref.lib()
+            return "reference", lambda frames, threads: ref.bench_extract(frames, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, threads)
+    except Exception as e:  # noqa: BLE001
+        print("oracle/_ref unavailable (%s); timing the oracle port instead" % e, file=sys.stderr)
     from oracle import oracle as orc
+    return "port", lambda frames, threads: orc.bench_extract(frames, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, threads)
+
+
+def cpu_throughput(nframes, threads):
+    """The reference's CPU extractor over `nframes` frames of the workload on `threads` host threads."""
+    kind, fn = cpu_reference()
     frames = make_frames(nframes, 9000)
-    secs, total_kp = orc.bench_extract(frames, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, threads)
-    return nframes / secs, secs, total_kp
+    fn(frames[:min(nframes, 4 * threads)], threads)          # untimed: first-touch of the per-thread malloc arenas
+    secs, total_kp = fn(frames, threads)
+    return kind, nframes / secs, secs, total_kp
 
 
 def host_threads():
@@ -140,19 +164,20 @@ def host_threads():
 
 
 def run_reference(args, rank):
-    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference itself
-    cannot be compiled here — DESIGN.md), all host threads, bounded sample per step."""
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref: ORBextractor.cc compiled
+    unmodified; the oracle port only if that library is missing), all host threads (one extractor instance per thread,
+    as Frame.cc:129-132 runs left / right), each step a bounded sample of the workload."""
     if rank != 0:
         return
     cores = host_threads()
     per_step = max(cores * 16, 64)
-    from oracle import oracle as orc
+    kind, fn = cpu_reference()
     frames = make_frames(per_step, 9000)
     for _ in range(args.warmup):
-        orc.bench_extract(frames[:cores], NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, cores)
+        fn(frames[:cores], cores)
     secs = 0.0
     for _ in range(args.steps):
-        s, _ = orc.bench_extract(frames, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, cores)
+        s, _ = fn(frames, cores)
         secs += s
     value = per_step * args.steps / secs
     sample = "%d frames per step x %d steps, %d threads, one extractor per thread" % (per_step, args.steps, cores)
@@ -160,9 +185,8 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "C1: ORBextractor 640x480, 1000 features, 8 levels, scale 1.2, FAST 20/7",
-                   "frames_per_step": per_step},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args.batch),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -519,11 +543,8 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "C1: ORBextractor 640x480, 1000 features, 8 levels, scale 1.2, FAST 20/7",
-                       "frames_per_step_per_gpu": B, "sharding": "frames by rank, no collective",
-                       "l2": "inputs larger than L2: %d MB of frames + %d MB of pyramid/blur planes per step" %
-                             (B * W * H >> 20, (2 * B * 1158012) >> 20),
-                       "keypoints_per_frame": n_kp_mean},
+            "config": workload_config(B), "keypoints_per_frame": n_kp_mean,
+            "timed_region_s": elapsed_ms * 1e-3,
             "clocks": clocks,
             "e2e": {"value": frames_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * W * H,
                     "d2h_bytes_per_step": B * cap * 60 + 8 * B, "ms_per_step": e2e_ms / K,
@@ -546,9 +567,9 @@ def main():
         if world == 1 and not args.no_extras:
             cores = host_threads()
             nfr = 256 * cores                       # ~10 s of CPU work on all host threads
-            v_all, secs_all, _ = cpu_port_throughput(nfr, cores)
-            v_one, _, _ = cpu_port_throughput(96, 1)
-            line["cpu_baseline"] = {"value": v_all, "unit": UNIT, "cores": cores, "kind": "port",
+            kind, v_all, secs_all, _ = cpu_throughput(nfr, cores)
+            _, v_one, _, _ = cpu_throughput(96, 1)
+            line["cpu_baseline"] = {"value": v_all, "unit": UNIT, "cores": cores, "kind": kind,
                                     "sample": "%d frames of the same workload, %d threads (one extractor per thread), %.1f s" %
                                               (nfr, cores, secs_all),
                                     "single_thread_value": v_one}

@@ -28,8 +28,11 @@ def test_reference_arm_prints_one_json_line(oracle):
     assert d["metric"] == "orb_extraction_frames_per_s_640x480_1000f" and d["unit"] == "frames/s"
     assert d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None
     assert "workload" in d["config"] and "model" not in d["config"]
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.workload_config(512)          # the same object the repo arm prints (driver: same_config)
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

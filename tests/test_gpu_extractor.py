@@ -69,7 +69,6 @@ def test_stage_parity_on_golden_cases(oracle, case):
     assert got[0] == meta["mono_index"] and len(got[1]) == meta["n_keypoints"]
     if len(got[1]):
         _compare_outputs(got, (meta["mono_index"], gold["keypoints"], gold["descriptors"]), name + "/golden")
-        assert np.array_equal(got[2], gold["descriptors"]) or True
 
 
 def test_descriptors_are_bit_exact_on_synthetic_frames(oracle):
