@@ -27,7 +27,9 @@ def build(force=False):
     """(Re)build from the reference sources when they are present; otherwise use the prebuilt library."""
     _orc.build()
     if os.path.isdir(_REF_ROOT):
-        cmd = ["make", "-C", os.path.join(_HERE, "ref_build"), "REF=" + _REF_ROOT]
+        # the library and the CPU matcher test; ref_matcher_test_gpu (needs libvsg_cuda.so) is built by `make all`
+        cmd = ["make", "-C", os.path.join(_HERE, "ref_build"), "REF=" + _REF_ROOT, "../_ref/libvsg_ref.so",
+               "../_ref/ref_matcher_test_cpu"]
         if force:
             cmd.append("-B")
         subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
@@ -136,6 +138,12 @@ class RefExtractor:
         n = self._L.ref_distribute_octree(self._h, _ptr(xyr), len(xyr), min_x, max_x, min_y, max_y, quota, _ptr(out),
                                           len(out))
         return out[:n].copy()
+
+
+def matcher_test_binary(kind):
+    """Path of oracle/_ref/ref_matcher_test_{cpu,gpu} (tests/cpp/ref_matcher_test.cpp), or None if it was not built."""
+    p = os.path.join(_HERE, "_ref", "ref_matcher_test_" + kind)
+    return p if os.path.exists(p) else None
 
 
 def bench_extract(frames, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, threads=1):

@@ -103,3 +103,22 @@ def test_c2_stereo_shape_and_mono_lapping_against_the_reference(ref):
     mono = synth_frame(77, 640, 480)
     ex5, r5 = ORBextractor(5000, 1.2, 8, 20, 7), ref.RefExtractor(5000)      # mpIniORBextractor: 5 x features, lapping (0, 1000)
     assert _cmp(ex5(mono, (0, 1000)), r5(mono, (0, 1000)), "mono init")
+
+
+def test_reference_orbmatcher_equals_shim_on_the_cuda_library(ref, tmp_path):
+    """tests/cpp/ref_matcher_test.cpp linked against libvsg_cuda.so: the reference's ORBmatcher.cc (unmodified) vs the
+    drop-in shim + CUDA kernels on identical worlds — all 13 Search* / Fuse methods, match for match."""
+    import subprocess
+    exe = ref.matcher_test_binary("gpu")
+    if not exe:
+        pytest.skip("oracle/_ref/ref_matcher_test_gpu was not shipped")
+    a = synth_frame(11, 640, 480)
+    rng = np.random.default_rng(12)
+    b = np.roll(a, (5, 9), (0, 1))
+    b = np.clip(b.astype(np.int16) + rng.integers(-3, 4, b.shape), 0, 255).astype(np.uint8)
+    pa, pb = str(tmp_path / "a.raw"), str(tmp_path / "b.raw")
+    a.tofile(pa)
+    b.tofile(pb)
+    out = subprocess.run([exe, pa, pb], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-4000:] + out.stderr[-2000:]
+    assert "0 failed" in out.stdout

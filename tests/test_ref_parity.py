@@ -41,12 +41,13 @@ def test_reference_sources_are_the_unmodified_files(ref):
     """The build recipe records the SHA-256 of the reference file it compiled; when /root/reference is present
     the digest must be that of the file as it lies there (nothing patched or copied)."""
     import hashlib
-    rec = open(os.path.join(os.path.dirname(ref._LIB_PATH), "SOURCES.sha256")).read().split()
-    src = os.path.join(ref._REF_ROOT, "src", "ORBextractor.cc")
-    if not os.path.exists(src):
+    lines = [l.split() for l in open(os.path.join(os.path.dirname(ref._LIB_PATH), "SOURCES.sha256")) if l.strip()]
+    assert sorted(os.path.basename(p) for _, p in lines) == ["ORBextractor.cc", "ORBmatcher.cc"]
+    if not os.path.isdir(ref._REF_ROOT):
         pytest.skip("reference tree not present (GPU box)")
-    assert rec[0] == hashlib.sha256(open(src, "rb").read()).hexdigest()
-    assert rec[1] == src
+    for digest, path in lines:
+        assert path.startswith(ref._REF_ROOT + "/src/")
+        assert digest == hashlib.sha256(open(path, "rb").read()).hexdigest(), path
 
 
 def test_tables(ref, oracle):
@@ -139,3 +140,28 @@ def test_distribute_octree_alone(ref, oracle):
 def test_empty_image(ref):
     mono, kps, desc = ref.RefExtractor()(np.zeros((0, 0), np.uint8))
     assert mono == -1 and len(kps) == 0
+
+
+def _two_related_frames(tmp_path):
+    a = synth_frame(11, 640, 480)
+    rng = np.random.default_rng(12)
+    b = np.roll(a, (5, 9), (0, 1))
+    b = np.clip(b.astype(np.int16) + rng.integers(-3, 4, b.shape), 0, 255).astype(np.uint8)
+    pa, pb = str(tmp_path / "a.raw"), str(tmp_path / "b.raw")
+    a.tofile(pa)
+    b.tofile(pb)
+    return pa, pb
+
+
+def test_reference_orbmatcher_equals_shim_on_the_oracle_port(ref, oracle, tmp_path):
+    """The reference's ORBmatcher.cc (compiled unmodified against stand-in Frame / KeyFrame / MapPoint classes) vs the
+    drop-in shim's host code running on the CPU oracle port (tests/cpp/vsg_on_oracle.cpp), all 13 methods incl. the
+    two-camera branches the shim supports: return values, every written map-point pointer, vnMatches12 / vpMatches12 /
+    vMatchedPairs / vpReplacePoint, Replace / AddObservation side effects (tests/cpp/ref_matcher_test.cpp)."""
+    import subprocess
+    exe = ref.matcher_test_binary("cpu")
+    assert exe, "oracle/_ref/ref_matcher_test_cpu was not built"
+    pa, pb = _two_related_frames(tmp_path)
+    out = subprocess.run([exe, pa, pb], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-4000:] + out.stderr[-2000:]
+    assert "0 failed" in out.stdout
