@@ -81,7 +81,7 @@ __device__ __forceinline__ void blur_strip(const uint8_t *__restrict__ src, int 
     }
 }
 
-// One blur work block (kBlurThreads threads) of frame `frame`: block `blur_block` of the per-level block table.
+// One blur work block (blockDim.x threads) of frame `frame`: block `blur_block` of the per-level block table.
 __device__ __forceinline__ void blur_block_body(const FrameGeom &g, const BlurLevels &bl, const uint8_t *__restrict__ lvl0_base,
                                                 int lvl0_pitch, int64_t lvl0_stride, const uint8_t *__restrict__ pyr,
                                                 uint8_t *__restrict__ blur, int blur_block, int frame) {
@@ -94,7 +94,7 @@ __device__ __forceinline__ void blur_block_body(const FrameGeom &g, const BlurLe
     else { src = pyr + L.plane_offset + (int64_t)frame * L.plane_stride; spitch = L.pitch; }
     uint8_t *dst = blur + L.plane_offset + (int64_t)frame * L.plane_stride;
 
-    const int item = (blur_block - bl.block_begin[level]) * kBlurThreads + threadIdx.x;
+    const int item = (blur_block - bl.block_begin[level]) * (int)blockDim.x + threadIdx.x;   // bl was built for this block size
     const int n_int = bl.n_int_cg[level], n_edge = bl.n_edge_cg[level];
     const int items_int = bl.n_strips[level] * n_int;
     if (item < items_int) {
@@ -112,7 +112,7 @@ __device__ __forceinline__ void blur_block_body(const FrameGeom &g, const BlurLe
 // Block table of one launch (host side).
 // Few frames in flight: the GPU is not full and a strip is a serial chain of row loads, so strips are kept short (more,
 // shorter threads); large batches amortise the 6-row prologue of a strip over 32 rows.
-inline BlurLevels make_blur_levels(const FrameGeom &g, int nframes) {
+inline BlurLevels make_blur_levels(const FrameGeom &g, int nframes, int threads = kBlurThreads) {
     BlurLevels bl;
     bl.nlevels = g.nlevels;
     bl.rows = nframes <= 8 ? kBlurRowsSmallBatch : kBlurRows;
@@ -128,7 +128,7 @@ inline BlurLevels make_blur_levels(const FrameGeom &g, int nframes) {
         bl.n_int_cg[l] = n_int;
         bl.n_edge_cg[l] = ncg - n_int;
         bl.n_strips[l] = (h + bl.rows - 1) / bl.rows;
-        total += (bl.n_strips[l] * ncg + kBlurThreads - 1) / kBlurThreads;
+        total += (bl.n_strips[l] * ncg + threads - 1) / threads;
     }
     bl.block_begin[g.nlevels] = total;
     return bl;

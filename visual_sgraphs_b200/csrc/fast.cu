@@ -31,16 +31,19 @@ __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) { uint32_t d; a
 __device__ __forceinline__ uint32_t min3(uint32_t a, uint32_t b, uint32_t c) { return min2(min2(a, b), c); }   // fused to VIMNMX3
 __device__ __forceinline__ uint32_t max3(uint32_t a, uint32_t b, uint32_t c) { return max2(max2(a, b), c); }
 
-constexpr int kFastThreads = 128;
-constexpr int kLoadIters = 3;      // 3 x 16 rows of 8 quads cover the usual 44-row cell without a loop
-// Row pitches of the two shared-memory planes, in words.  A warp's 32 consecutive pairs p = iy * S + j sit at word
-// iy * pitch + j + const = p + iy * (pitch - S) + const: with pitch = S + 32 every ring / neighbour read of a warp is
-// bank-conflict free.  S = 20 for every full cell of the usual 35..40-pixel grids, so the pitch is the constant 52 (a
-// run-time pitch costs more address arithmetic than the conflicts); other S only see the usual
-// two-way conflicts.  Minimum sizes: 3 (alignment) + S + 6 halo columns rounded to 4 for the pixel pairs, S + 2 for
-// the strengths.
+constexpr int kFastThreads = 160;
+#ifndef VSG_FAST_MINB
+#define VSG_FAST_MINB 6   // resident CTAs per SM the register budget is sized for (6 x 160 threads, 64 registers)
+#endif
+// Row pitches of the two shared-memory planes, in words.  Thread t of the CTA owns pair column j = t % S of row t / S, so a
+// warp's 32 consecutive pairs p = row * S + j sit at word row * pitch + j + const = p + row * (pitch - S) + const: with
+// pitch = S + 32 every ring / neighbour read of a warp is bank-conflict free.  S = 20 for every full cell of the usual
+// 35..40-pixel grids, so the pitch is the constant 52 (a run-time pitch costs more address arithmetic than the conflicts);
+// other S only see two-way conflicts on a few lanes.  Minimum sizes: 3 (alignment) + S + 6 halo columns rounded to 4 for
+// the pixel pairs, S + 2 for the strengths.
 constexpr int kT2Pitch = 52;
 constexpr int kS2Pitch = 52;
+constexpr int kMaxS = 28;
 
 // The 16-pixel Bresenham ring in OpenCV's order: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)
 // (-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3).  Strength K of both pixels of the pair at c: max over the 16
@@ -73,20 +76,16 @@ __device__ __forceinline__ uint32_t fast_strength2(const uint32_t *c) {
     return max2(max2(best_lo, v) - v, v - min2(best_hi, v));
 }
 
-// Flattened (row, pair) iteration without divisions: index i -> i + kFastThreads.
-struct PairIter {
-    int iy, j, di, dj, S;
-    __device__ PairIter(int tid, int S_) : S(S_) {
-        iy = tid / S_; j = tid - iy * S_;
-        di = kFastThreads / S_; dj = kFastThreads - di * S_;
-    }
-    __device__ __forceinline__ void next() {
-        j += dj; iy += di;
-        if (j >= S) { j -= S; ++iy; }
-    }
-};
+// thread -> (row, pair column) of a sweep: row = t / S by a multiply-high with ceil(2^32 / S); S is a multiple of 4
+__constant__ uint32_t kRcpS[kMaxS / 4 + 1] = {0u, 0x40000000u, 0x20000000u, 0x15555556u, 0x10000000u, 0x0CCCCCCDu, 0x0AAAAAABu, 0x0924924Au};
+__constant__ uint8_t kRowsPerSweep[kMaxS / 4 + 1] = {0, 40, 20, 13, 10, 8, 6, 5};   // kFastThreads / S
 
 // One FAST cell (kFastThreads threads): cell `cell_block` of the frame's flat cell table.
+//
+// Work layout: thread t owns pair column j = t % S and walks down the cell in sweeps of RB = kFastThreads / S rows
+// (rows t / S, t / S + RB, ...), for the strength pass and again for the NMS pass.  The column never changes, so the
+// column masks, the shared-memory pointers and the survivor coordinates need no per-iteration index arithmetic: one
+// pointer increment per sweep.
 __device__ __forceinline__ void fast_cell_body(const FrameGeom &g, const uint8_t *__restrict__ lvl0_base, int lvl0_pitch,
                                                int64_t lvl0_stride, const uint8_t *__restrict__ pyr,
                                                Cand *__restrict__ cand, int *__restrict__ cand_count, int ini_th,
@@ -99,67 +98,64 @@ __device__ __forceinline__ void fast_cell_body(const FrameGeom &g, const uint8_t
 
     // cell geometry from the level tables (kernel parameters): no dependent global load at kernel start.
     // Valid cells of a level form a rows_eff x cols_eff prefix of the reference's grid (:811-828).
-    Cell cell;
-    {
-        int level = 0;
-        while (level + 1 < g.nlevels && cell_block >= g.lv[level + 1].cell_begin) ++level;
-        const LevelGeom &G = g.lv[level];
-        const int local = cell_block - G.cell_begin;
-        const int ci = local / G.cols_eff, cj = local - ci * G.cols_eff;
-        cell.level = (short)level;
-        cell.x0 = (short)(kBorderMin + cj * G.w_cell);
-        cell.y0 = (short)(kBorderMin + ci * G.h_cell);
-        cell.cw = (short)(min(cell.x0 + G.w_cell + 6, G.w - kBorderMin) - cell.x0);
-        cell.ch = (short)(min(cell.y0 + G.h_cell + 6, G.h - kBorderMin) - cell.y0);
-    }
-    const LevelGeom &L = g.lv[cell.level];
+    int level = 0;       // cell_begin of the levels past nlevels is INT_MAX (vsg_api.cu)
+#pragma unroll
+    for (int l = 1; l < 8; ++l) level += cell_block >= g.lv[l].cell_begin ? 1 : 0;
+    for (int l = 8; l < g.nlevels; ++l) level += cell_block >= g.lv[l].cell_begin ? 1 : 0;
+    const LevelGeom &L = g.lv[level];
+    const int local = cell_block - L.cell_begin;
+    const int ci = (int)__umulhi((uint32_t)local, L.cols_rcp), cj = local - ci * L.cols_eff;
+    const int x0 = kBorderMin + cj * L.w_cell, y0 = kBorderMin + ci * L.h_cell;
+    const int cw = min(x0 + L.w_cell + 6, L.w - kBorderMin) - x0;
+    const int ch = min(y0 + L.h_cell + 6, L.h - kBorderMin) - y0;
     const uint8_t *src;
     int spitch;
-    if (cell.level == 0) { src = lvl0_base + (int64_t)frame * lvl0_stride; spitch = lvl0_pitch; }
+    if (level == 0) { src = lvl0_base + (int64_t)frame * lvl0_stride; spitch = lvl0_pitch; }
     else { src = pyr + L.plane_offset + (int64_t)frame * L.plane_stride; spitch = L.pitch; }
 
     const int tid = threadIdx.x;
-    const int iw = cell.cw - 6, ih = cell.ch - 6;  // interior = FAST's [3,w-3) x [3,h-3)
+    const int iw = cw - 6, ih = ch - 6;            // interior = FAST's [3,w-3) x [3,h-3)
     // lane 0 of a pair holds window column b, lane 1 column b + S; S is a multiple of 4 so that both halves of
     // four consecutive pairs come from two aligned 32-bit global loads
     const int S = (((iw + 1) >> 1) + 3) & ~3;
-    const int ax0 = cell.x0 & ~3;                  // 4-byte aligned origin of the pair columns
-    const int xoff = cell.x0 - ax0;                // window column w sits at pair column xoff + w
+    const int ax0 = x0 & ~3;                       // 4-byte aligned origin of the pair columns
+    const int xoff = x0 - ax0;                     // window column w sits at pair column xoff + w
     {
         const int nq = (xoff + S + 6 + 3) >> 2;    // quads of pair columns per row (7..9 typical, <= 12)
-        const uint8_t *base = src + (int64_t)cell.y0 * spitch + ax0;
+        const uint8_t *base = src + (int64_t)y0 * spitch + ax0;
         // thread -> (row, quad) by shift/mask: 8 (or 16) quad slots per row, threads beyond nq idle
         const int lq = nq <= 8 ? 3 : 4;
         const int q = tid & ((1 << lq) - 1), r0 = tid >> lq, rstep = kFastThreads >> lq;
         const bool qok = q < nq;
+        const uint8_t *row = base + (int64_t)r0 * spitch + 4 * q;
+        const int64_t rinc = (int64_t)rstep * spitch;
+        uint32_t *dst = t2 + r0 * kT2Pitch + 4 * q;
         // all global loads of the CTA are issued before the first one is consumed
+        constexpr int kLoadIters = 3;              // 3 x 20 rows of 8 quads cover the usual 44-row cell without a loop
         uint32_t a[kLoadIters], b[kLoadIters];
 #pragma unroll
         for (int it = 0; it < kLoadIters; ++it) {
-            const int r = r0 + it * rstep;
-            if (qok && r < cell.ch) {
-                const uint8_t *row = base + (int64_t)r * spitch + 4 * q;
-                a[it] = __ldg(reinterpret_cast<const uint32_t *>(row));
+            if (qok && r0 + it * rstep < ch) {
+                a[it] = __ldg(reinterpret_cast<const uint32_t *>(row + it * rinc));
                 // the second half may reach past the window, never past the image row (x0 + cw <= W - 16)
-                b[it] = __ldg(reinterpret_cast<const uint32_t *>(row + S));
+                b[it] = __ldg(reinterpret_cast<const uint32_t *>(row + it * rinc + S));
             }
         }
 #pragma unroll
         for (int it = 0; it < kLoadIters; ++it) {
-            const int r = r0 + it * rstep;
-            if (qok && r < cell.ch) {
+            if (qok && r0 + it * rstep < ch) {
                 uint4 o;
                 o.x = __byte_perm(a[it], b[it], 0x7470) & 0x00FF00FFu;   // [a0, -, b0, -]
                 o.y = __byte_perm(a[it], b[it], 0x7571) & 0x00FF00FFu;
                 o.z = __byte_perm(a[it], b[it], 0x7672) & 0x00FF00FFu;
                 o.w = __byte_perm(a[it], b[it], 0x7773) & 0x00FF00FFu;
-                *reinterpret_cast<uint4 *>(t2 + r * kT2Pitch + 4 * q) = o;
+                *reinterpret_cast<uint4 *>(dst + it * rstep * kT2Pitch) = o;
             }
         }
-        for (int r = r0 + kLoadIters * rstep; qok && r < cell.ch; r += rstep) {   // taller cells
-            const uint8_t *row = base + (int64_t)r * spitch + 4 * q;
-            const uint32_t aa = __ldg(reinterpret_cast<const uint32_t *>(row));
-            const uint32_t bb = __ldg(reinterpret_cast<const uint32_t *>(row + S));
+        for (int r = r0 + kLoadIters * rstep; qok && r < ch; r += rstep) {   // taller cells
+            const uint8_t *rp = base + (int64_t)r * spitch + 4 * q;
+            const uint32_t aa = __ldg(reinterpret_cast<const uint32_t *>(rp));
+            const uint32_t bb = __ldg(reinterpret_cast<const uint32_t *>(rp + S));
             uint4 o;
             o.x = __byte_perm(aa, bb, 0x7470) & 0x00FF00FFu;
             o.y = __byte_perm(aa, bb, 0x7571) & 0x00FF00FFu;
@@ -173,80 +169,65 @@ __device__ __forceinline__ void fast_cell_body(const FrameGeom &g, const uint8_t
         s2[(ih + 1) * kS2Pitch + i] = 0;
     }
     if (tid == 0) s_count = 0;
+
+    // this thread's place in a sweep
+    const int RB = kRowsPerSweep[S >> 2];
+    const int trow = (int)__umulhi((uint32_t)tid, kRcpS[S >> 2]);
+    const int j = tid - trow * S;
+    const int row0 = trow < RB ? trow : ih;                  // the last kFastThreads - S * RB threads sit the sweeps out
+    // lane 0 is interior column j, lane 1 column j + S; columns >= iw do not exist
+    const uint32_t kmask = (j < iw ? 0x0000FFFFu : 0u) | (j + S < iw ? 0xFFFF0000u : 0u);
     __syncthreads();
 
-    const uint32_t *t2c = t2 + 3 * kT2Pitch + xoff + 3;      // pair (row 0, interior column 0)
-    const int npairs = S * ih;
-    for (PairIter it(tid, S); it.iy < ih; it.next()) {
-        uint32_t K = fast_strength2(t2c + it.iy * kT2Pitch + it.j);
-        if (it.j + S >= iw) K &= 0x0000FFFFu;                // no second pixel in this pair
-        if (it.j >= iw) K = 0;
-        s2[(it.iy + 1) * kS2Pitch + it.j + 1] = K;
-    }
-    __syncthreads();
-    // the two halves meet in the middle: column S-1 (lane 0) and column S (lane 1) are neighbours
-    for (int iy = tid; iy < ih; iy += kFastThreads) {
-        uint32_t *row = s2 + (iy + 1) * kS2Pitch;
-        row[0] = row[S] << 16;          // left apron:  lane 0 = outside the cell (0), lane 1 = K(S-1)
-        row[S + 1] = row[1] >> 16;      // right apron: lane 0 = K(S), lane 1 = outside the cell (0)
+    {
+        const uint32_t *c = t2 + (3 + row0) * kT2Pitch + xoff + 3 + j;   // pair (row, interior column j)
+        uint32_t *k = s2 + (row0 + 1) * kS2Pitch + j + 1;
+        // the two halves meet in the middle: column S-1 (lane 0 of the last pair) and column S (lane 1 of the first pair)
+        // are neighbours; their owners also write the two apron pairs of the row
+        const bool first = j == 0, last = j == S - 1;
+        for (int row = row0; row < ih; row += RB, c += RB * kT2Pitch, k += RB * kS2Pitch) {
+            const uint32_t K = fast_strength2(c) & kmask;
+            *k = K;
+            if (last) k[-S] = K << 16;      // left apron:  lane 0 = outside the cell (0), lane 1 = K(S-1)
+            if (first) k[S] = K >> 16;      // right apron: lane 0 = K(S), lane 1 = outside the cell (0)
+        }
     }
     __syncthreads();
 
-    const int lane = tid & 31;
     for (int pass = 0; pass < 2; ++pass) {
         const int t = pass == 0 ? ini_th : min_th;
         const int tt = max(t, 1);       // a corner scoring 0 (K == 1, only possible at t == 0) never survives the NMS
-        // Survivors are only flagged inside the loop (bit `iter` of m0 / m1 for the two pixels of the pair); the
-        // compaction runs once per pass after it: one warp scan, one shared-memory atomic per warp.
-        // Per iteration the pair's two survivor flags are produced in packed form — K - min(K, max(nb, tt)) is
-        // non-zero in a lane iff that pixel beats the threshold and all 8 neighbours — and accumulated as bit `iter`
-        // of the two 16-bit lanes of acc[iter / 16] by a multiply-add (FMA pipe, not the ALU pipe the min/max use).
+        // Per sweep the pair's two survivor flags are produced in packed form — K - min(K, max(nb, tt)) is non-zero in
+        // a lane iff that pixel beats the threshold and all 8 neighbours — and accumulated as bit `sweep` of the two
+        // 16-bit lanes of acc by a multiply-add (FMA pipe, not the ALU pipe the min/max use).  At most 16 sweeps
+        // (checked by the launcher).
         const uint32_t tt2 = (uint32_t)tt * 0x00010001u;
-        uint32_t acc[2] = {0, 0};
-        PairIter it(tid, S);
-        int base = 0;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            uint32_t pw = 1;
-            for (int iter = 0; iter < 16 && base < npairs; ++iter, base += kFastThreads, it.next(), pw <<= 1) {
-                // lanes past the last pair read the (all-zero) top apron row and flag nothing: no branch around the loads
-                const uint32_t *c = s2 + (it.iy < ih ? (it.iy + 1) * kS2Pitch + it.j + 1 : 1);
-                const uint32_t K = c[0];
-                // strict maximum over the 8 neighbours: neighbours that are not corners at t are below K anyway
-                const uint32_t nb = max3(max3(c[-kS2Pitch - 1], c[-kS2Pitch], c[-kS2Pitch + 1]),
-                                         max3(c[-1], c[1], c[kS2Pitch - 1]), max2(c[kS2Pitch], c[kS2Pitch + 1]));
-                const uint32_t e = K - min2(K, max2(nb, tt2));
-                acc[half] += min2(e, 0x00010001u) * pw;
-            }
+        uint32_t acc = 0, pw = 1;
+        const uint32_t *c = s2 + (row0 + 1) * kS2Pitch + j + 1;
+        for (int row = row0; row < ih; row += RB, c += RB * kS2Pitch, pw <<= 1) {
+            const uint32_t K = c[0];
+            // strict maximum over the 8 neighbours: neighbours that are not corners at t are below K anyway
+            const uint32_t nb = max3(max3(c[-kS2Pitch - 1], c[-kS2Pitch], c[-kS2Pitch + 1]),
+                                     max3(c[-1], c[1], c[kS2Pitch - 1]), max3(c[kS2Pitch], c[kS2Pitch + 1], tt2));
+            const uint32_t e = K - min2(K, nb);
+            acc += min2(e, 0x00010001u) * pw;
         }
-        uint32_t m0 = (acc[0] & 0xFFFFu) | (acc[1] << 16);
-        uint32_t m1 = (acc[0] >> 16) | (acc[1] & 0xFFFF0000u);
-        const int cnt = __popc(m0) + __popc(m1);
-        int incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += v;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total > 0) {                                                    // warp-uniform
-            int wbase = 0;
-            if (lane == 31) wbase = atomicAdd(&s_count, total);
-            wbase = __shfl_sync(0xffffffffu, wbase, 31);
-            int pos = wbase + incl - cnt;
+        const int cnt = __popc(acc);
+        if (cnt) {
+            int pos = atomicAdd(&s_count, cnt);
+            uint32_t m0 = acc & 0xFFFFu, m1 = acc >> 16;
+            const uint32_t *kcol = s2 + (row0 + 1) * kS2Pitch + j + 1;
             while (m0) {
                 const int i = __ffs(m0) - 1;
                 m0 &= m0 - 1;
-                const int p = tid + i * kFastThreads, iy = p / S, j = p - iy * S;
-                const uint32_t K = s2[(iy + 1) * kS2Pitch + j + 1] & 0xFFFFu;
-                list[pos++] = (uint32_t)j | ((uint32_t)iy << 8) | ((K - 1) << 16);
+                const uint32_t K = kcol[i * RB * kS2Pitch] & 0xFFFFu;
+                list[pos++] = (uint32_t)j | ((uint32_t)(row0 + i * RB) << 8) | ((K - 1) << 16);
             }
             while (m1) {
                 const int i = __ffs(m1) - 1;
                 m1 &= m1 - 1;
-                const int p = tid + i * kFastThreads, iy = p / S, j = p - iy * S;
-                const uint32_t K = s2[(iy + 1) * kS2Pitch + j + 1] >> 16;
-                list[pos++] = (uint32_t)(j + S) | ((uint32_t)iy << 8) | ((K - 1) << 16);
+                const uint32_t K = kcol[i * RB * kS2Pitch] >> 16;
+                list[pos++] = (uint32_t)(j + S) | ((uint32_t)(row0 + i * RB) << 8) | ((K - 1) << 16);
             }
         }
         __syncthreads();
@@ -254,7 +235,7 @@ __device__ __forceinline__ void fast_cell_body(const FrameGeom &g, const uint8_t
     }
     const int n = min(s_count, list_cap);
     if (n == 0) return;
-    const int slot_idx = frame * g.nlevels + cell.level;
+    const int slot_idx = frame * g.nlevels + level;
     if (tid == 0) s_base = atomicAdd(&cand_count[slot_idx], n);
     __syncthreads();
     Cand *out = cand + L.cand_offset + (int64_t)frame * g.cand_total;
@@ -263,15 +244,15 @@ __device__ __forceinline__ void fast_cell_body(const FrameGeom &g, const uint8_t
         if (dst >= L.cand_cap) break;
         const uint32_t e = list[i];
         Cand c;
-        c.x = (unsigned short)(cell.x0 + 3 + (e & 0xff));
-        c.y = (unsigned short)(cell.y0 + 3 + ((e >> 8) & 0xff));
+        c.x = (unsigned short)(x0 + 3 + (e & 0xff));
+        c.y = (unsigned short)(y0 + 3 + ((e >> 8) & 0xff));
         c.score = (unsigned short)(e >> 16);
         c.pad = 0;
         out[dst] = c;
     }
 }
 
-__global__ void __launch_bounds__(kFastThreads, 8) fast_kernel(FrameGeom g,
+__global__ void __launch_bounds__(kFastThreads, VSG_FAST_MINB) fast_kernel(FrameGeom g,
                                                              const uint8_t *__restrict__ lvl0_base, int lvl0_pitch,
                                                              int64_t lvl0_stride, const uint8_t *__restrict__ pyr,
                                                              Cand *__restrict__ cand, int *__restrict__ cand_count,
@@ -289,22 +270,19 @@ __global__ void __launch_bounds__(kFastThreads, 8) fast_kernel(FrameGeom g,
 //   x < nblur * (ratio + 1):  group x / (ratio + 1); position x % (ratio + 1) < ratio is cell group*ratio + position,
 //                             position == ratio is blur block `group`;
 //   beyond that:              the remaining cells.
-static_assert(kFastThreads == kBlurThreads, "the fused kernel runs both roles with the same block size");
-#ifndef VSG_FAST_MINB
-#define VSG_FAST_MINB 8
-#endif
 __global__ void __launch_bounds__(kFastThreads, VSG_FAST_MINB) fast_blur_kernel(FrameGeom g, BlurLevels bl,
                                                                   const uint8_t *__restrict__ lvl0_base, int lvl0_pitch,
                                                                   int64_t lvl0_stride, const uint8_t *__restrict__ pyr,
                                                                   uint8_t *__restrict__ blur, Cand *__restrict__ cand,
                                                                   int *__restrict__ cand_count, int ini_th, int min_th,
-                                                                  int tile_rows, int list_cap, int nblur, int ratio) {
+                                                                  int tile_rows, int list_cap, int nblur, int ratio,
+                                                                  uint32_t group_rcp) {
     pdl_launch_dependents();
     pdl_wait();
     const int x = blockIdx.x, group = ratio + 1;
     int cell;
     if (x < nblur * group) {
-        const int gi = x / group, pos = x - gi * group;
+        const int gi = group == 1 ? x : (int)__umulhi((uint32_t)x, group_rcp), pos = x - gi * group;   // x / group
         if (pos == ratio) {
             blur_block_body(g, bl, lvl0_base, lvl0_pitch, lvl0_stride, pyr, blur, gi, blockIdx.y);
             return;
@@ -327,8 +305,9 @@ vsg_status launch_fast(const FrameGeom &g, const Cell *cells, const uint8_t *lvl
         return VSG_OK;
     }
     const int max_S = ((((max_cw - 6) + 1) >> 1) + 3) & ~3;
-    if (3 + max_S + 6 + 3 > kT2Pitch || max_S + 2 > kS2Pitch || max_S * (max_ch - 6) > 32 * kFastThreads) {
-        set_error("FAST cell larger than the shared-memory tile / the 32-iteration survivor masks");
+    // at most 16 sweeps of kFastThreads / S rows (the survivor flags of a thread are the 16-bit lanes of one register)
+    if (3 + max_S + 6 + 3 > kT2Pitch || max_S + 2 > kS2Pitch || max_S > kMaxS || (max_ch - 6) > 16 * (kFastThreads / max_S)) {
+        set_error("FAST cell larger than the shared-memory tile / the 16-sweep survivor masks");
         return VSG_ERR_INVALID;
     }
     const int tile_rows = max_ch;
@@ -342,11 +321,13 @@ vsg_status launch_fast(const FrameGeom &g, const Cell *cells, const uint8_t *lvl
         launch_kernel(fast_kernel, dim3(g.ncells, nframes), dim3(kFastThreads), smem, s, true, g, lvl0_base, lvl0_pitch,
                       lvl0_stride, pyr, cand, cand_count, ini_th, min_th, tile_rows, list_cap);
     } else {
-        const BlurLevels bl = make_blur_levels(g, nframes);
+        const BlurLevels bl = make_blur_levels(g, nframes, kFastThreads);   // blur blocks of the fused grid have the FAST block size
         const int nblur = bl.block_begin[g.nlevels];
         const int ratio = g.ncells / nblur;
+        const uint32_t group_rcp = (uint32_t)((0x100000000ull + (uint64_t)ratio) / (uint64_t)(ratio + 1));   // ceil(2^32 / group)
         launch_kernel(fast_blur_kernel, dim3(g.ncells + nblur, nframes), dim3(kFastThreads), smem, s, true, g, bl, lvl0_base,
-                      lvl0_pitch, lvl0_stride, pyr, blur, cand, cand_count, ini_th, min_th, tile_rows, list_cap, nblur, ratio);
+                      lvl0_pitch, lvl0_stride, pyr, blur, cand, cand_count, ini_th, min_th, tile_rows, list_cap, nblur, ratio,
+                      group_rcp);
     }
     count_launch();
     return VSG_OK;

@@ -278,6 +278,7 @@ vsg_status configure_shape(vsg_extractor *ex, int w, int h) {
             set_error("internal: level %d cell table is not a prefix rectangle", l);
             return VSG_ERR_INVALID;
         }
+        L.cols_rcp = (uint32_t)((0x100000000ull + (uint64_t)L.cols_eff - 1) / (uint64_t)std::max(L.cols_eff, 1));
         L.quota = ex->quota[l];
         L.n_ini = (int)std::round(static_cast<float>(max_bx - min_b) / (max_by - min_b));   // :566
         if (L.n_ini < 1) {
@@ -298,6 +299,7 @@ vsg_status configure_shape(vsg_extractor *ex, int w, int h) {
             build_resize_tables(g.lv[l - 1].w, g.lv[l - 1].h, L.w, L.h, (int)align_up(L.w, 4), xts[l], yts[l]);
     }
     g.ncells = (int)ex->cells_h.size();
+    for (int l = nl; l < kMaxLevels; ++l) g.lv[l].cell_begin = 0x7fffffff;   // fast.cu finds a cell's level by counting begins <= cell
     g.cand_total = cand_off;
     g.kp_total = kp_off;
     g.out_cap = kp_off;
