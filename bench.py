@@ -190,7 +190,7 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def latency_extras(torch, lib, device):
@@ -399,7 +399,127 @@ def matching_extras(torch, device):
     return out
 
 
+def sharded_matching_extras(torch, dist, local_rank, rank, world):
+    """The two matcher paths with a real exchange step, through the C ABI's communicator (vsg_comm_*: NCCL behind
+    include/vsg_cuda.h, no Python on the data path): C5 brute-force kNN-2 with the 1M train descriptors sharded over the
+    ranks (vsg_knn2_sharded: local search, ncclAllGather of the top-2 lists, (dist, idx) merge) and C3
+    SearchByProjection of a 200k-point map sharded over the ranks into a 1000-keypoint frame
+    (vsg_search_by_projection_map_sharded: claim-state token + ncclAllGather of the assignments).  Every rank's result is
+    compared with the single-GPU call on the whole set.  Runs on every rank (collective); rank 0 returns the numbers."""
+    from visual_sgraphs_b200._lib import KEYPOINT_DTYPE, TRACK_POINT_DTYPE
+    from visual_sgraphs_b200.comm import Comm
+    from visual_sgraphs_b200.frame import FrameData
+    from visual_sgraphs_b200.matcher import ORBmatcher
+    from visual_sgraphs_b200.sharded import shard_bounds
+    comm = Comm.from_torch_distributed(dist, local_rank) if world > 1 else Comm(Comm.unique_id(), 1, 0, local_rank)
+    m = ORBmatcher(nnratio=0.8, device=local_rank)
+    s = torch.cuda.ExternalStream(m.stream(), device=local_rank)
+    out = {"nccl_version": Comm.nccl_version(), "ranks": world}
+
+    def sync_all():
+        m.sync()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- C5: 100k x 1M, train rows sharded ----
+    nq, nt = 100_000, 1_000_000
+    g = torch.Generator(device="cuda").manual_seed(7)                 # same seed on every rank: same descriptors
+    q = torch.randint(0, 256, (nq, 32), dtype=torch.uint8, device="cuda", generator=g)
+    t = torch.randint(0, 256, (nt, 32), dtype=torch.uint8, device="cuda", generator=g)
+    b, e = shard_bounds(nt, world)[rank]
+    shard = t[b:e].contiguous()
+    idx = torch.zeros((nq, 2), dtype=torch.int32, device="cuda")
+    dd = torch.zeros((nq, 2), dtype=torch.int32, device="cuda")
+    m.knn2_sharded(comm, q, shard, b, idx, dd)
+    sync_all()
+    reps = 3
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(s)
+    for _ in range(reps):
+        m.knn2_sharded(comm, q, shard, b, idx, dd)
+    e1.record(s)
+    sync_all()
+    ms = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ref_i = torch.zeros_like(idx)
+    ref_d = torch.zeros_like(dd)
+    m.knn2_dev(q, t, ref_i, ref_d)                                    # the single-GPU call on the whole train set
+    m.sync()
+    same = bool(torch.equal(ref_i, idx) and torch.equal(ref_d, dd))
+    assert same, "vsg_knn2_sharded differs from vsg_knn2_dev on rank %d" % rank
+    out["c5_knn2_100k_x_1M_train_sharded"] = {"ms": float(ms[0]), "pairs_per_s": nq * nt / (float(ms[0]) * 1e-3),
+                                              "matches_per_s": nq / (float(ms[0]) * 1e-3), "identical_to_single_gpu": same,
+                                              "exchange": "ncclAllGather of %d B per rank" % (nq * 16)}
+    del q, t, shard, idx, dd, ref_i, ref_d
+    # ---- C3: 1000 keypoints x 200k map points, map sharded ----
+    rng = np.random.default_rng(3)
+    n_kp, n_map = 1000, 200_000
+    keys = np.zeros(n_kp, KEYPOINT_DTYPE)
+    keys["x"], keys["y"] = rng.uniform(20, 620, n_kp), rng.uniform(20, 460, n_kp)
+    keys["octave"] = rng.integers(0, 8, n_kp)
+    kdesc = rng.integers(0, 256, (n_kp, 32), dtype=np.uint8)
+    fdata = FrameData(keys, kdesc)
+    src = rng.integers(0, n_kp, n_map)
+    pts = np.zeros(n_map, TRACK_POINT_DTYPE)
+    pts["proj_x"] = keys["x"][src] + rng.normal(0, 2, n_map)
+    pts["proj_y"] = keys["y"][src] + rng.normal(0, 2, n_map)
+    pts["view_cos"] = rng.uniform(0.99, 1.0, n_map)
+    pts["level"] = np.clip(keys["octave"][src] + rng.integers(0, 2, n_map), 0, 7)
+    pts["in_view"], pts["blocks"] = True, rng.random(n_map) < 0.9
+    mp_desc = kdesc[src] ^ np.packbits(rng.random((n_map, 32, 8)) < 0.08, axis=2).reshape(n_map, 32)
+    occ = np.zeros(n_kp, np.uint8)
+    frame = m.frame(fdata)
+    b, e = shard_bounds(n_map, world)[rank]
+    pts_l, desc_l = pts[b:e].copy(), mp_desc[b:e].copy()
+    nm, assign = m.SearchByProjectionMapSharded(comm, frame, occ, b, pts_l, desc_l, 3.0)
+    sync_all()
+    reps = 5
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        nm, assign = m.SearchByProjectionMapSharded(comm, frame, occ, b, pts_l, desc_l, 3.0)
+    sync_all()
+    dt = torch.tensor([(time.perf_counter() - t0) / reps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    m.SearchByProjectionMap(frame, occ, pts, mp_desc, 3.0)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        nm1, assign1 = m.SearchByProjectionMap(frame, occ, pts, mp_desc, 3.0)
+    dt1 = (time.perf_counter() - t0) / reps
+    same = bool(nm == nm1 and np.array_equal(assign, assign1))
+    assert same, "vsg_search_by_projection_map_sharded differs from the one-call method on rank %d" % rank
+    out["c3_projection_1000kp_x_200k_map_sharded"] = {"ms_per_call": float(dt[0]) * 1e3, "map_points_per_s": n_map / float(dt[0]),
+                                                      "single_gpu_ms_per_call": dt1 * 1e3, "nmatches": int(nm),
+                                                      "identical_to_single_gpu": same,
+                                                      "exchange": "%d-byte claim token down the ranks + ncclAllGather of %d B per rank" %
+                                                                  (n_kp, 4 * (n_kp + 1))}
+    m.close()
+    comm.close()
+    return out
+
+
+_JSON_OUT = None
+
+
+def reserve_stdout_for_the_json_line():
+    """stdout carries exactly ONE line, the JSON result.  Anything libraries print there (NCCL prints its version line to
+    stdout) is sent to stderr instead: fd 1 is pointed at fd 2 for the whole run and the JSON line goes to the saved fd."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    reserve_stdout_for_the_json_line()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -528,6 +648,13 @@ def main():
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     elapsed_ms, e2e_ms = float(times[0]), float(times[1])
+    # the sharded matcher paths (C5 train-sharded kNN-2, C3 map-sharded SearchByProjection) at this N, every rank taking part
+    sharded_block = None
+    if not args.no_extras:
+        for hnd in handles:
+            hnd.close()
+        del kps_d, desc_d
+        sharded_block = sharded_matching_extras(torch, dist, local_rank, rank, world)
 
     if rank == 0:
         frames_total = world * B * K
@@ -564,6 +691,8 @@ def main():
                              "achieved_gbs": b_frame * B * K / (elapsed_ms * 1e-3) / 1e9,
                              "frac": b_frame * B * K / (elapsed_ms * 1e-3) / 1e9 / peak},
         }
+        if sharded_block is not None:
+            line["matching_sharded"] = sharded_block
         if world == 1 and not args.no_extras:
             cores = host_threads()
             nfr = 256 * cores                       # ~10 s of CPU work on all host threads
@@ -576,7 +705,7 @@ def main():
             line["single_frame_latency"] = latency_extras(torch, lib, local_rank)
             line["matching"] = matching_extras(torch, local_rank)
             line["other_configs"] = other_config_extras(torch, lib, local_rank)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -288,6 +288,45 @@ vsg_status vsg_projection_map_resolve(const vsg_frame_view *F, const uint8_t *oc
                                       const vsg_track_point *pts, const int32_t *cand_ptr, const int32_t *cand_idx,
                                       const int32_t *cand_dist, float nnratio, int32_t *assign_out, int *nmatches_out);
 
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink (the reference is a single CPU process) ----
+ * Only the two matcher paths with a real exchange step use a communicator; extraction shards by frame without one.
+ * vsg_comm_unique_id() is called on one rank, its 128 bytes are handed to every rank by the host application (MPI,
+ * torch.distributed, a file ...), and every rank calls vsg_comm_create with the same id.  NCCL is loaded at run time
+ * ("libnccl.so.2"); without it these calls return VSG_ERR_CUDA and everything else keeps working. */
+#define VSG_COMM_ID_BYTES 128
+typedef struct vsg_comm vsg_comm;
+vsg_status vsg_comm_unique_id(uint8_t id_out[VSG_COMM_ID_BYTES]);
+vsg_status vsg_comm_create(const uint8_t id[VSG_COMM_ID_BYTES], int nranks, int rank, int device, vsg_comm **out);
+void vsg_comm_destroy(vsg_comm *c);
+int vsg_comm_rank(const vsg_comm *c);
+int vsg_comm_size(const vsg_comm *c);
+int vsg_comm_nccl_version(void);   /* e.g. 22809; 0 if NCCL cannot be loaded */
+
+/* knnMatch(k = 2) with the TRAIN descriptors sharded over the ranks (BASELINE config 5): this rank holds nt_shard rows whose
+ * global index starts at train_index_offset; queries are replicated.  Local search, ncclAllGather of the per-rank top-2
+ * lists, (distance, index) merge on every rank: out_* equal vsg_knn2_dev on the concatenated train set.  Device pointers,
+ * asynchronous on the matcher's stream. */
+vsg_status vsg_knn2_sharded(vsg_comm *comm, vsg_matcher *m, const uint8_t *query_dev, int nq, const uint8_t *train_shard_dev,
+                            int nt_shard, int train_index_offset, int32_t *out_idx_dev, int32_t *out_dist_dev);
+
+/* vsg_search_by_projection_map with the MAP POINTS sharded over the ranks (BASELINE config 3): this rank holds the
+ * contiguous shard [shard_begin, shard_begin + n_local) of vpMapPoints (records + descriptors); F and occupied are
+ * replicated.  All ranks run the window search of their shard concurrently; the claim state (:88-90, :130) travels down the
+ * ranks as an F->n-byte token (ncclSend / ncclRecv), each rank replays its shard from it, and one ncclAllGather of the
+ * per-rank assignments gives every rank assign_out / nmatches_out identical to the one-call method on the whole map
+ * (assign_out holds GLOBAL map point indices).  Host pointers; synchronous. */
+vsg_status vsg_search_by_projection_map_sharded(vsg_comm *comm, vsg_matcher *m, const vsg_frame *F, const uint8_t *occupied,
+                                                int shard_begin, int n_local, const vsg_track_point *pts_local,
+                                                const uint8_t *desc_local, float th, int far_points, float th_far, float nnratio,
+                                                int32_t *assign_out, int *nmatches_out);
+/* Host-only building block of the sharded method (no device, no NCCL — for tests and for callers with their own
+ * transport): replays ONE shard's candidate lists (vsg_projection_map_candidates on that shard) from the claim state
+ * `blocked` (in / out, F->n bytes, initially `occupied`).  assign_out entries are overwritten with shard_begin + local index
+ * where this shard assigns and left alone elsewhere; *nmatches_out = this shard's assignment events. */
+vsg_status vsg_projection_map_resolve_shard(const vsg_frame_view *F, uint8_t *blocked, int shard_begin, int n_local,
+                                            const vsg_track_point *pts_local, const int32_t *cand_ptr, const int32_t *cand_idx,
+                                            const int32_t *cand_dist, float nnratio, int32_t *assign_out, int *nmatches_out);
+
 /* SearchByProjection(Frame& Cur, const Frame& Last, th, bMono) (ORBmatcher.cc:1667-1878).  mode: 0 = octaves
  * [o-1, o+1], 1 = forward (>= o), 2 = backward ([0, o]) (:1719-1724).  assign_out[i] = index of the last-frame
  * point written to Cur.mvpMapPoints[i], -1 untouched, -2 written and then cleared by the rotation check. */

@@ -256,3 +256,37 @@ def test_knn2_full_size_properties():
     m.knn2_merge_dev(parts_i, parts_d, mi, md)
     m.sync()
     assert torch.equal(mi, idx) and torch.equal(md, dist)
+
+
+def test_sharded_entry_points_on_a_single_rank_communicator(oracle):
+    """vsg_comm_* / vsg_knn2_sharded / vsg_search_by_projection_map_sharded with a one-rank NCCL communicator (the
+    pytest box has one GPU): the plumbing behind the C ABI — dlopen of NCCL, communicator, all-gather, merge, the replay
+    from the claim token — must reproduce the single-GPU calls.  The N > 1 runs are bench.py's `matching_sharded`
+    block (torchrun) and tools/multi_gpu_check.py."""
+    import torch
+    from tests import match_scenarios as sc
+    from visual_sgraphs_b200.comm import Comm
+    from visual_sgraphs_b200.matcher import ORBmatcher
+    assert Comm.nccl_version() >= 21000
+    comm = Comm(Comm.unique_id(), 1, 0, 0)
+    m = ORBmatcher(nnratio=0.8, device=0)
+    q, t = synth_query_train(9, 300, 20000)
+    qd, td = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
+    i0, d0 = (torch.zeros((300, 2), dtype=torch.int32, device="cuda") for _ in range(2))
+    i1, d1 = (torch.zeros((300, 2), dtype=torch.int32, device="cuda") for _ in range(2))
+    m.knn2_dev(qd, td, i0, d0)
+    m.knn2_sharded(comm, qd, td, 0, i1, d1)
+    m.sync()
+    assert torch.equal(i0, i1) and torch.equal(d0, d1)
+    ka, da, kb, db = sc.two_frames(oracle)
+    fd = sc.frame_data(ka, da, stereo_seed=5)
+    kb2, db2 = np.concatenate([kb] * 6), np.concatenate([db] * 6)
+    pts, desc, occ = sc.track_points(fd, kb2, db2, (9, 5), 21, True)
+    frame = m.frame(fd)
+    want = m.SearchByProjectionMap(frame, occ, pts, desc, 3.0)
+    got = m.SearchByProjectionMapSharded(comm, frame, occ, 0, pts, desc, 3.0)
+    assert got[0] == want[0] and np.array_equal(got[1], want[1]) and want[0] > 100
+    onm, oassign = oracle.search_by_projection_map(fd.view, occ, pts, desc, 3.0, False, 50.0, float(np.float32(0.8)))
+    assert got[0] == onm and np.array_equal(got[1], oassign)
+    comm.close()
+    m.close()

@@ -138,3 +138,48 @@ def test_map_sharded_search_by_projection_over_gloo(tmp_path, oracle):
     for r in range(world):
         got = np.load(str(tmp_path / ("proj%d.npz" % r)))
         assert int(got["nm"]) == wnm and np.array_equal(got["assign"], wassign)
+
+
+# ---- the token-ring form the C ABI implements with NCCL (vsg_search_by_projection_map_sharded) ----
+def test_shard_by_shard_replay_equals_the_one_call_resolve(oracle):
+    """vsg_projection_map_resolve_shard chained over 1, 2, 3 and 7 contiguous shards (claim state carried from shard to
+    shard, later shards overwriting slots) == vsg_projection_map_resolve on the whole map == the oracle's one-call method."""
+    from visual_sgraphs_b200.matcher import projection_map_resolve, projection_map_resolve_shard
+    fd, pts, desc, occ = _proj_scenario(oracle)
+    wnm, wassign = oracle.search_by_projection_map(fd.view, occ, pts, desc, 3.0, False, 50.0, float(np.float32(0.8)))
+    cp, ci, cd = _cpu_candidates(oracle, fd, pts, desc, 3.0)
+    nm1, a1 = projection_map_resolve(fd, occ, pts, cp, ci, cd, 0.8)
+    assert nm1 == wnm and np.array_equal(a1, wassign)
+    for world in (1, 2, 3, 7):
+        blocked = np.ascontiguousarray(occ, np.uint8).copy()
+        assign = np.full(fd.n, -1, np.int32)
+        total = 0
+        for b, e in sharded.shard_bounds(len(pts), world):
+            lp = (cp[b:e + 1] - cp[b]).astype(np.int32)
+            total += projection_map_resolve_shard(fd, blocked, assign, b, pts[b:e], lp, ci[cp[b]:cp[e]], cd[cp[b]:cp[e]], 0.8)
+        assert total == wnm and np.array_equal(assign, wassign), world
+
+
+def _ring_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as orc
+    from visual_sgraphs_b200.matcher import projection_map_resolve_shard
+    fd, pts, desc, occ = _proj_scenario(orc)
+    b, e = sharded.shard_bounds(len(pts), world)[rank]
+    cp, ci, cd = _cpu_candidates(orc, fd, pts[b:e], desc[b:e], 3.0)
+    nm, assign = sharded.search_by_projection_map_token_ring(
+        dist, fd.n, occ, b, lambda blocked, a: projection_map_resolve_shard(fd, blocked, a, b, pts[b:e], cp, ci, cd, 0.8))
+    np.savez(os.path.join(out_dir, "ring%d.npz" % rank), nm=nm, assign=assign)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_token_ring_search_by_projection_over_gloo(tmp_path, oracle, world):
+    mp.spawn(_ring_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    fd, pts, desc, occ = _proj_scenario(oracle)
+    wnm, wassign = oracle.search_by_projection_map(fd.view, occ, pts, desc, 3.0, False, 50.0, float(np.float32(0.8)))
+    for r in range(world):
+        got = np.load(str(tmp_path / ("ring%d.npz" % r)))
+        assert int(got["nm"]) == wnm and np.array_equal(got["assign"], wassign)

@@ -104,6 +104,19 @@ _SIGNATURES = {
                                                 C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "vsg_projection_map_resolve": (C.c_int, [C.POINTER(FrameView), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_void_p, C.c_float, C.c_void_p, C.POINTER(C.c_int)]),
+    "vsg_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "vsg_comm_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "vsg_comm_destroy": (None, [C.c_void_p]),
+    "vsg_comm_rank": (C.c_int, [C.c_void_p]),
+    "vsg_comm_size": (C.c_int, [C.c_void_p]),
+    "vsg_comm_nccl_version": (C.c_int, []),
+    "vsg_knn2_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                   C.c_void_p]),
+    "vsg_search_by_projection_map_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                                       C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_float, C.c_float,
+                                                       C.c_void_p, C.POINTER(C.c_int)]),
+    "vsg_projection_map_resolve_shard": (C.c_int, [C.POINTER(FrameView), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                                   C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.POINTER(C.c_int)]),
     "vsg_search_by_projection_last": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                                 C.c_float, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
     "vsg_search_for_initialization": (C.c_int, [C.c_void_p, C.POINTER(FrameView), C.c_void_p, C.c_void_p, C.c_int,

@@ -13,6 +13,7 @@
 #include <climits>
 
 #include "vsg_internal.cuh"
+#include "comm_internal.h"
 
 namespace vsg {
 
@@ -277,8 +278,8 @@ void vsg_matcher_destroy(vsg_matcher *m) {
     if (!m) return;
     cudaSetDevice(m->device);
     if (m->stream) { cudaStreamSynchronize(m->stream); cudaStreamDestroy(m->stream); }
-    for (int i = 0; i < 12; ++i) cudaFree(m->buf[i]);
-    for (int i = 0; i < 6; ++i) cudaFreeHost(m->hbuf[i]);
+    for (void *b : m->buf) cudaFree(b);
+    for (void *b : m->hbuf) cudaFreeHost(b);
     delete m;
 }
 
@@ -342,6 +343,32 @@ vsg_status vsg_knn2_merge_dev(vsg_matcher *m, const int32_t *idx_parts_dev, cons
     CK(cudaSetDevice(m->device));
     knn2_merge_parts_kernel<<<(nq + 255) / 256, 256, 0, m->stream>>>(idx_parts_dev, dist_parts_dev, nparts, nq, out_idx_dev,
                                                                     out_dist_dev);
+    count_launch();
+    CK(cudaGetLastError());
+    return VSG_OK;
+}
+
+// Brute-force kNN-2 with the TRAIN set sharded over the ranks of a communicator (BASELINE config 5): every rank
+// searches its shard (global train indices through train_index_offset), the per-rank (nq x 2) top-2 lists are exchanged by
+// ncclAllGather over NVLink and merged on every rank by (distance, index) — the knnMatch tie rule (Frame.cc:1200), so the
+// result equals the single-GPU call on the concatenated train set.  Asynchronous on the matcher's stream.
+vsg_status vsg_knn2_sharded(vsg_comm *comm, vsg_matcher *m, const uint8_t *query_dev, int nq, const uint8_t *train_shard_dev,
+                            int nt_shard, int train_index_offset, int32_t *out_idx_dev, int32_t *out_dist_dev) {
+    if (!comm || !m || nq < 0 || nt_shard < 0 || (nq > 0 && (!query_dev || !out_idx_dev || !out_dist_dev)) ||
+        (nt_shard > 0 && !train_shard_dev))
+        return VSG_ERR_INVALID;
+    if (nq == 0) return VSG_OK;
+    CK(cudaSetDevice(m->device));
+    const int nranks = comm_size(comm);
+    const size_t part = (size_t)nq * 2 * sizeof(int32_t);
+    vsg_status st;
+    if ((st = ensure(m, 13, 2 * part * (size_t)(nranks + 1)))) return st;
+    int32_t *my_idx = (int32_t *)m->buf[13], *my_dist = my_idx + (size_t)nq * 2;
+    int32_t *all_idx = my_dist + (size_t)nq * 2, *all_dist = all_idx + (size_t)nq * 2 * nranks;
+    if ((st = knn2_device(m, query_dev, nq, train_shard_dev, nt_shard, train_index_offset, my_idx, my_dist)) != VSG_OK) return st;
+    if ((st = comm_all_gather(comm, my_idx, all_idx, part, m->stream)) != VSG_OK) return st;
+    if ((st = comm_all_gather(comm, my_dist, all_dist, part, m->stream)) != VSG_OK) return st;
+    knn2_merge_parts_kernel<<<(nq + 255) / 256, 256, 0, m->stream>>>(all_idx, all_dist, nranks, nq, out_idx_dev, out_dist_dev);
     count_launch();
     CK(cudaGetLastError());
     return VSG_OK;

@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "match_internal.cuh"
+#include "comm_internal.h"
 
 namespace vsg {
 
@@ -539,12 +540,20 @@ vsg_status vsg_projection_map_resolve(const vsg_frame_view *F, const uint8_t *oc
     return VSG_OK;
 }
 
-// ORBmatcher.cc:42-144
-vsg_status vsg_search_by_projection_map(vsg_matcher *m, const vsg_frame *F, const uint8_t *occupied, int n_mp,
-                                        const vsg_track_point *pts, const uint8_t *mp_desc, float th, int far_points,
-                                        float th_far, float nnratio, int32_t *assign_out, int *nmatches_out) {
-    if (!m || !F || n_mp < 0 || !assign_out || (n_mp > 0 && (!pts || !mp_desc)) || (F->n > 0 && !occupied)) return VSG_ERR_INVALID;
-    CK(cudaSetDevice(m->device));
+// ---- SearchByProjection(Frame&, vector<MapPoint*>&) in two halves that the one-call and the sharded entry points share ----
+// GPU half: window queries of the map points that reach GetFeaturesInArea (:48-74), candidate lists with distances back
+// on the host (pinned staging of the matcher; valid until its next search).
+struct MapSearch {
+    int nq = 0;
+    const int *q_mp = nullptr;   // query -> map point index (local to the pts array given)
+    bool ordered = false;
+    AreaLists R;                 // nq < kOrderedReplayMinQueries: lists as the kernel left them
+    OrderedLists L;              // otherwise: entries in query order + the query of every entry
+};
+
+static vsg_status projection_map_search(vsg_matcher *m, const vsg_frame *F, int n_mp, const vsg_track_point *pts,
+                                        const uint8_t *mp_desc, float th, int far_points, float th_far, float nnratio,
+                                        MapSearch *out) {
     PhaseTimer pt("search_by_projection_map");
     // query list in the matcher's pinned staging (a 200k-point map is 7 MB of queries: no fresh pages per call, and the
     // upload runs at the PCIe rate instead of the pageable-memory rate)
@@ -573,52 +582,27 @@ vsg_status vsg_search_by_projection_map(vsg_matcher *m, const vsg_frame *F, cons
         }
     }
     pt.mark("queries");
-    std::vector<uint8_t> blocked(occupied, occupied + F->n);
-    for (int i = 0; i < F->n; ++i) assign_out[i] = -1;
-    const vsg_keypoint *keys = F->keys.data();
-    int nmatches = 0;
-    vsg_status st;
-    if (nq < kOrderedReplayMinQueries) {
-        // tracking-sized calls (a local map of a few thousand points): the lists come back as the kernel left them and
-        // the replay of :76-141 visits them query by query — two kernels and a copy less than the ordered form below
-        AreaLists R;
-        if ((st = area_search_raw(m, F, nq, qs, mp_desc, n_mp, &R)) != VSG_OK) return st;
-        pt.mark("area_search total");
-        for (int k = 0; k < nq; ++k) {
-            int best = 256, best_level = -1, best2 = 256, best_level2 = -1, best_idx = -1;
-            const int2 *c = R.raw + R.off[k], *ce = c + R.cnt[k];
-            for (; c < ce; ++c) {
-                const int idx = c->x, dist = c->y;
-                if (blocked[idx]) continue;
-                if (dist < best) { best2 = best; best = dist; best_level2 = best_level; best_level = keys[idx].octave; best_idx = idx; }
-                else if (dist < best2) { best_level2 = keys[idx].octave; best2 = dist; }
-            }
-            if (best <= TH_HIGH) {
-                if (best_level == best_level2 && best > nnratio * best2) continue;
-                if (best_level != best_level2 || best <= nnratio * best2) {
-                    assign_out[best_idx] = q_mp[k];
-                    blocked[best_idx] = pts[q_mp[k]].blocks;
-                    ++nmatches;
-                }
-            }
-        }
-        pt.mark("resolve");
-        if (nmatches_out) *nmatches_out = nmatches;
-        return VSG_OK;
-    }
-    OrderedLists L;
-    if ((st = area_search_ordered(m, F, nq, qs, mp_desc, n_mp, &L)) != VSG_OK) return st;
+    out->nq = nq;
+    out->q_mp = q_mp;
+    out->ordered = nq >= kOrderedReplayMinQueries;
+    // tracking-sized calls (a local map of a few thousand points): the lists come back as the kernel left them and the
+    // replay visits them query by query — two kernels and a copy less than the ordered form
+    const vsg_status st = out->ordered ? area_search_ordered(m, F, nq, qs, mp_desc, n_mp, &out->L)
+                                       : area_search_raw(m, F, nq, qs, mp_desc, n_mp, &out->R);
     pt.mark("area_search total");
-    // Sequential replay of :76-141 (query k = map point q_mp[k], in map order) as ONE walk over all entries in query
-    // order: an entry whose keypoint is already claimed is skipped by a one-byte test — with a map much larger than
-    // the frame that is nearly every entry — and only the first unclaimed entry of a query triggers the scan of that
-    // query's list.  (Claims only ever appear, so an entry found claimed stays irrelevant for its query.)
-    for (int e = 0; e < L.total;) {
-        if (blocked[L.ent[e].x]) { ++e; continue; }
-        const int k = L.qid[e];
+    return st;
+}
+
+// Host half: the sequential replay of :76-141 in map order.  `blocked` (keypoints holding a map point with observations,
+// :88-90) is updated in place so that the replay of the NEXT shard of the map can continue from it; assignments are
+// written as index_offset + local map point index.  Returns the number of nmatches++ events.
+static int projection_map_replay(const vsg_frame *F, uint8_t *blocked, const MapSearch &S, const vsg_track_point *pts,
+                                 float nnratio, int index_offset, int32_t *assign_out) {
+    const vsg_keypoint *keys = F->keys.data();
+    const int *q_mp = S.q_mp;
+    int nmatches = 0;
+    auto scan = [&](const int2 *c, const int2 *ce, int k) {
         int best = 256, best_level = -1, best2 = 256, best_level2 = -1, best_idx = -1;
-        const int2 *c = L.ent + e, *ce = L.ent + L.ptr[k + 1];
-        e = L.ptr[k + 1];
         for (; c < ce; ++c) {
             const int idx = c->x, dist = c->y;
             if (blocked[idx]) continue;
@@ -626,15 +610,133 @@ vsg_status vsg_search_by_projection_map(vsg_matcher *m, const vsg_frame *F, cons
             else if (dist < best2) { best_level2 = keys[idx].octave; best2 = dist; }
         }
         if (best <= TH_HIGH) {
-            if (best_level == best_level2 && best > nnratio * best2) continue;
+            if (best_level == best_level2 && best > nnratio * best2) return;
             if (best_level != best_level2 || best <= nnratio * best2) {
-                assign_out[best_idx] = q_mp[k];
+                assign_out[best_idx] = index_offset + q_mp[k];
                 blocked[best_idx] = pts[q_mp[k]].blocks;
                 ++nmatches;
             }
         }
+    };
+    if (!S.ordered) {
+        for (int k = 0; k < S.nq; ++k) scan(S.R.raw + S.R.off[k], S.R.raw + S.R.off[k] + S.R.cnt[k], k);
+        return nmatches;
     }
-    pt.mark("resolve");
+    // ONE walk over all entries in query order: an entry whose keypoint is already claimed is skipped by a one-byte test —
+    // with a map much larger than the frame that is nearly every entry — and only the first unclaimed entry of a query
+    // triggers the scan of that query's list.  (Claims only ever appear, so an entry found claimed stays irrelevant.)
+    const OrderedLists &L = S.L;
+    for (int e = 0; e < L.total;) {
+        if (blocked[L.ent[e].x]) { ++e; continue; }
+        const int k = L.qid[e];
+        const int2 *c = L.ent + e, *ce = L.ent + L.ptr[k + 1];
+        e = L.ptr[k + 1];
+        scan(c, ce, k);
+    }
+    return nmatches;
+}
+
+// ORBmatcher.cc:42-144
+vsg_status vsg_search_by_projection_map(vsg_matcher *m, const vsg_frame *F, const uint8_t *occupied, int n_mp,
+                                        const vsg_track_point *pts, const uint8_t *mp_desc, float th, int far_points,
+                                        float th_far, float nnratio, int32_t *assign_out, int *nmatches_out) {
+    if (!m || !F || n_mp < 0 || !assign_out || (n_mp > 0 && (!pts || !mp_desc)) || (F->n > 0 && !occupied)) return VSG_ERR_INVALID;
+    CK(cudaSetDevice(m->device));
+    MapSearch S;
+    const vsg_status st = projection_map_search(m, F, n_mp, pts, mp_desc, th, far_points, th_far, nnratio, &S);
+    if (st != VSG_OK) return st;
+    std::vector<uint8_t> blocked(occupied, occupied + F->n);
+    for (int i = 0; i < F->n; ++i) assign_out[i] = -1;
+    const int nmatches = projection_map_replay(F, blocked.data(), S, pts, nnratio, 0, assign_out);
+    if (nmatches_out) *nmatches_out = nmatches;
+    return VSG_OK;
+}
+
+// The same with the MAP POINTS sharded over the ranks of a communicator (BASELINE config 3): this rank holds the
+// contiguous shard [shard_begin, shard_begin + n_local) of the map; the frame and `occupied` are replicated.  Every rank runs
+// the window search of its shard on its own GPU at the same time.  The order-dependent part of the loop needs, per shard, only
+// the claim state the earlier shards left (F->n bytes): it travels down the ranks as a token (ncclSend / ncclRecv), each rank
+// replays its own lists when the token arrives, and one ncclAllGather of the per-rank assignments (F->n ints + a count per
+// rank) gives every rank the result of the one-call method: a later map point overwrites an earlier one's slot exactly as
+// `F.mvpMapPoints[bestIdx] = pMP` does (:130), nmatches counts every assignment event.
+vsg_status vsg_search_by_projection_map_sharded(vsg_comm *comm, vsg_matcher *m, const vsg_frame *F, const uint8_t *occupied,
+                                                int shard_begin, int n_local, const vsg_track_point *pts_local,
+                                                const uint8_t *desc_local, float th, int far_points, float th_far, float nnratio,
+                                                int32_t *assign_out, int *nmatches_out) {
+    if (!comm || !m || !F || n_local < 0 || shard_begin < 0 || !assign_out || (n_local > 0 && (!pts_local || !desc_local)) ||
+        (F->n > 0 && !occupied))
+        return VSG_ERR_INVALID;
+    CK(cudaSetDevice(m->device));
+    const int rank = comm_rank(comm), nranks = comm_size(comm), N = F->n;
+    MapSearch S;
+    vsg_status st = projection_map_search(m, F, n_local, pts_local, desc_local, th, far_points, th_far, nnratio, &S);
+    if (st != VSG_OK) return st;
+    // device: token (N bytes, padded), my record (N + 1 ints), everyone's records; pinned host mirrors
+    const size_t tok_bytes = ((size_t)N + 15) & ~(size_t)15, rec_ints = (size_t)N + 1;
+    if ((st = matcher_ensure(m, 12, tok_bytes + rec_ints * 4 * (1 + (size_t)nranks) + 64)) ||
+        (st = matcher_ensure_host(m, 6, tok_bytes + rec_ints * 4 * (1 + (size_t)nranks) + 64)))
+        return st;
+    uint8_t *tok_d = (uint8_t *)m->buf[12], *tok_h = (uint8_t *)m->hbuf[6];
+    int32_t *rec_d = (int32_t *)(tok_d + tok_bytes), *all_d = rec_d + rec_ints;
+    int32_t *rec_h = (int32_t *)(tok_h + tok_bytes), *all_h = rec_h + rec_ints;
+    cudaStream_t s = m->stream;
+    if (rank == 0) {
+        if (N) memcpy(tok_h, occupied, (size_t)N);
+    } else {
+        if ((st = comm_recv(comm, tok_d, tok_bytes, rank - 1, s)) != VSG_OK) return st;
+        CK(cudaMemcpyAsync(tok_h, tok_d, tok_bytes, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    for (int i = 0; i < N; ++i) rec_h[i] = -1;
+    rec_h[N] = projection_map_replay(F, tok_h, S, pts_local, nnratio, shard_begin, rec_h);
+    if (rank + 1 < nranks) {
+        CK(cudaMemcpyAsync(tok_d, tok_h, tok_bytes, cudaMemcpyHostToDevice, s));
+        if ((st = comm_send(comm, tok_d, tok_bytes, rank + 1, s)) != VSG_OK) return st;
+    }
+    CK(cudaMemcpyAsync(rec_d, rec_h, rec_ints * 4, cudaMemcpyHostToDevice, s));
+    if ((st = comm_all_gather(comm, rec_d, all_d, rec_ints * 4, s)) != VSG_OK) return st;
+    CK(cudaMemcpyAsync(all_h, all_d, rec_ints * 4 * nranks, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    int nmatches = 0;
+    for (int i = 0; i < N; ++i) assign_out[i] = -1;
+    for (int r = 0; r < nranks; ++r) {                      // shard order = map order: later shards overwrite
+        const int32_t *rec = all_h + (size_t)r * rec_ints;
+        for (int i = 0; i < N; ++i)
+            if (rec[i] >= 0) assign_out[i] = rec[i];
+        nmatches += rec[N];
+    }
+    if (nmatches_out) *nmatches_out = nmatches;
+    return VSG_OK;
+}
+
+// Host-only building block of the sharded method for tests without NCCL: replays ONE shard's candidate lists (as
+// vsg_projection_map_candidates returns them) from the claim state `blocked` (in / out, F->n bytes); assign_out entries are
+// overwritten with shard_begin + local index where this shard assigns, left alone elsewhere.
+vsg_status vsg_projection_map_resolve_shard(const vsg_frame_view *F, uint8_t *blocked, int shard_begin, int n_local,
+                                            const vsg_track_point *pts_local, const int32_t *cand_ptr, const int32_t *cand_idx,
+                                            const int32_t *cand_dist, float nnratio, int32_t *assign_out, int *nmatches_out) {
+    if (!F || n_local < 0 || !cand_ptr || (F->n > 0 && (!blocked || !assign_out || !F->keys)) || (n_local > 0 && !pts_local) ||
+        (cand_ptr[n_local] > 0 && (!cand_idx || !cand_dist)))
+        return VSG_ERR_INVALID;
+    int nmatches = 0;
+    for (int k = 0; k < n_local; ++k) {
+        int best = 256, best_level = -1, best2 = 256, best_level2 = -1, best_idx = -1;
+        for (int c = cand_ptr[k]; c < cand_ptr[k + 1]; ++c) {
+            const int idx = cand_idx[c], dist = cand_dist[c];
+            if (idx < 0 || idx >= F->n) { set_error("resolve: candidate index out of range"); return VSG_ERR_INVALID; }
+            if (blocked[idx]) continue;
+            if (dist < best) { best2 = best; best = dist; best_level2 = best_level; best_level = F->keys[idx].octave; best_idx = idx; }
+            else if (dist < best2) { best_level2 = F->keys[idx].octave; best2 = dist; }
+        }
+        if (best <= TH_HIGH) {
+            if (best_level == best_level2 && best > nnratio * best2) continue;
+            if (best_level != best_level2 || best <= nnratio * best2) {
+                assign_out[best_idx] = shard_begin + k;
+                blocked[best_idx] = pts_local[k].blocks;
+                ++nmatches;
+            }
+        }
+    }
     if (nmatches_out) *nmatches_out = nmatches;
     return VSG_OK;
 }

@@ -84,10 +84,10 @@ struct __align__(8) LevelKp {
 struct vsg_matcher {
     int device = 0;
     cudaStream_t stream = nullptr;
-    void *buf[12] = {};
-    size_t cap[12] = {};
-    void *hbuf[6] = {};      // pinned host staging (grows on demand): results come back without page faults
-    size_t hcap[6] = {};
+    void *buf[14] = {};
+    size_t cap[14] = {};
+    void *hbuf[8] = {};      // pinned host staging (grows on demand): results come back without page faults
+    size_t hcap[8] = {};
     std::vector<char> scratch[2];   // reusable host scratch of the search methods (query lists), kept across calls
     int sm_count = 148;
 };

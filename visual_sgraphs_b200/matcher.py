@@ -27,6 +27,21 @@ def projection_map_resolve(frame_data, occupied, track_points, cand_ptr, cand_id
     return nm.value, assign
 
 
+def projection_map_resolve_shard(frame_data, blocked, assign, shard_begin, track_points_local, cand_ptr, cand_idx, cand_dist,
+                                 nnratio):
+    """vsg_projection_map_resolve_shard: one shard's replay from the claim state `blocked` (updated in place, like
+    `assign`).  Host code.  Returns this shard's nmatches."""
+    L = _lib.load()
+    pts = np.ascontiguousarray(track_points_local, TRACK_POINT_DTYPE)
+    cand_ptr, cand_idx, cand_dist = (np.ascontiguousarray(a, np.int32) for a in (cand_ptr, cand_idx, cand_dist))
+    assert blocked.dtype == np.uint8 and assign.dtype == np.int32 and blocked.flags.c_contiguous and assign.flags.c_contiguous
+    nm = C.c_int(0)
+    check(L.vsg_projection_map_resolve_shard(C.byref(frame_data.view), ptr(blocked), int(shard_begin), len(pts), ptr(pts),
+                                             ptr(cand_ptr), ptr(cand_idx), ptr(cand_dist), float(np.float32(nnratio)),
+                                             ptr(assign), C.byref(nm)))
+    return nm.value
+
+
 class ORBmatcher:
     def __init__(self, nnratio=0.6, checkOri=True, device=0):
         self._L = _lib.load()
@@ -190,6 +205,25 @@ class ORBmatcher:
                 continue
             check(st)
             return cand_ptr, idx[: total.value].copy(), dist[: total.value].copy()
+
+    def knn2_sharded(self, comm, query_dev, train_shard_dev, train_index_offset, out_idx_dev, out_dist_dev):
+        """vsg_knn2_sharded: train rows sharded over the communicator's ranks (torch CUDA tensors; asynchronous)."""
+        check(self._L.vsg_knn2_sharded(comm._h, self._h, ptr(query_dev), query_dev.shape[0], ptr(train_shard_dev),
+                                       train_shard_dev.shape[0], int(train_index_offset), ptr(out_idx_dev), ptr(out_dist_dev)))
+
+    def SearchByProjectionMapSharded(self, comm, frame, occupied, shard_begin, track_points_local, desc_local, th=3.0,
+                                     bFarPoints=False, thFarPoints=50.0):
+        """vsg_search_by_projection_map_sharded: this rank's contiguous shard of the map points; returns the
+        (nmatches, assign[N]) of the one-call method on the whole map, assign holding global map point indices."""
+        pts = np.ascontiguousarray(track_points_local, TRACK_POINT_DTYPE)
+        desc = np.ascontiguousarray(desc_local, np.uint8).reshape(-1, 32)
+        occupied = np.ascontiguousarray(occupied, np.uint8)
+        assign = np.zeros(frame.data.n, np.int32)
+        nm = C.c_int(0)
+        check(self._L.vsg_search_by_projection_map_sharded(comm._h, self._h, frame._h, ptr(occupied), int(shard_begin), len(pts),
+                                                           ptr(pts), ptr(desc), float(th), int(bFarPoints), float(thFarPoints),
+                                                           float(self.mfNNratio), ptr(assign), C.byref(nm)))
+        return nm.value, assign
 
     def ProjectionMapResolve(self, frame_data, occupied, track_points, cand_ptr, cand_idx, cand_dist):
         """Host half: the order-dependent replay of ORBmatcher.cc:76-141 (vsg_projection_map_resolve)."""

@@ -111,3 +111,33 @@ def search_by_projection_map_sharded(dist, n_mp_total, pts_shard, local_candidat
     cand = np.concatenate(all_cand) if sum(totals) else np.zeros((0, 2), np.int32)
     pts_all = np.concatenate(all_pts).reshape(-1).view(pts_shard.dtype)
     return resolve(pts_all, gptr, np.ascontiguousarray(cand[:, 0]), np.ascontiguousarray(cand[:, 1]))
+
+
+def search_by_projection_map_token_ring(dist, n_kp, occupied, shard_begin, local_replay):
+    """The exchange of vsg_search_by_projection_map_sharded (csrc/match_methods.cu) restated over torch.distributed, so
+    that its logic runs on gloo in the CPU tests: the claim state (`blocked`, n_kp bytes, initially `occupied`) travels
+    down the ranks as a token; rank r replays its own shard when the token arrives —
+    local_replay(blocked, assign) -> nmatches updates both arrays in place (vsg_projection_map_resolve_shard) — and one
+    all-gather of the per-rank assignments (n_kp ints + a count) gives every rank the one-call result: shard order = map
+    order, so later shards overwrite earlier ones' slots, and nmatches adds up the assignment events."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    blocked = np.ascontiguousarray(occupied, np.uint8).copy()
+    if rank > 0:
+        tok = torch.zeros(n_kp, dtype=torch.uint8)
+        dist.recv(tok, src=rank - 1)
+        blocked = tok.numpy().copy()
+    assign = np.full(n_kp, -1, np.int32)
+    nm = local_replay(blocked, assign)
+    if rank + 1 < world:
+        dist.send(torch.from_numpy(blocked), dst=rank + 1)
+    rec = torch.from_numpy(np.concatenate([assign, np.array([nm], np.int32)]))
+    out = [torch.zeros_like(rec) for _ in range(world)]
+    dist.all_gather(out, rec)
+    final = np.full(n_kp, -1, np.int32)
+    total = 0
+    for r in range(world):
+        a = out[r].numpy()
+        final = np.where(a[:n_kp] >= 0, a[:n_kp], final).astype(np.int32)
+        total += int(a[n_kp])
+    return total, final
