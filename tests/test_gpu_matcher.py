@@ -290,3 +290,23 @@ def test_sharded_entry_points_on_a_single_rank_communicator(oracle):
     assert got[0] == onm and np.array_equal(got[1], oassign)
     comm.close()
     m.close()
+
+
+@pytest.mark.parametrize("nq,nt", [(1, 2), (5, 130), (256, 4096), (300, 5000), (1030, 20000), (777, 128 * 37 + 5), (2000, 3)])
+def test_knn2_tensor_core_path_matches_bruteforce(nq, nt, monkeypatch):
+    """The tcgen05.mma.kind::i8 formulation (csrc/knn_tc.cu: descriptors expanded to +-1 bytes, dot = 256 - 2 * Hamming,
+    top-2 epilogue out of tensor memory) forced on at small shapes (VSG_KNN_TC=2): distances AND indices must equal the
+    brute-force (distance, index) top-2 — ties to the lower train index, ragged last tiles, rows past nq / nt ignored."""
+    monkeypatch.setenv("VSG_KNN_TC", "2")
+    q, t = synth_query_train(nq * 13 + nt, nq, nt)
+    if nt >= 8:
+        t[3] = t[1]
+        t[nt - 1] = t[1]      # a tie in the last (partial) tile
+        q[0] = t[1]
+    idx, dist = _matcher().knn2(q, t, train_index_offset=1000)
+    widx, wdist = knn2_ref(q, t)
+    assert np.array_equal(dist, wdist)
+    assert np.array_equal(idx, widx + 1000)
+    monkeypatch.setenv("VSG_KNN_TC", "0")
+    idx0, dist0 = _matcher().knn2(q, t, train_index_offset=1000)
+    assert np.array_equal(idx0, idx) and np.array_equal(dist0, dist)

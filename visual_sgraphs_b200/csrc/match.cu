@@ -221,8 +221,18 @@ static void knn2_plan(const vsg_matcher *m, int nq, int nt, int *qtiles, int *nc
     *nchunks = std::max(1, (nt + rows - 1) / rows);
 }
 
+vsg_status launch_knn2_merge_parts(vsg_matcher *m, const int32_t *idx_parts, const int32_t *dist_parts, int nparts, int nq,
+                                   int32_t *out_idx, int32_t *out_dist) {
+    knn2_merge_parts_kernel<<<(nq + 255) / 256, 256, 0, m->stream>>>(idx_parts, dist_parts, nparts, nq, out_idx, out_dist);
+    count_launch();
+    CK(cudaGetLastError());
+    return VSG_OK;
+}
+
 static vsg_status knn2_device(vsg_matcher *m, const uint8_t *q_dev, int nq, const uint8_t *t_dev, int nt, int offset,
                               int *idx_dev, int *dist_dev) {
+    // large problems: the s8 GEMM formulation on the tensor cores (knn_tc.cu); small ones: the POPC kernel below
+    if (knn2_tc_supported(nq, nt)) return knn2_tc_device(m, q_dev, nq, t_dev, nt, offset, idx_dev, dist_dev);
     int qtiles, nchunks, chunk_rows;
     knn2_plan(m, nq, nt, &qtiles, &nchunks, &chunk_rows);
     vsg_status st = ensure(m, 0, (size_t)nchunks * nq * 2 * sizeof(unsigned));

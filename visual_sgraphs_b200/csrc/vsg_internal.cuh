@@ -84,8 +84,8 @@ struct __align__(8) LevelKp {
 struct vsg_matcher {
     int device = 0;
     cudaStream_t stream = nullptr;
-    void *buf[14] = {};
-    size_t cap[14] = {};
+    void *buf[16] = {};
+    size_t cap[16] = {};
     void *hbuf[8] = {};      // pinned host staging (grows on demand): results come back without page faults
     size_t hcap[8] = {};
     std::vector<char> scratch[2];   // reusable host scratch of the search methods (query lists), kept across calls
@@ -96,6 +96,13 @@ namespace vsg {
 
 vsg_status matcher_ensure(vsg_matcher *m, int slot, size_t bytes);
 vsg_status matcher_ensure_host(vsg_matcher *m, int slot, size_t bytes);
+// merge of `nparts` per-shard / per-segment top-2 lists ([nparts][nq][2]) by (distance, index) on the matcher's stream
+vsg_status launch_knn2_merge_parts(vsg_matcher *m, const int32_t *idx_parts, const int32_t *dist_parts, int nparts, int nq,
+                                   int32_t *out_idx, int32_t *out_dist);
+// tensor-core kNN-2 (knn_tc.cu): tcgen05.mma.kind::i8 on +-1 expanded descriptors; results identical to the POPC kernel
+bool knn2_tc_supported(int nq, int nt);
+vsg_status knn2_tc_device(vsg_matcher *m, const uint8_t *q_dev, int nq, const uint8_t *t_dev, int nt, int offset, int *idx_dev,
+                          int *dist_dev);
 // distances of every CSR candidate: all_dist[c] = |query[q] xor train[cand[c]]| for c in [cand_ptr[q], cand_ptr[q+1])
 void launch_window_dists(vsg_matcher *m, const uint8_t *query_dev, int nq, const uint8_t *train_dev,
                          const int *cand_ptr_dev, const int *cand_dev, int *all_dist_dev);
