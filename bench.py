@@ -259,6 +259,25 @@ def other_config_extras(torch, lib, device):
     ms = e0.elapsed_time(e1) / 5
     out["c4_1280x720_2000f"] = {"frames_per_s": B4 / (ms * 1e-3), "ms_per_128_frames": ms,
                                 "keypoints_per_frame": float(n.float().mean().item())}
+    # beside it: the reference's CPU extractor on the same shape (all host threads), and the pipeline's algorithmic bytes
+    # (B_frame = 5P - p0 - p7 + 60N) against the measured HBM peak
+    cores = host_threads()
+    try:
+        from oracle import ref
+        kind = "reference"
+        secs, _ = ref.bench_extract(fr[: 4 * cores], 2000, SCALE, NLEVELS, INI_TH, MIN_TH, cores)
+    except Exception:  # noqa: BLE001
+        from oracle import oracle as orc
+        kind = "port"
+        secs, _ = orc.bench_extract(fr[: 4 * cores], 2000, SCALE, NLEVELS, INI_TH, MIN_TH, cores)
+    px = [a * b for a, b in level_sizes(1280, 720)]
+    b_frame = 5 * sum(px) - px[0] - px[-1] + 60 * float(n.float().mean().item())
+    peak, peak_src = measured_peaks()
+    out["c4_1280x720_2000f"]["cpu_baseline"] = {"value": 4 * cores / secs, "unit": "frames/s", "cores": cores, "kind": kind,
+                                                "sample": "%d frames, %d threads" % (4 * cores, cores)}
+    out["c4_1280x720_2000f"]["roofline"] = {"bound": "hbm", "achieved": b_frame * B4 / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                            "frac": b_frame * B4 / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_frame": b_frame,
+                                            "scope": "whole pipeline (all kernels of the batch)", "peak_source": peak_src}
     ex.close()
     del d_frames, kps, desc
     # ---- C2 ----
@@ -293,6 +312,28 @@ def other_config_extras(torch, lib, device):
     out["c2_stereo_752x480_1200f"] = {"pairs_per_s": npairs / dt, "ms_per_pair": 1e3 * dt / npairs, "pairs_per_call": npairs,
                                       "stereo_matches_per_pair": matched / npairs,
                                       "api": "vsg_extract_batch (pinned frames in) + vsg_stereo_match_batch (u_right / depth out)"}
+    # beside it: the reference's path on the CPU for a sample of the same pairs — left / right extraction on two threads
+    # (Frame.cc:129-132, oracle/_ref when present) + ComputeStereoMatches (oracle port), pairs dealt over the host threads
+    try:
+        import concurrent.futures as cf
+        from oracle import oracle as orc
+        def one_pair(pr):
+            exl, exr = orc.OracleExtractor(1200), orc.OracleExtractor(1200)
+            with cf.ThreadPoolExecutor(2) as tp:
+                (ml, kl, dl), (mr, kr, dr) = tp.map(lambda a: a[0](a[1]), ((exl, pr[0]), (exr, pr[1])))
+            return orc.stereo_matches(exl, exr, kl, dl, kr, dr, 0.11, 47.9)
+        cores = host_threads()
+        sample = [base_pairs[i % 8] for i in range(max(8, cores))]
+        one_pair(sample[0])
+        t0 = time.perf_counter()
+        with cf.ThreadPoolExecutor(max(1, cores // 2)) as tp:
+            list(tp.map(one_pair, sample))
+        dt_cpu = time.perf_counter() - t0
+        out["c2_stereo_752x480_1200f"]["cpu_baseline"] = {"value": len(sample) / dt_cpu, "unit": "pairs/s", "cores": cores, "kind": "port",
+                                                          "sample": "%d pairs, %d workers x 2 extraction threads (ctypes calls release the GIL)" %
+                                                                    (len(sample), max(1, cores // 2))}
+    except Exception as e:  # noqa: BLE001
+        out["c2_stereo_752x480_1200f"]["cpu_baseline"] = {"error": str(e)}
     # the same with the rectification System::TrackStereo runs first (System.cc:284-292; EuRoC.yaml needs it): unrectified
     # frames in, cv::remap on the device with one map per camera, then extraction + stereo matching
     ys, xs = np.meshgrid(np.arange(480, dtype=np.float64), np.arange(752, dtype=np.float64), indexing="ij")
@@ -340,40 +381,88 @@ def other_config_extras(torch, lib, device):
         nm, _ = m.SearchByProjectionMap(frame, occ, pts, mp_desc, 3.0)
     dt = (time.perf_counter() - t0) / 5
     out["c3_projection_1000kp_x_200k_map"] = {"ms_per_call": dt * 1e3, "map_points_per_s": n_map / dt, "nmatches": nm}
+    try:   # beside it: the oracle port of ORBmatcher.cc:42-144 on the same scenario, one host thread (as Tracking calls it)
+        from oracle import oracle as orc
+        t0 = time.perf_counter()
+        wnm, wassign = orc.search_by_projection_map(fdata.view, occ, pts, mp_desc, 3.0, False, 50.0, float(m.mfNNratio))
+        dt_cpu = time.perf_counter() - t0
+        _, assign_g = m.SearchByProjectionMap(frame, occ, pts, mp_desc, 3.0)
+        out["c3_projection_1000kp_x_200k_map"]["cpu_baseline"] = {"value": dt_cpu * 1e3, "unit": "ms per call", "cores": 1, "kind": "port",
+                                                                  "identical_results": bool(wnm == nm and np.array_equal(wassign, assign_g))}
+    except Exception as e:  # noqa: BLE001
+        out["c3_projection_1000kp_x_200k_map"]["cpu_baseline"] = {"error": str(e)}
     m.close()
     return out
 
 
+def measured_popc_peak():
+    """POPC results per second of this GPU, measured now by tools/micro/popc_peak (built by __graft_entry__.build());
+    falls back to 16 / clk / SM at the measured SM clock (CUDA programming guide) if the binary is missing."""
+    exe = os.path.join(ROOT, "tools", "micro", "popc_peak")
+    try:
+        import subprocess
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=60).stdout.strip().splitlines()[-1]
+        d = json.loads(out)
+        return float(d["popc_per_s"]), "measured in this run (tools/micro/popc_peak: %.2f POPC / clk / SM)" % d["popc_per_clk_per_sm"]
+    except Exception:  # noqa: BLE001
+        return 16.0 * 148 * 1965e6, "fallback: 16 POPC / clk / SM x 148 SMs x 1965 MHz"
+
+
+def measured_int8_peak():
+    """Dense int8 tensor peak in OP/s: twice the measured dense bf16 rate of MEASURED_PEAKS.json (the tensor cores run 8-bit
+    operands at twice the 16-bit rate; the file has no int8 entry), else the nominal 4.5e15."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        if "bf16_tflops" in d:
+            return 2.0 * float(d["bf16_tflops"]) * 1e12, "2 x measured dense bf16 (MEASURED_PEAKS.json: %.0f TFLOP/s)" % d["bf16_tflops"]
+    return 4.5e15, "nominal dense int8 (B200_PROFILING.md)"
+
+
 def matching_extras(torch, device):
-    """Hamming matching throughput (BASELINE metric part 2): brute-force kNN-2, configs C5 (100k x 1M) and C3
-    (1000 x 200k), device-resident descriptors, CUDA events on the matcher stream."""
+    """Hamming matching throughput (BASELINE metric part 2): brute-force kNN-2, configs C5 (100k x 1M) and C3's shape
+    (1000 x 200k), device-resident descriptors, CUDA events on the matcher stream.  Two kernels, identical results: the
+    tensor-core formulation (csrc/knn_tc.cu: tcgen05.mma.kind::i8 on +-1 expanded descriptors; the default for large
+    problems) against the int8 tensor roofline, and the POPC kernel (VSG_KNN_TC=0) against the measured POPC peak."""
     from visual_sgraphs_b200.matcher import ORBmatcher
     m = ORBmatcher(device=device)
     s = torch.cuda.ExternalStream(m.stream(), device=device)
     out = {}
     g = torch.Generator(device="cuda").manual_seed(7)
-    for name, nq, nt, reps in (("knn2_100k_x_1M", 100_000, 1_000_000, 2), ("knn2_1000_x_200k", 1000, 200_000, 20)):
+    popc_peak, popc_src = measured_popc_peak()
+    int8_peak, int8_src = measured_int8_peak()
+    for name, nq, nt, reps in (("knn2_100k_x_1M", 100_000, 1_000_000, 3), ("knn2_1000_x_200k", 1000, 200_000, 20)):
         q = torch.randint(0, 256, (nq, 32), dtype=torch.uint8, device="cuda", generator=g)
         t = torch.randint(0, 256, (nt, 32), dtype=torch.uint8, device="cuda", generator=g)
-        idx = torch.zeros((nq, 2), dtype=torch.int32, device="cuda")
-        dist = torch.zeros((nq, 2), dtype=torch.int32, device="cuda")
-        torch.cuda.synchronize()
-        m.knn2_dev(q, t, idx, dist)
-        m.sync()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(s)
-        for _ in range(reps):
-            m.knn2_dev(q, t, idx, dist)
-        e1.record(s)
-        m.sync()
-        ms = e0.elapsed_time(e1) / reps
         pairs = nq * nt
-        sms = torch.cuda.get_device_properties(device).multi_processor_count
-        peak = 16.0 * sms * 1965e6          # POPC: 16 results / clk / SM on the XU pipe (measured: ncu pipe_xu 97 % active)
+        res = {}
+        for mode, label in (("2", "tensor"), ("0", "popc")):
+            os.environ["VSG_KNN_TC"] = mode
+            idx = torch.zeros((nq, 2), dtype=torch.int32, device="cuda")
+            dist = torch.zeros((nq, 2), dtype=torch.int32, device="cuda")
+            torch.cuda.synchronize()
+            m.knn2_dev(q, t, idx, dist)
+            m.sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(s)
+            for _ in range(reps):
+                m.knn2_dev(q, t, idx, dist)
+            e1.record(s)
+            m.sync()
+            res[label] = (e0.elapsed_time(e1) / reps, idx, dist)
+        os.environ.pop("VSG_KNN_TC", None)
+        assert torch.equal(res["tensor"][1], res["popc"][1]) and torch.equal(res["tensor"][2], res["popc"][2])
+        ms, ms_p = res["tensor"][0], res["popc"][0]
+        ops = 2.0 * 256 * pairs / (ms * 1e-3)                 # s8 multiply-adds counted as 2 ops, K = 256
         out[name] = {"ms": ms, "pairs_per_s": pairs / (ms * 1e-3), "matches_per_s": nq / (ms * 1e-3),
-                     "popc_per_s": 8 * pairs / (ms * 1e-3),
-                     "roofline": {"bound": "popc (xu pipe)", "achieved": 8 * pairs / (ms * 1e-3), "peak": peak,
-                                  "unit": "POPC/s", "frac": 8 * pairs / (ms * 1e-3) / peak}}
+                     "kernel": "knn2_tc_kernel (tcgen05.mma.kind::i8, TMA, TMEM epilogue)",
+                     "roofline": {"bound": "tensor", "achieved": ops / 1e12, "peak": int8_peak / 1e12, "unit": "TOP/s (int8)",
+                                  "frac": ops / int8_peak, "peak_source": int8_src, "frac_of_nominal_4500": ops / 4.5e15},
+                     "popc_kernel": {"ms": ms_p, "pairs_per_s": pairs / (ms_p * 1e-3), "identical_results": True,
+                                     "roofline": {"bound": "popc (xu pipe)", "achieved": 8 * pairs / (ms_p * 1e-3), "peak": popc_peak,
+                                                  "unit": "POPC/s", "frac": 8 * pairs / (ms_p * 1e-3) / popc_peak,
+                                                  "peak_source": popc_src}},
+                     "speedup_over_popc_kernel": ms_p / ms}
     # CPU baseline beside it (SURVEY 8d): the reference's brute-force loop with its bit-hack DescriptorDistance
     # (ORBmatcher.cc:2047-2063) and a __builtin_popcountll variant, built with the reference's flags (-O3, no -march),
     # all host threads, bounded sample; the GPU result on the same sample must be identical
@@ -516,6 +605,100 @@ def emit(line):
     out = _JSON_OUT or sys.stdout
     out.write(json.dumps(line) + "\n")
     out.flush()
+
+
+def matching_methods_extras(device):
+    """Every ORBmatcher method at tracking size (two related 640x480 frames, ~1000 features each): microseconds per call
+    through the C ABI (host arrays in and out, the searched frame uploaded inside the timed call, as the drop-in shim does)
+    beside the CPU oracle port of the same reference loop on the same scenario (one host thread, as the reference runs it).
+    Results are asserted identical.  Scenario builders: tests/match_scenarios.py."""
+    from oracle import oracle as orc
+    from tests import match_scenarios as sc
+    from visual_sgraphs_b200.matcher import ORBmatcher
+    ka, da, kb, db = sc.two_frames(orc)
+    rng = np.random.default_rng(5)
+    out = {"features": [int(len(ka)), int(len(kb))], "unit": "us per call (median of 30)", "cpu_kind": "port, 1 thread"}
+
+    def timed(fn, reps=30):
+        fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            r = fn()
+            ts.append(time.perf_counter() - t0)
+        return float(np.median(ts) * 1e6), r
+
+    def same(a, b):
+        return all(np.array_equal(np.asarray(x), np.asarray(y)) for x, y in zip(a, b))
+
+    def row(name, gpu_fn, cpu_fn):
+        g_us, g = timed(gpu_fn)
+        c_us, c = timed(cpu_fn)
+        assert same(g, c), name
+        out[name] = {"gpu_us": round(g_us, 1), "cpu_us": round(c_us, 1), "gpu_over_cpu": round(g_us / c_us, 2), "nmatches": int(g[0])}
+
+    f32 = lambda v: float(np.float32(v))  # noqa: E731
+    _, sigma2, inv_sigma2 = sc.sigma_tables()
+    # SearchByProjection(F, vpMapPoints) — a local map of 5 x the frame's features
+    fd = sc.frame_data(ka, da, stereo_seed=5)
+    pts, desc, occ = sc.track_points(fd, np.concatenate([kb] * 5), np.concatenate([db] * 5), (9, 5), 21, True)
+    m = ORBmatcher(0.8, True, device=device)
+    row("SearchByProjection(F, vpMapPoints) [%d points]" % len(pts),
+        lambda: m.SearchByProjectionMap(m.frame(fd), occ, pts, desc, 3.0, False, 40.0),
+        lambda: orc.search_by_projection_map(fd.view, occ, pts, desc, 3.0, False, 40.0, f32(0.8)))
+    m.close()
+    # SearchByProjection(Cur, Last)
+    m = ORBmatcher(0.9, True, device=device)
+    ppts, pdesc, pocc = sc.proj_points(fd, kb, db, (9, 5), 4)
+    row("SearchByProjection(Cur, Last)", lambda: m.SearchByProjectionLast(m.frame(fd), pocc, ppts, pdesc, 15.0, 0),
+        lambda: orc.search_by_projection_last(fd.view, pocc, ppts, pdesc, 15.0, 0, True))
+    # SearchByProjection(Cur, KF, sAlreadyFound)
+    spts = sc.search_points(kb, (9, 5), 3)
+    socc = (rng.random(fd.n) < 0.1).astype(np.uint8)
+    row("SearchByProjection(Cur, KF, sAlreadyFound)", lambda: m.SearchByProjectionReloc(m.frame(fd), socc, spts, db, 10.0, 100),
+        lambda: orc.search_by_projection_reloc(fd.view, socc, spts, db, 10.0, 100, True))
+    # SearchForInitialization (mpIniORBextractor-sized frames)
+    ia, ida, ib, idb = sc.two_frames(orc, nfeat=2000)
+    f1, f2 = sc.frame_data(ia, ida), sc.frame_data(ib, idb)
+    prev0 = np.stack([ia["x"], ia["y"]], 1).astype(np.float32)
+    row("SearchForInitialization [%d features]" % len(ia), lambda: m.SearchForInitialization(f1, m.frame(f2), prev0.copy(), 100),
+        lambda: orc.search_for_initialization(f1.view, f2.view, prev0.copy(), 100, f32(0.9), True))
+    m.close()
+    # SearchByBoW(KF, F) / (KF, KF)
+    m = ORBmatcher(0.7, True, device=device)
+    kf, f = sc.frame_data(kb, db), sc.frame_data(ka, da)
+    valid = (rng.random(kf.n) < 0.85).astype(np.uint8)
+    valid2 = (rng.random(f.n) < 0.85).astype(np.uint8)
+    kfv, ffv = sc.feature_vector(db, 24), sc.feature_vector(da, 24)
+    row("SearchByBoW(KF, F)", lambda: m.SearchByBoW(kf, valid, f, kfv, ffv), lambda: orc.search_by_bow(kf.view, valid, f.view, kfv, ffv, f32(0.7), True))
+    row("SearchByBoW(KF, KF)", lambda: m.SearchByBoWKF(kf, valid, f, valid2, kfv, ffv),
+        lambda: orc.search_by_bow_kf(kf.view, valid, f.view, valid2, kfv, ffv, f32(0.7), True))
+    m.close()
+    # Sim3 projections, Fuse x 2, SearchBySim3, SearchForTriangulation
+    m = ORBmatcher(0.6, True, device=device)
+    fd0 = sc.frame_data(ka, da)
+    matched = (rng.random(fd0.n) < 0.2).astype(np.uint8)
+    spts5 = sc.search_points(kb, (9, 5), 5)
+    row("SearchByProjection(KF, Scw, vpPoints)", lambda: m.SearchByProjectionSim3(m.frame(fd0), matched, spts5, db, 8, 1.0),
+        lambda: orc.search_by_projection_sim3(fd0.view, matched, spts5, db, 8, f32(1.0)))
+    fpts = sc.search_points(kb, (9, 5), 7, sigma=1.5)
+    row("Fuse(KF, vpMapPoints) search", lambda: m.FuseSearch(m.frame(fd), fpts, db, 3.0, inv_sigma2, sim3_variant=False),
+        lambda: orc.fuse_search(fd.view, fpts, db, 3.0, inv_sigma2, 0))
+    row("Fuse(KF, Scw, vpPoints) search", lambda: m.FuseSearch(m.frame(fd0), fpts, db, 3.0, inv_sigma2, sim3_variant=True),
+        lambda: orc.fuse_search(fd0.view, fpts, db, 3.0, inv_sigma2, 1))
+    g1, g2 = sc.frame_data(ka, da), sc.frame_data(kb, db)
+    p1, p2 = sc.search_points(ka, (-9, -5), 9), sc.search_points(kb, (9, 5), 10)
+    row("SearchBySim3", lambda: m.SearchBySim3(m.frame(g1), m.frame(g2), p1, da, p2, db, 7.5),
+        lambda: orc.search_by_sim3(g1.view, g2.view, p1, da, p2, db, 7.5))
+    ta, tda, tb, tdb = sc.two_frames(orc, shift=(9, 1))
+    k1, k2 = sc.frame_data(ta, tda, stereo_seed=2), sc.frame_data(tb, tdb, stereo_seed=3)
+    h1, h2 = (rng.random(k1.n) < 0.3).astype(np.uint8), (rng.random(k2.n) < 0.3).astype(np.uint8)
+    fv1, fv2 = sc.feature_vector(tda, 24), sc.feature_vector(tdb, 24)
+    f12, ep = sc.translation_f12((9, 1)), np.array([300.0, 200.0], np.float32)
+    row("SearchForTriangulation", lambda: m.SearchForTriangulation(k1, h1, k2, h2, fv1, fv2, f12, ep, sigma2, False, False),
+        lambda: orc.search_for_triangulation(k1.view, h1, k2.view, h2, fv1, fv2, False, False, f12, ep, sigma2, True))
+    m.close()
+    return out
 
 
 def main():
@@ -704,6 +887,7 @@ def main():
                                     "single_thread_value": v_one}
             line["single_frame_latency"] = latency_extras(torch, lib, local_rank)
             line["matching"] = matching_extras(torch, local_rank)
+            line["matching_methods"] = matching_methods_extras(local_rank)
             line["other_configs"] = other_config_extras(torch, lib, local_rank)
         emit(line)
     if world > 1:

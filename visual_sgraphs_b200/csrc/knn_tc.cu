@@ -308,7 +308,7 @@ bool knn2_tc_supported(int nq, int nt) {
 }
 
 // kNN-2 of nq x nt descriptors on the tensor cores; out as vsg_knn2_dev.  Device buffers of the matcher: 14 expanded queries,
-// 15 expanded train rows, 13 per-segment partial lists.
+// 15 expanded train rows, 16 per-segment partial lists (slot 13 belongs to vsg_knn2_sharded, which calls this).
 vsg_status knn2_tc_device(vsg_matcher *m, const uint8_t *q_dev, int nq, const uint8_t *t_dev, int nt, int offset, int *idx_dev,
                           int *dist_dev) {
     const int ntiles = (nt + kTcTileN - 1) / kTcTileN, n_mb = (nq + kTcRowsPerItem - 1) / kTcRowsPerItem;
@@ -320,10 +320,10 @@ vsg_status knn2_tc_device(vsg_matcher *m, const uint8_t *q_dev, int nq, const ui
     const int nitems = n_mb * nseg;
     vsg_status st;
     if ((st = matcher_ensure(m, 14, (size_t)nq * 256)) || (st = matcher_ensure(m, 15, (size_t)nt * 256)) ||
-        (st = matcher_ensure(m, 13, (size_t)nseg * nq * 2 * sizeof(int32_t) * 2)))
+        (st = matcher_ensure(m, 16, (size_t)nseg * nq * 2 * sizeof(int32_t) * 2)))
         return st;
     int8_t *q8 = (int8_t *)m->buf[14], *t8 = (int8_t *)m->buf[15];
-    int32_t *part_idx = (int32_t *)m->buf[13], *part_dist = part_idx + (size_t)nseg * nq * 2;
+    int32_t *part_idx = (int32_t *)m->buf[16], *part_dist = part_idx + (size_t)nseg * nq * 2;
     cudaStream_t s = m->stream;
     expand_pm1_kernel<<<(unsigned)(((int64_t)nq * 8 + 255) / 256), 256, 0, s>>>((const uint32_t *)q_dev, nq, q8);
     expand_pm1_kernel<<<(unsigned)(((int64_t)nt * 8 + 255) / 256), 256, 0, s>>>((const uint32_t *)t_dev, nt, t8);

@@ -84,8 +84,8 @@ struct __align__(8) LevelKp {
 struct vsg_matcher {
     int device = 0;
     cudaStream_t stream = nullptr;
-    void *buf[16] = {};
-    size_t cap[16] = {};
+    void *buf[20] = {};      // device scratch slots; each entry point documents the slots it owns
+    size_t cap[20] = {};
     void *hbuf[8] = {};      // pinned host staging (grows on demand): results come back without page faults
     size_t hcap[8] = {};
     std::vector<char> scratch[2];   // reusable host scratch of the search methods (query lists), kept across calls
