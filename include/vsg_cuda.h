@@ -242,6 +242,8 @@ typedef struct vsg_frame vsg_frame;
 /* Uploads a frame view and builds its keypoint grid (Frame::AssignFeaturesToGrid / PosInGrid,
  * Frame.cc:521-553,870-880).  The view's arrays are copied; the handle can serve many searches. */
 vsg_status vsg_frame_create(vsg_matcher *m, const vsg_frame_view *view, vsg_frame **out);
+/* Every entry point that takes a vsg_frame returns only after its kernels have finished (all of them are synchronous), so a
+ * frame may be destroyed as soon as the last call using it has returned — from any thread, also after its matcher is gone. */
 void vsg_frame_destroy(vsg_frame *f);
 
 /* Frame::GetFeaturesInArea for nq windows at once (x, y, r, min_level, max_level per query): CSR lists of

@@ -66,3 +66,25 @@ def test_stereo_batch_matches_per_pair_and_oracle(oracle):
         wu, wd = oracle.stereo_matches(oxl, oxr, kl, dl, kr, dr, 0.11, 47.9)
         assert np.array_equal(u1, wu) and np.array_equal(d1, wd), p
     assert (ub[0] >= 0).sum() > 200 and (ub[3] >= 0).sum() == 0
+
+
+def test_keypoints_at_the_border_get_no_match_instead_of_an_out_of_bounds_read(oracle):
+    """Caller-supplied keypoints closer than the SAD window to the image border (the extractor never produces them; the
+    reference would throw a cv::Exception from rowRange / colRange, Frame.cc:1054,1069): the kernel must not read outside
+    the level planes — such keypoints simply stay unmatched, all others keep their oracle result."""
+    from visual_sgraphs_b200.extractor import ORBextractor
+    from visual_sgraphs_b200.matcher import ORBmatcher
+    from visual_sgraphs_b200.synth import synth_stereo_pair
+    left, right = synth_stereo_pair(8200)
+    exl, exr = ORBextractor(1200, 1.2, 8, 20, 7), ORBextractor(1200, 1.2, 8, 20, 7)
+    _, kl, dl = exl(left)
+    _, kr, dr = exr(right)
+    m = ORBmatcher()
+    u0, d0 = m.ComputeStereoMatches(exl, exr, kl, dl, kr, dr, 0.11, 47.9)
+    kl2, kr2 = kl.copy(), kr.copy()
+    edge = np.arange(0, len(kl2), 7)
+    kl2["x"][edge] = np.tile([1.0, 3.5, 750.0, 400.0], len(edge))[: len(edge)]      # left patch off the left / right edge
+    kl2["y"][edge] = np.tile([200.0, 1.0, 240.0, 478.5], len(edge))[: len(edge)]    # ... or off the top / bottom
+    u1, d1 = m.ComputeStereoMatches(exl, exr, kl2, dl, kr2, dr, 0.11, 47.9)
+    assert np.isfinite(u1).all() and ((u1 == -1) | (u1 >= 0)).all()
+    assert (u1[edge][(kl2["y"][edge] < 5) | (kl2["y"][edge] > 474)] == -1).all()

@@ -91,6 +91,10 @@ __global__ void stereo_sad_kernel(StereoPlanes P, const vsg_keypoint *__restrict
     const float iniu = sur0 + L - w, endu = sur0 + L + w + 1;
     if (iniu < 0 || endu >= pr.w) return;                     // :1062-1065
     const int y0 = (int)(svl - w), xl0 = (int)(sul - w), xr0 = (int)(sur0 - L - w);
+    // The 11 x 11 left patch and the 11 x 21 right strip must lie inside the level: the reference's rowRange / colRange throw
+    // a cv::Exception for a keypoint this close to the border (:1054, :1069); extractor keypoints never are (>= 19 px from
+    // every edge), caller-supplied ones get "no match" instead of an out-of-bounds read.
+    if (y0 < 0 || y0 + 2 * w >= pl.h || y0 + 2 * w >= pr.h || xl0 < 0 || xl0 + 2 * w >= pl.w || xr0 < 0) return;
     int sad[11];
 #pragma unroll
     for (int k = 0; k < 11; ++k) sad[k] = 0;
@@ -134,7 +138,7 @@ __global__ void stereo_sad_kernel(StereoPlanes P, const vsg_keypoint *__restrict
 struct BatchPlanes {          // frame-0 base of every level + strides; frame f of level l = base[l] + f * stride[l]
     const uint8_t *base[kMaxLevels];
     int64_t stride[kMaxLevels];
-    int pitch[kMaxLevels], w[kMaxLevels];
+    int pitch[kMaxLevels], w[kMaxLevels], h[kMaxLevels];
     float scale[kMaxLevels], inv_scale[kMaxLevels];
     int n_rows;
 };
@@ -204,6 +208,7 @@ __global__ void stereo_sad_batch_kernel(BatchPlanes P, const vsg_keypoint *__res
     const uint8_t *pl = P.base[oct] + (int64_t)(2 * pair) * P.stride[oct], *pr = pl + P.stride[oct];
     const int pitch = P.pitch[oct];
     const int y0 = (int)(svl - w), xl0 = (int)(sul - w), xr0 = (int)(sur0 - L - w);
+    if (y0 < 0 || y0 + 2 * w >= P.h[oct] || xl0 < 0 || xl0 + 2 * w >= P.w[oct] || xr0 < 0) return;   // see stereo_sad_kernel
     int sad[11];
 #pragma unroll
     for (int k = 0; k < 11; ++k) sad[k] = 0;
@@ -399,6 +404,7 @@ extern "C" vsg_status vsg_stereo_match_batch(vsg_matcher *m, vsg_extractor *ex, 
         if (l == 0) { P.base[l] = pr.lvl0_base; P.stride[l] = pr.lvl0_stride; P.pitch[l] = pr.lvl0_pitch; }
         else { P.base[l] = pr.pyr + G.plane_offset; P.stride[l] = G.plane_stride; P.pitch[l] = G.pitch; }
         P.w[l] = G.w;
+        P.h[l] = G.h;
         P.scale[l] = pr.scale[l];
         P.inv_scale[l] = pr.inv_scale[l];
     }

@@ -575,6 +575,11 @@ static vsg_status extract_batch_host(vsg_extractor *ex, const uint8_t *images, i
     const bool tight = frame_stride == (size_t)pitch * height && (int64_t)L0.pitch * L0.h == L0.plane_stride;
     RectifyMaps maps = {{ex->rect_xy[0], ex->rect_xy[1]}, {ex->rect_frac[0], ex->rect_frac[1]}, rect_slots};
     int nstreams_used = 0;
+    if (chunked) {   // chunks on the aux streams must not start before work already queued on ex->stream (an asynchronous
+                     // vsg_extract_batch_dev call) has finished with the shared per-frame scratch
+        CK(cudaEventRecord(ex->fork_ev, ex->stream));
+        for (cudaStream_t a : ex->aux) CK(cudaStreamWaitEvent(a, ex->fork_ev, 0));
+    }
     for (int f0 = 0, c = 0; f0 < nframes; f0 += chunk, ++c) {
         const int nf = std::min(chunk, nframes - f0);
         cudaStream_t s = (c % 3 == 0) ? ex->stream : ex->aux[c % 3 - 1];
@@ -761,13 +766,13 @@ vsg_status vsg_extract_batch_dev(vsg_extractor *ex, const uint8_t *images_dev, i
         st = run_pipeline(ex, s, f0, images_dev + (size_t)f0 * frame_stride, pitch, (int64_t)frame_stride, nf, lap_x0, lap_x1,
                           keypoints_dev + (size_t)f0 * capacity, descriptors_dev + (size_t)f0 * capacity * 32, capacity,
                           n_dev + f0, mono_dev + f0);
-        if (st != VSG_OK) return st;
+        if (st != VSG_OK) break;       // the aux streams are joined below on the error path too
     }
     for (int k = 0; k < vsg_extractor::kAuxStreams; ++k) {
         CK(cudaEventRecord(ex->join_ev[k], ex->aux[k]));
         CK(cudaStreamWaitEvent(ex->stream, ex->join_ev[k], 0));
     }
-    return VSG_OK;
+    return st;
 }
 
 vsg_status vsg_extractor_sync(vsg_extractor *ex) {
