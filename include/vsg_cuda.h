@@ -424,6 +424,19 @@ vsg_status vsg_search_by_bow_kf(vsg_matcher *m, const vsg_frame_view *KF1, const
                                 const int32_t *nodes2, const int32_t *ptr2, const int32_t *idx2, float nnratio,
                                 int check_ori, int32_t *matches12_out, int *nmatches_out);
 
+/* The Hamming-distance half of the BoW-guided pairings, for callers that own the per-pair geometry test — two-camera
+ * SearchForTriangulation (ORBmatcher.cc:902-1146 with mpCamera2 != NULL), where the epipolar test is the caller's
+ * KannalaBrandt8 camera code.  The merge walk over the two feature vectors (:966-1118): for every feature i1 of KF1 with
+ * use1[i1] != 0 inside a vocabulary node both vectors share, ALL features of that node in KF2, in the reference's scan
+ * order, with their descriptor distances.  q1_out[k] = i1 (walk order), its candidates are
+ * cand_idx2_out / cand_dist_out[cand_ptr_out[k] .. cand_ptr_out[k + 1]).  VSG_ERR_CAPACITY with *nq_out / *total_out = the
+ * needed sizes when q_capacity (+ 1 for cand_ptr_out) or capacity is too small. */
+vsg_status vsg_bow_pair_distances(vsg_matcher *m, const vsg_frame_view *KF1, const uint8_t *use1, const vsg_frame_view *KF2,
+                                  int nnodes1, const int32_t *nodes1, const int32_t *ptr1, const int32_t *idx1, int nnodes2,
+                                  const int32_t *nodes2, const int32_t *ptr2, const int32_t *idx2, int32_t *q1_out,
+                                  int32_t *cand_ptr_out, int q_capacity, int32_t *cand_idx2_out, int32_t *cand_dist_out,
+                                  int capacity, int *nq_out, int *total_out);
+
 /* SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse) (ORBmatcher.cc:902-1146), single
  * pinhole camera per keyframe (mpCamera2 == NULL).  has_mp1/2[i] = GetMapPoint(i) != NULL.  f12 = the
  * fundamental matrix of Pinhole::epipolarConstrain (Pinhole.cpp:118-141), row-major; ep = epipole of KF1 in KF2

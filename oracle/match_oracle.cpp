@@ -645,7 +645,14 @@ int orc_fuse_search(const orc_frame_view *KF, int n, const orc_search_point *pts
 int orc_search_by_sim3(const orc_frame_view *KF1, const orc_frame_view *KF2, const orc_search_point *pts1,
                        const uint8_t *desc1, const orc_search_point *pts2, const uint8_t *desc2, float th,
                        int32_t *matches12) {
-    const int n1 = KF1->n, n2 = KF2->n;
+    return orc_search_by_sim3_n(KF1, KF2, KF1->n, pts1, desc1, KF2->n, pts2, desc2, th, matches12);
+}
+
+// the same with n1 / n2 map point slots that may exceed the searched feature counts: two-camera keyframes, whose
+// GetMapPointMatches() has Nleft + Nright entries while GetFeaturesInArea only walks the left camera (:1488-1652)
+int orc_search_by_sim3_n(const orc_frame_view *KF1, const orc_frame_view *KF2, int n1, const orc_search_point *pts1,
+                         const uint8_t *desc1, int n2, const orc_search_point *pts2, const uint8_t *desc2, float th,
+                         int32_t *matches12) {
     std::vector<int> match1(n1, -1), match2(n2, -1);
     std::vector<int> cand;
     for (int dir = 0; dir < 2; ++dir) {

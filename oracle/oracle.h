@@ -202,6 +202,10 @@ int orc_fuse_search(const orc_frame_view *KF, int n, const orc_search_point *pts
 int orc_search_by_sim3(const orc_frame_view *KF1, const orc_frame_view *KF2, const orc_search_point *pts1,
                        const uint8_t *desc1, const orc_search_point *pts2, const uint8_t *desc2, float th,
                        int32_t *matches12);
+/* ... with n1 / n2 map point slots >= the feature counts of the views (two-camera keyframes: the views are the left cameras). */
+int orc_search_by_sim3_n(const orc_frame_view *KF1, const orc_frame_view *KF2, int n1, const orc_search_point *pts1,
+                         const uint8_t *desc1, int n2, const orc_search_point *pts2, const uint8_t *desc2, float th,
+                         int32_t *matches12);
 /* SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (:758-900). */
 int orc_search_by_bow_kf(const orc_frame_view *KF1, const uint8_t *mp_valid1, const orc_frame_view *KF2,
                          const uint8_t *mp_valid2, int nn1, const int32_t *nodes1, const int32_t *ptr1,

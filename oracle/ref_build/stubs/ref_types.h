@@ -41,6 +41,7 @@ public:
     virtual ~GeometricCamera() {}
     virtual Eigen::Vector2f project(const Eigen::Vector3f &v3D) = 0;
     virtual Eigen::Matrix3f toK_() = 0;
+    virtual Eigen::Vector3f unprojectEig(const cv::Point2f &p2D) = 0;
     virtual bool epipolarConstrain(GeometricCamera *pCamera2, const cv::KeyPoint &kp1, const cv::KeyPoint &kp2,
                                    const Eigen::Matrix3f &R12, const Eigen::Vector3f &t12, const float sigmaLevel,
                                    const float unc) = 0;
@@ -60,6 +61,9 @@ public:
         Eigen::Matrix3f K;
         K << mvParameters[0], 0.f, mvParameters[2], 0.f, mvParameters[1], mvParameters[3], 0.f, 0.f, 1.f;
         return K;
+    }
+    Eigen::Vector3f unprojectEig(const cv::Point2f &p) override {
+        return Eigen::Vector3f((p.x - mvParameters[2]) / mvParameters[0], (p.y - mvParameters[3]) / mvParameters[1], 1.f);
     }
     bool epipolarConstrain(GeometricCamera *pCamera2, const cv::KeyPoint &kp1, const cv::KeyPoint &kp2, const Eigen::Matrix3f &R12,
                            const Eigen::Vector3f &t12, const float, const float unc) override {
@@ -101,7 +105,7 @@ public:
         K << mvParameters[0], 0.f, mvParameters[2], 0.f, mvParameters[1], mvParameters[3], 0.f, 0.f, 1.f;
         return K;
     }
-    Eigen::Vector3f ray(const cv::Point2f &p) {
+    Eigen::Vector3f unprojectEig(const cv::Point2f &p) override {
         const float mx = (p.x - mvParameters[2]) / mvParameters[0], my = (p.y - mvParameters[3]) / mvParameters[1];
         const float th = sqrtf(mx * mx + my * my);
         if (th < 1e-6f) return Eigen::Vector3f(mx, my, 1.f);
@@ -110,7 +114,7 @@ public:
     }
     bool epipolarConstrain(GeometricCamera *pCamera2, const cv::KeyPoint &kp1, const cv::KeyPoint &kp2, const Eigen::Matrix3f &R12,
                            const Eigen::Vector3f &t12, const float, const float unc) override {
-        Eigen::Vector3f r1 = ray(kp1.pt), r2 = static_cast<KannalaBrandt8 *>(pCamera2)->ray(kp2.pt);
+        Eigen::Vector3f r1 = unprojectEig(kp1.pt), r2 = pCamera2->unprojectEig(kp2.pt);
         Eigen::Vector3f r21 = R12 * r2;
         const float cosParallax = r1.dot(r21) / (r1.norm() * r21.norm());
         if (cosParallax > 0.9998f) return false;

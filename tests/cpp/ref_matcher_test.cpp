@@ -9,6 +9,7 @@
 //   ref_matcher_test_gpu  links libvsg_cuda.so:              shim host code + CUDA kernels      == reference   (B200)
 //
 //   usage: ref_matcher_test_{cpu,gpu} frame_a.raw frame_b.raw      (two 640x480 8-bit frames; b = a shifted by (9, 5))
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -25,6 +26,7 @@
 #define VS_GRAPHS VSG_SHIM
 #define VSG_HAVE_OPENCV 1
 #include "../../visual_sgraphs_b200/shim/ORBmatcher.h"
+#include "../../visual_sgraphs_b200/shim/FrameOps.h"
 #undef VS_GRAPHS
 
 using VS_GRAPHS::Frame;
@@ -375,27 +377,32 @@ int main(int argc, char **argv) {
     }
 
     // ---- SearchByProjection(Frame& Cur, KeyFrame*, sAlreadyFound, th, ORBdist)  :1880-2000 ----
+    for (int two = 0; two < 2; ++two)
     for (int variant = 0; variant < 2; ++variant) {
-        Options o; o.seed = 50 + variant;
+        Options o; o.seed = 50 + variant; o.two_cameras = two;
         Pair P(ea, eb, o);
         int got[2];
         for (int k = 0; k < 2; ++k) {
             World &w = k ? P.s : P.r;
+            // two cameras: the method has no code of its own for them; it reads pKF->mvKeysUn[i] for every map point slot i, so
+            // only the left camera's slots may hold points (anything else is out of bounds in the reference itself)
+            if (two) for (int i = w.KA->NLeft; i < w.KA->N; ++i) w.KA->mvpMapPoints[i] = nullptr;
             std::set<MapPoint *> found;
             for (int i = 0; i < w.B.N; ++i) if (i % 4 != 0) w.B.mvpMapPoints[i] = nullptr;
             for (int i = 0; i < w.nA; i += 6) found.insert(w.mp(i));
             if (k == 0) got[0] = RefMatcher(0.9f, variant == 0).SearchByProjection(w.B, w.KA.get(), found, variant ? 10.f : 3.f, variant ? 100 : 64);
             else { ShimMatcher m(0.9f, variant == 0); got[1] = m.SearchByProjection(w.B, w.KA.get(), found, variant ? 10.f : 3.f, variant ? 100 : 64); }
         }
-        report("SearchByProjection(Cur, KF, sAlreadyFound)", got[0], got[1]);
+        report(two ? "SearchByProjection(Cur, KF, sAlreadyFound) two cameras" : "SearchByProjection(Cur, KF, sAlreadyFound)", got[0], got[1]);
         EXPECT(got[0] == got[1] && got[0] > 50, "SearchByProjection(reloc) variant %d: %d vs %d", variant, got[0], got[1]);
         compare_worlds(P.r, P.s, "SearchByProjection(reloc)");
     }
 
     // ---- SearchByProjection(KeyFrame*, Sim3f&, vpPoints[, vpPointsKFs], vpMatched[, vpMatchedKF], th, ratioHamming)  :430-641 ----
-    for (int with_kfs = 0; with_kfs < 2; ++with_kfs)
+    for (int with_kfs = 0; with_kfs < 4; ++with_kfs)       // bit 0: vpPointsKFs overload, bit 1: two-camera keyframe
         for (int variant = 0; variant < 2; ++variant) {
-            Options o; o.seed = 60 + variant;
+            const int two = with_kfs >> 1;
+            Options o; o.seed = 60 + variant; o.two_cameras = two;
             Pair P(ea, eb, o);
             std::vector<int> out[2], outkf[2];
             int got[2];
@@ -414,17 +421,18 @@ int main(int argc, char **argv) {
                 const float rh = variant ? 1.5f : 1.0f;
                 if (k == 0) {
                     RefMatcher m(0.75f, true);
-                    got[0] = with_kfs ? m.SearchByProjection(w.KB.get(), Scw, vp, vpKFs, matched, matchedKF, th, rh)
+                    got[0] = (with_kfs & 1) ? m.SearchByProjection(w.KB.get(), Scw, vp, vpKFs, matched, matchedKF, th, rh)
                                       : m.SearchByProjection(w.KB.get(), Scw, vp, matched, th, rh);
                 } else {
                     ShimMatcher m(0.75f, true);
-                    got[1] = with_kfs ? m.SearchByProjection(w.KB.get(), Scw, vp, vpKFs, matched, matchedKF, th, rh)
+                    got[1] = (with_kfs & 1) ? m.SearchByProjection(w.KB.get(), Scw, vp, vpKFs, matched, matchedKF, th, rh)
                                       : m.SearchByProjection(w.KB.get(), Scw, vp, matched, th, rh);
                 }
                 out[k] = ids(matched);
                 for (KeyFrame *kf : matchedKF) outkf[k].push_back(kf == nullptr ? -1 : (kf == w.KA.get() ? 0 : 1));
             }
-            report(with_kfs ? "SearchByProjection(KF, Scw, vpPoints, vpPointsKFs)" : "SearchByProjection(KF, Scw, vpPoints)", got[0], got[1]);
+            report((with_kfs & 1) ? (two ? "SearchByProjection(KF, Scw, vpPoints, vpPointsKFs) two cameras" : "SearchByProjection(KF, Scw, vpPoints, vpPointsKFs)")
+                                  : (two ? "SearchByProjection(KF, Scw, vpPoints) two cameras" : "SearchByProjection(KF, Scw, vpPoints)"), got[0], got[1]);
             EXPECT(got[0] == got[1] && got[0] > 50, "SearchByProjection(Sim3) kfs=%d variant=%d: %d vs %d", with_kfs, variant, got[0], got[1]);
             EXPECT(out[0] == out[1] && outkf[0] == outkf[1], "SearchByProjection(Sim3) kfs=%d variant=%d: vpMatched differ", with_kfs, variant);
             compare_worlds(P.r, P.s, "SearchByProjection(Sim3)");
@@ -446,16 +454,17 @@ int main(int argc, char **argv) {
         }
 
     // ---- SearchForTriangulation(KF1, KF2, vMatchedPairs, bOnlyStereo, bCoarse)  :902-1146 ----
+    for (int two = 0; two < 2; ++two)
     for (int variant = 0; variant < 4; ++variant) {
-        Options o; o.seed = 80 + variant; o.keep_mp = 0.4f;
+        Options o; o.seed = 80 + variant; o.keep_mp = 0.4f; o.two_cameras = two;
         Pair P(ea, eb, o);
         const bool only_stereo = variant == 1, coarse = variant == 2, ori = variant != 3;
         std::vector<std::pair<size_t, size_t>> p0, p1;
         const int g0 = RefMatcher(0.6f, ori).SearchForTriangulation(P.r.KA.get(), P.r.KB.get(), p0, only_stereo, coarse);
         ShimMatcher sm(0.6f, ori);
         const int g1 = sm.SearchForTriangulation(P.s.KA.get(), P.s.KB.get(), p1, only_stereo, coarse);
-        report("SearchForTriangulation", g0, g1);
-        EXPECT(g0 == g1 && g0 > 20, "SearchForTriangulation variant %d: %d vs %d", variant, g0, g1);
+        report(two ? "SearchForTriangulation two cameras" : "SearchForTriangulation", g0, g1);
+        EXPECT(g0 == g1 && (g0 > 20 || (two && only_stereo)), "SearchForTriangulation variant %d: %d vs %d", variant, g0, g1);
         EXPECT(p0 == p1, "SearchForTriangulation variant %d: vMatchedPairs differ (%zu vs %zu)", variant, p0.size(), p1.size());
         compare_worlds(P.r, P.s, "SearchForTriangulation");
     }
@@ -483,8 +492,9 @@ int main(int argc, char **argv) {
         }
 
     // ---- Fuse(KeyFrame*, Sim3f&, vpPoints, th, vpReplacePoint)  :1337-1446 ----
+    for (int two = 0; two < 2; ++two)
     for (int variant = 0; variant < 2; ++variant) {
-        Options o; o.seed = 100 + variant;
+        Options o; o.seed = 100 + variant; o.two_cameras = two;
         Pair P(ea, eb, o);
         std::vector<int> rep[2];
         int got[2];
@@ -499,15 +509,16 @@ int main(int argc, char **argv) {
             else { ShimMatcher m; got[1] = m.Fuse(w.KB.get(), Scw, vp, variant ? 6.f : 4.f, replace); }
             rep[k] = ids(replace);
         }
-        report("Fuse(KF, Scw)", got[0], got[1]);
+        report(two ? "Fuse(KF, Scw) two cameras" : "Fuse(KF, Scw)", got[0], got[1]);
         EXPECT(got[0] == got[1] && got[0] > 50, "Fuse(KF, Scw) variant %d: %d vs %d", variant, got[0], got[1]);
         EXPECT(rep[0] == rep[1], "Fuse(KF, Scw) variant %d: vpReplacePoint differ", variant);
         compare_worlds(P.r, P.s, "Fuse(KF, Scw)");
     }
 
     // ---- SearchBySim3(KF1, KF2, vpMatches12, S12, th)  :1448-1665 ----
+    for (int two = 0; two < 2; ++two)
     for (int variant = 0; variant < 2; ++variant) {
-        Options o; o.seed = 110 + variant;
+        Options o; o.seed = 110 + variant; o.two_cameras = two;
         Pair P(ea, eb, o);
         std::vector<int> out[2];
         int got[2];
@@ -523,10 +534,68 @@ int main(int argc, char **argv) {
             else { ShimMatcher m; got[1] = m.SearchBySim3(w.KA.get(), w.KB.get(), m12, S12, variant ? 10.f : 7.5f); }
             out[k] = ids(m12);
         }
-        report("SearchBySim3", got[0], got[1]);
+        report(two ? "SearchBySim3 two cameras" : "SearchBySim3", got[0], got[1]);
         EXPECT(got[0] == got[1] && got[0] > 20, "SearchBySim3 variant %d: %d vs %d", variant, got[0], got[1]);
         EXPECT(out[0] == out[1], "SearchBySim3 variant %d: vpMatches12 differ (%d vs %d set)", variant, count_set(out[0]), count_set(out[1]));
         compare_worlds(P.r, P.s, "SearchBySim3");
+    }
+
+    // ---- Frame::ComputeStereoFishEyeMatches (Frame.cc:1181-1225): kNN-2 + ratio 0.7 + the camera's triangulation gate ----
+    {
+        struct FishCamera {     // stand-in for KannalaBrandt8::TriangulateMatches: a deterministic function of its arguments
+            float TriangulateMatches(FishCamera *other, const cv::KeyPoint &kp1, const cv::KeyPoint &kp2, const Eigen::Matrix3f &R12,
+                                     const Eigen::Vector3f &t12, const float sigma1, const float sigma2, Eigen::Vector3f &p3D) {
+                const float dx = kp2.pt.x - kp1.pt.x - t12(0) * 100.f, dy = kp1.pt.y - kp2.pt.y;   // frame b = frame a shifted by (+9, +5)
+                if (std::fabs(dy) > 5.4f * sigma1 || dx <= 3.2f * sigma2 || other == nullptr) return -1.f;
+                p3D = Eigen::Vector3f(kp1.pt.x * R12(0, 0), kp1.pt.y, 400.f / dx);
+                return 400.f / dx;
+            }
+        };
+        struct FishFrame {
+            int Nleft = 0, Nright = 0, monoLeft = 0, monoRight = 0, mnCloseMPs = 7;
+            std::vector<cv::KeyPoint> mvKeys, mvKeysRight;
+            cv::Mat mDescriptors, mDescriptorsRight;
+            std::vector<int> mvLeftToRightMatch, mvRightToLeftMatch;
+            std::vector<float> mvDepth, mvuRight, mvLevelSigma2;
+            std::vector<Eigen::Vector3f> mvStereo3Dpoints;
+            FishCamera camL, camR;
+            FishCamera *mpCamera = &camL, *mpCamera2 = &camR;
+            Eigen::Matrix3f mRlr = Eigen::Matrix3f::Identity();
+            Eigen::Vector3f mtlr = Eigen::Vector3f(0.05f, 0.f, 0.f);
+        };
+        FishFrame F;
+        F.mvKeys = ea.keys; F.mvKeysRight = eb.keys;
+        F.mDescriptors = ea.desc.clone(); F.mDescriptorsRight = eb.desc.clone();
+        F.Nleft = (int)ea.keys.size(); F.Nright = (int)eb.keys.size();
+        F.monoLeft = 120; F.monoRight = 77;
+        F.mvLevelSigma2 = ea.sigma2;
+        FishFrame G = F;
+        VSG_SHIM::frame_ops::ComputeStereoFishEyeMatches<FishCamera>(F);
+        // the reference's loop on the host, with cv::BFMatcher's order (distance, then train index)
+        G.mvLeftToRightMatch.assign(G.Nleft, -1); G.mvRightToLeftMatch.assign(G.Nright, -1);
+        G.mvDepth.assign(G.Nleft, -1.f); G.mvuRight.assign(G.Nleft, -1.f); G.mvStereo3Dpoints.assign(G.Nleft, Eigen::Vector3f());
+        G.mnCloseMPs = 0;
+        int nGood = 0;
+        for (int q = G.monoLeft; q < G.Nleft; ++q) {
+            int b0 = 1 << 30, b1 = 1 << 30, i0 = -1, i1 = -1;
+            for (int t = G.monoRight; t < G.Nright; ++t) {
+                const int d = RefMatcher::DescriptorDistance(G.mDescriptors.row(q), G.mDescriptorsRight.row(t));
+                if (d < b0) { b1 = b0; i1 = i0; b0 = d; i0 = t; }
+                else if (d < b1) { b1 = d; i1 = t; }
+            }
+            if (i1 < 0 || !((float)b0 < (float)b1 * 0.7)) continue;
+            Eigen::Vector3f p3D;
+            const float depth = G.camL.TriangulateMatches(G.mpCamera2, G.mvKeys[q], G.mvKeysRight[i0], G.mRlr, G.mtlr,
+                                                          G.mvLevelSigma2[G.mvKeys[q].octave], G.mvLevelSigma2[G.mvKeysRight[i0].octave], p3D);
+            if (depth > 0.0001f) { G.mvLeftToRightMatch[q] = i0; G.mvRightToLeftMatch[i0] = q; G.mvStereo3Dpoints[q] = p3D; G.mvDepth[q] = depth; ++nGood; }
+        }
+        bool same3d = true;
+        for (int i = 0; i < F.Nleft; ++i)
+            for (int k = 0; k < 3; ++k) same3d = same3d && F.mvStereo3Dpoints[i](k) == G.mvStereo3Dpoints[i](k);
+        report("ComputeStereoFishEyeMatches (matches)", nGood, (int)std::count_if(F.mvLeftToRightMatch.begin(), F.mvLeftToRightMatch.end(), [](int v) { return v >= 0; }));
+        EXPECT(nGood > 20, "ComputeStereoFishEyeMatches: only %d matches", nGood);
+        EXPECT(F.mvLeftToRightMatch == G.mvLeftToRightMatch && F.mvRightToLeftMatch == G.mvRightToLeftMatch && F.mvDepth == G.mvDepth &&
+                   F.mvuRight == G.mvuRight && same3d && F.mnCloseMPs == 0, "ComputeStereoFishEyeMatches differs from the reference loop");
     }
 
     std::printf("%s: %d checks, %d failed\n", g_fail ? "FAILED" : "ok", g_checks, g_fail);

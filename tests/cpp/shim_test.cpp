@@ -97,6 +97,9 @@ struct Camera {
     float fx = 500, fy = 500, cx = 320, cy = 240;
     Vec2 project(const Vec3 &p) const { return Vec2{{fx * p.v[0] / p.v[2] + cx, fy * p.v[1] / p.v[2] + cy}}; }
     Mat3 toK_() const { Mat3 K; K << fx, 0.f, cx, 0.f, fy, cy, 0.f, 0.f, 1.f; return K; }
+    // the per-pair test of two-camera SearchForTriangulation (the caller's camera code); not reached by this program's
+    // single-camera scenarios — tests/cpp/ref_matcher_test.cpp covers that branch against the reference itself
+    bool epipolarConstrain(Camera *, const cv::KeyPoint &, const cv::KeyPoint &, const Mat3 &, const Vec3 &, float, float) const { return false; }
 };
 struct KeyFrame;
 struct Frame;
@@ -175,6 +178,7 @@ struct KeyFrame : Frame {   // the members ORBmatcher reads from a KeyFrame (Key
     Pose GetRightPose() const { return right_pose; }
     Vec3 GetRightCameraCenter() const { return right_pose.inverse().translation(); }
     Pose GetPoseInverse() const { return pose.inverse(); }
+    Pose GetRightPoseInverse() const { return right_pose.inverse(); }
 };
 
 static std::vector<unsigned char> read_raw(const char *path, size_t n) {

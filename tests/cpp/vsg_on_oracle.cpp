@@ -32,6 +32,26 @@ const char *vsg_last_error(void) { return "vsg_on_oracle adapter"; }
 vsg_status vsg_matcher_create(int, vsg_matcher **out) { *out = new vsg_matcher{0}; return VSG_OK; }
 void vsg_matcher_destroy(vsg_matcher *m) { delete m; }
 
+// knnMatch(k = 2): (distance, index) lexicographic top-2, missing neighbours idx -1 / dist INT32_MAX (include/vsg_cuda.h)
+vsg_status vsg_knn2(vsg_matcher *, const uint8_t *query, int nq, const uint8_t *train, int nt, int offset, int32_t *out_idx, int32_t *out_dist) {
+    for (int q = 0; q < nq; ++q) {
+        int b0 = 0x7fffffff, b1 = 0x7fffffff, i0 = -1, i1 = -1;
+        for (int t = 0; t < nt; ++t) {
+            const int d = orc_descriptor_distance(query + (size_t)q * 32, train + (size_t)t * 32);
+            if (d < b0) { b1 = b0; i1 = i0; b0 = d; i0 = t; }
+            else if (d < b1) { b1 = d; i1 = t; }
+        }
+        out_idx[2 * q] = i0 >= 0 ? i0 + offset : -1; out_dist[2 * q] = b0;
+        out_idx[2 * q + 1] = i1 >= 0 ? i1 + offset : -1; out_dist[2 * q + 1] = b1;
+    }
+    return VSG_OK;
+}
+vsg_status vsg_undistort_keypoints(vsg_matcher *, int n, const float *xy_in, double fx, double fy, double cx, double cy, const double *dist,
+                                   int dist_n, float *xy_out) {
+    orc_undistort_points(n, xy_in, fx, fy, cx, cy, dist, dist_n, xy_out);
+    return VSG_OK;
+}
+
 vsg_status vsg_frame_create(vsg_matcher *, const vsg_frame_view *view, vsg_frame **out) {
     vsg_frame *f = new vsg_frame;
     const orc_frame_view *s = V(view);
@@ -110,10 +130,10 @@ vsg_status vsg_fuse_search(vsg_matcher *, const vsg_frame *KF, int n, const vsg_
     if (nfused_out) *nfused_out = nf;
     return VSG_OK;
 }
-vsg_status vsg_search_by_sim3(vsg_matcher *, const vsg_frame *KF1, const vsg_frame *KF2, int, const vsg_search_point *pts1, const uint8_t *desc1,
-                              int, const vsg_search_point *pts2, const uint8_t *desc2, float th, int32_t *matches12_out, int *nfound_out) {
-    *nfound_out = orc_search_by_sim3(V(KF1), V(KF2), reinterpret_cast<const orc_search_point *>(pts1), desc1,
-                                     reinterpret_cast<const orc_search_point *>(pts2), desc2, th, matches12_out);
+vsg_status vsg_search_by_sim3(vsg_matcher *, const vsg_frame *KF1, const vsg_frame *KF2, int n1, const vsg_search_point *pts1, const uint8_t *desc1,
+                              int n2, const vsg_search_point *pts2, const uint8_t *desc2, float th, int32_t *matches12_out, int *nfound_out) {
+    *nfound_out = orc_search_by_sim3_n(V(KF1), V(KF2), n1, reinterpret_cast<const orc_search_point *>(pts1), desc1, n2,
+                                       reinterpret_cast<const orc_search_point *>(pts2), desc2, th, matches12_out);
     return VSG_OK;
 }
 vsg_status vsg_search_by_bow_kf(vsg_matcher *, const vsg_frame_view *KF1, const uint8_t *mp_valid1, const vsg_frame_view *KF2,
@@ -122,6 +142,39 @@ vsg_status vsg_search_by_bow_kf(vsg_matcher *, const vsg_frame_view *KF1, const 
                                 int32_t *matches12_out, int *nmatches_out) {
     *nmatches_out = orc_search_by_bow_kf(V(KF1), mp_valid1, V(KF2), mp_valid2, nn1, nodes1, ptr1, idx1, nn2, nodes2, ptr2, idx2, nnratio,
                                          check_ori, matches12_out);
+    return VSG_OK;
+}
+vsg_status vsg_bow_pair_distances(vsg_matcher *, const vsg_frame_view *KF1, const uint8_t *use1, const vsg_frame_view *KF2, int nn1,
+                                  const int32_t *nodes1, const int32_t *ptr1, const int32_t *idx1, int nn2, const int32_t *nodes2,
+                                  const int32_t *ptr2, const int32_t *idx2, int32_t *q1_out, int32_t *cand_ptr_out, int q_capacity,
+                                  int32_t *cand_idx2_out, int32_t *cand_dist_out, int capacity, int *nq_out, int *total_out) {
+    std::vector<int> q1, cptr(1, 0), cand, dist;
+    int ia = 0, ib = 0;
+    while (ia < nn1 && ib < nn2) {                 // the merge walk of two DBoW2::FeatureVectors (ORBmatcher.cc:961-1118)
+        if (nodes1[ia] == nodes2[ib]) {
+            for (int k = ptr1[ia]; k < ptr1[ia + 1]; ++k) {
+                const int i1 = idx1[k];
+                if (!use1[i1]) continue;
+                q1.push_back(i1);
+                for (int j = ptr2[ib]; j < ptr2[ib + 1]; ++j) {
+                    cand.push_back(idx2[j]);
+                    dist.push_back(orc_descriptor_distance(KF1->descriptors + (size_t)i1 * 32, KF2->descriptors + (size_t)idx2[j] * 32));
+                }
+                cptr.push_back((int)cand.size());
+            }
+            ++ia; ++ib;
+        } else if (nodes1[ia] < nodes2[ib]) {
+            ++ia;
+        } else {
+            ++ib;
+        }
+    }
+    *nq_out = (int)q1.size();
+    *total_out = (int)cand.size();
+    if ((int)q1.size() > q_capacity || (int)cand.size() > capacity) return VSG_ERR_CAPACITY;
+    for (size_t k = 0; k < q1.size(); ++k) { q1_out[k] = q1[k]; cand_ptr_out[k] = cptr[k]; }
+    cand_ptr_out[q1.size()] = (int)cand.size();
+    for (size_t c = 0; c < cand.size(); ++c) { cand_idx2_out[c] = cand[c]; cand_dist_out[c] = dist[c]; }
     return VSG_OK;
 }
 vsg_status vsg_search_for_triangulation(vsg_matcher *, const vsg_frame_view *KF1, const uint8_t *has_mp1, const vsg_frame_view *KF2,

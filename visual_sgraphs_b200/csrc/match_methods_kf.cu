@@ -247,9 +247,11 @@ vsg_status vsg_search_by_sim3(vsg_matcher *m, const vsg_frame *KF1, const vsg_fr
                               const vsg_search_point *pts1, const uint8_t *desc1, int n2,
                               const vsg_search_point *pts2, const uint8_t *desc2, float th, int32_t *matches12_out,
                               int *nfound_out) {
-    if (!m || !KF1 || !KF2 || n1 != KF1->n || n2 != KF2->n || (n1 > 0 && (!pts1 || !desc1 || !matches12_out)) ||
+    // n1 / n2 = map point slots of the keyframes; more than the searched features for two-camera keyframes (KF1 / KF2 are then
+    // their left cameras): slot i of KF1 searches KF2's features, the answer is cross-checked through slot idx2 of KF2
+    if (!m || !KF1 || !KF2 || n1 < KF1->n || n2 < KF2->n || (n1 > 0 && (!pts1 || !desc1 || !matches12_out)) ||
         (n2 > 0 && (!pts2 || !desc2))) {
-        set_error("vsg_search_by_sim3: pts1 / pts2 must have one entry per keyframe feature");
+        set_error("vsg_search_by_sim3: pts1 / pts2 need at least one entry per keyframe feature");
         return VSG_ERR_INVALID;
     }
     CK(cudaSetDevice(m->device));
@@ -321,6 +323,32 @@ vsg_status vsg_search_by_bow_kf(vsg_matcher *m, const vsg_frame_view *KF1, const
     }
     if (check_ori) apply_rot_filter(rot_hist, [&](int i1) { matches12_out[i1] = -1; --nmatches; });
     if (nmatches_out) *nmatches_out = nmatches;
+    return VSG_OK;
+}
+
+// The Hamming-distance half of the BoW-guided pairings for callers that own the per-pair geometry test (two-camera
+// SearchForTriangulation: KannalaBrandt8::epipolarConstrain is the caller's camera code): the merge walk of :966-1118 with
+// every candidate's distance from the GPU, in the reference's scan order.
+vsg_status vsg_bow_pair_distances(vsg_matcher *m, const vsg_frame_view *KF1, const uint8_t *use1, const vsg_frame_view *KF2,
+                                  int nnodes1, const int32_t *nodes1, const int32_t *ptr1, const int32_t *idx1, int nnodes2,
+                                  const int32_t *nodes2, const int32_t *ptr2, const int32_t *idx2, int32_t *q1_out,
+                                  int32_t *cand_ptr_out, int q_capacity, int32_t *cand_idx2_out, int32_t *cand_dist_out,
+                                  int capacity, int *nq_out, int *total_out) {
+    if (!m || !KF1 || !KF2 || !featvec_ok(nnodes1, nodes1, ptr1, idx1) || !featvec_ok(nnodes2, nodes2, ptr2, idx2) ||
+        (KF1->n > 0 && !use1) || !nq_out || !total_out)
+        return VSG_ERR_INVALID;
+    CK(cudaSetDevice(m->device));
+    std::vector<int> q1, cptr, cand, dist;
+    vsg_status st = bow_pair_dists(m, KF1, KF2, FeatVec{nnodes1, nodes1, ptr1, idx1}, FeatVec{nnodes2, nodes2, ptr2, idx2},
+                                   [&](int i1) { return use1[i1] != 0; }, q1, cptr, cand, dist);
+    if (st != VSG_OK) return st;
+    *nq_out = (int)q1.size();
+    *total_out = (int)cand.size();
+    if ((int)q1.size() > q_capacity || (int)cand.size() > capacity) return VSG_ERR_CAPACITY;
+    if ((!q1.empty() && (!q1_out || !cand_ptr_out)) || (!cand.empty() && (!cand_idx2_out || !cand_dist_out))) return VSG_ERR_INVALID;
+    for (size_t k = 0; k < q1.size(); ++k) { q1_out[k] = q1[k]; cand_ptr_out[k] = cptr[k]; }
+    if (cand_ptr_out) cand_ptr_out[q1.size()] = (int)cand.size();
+    for (size_t c = 0; c < cand.size(); ++c) { cand_idx2_out[c] = cand[c]; cand_dist_out[c] = dist[c]; }
     return VSG_OK;
 }
 

@@ -3,6 +3,7 @@
 //   Frame::UndistortKeyPoints      :891-922    cv::undistortPoints(mat, mat, mK, mDistCoef, cv::Mat(), mK)
 //   Frame::ComputeImageBounds      :924-955    the same call on the four image corners
 //   Frame::ComputeStereoFromRGBD   :1129-1150  one depth look-up per keypoint
+//   Frame::ComputeStereoFishEyeMatches :1181-1225  BFMatcher.knnMatch(k = 2) + Lowe ratio 0.7 + the camera's triangulation gate
 // The undistortion runs on the device (vsg_undistort_keypoints, bit-identical to OpenCV's double-precision path); the
 // depth association is a gather of N values from a host image and stays host code.
 //
@@ -12,8 +13,11 @@
 #ifndef VSG_SHIM_FRAMEOPS_H
 #define VSG_SHIM_FRAMEOPS_H
 
+#include <cstdint>
+#include <cstring>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/vsg_cuda.h"
@@ -89,6 +93,46 @@ inline void ComputeStereoFromRGBD(const std::vector<cv::KeyPoint> &mvKeys, const
         if (d > 0) {
             mvDepth[i] = d;
             mvuRight[i] = mvKeysUn[i].pt.x - mbf / d;
+        }
+    }
+}
+
+// Frame::ComputeStereoFishEyeMatches (Frame.cc:1181-1225) for a two-camera frame F: the brute-force kNN-2 between the
+// lapping-area descriptors of the left and the right image runs on the device (vsg_knn2: ties to the lower train index,
+// as cv::BFMatcher orders them); Lowe's ratio test is evaluated exactly as the reference writes it (float distance against
+// float * double 0.7); the parallax / reprojection gate is the frame's own camera model — KB8T = KannalaBrandt8, the class the
+// reference static_casts mpCamera to (:1212) — called per surviving match in the reference's order.
+template <class KB8T, class FrameT>
+inline void ComputeStereoFishEyeMatches(FrameT &F) {
+    typedef typename std::decay<decltype(F.mvStereo3Dpoints[0])>::type Vec3T;
+    F.mvLeftToRightMatch = std::vector<int>(F.Nleft, -1);
+    F.mvRightToLeftMatch = std::vector<int>(F.Nright, -1);
+    F.mvDepth = std::vector<float>(F.Nleft, -1.0f);
+    F.mvuRight = std::vector<float>(F.Nleft, -1);
+    F.mvStereo3Dpoints = std::vector<Vec3T>(F.Nleft);
+    F.mnCloseMPs = 0;
+    const int nl = F.Nleft - F.monoLeft, nr = F.Nright - F.monoRight;      // stereoDescLeft / stereoDescRight (:1187-1188)
+    if (nl <= 0 || nr <= 0) return;
+    std::vector<uint8_t> dl((size_t)nl * 32), dr((size_t)nr * 32);
+    for (int i = 0; i < nl; ++i) std::memcpy(&dl[(size_t)i * 32], F.mDescriptors.ptr(F.monoLeft + i), 32);
+    for (int i = 0; i < nr; ++i) std::memcpy(&dr[(size_t)i * 32], F.mDescriptorsRight.ptr(F.monoRight + i), 32);
+    std::vector<int32_t> idx((size_t)nl * 2), dist((size_t)nl * 2);
+    if (vsg_knn2(Workspace(), dl.data(), nl, dr.data(), nr, 0, idx.data(), dist.data()) != VSG_OK)
+        throw std::runtime_error(std::string("vsg_knn2: ") + vsg_last_error());
+    for (int q = 0; q < nl; ++q) {                                          // :1206-1224
+        if (idx[2 * q + 1] < 0) continue;                                   // (*it).size() >= 2
+        const float d0 = (float)dist[2 * q], d1 = (float)dist[2 * q + 1];   // cv::DMatch::distance is a float
+        if (!(d0 < d1 * 0.7)) continue;
+        const int iL = q + F.monoLeft, iR = idx[2 * q] + F.monoRight;
+        Vec3T p3D;
+        const float sigma1 = F.mvLevelSigma2[F.mvKeys[iL].octave], sigma2 = F.mvLevelSigma2[F.mvKeysRight[iR].octave];
+        const float depth = static_cast<KB8T *>(F.mpCamera)->TriangulateMatches(F.mpCamera2, F.mvKeys[iL], F.mvKeysRight[iR], F.mRlr,
+                                                                               F.mtlr, sigma1, sigma2, p3D);
+        if (depth > 0.0001f) {
+            F.mvLeftToRightMatch[iL] = iR;
+            F.mvRightToLeftMatch[iR] = iL;
+            F.mvStereo3Dpoints[iL] = p3D;
+            F.mvDepth[iL] = depth;
         }
     }
 }

@@ -12,14 +12,17 @@
 // Each template flattens those members into the C ABI's view structs, calls the library and writes the
 // results back exactly where the reference does.
 //
-// Scope: single-camera frames (Frame::Nleft == -1), plus the two-camera branches (Nleft != -1, stereo-fisheye rigs) of the
-// tracking calls SearchByProjection(Frame&, vector<MapPoint*>&), SearchByProjection(Frame&, const Frame&) and
-// SearchByBoW(KeyFrame*, Frame&, ...), and of SearchByBoW(KeyFrame*, KeyFrame*, ...) and Fuse(KeyFrame*, vpMapPoints, th,
-// bRight).  The other methods throw for two-camera frames — keep the reference's
-// CPU ORBmatcher for them in that configuration.
+// Scope: all 13 methods for single-camera frames (Frame::Nleft == -1) and for two-camera frames / keyframes (Nleft != -1,
+// stereo-fisheye rigs): the methods with two-camera code of their own (SearchByProjection(Frame&, vector<MapPoint*>&),
+// SearchByProjection(Frame&, const Frame&), SearchByBoW x 2, Fuse(..., bRight), SearchForTriangulation) follow it branch
+// by branch; the others (relocalisation / Sim3 projections, SearchBySim3, Fuse(KF, Scw, ...)) search the left camera, as
+// the reference's GetFeaturesInArea(..., bRight = false) does.  Every method is compared with the reference's own
+// ORBmatcher.cc in tests/cpp/ref_matcher_test.cpp.
 #ifndef VSG_SHIM_ORBMATCHER_H
 #define VSG_SHIM_ORBMATCHER_H
 
+#include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <set>
@@ -125,6 +128,21 @@ protected:
     template <class FrameT, class MapPointT>
     int SearchByProjectionTwoCameras(FrameT &F, const std::vector<MapPointT *> &vpMapPoints, const float th,
                                      const bool bFarPoints, const float thFarPoints);
+    template <class KeyFrameT>
+    int SearchForTriangulationTwoCameras(KeyFrameT *pKF1, KeyFrameT *pKF2, std::vector<std::pair<size_t, size_t>> &vMatchedPairs,
+                                         const bool bOnlyStereo, const bool bCoarse);
+    // ORBmatcher::ComputeThreeMaxima (ORBmatcher.cc:2002-2043) for the host-side replays
+    static void ComputeThreeMaxima(std::vector<int> *histo, const int L, int &ind1, int &ind2, int &ind3) {
+        int max1 = 0, max2 = 0, max3 = 0;
+        for (int i = 0; i < L; i++) {
+            const int s = (int)histo[i].size();
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+            else if (s > max3) { max3 = s; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+    }
 
     // ---- plumbing ----
     vsg_matcher *mpWorkspace = nullptr;
@@ -242,6 +260,14 @@ protected:
             FlattenCamera(F, c == 1, F.Nleft, nullptr, cam[c]);
             Check(vsg_frame_create(Workspace(), &cam[c].view, &fr[c].h), "vsg_frame_create");
         }
+    }
+    // What the methods without two-camera code of their own search on (reloc / Sim3 projections, SearchBySim3,
+    // Fuse(KF, Scw, ...)): Frame::GetFeaturesInArea / KeyFrame::GetFeaturesInArea with bRight == false walk the left
+    // camera's grid and keypoints (mvKeys, Frame.cc:840-848, KeyFrame.cc:862-868) and the descriptor rows [0, Nleft).
+    template <class FrameT>
+    static void FlattenSearched(const FrameT &F, int nLeft, Flat &out) {
+        if (nLeft != -1) FlattenCamera(F, false, nLeft, nullptr, out);
+        else Flatten(F, out);
     }
     template <class FrameT>
     static void RequireSingleCamera(const FrameT &F) {
@@ -460,9 +486,8 @@ int ORBmatcher::SearchForInitialization(FrameT &F1, FrameT &F2, std::vector<cv::
 template <class FrameT, class KeyFrameT, class MapPointT>
 int ORBmatcher::SearchByProjection(FrameT &CurrentFrame, KeyFrameT *pKF, const std::set<MapPointT *> &sAlreadyFound,
                                    const float th, const int ORBdist) {
-    RequireSingleCamera(CurrentFrame);
     Flat flat;
-    Flatten(CurrentFrame, flat);
+    FlattenSearched(CurrentFrame, CurrentFrame.Nleft, flat);      // two-camera frames: the left camera (no code of its own, :1880-2000)
     FrameGuard fr;
     Check(vsg_frame_create(Workspace(), &flat.view, &fr.h), "vsg_frame_create");
     const auto Tcw = CurrentFrame.GetPose();
@@ -615,10 +640,9 @@ template <class KeyFrameT, class MapPointT>
 int ORBmatcher::SearchByProjection(KeyFrameT *pKF, Sophus::Sim3<float> &Scw, const std::vector<MapPointT *> &vpPoints,
                                    const std::vector<KeyFrameT *> &vpPointsKFs, std::vector<MapPointT *> &vpMatched,
                                    std::vector<KeyFrameT *> &vpMatchedKF, int th, float ratioHamming) {
-    RequireSingleCameraKF(*pKF);
     const bool bWithKFs = !vpPointsKFs.empty();
     Flat flat;
-    Flatten(*pKF, flat);
+    FlattenSearched(*pKF, pKF->NLeft, flat);
     FrameGuard fr;
     Check(vsg_frame_create(Workspace(), &flat.view, &fr.h), "vsg_frame_create");
     const float &fx = pKF->fx, &fy = pKF->fy, &cx = pKF->cx, &cy = pKF->cy;
@@ -670,8 +694,6 @@ int ORBmatcher::SearchByProjection(KeyFrameT *pKF, Sophus::Sim3<float> &Scw, con
 template <class KeyFrameT, class MapPointT>
 int ORBmatcher::SearchBySim3(KeyFrameT *pKF1, KeyFrameT *pKF2, std::vector<MapPointT *> &vpMatches12, const Sophus::Sim3f &S12,
                              const float th) {
-    RequireSingleCameraKF(*pKF1);
-    RequireSingleCameraKF(*pKF2);
     const float &fx = pKF1->fx, &fy = pKF1->fy, &cx = pKF1->cx, &cy = pKF1->cy;
     Sophus::SE3f T1w = pKF1->GetPose();
     Sophus::SE3f T2w = pKF2->GetPose();
@@ -688,9 +710,9 @@ int ORBmatcher::SearchBySim3(KeyFrameT *pKF1, KeyFrameT *pKF2, std::vector<MapPo
             if (idx2 >= 0 && idx2 < N2) vbAlreadyMatched2[idx2] = true;
         }
     }
-    Flat f1, f2;
-    Flatten(*pKF1, f1);
-    Flatten(*pKF2, f2);
+    Flat f1, f2;                                   // N1 / N2 map point slots (both cameras) search the left cameras' features
+    FlattenSearched(*pKF1, pKF1->NLeft, f1);
+    FlattenSearched(*pKF2, pKF2->NLeft, f2);
     FrameGuard fr1, fr2;
     Check(vsg_frame_create(Workspace(), &f1.view, &fr1.h), "vsg_frame_create");
     Check(vsg_frame_create(Workspace(), &f2.view, &fr2.h), "vsg_frame_create");
@@ -737,9 +759,8 @@ int ORBmatcher::SearchBySim3(KeyFrameT *pKF1, KeyFrameT *pKF2, std::vector<MapPo
 template <class KeyFrameT, class MapPointT>
 int ORBmatcher::Fuse(KeyFrameT *pKF, Sophus::Sim3f &Scw, const std::vector<MapPointT *> &vpPoints, float th,
                      std::vector<MapPointT *> &vpReplacePoint) {
-    RequireSingleCameraKF(*pKF);
     Flat flat;
-    Flatten(*pKF, flat);
+    FlattenSearched(*pKF, pKF->NLeft, flat);
     FrameGuard fr;
     Check(vsg_frame_create(Workspace(), &flat.view, &fr.h), "vsg_frame_create");
     Sophus::SE3f Tcw = Sophus::SE3f(Scw.rotationMatrix(), Scw.translation() / Scw.scale());
@@ -787,10 +808,8 @@ int ORBmatcher::Fuse(KeyFrameT *pKF, Sophus::Sim3f &Scw, const std::vector<MapPo
 template <class KeyFrameT>
 int ORBmatcher::SearchForTriangulation(KeyFrameT *pKF1, KeyFrameT *pKF2, std::vector<std::pair<size_t, size_t>> &vMatchedPairs,
                                        const bool bOnlyStereo, const bool bCoarse) {
-    RequireSingleCameraKF(*pKF1);
-    RequireSingleCameraKF(*pKF2);
-    if (pKF1->mpCamera2 || pKF2->mpCamera2)
-        throw std::runtime_error("vsg ORBmatcher::SearchForTriangulation: two-camera keyframes are not supported");
+    if (pKF1->NLeft != -1 || pKF2->NLeft != -1 || pKF1->mpCamera2 || pKF2->mpCamera2)
+        return SearchForTriangulationTwoCameras(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse);
     // epipole in the second image and the fundamental matrix of Pinhole::epipolarConstrain (Pinhole.cpp:120-124),
     // built once with the reference's own Eigen expressions (it does not depend on the keypoints)
     const auto T1w = pKF1->GetPose();
@@ -834,6 +853,140 @@ int ORBmatcher::SearchForTriangulation(KeyFrameT *pKF1, KeyFrameT *pKF2, std::ve
         if (m12[i] < 0) continue;
         vMatchedPairs.push_back(std::make_pair(i, (size_t)m12[i]));
     }
+    return nmatches;
+}
+
+// ---- SearchForTriangulation on two-camera keyframes (ORBmatcher.cc:902-1146 with mpCamera2 != NULL) ----
+// The descriptor distances of every BoW-paired candidate come from the GPU (vsg_bow_pair_distances); the loop is replayed
+// here in the reference's order because its per-pair test is the caller's camera code: which of the four camera pairs
+// (left / right of either keyframe) a pair belongs to selects R12 / t12 and the two GeometricCamera objects whose
+// epipolarConstrain — KannalaBrandt8's triangulation for fisheye rigs — decides (:1033-1077).
+template <class KeyFrameT>
+int ORBmatcher::SearchForTriangulationTwoCameras(KeyFrameT *pKF1, KeyFrameT *pKF2,
+                                                 std::vector<std::pair<size_t, size_t>> &vMatchedPairs, const bool bOnlyStereo,
+                                                 const bool bCoarse) {
+    const auto T1w = pKF1->GetPose();
+    const auto T2w = pKF2->GetPose();
+    const auto Tw2 = pKF2->GetPoseInverse();
+    const auto Cw = pKF1->GetCameraCenter();
+    const auto C2 = T2w * Cw;
+    const auto ep = pKF2->mpCamera->project(C2);
+    typedef typename std::decay<decltype(T1w)>::type SE3T;
+    SE3T T12, Tll, Tlr, Trl, Trr;
+    typename std::decay<decltype(T12.rotationMatrix())>::type R12;
+    typename std::decay<decltype(T12.translation())>::type t12;
+    auto *pCamera1 = pKF1->mpCamera;
+    auto *pCamera2 = pKF2->mpCamera;
+    if (!pKF1->mpCamera2 && !pKF2->mpCamera2) {                                              // :922-928
+        T12 = T1w * Tw2;
+        R12 = T12.rotationMatrix();
+        t12 = T12.translation();
+    } else {                                                                                 // :929-937
+        const auto Tr1w = pKF1->GetRightPose();
+        const auto Twr2 = pKF2->GetRightPoseInverse();
+        Tll = T1w * Tw2;
+        Tlr = T1w * Twr2;
+        Trl = Tr1w * Tw2;
+        Trr = Tr1w * Twr2;
+    }
+    const auto Rll = Tll.rotationMatrix(), Rlr = Tlr.rotationMatrix(), Rrl = Trl.rotationMatrix(), Rrr = Trr.rotationMatrix();
+    const auto tll = Tll.translation(), tlr = Tlr.translation(), trl = Trl.translation(), trr = Trr.translation();
+
+    // all features of both cameras, in mDescriptors / mFeatVec index order
+    Flat k1, k2;
+    if (pKF1->NLeft != -1) FlattenBothCameras(*pKF1, k1); else Flatten(*pKF1, k1);
+    if (pKF2->NLeft != -1) FlattenBothCameras(*pKF2, k2); else Flatten(*pKF2, k2);
+    const int n1 = k1.view.n, n2 = k2.view.n;
+    auto stereo1 = [&](size_t i) { return !pKF1->mpCamera2 && pKF1->mvuRight[i] >= 0; };     // :977
+    auto stereo2 = [&](size_t i) { return !pKF2->mpCamera2 && pKF2->mvuRight[i] >= 0; };     // :1005
+    std::vector<uint8_t> use1(n1, 0);
+    for (int i = 0; i < n1; ++i) use1[i] = !pKF1->GetMapPoint(i) && (!bOnlyStereo || stereo1(i));   // :968-981
+    std::vector<int32_t> nd1, p1, i1v, nd2, p2, i2v;
+    FlattenFeatVec(pKF1->mFeatVec, nd1, p1, i1v);
+    FlattenFeatVec(pKF2->mFeatVec, nd2, p2, i2v);
+    std::vector<int32_t> q1(n1 + 1), cptr(n1 + 2), cand, dist;
+    int nq = 0, total = 0;
+    size_t cap = (size_t)std::max(1024, 32 * n1);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        cand.resize(cap);
+        dist.resize(cap);
+        const vsg_status st = vsg_bow_pair_distances(Workspace(), &k1.view, use1.data(), &k2.view, (int)nd1.size(), nd1.data(), p1.data(),
+                                                     i1v.data(), (int)nd2.size(), nd2.data(), p2.data(), i2v.data(), q1.data(),
+                                                     cptr.data(), n1 + 1, cand.data(), dist.data(), (int)cap, &nq, &total);
+        if (st == VSG_ERR_CAPACITY && attempt == 0) { cap = (size_t)total + 1; continue; }
+        Check(st, "vsg_bow_pair_distances");
+        break;
+    }
+    auto key_of = [](KeyFrameT *kf, size_t idx) -> const cv::KeyPoint & {                    // :982-984, :1017-1019
+        return (kf->NLeft == -1) ? kf->mvKeysUn[idx] : ((int)idx < kf->NLeft) ? kf->mvKeys[idx] : kf->mvKeysRight[idx - kf->NLeft];
+    };
+    int nmatches = 0;
+    std::vector<int> vMatches12(pKF1->N, -1);
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    for (int k = 0; k < nq; ++k) {
+        const size_t idx1 = (size_t)q1[k];
+        const bool bStereo1 = stereo1(idx1);
+        const cv::KeyPoint &kp1 = key_of(pKF1, idx1);
+        const bool bRight1 = !(pKF1->NLeft == -1 || (int)idx1 < pKF1->NLeft);
+        int bestDist = TH_LOW, bestIdx2 = -1;
+        for (int c = cptr[k]; c < cptr[k + 1]; ++c) {
+            const size_t idx2 = (size_t)cand[c];
+            if (pKF2->GetMapPoint(idx2)) continue;                                           // :1001 (vbMatched2 is never set)
+            const bool bStereo2 = stereo2(idx2);
+            if (bOnlyStereo && !bStereo2) continue;
+            const int d = dist[c];
+            if (d > TH_LOW || d > bestDist) continue;                                        // :1014
+            const cv::KeyPoint &kp2 = key_of(pKF2, idx2);
+            const bool bRight2 = !(pKF2->NLeft == -1 || (int)idx2 < pKF2->NLeft);
+            if (!bStereo1 && !bStereo2 && !pKF1->mpCamera2) {                                // :1023-1031
+                const float distex = ep(0) - kp2.pt.x;
+                const float distey = ep(1) - kp2.pt.y;
+                if (distex * distex + distey * distey < 100 * pKF2->mvScaleFactors[kp2.octave]) continue;
+            }
+            if (pKF1->mpCamera2 && pKF2->mpCamera2) {                                        // :1033-1070
+                if (bRight1 && bRight2) { R12 = Rrr; t12 = trr; T12 = Trr; pCamera1 = pKF1->mpCamera2; pCamera2 = pKF2->mpCamera2; }
+                else if (bRight1 && !bRight2) { R12 = Rrl; t12 = trl; T12 = Trl; pCamera1 = pKF1->mpCamera2; pCamera2 = pKF2->mpCamera; }
+                else if (!bRight1 && bRight2) { R12 = Rlr; t12 = tlr; T12 = Tlr; pCamera1 = pKF1->mpCamera; pCamera2 = pKF2->mpCamera2; }
+                else { R12 = Rll; t12 = tll; T12 = Tll; pCamera1 = pKF1->mpCamera; pCamera2 = pKF2->mpCamera; }
+            }
+            if (bCoarse || pCamera1->epipolarConstrain(pCamera2, kp1, kp2, R12, t12, pKF1->mvLevelSigma2[kp1.octave],
+                                                       pKF2->mvLevelSigma2[kp2.octave])) {
+                bestIdx2 = (int)idx2;
+                bestDist = d;
+            }
+        }
+        if (bestIdx2 >= 0) {                                                                 // :1080-1100
+            const cv::KeyPoint &kp2 = key_of(pKF2, (size_t)bestIdx2);
+            vMatches12[idx1] = bestIdx2;
+            nmatches++;
+            if (mbCheckOrientation) {
+                float rot = kp1.angle - kp2.angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = round(rot * factor);
+                if (bin == HISTO_LENGTH) bin = 0;
+                rotHist[bin].push_back((int)idx1);
+            }
+        }
+    }
+    if (mbCheckOrientation) {                                                                // :1120-1137
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0, jend = rotHist[i].size(); j < jend; j++) {
+                vMatches12[rotHist[i][j]] = -1;
+                nmatches--;
+            }
+        }
+    }
+    vMatchedPairs.clear();
+    vMatchedPairs.reserve(nmatches);
+    for (size_t i = 0, iend = vMatches12.size(); i < iend; i++) {
+        if (vMatches12[i] < 0) continue;
+        vMatchedPairs.push_back(std::make_pair(i, (size_t)vMatches12[i]));
+    }
+    (void)n2;
     return nmatches;
 }
 
