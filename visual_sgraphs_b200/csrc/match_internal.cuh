@@ -49,6 +49,10 @@ struct AreaQuery {          // one GetFeaturesInArea call + the per-candidate st
 
 // Candidate lists as the kernel left them: query q's (idx, dist) pairs are raw[off[q] .. off[q] + cnt[q]) (segments in
 // arbitrary order).  The arrays live in the matcher's pinned staging and stay valid until its next search.
+struct Chi2Gate {            // inverse level variances for the reprojection gates of the pose-based Fuse (:1273-1299)
+    float inv_sigma2[kMaxLevels];
+};
+
 struct AreaLists {
     const int2 *raw = nullptr;
     const int *off = nullptr, *cnt = nullptr;
@@ -60,6 +64,10 @@ struct AreaLists {
 vsg_status area_search(vsg_matcher *m, const vsg_frame *f, int nq, const AreaQuery *qs, const uint8_t *qdesc,
                        std::vector<int> &ptr, std::vector<int2> &ent);
 // the same without the re-pack into query order; n_qdesc rows of qdesc are uploaded (queries pick theirs by desc_idx)
+// Best candidate per query on the device (window / level gates, optional chi-square gates when inv_sigma2 != nullptr): the
+// whole search of the methods whose queries are independent of one another.  out[k] = (index or -1, distance or INT_MAX).
+vsg_status area_best(vsg_matcher *m, const vsg_frame *f, int nq, const AreaQuery *qs, const uint8_t *qdesc, const float *inv_sigma2,
+                     std::vector<int2> &out);
 vsg_status area_search_raw(vsg_matcher *m, const vsg_frame *f, int nq, const AreaQuery *qs, const uint8_t *qdesc,
                            int n_qdesc, AreaLists *out);
 // ORBmatcher::ComputeThreeMaxima (ORBmatcher.cc:2002-2043)

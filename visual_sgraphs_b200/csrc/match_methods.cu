@@ -133,6 +133,108 @@ struct PhaseTimer {
     }
 };
 
+// The same walk, but instead of listing the candidates it keeps each query's BEST one on the device: the smallest Hamming
+// distance among the keypoints that pass the window / level gates (and, for the pose-based Fuse, the chi-square reprojection
+// gates of ORBmatcher.cc:1273-1299), first candidate in the reference's scan order on ties (its updates are strict '<').
+// For the methods whose queries do not depend on one another — the Fuse searches and SearchBySim3 — this is the whole
+// search: one launch, one (index, distance) pair per query back to the host.
+template <bool kChi2>
+__global__ void __launch_bounds__(256) window_best_kernel(FrameDev f, int nq, const AreaQuery *__restrict__ qs,
+                                                          const uint4 *__restrict__ qdesc, Chi2Gate gate,
+                                                          int2 *__restrict__ best_out) {
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const AreaQuery a = qs[q];
+    const int min_cx = max(0, (int)floorf((a.x - f.min_x - a.r) * f.inv_w));
+    const int max_cx = min(f.cols - 1, (int)ceilf((a.x - f.min_x + a.r) * f.inv_w));
+    const int min_cy = max(0, (int)floorf((a.y - f.min_y - a.r) * f.inv_h));
+    const int max_cy = min(f.rows - 1, (int)ceilf((a.y - f.min_y + a.r) * f.inv_h));
+    const bool ok = !(min_cx >= f.cols || max_cx < 0 || min_cy >= f.rows || max_cy < 0) && a.r == a.r;
+    int best = INT_MAX, best_idx = -1;
+    if (ok) {
+        const bool check_levels = (a.min_level > 0) || (a.max_level >= 0);
+        const int di = a.desc_idx >= 0 ? a.desc_idx : q;
+        const uint4 qa = __ldg(qdesc + 2 * di), qb = __ldg(qdesc + 2 * di + 1);
+        const int ncy = max_cy - min_cy + 1, ncell = (max_cx - min_cx + 1) * ncy;
+        for (int base = 0; base < ncell; base += 32) {            // cells in the reference's walk order, 32 per round
+            const int k = base + lane;
+            int jb = 0, je = 0;
+            if (k < ncell) {
+                const int ix = min_cx + k / ncy, iy = min_cy + k % ncy;
+                const int c = ix * f.rows + iy;
+                jb = f.cell_ptr[c];
+                je = f.cell_ptr[c + 1];
+            }
+            int mine = INT_MAX, mine_idx = -1;
+            for (int j = jb; j < je; ++j) {
+                const int idx = f.cell_idx[j];
+                const int o = f.octave[idx];
+                if (check_levels) {
+                    if (o < a.min_level) continue;
+                    if (a.max_level >= 0 && o > a.max_level) continue;
+                }
+                const float2 p = f.xy[idx];
+                if (!(fabsf(p.x - a.x) < a.r && fabsf(p.y - a.y) < a.r)) continue;
+                if (kChi2) {                                      // :1273-1299 (a.xr carries the projected right coordinate)
+                    const float ex = a.x - p.x, ey = a.y - p.y;
+                    const float ur = f.u_right ? f.u_right[idx] : -1.f;
+                    if (ur >= 0) {
+                        const float er = a.xr - ur;
+                        const float e2 = ex * ex + ey * ey + er * er;
+                        if ((double)(e2 * gate.inv_sigma2[o]) > 7.8) continue;
+                    } else {
+                        const float e2 = ex * ex + ey * ey;
+                        if ((double)(e2 * gate.inv_sigma2[o]) > 5.99) continue;
+                    }
+                }
+                const int d = hamming256(qa, qb, __ldg(f.desc + 2 * idx), __ldg(f.desc + 2 * idx + 1));
+                if (d < mine) { mine = d; mine_idx = idx; }
+            }
+            // the round's winner: smallest distance, lowest lane (= earliest cell) on ties
+            unsigned key = mine == INT_MAX ? 0xFFFFFFFFu : ((unsigned)mine << 5) | (unsigned)lane;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, d));
+            if (key != 0xFFFFFFFFu) {
+                const int rd = (int)(key >> 5), rl = (int)(key & 31);
+                const int ridx = __shfl_sync(0xffffffffu, mine_idx, rl);
+                if (rd < best) { best = rd; best_idx = ridx; }    // strict: an earlier round keeps a tie
+            }
+        }
+    }
+    if (lane == 0) best_out[q] = make_int2(best_idx, best);
+}
+
+// Best candidate of every query (see window_best_kernel); out[k] = (keypoint index or -1, distance or INT_MAX), host memory.
+vsg_status area_best(vsg_matcher *m, const vsg_frame *f, int nq, const AreaQuery *qs, const uint8_t *qdesc, const float *inv_sigma2,
+                     std::vector<int2> &out) {
+    out.assign(nq, make_int2(-1, INT_MAX));
+    if (nq == 0) return VSG_OK;
+    cudaStream_t s = m->stream;
+    vsg_status st;
+    // device slots: 7 queries, 8 qdesc, 9 results; pinned host slot 0
+    if ((st = matcher_ensure(m, 7, (size_t)nq * sizeof(AreaQuery))) || (st = matcher_ensure(m, 8, (size_t)nq * 32)) ||
+        (st = matcher_ensure(m, 9, (size_t)nq * sizeof(int2))) || (st = matcher_ensure_host(m, 0, (size_t)nq * sizeof(int2))))
+        return st;
+    CK(cudaMemcpyAsync(m->buf[7], qs, (size_t)nq * sizeof(AreaQuery), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(m->buf[8], qdesc, (size_t)nq * 32, cudaMemcpyHostToDevice, s));
+    FrameDev fd{f->n, f->cols, f->rows, f->min_x, f->min_y, f->inv_w, f->inv_h, f->xy, f->octave,
+                f->has_right ? f->u_right : nullptr, (const uint4 *)f->desc, f->cell_ptr, f->cell_idx};
+    Chi2Gate gate;
+    for (int l = 0; l < kMaxLevels; ++l) gate.inv_sigma2[l] = inv_sigma2 && l < f->n_levels ? inv_sigma2[l] : 0.f;
+    if (inv_sigma2)
+        window_best_kernel<true><<<(nq + 7) / 8, 256, 0, s>>>(fd, nq, (const AreaQuery *)m->buf[7], (const uint4 *)m->buf[8], gate,
+                                                              (int2 *)m->buf[9]);
+    else
+        window_best_kernel<false><<<(nq + 7) / 8, 256, 0, s>>>(fd, nq, (const AreaQuery *)m->buf[7], (const uint4 *)m->buf[8], gate,
+                                                               (int2 *)m->buf[9]);
+    count_launch();
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(m->hbuf[0], m->buf[9], (size_t)nq * sizeof(int2), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    memcpy(out.data(), m->hbuf[0], (size_t)nq * sizeof(int2));
+    return VSG_OK;
+}
+
 vsg_status area_search_raw(vsg_matcher *m, const vsg_frame *f, int nq, const AreaQuery *qs, const uint8_t *qdesc,
                            int n_qdesc, AreaLists *out) {
     PhaseTimer pt("area_search");

@@ -205,36 +205,22 @@ vsg_status vsg_fuse_search(vsg_matcher *m, const vsg_frame *KF, int n, const vsg
         return VSG_ERR_INVALID;
     CK(cudaSetDevice(m->device));
     std::vector<AreaQuery> qs;
-    std::vector<int> q_src, ptr;
+    std::vector<int> q_src;
     std::vector<uint8_t> qdesc;
-    std::vector<int2> ent;
     vsg_status st = build_queries(KF, n, pts, desc, th, -1, 0, qs, q_src, qdesc);     // :1246, :1270-1271
     if (st != VSG_OK) return st;
-    if ((st = area_search(m, KF, (int)qs.size(), qs.data(), qdesc.data(), ptr, ent)) != VSG_OK) return st;
+    if (variant == 0)
+        for (size_t k = 0; k < qs.size(); ++k) qs[k].xr = pts[q_src[k]].ur;         // the right coordinate of the chi-square gate
+    // every map point's search is independent of the others: the best candidate (with the chi-square gates of :1273-1299 for
+    // the pose-based variant) is picked on the device, one (index, distance) pair per point comes back
+    std::vector<int2> best;
+    if ((st = area_best(m, KF, (int)qs.size(), qs.data(), qdesc.data(), variant == 0 ? inv_level_sigma2 : nullptr, best)) != VSG_OK)
+        return st;
     for (int i = 0; i < n; ++i) best_idx_out[i] = -1;
     int nfused = 0;
-    const bool has_right = !KF->u_right_h.empty();
     for (size_t k = 0; k < qs.size(); ++k) {
-        const vsg_search_point &p = pts[q_src[k]];
-        int best = variant == 0 ? 256 : INT_MAX, best_idx = -1;
-        for (int c = ptr[k]; c < ptr[k + 1]; ++c) {
-            const int idx = ent[c].x, dist = ent[c].y;
-            if (variant == 0) {                                                      // :1273-1299
-                const vsg_keypoint &kp = KF->keys[idx];
-                const float ex = p.u - kp.x, ey = p.v - kp.y;
-                if (has_right && KF->u_right_h[idx] >= 0) {
-                    const float er = p.ur - KF->u_right_h[idx];
-                    const float e2 = ex * ex + ey * ey + er * er;
-                    if (e2 * inv_level_sigma2[kp.octave] > 7.8) continue;
-                } else {
-                    const float e2 = ex * ex + ey * ey;
-                    if (e2 * inv_level_sigma2[kp.octave] > 5.99) continue;
-                }
-            }
-            if (dist < best) { best = dist; best_idx = idx; }
-        }
-        if (best <= TH_LOW && best_idx >= 0) {                                       // :1316, :1428
-            best_idx_out[q_src[k]] = best_idx;
+        if (best[k].x >= 0 && best[k].y <= TH_LOW) {                                 // :1316, :1428
+            best_idx_out[q_src[k]] = best[k].x;
             ++nfused;
         }
     }
@@ -261,18 +247,14 @@ vsg_status vsg_search_by_sim3(vsg_matcher *m, const vsg_frame *KF1, const vsg_fr
         const int n = dir == 0 ? n1 : n2;
         std::vector<int> &out = dir == 0 ? match1 : match2;
         std::vector<AreaQuery> qs;
-        std::vector<int> q_src, ptr;
+        std::vector<int> q_src;
         std::vector<uint8_t> qdesc;
-        std::vector<int2> ent;
         vsg_status st = build_queries(target, n, dir == 0 ? pts1 : pts2, dir == 0 ? desc1 : desc2, th, -1, 0, qs, q_src, qdesc);
         if (st != VSG_OK) return st;
-        if ((st = area_search(m, target, (int)qs.size(), qs.data(), qdesc.data(), ptr, ent)) != VSG_OK) return st;
-        for (size_t k = 0; k < qs.size(); ++k) {
-            int best = INT_MAX, best_idx = -1;
-            for (int c = ptr[k]; c < ptr[k + 1]; ++c)
-                if (ent[c].y < best) { best = ent[c].y; best_idx = ent[c].x; }
-            if (best <= TH_HIGH) out[q_src[k]] = best_idx;                           // :1556, :1631
-        }
+        std::vector<int2> best;                                                      // independent queries: best on the device
+        if ((st = area_best(m, target, (int)qs.size(), qs.data(), qdesc.data(), nullptr, best)) != VSG_OK) return st;
+        for (size_t k = 0; k < qs.size(); ++k)
+            if (best[k].x >= 0 && best[k].y <= TH_HIGH) out[q_src[k]] = best[k].x;   // :1556, :1631
     }
     int nfound = 0;
     for (int i1 = 0; i1 < n1; ++i1) {                                                // :1638-1652

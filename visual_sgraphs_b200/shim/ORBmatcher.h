@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <set>
 #include <tuple>
@@ -45,10 +46,10 @@ namespace VS_GRAPHS {
 
 class ORBmatcher {
 public:
+    // Stateless like the reference's class (two members, ORBmatcher.h:97-98): copyable, cheap to construct on the stack per call
+    // as Tracking / LocalMapping / LoopClosing do.  The CUDA stream and scratch buffers live in one workspace per calling
+    // thread (below), not in the object.
     ORBmatcher(float nnratio = 0.6, bool checkOri = true) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
-    ~ORBmatcher() { vsg_matcher_destroy(mpWorkspace); }
-    ORBmatcher(const ORBmatcher &) = delete;
-    ORBmatcher &operator=(const ORBmatcher &) = delete;
 
     // Computes the Hamming distance between two ORB descriptors (ORBmatcher.cc:2047-2063).  Stays a cheap host
     // function: it is also called one pair at a time from MapPoint.cc:391 and Frame.cc:1032.
@@ -145,15 +146,23 @@ protected:
     }
 
     // ---- plumbing ----
-    vsg_matcher *mpWorkspace = nullptr;
-    int mnDevice = 0;
-
     static void Check(vsg_status st, const char *what) {
         if (st != VSG_OK) throw std::runtime_error(std::string(what) + ": " + vsg_last_error());
     }
-    vsg_matcher *Workspace() {
-        if (!mpWorkspace) Check(vsg_matcher_create(mnDevice, &mpWorkspace), "vsg_matcher_create");
-        return mpWorkspace;
+    // One vsg_matcher (stream + device / pinned scratch) per calling thread, created on first use and kept for the thread's
+    // lifetime: the SLAM threads construct a fresh ORBmatcher for nearly every call, and a stream plus buffers per object would
+    // cost more than the search.  Device: VSG_DEVICE (default 0).
+    static vsg_matcher *Workspace() {
+        struct Holder {
+            vsg_matcher *m = nullptr;
+            ~Holder() { vsg_matcher_destroy(m); }
+        };
+        static thread_local Holder h;
+        if (!h.m) {
+            const char *e = std::getenv("VSG_DEVICE");
+            Check(vsg_matcher_create(e ? std::atoi(e) : 0, &h.m), "vsg_matcher_create");
+        }
+        return h.m;
     }
 
     // Flatten what the Search* methods read from a Frame / KeyFrame.
