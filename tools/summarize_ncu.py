@@ -67,3 +67,28 @@ if os.path.exists(rep):
         for r in rows[2:]:
             wr.writerow([r[i].split("(")[0] if w == "Kernel Name" else r[i] for w, i in idx])
     print("wrote kernel metrics,", len(rows) - 2, "kernels")
+
+    # DRAM traffic per launch of every captured kernel (dram__bytes_read.sum + dram__bytes_write.sum of its largest launch):
+    # bench.py's roofline.traffic reads this file; the commit it was measured on is stamped into it.
+    import json
+    try:
+        head = subprocess.run(["git", "-C", root, "rev-parse", "--short=12", "HEAD"], capture_output=True, text=True).stdout.strip()
+    except Exception:  # noqa: BLE001
+        head = "unknown"
+    col = {w: hdr.index(w) for w in ("Kernel Name", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum") if w in hdr}
+    unit_scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    traffic = {"source": "ncu --set full --clock-control none (tools/gpu_round.sh %s): dram__bytes_read.sum + dram__bytes_write.sum of the "
+                         "kernel's longest captured launch" % tag,
+               "head": head, "frames_per_launch": int(os.environ.get("VSG_PROFILE_BATCH", "512"))}
+    best = {}
+    for r in rows[2:]:
+        name = r[col["Kernel Name"]].split("(")[0].split("<")[0].replace("void ", "").replace("vsg::", "")
+        rd = float(r[col["dram__bytes_read.sum"]]) * unit_scale.get(units[col["dram__bytes_read.sum"]], 1.0)
+        wr_ = float(r[col["dram__bytes_write.sum"]]) * unit_scale.get(units[col["dram__bytes_write.sum"]], 1.0)
+        dur = float(r[col["gpu__time_duration.sum"]])
+        if name not in best or dur > best[name][0]:
+            best[name] = (dur, rd + wr_)
+    for name, (dur, b) in best.items():
+        traffic[name] = {"dram_bytes_per_launch": int(b)}
+    json.dump(traffic, open(os.path.join(out_dir, "ncu_traffic.json"), "w"), indent=1)
+    print("wrote ncu_traffic.json for", sorted(best))
