@@ -339,3 +339,33 @@ def test_persistent_tma_fast_kernel_matches_the_default_grid(monkeypatch):
     want2 = ORBextractor(1200, 1.2, 8, 20, 7, max_batch=20).extract_batch(frames2)
     for a, b in zip(got2, want2):
         assert a[0] == b[0] and a[1].tobytes() == b[1].tobytes() and np.array_equal(a[2], b[2])
+
+
+@pytest.mark.parametrize("wh", [(640, 480), (752, 480), (1241, 376), (200, 150)])
+def test_tensor_core_blur_is_bit_identical(monkeypatch, wh):
+    """VSG_BLUR_TC=1: the 7x7 Gaussian blur (ORBextractor.cc:1129-1130) runs as banded u8 GEMMs on tcgen05 (csrc/blur_tc.cu).
+    Every blurred plane and every output must equal the CUDA-core blur's, borders (REFLECT_101) included."""
+    from visual_sgraphs_b200.extractor import ORBextractor
+    w, h = wh
+    nf = 6
+    frames = np.stack([synth_frame(500 + i, w, h) for i in range(nf)])
+    frames[1, :, :4] = 255          # strong content on the borders
+    frames[1, :, -4:] = 7
+    frames[2, :4] = 200
+    frames[2, -4:] = 31
+    monkeypatch.setenv("VSG_BLUR_TC", "0")
+    ex0 = ORBextractor(1000, 1.2, 8, 20, 7, max_batch=nf)
+    want = ex0.extract_batch(frames)
+    planes0 = [[ex0.blurred_level(l, f) for l in range(8)] for f in range(nf)]
+    monkeypatch.setenv("VSG_BLUR_TC", "1")
+    ex1 = ORBextractor(1000, 1.2, 8, 20, 7, max_batch=nf)
+    got = ex1.extract_batch(frames)
+    for f in range(nf):
+        for l in range(8):
+            p1 = ex1.blurred_level(l, f)
+            if not np.array_equal(p1, planes0[f][l]):
+                bad = np.argwhere(p1 != planes0[f][l])
+                raise AssertionError("frame %d level %d: %d pixels differ, first %s (%d vs %d)" % (
+                    f, l, len(bad), bad[0], p1[tuple(bad[0])], planes0[f][l][tuple(bad[0])]))
+    for a, b in zip(got, want):
+        assert a[0] == b[0] and a[1].tobytes() == b[1].tobytes() and np.array_equal(a[2], b[2])
