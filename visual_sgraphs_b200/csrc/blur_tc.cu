@@ -1,25 +1,26 @@
-// blur_tc.cu — the 7x7 Gaussian blur of every pyramid level as two banded int8 GEMMs on the tensor cores.
+// blur_tc.cu — the 7x7 Gaussian blur of every pyramid level as two banded u8 GEMMs on the tensor cores.
 //
 // Reference (snt-arg/visual_sgraphs): GaussianBlur(workingMat, workingMat, Size(7, 7), 2, 2, BORDER_REFLECT_101) on a clone of
 // every level, orb_slam3/src/ORBextractor.cc:1129-1130.  OpenCV's 8-bit path is exactly linear:
 //   h = sum_k taps[k] * src(x + k - 3)   (<= 65280),   v = sum_j taps[j] * h(y + j - 3),   out = (v + 32768) >> 16,
 // taps = {18, 34, 48, 56, 48, 34, 18}.  A linear stencil is a product with a banded (Toeplitz) matrix, and u8 x u8 -> s32 is
-// exact on tcgen05.mma.kind::i8, so per tile of 122 output rows x 96 output columns:
-//   GEMM 1 (horizontal):  H[128 rows][96] = In[128 rows][128 cols] * Bh^T,  Bh[n][k] = taps[k - 13 - n]
-//   GEMM 2 (vertical)  :  V[128][96]      = Bv[128][128] * H,               Bv[r][k] = taps[k - r]
-// H has 16-bit entries, so it is split into its high and low bytes (two u8 operands, two accumulators, v = (Vh << 8) + Vl).
-// The stencil's 98 multiply-adds per pixel become a few hundred on the tensor pipe — 90 % of them with zero taps — and
-// still cost a fraction of what the CUDA cores need, because they leave the issue slots and the ALU pipe to the FAST kernel.
+// exact on tcgen05.mma.kind::i8, so per tile of 122 output rows x 96 output columns, with W the 128 x 128-byte source window
+// (3 rows above the tile, 16 columns left of it so that the TMA box starts on a 16-byte boundary):
+//   GEMM 1 (horizontal, transposed):  Ht[n][i] = sum_k Bh[n][k] * W[i][k],   Bh[n][k] = taps[k - 13 - n]     M128 N128 K128
+//   GEMM 2 (vertical):                V[r][n]  = sum_k Bv[r][k] * Ht[n][k],  Bv[r][k] = taps[k - r]          M128 N96  K128
+// Ht has 16-bit entries, so it is split into its high and low bytes (two u8 operands, two accumulators, v = 256 Vh + Vl).
+// GEMM 1 is computed transposed so that one thread reads one row of Ht from tensor memory and writes it as one contiguous
+// (swizzled) 128-byte row of GEMM 2's K-major operand.  Nine in ten multiplications are by a zero tap; they still cost a
+// fraction of the issue slots the CUDA-core stencil needs, which is what the FAST kernel is short of.
 //
-// One persistent warp-specialised CTA per SM:
-//   warp 0      TMA: the tile's 128 x 128-byte source window (cp.async.bulk.tensor.3d, SWIZZLE_128B, starts 16 bytes left of
-//               the tile so that the box is 16-byte aligned, 3 rows above it), two stages
-//   warps 2-5   (a) REFLECT_101: tiles that touch the plane's border get the three out-of-plane columns / rows patched in
-//               shared memory from their mirror images (TMA fills out-of-bounds bytes with zeros);
-//               (b) after GEMM 1: tcgen05.ld of H, split into bytes, written as the K-major operand of GEMM 2
-//   warp 1      one lane issues GEMM 1 (4 x M128 N96 K32) and GEMM 2 (2 x 4), tcgen05.commit
-//   warps 6-9   tcgen05.ld of Vh / Vl, rounding, 16-byte stores of the blurred rows
-// Results are bit-identical to blur_block_body (blur_device.cuh), which stays for small batches and unaligned inputs.
+// One persistent warp-specialised CTA per SM (448 threads):
+//   warp 0       TMA: source windows (cp.async.bulk.tensor.3d, SWIZZLE_128B, out-of-plane bytes zero-filled), 3 stages
+//   warp 1       one lane issues GEMM 1 of tile t+1, then GEMM 2 of tile t (tcgen05.mma, tcgen05.commit -> mbarriers)
+//   warps 2-5    (a) REFLECT_101: windows that touch the plane's border get the three out-of-plane columns / rows patched in
+//                shared memory from their mirror images; (b) tcgen05.ld of Ht, byte split, operand rows of GEMM 2 (2 buffers)
+//   warps 6-13   tcgen05.ld of Vh / Vl, rounding, 16-byte stores of the blurred rows
+// Tensor memory: Ht x 2 buffers (256 columns), Vh, Vl (96 each).  Results are bit-identical to blur_block_body
+// (blur_device.cuh), which stays for small batches and planes TMA cannot address.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -34,10 +35,14 @@ namespace vsg {
 
 constexpr int kBtW = 96, kBtH = 122;            // output tile
 constexpr int kBtXoff = 16;                     // the source box starts this many columns left of the tile (16-byte alignment)
-constexpr int kBtThreads = 32 * 10;
-constexpr int kBtTileA = 128 * 128;             // source window / Bv: 128 rows of 128 bytes
-constexpr int kBtTileB = kBtW * 128;            // Bh / H operands: 96 rows of 128 bytes
-constexpr int kBtSmem = 2 * kBtTileA + kBtTileB + kBtTileA + 2 * kBtTileB + 256 + 1024;
+constexpr int kBtStages = 4;
+constexpr int kBtThreads = 32 * 18;
+// warps 0-2 / 4-6: Ht epilogue of the even / odd tiles (TMEM lane quarters 0-2; quarter 3 of Ht is padding, so the two warps
+// that could only read it, 3 and 7, do other work); warps 8-15: V epilogue; 16, 17: patch, GEMM 2 issue
+constexpr int kWarpTma = 3, kWarpMma1 = 7, kWarpPatch = 16, kWarpMma2 = 17;
+constexpr int kBtTileA = 128 * 128;             // source window / Bh / Bv: 128 rows of 128 bytes
+constexpr int kBtTileB = kBtW * 128;            // byte planes of Ht: 96 rows of 128 bytes
+constexpr int kBtSmem = kBtStages * kBtTileA + 4 * kBtTileB + 256 + 1024;
 
 struct BlurTcParams {
     CUtensorMap map[8];       // per level: (x bytes, y rows, frame), box 128 x 128 x 1, SWIZZLE_128B
@@ -46,6 +51,7 @@ struct BlurTcParams {
     int ntx[8], w[8], h[8], dst_pitch[8];
     int64_t dst_offset[8], dst_stride[8];
     int tiles_per_frame;
+    uint32_t tpf_rcp, ntx_rcp[8];   // ceil(2^32 / d): x / d == umulhi(x, rcp) for x * d < 2^32; 0 stands for d == 1
 };
 
 // byte (row, col) of a 128-byte-row tile in the SWIZZLE_128B layout (tile base 1024-byte aligned)
@@ -56,230 +62,358 @@ struct BtTile {
 };
 __device__ __forceinline__ BtTile bt_tile(const BlurTcParams &p, int t) {
     BtTile r;
-    r.frame = t / p.tiles_per_frame;
+    r.frame = p.tpf_rcp ? (int)__umulhi((uint32_t)t, p.tpf_rcp) : t;
     const int rem = t - r.frame * p.tiles_per_frame;
     int level = 0;
 #pragma unroll
     for (int l = 1; l < 8; ++l) level += (l < p.nlevels && rem >= p.tile_begin[l]) ? 1 : 0;
     r.level = level;
     const int local = rem - p.tile_begin[level];
-    const int ty = local / p.ntx[level], tx = local - ty * p.ntx[level];
+    const uint32_t nr = p.ntx_rcp[level];
+    const int ty = nr ? (int)__umulhi((uint32_t)local, nr) : local, tx = local - ty * p.ntx[level];
     r.x0 = tx * kBtW;
     r.y0 = ty * kBtH;
     return r;
 }
 
-__device__ __forceinline__ void bar_sync_128(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// tcgen05.ld .pack::16b: register j = low 16 bits of column 2j | low 16 bits of column 2j + 1 << 16.  Every accumulator of
+// this kernel is below 2^16, and tensor-memory reads are the kernel's bound (64 B / clk / SM), so half the registers per
+// column is half the time.
+#define R4(v, o) "=r"(v[o]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3])
+__device__ __forceinline__ void tc_ld_pack8(uint32_t taddr, uint32_t (&v)[8]) {        // 16 columns
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : R4(v, 0), R4(v, 4) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_ld_pack16(uint32_t taddr, uint32_t (&v)[16]) {      // 32 columns
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : R4(v, 0), R4(v, 4), R4(v, 8), R4(v, 12) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_ld_pack32(uint32_t taddr, uint32_t (&v)[32]) {      // 64 columns
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+        "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : R4(v, 0), R4(v, 4), R4(v, 8), R4(v, 12), R4(v, 16), R4(v, 20), R4(v, 24), R4(v, 28) : "r"(taddr) : "memory");
+}
+#undef R4
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+        "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
+        "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),
+        "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T, u8 x u8 -> s32, M128 x N x K32; A: lane = row, 8 columns = the 32 K bytes
+__device__ __forceinline__ void tc_mma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 
-// u8 x u8 -> s32, both operands K-major, M = 128, N = 96
-constexpr uint32_t kBtIdesc = (2u << 4) | ((uint32_t)(kBtW >> 3) << 17) | ((128u >> 4) << 24);
+// u8 x u8 -> s32, both operands K-major, M = 128
+__host__ __device__ constexpr uint32_t bt_idesc(int n) { return (2u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
+
+// ring position of the k-th use of an n-deep ring: slot and the parity its `full` barrier completes with
+struct Ring {
+    int slot = 0;
+    uint32_t phase = 0;
+    __device__ __forceinline__ void next(int n) { if (++slot == n) { slot = 0; phase ^= 1u; } }
+};
+
+// -DBT_TRACE: CTA 0 records clock64() at the hand-offs of its first 64 tiles (tools/micro/bt_trace.py prints the timeline)
+#ifdef BT_TRACE
+__device__ long long g_bt_trace[6][64][4];
+#define TR(role, it, ev) do { if (blockIdx.x == 0 && lane == 0 && (it) < 64) g_bt_trace[role][it][ev] = clock64(); } while (0)
+#else
+#define TR(role, it, ev) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(kBtThreads, 1) blur_tc_kernel(const __grid_constant__ BlurTcParams p, uint8_t *__restrict__ blur,
                                                                 int total_tiles) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t *a1 = smem;                               // 2 stages of the source window
-    uint8_t *bh = a1 + 2 * kBtTileA;                  // Bh[n][k]
-    uint8_t *bv = bh + kBtTileB;                      // Bv[r][k]
-    uint8_t *b2h = bv + kBtTileA, *b2l = b2h + kBtTileB;   // H high / low bytes as [n][k]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(b2l + kBtTileB);
-    uint64_t *in_full = bars, *in_empty = bars + 2, *a_ready = bars + 4;
-    uint64_t *d1_full = bars + 6, *d1_empty = bars + 7, *b2_full = bars + 8, *b2_empty = bars + 9, *d2_full = bars + 10,
-             *d2_empty = bars + 11;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 12);
+    uint8_t *a1 = smem;                                   // kBtStages source windows
+    uint8_t *b2 = a1 + kBtStages * kBtTileA;              // 2 buffers x {high, low} byte plane of Ht as [n][k]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(b2 + 4 * kBtTileB);
+    uint64_t *in_full = bars, *in_empty = bars + kBtStages, *a_ready = bars + 2 * kBtStages;
+    uint64_t *d1_full = bars + 3 * kBtStages, *d1_empty = d1_full + 2, *b2_full = d1_full + 4, *b2_empty = d1_full + 6;
+    uint64_t *d2_full = d1_full + 8, *d2_empty = d1_full + 9;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d1_full + 10);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // the two constant band matrices
-    for (int i = threadIdx.x; i < (kBtTileB + kBtTileA) / 16; i += kBtThreads) reinterpret_cast<uint4 *>(bh)[i] = make_uint4(0, 0, 0, 0);
-    __syncthreads();
-    {
-        const uint64_t taps = 0x12223038302212ull;          // {18, 34, 48, 56, 48, 34, 18}, one byte each
-        for (int i = threadIdx.x; i < kBtW * 7; i += kBtThreads) {
-            const int n = i / 7, j = i - n * 7;
-            bh[swz(n, kBtXoff - 3 + n + j)] = (uint8_t)(taps >> (8 * j));
-        }
-        for (int i = threadIdx.x; i < kBtH * 7; i += kBtThreads) {
-            const int r = i / 7, j = i - r * 7;
-            bv[swz(r, r + j)] = (uint8_t)(taps >> (8 * j));
-        }
-    }
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], 1); mbar_init(&a_ready[i], 4); }
-        mbar_init(d1_full, 1); mbar_init(d1_empty, 4);
-        mbar_init(b2_full, 4); mbar_init(b2_empty, 1);
-        mbar_init(d2_full, 1); mbar_init(d2_empty, 4);
+        for (int i = 0; i < kBtStages; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], 1); mbar_init(&a_ready[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], 3); mbar_init(&b2_full[i], 3); mbar_init(&b2_empty[i], 1); }
+        mbar_init(d2_full, 1);
+        mbar_init(d2_empty, 8);
         mbar_init_fence();
     }
-    if (warp == 1) {
+    if (warp == kWarpMma1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    fence_async_smem();                               // the band matrices were written by ordinary stores
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tD1 = tmem, tD2h = tmem + 128, tD2l = tmem + 256;
+    // tensor-memory columns: Ht buffers at 0 and 128, Vh, Vl, then the two constant band matrices as A operands
+    const uint32_t tD2h = tmem + 256, tD2l = tmem + 256 + kBtW, tBh = tmem + 448, tBv = tmem + 480;
+    if (warp < 4) {
+        // A operands live in tensor memory (they never change, and operand reads are what saturates shared memory): lane m holds
+        // row m of the M x K matrix, column j its bytes k = 4j .. 4j + 3.  Bh[n][k] = taps[k - 13 - n] (n < 96), Bv[r][k] = taps[k - r] (r < 122)
+        const uint64_t taps = 0x12223038302212ull;          // {18, 34, 48, 56, 48, 34, 18}, one byte each
+        const int m = warp * 32 + lane;
+        uint32_t ah[32], av[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            uint32_t wh = 0, wv = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int k = 4 * j + b, th = k - (kBtXoff - 3) - m, tv = k - m;
+                if (m < kBtW && th >= 0 && th < 7) wh |= (uint32_t)((taps >> (8 * th)) & 255) << (8 * b);
+                if (m < kBtH && tv >= 0 && tv < 7) wv |= (uint32_t)((taps >> (8 * tv)) & 255) << (8 * b);
+            }
+            ah[j] = wh;
+            av[j] = wv;
+        }
+        tc_st32(tBh + ((uint32_t)(warp * 32) << 16), ah);
+        tc_st32(tBv + ((uint32_t)(warp * 32) << 16), av);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
 
-    if (warp == 0) {
+    if (warp == kWarpTma) {
         // ===== TMA producer =====
         if (lane == 0) {
-            uint32_t it = 0;
+            Ring ld;
+            int it = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-                const int stage = it & 1;
+                TR(0, it, 0);
                 const BtTile tl = bt_tile(p, t);
-                mbar_wait(&in_empty[stage], ((it >> 1) & 1) ^ 1);
-                mbar_expect_tx(&in_full[stage], kBtTileA);
-                tma_load_3d(a1 + stage * kBtTileA, &p.map[tl.level], tl.x0 - kBtXoff, tl.y0 - 3, tl.frame, &in_full[stage]);
+                mbar_wait(&in_empty[ld.slot], ld.phase ^ 1);
+                TR(0, it, 1);
+                mbar_expect_tx(&in_full[ld.slot], kBtTileA);
+                tma_load_3d(a1 + ld.slot * kBtTileA, &p.map[tl.level], tl.x0 - kBtXoff, tl.y0 - 3, tl.frame, &in_full[ld.slot]);
+                TR(0, it, 2);
+                ld.next(kBtStages);
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            uint32_t it = 0;
-            const uint64_t d_bh = tc_smem_desc(bh), d_bv = tc_smem_desc(bv), d_b2h = tc_smem_desc(b2h), d_b2l = tc_smem_desc(b2l);
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-                const int stage = it & 1;
-                mbar_wait(&in_full[stage], (it >> 1) & 1);       // window landed ...
-                mbar_wait(&a_ready[stage], (it >> 1) & 1);       // ... and, on border tiles, patched
-                mbar_wait(d1_empty, (it & 1) ^ 1);               // H of the previous tile has been read
-                tc_fence_after();
-                const uint64_t d_a1 = tc_smem_desc(a1 + stage * kBtTileA);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) tc_mma_i8(tD1, d_a1 + 2 * k, d_bh + 2 * k, kBtIdesc, k ? 1u : 0u);
-                tc_commit(&in_empty[stage]);
-                tc_commit(d1_full);
-                mbar_wait(b2_full, it & 1);                      // H bytes are in shared memory
-                mbar_wait(d2_empty, (it & 1) ^ 1);               // V of the previous tile has been read
-                tc_fence_after();
-#pragma unroll
-                for (int k = 0; k < 4; ++k) tc_mma_i8(tD2h, d_bv + 2 * k, d_b2h + 2 * k, kBtIdesc, k ? 1u : 0u);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) tc_mma_i8(tD2l, d_bv + 2 * k, d_b2l + 2 * k, kBtIdesc, k ? 1u : 0u);
-                tc_commit(b2_empty);
-                tc_commit(d2_full);
-            }
-        }
-    } else if (warp < 6) {
-        // ===== border patch, then H -> byte operands =====
-        const int q = warp & 3, row = q * 32 + lane;             // TMEM lane = window row = K index of GEMM 2
-        const int tid = (warp - 2) * 32 + lane;                  // 0..127 within this group
-        uint32_t it = 0;
+    } else if (warp == kWarpPatch) {
+        // ===== REFLECT_101 of the plane itself: windows that touch its border get the three out-of-plane columns /
+        // rows from their mirror images.  Loads are staged in registers so that they do not queue behind the stores. =====
+        Ring pt;
+        int it = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-            const int stage = it & 1;
+            TR(1, it, 0);
             const BtTile tl = bt_tile(p, t);
-            uint8_t *A = a1 + stage * kBtTileA;
-            mbar_wait(&in_full[stage], (it >> 1) & 1);
+            uint8_t *A = a1 + pt.slot * kBtTileA;
             const int w = p.w[tl.level], h = p.h[tl.level];
-            const int kw = kBtXoff + (w - tl.x0);                // window column of x = w
-            const int rb = h - tl.y0 + 3;                        // window row of y = h
+            const int kw = kBtXoff + (w - tl.x0);                // window column of x = w   (>= 17)
+            const int rb = h - tl.y0 + 3;                        // window row of y = h      (>= 4)
             const bool left = tl.x0 == 0, right = kw < 128, top = tl.y0 == 0, bottom = rb < 128;
-            if (left || right || top || bottom) {                // REFLECT_101 of the plane itself
-                if (left) {
+            TR(1, it, 1);
+            mbar_wait(&in_full[pt.slot], pt.phase);
+            TR(1, it, 2);
+            if (left || right || top || bottom) {
+                if (left || right) {                             // columns first (every row of the window) ...
+                    uint8_t cl[4][3], cr[4][3];
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) A[swz(tid, kBtXoff - 3 + j)] = A[swz(tid, kBtXoff + 3 - j)];
-                }
-                if (right) {
+                    for (int rr = 0; rr < 4; ++rr) {
+                        const int row = rr * 32 + lane;
 #pragma unroll
-                    for (int j = 0; j < 3; ++j)
-                        if (kw + j < 128 && kw - 2 - j >= 0) A[swz(tid, kw + j)] = A[swz(tid, kw - 2 - j)];
+                        for (int j = 0; j < 3; ++j) {
+                            cl[rr][j] = left ? A[swz(row, kBtXoff + 3 - j)] : 0;      // x = -3 + j  <-  x = 3 - j
+                            cr[rr][j] = right ? A[swz(row, kw - 2 - j)] : 0;          // x = w + j   <-  x = w - 2 - j
+                        }
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        const int row = rr * 32 + lane;
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            if (left) A[swz(row, kBtXoff - 3 + j)] = cl[rr][j];
+                            if (right && kw + j < 128) A[swz(row, kw + j)] = cr[rr][j];
+                        }
+                    }
+                    __syncwarp();
                 }
-                bar_sync_128(1);
-                if (top && tid < 96) {                           // rows y = -3..-1 <- y = 3, 2, 1
-                    const int j = tid >> 5, c = (tid & 31) * 4;
-                    *reinterpret_cast<uint32_t *>(A + swz(j, c)) = *reinterpret_cast<const uint32_t *>(A + swz(6 - j, c));
-                }
-                if (bottom && tid < 96) {                        // rows y = h..h+2 <- y = h-2, h-3, h-4
-                    const int j = tid >> 5, c = (tid & 31) * 4;
-                    if (rb + j < 128 && rb - 2 - j >= 0)
-                        *reinterpret_cast<uint32_t *>(A + swz(rb + j, c)) = *reinterpret_cast<const uint32_t *>(A + swz(rb - 2 - j, c));
+                if (top || bottom) {                             // ... then whole rows, corners included
+                    const int c = lane * 4;
+                    uint32_t rt[3], rbm[3];
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        rt[j] = top ? *reinterpret_cast<const uint32_t *>(A + swz(6 - j, c)) : 0;                          // y = -3 + j <- 3 - j
+                        rbm[j] = bottom && rb - 2 - j >= 0 ? *reinterpret_cast<const uint32_t *>(A + swz(rb - 2 - j, c)) : 0;   // y = h + j <- h - 2 - j
+                    }
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        if (top) *reinterpret_cast<uint32_t *>(A + swz(j, c)) = rt[j];
+                        if (bottom && rb + j < 128 && rb - 2 - j >= 0) *reinterpret_cast<uint32_t *>(A + swz(rb + j, c)) = rbm[j];
+                    }
                 }
                 fence_async_smem();
+                __syncwarp();
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&a_ready[stage]);
-
-            mbar_wait(d1_full, it & 1);
+            if (lane == 0) mbar_arrive(&a_ready[pt.slot]);
+            TR(1, it, 3);
+            pt.next(kBtStages);
+        }
+    } else if (warp == kWarpMma1) {
+        // ===== GEMM 1 issuer: Ht[n][i] = sum_k Bh[n][k] W[i][k] into Ht buffer (tile & 1) =====
+        if (lane == 0) {
+            Ring in;
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+                const int buf = it & 1;
+                TR(2, it, 0);
+                mbar_wait(&a_ready[in.slot], in.phase);              // window landed (the patch warp saw in_full) and patched
+                TR(2, it, 1);
+                mbar_wait(&d1_empty[buf], ((it >> 1) & 1) ^ 1);      // this Ht buffer has been read
+                TR(2, it, 2);
+                tc_fence_after();
+                const uint64_t d_w = tc_smem_desc(a1 + in.slot * kBtTileA);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) tc_mma_i8_ts(tmem + buf * 128, tBh + 8 * k, d_w + 2 * k, bt_idesc(128), k ? 1u : 0u);
+                tc_commit(&in_empty[in.slot]);
+                tc_commit(&d1_full[buf]);
+                TR(2, it, 3);
+                in.next(kBtStages);
+            }
+        }
+    } else if (warp == kWarpMma2) {
+        // ===== GEMM 2 issuer: V[r][n] = sum_k Bv[r][k] Ht[n][k], once per byte plane =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+                const int buf = it & 1;
+                TR(3, it, 0);
+                mbar_wait(&b2_full[buf], (it >> 1) & 1);             // byte planes of Ht are in shared memory
+                TR(3, it, 1);
+                mbar_wait(d2_empty, (it & 1) ^ 1);                   // V of the previous tile has been read
+                TR(3, it, 2);
+                tc_fence_after();
+                const uint64_t d_h = tc_smem_desc(b2 + buf * 2 * kBtTileB), d_l = tc_smem_desc(b2 + buf * 2 * kBtTileB + kBtTileB);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) tc_mma_i8_ts(tD2h, tBv + 8 * k, d_h + 2 * k, bt_idesc(kBtW), k ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) tc_mma_i8_ts(tD2l, tBv + 8 * k, d_l + 2 * k, bt_idesc(kBtW), k ? 1u : 0u);
+                tc_commit(&b2_empty[buf]);
+                tc_commit(d2_full);
+                TR(3, it, 3);
+            }
+        }
+    } else if (warp < 8) {
+        // ===== Ht -> byte operands of GEMM 2: warps 0-2 take the even tiles (buffer 0), warps 4-6 the odd ones (buffer 1) =====
+        const int buf = warp >> 2, q = warp & 3, n = q * 32 + lane;    // TMEM lane = output column of the tile
+        const uint32_t taddr = tmem + buf * 128 + ((uint32_t)(q * 32) << 16);
+        uint8_t *row_h = b2 + buf * 2 * kBtTileB + n * 128, *row_l = row_h + kBtTileB;
+        const int x7 = (n & 7) << 4;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int64_t t = (int64_t)blockIdx.x + (int64_t)buf * gridDim.x; t < total_tiles; t += 2 * (int64_t)gridDim.x, phase ^= 1, ++it) {
+            mbar_wait(&d1_full[buf], phase);
             tc_fence_after();
-            mbar_wait(b2_empty, (it & 1) ^ 1);                   // GEMM 2 of the previous tile no longer reads the byte planes
-            const uint32_t taddr = tD1 + ((uint32_t)(q * 32) << 16);
-            const int kc = row >> 4, kl = row & 15;
-            uint8_t *ph[8], *pl[8];
+            mbar_wait(&b2_empty[buf], phase ^ 1);                // GEMM 2 of two tiles ago no longer reads these byte planes
 #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const int off = m * 128 + (((kc ^ m) << 4) | kl);
-                ph[m] = b2h + off;
-                pl[m] = b2l + off;
-            }
-#pragma unroll
-            for (int c = 0; c < kBtW / 32; ++c) {
-                int v[32];
-                tc_ld32(taddr + c * 32, v);
+            for (int c = 0; c < 2; ++c) {                        // window rows 64c .. 64c + 63, two per register
+                uint32_t v[32];
+                tc_ld_pack32(taddr + c * 64, v);
                 tc_wait_ld();
+                if (c == 1) {                                    // everything is in registers: GEMM 1 may overwrite this buffer
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&d1_empty[buf]);
+                    if (q == 0) TR(4, it, 2);
+                }
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int n = c * 32 + j;                    // operand row n, byte `row`: offset n * 128 + swizzled(row)
-                    ph[n & 7][(n >> 3) * 1024] = (uint8_t)(v[j] >> 8);
-                    pl[n & 7][(n >> 3) * 1024] = (uint8_t)v[j];
+                for (int m = 0; m < 4; ++m) {                    // 16-byte chunk 4c + m of the row, swizzled
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {                // bytes of a register: lo(H0) hi(H0) lo(H1) hi(H1)
+                        lo[g] = __byte_perm(v[8 * m + 2 * g], v[8 * m + 2 * g + 1], 0x6420);
+                        hi[g] = __byte_perm(v[8 * m + 2 * g], v[8 * m + 2 * g + 1], 0x7531);
+                    }
+                    const int off = ((4 * c + m) << 4) ^ x7;
+                    *reinterpret_cast<uint4 *>(row_h + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4 *>(row_l + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                 }
             }
             fence_async_smem();
-            tc_fence_before();
             __syncwarp();
-            if (lane == 0) { mbar_arrive(d1_empty); mbar_arrive(b2_full); }
+            if (lane == 0) mbar_arrive(&b2_full[buf]);
+            if (q == 0) TR(4, it, 3);
         }
-    } else {
-        // ===== V -> blurred rows =====
-        const int q = warp & 3, r = q * 32 + lane;
-        uint32_t it = 0;
+    } else if (warp < 16) {
+        // ===== V -> blurred rows: warp (q, half) owns rows 32q.. and columns 48 half.. =====
+        const int q = warp & 3, half = (warp - 8) >> 2, r = q * 32 + lane;
+        uint32_t v_phase = 0;
+        int it = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
             const BtTile tl = bt_tile(p, t);
             const int w = p.w[tl.level], h = p.h[tl.level];
-            mbar_wait(d2_full, it & 1);
-            tc_fence_after();
-            const uint32_t lane_bits = (uint32_t)(q * 32) << 16;
             const int y = tl.y0 + r;
             const bool row_ok = r < kBtH && y < h;
-            uint8_t *dst = blur + p.dst_offset[tl.level] + (int64_t)tl.frame * p.dst_stride[tl.level] + (int64_t)y * p.dst_pitch[tl.level] + tl.x0;
-#pragma unroll
-            for (int c = 0; c < kBtW / 32; ++c) {
-                int vh[32], vl[32];
-                tc_ld32(tD2h + lane_bits + c * 32, vh);
-                tc_ld32(tD2l + lane_bits + c * 32, vl);
-                tc_wait_ld();
-                uint32_t o[8];
-#pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    uint32_t wv = 0;
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        const uint32_t v = ((uint32_t)vh[4 * g + b] << 8) + (uint32_t)vl[4 * g + b] + 32768u;
-                        wv |= (v >> 16) << (8 * b);
-                    }
-                    o[g] = wv;
-                }
-                if (row_ok) {
-                    const int x = tl.x0 + c * 32;
-                    if (x + 32 <= w) {
-                        reinterpret_cast<uint4 *>(dst + c * 32)[0] = make_uint4(o[0], o[1], o[2], o[3]);
-                        reinterpret_cast<uint4 *>(dst + c * 32)[1] = make_uint4(o[4], o[5], o[6], o[7]);
-                    } else {
-#pragma unroll
-                        for (int b = 0; b < 32; ++b)
-                            if (x + b < w) dst[c * 32 + b] = (uint8_t)(o[b >> 2] >> (8 * (b & 3)));
-                    }
-                }
-            }
+            const int xh = tl.x0 + half * 48;
+            uint8_t *dst = blur + p.dst_offset[tl.level] + (int64_t)tl.frame * p.dst_stride[tl.level] + (int64_t)y * p.dst_pitch[tl.level] + xh;
+            const uint32_t col = ((uint32_t)(q * 32) << 16) + half * 48;
+            mbar_wait(d2_full, v_phase);
+            tc_fence_after();
+            if (warp == 8) TR(5, it, 1);
+            // 256 Vh + Vl + 32768 >> 16  ==  Vh + (Vl >> 8) + 128 >> 8, and Vh + (Vl >> 8) <= 65280: it stays inside 16-bit lanes
+            uint32_t vh0[16], vl0[16], vh1[8], vl1[8];       // all loads first: V is released as early as possible
+            tc_ld_pack16(tD2h + col, vh0);
+            tc_ld_pack16(tD2l + col, vl0);
+            tc_ld_pack8(tD2h + col + 32, vh1);
+            tc_ld_pack8(tD2l + col + 32, vl1);
+            tc_wait_ld();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(d2_empty);
+            if (warp == 8) TR(5, it, 2);
+            auto round2 = [](uint32_t h, uint32_t l) { return h + __byte_perm(l, 0, 0x4341) + 0x00800080u; };   // results in bytes 1 and 3
+            uint4 o[3];
+            {
+                uint32_t wv[12];
+#pragma unroll
+                for (int g = 0; g < 8; ++g) wv[g] = __byte_perm(round2(vh0[2 * g], vl0[2 * g]), round2(vh0[2 * g + 1], vl0[2 * g + 1]), 0x7531);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) wv[8 + g] = __byte_perm(round2(vh1[2 * g], vl1[2 * g]), round2(vh1[2 * g + 1], vl1[2 * g + 1]), 0x7531);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) o[c] = make_uint4(wv[4 * c], wv[4 * c + 1], wv[4 * c + 2], wv[4 * c + 3]);
+            }
+            if (row_ok) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const int x = xh + c * 16;
+                    if (x + 16 <= w) {
+                        *reinterpret_cast<uint4 *>(dst + c * 16) = o[c];
+                    } else {
+                        const uint32_t wv[4] = {o[c].x, o[c].y, o[c].z, o[c].w};
+#pragma unroll
+                        for (int b = 0; b < 16; ++b)
+                            if (x + b < w) dst[c * 16 + b] = (uint8_t)(wv[b >> 2] >> (8 * (b & 3)));
+                    }
+                }
+            }
+            if (warp == 8) TR(5, it, 3);
+            v_phase ^= 1;
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    if (warp == kWarpMma1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
+
+#ifdef BT_TRACE
+extern "C" int vsg_debug_bt_trace(long long *out) { return (int)cudaMemcpyFromSymbol(out, g_bt_trace, sizeof(g_bt_trace)); }
+#endif
 
 // VSG_BLUR_TC = n: batches of at least n frames blur on the tensor cores (0 = never); default 16
 static int blur_tc_min_frames() {
@@ -312,15 +446,17 @@ bool launch_blur_tc(const FrameGeom &g, const uint8_t *lvl0_base, int lvl0_pitch
             return false;
         p.tile_begin[l] = total;
         p.ntx[l] = (L.w + kBtW - 1) / kBtW;
+        p.ntx_rcp[l] = p.ntx[l] == 1 ? 0u : (uint32_t)((0x100000000ull + p.ntx[l] - 1) / p.ntx[l]);
         total += p.ntx[l] * ((L.h + kBtH - 1) / kBtH);
         p.w[l] = L.w; p.h[l] = L.h; p.dst_pitch[l] = L.pitch;
         p.dst_offset[l] = L.plane_offset; p.dst_stride[l] = L.plane_stride;
     }
-    for (int l = g.nlevels; l < 8; ++l) { p.map[l] = p.map[0]; p.tile_begin[l] = total; p.ntx[l] = 1; p.w[l] = p.h[l] = 0; p.dst_pitch[l] = 0; p.dst_offset[l] = p.dst_stride[l] = 0; }
+    for (int l = g.nlevels; l < 8; ++l) { p.map[l] = p.map[0]; p.tile_begin[l] = total; p.ntx[l] = 1; p.ntx_rcp[l] = 0; p.w[l] = p.h[l] = 0; p.dst_pitch[l] = 0; p.dst_offset[l] = p.dst_stride[l] = 0; }
     p.tile_begin[8] = total;
     p.tiles_per_frame = total;
     const int64_t tiles = (int64_t)total * nframes;
-    if (tiles <= 0 || tiles > INT32_MAX) return false;
+    if (tiles <= 0 || tiles * total >= (1ll << 32)) return false;
+    p.tpf_rcp = total == 1 ? 0u : (uint32_t)((0x100000000ull + total - 1) / total);
     if (cudaFuncSetAttribute(blur_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBtSmem) != cudaSuccess) { cudaGetLastError(); return false; }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
