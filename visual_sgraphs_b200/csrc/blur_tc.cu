@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kBtThreads, 1) blur_tc_kernel(const __grid_con
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
             TR(1, it, 0);
             const BtTile tl = bt_tile(p, t);
-            uint8_t *A = a1 + pt.slot * kBtTileA;
+            const uint32_t A = smem_u32(a1) + pt.slot * kBtTileA;
             const int w = p.w[tl.level], h = p.h[tl.level];
             const int kw = kBtXoff + (w - tl.x0);                // window column of x = w   (>= 17)
             const int rb = h - tl.y0 + 3;                        // window row of y = h      (>= 4)
@@ -223,14 +223,14 @@ __global__ void __launch_bounds__(kBtThreads, 1) blur_tc_kernel(const __grid_con
             TR(1, it, 2);
             if (left || right || top || bottom) {
                 if (left || right) {                             // columns first (every row of the window) ...
-                    uint8_t cl[4][3], cr[4][3];
+                    uint32_t cl[4][3], cr[4][3];
 #pragma unroll
                     for (int rr = 0; rr < 4; ++rr) {
                         const int row = rr * 32 + lane;
 #pragma unroll
                         for (int j = 0; j < 3; ++j) {
-                            cl[rr][j] = left ? A[swz(row, kBtXoff + 3 - j)] : 0;      // x = -3 + j  <-  x = 3 - j
-                            cr[rr][j] = right ? A[swz(row, kw - 2 - j)] : 0;          // x = w + j   <-  x = w - 2 - j
+                            cl[rr][j] = left ? lds_u8(A + swz(row, kBtXoff + 3 - j)) : 0;      // x = -3 + j  <-  x = 3 - j
+                            cr[rr][j] = right ? lds_u8(A + swz(row, kw - 2 - j)) : 0;          // x = w + j   <-  x = w - 2 - j
                         }
                     }
 #pragma unroll
@@ -238,8 +238,8 @@ __global__ void __launch_bounds__(kBtThreads, 1) blur_tc_kernel(const __grid_con
                         const int row = rr * 32 + lane;
 #pragma unroll
                         for (int j = 0; j < 3; ++j) {
-                            if (left) A[swz(row, kBtXoff - 3 + j)] = cl[rr][j];
-                            if (right && kw + j < 128) A[swz(row, kw + j)] = cr[rr][j];
+                            if (left) sts_u8(A + swz(row, kBtXoff - 3 + j), cl[rr][j]);
+                            if (right && kw + j < 128) sts_u8(A + swz(row, kw + j), cr[rr][j]);
                         }
                     }
                     __syncwarp();
@@ -249,13 +249,13 @@ __global__ void __launch_bounds__(kBtThreads, 1) blur_tc_kernel(const __grid_con
                     uint32_t rt[3], rbm[3];
 #pragma unroll
                     for (int j = 0; j < 3; ++j) {
-                        rt[j] = top ? *reinterpret_cast<const uint32_t *>(A + swz(6 - j, c)) : 0;                          // y = -3 + j <- 3 - j
-                        rbm[j] = bottom && rb - 2 - j >= 0 ? *reinterpret_cast<const uint32_t *>(A + swz(rb - 2 - j, c)) : 0;   // y = h + j <- h - 2 - j
+                        rt[j] = top ? lds_u32(A + swz(6 - j, c)) : 0;                                 // y = -3 + j <- 3 - j
+                        rbm[j] = bottom && rb - 2 - j >= 0 ? lds_u32(A + swz(rb - 2 - j, c)) : 0;     // y = h + j <- h - 2 - j
                     }
 #pragma unroll
                     for (int j = 0; j < 3; ++j) {
-                        if (top) *reinterpret_cast<uint32_t *>(A + swz(j, c)) = rt[j];
-                        if (bottom && rb + j < 128 && rb - 2 - j >= 0) *reinterpret_cast<uint32_t *>(A + swz(rb + j, c)) = rbm[j];
+                        if (top) sts_u32(A + swz(j, c), rt[j]);
+                        if (bottom && rb + j < 128 && rb - 2 - j >= 0) sts_u32(A + swz(rb + j, c), rbm[j]);
                     }
                 }
                 fence_async_smem();
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(kBtThreads, 1) blur_tc_kernel(const __grid_con
         // ===== Ht -> byte operands of GEMM 2: warps 0-2 take the even tiles (buffer 0), warps 4-6 the odd ones (buffer 1) =====
         const int buf = warp >> 2, q = warp & 3, n = q * 32 + lane;    // TMEM lane = output column of the tile
         const uint32_t taddr = tmem + buf * 128 + ((uint32_t)(q * 32) << 16);
-        uint8_t *row_h = b2 + buf * 2 * kBtTileB + n * 128, *row_l = row_h + kBtTileB;
+        const uint32_t row_h = smem_u32(b2) + buf * 2 * kBtTileB + n * 128, row_l = row_h + kBtTileB;
         const int x7 = (n & 7) << 4;
         uint32_t phase = 0;
         int it = 0;
@@ -341,8 +341,8 @@ __global__ void __launch_bounds__(kBtThreads, 1) blur_tc_kernel(const __grid_con
                         hi[g] = __byte_perm(v[8 * m + 2 * g], v[8 * m + 2 * g + 1], 0x7531);
                     }
                     const int off = ((4 * c + m) << 4) ^ x7;
-                    *reinterpret_cast<uint4 *>(row_h + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<uint4 *>(row_l + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    sts_v4(row_h + off, hi[0], hi[1], hi[2], hi[3]);
+                    sts_v4(row_l + off, lo[0], lo[1], lo[2], lo[3]);
                 }
             }
             fence_async_smem();
