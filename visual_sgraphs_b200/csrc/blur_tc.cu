@@ -389,18 +389,12 @@ __global__ void __launch_bounds__(kBtThreads, 1) blur_tc_kernel(const __grid_con
                 for (int c = 0; c < 3; ++c) o[c] = make_uint4(wv[4 * c], wv[4 * c + 1], wv[4 * c + 2], wv[4 * c + 3]);
             }
             if (row_ok) {
+                // whole 16-byte chunks only: x and the pitch are multiples of 16, so a chunk that starts inside the row's pitch ends
+                // inside it, and the bytes between w and the pitch are padding nobody reads
+                const int pitch = p.dst_pitch[tl.level];
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const int x = xh + c * 16;
-                    if (x + 16 <= w) {
-                        *reinterpret_cast<uint4 *>(dst + c * 16) = o[c];
-                    } else {
-                        const uint32_t wv[4] = {o[c].x, o[c].y, o[c].z, o[c].w};
-#pragma unroll
-                        for (int b = 0; b < 16; ++b)
-                            if (x + b < w) dst[c * 16 + b] = (uint8_t)(wv[b >> 2] >> (8 * (b & 3)));
-                    }
-                }
+                for (int c = 0; c < 3; ++c)
+                    if (xh + c * 16 < w && xh + c * 16 + 16 <= pitch) *reinterpret_cast<uint4 *>(dst + c * 16) = o[c];
             }
             if (warp == 8) TR(5, it, 3);
             v_phase ^= 1;
@@ -436,7 +430,9 @@ bool launch_blur_tc(const FrameGeom &g, const uint8_t *lvl0_base, int lvl0_pitch
         const LevelGeom &L = g.lv[l];
         const uint8_t *base = l == 0 ? lvl0_base : pyr + L.plane_offset;
         const int64_t pitch = l == 0 ? lvl0_pitch : L.pitch, stride = l == 0 ? lvl0_stride : L.plane_stride;
-        if (((uintptr_t)base & 15) || (pitch & 15) || (stride & 15) || (((uintptr_t)(blur + L.plane_offset)) & 15)) return false;
+        if (((uintptr_t)base & 15) || (pitch & 15) || (stride & 15) || (((uintptr_t)(blur + L.plane_offset)) & 15) ||
+            (L.pitch & 15) || (L.plane_stride & 15))
+            return false;
         const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)L.h, (cuuint64_t)nframes};
         const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)stride};
         const cuuint32_t box[3] = {128, 128, 1};
