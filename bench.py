@@ -920,8 +920,15 @@ def main():
     if rank == 0:
         frames_total = world * B * K
         value = frames_total / (elapsed_ms * 1e-3)
-        fused = os.environ.get("VSG_FUSE_FAST_BLUR", "1") != "0"
+        tc_min = int(os.environ.get("VSG_BLUR_TC", "16") or 0)
+        tc_blur = 0 < tc_min <= B                    # batches this large blur on the tensor cores (csrc/blur_tc.cu), a stage of its own
+        fused = os.environ.get("VSG_FUSE_FAST_BLUR", "1") != "0" and not tc_blur
         stages_bytes, b_frame = algorithmic_bytes(W, H, n_kp_mean, fused)
+        kernel_of = {"fast": "fast_blur_kernel" if fused else "fast_kernel", "blur": "blur_tc_kernel" if tc_blur else "blur_kernel",
+                     "pyramid": "resize_kernel", "describe": "describe_kernel", "octree": "octree_kernel"}
+        what_of = {"fast_blur_kernel": "FAST cells + Gaussian blur in one grid", "fast_kernel": "FAST-9/16 cells, threshold retry, 3x3 NMS",
+                   "blur_tc_kernel": "7x7 Gaussian blur as banded u8 GEMMs on tcgen05", "blur_kernel": "7x7 Gaussian blur",
+                   "resize_kernel": "pyramid levels, one launch each", "describe_kernel": "IC_Angle + rBRIEF", "octree_kernel": "DistributeOctTree"}
         peak, peak_src = measured_peaks()
         dominant = max(stage_ms, key=lambda k: stage_ms[k])
         roof_stage = dominant if stages_bytes[dominant] > 0 else "fast"
@@ -941,10 +948,10 @@ def main():
                                      "what": "the same bytes per step with plain cudaMemcpyAsync (H2D + D2H concurrently) on all ranks at once, no kernels",
                                      "e2e_frac": (frames_total / (e2e_ms * 1e-3)) / (world * B / (copy_ms * 1e-3))}},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "fast_blur_kernel (FAST cells + Gaussian blur in one grid)" if fused and roof_stage == "fast" else roof_stage,
+            "roofline": {"bound": "hbm", "kernel": "%s (%s)" % (kernel_of[roof_stage], what_of[kernel_of[roof_stage]]),
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
-                         "traffic": ncu_traffic("fast_blur_kernel", B) if fused and roof_stage == "fast" else None,
+                         "traffic": ncu_traffic(kernel_of[roof_stage], B),
                          "traffic_note": "bytes per launch, from the committed ncu --set full capture (profiles/ncu_traffic.json), scaled to this batch if the capture used another",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_frame": stages_bytes[roof_stage], "launch_ms": dur_ms,

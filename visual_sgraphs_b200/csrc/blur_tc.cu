@@ -416,14 +416,20 @@ static int blur_tc_min_frames() {
     return v <= 0 ? INT32_MAX : v;
 }
 
-// Launches the tensor-core blur of `nframes` frames if the planes can be addressed by TMA; returns false (nothing launched)
-// otherwise — the caller then uses the CUDA-core blur.
-bool launch_blur_tc(const FrameGeom &g, const uint8_t *lvl0_base, int lvl0_pitch, int64_t lvl0_stride, const uint8_t *pyr, uint8_t *blur,
-                    int nframes, cudaStream_t s) {
-    if (nframes < blur_tc_min_frames() || g.nlevels > 8) return false;
-    EncodeTiledFn fn = encode_tiled_fn();
-    if (!fn) return false;
+struct BlurTcPlan {
     BlurTcParams p;
+    int64_t tiles;
+};
+
+// Plans the tensor-core blur of `nframes` frames: tensor maps and the tile table.  nullptr if it does not apply (small batch,
+// planes TMA cannot address) — the caller then uses the CUDA-core blur.  The plan lives in thread-local storage until the next call.
+const BlurTcPlan *plan_blur_tc(const FrameGeom &g, const uint8_t *lvl0_base, int lvl0_pitch, int64_t lvl0_stride, const uint8_t *pyr,
+                               const uint8_t *blur, int nframes) {
+    if (nframes < blur_tc_min_frames() || g.nlevels > 8) return nullptr;
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return nullptr;
+    static thread_local BlurTcPlan plan;
+    BlurTcParams &p = plan.p;
     p.nlevels = g.nlevels;
     int total = 0;
     for (int l = 0; l < g.nlevels; ++l) {
@@ -432,14 +438,14 @@ bool launch_blur_tc(const FrameGeom &g, const uint8_t *lvl0_base, int lvl0_pitch
         const int64_t pitch = l == 0 ? lvl0_pitch : L.pitch, stride = l == 0 ? lvl0_stride : L.plane_stride;
         if (((uintptr_t)base & 15) || (pitch & 15) || (stride & 15) || (((uintptr_t)(blur + L.plane_offset)) & 15) ||
             (L.pitch & 15) || (L.plane_stride & 15))
-            return false;
+            return nullptr;
         const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)L.h, (cuuint64_t)nframes};
         const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)stride};
         const cuuint32_t box[3] = {128, 128, 1};
         const cuuint32_t estr[3] = {1, 1, 1};
         if (fn(&p.map[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-            return false;
+            return nullptr;
         p.tile_begin[l] = total;
         p.ntx[l] = (L.w + kBtW - 1) / kBtW;
         p.ntx_rcp[l] = p.ntx[l] == 1 ? 0u : (uint32_t)((0x100000000ull + p.ntx[l] - 1) / p.ntx[l]);
@@ -451,15 +457,19 @@ bool launch_blur_tc(const FrameGeom &g, const uint8_t *lvl0_base, int lvl0_pitch
     p.tile_begin[8] = total;
     p.tiles_per_frame = total;
     const int64_t tiles = (int64_t)total * nframes;
-    if (tiles <= 0 || tiles * total >= (1ll << 32)) return false;
+    if (tiles <= 0 || tiles * total >= (1ll << 32)) return nullptr;
     p.tpf_rcp = total == 1 ? 0u : (uint32_t)((0x100000000ull + total - 1) / total);
-    if (cudaFuncSetAttribute(blur_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBtSmem) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (cudaFuncSetAttribute(blur_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBtSmem) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    plan.tiles = tiles;
+    return &plan;
+}
+
+void launch_blur_tc(const BlurTcPlan *plan, uint8_t *blur, cudaStream_t s) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    blur_tc_kernel<<<(unsigned)std::min<int64_t>(tiles, sms), kBtThreads, kBtSmem, s>>>(p, blur, (int)tiles);
+    blur_tc_kernel<<<(unsigned)std::min<int64_t>(plan->tiles, sms), kBtThreads, kBtSmem, s>>>(plan->p, blur, (int)plan->tiles);
     count_launch();
-    return true;
 }
 
 }  // namespace vsg

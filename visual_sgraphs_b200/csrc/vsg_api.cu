@@ -394,16 +394,17 @@ vsg_status run_pipeline(vsg_extractor *ex, cudaStream_t s, int f0, const uint8_t
     }
     STAGE_MARK(1);
     // FAST cells and the Gaussian blur share one grid (fast.cu) unless VSG_FUSE_FAST_BLUR=0
-    // large batches blur on the tensor cores instead (blur_tc.cu)
-    const bool blur_done = launch_blur_tc(g, lvl0_base, lvl0_pitch, lvl0_stride, ex->pyr, ex->blur, nframes, s);
+    // large batches blur on the tensor cores instead (blur_tc.cu), as a stage of its own after the oct-tree
+    const BlurTcPlan *blur_tc = plan_blur_tc(g, lvl0_base, lvl0_pitch, lvl0_stride, ex->pyr, ex->blur, nframes);
     const vsg_status fst = launch_fast(g, ex->cells_d, lvl0_base, lvl0_pitch, lvl0_stride, ex->pyr,
-                                       ex->fuse_fast_blur && !blur_done ? ex->blur : nullptr, ex->cand, cand_count, ex->p.ini_th_fast,
+                                       ex->fuse_fast_blur && !blur_tc ? ex->blur : nullptr, ex->cand, cand_count, ex->p.ini_th_fast,
                                        ex->p.min_th_fast, ex->max_cw, ex->max_ch, nframes, s);
     if (fst != VSG_OK) return fst;
     STAGE_MARK(2);
     launch_octree(g, ex->cand, cand_count, ex->node_of, level_kps, level_kp_count, ex->max_nodes, nframes, s);
     STAGE_MARK(3);
-    if (!ex->fuse_fast_blur && !blur_done) launch_blur(g, lvl0_base, lvl0_pitch, lvl0_stride, ex->pyr, ex->blur, nframes, s);
+    if (blur_tc) launch_blur_tc(blur_tc, ex->blur, s);
+    else if (!ex->fuse_fast_blur) launch_blur(g, lvl0_base, lvl0_pitch, lvl0_stride, ex->pyr, ex->blur, nframes, s);
     STAGE_MARK(4);
     launch_describe(g, lvl0_base, lvl0_pitch, lvl0_stride, ex->pyr, ex->blur, level_kps, level_kp_count, lap_x0,
                     lap_x1, kps_dev, desc_dev, out_cap, n_dev, mono_dev, slot, nframes, s);

@@ -176,9 +176,11 @@ struct RectifyMaps {
 };
 void launch_remap(const uint8_t *src, int src_pitch, int64_t src_stride, int sw, int sh, const RectifyMaps &maps, int first_frame,
                   uint8_t *dst, int dst_pitch, int64_t dst_stride, int w, int h, int nframes, cudaStream_t s);
-// blur_tc.cu: the blur as banded int8 GEMMs on the tensor cores; false = not applicable, nothing launched
-bool launch_blur_tc(const FrameGeom &g, const uint8_t *lvl0_base, int lvl0_pitch, int64_t lvl0_stride, const uint8_t *pyr, uint8_t *blur,
-                    int nframes, cudaStream_t s);
+// blur_tc.cu: the blur as banded u8 GEMMs on the tensor cores; plan == nullptr: not applicable (use launch_blur)
+struct BlurTcPlan;
+const BlurTcPlan *plan_blur_tc(const FrameGeom &g, const uint8_t *lvl0_base, int lvl0_pitch, int64_t lvl0_stride, const uint8_t *pyr,
+                               const uint8_t *blur, int nframes);
+void launch_blur_tc(const BlurTcPlan *plan, uint8_t *blur, cudaStream_t s);
 void launch_blur(const FrameGeom &g, const uint8_t *lvl0_base, int lvl0_pitch, int64_t lvl0_stride, const uint8_t *pyr,
                  uint8_t *blur, int nframes, cudaStream_t s);
 // blur != nullptr: the Gaussian blur of the same frames runs inside the same grid (fast_blur_kernel)
