@@ -13,14 +13,17 @@
 // (swizzled) 128-byte row of GEMM 2's K-major operand.  Nine in ten multiplications are by a zero tap; they still cost a
 // fraction of the issue slots the CUDA-core stencil needs, which is what the FAST kernel is short of.
 //
-// One persistent warp-specialised CTA per SM (448 threads):
-//   warp 0       TMA: source windows (cp.async.bulk.tensor.3d, SWIZZLE_128B, out-of-plane bytes zero-filled), 3 stages
-//   warp 1       one lane issues GEMM 1 of tile t+1, then GEMM 2 of tile t (tcgen05.mma, tcgen05.commit -> mbarriers)
-//   warps 2-5    (a) REFLECT_101: windows that touch the plane's border get the three out-of-plane columns / rows patched in
-//                shared memory from their mirror images; (b) tcgen05.ld of Ht, byte split, operand rows of GEMM 2 (2 buffers)
-//   warps 6-13   tcgen05.ld of Vh / Vl, rounding, 16-byte stores of the blurred rows
-// Tensor memory: Ht x 2 buffers (256 columns), Vh, Vl (96 each).  Results are bit-identical to blur_block_body
-// (blur_device.cuh), which stays for small batches and planes TMA cannot address.
+// One persistent warp-specialised CTA per SM (640 threads); every hand-off is an mbarrier:
+//   warp 3          TMA: source windows (cp.async.bulk.tensor.3d, SWIZZLE_128B, out-of-plane bytes zero-filled), 4 stages
+//   warps 16, 19    REFLECT_101 (even / odd tiles): windows that touch the plane's border get the three out-of-plane columns /
+//                   rows patched in shared memory from their mirror images
+//   warp 7          one lane issues GEMM 1 (tcgen05.mma, A = Bh in tensor memory, B = the window), tcgen05.commit
+//   warps 0-2, 4-6  tcgen05.ld of Ht (even / odd tiles, two buffers), byte split, operand rows of GEMM 2
+//   warps 17, 18    one lane each issues GEMM 2 for the high / low byte plane (A = Bv in tensor memory)
+//   warps 8-15      tcgen05.ld of Vh / Vl, rounding, 16-byte stores of the blurred rows
+// Tensor memory: Ht x 2 buffers (256 columns), Vh, Vl (96 each), Bh, Bv (32 each).  Results are bit-identical to
+// blur_block_body (blur_device.cuh), which stays for small batches and planes TMA cannot address.  profiles/r02_blur_tc.md
+// has the measurements behind this layout.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -36,10 +39,11 @@ namespace vsg {
 constexpr int kBtW = 96, kBtH = 122;            // output tile
 constexpr int kBtXoff = 16;                     // the source box starts this many columns left of the tile (16-byte alignment)
 constexpr int kBtStages = 4;
-constexpr int kBtThreads = 32 * 18;
+constexpr int kBtThreads = 32 * 20;
 // warps 0-2 / 4-6: Ht epilogue of the even / odd tiles (TMEM lane quarters 0-2; quarter 3 of Ht is padding, so the two warps
-// that could only read it, 3 and 7, do other work); warps 8-15: V epilogue; 16, 17: patch, GEMM 2 issue
-constexpr int kWarpTma = 3, kWarpMma1 = 7, kWarpPatch = 16, kWarpMma2 = 17;
+// that could only read it, 3 and 7, do other work); warps 8-15: V epilogue; 16, 19: patch (even / odd tiles); 17, 18: GEMM 2
+// issue for the high / low byte plane
+constexpr int kWarpTma = 3, kWarpMma1 = 7, kWarpPatch0 = 16, kWarpMma2h = 17, kWarpMma2l = 18, kWarpPatch1 = 19;
 constexpr int kBtTileA = 128 * 128;             // source window / Bh / Bv: 128 rows of 128 bytes
 constexpr int kBtTileB = kBtW * 128;            // byte planes of Ht: 96 rows of 128 bytes
 constexpr int kBtSmem = kBtStages * kBtTileA + 4 * kBtTileB + 256 + 1024;
@@ -148,8 +152,8 @@ __global__ void __launch_bounds__(kBtThreads, 1) blur_tc_kernel(const __grid_con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int i = 0; i < kBtStages; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], 1); mbar_init(&a_ready[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], 3); mbar_init(&b2_full[i], 3); mbar_init(&b2_empty[i], 1); }
-        mbar_init(d2_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], 3); mbar_init(&b2_full[i], 3); mbar_init(&b2_empty[i], 2); }
+        mbar_init(d2_full, 2);
         mbar_init(d2_empty, 8);
         mbar_init_fence();
     }
@@ -205,14 +209,17 @@ __global__ void __launch_bounds__(kBtThreads, 1) blur_tc_kernel(const __grid_con
                 ld.next(kBtStages);
             }
         }
-    } else if (warp == kWarpPatch) {
+    } else if (warp == kWarpPatch0 || warp == kWarpPatch1) {
         // ===== REFLECT_101 of the plane itself: windows that touch its border get the three out-of-plane columns /
         // rows from their mirror images.  Loads are staged in registers so that they do not queue behind the stores. =====
-        Ring pt;
-        int it = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        static_assert(kBtStages == 4, "slot / phase arithmetic below");
+        struct { int slot; uint32_t phase; } pt;
+        int it = warp == kWarpPatch1 ? 1 : 0;
+        for (int64_t t = (int64_t)blockIdx.x + (int64_t)it * gridDim.x; t < total_tiles; t += 2 * (int64_t)gridDim.x, it += 2) {
             TR(1, it, 0);
-            const BtTile tl = bt_tile(p, t);
+            pt.slot = it & 3;
+            pt.phase = (it >> 2) & 1;
+            const BtTile tl = bt_tile(p, (int)t);
             const uint32_t A = smem_u32(a1) + pt.slot * kBtTileA;
             const int w = p.w[tl.level], h = p.h[tl.level];
             const int kw = kBtXoff + (w - tl.x0);                // window column of x = w   (>= 17)
@@ -263,7 +270,6 @@ __global__ void __launch_bounds__(kBtThreads, 1) blur_tc_kernel(const __grid_con
             }
             if (lane == 0) mbar_arrive(&a_ready[pt.slot]);
             TR(1, it, 3);
-            pt.next(kBtStages);
         }
     } else if (warp == kWarpMma1) {
         // ===== GEMM 1 issuer: Ht[n][i] = sum_k Bh[n][k] W[i][k] into Ht buffer (tile & 1) =====
@@ -287,26 +293,26 @@ __global__ void __launch_bounds__(kBtThreads, 1) blur_tc_kernel(const __grid_con
                 in.next(kBtStages);
             }
         }
-    } else if (warp == kWarpMma2) {
-        // ===== GEMM 2 issuer: V[r][n] = sum_k Bv[r][k] Ht[n][k], once per byte plane =====
+    } else if (warp == kWarpMma2h || warp == kWarpMma2l) {
+        // ===== GEMM 2 issuers: V[r][n] = sum_k Bv[r][k] Ht[n][k], one thread per byte plane =====
         if (lane == 0) {
+            const int plane = warp == kWarpMma2l ? 1 : 0;
+            const uint32_t tD2 = plane ? tD2l : tD2h;
             uint32_t it = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
                 const int buf = it & 1;
-                TR(3, it, 0);
+                if (plane == 0) TR(3, it, 0);
                 mbar_wait(&b2_full[buf], (it >> 1) & 1);             // byte planes of Ht are in shared memory
-                TR(3, it, 1);
+                if (plane == 0) TR(3, it, 1);
                 mbar_wait(d2_empty, (it & 1) ^ 1);                   // V of the previous tile has been read
-                TR(3, it, 2);
+                if (plane == 0) TR(3, it, 2);
                 tc_fence_after();
-                const uint64_t d_h = tc_smem_desc(b2 + buf * 2 * kBtTileB), d_l = tc_smem_desc(b2 + buf * 2 * kBtTileB + kBtTileB);
+                const uint64_t d_b = tc_smem_desc(b2 + (buf * 2 + plane) * kBtTileB);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) tc_mma_i8_ts(tD2h, tBv + 8 * k, d_h + 2 * k, bt_idesc(kBtW), k ? 1u : 0u);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) tc_mma_i8_ts(tD2l, tBv + 8 * k, d_l + 2 * k, bt_idesc(kBtW), k ? 1u : 0u);
+                for (int k = 0; k < 4; ++k) tc_mma_i8_ts(tD2, tBv + 8 * k, d_b + 2 * k, bt_idesc(kBtW), k ? 1u : 0u);
                 tc_commit(&b2_empty[buf]);
                 tc_commit(d2_full);
-                TR(3, it, 3);
+                if (plane == 0) TR(3, it, 3);
             }
         }
     } else if (warp < 8) {
@@ -316,11 +322,13 @@ __global__ void __launch_bounds__(kBtThreads, 1) blur_tc_kernel(const __grid_con
         const uint32_t row_h = smem_u32(b2) + buf * 2 * kBtTileB + n * 128, row_l = row_h + kBtTileB;
         const int x7 = (n & 7) << 4;
         uint32_t phase = 0;
-        int it = 0;
-        for (int64_t t = (int64_t)blockIdx.x + (int64_t)buf * gridDim.x; t < total_tiles; t += 2 * (int64_t)gridDim.x, phase ^= 1, ++it) {
+        int it = buf;                                            // tile index within this CTA (trace only)
+        for (int64_t t = (int64_t)blockIdx.x + (int64_t)buf * gridDim.x; t < total_tiles; t += 2 * (int64_t)gridDim.x, phase ^= 1, it += 2) {
+            if (q == 0) TR(4, it, 0);
             mbar_wait(&d1_full[buf], phase);
             tc_fence_after();
             mbar_wait(&b2_empty[buf], phase ^ 1);                // GEMM 2 of two tiles ago no longer reads these byte planes
+            if (q == 0) TR(4, it, 1);
 #pragma unroll
             for (int c = 0; c < 2; ++c) {                        // window rows 64c .. 64c + 63, two per register
                 uint32_t v[32];
