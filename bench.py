@@ -67,6 +67,17 @@ def make_frames(n, seed0):
     return out
 
 
+def ncu_pipes(kernel):
+    """Issue-slot / ALU-pipe / tensor-pipe utilisation of the kernel from the same committed capture (what bounds a kernel
+    that the byte roofline does not explain)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p)).get(kernel, {})
+    out = {k: d[k] for k in ("issue_active_pct", "alu_pipe_active_pct", "tensor_pipe_active_pct") if k in d}
+    return out or None
+
+
 def ncu_traffic(kernel, frames):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture
     (profiles/ncu_traffic.json), scaled from the captured frames per launch to this run's."""
@@ -952,11 +963,13 @@ def main():
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
                          "traffic": ncu_traffic(kernel_of[roof_stage], B),
+                         "pipes": ncu_pipes(kernel_of[roof_stage]),
                          "traffic_note": "bytes per launch, from the committed ncu --set full capture (profiles/ncu_traffic.json), scaled to this batch if the capture used another",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_frame": stages_bytes[roof_stage], "launch_ms": dur_ms,
                          "dominant_stage_by_time": dominant,
-                         "note": "FAST/pyramid/blur are HBM-bound by bytes but issue-bound in practice (see DESIGN.md)"},
+                         "note": "FAST is HBM-bound by bytes but ALU-pipe bound in practice: its packed min/max alone need 1.13 ms per 512 frames "
+                                 "at 100 % of the pipe (`pipes` = the committed ncu capture; DESIGN.md section 4)"},
             "stages_ms_per_step": {k: v / max(runs, 1) for k, v in stage_ms.items()},
             "pipeline_hbm": {"algorithmic_bytes_per_frame": b_frame,
                              "achieved_gbs": b_frame * B * K / (elapsed_ms * 1e-3) / 1e9,

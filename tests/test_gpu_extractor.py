@@ -369,3 +369,36 @@ def test_tensor_core_blur_is_bit_identical(monkeypatch, wh):
                     f, l, len(bad), bad[0], p1[tuple(bad[0])], planes0[f][l][tuple(bad[0])]))
     for a, b in zip(got, want):
         assert a[0] == b[0] and a[1].tobytes() == b[1].tobytes() and np.array_equal(a[2], b[2])
+
+
+def test_tensor_core_blur_falls_back_when_tma_cannot_address_the_planes(monkeypatch):
+    """More than 8 levels, or a caller-owned level 0 whose pitch is not a multiple of 16 bytes: the batch takes the CUDA-core
+    blur (csrc/blur_tc.cu: plan_blur_tc returns no plan) and the results do not change."""
+    import torch
+    from visual_sgraphs_b200.extractor import ORBextractor
+    frames = np.stack([synth_frame(700 + i, 640, 480) for i in range(4)])
+    outs = []
+    for tc in ("0", "1"):
+        monkeypatch.setenv("VSG_BLUR_TC", tc)
+        outs.append(ORBextractor(1500, 1.2, 10, 20, 7, max_batch=4).extract_batch(frames))
+    for a, b in zip(*outs):
+        assert a[0] == b[0] and a[1].tobytes() == b[1].tobytes() and np.array_equal(a[2], b[2])
+    # device-resident frames, 642 bytes per row
+    odd = np.stack([synth_frame(710 + i, 642, 480) for i in range(4)])
+    res = []
+    for tc in ("0", "1"):
+        monkeypatch.setenv("VSG_BLUR_TC", tc)
+        ex = ORBextractor(1000, 1.2, 8, 20, 7, max_batch=4)
+        cap = ex.max_keypoints(642, 480)
+        d = torch.from_numpy(odd).cuda()
+        kd = torch.zeros((4, cap, 28), dtype=torch.uint8, device="cuda")
+        dd = torch.zeros((4, cap, 32), dtype=torch.uint8, device="cuda")
+        nd = torch.zeros(4, dtype=torch.int32, device="cuda")
+        md = torch.zeros(4, dtype=torch.int32, device="cuda")
+        ex.extract_batch_dev(d, kd, dd, nd, md)
+        ex.sync()
+        res.append((nd.cpu().numpy(), kd.cpu().numpy(), dd.cpu().numpy()))
+    assert np.array_equal(res[0][0], res[1][0])
+    for f in range(4):
+        n = res[0][0][f]
+        assert res[0][1][f, :n].tobytes() == res[1][1][f, :n].tobytes() and res[0][2][f, :n].tobytes() == res[1][2][f, :n].tobytes()

@@ -81,14 +81,23 @@ if os.path.exists(rep):
                          "kernel's longest captured launch" % tag,
                "head": head, "frames_per_launch": int(os.environ.get("VSG_PROFILE_BATCH", "512"))}
     best = {}
+    extra_cols = {"issue_active_pct": "smsp__issue_active.avg.pct_of_peak_sustained_active",
+                  "alu_pipe_active_pct": "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+                  "tensor_pipe_active_pct": "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+                  "warp_instructions": "smsp__inst_executed.sum"}
     for r in rows[2:]:
         name = r[col["Kernel Name"]].split("(")[0].split("<")[0].replace("void ", "").replace("vsg::", "")
         rd = float(r[col["dram__bytes_read.sum"]]) * unit_scale.get(units[col["dram__bytes_read.sum"]], 1.0)
         wr_ = float(r[col["dram__bytes_write.sum"]]) * unit_scale.get(units[col["dram__bytes_write.sum"]], 1.0)
         dur = float(r[col["gpu__time_duration.sum"]])
         if name not in best or dur > best[name][0]:
-            best[name] = (dur, rd + wr_)
-    for name, (dur, b) in best.items():
-        traffic[name] = {"dram_bytes_per_launch": int(b)}
+            ex = {}
+            for k, c in extra_cols.items():
+                hit = [i for i, hname in enumerate(hdr) if hname == c or hname.endswith("." + c)]
+                if hit and r[hit[0]] not in ("", "n/a"):
+                    ex[k] = round(float(r[hit[0]]), 2)
+            best[name] = (dur, rd + wr_, ex)
+    for name, (dur, b, ex) in best.items():
+        traffic[name] = dict({"dram_bytes_per_launch": int(b)}, **ex)
     json.dump(traffic, open(os.path.join(out_dir, "ncu_traffic.json"), "w"), indent=1)
     print("wrote ncu_traffic.json for", sorted(best))
