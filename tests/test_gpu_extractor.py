@@ -383,13 +383,13 @@ def test_tensor_core_blur_falls_back_when_tma_cannot_address_the_planes(monkeypa
         outs.append(ORBextractor(1500, 1.2, 10, 20, 7, max_batch=4).extract_batch(frames))
     for a, b in zip(*outs):
         assert a[0] == b[0] and a[1].tobytes() == b[1].tobytes() and np.array_equal(a[2], b[2])
-    # device-resident frames, 642 bytes per row
-    odd = np.stack([synth_frame(710 + i, 642, 480) for i in range(4)])
+    # device-resident frames, 644 bytes per row (the device API wants 4-byte alignment; TMA wants 16)
+    odd = np.stack([synth_frame(710 + i, 644, 480) for i in range(4)])
     res = []
     for tc in ("0", "1"):
         monkeypatch.setenv("VSG_BLUR_TC", tc)
         ex = ORBextractor(1000, 1.2, 8, 20, 7, max_batch=4)
-        cap = ex.max_keypoints(642, 480)
+        cap = ex.max_keypoints(644, 480)
         d = torch.from_numpy(odd).cuda()
         kd = torch.zeros((4, cap, 28), dtype=torch.uint8, device="cuda")
         dd = torch.zeros((4, cap, 32), dtype=torch.uint8, device="cuda")

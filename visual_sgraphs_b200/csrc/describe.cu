@@ -145,7 +145,28 @@ __global__ void __launch_bounds__(256, VSG_DESC_MINB) describe_kernel(FrameGeom 
     __syncthreads();
     if (s_row[0] < 0 && s_level[0] >= g.nlevels) return;   // whole CTA is past the last keypoint
 
-    // ---- IC_Angle moments (:73-100): lanes = columns u = lane-15 of the disc ----
+    // ---- IC_Angle moments (:73-100).  The disc is 31 rows of 31 bytes (u = -15..15); a row is eight 4-byte words once it is
+    // shifted to start at u = -15.  Lane l owns word j = l % 8 of the rows l / 8 + 4 i (i = 0..7): a load instruction of the
+    // warp reads four rows x 36 contiguous bytes.  Bytes outside the disc (|u| > umax[|v|]) are masked (table in shared
+    // memory), and m10 += sum u * I, m01 += v * sum I are two DP4A per word — exact integer sums, any order.  Every plane's
+    // pitch is a multiple of 4, so the misalignment of a row start is the same for all rows of a keypoint. ----
+    __shared__ uint32_t s_umask[32 * 8];
+    {
+        const int row = tid >> 3, j = tid & 7;               // 256 threads = 32 rows x 8 words
+        const int um = row < 31 ? c_umax[abs(row - kHalfPatch)] : -1;
+        uint32_t mk = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int u = 4 * j + b - kHalfPatch;
+            if (u <= kHalfPatch && abs(u) <= um) mk |= 0xFFu << (8 * b);
+        }
+        s_umask[tid] = mk;
+    }
+    __syncthreads();
+    const int wj = lane & 7, wr = lane >> 3;
+    const int u0 = 4 * wj - kHalfPatch;                      // weights u0 .. u0 + 3 as signed bytes
+    const uint32_t wt = (uint32_t)(uint8_t)u0 | ((uint32_t)(uint8_t)(u0 + 1) << 8) | ((uint32_t)(uint8_t)(u0 + 2) << 16) |
+                        ((uint32_t)(uint8_t)(u0 + 3) << 24);
     for (int k = warp; k < kDescKp; k += 8) {
         if (s_row[k] < 0) continue;
         const int level = s_level[k];
@@ -154,19 +175,25 @@ __global__ void __launch_bounds__(256, VSG_DESC_MINB) describe_kernel(FrameGeom 
         int ipitch;
         if (level == 0) { img = lvl0_base + (int64_t)frame * lvl0_stride; ipitch = lvl0_pitch; }
         else { img = pyr + L.plane_offset + (int64_t)frame * L.plane_stride; ipitch = L.pitch; }
-        int m10 = 0, m01 = 0;
-        if (lane < 31) {
-            const int u = lane - kHalfPatch;
-            const int au = abs(u);
-            const uint8_t *c = img + (int64_t)s_y[k] * ipitch + s_x[k] + u;
+        // keypoints keep 16 pixels to every border (EDGE_THRESHOLD - 3): all 31 rows exist, and the up to four bytes a word
+        // reaches beyond u = 15 still belong to the plane (or to the row below)
+        const uint8_t *p0 = img + (int64_t)(s_y[k] - kHalfPatch + wr) * ipitch + (s_x[k] - kHalfPatch);
+        const uint32_t off = (uint32_t)((uintptr_t)p0 & 3);
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(p0 - off) + wj;
+        const int step = ipitch;                             // four rows down, in words
+        uint32_t lo[8], hi[8];
 #pragma unroll
-            for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
-                if (au <= c_umax[v < 0 ? -v : v]) {
-                    const int val = __ldg(c + v * ipitch);
-                    m10 += u * val;
-                    m01 += v * val;
-                }
-            }
+        for (int i = 0; i < 8; ++i) {
+            const bool ok = wr + 4 * i < 31;
+            lo[i] = ok ? __ldg(wp + (int64_t)i * step) : 0u;
+            hi[i] = ok && off ? __ldg(wp + (int64_t)i * step + 1) : 0u;
+        }
+        int m10 = 0, m01 = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t px = __funnelshift_r(lo[i], hi[i], 8 * off) & s_umask[(wr + 4 * i) * 8 + wj];
+            asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(m10) : "r"(px), "r"(wt));
+            m01 += (wr + 4 * i - kHalfPatch) * (int)__dp4a(px, 0x01010101u, 0u);
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
