@@ -233,10 +233,14 @@ __global__ void __launch_bounds__(256, VSG_DESC_MINB) describe_kernel(FrameGeom 
     __syncthreads();
 
     // ---- computeOrbDescriptor (:103-149) on the blurred level: lane i -> descriptor byte i ----
+    // the lane's 16 pattern points as floats, converted once (they are the same for every keypoint of the CTA)
     const char4 *pat = reinterpret_cast<const char4 *>(d_pattern) + lane * 8;
-    char4 p[8];
+    float4 p[8];
 #pragma unroll
-    for (int bit = 0; bit < 8; ++bit) p[bit] = pat[bit];
+    for (int bit = 0; bit < 8; ++bit) {
+        const char4 c = pat[bit];
+        p[bit] = make_float4((float)c.x, (float)c.y, (float)c.z, (float)c.w);
+    }
     for (int k = warp; k < kDescKp; k += 8) {
         const int out_row = s_row[k];
         if (out_row < 0) continue;
@@ -246,7 +250,7 @@ __global__ void __launch_bounds__(256, VSG_DESC_MINB) describe_kernel(FrameGeom 
         int val = 0;
 #pragma unroll
         for (int bit = 0; bit < 8; ++bit) {
-            const float x0 = (float)p[bit].x, y0 = (float)p[bit].y, x1 = (float)p[bit].z, y1 = (float)p[bit].w;
+            const float x0 = p[bit].x, y0 = p[bit].y, x1 = p[bit].z, y1 = p[bit].w;
             const int ry0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
             const int rx0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
             const int ry1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
