@@ -402,3 +402,29 @@ def test_tensor_core_blur_falls_back_when_tma_cannot_address_the_planes(monkeypa
     for f in range(4):
         n = res[0][0][f]
         assert res[0][1][f, :n].tobytes() == res[1][1][f, :n].tobytes() and res[0][2][f, :n].tobytes() == res[1][2][f, :n].tobytes()
+
+
+@pytest.mark.parametrize("shape", [(640, 480, 8, 1.2), (752, 480, 8, 1.2), (1241, 376, 8, 1.2), (1280, 720, 8, 1.2), (640, 480, 5, 1.5),
+                                   (800, 600, 4, 1.7), (640, 480, 12, 1.1)])
+def test_one_launch_pyramid_matches_the_level_by_level_kernels(monkeypatch, shape):
+    """Batches of up to VSG_PYR_TILE (4) frames build the whole pyramid in one launch (csrc/pyramid.cu: pyramid_tile_kernel,
+    every level of a tile from the previous one in shared memory).  Planes and results must equal the seven resize launches'
+    (ORBextractor::ComputePyramid, ORBextractor.cc:1171-1195)."""
+    from visual_sgraphs_b200.extractor import ORBextractor
+    w, h, nlev, sf = shape
+    frames = np.stack([synth_frame(900 + i, w, h) for i in range(3)])
+    monkeypatch.setenv("VSG_PYR_TILE", "0")
+    ex0 = ORBextractor(1000, sf, nlev, 20, 7, max_batch=3)
+    want = ex0.extract_batch(frames)
+    planes0 = [[ex0.pyramid_level(l, f) for l in range(nlev)] for f in range(3)]
+    monkeypatch.setenv("VSG_PYR_TILE", "4")
+    ex1 = ORBextractor(1000, sf, nlev, 20, 7, max_batch=3)
+    got = ex1.extract_batch(frames)
+    for f in range(3):
+        for l in range(nlev):
+            p1 = ex1.pyramid_level(l, f)
+            if not np.array_equal(p1, planes0[f][l]):
+                bad = np.argwhere(p1 != planes0[f][l])
+                raise AssertionError("frame %d level %d: %d pixels differ, first %s" % (f, l, len(bad), bad[0]))
+    for a, b in zip(got, want):
+        assert a[0] == b[0] and a[1].tobytes() == b[1].tobytes() and np.array_equal(a[2], b[2])

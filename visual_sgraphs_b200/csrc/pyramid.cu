@@ -119,6 +119,122 @@ __global__ void __launch_bounds__(kResizeThreads, VSG_RESIZE_MINB) resize_kernel
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same pyramid for a few frames in one launch (single-frame latency: seven dependent launches cost 33 us, of which the
+// arithmetic is a few).  CTA = (tile, frame).  Level l of a tile is computed from level l-1 of the SAME tile in shared
+// memory, so no CTA ever waits for another: the region a tile computes at level l-1 is the bounding box of the taps its
+// level-l region reads and of the box it owns there; it stores only what it owns.  Halo pixels are computed by two or
+// more tiles from the same inputs with the same formula, i.e. identically.  Arithmetic as in resize_kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTileThreads = 256;
+#ifdef PT_TRACE
+__device__ long long g_pt_trace[4][20];
+#define PT(i) do { if (tid == 0 && blockIdx.x % 48 == 0 && blockIdx.x / 48 < 4) g_pt_trace[blockIdx.x / 48][i] = clock64(); } while (0)
+extern "C" int vsg_debug_pt_trace(long long *out) { return (int)cudaMemcpyFromSymbol(out, g_pt_trace, sizeof(g_pt_trace)); }
+#else
+#define PT(i) do { } while (0)
+#endif
+
+__global__ void __launch_bounds__(kTileThreads) pyramid_tile_kernel(FrameGeom g, const PyrTile *__restrict__ tiles,
+                                                                    const uint8_t *__restrict__ lvl0_base, int lvl0_pitch,
+                                                                    int64_t lvl0_stride, uint8_t *__restrict__ pyr, int buf_bytes) {
+    extern __shared__ __align__(16) uint8_t tile_smem[];
+    __shared__ PyrTile T;
+    pdl_launch_dependents();
+    pdl_wait();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, frame = blockIdx.y;
+    PT(0);
+    if (tid < (int)(sizeof(PyrTile) / 4))
+        reinterpret_cast<uint32_t *>(&T)[tid] = __ldg(reinterpret_cast<const uint32_t *>(tiles + blockIdx.x) + tid);
+    __syncthreads();
+    PT(1);
+    short4 *tab = reinterpret_cast<short4 *>(tile_smem + 2 * buf_bytes);
+    // every table entry the tile will use (x entries of a level, then its y entries) and the level-0 region in ONE round
+    // trip: all loads are issued before the first store (a region is at most kTileThreads wide and high — checked on the host)
+    {
+        short4 vx[kMaxLevels - 1], vy[kMaxLevels - 1];
+#pragma unroll
+        for (int l = 1; l < kMaxLevels; ++l) {
+            if (l < g.nlevels) {
+                const PyrTileBox R = T.region[l];
+                if (tid <= R.x1 - R.x0) vx[l - 1] = __ldg(&g.lv[l].xtab[R.x0 + tid]);
+                if (tid <= R.y1 - R.y0) vy[l - 1] = __ldg(&g.lv[l].ytab[R.y0 + tid]);
+            }
+        }
+        const PyrTileBox R0 = T.region[0];
+        const int rw0 = R0.x1 - R0.x0 + 1, area0 = rw0 * (R0.y1 - R0.y0 + 1);
+        const uint32_t rcp0 = T.rcp_w[0];
+        const uint8_t *src = lvl0_base + (int64_t)frame * lvl0_stride + (int64_t)R0.y0 * lvl0_pitch + R0.x0;
+        for (int base = 0; base < area0; base += 16 * kTileThreads) {       // 16 loads in flight per thread
+            uint8_t px[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int i = base + k * kTileThreads + tid;
+                const int r = (int)__umulhi((uint32_t)i, rcp0);
+                px[k] = i < area0 ? __ldg(src + (int64_t)r * lvl0_pitch + (i - r * rw0)) : 0;
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int i = base + k * kTileThreads + tid;
+                if (i < area0) tile_smem[i] = px[k];
+            }
+        }
+        int off = 0;
+#pragma unroll
+        for (int l = 1; l < kMaxLevels; ++l) {
+            if (l < g.nlevels) {
+                const PyrTileBox R = T.region[l];
+                const int rw = R.x1 - R.x0 + 1, rh = R.y1 - R.y0 + 1;
+                if (tid < rw) tab[off + tid] = vx[l - 1];
+                if (tid < rh) tab[off + rw + tid] = vy[l - 1];
+                off += rw + rh;
+            }
+        }
+    }
+    __syncthreads();
+    PT(2);
+    int off = 0;
+    for (int l = 1; l < g.nlevels; ++l) {
+        const PyrTileBox S = T.region[l - 1], R = T.region[l], O = T.owned[l];
+        const int sw = S.x1 - S.x0 + 1, rw = R.x1 - R.x0 + 1, rh = R.y1 - R.y0 + 1;
+        const uint8_t *__restrict__ src = tile_smem + ((l - 1) & 1) * buf_bytes - (S.y0 * sw + S.x0);   // indexable by plane coordinates
+        uint8_t *__restrict__ dst = tile_smem + (l & 1) * buf_bytes;
+        const short4 *__restrict__ tx = tab + off, *__restrict__ ty = tx + rw;
+        const LevelGeom &L = g.lv[l];
+        uint8_t *out = pyr + L.plane_offset + (int64_t)frame * L.plane_stride;
+        const uint32_t rcp = T.rcp_w[l];
+        const int area = rw * rh;
+        for (int base = 0; base < area; base += 4 * kTileThreads) {         // four independent pixels per thread and pass
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = base + k * kTileThreads + tid;
+                if (i < area) {
+                    const int r = (int)__umulhi((uint32_t)i, rcp), c = i - r * rw;
+                    const short4 xt = tx[c], yt = ty[r];
+                    const uint8_t *s0 = src + yt.x * sw, *s1 = src + yt.y * sw;
+                    const uint32_t ga = (uint32_t)(s0[xt.x] * xt.z + s0[xt.y] * xt.w) >> 4;
+                    const uint32_t gb = (uint32_t)(s1[xt.x] * xt.z + s1[xt.y] * xt.w) >> 4;
+                    const uint32_t v = (__umulhi((uint32_t)yt.z << 16, ga) + __umulhi((uint32_t)yt.w << 16, gb) + 2u) >> 2;
+                    dst[i] = (uint8_t)v;
+                    const int x = R.x0 + c, y = R.y0 + r;
+                    if (x >= O.x0 && x <= O.x1 && y >= O.y0 && y <= O.y1) out[(int64_t)y * L.pitch + x] = (uint8_t)v;
+                }
+            }
+        }
+        off += rw + rh;
+        __syncthreads();
+        PT(2 + l);
+    }
+}
+
+void launch_pyramid_tiles(const FrameGeom &g, const PyrTile *tiles, int ntiles, int buf_bytes, size_t smem, const uint8_t *lvl0_base,
+                          int lvl0_pitch, int64_t lvl0_stride, uint8_t *pyr, int nframes, cudaStream_t s) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(pyramid_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    launch_kernel(pyramid_tile_kernel, dim3(ntiles, nframes), dim3(kTileThreads), smem, s, true, g, tiles, lvl0_base, lvl0_pitch,
+                  lvl0_stride, pyr, buf_bytes);
+    count_launch();
+}
+
 void launch_resize_level(const FrameGeom &g, int level, const uint8_t *src_base, int src_pitch, int64_t src_stride,
                          uint8_t *pyr, int nframes, cudaStream_t s) {
     const LevelGeom &P = g.lv[level - 1];

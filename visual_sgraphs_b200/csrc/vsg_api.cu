@@ -95,6 +95,9 @@ struct vsg_extractor {
 
     Cell *cells_d = nullptr;
     short4 *tabs_d = nullptr;
+    PyrTile *pyr_tiles_d = nullptr;        // one-launch pyramid for small batches (pyramid.cu); nullptr = not available
+    int pyr_ntiles = 0, pyr_tile_buf = 0;
+    size_t pyr_tile_smem = 0;
     uint8_t *pyr = nullptr, *blur = nullptr;
     Cand *cand = nullptr;
     unsigned short *node_of = nullptr;
@@ -141,13 +144,13 @@ struct vsg_extractor {
     bool results_on_handle = false;    // kps_d / desc_d / n_d hold the last call's results (host-pointer API)
 
     void free_shape() {
-        cudaFree(cells_d); cudaFree(tabs_d); cudaFree(pyr); cudaFree(blur); cudaFree(cand); cudaFree(node_of);
+        cudaFree(cells_d); cudaFree(tabs_d); cudaFree(pyr_tiles_d); cudaFree(pyr); cudaFree(blur); cudaFree(cand); cudaFree(node_of);
         cudaFree(cand_count); cudaFree(level_kps); cudaFree(level_kp_count); cudaFree(slot); cudaFree(out_block_d);
         cudaFree(color_d);
         color_d = nullptr; color_bytes = 0;
         cudaFreeHost(out_block_h);
         out_block_d = out_block_h = nullptr; out_block_bytes = 0;
-        cells_d = nullptr; tabs_d = nullptr; pyr = blur = nullptr; cand = nullptr; node_of = nullptr;
+        cells_d = nullptr; tabs_d = nullptr; pyr_tiles_d = nullptr; pyr_ntiles = 0; pyr = blur = nullptr; cand = nullptr; node_of = nullptr;
         cand_count = nullptr; level_kps = nullptr; level_kp_count = nullptr; slot = nullptr; kps_d = nullptr;
         desc_d = nullptr; n_d = mono_d = nullptr; kps_h = nullptr; desc_h = nullptr; n_h = mono_h = nullptr;
         cur_w = cur_h = 0;
@@ -320,6 +323,45 @@ vsg_status configure_shape(vsg_extractor *ex, int w, int h) {
         g.lv[l].ytab = ex->tabs_d + toff;
         toff += yts[l].size();
     }
+    // tiles of the one-launch pyramid: a 12 x 12 partition of every level; going down from the top level, a tile's region
+    // is the bounding box of what it owns and of the taps of its region one level up
+    if (nl >= 2) {
+        const char *ev = getenv("VSG_PYR_TILES");
+        const int ntx = ev && atoi(ev) > 0 ? atoi(ev) : 12, nty = ntx;
+        std::vector<PyrTile> tiles((size_t)ntx * nty);
+        int buf = 0, ntab_max = 0, dim_max = 0;
+        for (int ty = 0; ty < nty; ++ty)
+            for (int tx = 0; tx < ntx; ++tx) {
+                PyrTile &t = tiles[(size_t)ty * ntx + tx];
+                int ntab_t = 0;
+                for (int l = nl - 1; l >= 0; --l) {
+                    const int W = g.lv[l].w, H = g.lv[l].h;
+                    PyrTileBox o{(short)(tx * W / ntx), (short)(ty * H / nty), (short)((tx + 1) * W / ntx - 1), (short)((ty + 1) * H / nty - 1)};
+                    PyrTileBox r = o;
+                    if (l < nl - 1) {
+                        const PyrTileBox &u = t.region[l + 1];
+                        const short nx0 = xts[l + 1][u.x0].x, nx1 = xts[l + 1][u.x1].y, ny0 = yts[l + 1][u.y0].x, ny1 = yts[l + 1][u.y1].y;
+                        if (l == 0) r = PyrTileBox{nx0, ny0, nx1, ny1};      // nothing is stored at level 0
+                        else r = PyrTileBox{std::min(o.x0, nx0), std::min(o.y0, ny0), std::max(o.x1, nx1), std::max(o.y1, ny1)};
+                    }
+                    t.owned[l] = o;
+                    t.region[l] = r;
+                    t.rcp_w[l] = (uint32_t)((0x100000000ull + (uint64_t)(r.x1 - r.x0)) / (uint64_t)(r.x1 - r.x0 + 1));
+                    buf = std::max(buf, (r.x1 - r.x0 + 1) * (r.y1 - r.y0 + 1));
+                    if (l > 0) dim_max = std::max(dim_max, std::max(r.x1 - r.x0 + 1, r.y1 - r.y0 + 1));
+                    if (l > 0) ntab_t += (r.x1 - r.x0 + 1) + (r.y1 - r.y0 + 1);
+                }
+                for (int l = nl; l < kMaxLevels; ++l) { t.owned[l] = t.region[l] = PyrTileBox{0, 0, -1, -1}; t.rcp_w[l] = 0; }
+                ntab_max = std::max(ntab_max, ntab_t);
+            }
+        ex->pyr_tile_buf = (int)align_up(buf, 16);
+        ex->pyr_tile_smem = 2 * (size_t)ex->pyr_tile_buf + (size_t)ntab_max * sizeof(short4);
+        if (ex->pyr_tile_smem <= 160 * 1024 && dim_max <= 256 && buf < 65536 && nl <= kMaxLevels && g.lv[nl - 1].w >= 2 * ntx && g.lv[nl - 1].h >= 2 * nty) {
+            CK(cudaMalloc(&ex->pyr_tiles_d, tiles.size() * sizeof(PyrTile)));
+            CK(cudaMemcpy(ex->pyr_tiles_d, tiles.data(), tiles.size() * sizeof(PyrTile), cudaMemcpyHostToDevice));
+            ex->pyr_ntiles = (int)tiles.size();
+        }
+    }
     CK(cudaMalloc(&ex->cells_d, std::max<size_t>(ex->cells_h.size(), 1) * sizeof(Cell)));
     CK(cudaMemcpy(ex->cells_d, ex->cells_h.data(), ex->cells_h.size() * sizeof(Cell), cudaMemcpyHostToDevice));
     CK(cudaMalloc(&ex->pyr, plane_off + 256));
@@ -359,6 +401,12 @@ vsg_status configure_shape(vsg_extractor *ex, int w, int h) {
 // The device pipeline for frames [f0, f0 + nframes) of the handle's scratch buffers, on stream `s`.  Level 0 of frame
 // f0 is at lvl0_base; the output pointers address frame f0 as well.  Chunks of one batch run this concurrently on
 // different streams: every per-frame array is addressed through a geometry whose offsets are shifted to frame f0.
+// VSG_PYR_TILE = n: batches of at most n frames build the pyramid in one launch (default 4; 0 = always level by level)
+static int pyr_tile_max_frames() {
+    const char *e = getenv("VSG_PYR_TILE");
+    return e ? atoi(e) : 4;
+}
+
 vsg_status run_pipeline(vsg_extractor *ex, cudaStream_t s, int f0, const uint8_t *lvl0_base, int lvl0_pitch,
                         int64_t lvl0_stride, int nframes, int lap_x0, int lap_x1, vsg_keypoint *kps_dev,
                         uint8_t *desc_dev, int out_cap, int *n_dev, int *mono_dev) {
@@ -387,10 +435,15 @@ vsg_status run_pipeline(vsg_extractor *ex, cudaStream_t s, int f0, const uint8_t
     }
 #define STAGE_MARK(k) do { if (ev) CK(cudaEventRecord(ev[k], s)); } while (0)
     STAGE_MARK(0);
-    for (int l = 1; l < g.nlevels; ++l) {                         // ComputePyramid (:1171-1195)
-        const LevelGeom &P = g.lv[l - 1];
-        if (l == 1) launch_resize_level(g, l, lvl0_base, lvl0_pitch, lvl0_stride, ex->pyr, nframes, s);
-        else launch_resize_level(g, l, ex->pyr + P.plane_offset, P.pitch, P.plane_stride, ex->pyr, nframes, s);
+    if (ex->pyr_tiles_d && nframes <= pyr_tile_max_frames()) {    // ComputePyramid (:1171-1195) in one launch
+        launch_pyramid_tiles(g, ex->pyr_tiles_d, ex->pyr_ntiles, ex->pyr_tile_buf, ex->pyr_tile_smem, lvl0_base, lvl0_pitch, lvl0_stride,
+                             ex->pyr, nframes, s);
+    } else {
+        for (int l = 1; l < g.nlevels; ++l) {                     // ... or level by level
+            const LevelGeom &P = g.lv[l - 1];
+            if (l == 1) launch_resize_level(g, l, lvl0_base, lvl0_pitch, lvl0_stride, ex->pyr, nframes, s);
+            else launch_resize_level(g, l, ex->pyr + P.plane_offset, P.pitch, P.plane_stride, ex->pyr, nframes, s);
+        }
     }
     STAGE_MARK(1);
     // FAST cells and the Gaussian blur share one grid (fast.cu) unless VSG_FUSE_FAST_BLUR=0

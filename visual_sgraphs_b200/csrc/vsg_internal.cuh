@@ -162,6 +162,16 @@ bool cuda_ok(cudaError_t e, const char *what);
 void count_launch(int n = 1);
 
 // --- kernel launchers (each file documents the reference lines it implements) ---
+// pyramid_tile_kernel (pyramid.cu): the whole pyramid of a few frames in ONE launch.  A tile owns a box of every level (the
+// boxes of a level partition its plane) and computes, level by level in shared memory, the slightly larger region the next
+// level's region needs; both boxes are inclusive and come from the host, which built the resize tables.
+struct PyrTileBox { short x0, y0, x1, y1; };
+struct PyrTile {
+    PyrTileBox region[kMaxLevels], owned[kMaxLevels];
+    uint32_t rcp_w[kMaxLevels];      // ceil(2^32 / region width): pixel index -> row by multiply-high
+};
+void launch_pyramid_tiles(const FrameGeom &g, const PyrTile *tiles, int ntiles, int buf_bytes, size_t smem, const uint8_t *lvl0_base,
+                          int lvl0_pitch, int64_t lvl0_stride, uint8_t *pyr, int nframes, cudaStream_t s);
 void launch_resize_level(const FrameGeom &g, int level, const uint8_t *src_base, int src_pitch, int64_t src_stride,
                          uint8_t *pyr, int nframes, cudaStream_t s);
 // cv::cvtColor(..., COLOR_{RGB,BGR,RGBA,BGRA}2GRAY) of `nframes` device frames into 8-bit planes (src 4-byte aligned)
