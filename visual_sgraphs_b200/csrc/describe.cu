@@ -115,7 +115,8 @@ __global__ void __launch_bounds__(256, VSG_DESC_MINB) describe_kernel(FrameGeom 
                                                        const LevelKp *__restrict__ level_kps,
                                                        const int *__restrict__ level_kp_count,
                                                        const int *__restrict__ slot, vsg_keypoint *__restrict__ kps_out,
-                                                       uint8_t *__restrict__ desc_out, int out_cap) {
+                                                       uint8_t *__restrict__ desc_out, int out_cap, int *__restrict__ n_out,
+                                                       int *__restrict__ mono_out) {
     __shared__ int s_x[kDescKp], s_y[kDescKp], s_level[kDescKp], s_row[kDescKp], s_score[kDescKp];
     __shared__ int s_m01[kDescKp], s_m10[kDescKp];
     __shared__ float s_angle[kDescKp], s_cos[kDescKp], s_sin[kDescKp];
@@ -136,11 +137,18 @@ __global__ void __launch_bounds__(256, VSG_DESC_MINB) describe_kernel(FrameGeom 
         int row = -1;
         if (level < g.nlevels) {
             const LevelKp kp = level_kps[(int64_t)frame * g.kp_total + g.lv[level].kp_offset + (i - off)];
-            row = slot[(int64_t)frame * g.kp_total + i];
+            // no lapping area (monocular / rectified stereo): output order = level-major order (:1113-1168), no slot kernel
+            row = slot ? slot[(int64_t)frame * g.kp_total + i] : (i < out_cap ? i : -1);
             s_x[tid] = kp.x; s_y[tid] = kp.y; s_score[tid] = kp.score;
         }
         s_level[tid] = level;
         s_row[tid] = row;
+        if (!slot && tid == 0 && blockIdx.x == 0) {          // ... and the counts the slot kernel would have written
+            int total = 0;
+            for (int l = 0; l < g.nlevels; ++l) total += level_kp_count[frame * g.nlevels + l];
+            n_out[frame] = total;
+            mono_out[frame] = total;
+        }
     }
     __syncthreads();
     if (s_row[0] < 0 && s_level[0] >= g.nlevels) return;   // whole CTA is past the last keypoint
@@ -267,15 +275,19 @@ void launch_describe(const FrameGeom &g, const uint8_t *lvl0_base, int lvl0_pitc
                      const uint8_t *pyr, const uint8_t *blur, const LevelKp *level_kps, const int *level_kp_count,
                      int lap_x0, int lap_x1, vsg_keypoint *kps_out, uint8_t *desc_out, int out_cap, int *n_out,
                      int *mono_out, int *slot_scratch, int nframes, cudaStream_t s) {
-    launch_kernel(slot_kernel, dim3(nframes), dim3(256), 0, s, true, g, level_kps, level_kp_count, lap_x0, lap_x1, out_cap,
-                  n_out, mono_out, slot_scratch);
+    // keypoints keep 16 pixels to the left border, so an empty lapping area [0, 0] holds none of them
+    const bool lapping = !(lap_x0 == 0 && lap_x1 == 0);
+    if (lapping)
+        launch_kernel(slot_kernel, dim3(nframes), dim3(256), 0, s, true, g, level_kps, level_kp_count, lap_x0, lap_x1, out_cap,
+                      n_out, mono_out, slot_scratch);
+    const int *slot = lapping ? slot_scratch : nullptr;
     if (nframes <= 8)
         launch_kernel(describe_kernel<16>, dim3((g.kp_total + 15) / 16, nframes), dim3(256), 0, s, true, g, lvl0_base, lvl0_pitch,
-                      lvl0_stride, pyr, blur, level_kps, level_kp_count, (const int *)slot_scratch, kps_out, desc_out, out_cap);
+                      lvl0_stride, pyr, blur, level_kps, level_kp_count, slot, kps_out, desc_out, out_cap, n_out, mono_out);
     else
         launch_kernel(describe_kernel<64>, dim3((g.kp_total + 63) / 64, nframes), dim3(256), 0, s, true, g, lvl0_base, lvl0_pitch,
-                      lvl0_stride, pyr, blur, level_kps, level_kp_count, (const int *)slot_scratch, kps_out, desc_out, out_cap);
-    count_launch(2);
+                      lvl0_stride, pyr, blur, level_kps, level_kp_count, slot, kps_out, desc_out, out_cap, n_out, mono_out);
+    count_launch(lapping ? 2 : 1);
 }
 
 }  // namespace vsg
