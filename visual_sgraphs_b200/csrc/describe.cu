@@ -254,6 +254,7 @@ __global__ void __launch_bounds__(256, VSG_DESC_MINB) describe_kernel(FrameGeom 
         if (out_row < 0) continue;
         const LevelGeom &L = g.lv[s_level[k]];
         const float a = s_cos[k], b = s_sin[k];
+        const int bpitch = L.pitch;
         const uint8_t *bc = blur + L.plane_offset + (int64_t)frame * L.plane_stride + (int64_t)s_y[k] * L.pitch + s_x[k];
         int val = 0;
 #pragma unroll
@@ -263,8 +264,8 @@ __global__ void __launch_bounds__(256, VSG_DESC_MINB) describe_kernel(FrameGeom 
             const int rx0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
             const int ry1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
             const int rx1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-            const int t0 = __ldg(bc + ry0 * L.pitch + rx0);
-            const int t1 = __ldg(bc + ry1 * L.pitch + rx1);
+            const int t0 = __ldg(bc + (ry0 * bpitch + rx0));       // one 32-bit offset, one widening add
+            const int t1 = __ldg(bc + (ry1 * bpitch + rx1));
             val |= (t0 < t1) << bit;
         }
         desc_out[((int64_t)frame * out_cap + out_row) * 32 + lane] = (uint8_t)val;
