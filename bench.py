@@ -971,6 +971,11 @@ def main():
                          "note": "FAST is HBM-bound by bytes but ALU-pipe bound in practice: its packed min/max alone need 1.13 ms per 512 frames "
                                  "at 100 % of the pipe (`pipes` = the committed ncu capture; DESIGN.md section 4)"},
             "stages_ms_per_step": {k: v / max(runs, 1) for k, v in stage_ms.items()},
+            # every stage against the same byte roofline (SURVEY 8(d) bytes x frames / its CUDA-event time)
+            "stages_hbm": {k: {"kernel": kernel_of[k], "algorithmic_bytes_per_frame": stages_bytes[k],
+                               "achieved_gbs": stages_bytes[k] * B / (stage_ms[k] / max(runs, 1) * 1e-3) / 1e9,
+                               "frac": stages_bytes[k] * B / (stage_ms[k] / max(runs, 1) * 1e-3) / 1e9 / peak}
+                           for k in stage_ms if stages_bytes.get(k, 0) > 0 and stage_ms[k] > 0 and runs},
             "pipeline_hbm": {"algorithmic_bytes_per_frame": b_frame,
                              "achieved_gbs": b_frame * B * K / (elapsed_ms * 1e-3) / 1e9,
                              "frac": b_frame * B * K / (elapsed_ms * 1e-3) / 1e9 / peak},
