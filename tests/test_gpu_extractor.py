@@ -428,3 +428,32 @@ def test_one_launch_pyramid_matches_the_level_by_level_kernels(monkeypatch, shap
                 raise AssertionError("frame %d level %d: %d pixels differ, first %s" % (f, l, len(bad), bad[0]))
     for a, b in zip(got, want):
         assert a[0] == b[0] and a[1].tobytes() == b[1].tobytes() and np.array_equal(a[2], b[2])
+
+
+@pytest.mark.parametrize("shape", [(640, 480, 8, 1.2), (752, 480, 8, 1.2), (1241, 376, 8, 1.2), (1280, 720, 8, 1.2), (640, 480, 5, 1.5),
+                                   (644, 484, 10, 1.1)])
+def test_tma_staged_resize_matches_the_register_kernel(monkeypatch, shape):
+    """VSG_RESIZE_TMA: large batches resize through resize_tma_kernel (csrc/resize_tma.cu: the tile's source window staged by one
+    cp.async.bulk.tensor, every source row interpolated once).  Planes and results must equal resize_kernel's
+    (ORBextractor::ComputePyramid, ORBextractor.cc:1171-1195); scale factors whose windows exceed the box fall back."""
+    from visual_sgraphs_b200.extractor import ORBextractor
+    w, h, nlev, sf = shape
+    nf = 5
+    frames = np.stack([synth_frame(950 + i, w, h) for i in range(nf)])
+    monkeypatch.setenv("VSG_PYR_TILE", "0")
+    monkeypatch.setenv("VSG_RESIZE_TMA", "0")
+    ex0 = ORBextractor(1000, sf, nlev, 20, 7, max_batch=nf)
+    want = ex0.extract_batch(frames)
+    planes0 = [[ex0.pyramid_level(l, f) for l in range(nlev)] for f in range(nf)]
+    monkeypatch.setenv("VSG_RESIZE_TMA", "1")
+    ex1 = ORBextractor(1000, sf, nlev, 20, 7, max_batch=nf)
+    got = ex1.extract_batch(frames)
+    for f in range(nf):
+        for l in range(nlev):
+            p1 = ex1.pyramid_level(l, f)
+            if not np.array_equal(p1, planes0[f][l]):
+                bad = np.argwhere(p1 != planes0[f][l])
+                raise AssertionError("frame %d level %d: %d pixels differ, first %s (%d vs %d)" % (
+                    f, l, len(bad), bad[0], p1[tuple(bad[0])], planes0[f][l][tuple(bad[0])]))
+    for a, b in zip(got, want):
+        assert a[0] == b[0] and a[1].tobytes() == b[1].tobytes() and np.array_equal(a[2], b[2])

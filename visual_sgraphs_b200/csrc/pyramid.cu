@@ -237,6 +237,7 @@ void launch_pyramid_tiles(const FrameGeom &g, const PyrTile *tiles, int ntiles, 
 
 void launch_resize_level(const FrameGeom &g, int level, const uint8_t *src_base, int src_pitch, int64_t src_stride,
                          uint8_t *pyr, int nframes, cudaStream_t s) {
+    if (launch_resize_level_tma(g, level, src_base, src_pitch, src_stride, pyr, nframes, s)) return;
     const LevelGeom &P = g.lv[level - 1];
     // one past the last byte of the source batch (our own planes have slack behind them, but stay exact)
     const uint8_t *src_end = src_base + (int64_t)(nframes - 1) * src_stride + (int64_t)(P.h - 1) * src_pitch + P.w;

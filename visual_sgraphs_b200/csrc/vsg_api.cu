@@ -298,8 +298,11 @@ vsg_status configure_shape(vsg_extractor *ex, int w, int h) {
         ex->max_nodes = std::max(ex->max_nodes, L.kp_cap + 4);
         L.scale = ex->scale[l];
         L.kp_size = (float)(int)(kPatch * ex->scale[l]);                                    // :884
-        if (l > 0)
+        L.resize_tma_ok = 0;
+        if (l > 0) {
             build_resize_tables(g.lv[l - 1].w, g.lv[l - 1].h, L.w, L.h, (int)align_up(L.w, 4), xts[l], yts[l]);
+            L.resize_tma_ok = resize_tma_fits(xts[l], yts[l], L.w, L.h) ? 1 : 0;
+        }
     }
     g.ncells = (int)ex->cells_h.size();
     for (int l = nl; l < kMaxLevels; ++l) g.lv[l].cell_begin = 0x7fffffff;   // fast.cu finds a cell's level by counting begins <= cell

@@ -43,6 +43,7 @@ struct LevelGeom {
     float scale;           // mvScaleFactor[level]
     float kp_size;         // (float)(int)(PATCH_SIZE * scale) (:884)
     // resize tables (device pointers) for building this level from the previous one
+    int resize_tma_ok;     // every 128 x 32 tile's source window fits resize_tma_kernel's box (resize_tma.cu)
     const short4 *xtab;    // per dst x: {sx0, sx1, a0, a1}
     const short4 *ytab;    // per dst y: {sy0, sy1, b0, b1}
 };
@@ -172,6 +173,9 @@ struct PyrTile {
 };
 void launch_pyramid_tiles(const FrameGeom &g, const PyrTile *tiles, int ntiles, int buf_bytes, size_t smem, const uint8_t *lvl0_base,
                           int lvl0_pitch, int64_t lvl0_stride, uint8_t *pyr, int nframes, cudaStream_t s);
+bool launch_resize_level_tma(const FrameGeom &g, int level, const uint8_t *src_base, int src_pitch, int64_t src_stride, uint8_t *pyr,
+                             int nframes, cudaStream_t s);
+bool resize_tma_fits(const std::vector<short4> &xt, const std::vector<short4> &yt, int dw, int dh);
 void launch_resize_level(const FrameGeom &g, int level, const uint8_t *src_base, int src_pitch, int64_t src_stride,
                          uint8_t *pyr, int nframes, cudaStream_t s);
 // cv::cvtColor(..., COLOR_{RGB,BGR,RGBA,BGRA}2GRAY) of `nframes` device frames into 8-bit planes (src 4-byte aligned)
