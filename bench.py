@@ -642,11 +642,15 @@ def matching_methods_extras(device):
     def same(a, b):
         return all(np.array_equal(np.asarray(x), np.asarray(y)) for x, y in zip(a, b))
 
-    def row(name, gpu_fn, cpu_fn):
+    def row(name, gpu_fn, cpu_fn, reuse_fn=None):
         g_us, g = timed(gpu_fn)
         c_us, c = timed(cpu_fn)
         assert same(g, c), name
         out[name] = {"gpu_us": round(g_us, 1), "cpu_us": round(c_us, 1), "gpu_over_cpu": round(g_us / c_us, 2), "nmatches": int(g[0])}
+        if reuse_fn is not None:      # the searched frame uploaded once (vsg_frame_create) and reused, as one Track() could
+            r_us, r = timed(reuse_fn)
+            assert same(r, c), name
+            out[name]["gpu_us_frame_reused"] = round(r_us, 1)
 
     f32 = lambda v: float(np.float32(v))  # noqa: E731
     _, sigma2, inv_sigma2 = sc.sigma_tables()
@@ -656,18 +660,22 @@ def matching_methods_extras(device):
     m = ORBmatcher(0.8, True, device=device)
     row("SearchByProjection(F, vpMapPoints) [%d points]" % len(pts),
         lambda: m.SearchByProjectionMap(m.frame(fd), occ, pts, desc, 3.0, False, 40.0),
-        lambda: orc.search_by_projection_map(fd.view, occ, pts, desc, 3.0, False, 40.0, f32(0.8)))
+        lambda: orc.search_by_projection_map(fd.view, occ, pts, desc, 3.0, False, 40.0, f32(0.8)),
+        (lambda fr: lambda: m.SearchByProjectionMap(fr, occ, pts, desc, 3.0, False, 40.0))(m.frame(fd)))
     m.close()
     # SearchByProjection(Cur, Last)
     m = ORBmatcher(0.9, True, device=device)
     ppts, pdesc, pocc = sc.proj_points(fd, kb, db, (9, 5), 4)
+    fr_fd = m.frame(fd)
     row("SearchByProjection(Cur, Last)", lambda: m.SearchByProjectionLast(m.frame(fd), pocc, ppts, pdesc, 15.0, 0),
-        lambda: orc.search_by_projection_last(fd.view, pocc, ppts, pdesc, 15.0, 0, True))
+        lambda: orc.search_by_projection_last(fd.view, pocc, ppts, pdesc, 15.0, 0, True),
+        lambda: m.SearchByProjectionLast(fr_fd, pocc, ppts, pdesc, 15.0, 0))
     # SearchByProjection(Cur, KF, sAlreadyFound)
     spts = sc.search_points(kb, (9, 5), 3)
     socc = (rng.random(fd.n) < 0.1).astype(np.uint8)
     row("SearchByProjection(Cur, KF, sAlreadyFound)", lambda: m.SearchByProjectionReloc(m.frame(fd), socc, spts, db, 10.0, 100),
-        lambda: orc.search_by_projection_reloc(fd.view, socc, spts, db, 10.0, 100, True))
+        lambda: orc.search_by_projection_reloc(fd.view, socc, spts, db, 10.0, 100, True),
+        lambda: m.SearchByProjectionReloc(fr_fd, socc, spts, db, 10.0, 100))
     # SearchForInitialization (mpIniORBextractor-sized frames)
     ia, ida, ib, idb = sc.two_frames(orc, nfeat=2000)
     f1, f2 = sc.frame_data(ia, ida), sc.frame_data(ib, idb)
