@@ -422,10 +422,17 @@ void launch_octree(const FrameGeom &g, const Cand *cand, const int *cand_count, 
     // sort_buf (8 B), split (4 B)
     const size_t smem = (size_t)cap * (12 + 12 + 16 + 8 + 2 + 2 + 2 + 2 + 8 + 4) + 64;
     if (smem > 48 * 1024) cudaFuncSetAttribute(octree_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    // (a 1024-thread variant for single frames was measured: the passes over the keys get faster, the block-wide scans
-    // and barriers slower — 69.7 us vs 67.0 us for one 640x480 frame — so every batch size uses 8-warp CTAs)
-    launch_kernel(octree_kernel<256>, dim3(g.nlevels, nframes), dim3(256), smem, s, true, g, cand, cand_count, node_of,
-                  level_kps, level_kp_count, cap);
+    // A few frames: one CTA per SM at most, and a CTA of 8 warps leaves three quarters of the SM's issue slots empty while it
+    // walks its keys — 16 warps: 51 -> 44 us for one 640x480 frame (24 warps: 46, 32 warps: the block-wide scans and barriers
+    // cost more than the key passes gain).  Large batches fill the SMs with several 8-warp CTAs instead.
+    if (nframes <= 8) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(octree_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        launch_kernel(octree_kernel<512>, dim3(g.nlevels, nframes), dim3(512), smem, s, true, g, cand, cand_count, node_of,
+                      level_kps, level_kp_count, cap);
+    } else {
+        launch_kernel(octree_kernel<256>, dim3(g.nlevels, nframes), dim3(256), smem, s, true, g, cand, cand_count, node_of,
+                      level_kps, level_kp_count, cap);
+    }
     count_launch();
 }
 
