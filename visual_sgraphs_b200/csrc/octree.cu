@@ -44,15 +44,17 @@ struct ONode {
     int count;             // vKeys.size(); bNoMore <=> count == 1
 };
 
-// Everything a key pass needs to know about a node in one shared-memory word: the split point (15 bits each) and, in
-// bit 31, whether the node is divided (in the histogram pass: whether it holds more than one key).
+// Everything a key pass needs to know about a node in one shared-memory word: the split point in the keys' own (absolute
+// level) coordinates, x in bits 0-14 and y in bits 16-30 — the layout of a key word x | y << 16 — and, in bit 31, whether
+// the node is divided (in the histogram pass: whether it holds more than one key).
 constexpr uint32_t kDivided = 0x80000000u;
 __device__ __forceinline__ uint32_t split_word(const ONode &n) {
-    const int mx = n.x0 + ((n.x1 - n.x0 + 1) >> 1), my = n.y0 + ((n.y1 - n.y0 + 1) >> 1);
-    return (uint32_t)mx | ((uint32_t)my << 15) | (n.count > 1 ? kDivided : 0u);
+    const int mx = n.x0 + ((n.x1 - n.x0 + 1) >> 1) + kBorderMin, my = n.y0 + ((n.y1 - n.y0 + 1) >> 1) + kBorderMin;
+    return (uint32_t)mx | ((uint32_t)my << 16) | (n.count > 1 ? kDivided : 0u);
 }
-__device__ __forceinline__ int quadrant(uint32_t split, int kx, int ky) {
-    return (kx < (int)(split & 0x7FFFu) ? 0 : 1) + (ky < (int)((split >> 15) & 0x7FFFu) ? 0 : 2);
+// child of a key (:498-520: x < midpoint -> left, y < midpoint -> top): 0 .. 3 in n1 .. n4 order
+__device__ __forceinline__ int quadrant(uint32_t split, uint32_t xy) {
+    return ((xy & 0xFFFFu) >= (split & 0x7FFFu) ? 1 : 0) + ((xy >> 16) >= ((split >> 16) & 0x7FFFu) ? 2 : 0);
 }
 
 __device__ __forceinline__ ONode child_of(const ONode &n, int q, int count) {
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(kThreads) octree_kernel(FrameGeom g, const Can
                 if (nd[u] < 0) continue;
                 const uint32_t w = split[nd[u]];
                 if (w & kDivided)
-                    atomicAdd(&cc[nd[u] * 4 + quadrant(w, (int)(xy[u] & 0xFFFF) - kBorderMin, (int)(xy[u] >> 16) - kBorderMin)], 1);
+                    atomicAdd(&cc[nd[u] * 4 + quadrant(w, xy[u])], 1);
             }
         }
         __syncthreads();
@@ -361,7 +363,7 @@ __global__ void __launch_bounds__(kThreads) octree_kernel(FrameGeom g, const Can
                 const int k = k0 + u * kThreads;
                 const uint32_t w = split[nd[u]];
                 if (w & kDivided)
-                    nof[k] = child_pos[nd[u] * 4 + quadrant(w, (int)(xy[u] & 0xFFFF) - kBorderMin, (int)(xy[u] >> 16) - kBorderMin)];
+                    nof[k] = child_pos[nd[u] * 4 + quadrant(w, xy[u])];
                 else
                     nof[k] = stay_pos[nd[u]];
             }
@@ -389,7 +391,7 @@ __global__ void __launch_bounds__(kThreads) octree_kernel(FrameGeom g, const Can
         const int node = nof[k];
         if ((unsigned)c.score + 1u != best_score[node]) continue;
         const int rx = c.x - kEdge, ry = c.y - kEdge;          // offset inside the FAST-able area
-        const int cx = rx / L.w_cell, cy = ry / L.h_cell;
+        const int cx = (int)__umulhi((uint32_t)rx, L.wcell_rcp), cy = (int)__umulhi((uint32_t)ry, L.hcell_rcp);   // rx / w_cell, ry / h_cell
         const unsigned order = ((unsigned)(cy * L.n_cols + cx) << 14) | ((unsigned)(ry - cy * L.h_cell) << 7) |
                                (unsigned)(rx - cx * L.w_cell);
         atomicMin(&best_order[node], order);

@@ -282,6 +282,8 @@ vsg_status configure_shape(vsg_extractor *ex, int w, int h) {
             return VSG_ERR_INVALID;
         }
         L.cols_rcp = (uint32_t)((0x100000000ull + (uint64_t)L.cols_eff - 1) / (uint64_t)std::max(L.cols_eff, 1));
+        L.wcell_rcp = L.w_cell > 1 ? (uint32_t)((0x100000000ull + (uint64_t)L.w_cell - 1) / (uint64_t)L.w_cell) : 0xFFFFFFFFu;
+        L.hcell_rcp = L.h_cell > 1 ? (uint32_t)((0x100000000ull + (uint64_t)L.h_cell - 1) / (uint64_t)L.h_cell) : 0xFFFFFFFFu;
         L.quota = ex->quota[l];
         L.n_ini = (int)std::round(static_cast<float>(max_bx - min_b) / (max_by - min_b));   // :566
         if (L.n_ini < 1) {

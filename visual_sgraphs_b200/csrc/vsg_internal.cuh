@@ -32,6 +32,7 @@ struct LevelGeom {
     int cell_begin, cell_count;  // slice of the flat cell table
     int cols_eff, rows_eff;      // the cells that survive the skip rules (:816,825) form this prefix rectangle
     uint32_t cols_rcp;           // ceil(2^32 / cols_eff): cell row = umulhi(cell index, cols_rcp)
+    uint32_t wcell_rcp, hcell_rcp;   // ceil(2^32 / w_cell), ceil(2^32 / h_cell): exact quotients for coordinates below 2^16
     // oct-tree
     int quota;             // mnFeaturesPerLevel[level]
     int n_ini;             // round(width/height) root nodes (:566)
