@@ -173,8 +173,10 @@ public:
     }
 };
 
+inline long unsigned int &NextFrameId() { static long unsigned int n = 0; return n; }
 class Frame {
 public:
+    long unsigned int mnId = NextFrameId()++;      // Frame.h:217 / KeyFrame.h:312 (copies keep it, like the reference's copy constructor)
     int N = 0;
     int Nleft = -1, Nright = -1;
     std::vector<cv::KeyPoint> mvKeys, mvKeysRight, mvKeysUn;

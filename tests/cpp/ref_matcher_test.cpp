@@ -336,6 +336,35 @@ int main(int argc, char **argv) {
             compare_worlds(P.r, P.s, what);
         }
 
+    // ---- one Track(): three searches on the SAME current frame — TrackWithMotionModel's search, its retry with twice the
+    // window after clearing the matches (Tracking.cc:2916-2935), then SearchLocalPoints' SearchByProjection(F, MPs).  The shim
+    // serves the second and third call from its per-thread frame cache; every call must still equal the reference's. ----
+    for (int two = 0; two < 2; ++two) {
+        Options o; o.seed = 25; o.two_cameras = two;
+        Pair P(ea, eb, o);
+        int got[2][3];
+        for (int k = 0; k < 2; ++k) {
+            World &w = k ? P.s : P.r;
+            std::mt19937 rng(7);
+            for (int i = 0; i < w.B.N; ++i) if (i % 9 != 0) w.B.mvpMapPoints[i] = nullptr;
+            const float th = two ? 12.f : 7.f;
+            if (k == 0) got[0][0] = RefMatcher(0.9f, true).SearchByProjection(w.B, w.A, th, false);
+            else { ShimMatcher m(0.9f, true); got[1][0] = m.SearchByProjection(w.B, w.A, th, false); }
+            std::fill(w.B.mvpMapPoints.begin(), w.B.mvpMapPoints.end(), static_cast<MapPoint *>(nullptr));
+            if (k == 0) got[0][1] = RefMatcher(0.9f, true).SearchByProjection(w.B, w.A, 2 * th, false);
+            else { ShimMatcher m(0.9f, true); got[1][1] = m.SearchByProjection(w.B, w.A, 2 * th, false); }
+            set_track_fields(w, w.B, rng, two);
+            std::vector<MapPoint *> vp = raw(w.mps, 0, w.nA);
+            std::shuffle(vp.begin(), vp.end(), rng);
+            if (k == 0) got[0][2] = RefMatcher(0.8f).SearchByProjection(w.B, vp, 3.f, true, 45.f);
+            else { ShimMatcher m(0.8f); got[1][2] = m.SearchByProjection(w.B, vp, 3.f, true, 45.f); }
+        }
+        char what[96]; std::snprintf(what, sizeof what, "one Track() on a cached frame two=%d", two);
+        report(what, got[0][0] + got[0][1] + got[0][2], got[1][0] + got[1][1] + got[1][2]);
+        for (int c = 0; c < 3; ++c) EXPECT(got[0][c] == got[1][c] && got[0][c] > 20, "%s: call %d: %d vs %d", what, c, got[0][c], got[1][c]);
+        compare_worlds(P.r, P.s, what);
+    }
+
     // ---- SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches)  :226-428 ----
     for (int two = 0; two < 2; ++two)
         for (int variant = 0; variant < 2; ++variant) {

@@ -136,7 +136,9 @@ struct MapPoint {
     void Replace(MapPoint *o) { bad = true; replaced_by = o; o->in_kf.insert(in_kf.begin(), in_kf.end()); o->obs += obs; }
     std::tuple<int, int> GetIndexInKeyFrame(const void *kf) const { auto it = index_in.find(kf); return std::make_tuple(it == index_in.end() ? -1 : it->second, -1); }
 };
+static long unsigned int g_next_frame_id = 0;
 struct Frame {
+    long unsigned int mnId = g_next_frame_id++;      // Frame.h:217 / KeyFrame.h:312: what the shim's frame cache keys on
     int N = 0, Nleft = -1;
     std::vector<cv::KeyPoint> mvKeys, mvKeysUn, mvKeysRight;
     std::vector<int> mvLeftToRightMatch, mvRightToLeftMatch;

@@ -5,6 +5,8 @@ prebuilt in the build container and travels to the GPU box; /root/reference is n
 Bars (BASELINE.json north_star): keypoint sets, order, positions, sizes, responses, octaves bit-exact; angles within
 1e-3 degrees; >= 99.9 % of descriptor bits — the tests also REPORT exact equality, which holds on every frame so far.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -119,6 +121,9 @@ def test_reference_orbmatcher_equals_shim_on_the_cuda_library(ref, tmp_path):
     pa, pb = str(tmp_path / "a.raw"), str(tmp_path / "b.raw")
     a.tofile(pa)
     b.tofile(pb)
-    out = subprocess.run([exe, pa, pb], capture_output=True, text=True, timeout=600)
+    out = subprocess.run([exe, pa, pb], capture_output=True, text=True, timeout=600, env=dict(os.environ, VSG_FRAME_CACHE_STATS="1"))
     assert out.returncode == 0, out.stdout[-4000:] + out.stderr[-2000:]
     assert "0 failed" in out.stdout
+    import re
+    m = re.search(r"vsg frame cache: (\d+) hits", out.stderr)       # the "one Track()" block reuses uploaded frames
+    assert m and int(m.group(1)) >= 6, out.stderr[-500:]

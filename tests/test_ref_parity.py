@@ -162,6 +162,13 @@ def test_reference_orbmatcher_equals_shim_on_the_oracle_port(ref, oracle, tmp_pa
     exe = ref.matcher_test_binary("cpu")
     assert exe, "oracle/_ref/ref_matcher_test_cpu was not built"
     pa, pb = _two_related_frames(tmp_path)
-    out = subprocess.run([exe, pa, pb], capture_output=True, text=True, timeout=600)
+    out = subprocess.run([exe, pa, pb], capture_output=True, text=True, timeout=600, env=dict(os.environ, VSG_FRAME_CACHE_STATS="1"))
     assert out.returncode == 0, out.stdout[-4000:] + out.stderr[-2000:]
     assert "0 failed" in out.stdout
+    # the "one Track()" block runs three searches per frame: the shim's frame cache must have served the repeats
+    import re
+    m = re.search(r"vsg frame cache: (\d+) hits, (\d+) uploads", out.stderr)
+    assert m and int(m.group(1)) >= 6, out.stderr[-500:]
+    # ... and switching it off changes nothing
+    off = subprocess.run([exe, pa, pb], capture_output=True, text=True, timeout=600, env=dict(os.environ, VSG_FRAME_CACHE="0"))
+    assert off.returncode == 0 and off.stdout == out.stdout

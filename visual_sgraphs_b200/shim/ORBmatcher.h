@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <set>
@@ -192,10 +193,76 @@ protected:
         v.scale_factors = out.scale.data();
         v.n_levels = (int)out.scale.size();
     }
-    struct FrameGuard {   // RAII for the uploaded frame
+    struct FrameGuard {   // RAII for an uploaded frame; a frame that lives in the thread's cache is only borrowed
         vsg_frame *h = nullptr;
-        ~FrameGuard() { vsg_frame_destroy(h); }
+        bool owned = true;
+        ~FrameGuard() { if (owned) vsg_frame_destroy(h); }
     };
+    // Uploaded frames are kept per calling thread: Tracking runs up to three projection searches on the same current frame,
+    // LocalMapping / LoopClosing several on the same keyframe, and what the searches read from a Frame / KeyFrame (mvKeysUn,
+    // mvKeys(Right), mDescriptors, mvuRight, the grid parameters) does not change after construction.  An entry is identified
+    // by the object's address, its mnId (Frame.h:217, KeyFrame.h:312 — a recycled address gets a new id), which of its feature
+    // lists was flattened, and the size / address of its descriptor matrix.  Types without mnId, and VSG_FRAME_CACHE=0, upload
+    // per call as before.
+    struct CacheEntry {
+        const void *obj = nullptr, *desc = nullptr;
+        unsigned long id = 0;
+        int kind = -1, n = 0;
+        unsigned long long stamp = 0;
+        Flat flat;
+        vsg_frame *h = nullptr;
+    };
+    struct FrameCache {
+        static constexpr int kEntries = 6;
+        CacheEntry e[kEntries];
+        unsigned long long clock = 0, hits = 0, misses = 0;
+        ~FrameCache() {
+            for (CacheEntry &c : e) vsg_frame_destroy(c.h);
+            if (std::getenv("VSG_FRAME_CACHE_STATS")) std::fprintf(stderr, "vsg frame cache: %llu hits, %llu uploads\n", hits, misses);
+        }
+    };
+    static FrameCache &Cache() { static thread_local FrameCache c; return c; }
+    static bool CacheEnabled() {
+        static const bool on = [] { const char *e = std::getenv("VSG_FRAME_CACHE"); return !e || std::atoi(e) != 0; }();
+        return on;
+    }
+    template <class T> static auto FrameIdOf(const T &f, int) -> decltype((unsigned long)f.mnId) { return (unsigned long)f.mnId; }
+    template <class T> static unsigned long FrameIdOf(const T &, long) { return 0; }
+    template <class T> static constexpr auto HasFrameId(int) -> decltype((void)std::declval<const T &>().mnId, true) { return true; }
+    template <class T> static constexpr bool HasFrameId(long) { return false; }
+    // Flatten (fill) + vsg_frame_create, or the cached result of an earlier call on the same object.  `kind` names the
+    // flattened feature list.  Returns the flat view to read; `guard.h` is the device frame.
+    template <class FrameT, class Fill>
+    static const Flat &Upload(const FrameT &F, int kind, Fill fill, Flat &local, FrameGuard &guard) {
+        if (HasFrameId<FrameT>(0) && CacheEnabled()) {
+            FrameCache &c = Cache();
+            const void *desc = F.mDescriptors.rows > 0 ? (const void *)F.mDescriptors.ptr(0) : nullptr;
+            const unsigned long id = FrameIdOf(F, 0);
+            CacheEntry *slot = &c.e[0];
+            for (CacheEntry &x : c.e) {
+                if (x.h && x.obj == (const void *)&F && x.id == id && x.kind == kind && x.n == F.mDescriptors.rows && x.desc == desc) {
+                    x.stamp = ++c.clock;
+                    ++c.hits;
+                    guard.h = x.h;
+                    guard.owned = false;
+                    return x.flat;
+                }
+                if (x.stamp < slot->stamp) slot = &x;
+            }
+            ++c.misses;
+            vsg_frame_destroy(slot->h);
+            slot->h = nullptr;
+            fill(slot->flat);
+            Check(vsg_frame_create(Workspace(), &slot->flat.view, &slot->h), "vsg_frame_create");
+            slot->obj = &F; slot->id = id; slot->kind = kind; slot->n = F.mDescriptors.rows; slot->desc = desc; slot->stamp = ++c.clock;
+            guard.h = slot->h;
+            guard.owned = false;
+            return slot->flat;
+        }
+        fill(local);
+        Check(vsg_frame_create(Workspace(), &local.view, &guard.h), "vsg_frame_create");
+        return local;
+    }
     template <class FV>
     static void FlattenFeatVec(const FV &fv, std::vector<int32_t> &nodes, std::vector<int32_t> &ptr, std::vector<int32_t> &idx,
                                size_t limit = (size_t)-1) {   // features >= limit are skipped (two-camera keyframes, :793-796)
@@ -264,12 +331,11 @@ protected:
         FlattenKeys(F, bRight ? F.mvKeysRight : F.mvKeys, nullptr, bRight ? nLeft : 0, u_right, out);
     }
     template <class FrameT>
-    void UploadCameras(const FrameT &F, Flat cam[2], FrameGuard fr[2]) {
-        for (int c = 0; c < 2; ++c) {
-            FlattenCamera(F, c == 1, F.Nleft, nullptr, cam[c]);
-            Check(vsg_frame_create(Workspace(), &cam[c].view, &fr[c].h), "vsg_frame_create");
-        }
+    void UploadCameras(const FrameT &F, Flat local[2], const Flat *cam[2], FrameGuard fr[2]) {
+        for (int c = 0; c < 2; ++c)
+            cam[c] = &Upload(F, 1 + c, [&](Flat &o) { FlattenCamera(F, c == 1, F.Nleft, nullptr, o); }, local[c], fr[c]);
     }
+    // kinds: 0 = Flatten (mvKeysUn), 1 / 2 = left / right camera, 3 / 4 = left / right camera with mvuRight
     // What the methods without two-camera code of their own search on (reloc / Sim3 projections, SearchBySim3,
     // Fuse(KF, Scw, ...)): Frame::GetFeaturesInArea / KeyFrame::GetFeaturesInArea with bRight == false walk the left
     // camera's grid and keypoints (mvKeys, Frame.cc:840-848, KeyFrame.cc:862-868) and the descriptor rows [0, Nleft).
@@ -292,9 +358,10 @@ template <class FrameT, class MapPointT>
 int ORBmatcher::SearchByProjectionTwoCameras(FrameT &F, const std::vector<MapPointT *> &vpMapPoints, const float th,
                                              const bool bFarPoints, const float thFarPoints) {
     const int nL = F.Nleft, nR = (int)F.mvKeysRight.size(), N = nL + nR, nMP = (int)vpMapPoints.size();
-    Flat cam[2];
+    Flat camLocal[2];
+    const Flat *cam[2];
     FrameGuard fr[2];
-    UploadCameras(F, cam, fr);
+    UploadCameras(F, camLocal, cam, fr);
     std::vector<uint8_t> occupied(N, 0);
     for (int i = 0; i < N; ++i)
         if (F.mvpMapPoints[i] && F.mvpMapPoints[i]->Observations() > 0) occupied[i] = 1;
@@ -335,10 +402,9 @@ template <class FrameT, class MapPointT>
 int ORBmatcher::SearchByProjection(FrameT &F, const std::vector<MapPointT *> &vpMapPoints, const float th,
                                    const bool bFarPoints, const float thFarPoints) {
     if (F.Nleft != -1) return SearchByProjectionTwoCameras(F, vpMapPoints, th, bFarPoints, thFarPoints);
-    Flat flat;
-    Flatten(F, flat);
+    Flat flatLocal;
     FrameGuard fr;
-    Check(vsg_frame_create(Workspace(), &flat.view, &fr.h), "vsg_frame_create");
+    const Flat &flat = Upload(F, 0, [&](Flat &o) { Flatten(F, o); }, flatLocal, fr);
     const int N = flat.view.n, nMP = (int)vpMapPoints.size();
     std::vector<uint8_t> occupied(N, 0);
     for (int i = 0; i < N; ++i)
@@ -371,14 +437,11 @@ int ORBmatcher::SearchByProjection(FrameT &F, const std::vector<MapPointT *> &vp
 template <class FrameT>
 int ORBmatcher::SearchByProjection(FrameT &CurrentFrame, const FrameT &LastFrame, const float th, const bool bMono) {
     const bool bTwoCameras = CurrentFrame.Nleft != -1;
-    Flat flat, cam[2];
+    Flat flatLocal, camLocal[2];
+    const Flat *cam[2] = {nullptr, nullptr}, *flatp = nullptr;
     FrameGuard fr, frc[2];
-    if (bTwoCameras) {
-        UploadCameras(CurrentFrame, cam, frc);
-    } else {
-        Flatten(CurrentFrame, flat);
-        Check(vsg_frame_create(Workspace(), &flat.view, &fr.h), "vsg_frame_create");
-    }
+    if (bTwoCameras) UploadCameras(CurrentFrame, camLocal, cam, frc);
+    else flatp = &Upload(CurrentFrame, 0, [&](Flat &o) { Flatten(CurrentFrame, o); }, flatLocal, fr);
     // pose arithmetic stays with the reference's Sophus / camera classes (:1677-1716)
     const auto Tcw = CurrentFrame.GetPose();
     const auto twc = Tcw.inverse().translation();
@@ -386,7 +449,7 @@ int ORBmatcher::SearchByProjection(FrameT &CurrentFrame, const FrameT &LastFrame
     const auto tlc = Tlw * twc;
     const bool bForward = tlc(2) > CurrentFrame.mb && !bMono;
     const bool bBackward = -tlc(2) > CurrentFrame.mb && !bMono;
-    const int nLast = LastFrame.N, N = bTwoCameras ? cam[0].view.n + cam[1].view.n : flat.view.n;
+    const int nLast = LastFrame.N, N = bTwoCameras ? cam[0]->view.n + cam[1]->view.n : flatp->view.n;
     std::vector<vsg_proj_point> pts(nLast), ptsR(bTwoCameras ? nLast : 0);
     std::vector<uint8_t> desc((size_t)nLast * 32, 0);
     for (int i = 0; i < nLast; ++i) {
@@ -477,11 +540,10 @@ int ORBmatcher::SearchByBoW(KeyFrameT *pKF, FrameT &F, std::vector<MapPointT *> 
 template <class FrameT>
 int ORBmatcher::SearchForInitialization(FrameT &F1, FrameT &F2, std::vector<cv::Point2f> &vbPrevMatched,
                                         std::vector<int> &vnMatches12, int windowSize) {
-    Flat f1, f2;
+    Flat f1, f2Local;
     Flatten(F1, f1);
-    Flatten(F2, f2);
     FrameGuard fr2;
-    Check(vsg_frame_create(Workspace(), &f2.view, &fr2.h), "vsg_frame_create");
+    const Flat &f2 = Upload(F2, 0, [&](Flat &o) { Flatten(F2, o); }, f2Local, fr2);
     static_assert(sizeof(cv::Point2f) == 2 * sizeof(float), "cv::Point2f layout");
     vnMatches12 = std::vector<int>(F1.mvKeysUn.size(), -1);
     int nmatches = 0;
@@ -495,10 +557,10 @@ int ORBmatcher::SearchForInitialization(FrameT &F1, FrameT &F2, std::vector<cv::
 template <class FrameT, class KeyFrameT, class MapPointT>
 int ORBmatcher::SearchByProjection(FrameT &CurrentFrame, KeyFrameT *pKF, const std::set<MapPointT *> &sAlreadyFound,
                                    const float th, const int ORBdist) {
-    Flat flat;
-    FlattenSearched(CurrentFrame, CurrentFrame.Nleft, flat);      // two-camera frames: the left camera (no code of its own, :1880-2000)
+    Flat flatLocal;      // two-camera frames: the left camera (no code of its own, :1880-2000)
     FrameGuard fr;
-    Check(vsg_frame_create(Workspace(), &flat.view, &fr.h), "vsg_frame_create");
+    const Flat &flat = Upload(CurrentFrame, CurrentFrame.Nleft != -1 ? 1 : 0,
+                              [&](Flat &o) { FlattenSearched(CurrentFrame, CurrentFrame.Nleft, o); }, flatLocal, fr);
     const auto Tcw = CurrentFrame.GetPose();
     const auto Ow = Tcw.inverse().translation();
     const std::vector<MapPointT *> vpMPs = pKF->GetMapPointMatches();
@@ -573,17 +635,18 @@ template <class KeyFrameT, class MapPointT>
 int ORBmatcher::Fuse(KeyFrameT *pKF, const std::vector<MapPointT *> &vpMapPoints, const float th, const bool bRight) {
     const bool bTwoCameras = pKF->NLeft != -1;
     if (bRight && !bTwoCameras) throw std::runtime_error("vsg ORBmatcher::Fuse: bRight needs a two-camera keyframe");
-    Flat flat;
-    if (bTwoCameras) {
-        // the camera searched: mvKeys / mvKeysRight with their descriptor rows and grid (KeyFrame::GetFeaturesInArea(...,
-        // bRight)); the stereo gate reads mvuRight[idx] with the camera-local index on both sides (:1266)
-        const int n = (int)(bRight ? pKF->mvKeysRight : pKF->mvKeys).size();
-        FlattenCamera(*pKF, bRight, pKF->NLeft, (int)pKF->mvuRight.size() >= n && n > 0 ? pKF->mvuRight.data() : nullptr, flat);
-    } else {
-        Flatten(*pKF, flat);
-    }
+    Flat flatLocal;
     FrameGuard fr;
-    Check(vsg_frame_create(Workspace(), &flat.view, &fr.h), "vsg_frame_create");
+    // two cameras: the camera searched — mvKeys / mvKeysRight with their descriptor rows and grid (KeyFrame::GetFeaturesInArea(...,
+    // bRight)); the stereo gate reads mvuRight[idx] with the camera-local index on both sides (:1266)
+    const Flat &flat = Upload(*pKF, bTwoCameras ? 3 + (bRight ? 1 : 0) : 0, [&](Flat &o) {
+        if (bTwoCameras) {
+            const int n = (int)(bRight ? pKF->mvKeysRight : pKF->mvKeys).size();
+            FlattenCamera(*pKF, bRight, pKF->NLeft, (int)pKF->mvuRight.size() >= n && n > 0 ? pKF->mvuRight.data() : nullptr, o);
+        } else {
+            Flatten(*pKF, o);
+        }
+    }, flatLocal, fr);
     const auto Tcw = bRight ? pKF->GetRightPose() : pKF->GetPose();                          // :1154-1165
     const auto Ow = bRight ? pKF->GetRightCameraCenter() : pKF->GetCameraCenter();
     auto *pCamera = bRight ? pKF->mpCamera2 : pKF->mpCamera;
@@ -650,10 +713,9 @@ int ORBmatcher::SearchByProjection(KeyFrameT *pKF, Sophus::Sim3<float> &Scw, con
                                    const std::vector<KeyFrameT *> &vpPointsKFs, std::vector<MapPointT *> &vpMatched,
                                    std::vector<KeyFrameT *> &vpMatchedKF, int th, float ratioHamming) {
     const bool bWithKFs = !vpPointsKFs.empty();
-    Flat flat;
-    FlattenSearched(*pKF, pKF->NLeft, flat);
+    Flat flatLocal;
     FrameGuard fr;
-    Check(vsg_frame_create(Workspace(), &flat.view, &fr.h), "vsg_frame_create");
+    const Flat &flat = Upload(*pKF, pKF->NLeft != -1 ? 1 : 0, [&](Flat &o) { FlattenSearched(*pKF, pKF->NLeft, o); }, flatLocal, fr);
     const float &fx = pKF->fx, &fy = pKF->fy, &cx = pKF->cx, &cy = pKF->cy;
     Sophus::SE3f Tcw = Sophus::SE3f(Scw.rotationMatrix(), Scw.translation() / Scw.scale());
     const auto Ow = Tcw.inverse().translation();
@@ -719,12 +781,10 @@ int ORBmatcher::SearchBySim3(KeyFrameT *pKF1, KeyFrameT *pKF2, std::vector<MapPo
             if (idx2 >= 0 && idx2 < N2) vbAlreadyMatched2[idx2] = true;
         }
     }
-    Flat f1, f2;                                   // N1 / N2 map point slots (both cameras) search the left cameras' features
-    FlattenSearched(*pKF1, pKF1->NLeft, f1);
-    FlattenSearched(*pKF2, pKF2->NLeft, f2);
+    Flat f1Local, f2Local;                         // N1 / N2 map point slots (both cameras) search the left cameras' features
     FrameGuard fr1, fr2;
-    Check(vsg_frame_create(Workspace(), &f1.view, &fr1.h), "vsg_frame_create");
-    Check(vsg_frame_create(Workspace(), &f2.view, &fr2.h), "vsg_frame_create");
+    const Flat &f1 = Upload(*pKF1, pKF1->NLeft != -1 ? 1 : 0, [&](Flat &o) { FlattenSearched(*pKF1, pKF1->NLeft, o); }, f1Local, fr1);
+    const Flat &f2 = Upload(*pKF2, pKF2->NLeft != -1 ? 1 : 0, [&](Flat &o) { FlattenSearched(*pKF2, pKF2->NLeft, o); }, f2Local, fr2);
     std::vector<vsg_search_point> pts1(N1), pts2(N2);
     std::vector<uint8_t> desc1((size_t)N1 * 32, 0), desc2((size_t)N2 * 32, 0);
     auto project = [&](const std::vector<MapPointT *> &vp, const std::vector<bool> &already, const Sophus::SE3f &Tw,
@@ -768,10 +828,9 @@ int ORBmatcher::SearchBySim3(KeyFrameT *pKF1, KeyFrameT *pKF2, std::vector<MapPo
 template <class KeyFrameT, class MapPointT>
 int ORBmatcher::Fuse(KeyFrameT *pKF, Sophus::Sim3f &Scw, const std::vector<MapPointT *> &vpPoints, float th,
                      std::vector<MapPointT *> &vpReplacePoint) {
-    Flat flat;
-    FlattenSearched(*pKF, pKF->NLeft, flat);
+    Flat flatLocal;
     FrameGuard fr;
-    Check(vsg_frame_create(Workspace(), &flat.view, &fr.h), "vsg_frame_create");
+    const Flat &flat = Upload(*pKF, pKF->NLeft != -1 ? 1 : 0, [&](Flat &o) { FlattenSearched(*pKF, pKF->NLeft, o); }, flatLocal, fr);
     Sophus::SE3f Tcw = Sophus::SE3f(Scw.rotationMatrix(), Scw.translation() / Scw.scale());
     const auto Ow = Tcw.inverse().translation();
     const std::set<MapPointT *> spAlreadyFound = pKF->GetMapPoints();
