@@ -201,11 +201,11 @@ protected:
     // Uploaded frames are kept per calling thread: Tracking runs up to three projection searches on the same current frame,
     // LocalMapping / LoopClosing several on the same keyframe, and what the searches read from a Frame / KeyFrame (mvKeysUn,
     // mvKeys(Right), mDescriptors, mvuRight, the grid parameters) does not change after construction.  An entry is identified
-    // by the object's address, its mnId (Frame.h:217, KeyFrame.h:312 — a recycled address gets a new id), which of its feature
+    // by the object's address and type, its mnId (Frame.h:217, KeyFrame.h:312 — a recycled address gets a new id), which of its feature
     // lists was flattened, and the size / address of its descriptor matrix.  Types without mnId, and VSG_FRAME_CACHE=0, upload
     // per call as before.
     struct CacheEntry {
-        const void *obj = nullptr, *desc = nullptr;
+        const void *obj = nullptr, *desc = nullptr, *type = nullptr;
         unsigned long id = 0;
         int kind = -1, n = 0;
         unsigned long long stamp = 0;
@@ -226,6 +226,7 @@ protected:
         static const bool on = [] { const char *e = std::getenv("VSG_FRAME_CACHE"); return !e || std::atoi(e) != 0; }();
         return on;
     }
+    template <class T> static const void *TypeKey() { static const char k = 0; return &k; }   // Frame and KeyFrame count mnId separately
     template <class T> static auto FrameIdOf(const T &f, int) -> decltype((unsigned long)f.mnId) { return (unsigned long)f.mnId; }
     template <class T> static unsigned long FrameIdOf(const T &, long) { return 0; }
     template <class T> static constexpr auto HasFrameId(int) -> decltype((void)std::declval<const T &>().mnId, true) { return true; }
@@ -240,7 +241,8 @@ protected:
             const unsigned long id = FrameIdOf(F, 0);
             CacheEntry *slot = &c.e[0];
             for (CacheEntry &x : c.e) {
-                if (x.h && x.obj == (const void *)&F && x.id == id && x.kind == kind && x.n == F.mDescriptors.rows && x.desc == desc) {
+                if (x.h && x.obj == (const void *)&F && x.type == TypeKey<FrameT>() && x.id == id && x.kind == kind &&
+                    x.n == F.mDescriptors.rows && x.desc == desc) {
                     x.stamp = ++c.clock;
                     ++c.hits;
                     guard.h = x.h;
@@ -254,7 +256,7 @@ protected:
             slot->h = nullptr;
             fill(slot->flat);
             Check(vsg_frame_create(Workspace(), &slot->flat.view, &slot->h), "vsg_frame_create");
-            slot->obj = &F; slot->id = id; slot->kind = kind; slot->n = F.mDescriptors.rows; slot->desc = desc; slot->stamp = ++c.clock;
+            slot->obj = &F; slot->type = TypeKey<FrameT>(); slot->id = id; slot->kind = kind; slot->n = F.mDescriptors.rows; slot->desc = desc; slot->stamp = ++c.clock;
             guard.h = slot->h;
             guard.owned = false;
             return slot->flat;
